@@ -1,0 +1,670 @@
+// gridencoder.cu -- multiresolution hash / tiled grid encoding for sm_100a.
+//
+// Replaces gridencoder/src/gridencoder.cu of the reference (per-entry file:line map in include/nerf_b200.h).
+//
+// Two families of kernels:
+//   * generic  <T, D, C>: one thread per (point, level), any D in 2..5, C in {1,2,4,8}; produces dy_dx,
+//     supports both output layouts.  Used for every shape that is not the product's.
+//   * d3c2 fast path (D=3, C=2, layout [B, L*C], L <= 32 -- the only shape nerf/network_grid.py:95 and
+//     nerf/encoding.py:55-58 ever build): one thread per POINT looping over levels, so that
+//       - a warp holds 32 consecutive samples of a ray: at coarse levels their 8 corners fall in the same
+//         cells and the gathers coalesce into a few sectors,
+//       - each thread owns one [L*C] output row and writes it with 16/32-byte vector stores straight in the
+//         MLP-ready layout (no [L,B,C] -> [B,L*C] permute copy, grid.py:63),
+//       - per-level constants (offset, size, strides, scale) are computed once per CTA into shared memory,
+//       - backward: adjacent lanes that share a base cell are summed with a segmented shuffle reduction and
+//         only the run head issues the (float2) atomic -- the warp-aggregated scatter that replaces the
+//         reference's per-element __half2 atomics (gridencoder.cu:324-337).  Accumulation is fp32.
+//
+// Index arithmetic is uint32 with wrap-around exactly as gridencoder.cu:50-84; scale is computed on the
+// device with the reference's expression exp2f(level * S) * H - 1.0f so fine-level positions are identical.
+#include "common.cuh"
+
+namespace {
+
+
+__device__ __forceinline__ float ge_level_scale(uint32_t level, float S, uint32_t H) {
+    return exp2f(level * S) * H - 1.0f;      // gridencoder.cu:138 (same expression => same FFMA contraction)
+}
+
+template <uint32_t D>
+__device__ __forceinline__ uint32_t ge_fast_hash(const uint32_t pos_grid[D]) {
+    constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
+    uint32_t result = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < D; ++i) result ^= pos_grid[i] * primes[i];
+    return result;
+}
+
+// gridencoder.cu:66-84, returns the ROW index (the reference multiplies by C and adds the channel)
+template <uint32_t D>
+__device__ __forceinline__ uint32_t ge_grid_row(uint32_t gridtype, bool align_corners, uint32_t hashmap_size,
+                                                uint32_t resolution, const uint32_t pos_grid[D]) {
+    uint32_t stride = 1, index = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < D && stride <= hashmap_size; d++) {
+        index += pos_grid[d] * stride;
+        stride *= align_corners ? resolution : (resolution + 1);
+    }
+    if (gridtype == 0 && stride > hashmap_size) index = ge_fast_hash<D>(pos_grid);
+    return index % hashmap_size;
+}
+
+__device__ __forceinline__ float ge_smoothstep(float v) { return v * v * (3.0f - 2.0f * v); }
+__device__ __forceinline__ float ge_smoothstep_d(float v) { return 6 * v * (1.0f - v); }
+
+// ------------------------------------------------------------------------------------------------
+// generic forward: gridencoder.cu:87-244
+// ------------------------------------------------------------------------------------------------
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256)
+k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ grid, const int32_t *__restrict__ offsets,
+           T *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, T *__restrict__ dy_dx,
+           uint32_t gridtype, bool align_corners, uint32_t interp, int layout) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    grid += (size_t)(uint32_t)offsets[level] * C;
+    inputs += (size_t)b * D;
+    outputs += (layout == NB200_LAYOUT_LBC) ? ((size_t)level * B + b) * C : ((size_t)b * L + level) * C;
+    if (dy_dx) dy_dx += (size_t)b * D * L * C + (size_t)level * D * C;
+
+    float x[D];
+    bool oob = false;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        x[d] = inputs[d];
+        if (x[d] < 0 || x[d] > 1) oob = true;
+    }
+    if (oob) {
+#pragma unroll
+        for (uint32_t ch = 0; ch < C; ch++) outputs[ch] = nb_from_float<T>(0.0f);
+        if (dy_dx) {
+#pragma unroll
+            for (uint32_t i = 0; i < D * C; i++) dy_dx[i] = nb_from_float<T>(0.0f);
+        }
+        return;
+    }
+    const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
+    const float scale = ge_level_scale(level, S, H);
+    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+
+    float pos[D], pos_deriv[D];
+    uint32_t pos_grid[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        pos[d] = x[d] * scale + (align_corners ? 0.0f : 0.5f);
+        pos_grid[d] = (uint32_t)floorf(pos[d]);
+        pos[d] -= (float)pos_grid[d];
+        if (interp == 1) {
+            pos_deriv[d] = ge_smoothstep_d(pos[d]);
+            pos[d] = ge_smoothstep(pos[d]);
+        } else {
+            pos_deriv[d] = 1.0f;
+        }
+    }
+    float results[C];
+#pragma unroll
+    for (uint32_t ch = 0; ch < C; ch++) results[ch] = 0.0f;
+#pragma unroll
+    for (uint32_t idx = 0; idx < (1u << D); idx++) {
+        float w = 1;
+        uint32_t pgl[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) {
+            if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pgl[d] = pos_grid[d]; }
+            else { w *= pos[d]; pgl[d] = pos_grid[d] + 1; }
+        }
+        const size_t row = ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
+#pragma unroll
+        for (uint32_t ch = 0; ch < C; ch++) results[ch] += w * nb_to_float<T>(grid[row * C + ch]);
+    }
+#pragma unroll
+    for (uint32_t ch = 0; ch < C; ch++) outputs[ch] = nb_from_float<T>(results[ch]);
+
+    if (dy_dx) {   // gridencoder.cu:200-243
+#pragma unroll
+        for (uint32_t gd = 0; gd < D; gd++) {
+            float rg[C];
+#pragma unroll
+            for (uint32_t ch = 0; ch < C; ch++) rg[ch] = 0.0f;
+#pragma unroll
+            for (uint32_t idx = 0; idx < (1u << (D - 1)); idx++) {
+                float w = scale;
+                uint32_t pgl[D];
+#pragma unroll
+                for (uint32_t nd = 0; nd < D - 1; nd++) {
+                    const uint32_t d = (nd >= gd) ? (nd + 1) : nd;
+                    if ((idx & (1u << nd)) == 0) { w *= 1 - pos[d]; pgl[d] = pos_grid[d]; }
+                    else { w *= pos[d]; pgl[d] = pos_grid[d] + 1; }
+                }
+                pgl[gd] = pos_grid[gd];
+                const size_t il = ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
+                pgl[gd] = pos_grid[gd] + 1;
+                const size_t ir = ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
+#pragma unroll
+                for (uint32_t ch = 0; ch < C; ch++)
+                    rg[ch] += w * (nb_to_float<T>(grid[ir * C + ch]) - nb_to_float<T>(grid[il * C + ch])) * pos_deriv[gd];
+            }
+#pragma unroll
+            for (uint32_t ch = 0; ch < C; ch++) dy_dx[gd * C + ch] = nb_from_float<T>(rg[ch]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic backward: gridencoder.cu:247-339 (fp32 accumulation, one thread per (point, level))
+// ------------------------------------------------------------------------------------------------
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256)
+k_grid_bwd(const T *__restrict__ grad, const float *__restrict__ inputs, const int32_t *__restrict__ offsets,
+           float *__restrict__ grad_grid, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+           bool align_corners, uint32_t interp, int layout) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    grad_grid += (size_t)(uint32_t)offsets[level] * C;
+    inputs += (size_t)b * D;
+    grad += (layout == NB200_LAYOUT_LBC) ? ((size_t)level * B + b) * C : ((size_t)b * L + level) * C;
+    const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
+    const float scale = ge_level_scale(level, S, H);
+    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+    float pos[D];
+    uint32_t pos_grid[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        const float xd = inputs[d];
+        if (xd < 0 || xd > 1) return;
+        pos[d] = xd * scale + (align_corners ? 0.0f : 0.5f);
+        pos_grid[d] = (uint32_t)floorf(pos[d]);
+        pos[d] -= (float)pos_grid[d];
+        if (interp == 1) pos[d] = ge_smoothstep(pos[d]);
+    }
+    float g[C];
+#pragma unroll
+    for (uint32_t ch = 0; ch < C; ch++) g[ch] = nb_to_float<T>(grad[ch]);
+#pragma unroll
+    for (uint32_t idx = 0; idx < (1u << D); idx++) {
+        float w = 1;
+        uint32_t pgl[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) {
+            if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pgl[d] = pos_grid[d]; }
+            else { w *= pos[d]; pgl[d] = pos_grid[d] + 1; }
+        }
+        const size_t row = ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
+        if constexpr (C % 2 == 0) {
+#pragma unroll
+            for (uint32_t ch = 0; ch < C; ch += 2)
+                atomicAdd(reinterpret_cast<float2 *>(grad_grid + row * C + ch), make_float2(w * g[ch], w * g[ch + 1]));
+        } else {
+#pragma unroll
+            for (uint32_t ch = 0; ch < C; ch++) atomicAdd(grad_grid + row * C + ch, w * g[ch]);
+        }
+    }
+}
+
+// gridencoder.cu:342-368
+template <typename T>
+__global__ void k_input_bwd(const T *__restrict__ grad, const T *__restrict__ dy_dx, T *__restrict__ grad_inputs,
+                            uint32_t B, uint32_t D, uint32_t C, uint32_t L, int layout) {
+    const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
+    if (t >= B * D) return;
+    const uint32_t b = t / D, d = t - b * D;
+    dy_dx += (size_t)b * L * D * C;
+    float result = 0;
+    for (uint32_t l = 0; l < L; l++)
+        for (uint32_t ch = 0; ch < C; ch++) {
+            const size_t gi = (layout == NB200_LAYOUT_LBC) ? ((size_t)l * B + b) * C + ch : ((size_t)b * L + l) * C + ch;
+            result += nb_to_float<T>(grad[gi]) * nb_to_float<T>(dy_dx[l * D * C + d * C + ch]);
+        }
+    grad_inputs[t] = nb_from_float<T>(result);
+}
+
+// gridencoder.cu:505-609
+template <uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256)
+k_grad_tv(const float *__restrict__ inputs, const float *__restrict__ grid, float *__restrict__ grad,
+          const int32_t *__restrict__ offsets, float weight, uint32_t B, uint32_t L, float S, uint32_t H,
+          uint32_t gridtype, bool align_corners) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    inputs += (size_t)b * D;
+    grid += (size_t)(uint32_t)offsets[level] * C;
+    grad += (size_t)(uint32_t)offsets[level] * C;
+    const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
+    const float scale = ge_level_scale(level, S, H);
+    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+    uint32_t pos_grid[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        const float xd = inputs[d];
+        if (xd < 0 || xd > 1) return;
+        pos_grid[d] = (uint32_t)floorf(xd * scale + (align_corners ? 0.0f : 0.5f));
+    }
+    float results[C], idelta[C];
+#pragma unroll
+    for (uint32_t ch = 0; ch < C; ch++) results[ch] = idelta[ch] = 0.0f;
+    const size_t index = (size_t)ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pos_grid) * C;
+    const float w = weight / (2 * D);
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        const uint32_t cur_d = pos_grid[d];
+        if (cur_d < resolution) {
+            pos_grid[d] = cur_d + 1;
+            const size_t ir = (size_t)ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pos_grid) * C;
+#pragma unroll
+            for (uint32_t ch = 0; ch < C; ch++) {
+                const float gv = grid[index + ch] - grid[ir + ch];
+                results[ch] += gv; idelta[ch] += gv * gv;
+            }
+        }
+        if (cur_d > 0) {
+            pos_grid[d] = cur_d - 1;
+            const size_t il = (size_t)ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pos_grid) * C;
+#pragma unroll
+            for (uint32_t ch = 0; ch < C; ch++) {
+                const float gv = grid[index + ch] - grid[il + ch];
+                results[ch] += gv; idelta[ch] += gv * gv;
+            }
+        }
+        pos_grid[d] = cur_d;
+    }
+#pragma unroll
+    for (uint32_t ch = 0; ch < C; ch++) atomicAdd(&grad[index + ch], w * results[ch] * rsqrtf(idelta[ch] + 1e-9f));
+}
+
+// ------------------------------------------------------------------------------------------------
+// d3c2 fast path
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kMaxFastLevels = 32;
+constexpr uint32_t P1 = 2654435761u, P2 = 805459861u;
+
+struct LevelInfo {
+    uint32_t offset;     // first row of the level
+    uint32_t size;       // rows in the level (hashmap_size)
+    uint32_t m1, m2;     // dense strides of y and z (0 when the reference's stride loop has stopped)
+    uint32_t mask;       // size-1 when size is a power of two, else 0
+    uint32_t use_hash;
+    float scale;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ void ge_fill_level_info(LevelInfo *info, const int32_t *__restrict__ offsets, uint32_t nlev,
+                                                   float S, uint32_t H, uint32_t gridtype, bool align_corners) {
+    for (uint32_t l = threadIdx.x; l < nlev; l += blockDim.x) {
+        LevelInfo li;
+        li.offset = (uint32_t)offsets[l];
+        li.size = (uint32_t)(offsets[l + 1] - offsets[l]);
+        li.scale = ge_level_scale(l, S, H);
+        const uint32_t resolution = (uint32_t)ceilf(li.scale) + 1;
+        const uint32_t r1 = align_corners ? resolution : resolution + 1;
+        // replay of the stride loop of get_grid_index (gridencoder.cu:71-75) for D = 3
+        uint32_t stride = 1;
+        stride *= r1;                                   // d = 0 always executes (1 <= size)
+        li.m1 = 0; li.m2 = 0;
+        if (stride <= li.size) {
+            li.m1 = stride; stride *= r1;
+            if (stride <= li.size) { li.m2 = stride; stride *= r1; }
+        }
+        li.use_hash = (gridtype == 0 && stride > li.size) ? 1u : 0u;
+        li.mask = ((li.size & (li.size - 1)) == 0) ? li.size - 1 : 0u;
+        li.pad = 0;
+        info[l] = li;
+    }
+}
+
+__device__ __forceinline__ uint32_t ge_row_d3(const LevelInfo &li, uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t raw = li.use_hash ? (x ^ (y * P1) ^ (z * P2)) : (x + y * li.m1 + z * li.m2);
+    if (li.mask) return raw & li.mask;
+    return raw < li.size ? raw : raw % li.size;
+}
+
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<__half> { using type = __half2; };
+__device__ __forceinline__ float2 ge_ld2(const float *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
+__device__ __forceinline__ float2 ge_ld2(const __half *p) { return __half22float2(__ldg(reinterpret_cast<const __half2 *>(p))); }
+
+// one thread per point; outputs [B, L*2]
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_grid_fwd_d3c2(const float *__restrict__ inputs, const T *__restrict__ grid, const int32_t *__restrict__ offsets,
+                T *__restrict__ outputs, uint32_t B, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                uint32_t gridtype, bool align_corners, uint32_t interp) {
+    __shared__ LevelInfo info[kMaxFastLevels];
+    ge_fill_level_info(info, offsets, max_level, S, H, gridtype, align_corners);
+    __syncthreads();
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float x0 = inputs[(size_t)b * 3], x1 = inputs[(size_t)b * 3 + 1], x2 = inputs[(size_t)b * 3 + 2];
+    const bool oob = (x0 < 0 || x0 > 1) || (x1 < 0 || x1 > 1) || (x2 < 0 || x2 > 1);
+    T *out = outputs + (size_t)b * L * 2;
+    const float half_off = align_corners ? 0.0f : 0.5f;
+
+    for (uint32_t l0 = 0; l0 < max_level; l0 += 4) {
+        float res[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+            const uint32_t l = l0 + j;
+            float r0 = 0.0f, r1 = 0.0f;
+            if (l < max_level && !oob) {
+                const LevelInfo li = info[l];
+                float p0 = x0 * li.scale + half_off, p1 = x1 * li.scale + half_off, p2 = x2 * li.scale + half_off;
+                const uint32_t g0 = (uint32_t)floorf(p0), g1 = (uint32_t)floorf(p1), g2 = (uint32_t)floorf(p2);
+                p0 -= (float)g0; p1 -= (float)g1; p2 -= (float)g2;
+                if (interp == 1) { p0 = ge_smoothstep(p0); p1 = ge_smoothstep(p1); p2 = ge_smoothstep(p2); }
+                const T *lg = grid + (size_t)li.offset * 2;
+                float2 v[8];
+#pragma unroll
+                for (uint32_t idx = 0; idx < 8; idx++) {
+                    const uint32_t row = ge_row_d3(li, g0 + (idx & 1u), g1 + ((idx >> 1) & 1u), g2 + ((idx >> 2) & 1u));
+                    v[idx] = ge_ld2(lg + (size_t)row * 2);
+                }
+#pragma unroll
+                for (uint32_t idx = 0; idx < 8; idx++) {
+                    float w = 1;
+                    w *= (idx & 1u) ? p0 : 1 - p0;
+                    w *= (idx & 2u) ? p1 : 1 - p1;
+                    w *= (idx & 4u) ? p2 : 1 - p2;
+                    r0 += w * v[idx].x;
+                    r1 += w * v[idx].y;
+                }
+            }
+            res[j * 2] = r0; res[j * 2 + 1] = r1;
+        }
+        // rows are (L*2) elements; L*2*sizeof(T) is a multiple of 16 bytes only when L % 4 == 0 (f16) / L % 2 == 0 (f32)
+        const uint32_t nvalid = min(4u, L - l0);   // levels >= max_level but < L are the caller's to zero (grid.py:52)
+        if (l0 + 4 <= max_level && (L % 4 == 0)) {
+            if constexpr (sizeof(T) == 2) {
+                __half2 h0 = __floats2half2_rn(res[0], res[1]), h1 = __floats2half2_rn(res[2], res[3]);
+                __half2 h2 = __floats2half2_rn(res[4], res[5]), h3 = __floats2half2_rn(res[6], res[7]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                *reinterpret_cast<uint4 *>(out + l0 * 2) = pk;
+            } else {
+                *reinterpret_cast<float4 *>(out + l0 * 2) = make_float4(res[0], res[1], res[2], res[3]);
+                *reinterpret_cast<float4 *>(out + l0 * 2 + 4) = make_float4(res[4], res[5], res[6], res[7]);
+            }
+        } else {
+            for (uint32_t j = 0; j < nvalid && l0 + j < max_level; j++) {
+                out[(l0 + j) * 2] = nb_from_float<T>(res[j * 2]);
+                out[(l0 + j) * 2 + 1] = nb_from_float<T>(res[j * 2 + 1]);
+            }
+        }
+    }
+}
+
+// one thread per point; grad [B, L*2]; fp32 float2 atomics; optional warp aggregation
+template <typename T, bool kAgg>
+__global__ void __launch_bounds__(256)
+k_grid_bwd_d3c2(const T *__restrict__ grad, const float *__restrict__ inputs, const int32_t *__restrict__ offsets,
+                float *__restrict__ grad_grid, uint32_t B, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                uint32_t gridtype, bool align_corners, uint32_t interp) {
+    __shared__ LevelInfo info[kMaxFastLevels];
+    ge_fill_level_info(info, offsets, max_level, S, H, gridtype, align_corners);
+    __syncthreads();
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = nb_lane();
+    const bool inb = b < B;            // keep whole warps alive for the shuffles
+    float x0 = -1.0f, x1 = -1.0f, x2 = -1.0f;
+    if (inb) { x0 = inputs[(size_t)b * 3]; x1 = inputs[(size_t)b * 3 + 1]; x2 = inputs[(size_t)b * 3 + 2]; }
+    const bool oob = (x0 < 0 || x0 > 1) || (x1 < 0 || x1 > 1) || (x2 < 0 || x2 > 1);   // !inb => oob
+    const T *g = grad + (size_t)(inb ? b : 0) * L * 2;
+    const float half_off = align_corners ? 0.0f : 0.5f;
+
+    for (uint32_t l = 0; l < max_level; l++) {
+        const LevelInfo li = info[l];
+        float g0v = 0.0f, g1v = 0.0f;
+        if (!oob) { g0v = nb_to_float<T>(g[l * 2]); g1v = nb_to_float<T>(g[l * 2 + 1]); }
+        float p0 = x0 * li.scale + half_off, p1 = x1 * li.scale + half_off, p2 = x2 * li.scale + half_off;
+        const uint32_t c0 = (uint32_t)floorf(p0), c1 = (uint32_t)floorf(p1), c2 = (uint32_t)floorf(p2);
+        p0 -= (float)c0; p1 -= (float)c1; p2 -= (float)c2;
+        if (interp == 1) { p0 = ge_smoothstep(p0); p1 = ge_smoothstep(p1); p2 = ge_smoothstep(p2); }
+        float2 v[8];
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; idx++) {
+            float w = 1;
+            w *= (idx & 1u) ? p0 : 1 - p0;
+            w *= (idx & 2u) ? p1 : 1 - p1;
+            w *= (idx & 4u) ? p2 : 1 - p2;
+            v[idx] = make_float2(w * g0v, w * g1v);
+        }
+        bool emit = !oob;
+        if (kAgg) {
+            // runs of adjacent lanes (consecutive samples of a ray) that share the base cell share all 8 corners
+            const uint32_t q0 = __shfl_up_sync(0xffffffffu, c0, 1), q1 = __shfl_up_sync(0xffffffffu, c1, 1),
+                           q2 = __shfl_up_sync(0xffffffffu, c2, 1);
+            const bool poob = __shfl_up_sync(0xffffffffu, (int)oob, 1) != 0;
+            const bool head = (lane == 0) || oob || poob || (q0 != c0) || (q1 != c1) || (q2 != c2);
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            if (__popc(heads) <= 16) {                       // warp-uniform: at least half of the atomics disappear
+                const uint32_t nh = (lane == 31) ? 0u : (heads >> (lane + 1));
+                const uint32_t run_last = nh ? lane + (uint32_t)__ffs(nh) - 1u : 31u;
+#pragma unroll
+                for (uint32_t o = 1; o < 32; o <<= 1) {
+                    const bool take = (lane + o) <= run_last;
+#pragma unroll
+                    for (uint32_t idx = 0; idx < 8; idx++) {
+                        const float ax = __shfl_down_sync(0xffffffffu, v[idx].x, o);
+                        const float ay = __shfl_down_sync(0xffffffffu, v[idx].y, o);
+                        if (take) { v[idx].x += ax; v[idx].y += ay; }
+                    }
+                }
+                emit = head && !oob;
+            }
+        }
+        if (emit) {
+            float *lg = grad_grid + (size_t)li.offset * 2;
+#pragma unroll
+            for (uint32_t idx = 0; idx < 8; idx++) {
+                const uint32_t row = ge_row_d3(li, c0 + (idx & 1u), c1 + ((idx >> 1) & 1u), c2 + ((idx >> 2) & 1u));
+                atomicAdd(reinterpret_cast<float2 *>(lg + (size_t)row * 2), v[idx]);
+            }
+        }
+    }
+}
+
+__global__ void k_level_scales(float *scales, uint32_t L, float S, uint32_t H) {
+    const uint32_t l = threadIdx.x + blockIdx.x * blockDim.x;
+    if (l < L) scales[l] = ge_level_scale(l, S, H);
+}
+
+__global__ void k_cast_f32_f16(const float *__restrict__ src, __half *__restrict__ dst, uint64_t n) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(src + i));
+        __half2 a = __floats2half2_rn(v.x, v.y), b2 = __floats2half2_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t *>(&a); pk.y = *reinterpret_cast<uint32_t *>(&b2);
+        *reinterpret_cast<uint2 *>(dst + i) = pk;
+    } else {
+        for (uint64_t j = i; j < n; j++) dst[j] = __float2half_rn(src[j]);
+    }
+}
+
+// ---- dispatch helpers ------------------------------------------------------------------------------
+template <typename T, uint32_t D>
+int launch_fwd_c(const float *inputs, const T *emb, const int32_t *offsets, T *out, uint32_t B, uint32_t C, uint32_t L,
+                 uint32_t max_level, float S, uint32_t H, T *dy_dx, uint32_t gridtype, bool ac, uint32_t interp,
+                 int layout, cudaStream_t st) {
+    const dim3 grid(nb_div_up(B, 256), max_level, 1);
+    switch (C) {
+        case 1: k_grid_fwd<T, D, 1><<<grid, 256, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, dy_dx, gridtype, ac, interp, layout); break;
+        case 2: k_grid_fwd<T, D, 2><<<grid, 256, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, dy_dx, gridtype, ac, interp, layout); break;
+        case 4: k_grid_fwd<T, D, 4><<<grid, 256, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, dy_dx, gridtype, ac, interp, layout); break;
+        case 8: k_grid_fwd<T, D, 8><<<grid, 256, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, dy_dx, gridtype, ac, interp, layout); break;
+        default: return NB200_E_BAD_DIM;
+    }
+    return 0;
+}
+
+template <typename T>
+int launch_fwd(const float *inputs, const T *emb, const int32_t *offsets, T *out, uint32_t B, uint32_t D, uint32_t C,
+               uint32_t L, uint32_t max_level, float S, uint32_t H, T *dy_dx, uint32_t gridtype, bool ac,
+               uint32_t interp, int layout, cudaStream_t st) {
+    if (D == 3 && C == 2 && layout == NB200_LAYOUT_BLC && !dy_dx && L <= kMaxFastLevels) {
+        k_grid_fwd_d3c2<T><<<nb_div_up(B, 256), 256, 0, st>>>(inputs, emb, offsets, out, B, L, max_level, S, H, gridtype, ac, interp);
+        return 0;
+    }
+    switch (D) {
+        case 2: return launch_fwd_c<T, 2>(inputs, emb, offsets, out, B, C, L, max_level, S, H, dy_dx, gridtype, ac, interp, layout, st);
+        case 3: return launch_fwd_c<T, 3>(inputs, emb, offsets, out, B, C, L, max_level, S, H, dy_dx, gridtype, ac, interp, layout, st);
+        case 4: return launch_fwd_c<T, 4>(inputs, emb, offsets, out, B, C, L, max_level, S, H, dy_dx, gridtype, ac, interp, layout, st);
+        case 5: return launch_fwd_c<T, 5>(inputs, emb, offsets, out, B, C, L, max_level, S, H, dy_dx, gridtype, ac, interp, layout, st);
+        default: return NB200_E_BAD_DIM;
+    }
+}
+
+template <typename T, uint32_t D>
+int launch_bwd_c(const T *grad, const float *inputs, const int32_t *offsets, float *gg, uint32_t B, uint32_t C,
+                 uint32_t L, uint32_t max_level, float S, uint32_t H, uint32_t gridtype, bool ac, uint32_t interp,
+                 int layout, cudaStream_t st) {
+    const dim3 grid(nb_div_up(B, 256), max_level, 1);
+    switch (C) {
+        case 1: k_grid_bwd<T, D, 1><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype, ac, interp, layout); break;
+        case 2: k_grid_bwd<T, D, 2><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype, ac, interp, layout); break;
+        case 4: k_grid_bwd<T, D, 4><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype, ac, interp, layout); break;
+        case 8: k_grid_bwd<T, D, 8><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype, ac, interp, layout); break;
+        default: return NB200_E_BAD_DIM;
+    }
+    return 0;
+}
+
+template <typename T>
+int launch_bwd(const T *grad, const float *inputs, const int32_t *offsets, float *gg, uint32_t B, uint32_t D, uint32_t C,
+               uint32_t L, uint32_t max_level, float S, uint32_t H, const T *dy_dx, T *grad_inputs, uint32_t gridtype,
+               bool ac, uint32_t interp, int layout, int agg, cudaStream_t st) {
+    int rc = 0;
+    if (D == 3 && C == 2 && layout == NB200_LAYOUT_BLC && L <= kMaxFastLevels) {
+        const uint32_t nblk = nb_div_up(B, 256);
+        if (agg) k_grid_bwd_d3c2<T, true><<<nblk, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, max_level, S, H, gridtype, ac, interp);
+        else k_grid_bwd_d3c2<T, false><<<nblk, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, max_level, S, H, gridtype, ac, interp);
+    } else {
+        switch (D) {
+            case 2: rc = launch_bwd_c<T, 2>(grad, inputs, offsets, gg, B, C, L, max_level, S, H, gridtype, ac, interp, layout, st); break;
+            case 3: rc = launch_bwd_c<T, 3>(grad, inputs, offsets, gg, B, C, L, max_level, S, H, gridtype, ac, interp, layout, st); break;
+            case 4: rc = launch_bwd_c<T, 4>(grad, inputs, offsets, gg, B, C, L, max_level, S, H, gridtype, ac, interp, layout, st); break;
+            case 5: rc = launch_bwd_c<T, 5>(grad, inputs, offsets, gg, B, C, L, max_level, S, H, gridtype, ac, interp, layout, st); break;
+            default: return NB200_E_BAD_DIM;
+        }
+    }
+    if (rc) return rc;
+    if (dy_dx && grad_inputs)
+        k_input_bwd<T><<<nb_div_up((uint64_t)B * D, 256), 256, 0, st>>>(grad, dy_dx, grad_inputs, B, D, C, L, layout);
+    return 0;
+}
+
+template <uint32_t D>
+int launch_tv_c(const float *inputs, const float *emb, float *grad, const int32_t *offsets, float weight, uint32_t B,
+                uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool ac, cudaStream_t st) {
+    const dim3 grid(nb_div_up(B, 256), L, 1);
+    switch (C) {
+        case 1: k_grad_tv<D, 1><<<grid, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
+        case 2: k_grad_tv<D, 2><<<grid, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
+        case 4: k_grad_tv<D, 4><<<grid, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
+        case 8: k_grad_tv<D, 8><<<grid, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
+        default: return NB200_E_BAD_DIM;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nb200_grid_encode_forward(const float *inputs, const void *embeddings, const int32_t *offsets, void *outputs,
+                              uint32_t B, uint32_t D, uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                              void *dy_dx, uint32_t gridtype, int align_corners, uint32_t interp,
+                              int emb_dtype, int layout, void *stream) {
+    if (B == 0 || max_level == 0) return 0;
+    if (!inputs || !embeddings || !offsets || !outputs || max_level > L) return NB200_E_BAD_ARG;
+    if (layout != NB200_LAYOUT_LBC && layout != NB200_LAYOUT_BLC) return NB200_E_BAD_ARG;
+    int rc;
+    if (emb_dtype == NB200_F32)
+        rc = launch_fwd<float>(inputs, (const float *)embeddings, offsets, (float *)outputs, B, D, C, L, max_level, S, H,
+                               (float *)dy_dx, gridtype, align_corners != 0, interp, layout, nb_stream(stream));
+    else if (emb_dtype == NB200_F16)
+        rc = launch_fwd<__half>(inputs, (const __half *)embeddings, offsets, (__half *)outputs, B, D, C, L, max_level, S,
+                                H, (__half *)dy_dx, gridtype, align_corners != 0, interp, layout, nb_stream(stream));
+    else
+        return NB200_E_BAD_DTYPE;
+    if (rc) return rc;
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_grid_encode_backward(const void *grad, const float *inputs, const int32_t *offsets, float *grad_embeddings,
+                               uint32_t B, uint32_t D, uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                               const void *dy_dx, void *grad_inputs, uint32_t gridtype, int align_corners,
+                               uint32_t interp, int grad_dtype, int layout, int agg, void *stream) {
+    if (B == 0 || max_level == 0) return 0;
+    if (!grad || !inputs || !offsets || !grad_embeddings || max_level > L) return NB200_E_BAD_ARG;
+    if (layout != NB200_LAYOUT_LBC && layout != NB200_LAYOUT_BLC) return NB200_E_BAD_ARG;
+    int rc;
+    if (grad_dtype == NB200_F32)
+        rc = launch_bwd<float>((const float *)grad, inputs, offsets, grad_embeddings, B, D, C, L, max_level, S, H,
+                               (const float *)dy_dx, (float *)grad_inputs, gridtype, align_corners != 0, interp, layout,
+                               agg, nb_stream(stream));
+    else if (grad_dtype == NB200_F16)
+        rc = launch_bwd<__half>((const __half *)grad, inputs, offsets, grad_embeddings, B, D, C, L, max_level, S, H,
+                                (const __half *)dy_dx, (__half *)grad_inputs, gridtype, align_corners != 0, interp,
+                                layout, agg, nb_stream(stream));
+    else
+        return NB200_E_BAD_DTYPE;
+    if (rc) return rc;
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_grad_total_variation(const float *inputs, const float *embeddings, float *grad, const int32_t *offsets,
+                               float weight, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                               uint32_t gridtype, int align_corners, void *stream) {
+    if (B == 0 || L == 0) return 0;
+    if (!inputs || !embeddings || !grad || !offsets) return NB200_E_BAD_ARG;
+    int rc;
+    cudaStream_t st = nb_stream(stream);
+    switch (D) {
+        case 2: rc = launch_tv_c<2>(inputs, embeddings, grad, offsets, weight, B, C, L, S, H, gridtype, align_corners != 0, st); break;
+        case 3: rc = launch_tv_c<3>(inputs, embeddings, grad, offsets, weight, B, C, L, S, H, gridtype, align_corners != 0, st); break;
+        case 4: rc = launch_tv_c<4>(inputs, embeddings, grad, offsets, weight, B, C, L, S, H, gridtype, align_corners != 0, st); break;
+        case 5: rc = launch_tv_c<5>(inputs, embeddings, grad, offsets, weight, B, C, L, S, H, gridtype, align_corners != 0, st); break;
+        default: return NB200_E_BAD_DIM;
+    }
+    if (rc) return rc;
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_grid_level_scales(float *scales, uint32_t L, float S, uint32_t H, void *stream) {
+    if (L == 0) return 0;
+    k_level_scales<<<nb_div_up(L, 64), 64, 0, nb_stream(stream)>>>(scales, L, S, H);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_cast_f32_to_f16(const float *src, void *dst, uint64_t n, void *stream) {
+    if (n == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) || (reinterpret_cast<uintptr_t>(dst) & 7u)) return NB200_E_BAD_ARG;
+    k_cast_f32_f16<<<nb_div_up((n + 3) / 4, 256), 256, 0, nb_stream(stream)>>>(src, (__half *)dst, n);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+const char *nb200_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    switch (code) {
+        case NB200_E_BAD_DIM: return "GridEncoding: C must be 1, 2, 4, or 8 and D must be 2, 3, 4 or 5.";
+        case NB200_E_BAD_DTYPE: return "unsupported dtype (f32 and f16 are built)";
+        case NB200_E_BAD_ARG: return "bad argument (null pointer, misaligned buffer or inconsistent sizes)";
+        case NB200_E_SCRATCH: return "scratch buffer too small";
+        default: return "unknown nb200 error";
+    }
+}
+
+int nb200_version(void) { return 1; }
+
+}  // extern "C"

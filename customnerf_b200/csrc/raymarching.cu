@@ -1,0 +1,606 @@
+// raymarching.cu -- occupancy-grid ray marching and alpha compositing for sm_100a.
+//
+// Replaces raymarching/src/raymarching.cu of the reference (see include/nerf_b200.h for the per-entry
+// file:line map).  Design differences from the reference's one-thread-per-ray kernels:
+//   * march_rays_train: count -> scan -> write.  Slot offsets are the exclusive scan of the per-ray
+//     counts in ray-id order (warp shuffles + one block-sum pass) instead of two global atomics per ray,
+//     so outputs are deterministic and the caller can size them exactly.
+//   * composite_rays_train fwd/bwd: one WARP per ray, 32 samples per trip, transmittance / colour
+//     prefixes through warp-shuffle scans; loads of a ray's segment are coalesced.
+// The per-step arithmetic of the marcher is pinned with explicit round-to-nearest intrinsics in the
+// order nvcc emits for the reference source, because per-ray sample COUNTS
+// are integers that must match the reference bit-exactly.
+#include "common.cuh"
+#include <float.h>
+
+namespace {
+
+constexpr float kSqrt3 = 1.7320508075688772f;
+
+__device__ __forceinline__ float rm_clamp(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }
+
+// frexpf exponent of a finite non-negative float, clamped to [0, C-1] (raymarching.cu:42-54).
+__device__ __forceinline__ int rm_mip_level(float mx, int Cm1) {
+    const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 126;
+    return min(Cm1, max(0, e));
+}
+
+struct RayCtx {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+    float sx, sy, sz;          // 0.5f * sign(d)
+    float rH, H3, Hf, Hm1f, bound, dt_gamma, dt_min, dt_max;
+    double Hd;
+    int Cm1;
+    const uint8_t *grid;
+};
+
+__device__ __forceinline__ void rm_setup(RayCtx &r, const float *__restrict__ o, const float *__restrict__ d,
+                                         const uint8_t *grid, float bound, float dt_gamma, uint32_t max_steps,
+                                         uint32_t C, uint32_t H) {
+    r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+    r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+    r.rdx = __fdiv_rn(1.0f, r.dx); r.rdy = __fdiv_rn(1.0f, r.dy); r.rdz = __fdiv_rn(1.0f, r.dz);
+    r.sx = copysignf(0.5f, r.dx); r.sy = copysignf(0.5f, r.dy); r.sz = copysignf(0.5f, r.dz);
+    r.rH = __fdiv_rn(1.0f, (float)H);
+    r.H3 = (float)(H * H * H);
+    r.Hf = (float)H; r.Hm1f = (float)(H - 1); r.Hd = (double)H;
+    r.bound = bound; r.dt_gamma = dt_gamma;
+    r.dt_min = __fdiv_rn(2 * kSqrt3, (float)max_steps);                                   // :345
+    r.dt_max = __fdiv_rn(__fmul_rn(2 * kSqrt3, (float)(1 << (C - 1))), (float)H);          // :346
+    r.Cm1 = (int)C - 1;
+    r.grid = grid;
+}
+
+__device__ __forceinline__ float rm_dt(const RayCtx &r, float t) {
+    return rm_clamp(__fmul_rn(t, r.dt_gamma), r.dt_min, r.dt_max);
+}
+
+// (int) clamp(0.5 * (p * mip_rbound + 1) * H, 0, H-1): fp64 product because the literal is a double (:374-376)
+__device__ __forceinline__ int rm_cell(const RayCtx &r, float p, float mip_rbound) {
+    const double v = __dmul_rn(__dmul_rn(0.5, (double)__fmaf_rn(p, mip_rbound, 1.0f)), r.Hd);
+    return __float2int_rz(rm_clamp(__double2float_rn(v), 0.0f, r.Hm1f));
+}
+
+__device__ __forceinline__ float rm_exit(float n, float s, float rH, float mip_bound, float p, float rd) {
+    // (((n + 0.5f + 0.5f * sign(d)) * rH * 2 - 1) * mip_bound - p) * rd   (:390-392).  s = 0.5f*sign(d) is exact,
+    // so the FFMA(0.5, sign, n + 0.5) nvcc emits for the reference equals this second add.
+    const float b = __fmul_rn(__fadd_rn(__fadd_rn(n, 0.5f), s), rH);
+    return __fmul_rn(__fmaf_rn(__fmaf_rn(b, 2.0f, -1.0f), mip_bound, -p), rd);
+}
+
+// One iteration of the marching loop (:359-399).  Returns true when the cell at t is occupied: x,y,z,dt are the
+// sample; the caller emits it and advances t by dt.  Otherwise t has been advanced past the empty voxel.
+__device__ __forceinline__ bool rm_step(const RayCtx &r, float &t, float &x, float &y, float &z, float &dt) {
+    x = rm_clamp(__fmaf_rn(t, r.dx, r.ox), -r.bound, r.bound);
+    y = rm_clamp(__fmaf_rn(t, r.dy, r.oy), -r.bound, r.bound);
+    z = rm_clamp(__fmaf_rn(t, r.dz, r.oz), -r.bound, r.bound);
+    dt = rm_dt(r, t);
+    const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    const int level = max(rm_mip_level(mx, r.Cm1), rm_mip_level(__fmul_rn(__fmul_rn(dt, r.Hf), 0.5f), r.Cm1));
+    const float mip_bound = fminf(__int_as_float((127 + level) << 23), r.bound);           // scalbnf(1, level)
+    const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    const int nx = rm_cell(r, x, mip_rbound);
+    const int ny = rm_cell(r, y, mip_rbound);
+    const int nz = rm_cell(r, z, mip_rbound);
+    const uint32_t index = __float2uint_rz(__fmaf_rn((float)level, r.H3, (float)nb_morton3D(nx, ny, nz)));   // :378
+    const bool occ = (__ldg(r.grid + (index >> 3)) >> (index & 7u)) & 1u;
+    if (occ) return true;
+    const float tx = rm_exit((float)nx, r.sx, r.rH, mip_bound, x, r.rdx);
+    const float ty = rm_exit((float)ny, r.sy, r.rH, mip_bound, y, r.rdy);
+    const float tz = rm_exit((float)nz, r.sz, r.rH, mip_bound, z, r.rdz);
+    const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    do {
+        t = __fadd_rn(t, rm_dt(r, t));
+    } while (t < tt);
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// utils
+// ------------------------------------------------------------------------------------------------
+__global__ void k_near_far_from_aabb(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                                     const float *__restrict__ aabb, uint32_t N, float min_near,
+                                     float *__restrict__ nears, float *__restrict__ fars) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float rdx = __fdiv_rn(1.0f, rays_d[n * 3]), rdy = __fdiv_rn(1.0f, rays_d[n * 3 + 1]),
+                rdz = __fdiv_rn(1.0f, rays_d[n * 3 + 2]);
+    float near = __fmul_rn(__fsub_rn(aabb[0], ox), rdx), far = __fmul_rn(__fsub_rn(aabb[3], ox), rdx), tmp;
+    if (near > far) { tmp = near; near = far; far = tmp; }
+    float near_y = __fmul_rn(__fsub_rn(aabb[1], oy), rdy), far_y = __fmul_rn(__fsub_rn(aabb[4], oy), rdy);
+    if (near_y > far_y) { tmp = near_y; near_y = far_y; far_y = tmp; }
+    if (near > far_y || near_y > far) { nears[n] = fars[n] = FLT_MAX; return; }
+    if (near_y > near) near = near_y;
+    if (far_y < far) far = far_y;
+    float near_z = __fmul_rn(__fsub_rn(aabb[2], oz), rdz), far_z = __fmul_rn(__fsub_rn(aabb[5], oz), rdz);
+    if (near_z > far_z) { tmp = near_z; near_z = far_z; far_z = tmp; }
+    if (near > far_z || near_z > far) { nears[n] = fars[n] = FLT_MAX; return; }
+    if (near_z > near) near = near_z;
+    if (far_z < far) far = far_z;
+    if (near < min_near) near = min_near;
+    nears[n] = near;
+    fars[n] = far;
+}
+
+__global__ void k_sph_from_ray(const float *__restrict__ rays_o, const float *__restrict__ rays_d, float radius,
+                               uint32_t N, float *__restrict__ coords) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    constexpr float RPI = 0.3183098861837907f;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float B = ox * dx + oy * dy + oz * dz;
+    const float Cq = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-B + sqrtf(B * B - A * Cq)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    coords[n * 2] = 2 * atan2f(sqrtf(x * x + z * z), y) * RPI - 1;
+    coords[n * 2 + 1] = atan2f(z, x) * RPI;
+}
+
+__global__ void k_morton3D(const int32_t *__restrict__ coords, uint32_t N, int32_t *__restrict__ indices) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    indices[n] = (int32_t)nb_morton3D((uint32_t)coords[n * 3], (uint32_t)coords[n * 3 + 1], (uint32_t)coords[n * 3 + 2]);
+}
+
+__global__ void k_morton3D_invert(const int32_t *__restrict__ indices, uint32_t N, int32_t *__restrict__ coords) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const int32_t ind = indices[n];
+    coords[n * 3] = (int32_t)nb_morton3D_invert((uint32_t)(ind >> 0));
+    coords[n * 3 + 1] = (int32_t)nb_morton3D_invert((uint32_t)(ind >> 1));
+    coords[n * 3 + 2] = (int32_t)nb_morton3D_invert((uint32_t)(ind >> 2));
+}
+
+// one thread per output byte, 2 x float4 loads
+__global__ void k_packbits(const float *__restrict__ grid, uint32_t N, float thresh, uint8_t *__restrict__ bitfield) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(grid) + (size_t)n * 2);
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(grid) + (size_t)n * 2 + 1);
+    uint32_t bits = 0;
+    bits |= (a.x > thresh) ? 1u : 0u;   bits |= (a.y > thresh) ? 2u : 0u;
+    bits |= (a.z > thresh) ? 4u : 0u;   bits |= (a.w > thresh) ? 8u : 0u;
+    bits |= (b.x > thresh) ? 16u : 0u;  bits |= (b.y > thresh) ? 32u : 0u;
+    bits |= (b.z > thresh) ? 64u : 0u;  bits |= (b.w > thresh) ? 128u : 0u;
+    bitfield[n] = (uint8_t)bits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// march_rays_train: count -> scan -> write
+// ------------------------------------------------------------------------------------------------
+constexpr int kMarchBlock = 256;
+
+// pass 1 (:353-400): counts, block-local exclusive offsets (warp shuffles), per-block sums
+__global__ void __launch_bounds__(kMarchBlock)
+k_march_count(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+              float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+              const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
+              int32_t *__restrict__ rays, int32_t *__restrict__ block_sums) {
+    __shared__ int warp_tot[kMarchBlock / 32];
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    int num_steps = 0;
+    if (n < N) {
+        RayCtx r;
+        rm_setup(r, rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H);
+        const float far = fars[n];
+        float t = nears[n];
+        t = __fmaf_rn(rm_dt(r, t), noises ? noises[n] : 0.0f, t);      // :351
+        float x, y, z, dt;
+        while (t < far && (uint32_t)num_steps < max_steps) {
+            if (rm_step(r, t, x, y, z, dt)) { num_steps++; t = __fadd_rn(t, dt); }
+        }
+    }
+    const int incl = nb_warp_incl_scan(num_steps);
+    const uint32_t w = threadIdx.x >> 5;
+    if (nb_lane() == 31) warp_tot[w] = incl;
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int i = 0; i < kMarchBlock / 32; i++) base += (i < (int)w) ? warp_tot[i] : 0;
+    if (n < N) {
+        rays[n * 3] = (int32_t)n;
+        rays[n * 3 + 1] = base + incl - num_steps;      // block-local exclusive offset, globalised by k_march_fixup
+        rays[n * 3 + 2] = num_steps;
+    }
+    if (threadIdx.x == kMarchBlock - 1) block_sums[blockIdx.x] = base + incl;
+}
+
+// single block: exclusive scan of the block sums starting at counter[0]; counter += (sum, N)  (:405-406)
+__global__ void __launch_bounds__(1024)
+k_march_scan(const int32_t *__restrict__ block_sums, int32_t *__restrict__ block_prefix, uint32_t nb, uint32_t N,
+             int32_t *__restrict__ counter) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s, chunk_total_s;
+    if (threadIdx.x == 0) carry_s = counter[0];
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const int v = (i < nb) ? block_sums[i] : 0;
+        const int incl = nb_warp_incl_scan(v);
+        if (nb_lane() == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int wt = warp_tot[threadIdx.x];
+            const int wi = nb_warp_incl_scan(wt);
+            warp_tot[threadIdx.x] = wi - wt;            // exclusive warp offsets
+            if (threadIdx.x == 31) chunk_total_s = wi;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        if (i < nb) block_prefix[i] = carry + warp_tot[threadIdx.x >> 5] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + chunk_total_s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        counter[0] = carry_s;
+        counter[1] += (int32_t)N;
+    }
+}
+
+__global__ void k_march_fixup(int32_t *__restrict__ rays, const int32_t *__restrict__ block_prefix, uint32_t N) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    rays[n * 3 + 1] += block_prefix[n / kMarchBlock];
+}
+
+// pass 2 (:418-479)
+__global__ void __launch_bounds__(kMarchBlock)
+k_march_write(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+              float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+              const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
+              const int32_t *__restrict__ rays, float *__restrict__ xyzs, float *__restrict__ dirs,
+              float *__restrict__ deltas) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const uint32_t point_index = (uint32_t)rays[n * 3 + 1];
+    const uint32_t num_steps = (uint32_t)rays[n * 3 + 2];
+    if (num_steps == 0) return;
+    if (point_index + num_steps > M) return;
+    RayCtx r;
+    rm_setup(r, rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H);
+    const float far = fars[n];
+    float t = nears[n];
+    t = __fmaf_rn(rm_dt(r, t), noises ? noises[n] : 0.0f, t);
+    float *px = xyzs + (size_t)point_index * 3, *pd = dirs + (size_t)point_index * 3, *pl = deltas + (size_t)point_index * 2;
+    float last_t = t, x, y, z, dt;
+    uint32_t step = 0;
+    while (t < far && step < num_steps) {
+        if (rm_step(r, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t = __fadd_rn(t, dt);
+            pl[0] = dt; pl[1] = __fsub_rn(t, last_t);
+            last_t = t;
+            px += 3; pd += 3; pl += 2; step++;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compositing (training): one warp per ray
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_incl_prod(float p) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float q = __shfl_up_sync(0xffffffffu, p, o);
+        if ((int)nb_lane() >= o) p *= q;
+    }
+    return p;
+}
+__device__ __forceinline__ float warp_incl_sum(float p) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float q = __shfl_up_sync(0xffffffffu, p, o);
+        if ((int)nb_lane() >= o) p += q;
+    }
+    return p;
+}
+
+constexpr int kCompBlock = 256;   // 8 rays per block
+
+__global__ void __launch_bounds__(kCompBlock)
+k_composite_train_fwd(const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
+                      const int32_t *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
+                      float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image) {
+    const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
+    if (n >= N) return;
+    const uint32_t lane = nb_lane();
+    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+    float r = 0, g = 0, b = 0, ws = 0, d = 0;
+    if (num_steps != 0 && offset + num_steps <= M) {
+        float T_carry = 1.0f, t_carry = 0.0f;
+        for (uint32_t base = 0; base < num_steps; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < num_steps;
+            const size_t s = (size_t)offset + i;
+            float sigma = 0, d0 = 0, d1 = 0, c0 = 0, c1 = 0, c2 = 0;
+            if (valid) {
+                sigma = __ldg(sigmas + s);
+                const float2 dl = __ldg(reinterpret_cast<const float2 *>(deltas) + s);
+                d0 = dl.x; d1 = dl.y;
+                c0 = __ldg(rgbs + s * 3); c1 = __ldg(rgbs + s * 3 + 1); c2 = __ldg(rgbs + s * 3 + 2);
+            }
+            const float alpha = valid ? 1.0f - __expf(-sigma * d0) : 0.0f;
+            const float pin = warp_incl_prod(1.0f - alpha);
+            float pex = __shfl_up_sync(0xffffffffu, pin, 1);
+            if (lane == 0) pex = 1.0f;
+            const float T_after = T_carry * pin;
+            const float t_i = t_carry + warp_incl_sum(d1);
+            const uint32_t term = __ballot_sync(0xffffffffu, valid && (T_after < T_thresh));
+            const uint32_t last = term ? (uint32_t)(__ffs(term) - 1) : 31u;   // the breaking sample is included (:554-557)
+            const float weight = (valid && lane <= last) ? alpha * (T_carry * pex) : 0.0f;
+            r = fmaf(weight, c0, r); g = fmaf(weight, c1, g); b = fmaf(weight, c2, b);
+            d = fmaf(weight, t_i, d);
+            ws += weight;
+            if (term) break;
+            T_carry = __shfl_sync(0xffffffffu, T_after, 31);
+            t_carry = __shfl_sync(0xffffffffu, t_i, 31);
+        }
+        r = nb_warp_sum(r); g = nb_warp_sum(g); b = nb_warp_sum(b); ws = nb_warp_sum(ws); d = nb_warp_sum(d);
+    }
+    if (lane == 0) {
+        weights_sum[index] = ws;
+        depth[index] = d;
+        image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+    }
+}
+
+__global__ void __launch_bounds__(kCompBlock)
+k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *__restrict__ grad_image,
+                      const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
+                      const int32_t *__restrict__ rays, const float *__restrict__ weights_sum,
+                      const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
+                      float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs) {
+    const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
+    if (n >= N) return;
+    const uint32_t lane = nb_lane();
+    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) return;
+    const float gws = grad_weights_sum[index];
+    const float gi0 = grad_image[index * 3], gi1 = grad_image[index * 3 + 1], gi2 = grad_image[index * 3 + 2];
+    const float r_final = image[index * 3], g_final = image[index * 3 + 1], b_final = image[index * 3 + 2];
+    const float ws_term = gws * (1.0f - weights_sum[index]);
+    float T_carry = 1.0f, r_c = 0, g_c = 0, b_c = 0;
+    bool done = false;
+    for (uint32_t base = 0; base < num_steps; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < num_steps;
+        const size_t s = (size_t)offset + i;
+        float gs = 0, gr0 = 0, gr1 = 0, gr2 = 0;
+        if (!done) {
+            float sigma = 0, d0 = 0, c0 = 0, c1 = 0, c2 = 0;
+            if (valid) {
+                sigma = __ldg(sigmas + s);
+                d0 = __ldg(deltas + s * 2);
+                c0 = __ldg(rgbs + s * 3); c1 = __ldg(rgbs + s * 3 + 1); c2 = __ldg(rgbs + s * 3 + 2);
+            }
+            const float alpha = valid ? 1.0f - __expf(-sigma * d0) : 0.0f;
+            const float pin = warp_incl_prod(1.0f - alpha);
+            float pex = __shfl_up_sync(0xffffffffu, pin, 1);
+            if (lane == 0) pex = 1.0f;
+            const float T_after = T_carry * pin;
+            const uint32_t term = __ballot_sync(0xffffffffu, valid && (T_after < T_thresh));
+            const uint32_t last = term ? (uint32_t)(__ffs(term) - 1) : 31u;
+            const bool act = valid && lane <= last;
+            const float weight = act ? alpha * (T_carry * pex) : 0.0f;
+            const float r_i = r_c + warp_incl_sum(weight * c0);
+            const float g_i = g_c + warp_incl_sum(weight * c1);
+            const float b_i = b_c + warp_incl_sum(weight * c2);
+            if (act) {
+                gr0 = gi0 * weight; gr1 = gi1 * weight; gr2 = gi2 * weight;
+                gs = d0 * (gi0 * (T_after * c0 - (r_final - r_i)) + gi1 * (T_after * c1 - (g_final - g_i)) +
+                           gi2 * (T_after * c2 - (b_final - b_i)) + ws_term);             // :752-757
+            }
+            if (term) done = true;
+            T_carry = __shfl_sync(0xffffffffu, T_after, 31);
+            r_c = __shfl_sync(0xffffffffu, r_i, 31);
+            g_c = __shfl_sync(0xffffffffu, g_i, 31);
+            b_c = __shfl_sync(0xffffffffu, b_i, 31);
+        }
+        if (valid) {   // rows after the early-out get explicit zeros (raymarching.py:284-285 zero-fills instead)
+            grad_sigmas[s] = gs;
+            grad_rgbs[s * 3] = gr0; grad_rgbs[s * 3 + 1] = gr1; grad_rgbs[s * 3 + 2] = gr2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// inference
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *__restrict__ rays_alive, const float *__restrict__ rays_t,
+             const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, float dt_gamma,
+             uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *__restrict__ grid,
+             const float *__restrict__ fars, float *__restrict__ xyzs, float *__restrict__ dirs,
+             float *__restrict__ deltas, const float *__restrict__ noises) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int32_t index = rays_alive[n];
+    RayCtx r;
+    rm_setup(r, rays_o + (size_t)index * 3, rays_d + (size_t)index * 3, grid, bound, dt_gamma, max_steps, C, H);
+    float *px = xyzs + (size_t)n * n_step * 3, *pd = dirs + (size_t)n * n_step * 3, *pl = deltas + (size_t)n * n_step * 2;
+    float t = rays_t[index];
+    const float far = fars[index];
+    t = __fmaf_rn(rm_dt(r, t), noises ? noises[n] : 0.0f, t);       // :930
+    float last_t = t, x, y, z, dt;
+    uint32_t step = 0;
+    while (t < far && step < n_step) {
+        if (rm_step(r, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t = __fadd_rn(t, dt);
+            pl[0] = dt; pl[1] = __fsub_rn(t, last_t);
+            last_t = t;
+            px += 3; pd += 3; pl += 2; step++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *__restrict__ rays_alive,
+                 float *__restrict__ rays_t, const float *__restrict__ sigmas, const float *__restrict__ rgbs,
+                 const float *__restrict__ deltas, float *__restrict__ weights_sum, float *__restrict__ depth,
+                 float *__restrict__ image) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int32_t index = rays_alive[n];
+    const float *s = sigmas + (size_t)n * n_step, *c = rgbs + (size_t)n * n_step * 3, *dl = deltas + (size_t)n * n_step * 2;
+    float t = rays_t[index];
+    float weight_sum = weights_sum[index], d = depth[index];
+    float r = image[index * 3], g = image[index * 3 + 1], b = image[index * 3 + 2];
+    uint32_t step = 0;
+    while (step < n_step) {
+        if (dl[0] == 0) break;                                   // :1042
+        const float alpha = 1.0f - __expf(-s[0] * dl[0]);
+        const float T = 1 - weight_sum;                          // :1052
+        const float weight = alpha * T;
+        weight_sum += weight;
+        t += dl[1];
+        d = fmaf(weight, t, d);
+        r = fmaf(weight, c[0], r); g = fmaf(weight, c[1], g); b = fmaf(weight, c[2], b);
+        if (T < T_thresh) break;                                 // :1066
+        s++; c += 3; dl += 2; step++;
+    }
+    if (step < n_step) rays_alive[n] = -1; else rays_t[index] = t;   // :1078-1082
+    weights_sum[index] = weight_sum; depth[index] = d;
+    image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int nb200_near_far_from_aabb(const float *rays_o, const float *rays_d, const float *aabb, uint32_t N, float min_near,
+                             float *nears, float *fars, void *stream) {
+    if (N == 0) return 0;
+    k_near_far_from_aabb<<<nb_div_up(N, 128), 128, 0, nb_stream(stream)>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_sph_from_ray(const float *rays_o, const float *rays_d, float radius, uint32_t N, float *coords, void *stream) {
+    if (N == 0) return 0;
+    k_sph_from_ray<<<nb_div_up(N, 128), 128, 0, nb_stream(stream)>>>(rays_o, rays_d, radius, N, coords);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_morton3D(const int32_t *coords, uint32_t N, int32_t *indices, void *stream) {
+    if (N == 0) return 0;
+    k_morton3D<<<nb_div_up(N, 256), 256, 0, nb_stream(stream)>>>(coords, N, indices);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_morton3D_invert(const int32_t *indices, uint32_t N, int32_t *coords, void *stream) {
+    if (N == 0) return 0;
+    k_morton3D_invert<<<nb_div_up(N, 256), 256, 0, nb_stream(stream)>>>(indices, N, coords);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *bitfield, void *stream) {
+    if (N == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(grid) & 15u) != 0) return NB200_E_BAD_ARG;
+    k_packbits<<<nb_div_up(N, 256), 256, 0, nb_stream(stream)>>>(grid, N, density_thresh, bitfield);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+uint32_t nb200_march_scratch_ints(uint32_t N) { return 2 * nb_div_up(N, kMarchBlock) + 8; }
+
+int nb200_march_rays_train_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                 const float *nears, const float *fars, const float *noises,
+                                 int32_t *rays, int32_t *counter, int32_t *scratch, void *stream) {
+    if (N == 0) return 0;
+    if (!scratch || !rays || !counter) return NB200_E_BAD_ARG;
+    const uint32_t nb = nb_div_up(N, kMarchBlock);
+    int32_t *block_sums = scratch, *block_prefix = scratch + nb;
+    cudaStream_t st = nb_stream(stream);
+    k_march_count<<<nb, kMarchBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
+                                              noises, rays, block_sums);
+    NB_LAUNCH_CHECK();
+    k_march_scan<<<1, 1024, 0, st>>>(block_sums, block_prefix, nb, N, counter);
+    NB_LAUNCH_CHECK();
+    k_march_fixup<<<nb_div_up(N, 256), 256, 0, st>>>(rays, block_prefix, N);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_march_rays_train_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                 const float *nears, const float *fars, const float *noises, const int32_t *rays,
+                                 float *xyzs, float *dirs, float *deltas, void *stream) {
+    if (N == 0) return 0;
+    k_march_write<<<nb_div_up(N, kMarchBlock), kMarchBlock, 0, nb_stream(stream)>>>(
+        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, noises, rays, xyzs, dirs, deltas);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                           uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
+                           const float *fars, float *xyzs, float *dirs, float *deltas, int32_t *rays, int32_t *counter,
+                           const float *noises, int32_t *scratch, void *stream) {
+    int rc = nb200_march_rays_train_count(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises,
+                                          rays, counter, scratch, stream);
+    if (rc) return rc;
+    return nb200_march_rays_train_write(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars,
+                                        noises, rays, xyzs, dirs, deltas, stream);
+}
+
+int nb200_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas, const int32_t *rays,
+                                       uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth,
+                                       float *image, void *stream) {
+    if (N == 0) return 0;
+    k_composite_train_fwd<<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
+        sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_image, const float *sigmas,
+                                        const float *rgbs, const float *deltas, const int32_t *rays,
+                                        const float *weights_sum, const float *image, uint32_t M, uint32_t N,
+                                        float T_thresh, float *grad_sigmas, float *grad_rgbs, void *stream) {
+    if (N == 0) return 0;
+    k_composite_train_bwd<<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
+        grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas,
+        grad_rgbs);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t,
+                     const float *rays_o, const float *rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                     uint32_t C, uint32_t H, const uint8_t *grid, const float *nears, const float *fars,
+                     float *xyzs, float *dirs, float *deltas, const float *noises, void *stream) {
+    (void)nears;
+    if (n_alive == 0) return 0;
+    k_march_rays<<<nb_div_up(n_alive, 128), 128, 0, nb_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o,
+                                                                        rays_d, bound, dt_gamma, max_steps, C, H, grid,
+                                                                        fars, xyzs, dirs, deltas, noises);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t,
+                         const float *sigmas, const float *rgbs, const float *deltas, float *weights_sum, float *depth,
+                         float *image, void *stream) {
+    if (n_alive == 0) return 0;
+    k_composite_rays<<<nb_div_up(n_alive, 128), 128, 0, nb_stream(stream)>>>(n_alive, n_step, T_thresh, rays_alive,
+                                                                            rays_t, sigmas, rgbs, deltas, weights_sum,
+                                                                            depth, image);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

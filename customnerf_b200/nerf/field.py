@@ -1,0 +1,105 @@
+"""NeRFNetwork: the reference's grid-backbone field network (nerf/network_grid.py:70-206) on the B200 ops.
+
+Module and state-dict names follow the reference so its checkpoints map one-to-one:
+    pos_en.embeddings [rows, 2] fp32, pos_en.offsets [17] int32,
+    network.params, density_network.params, rgb_network.params (flat fp32 vectors).
+"""
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+from torch.amp import custom_bwd, custom_fwd
+
+from ..gridencoder import GridEncoder
+from .mlp import Network
+from .rendering import NeRFRenderer
+
+
+class _trunc_exp(Function):
+    """exp forward, gradient through exp(clamp(x, -15, 15))  (nerf/provider_utils.py:16-29)"""
+
+    @staticmethod
+    @custom_fwd(device_type='cuda', cast_inputs=torch.float)
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    @custom_bwd(device_type='cuda')
+    def backward(ctx, g):
+        x = ctx.saved_tensors[0]
+        return g * torch.exp(x.clamp(-15, 15))
+
+
+trunc_exp = _trunc_exp.apply
+
+
+def freq_embed(d, multires=4):
+    """get_embedder(4): [d, sin(2^k d), cos(2^k d)] for k < 4 -> 27 dims  (nerf/base.py:42-77)"""
+    feats = [d]
+    for k in range(multires):
+        feats += [torch.sin(d * (2.0 ** k)), torch.cos(d * (2.0 ** k))]
+    return torch.cat(feats, -1)
+
+
+def get_encoder(encoding, input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
+                desired_resolution=2048, align_corners=False, **kwargs):
+    """nerf/encoding.py:53-70 (grid encodings only)."""
+    if encoding == 'None':
+        return (lambda x, **kw: x), input_dim
+    if encoding not in ('hashgrid', 'tiledgrid'):
+        raise NotImplementedError('Unknown encoding mode, choose from [None, hashgrid, tiledgrid]')
+    enc = GridEncoder(input_dim=input_dim, num_levels=num_levels, level_dim=level_dim,
+                      base_resolution=base_resolution, log2_hashmap_size=log2_hashmap_size,
+                      desired_resolution=desired_resolution,
+                      gridtype='hash' if encoding == 'hashgrid' else 'tiled', align_corners=align_corners)
+    return enc, enc.output_dim
+
+
+def _mlp_cfg(out_act, n_hidden):
+    return {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": out_act, "n_neurons": 64,
+            "n_hidden_layers": n_hidden}
+
+
+class NeRFNetwork(NeRFRenderer):
+    def __init__(self, opt, encoding='tiledgrid', log2_hashmap_size=21, desired_resolution=8192, **unused):
+        """Defaults are the reference's hard-coded grid (network_grid.py:89-96); BASELINE.json's configs use
+        encoding='hashgrid', log2_hashmap_size=19, desired_resolution=2048 (nerf/encoding.py:55-58)."""
+        super().__init__(opt)
+        self.pos_en, self.pos_en_dim = get_encoder(encoding, input_dim=3, log2_hashmap_size=log2_hashmap_size,
+                                                   desired_resolution=desired_resolution)
+        self.network = Network(self.pos_en_dim, 64, _mlp_cfg("None", 2), seed=1337)
+        self.density_network = Network(64, 1, _mlp_cfg("None", 1), seed=1338)
+        self.input_ch_views = 27
+        n_out = 3 + (1 if getattr(opt, 'train_conf', 0) else 0)
+        self.rgb_network = Network(self.input_ch_views + 64, n_out, _mlp_cfg("Sigmoid", 1), seed=1339)
+        self.bg_net = None
+
+    def background(self, d):
+        return torch.zeros(d.size(), dtype=d.dtype, device=d.device)
+
+    def gaussian(self, x):
+        """density blob at the scene centre (network_grid.py:150-156)"""
+        return 5 * torch.exp(-(x ** 2).sum(-1) / (2 * 0.2 ** 2))
+
+    def forward(self, x, d, l=None, ratio=1, shading='albedo'):
+        x_en = self.pos_en(x, bound=self.opt.bound)
+        fea = self.network(x_en)
+        sigma = self.density_network(fea)
+        sigma = trunc_exp(sigma.squeeze(-1) + self.gaussian(x))
+        rgb_input = torch.cat([freq_embed(d).to(fea.dtype), fea], dim=-1)
+        radiances = self.rgb_network(rgb_input)
+        return sigma, radiances, None
+
+    def density(self, x):
+        x_en = self.pos_en(x, bound=self.opt.bound)
+        fea = self.network(x_en)
+        sigma = self.density_network(fea)
+        return {'sigma': trunc_exp(sigma.squeeze(-1) + self.gaussian(x))}
+
+    def get_params(self, lr):
+        return [
+            {'params': self.pos_en.parameters(), 'lr': lr * 10},
+            {'params': self.network.parameters(), 'lr': lr},
+            {'params': self.density_network.parameters(), 'lr': lr},
+            {'params': self.rgb_network.parameters(), 'lr': lr},
+        ]

@@ -1,0 +1,282 @@
+"""NeRFRenderer: the hot-path half of the reference's ``nerf/renderer.py`` on the B200 ops.
+
+Covered (reference line numbers):
+  render()              :1719-1733   dispatch dense / occupancy path
+  run()                 :278-405     dense 64+64 sampler with LGIE outputs (fg / bg / soft mask / detach_bg)
+  weights_sum_i()       :407-474     torch compositing used by run()
+  run_cuda()            :597-718     occupancy-grid renderer (train: march + composite; eval: n_step loop)
+                                     following run_cuda2 (:476-595) where run_cuda is broken as shipped
+                                     (4-channel rgbs / image)
+  update_extra_state()  :1658-1715   occupancy-grid EMA update + packbits
+  reset_extra_state()   :262-276
+
+Out of scope (never reachable with --backbone grid): run_sdf, run_composite, sample_pts_*, mesh export.
+
+The reference reads ``opt.bg_color`` which main.py never defines (Appendix B1); a missing attribute is None here.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import raymarching
+
+
+def sample_pdf(bins, weights, n_samples, det=False):
+    """Inverse-CDF sampling of ``n_samples`` depths per ray (reference :21-55, from the original NeRF)."""
+    weights = weights + 1e-5
+    pdf = weights / weights.sum(-1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    if det:
+        u = torch.linspace(0.5 / n_samples, 1.0 - 0.5 / n_samples, steps=n_samples, device=weights.device)
+        u = u.expand(list(cdf.shape[:-1]) + [n_samples])
+    else:
+        u = torch.rand(list(cdf.shape[:-1]) + [n_samples], device=weights.device)
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = (inds - 1).clamp_min(0)
+    above = inds.clamp_max(cdf.shape[-1] - 1)
+    cdf_lo, cdf_hi = torch.gather(cdf, 1, below), torch.gather(cdf, 1, above)
+    bin_lo, bin_hi = torch.gather(bins, 1, below), torch.gather(bins, 1, above)
+    denom = cdf_hi - cdf_lo
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    return bin_lo + (u - cdf_lo) / denom * (bin_hi - bin_lo)
+
+
+class NeRFRenderer(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.bound = opt.bound
+        self.cascade = 1 + math.ceil(math.log2(opt.bound))
+        self.grid_size = 128
+        self.cuda_ray = opt.cuda_ray
+        self.min_near = opt.min_near
+        self.density_thresh = opt.density_thresh
+
+        box = torch.tensor([-opt.bound] * 3 + [opt.bound] * 3, dtype=torch.float32)
+        self.register_buffer('aabb_train', box)
+        self.register_buffer('aabb_infer', box.clone())
+        self.register_buffer('aabb_train_bg', 2 * box)
+        self.register_buffer('aabb_infer_bg', 2 * box)
+
+        if self.cuda_ray:   # state-dict keys as in the reference (:224-241)
+            self.register_buffer('density_grid', torch.zeros(self.cascade, self.grid_size ** 3))
+            self.register_buffer('density_bitfield',
+                                 torch.zeros(self.cascade * self.grid_size ** 3 // 8, dtype=torch.uint8))
+            self.register_buffer('step_counter', torch.zeros(16, 2, dtype=torch.int32))
+            self.mean_density = 0
+            self.iter_density = 0
+            self.mean_count = 0
+            self.local_step = 0
+
+    # the field network provides these
+    def forward(self, x, d):
+        raise NotImplementedError()
+
+    def density(self, x):
+        raise NotImplementedError()
+
+    def reset_extra_state(self):
+        if not self.cuda_ray:
+            return
+        self.density_grid.zero_()
+        self.mean_density = 0
+        self.iter_density = 0
+        self.step_counter.zero_()
+        self.mean_count = 0
+        self.local_step = 0
+
+    def _flag(self, name, default=None):
+        return getattr(self.opt, name, default)
+
+    # ------------------------------------------------------------------------------------- dense path
+    def run(self, rays_o, rays_d, num_steps=128, upsample_steps=128, bg_color=None, perturb=False, **kwargs):
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        N = rays_o.shape[0]
+        dev = rays_o.device
+        aabb = self.aabb_train if self.training else self.aabb_infer
+
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, aabb, self.min_near)
+        nears = nears.unsqueeze(-1)
+        fars = fars.unsqueeze(-1)
+
+        # stratified coarse samples
+        z_vals = nears + (fars - nears) * torch.linspace(0.0, 1.0, num_steps, device=dev).unsqueeze(0)
+        sample_dist = (fars - nears) / num_steps
+        if perturb:
+            z_vals = z_vals + (torch.rand(z_vals.shape, device=dev) - 0.5) * sample_dist
+        xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z_vals.unsqueeze(-1)
+        xyzs = torch.min(torch.max(xyzs, aabb[:3]), aabb[3:])
+        sigma_c = self.density(xyzs.reshape(-1, 3))['sigma'].view(N, num_steps)
+
+        if upsample_steps > 0:   # importance samples from the coarse weights
+            with torch.no_grad():
+                deltas = torch.cat([z_vals[..., 1:] - z_vals[..., :-1], sample_dist], dim=-1)
+                alphas = 1 - torch.exp(-deltas * sigma_c)
+                trans = torch.cumprod(torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1), dim=-1)
+                weights = alphas * trans[..., :-1]
+                z_mid = z_vals[..., :-1] + 0.5 * deltas[..., :-1]
+                new_z = sample_pdf(z_mid, weights[:, 1:-1], upsample_steps, det=not self.training).detach()
+                new_xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * new_z.unsqueeze(-1)
+                new_xyzs = torch.min(torch.max(new_xyzs, aabb[:3]), aabb[3:])
+            # the reference also evaluates density(new_xyzs) here (:353) and merges it into a dict nothing reads;
+            # no output depends on it, so it is skipped
+            z_vals, order = torch.sort(torch.cat([z_vals, new_z], dim=1), dim=1)
+            xyzs = torch.gather(torch.cat([xyzs, new_xyzs], dim=1), 1, order.unsqueeze(-1).expand(-1, -1, 3))
+
+        dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)
+        sigmas, rgbs, _ = self(xyzs.reshape(-1, 3), dirs.reshape(-1, 3))
+        masks = None
+        if rgbs.shape[-1] > 3:
+            n_dim = rgbs.shape[-1] - 3
+            rgbs, masks = rgbs.split([3, n_dim], dim=-1)
+            masks = masks.reshape(N, -1, n_dim)
+        sigmas = sigmas.view(N, -1, 1)
+        rgbs = rgbs.reshape(N, -1, 3)
+
+        args = (sample_dist, z_vals, nears, fars, rgbs, prefix)
+        if self._flag('train_conf') and masks is not None:
+            results = self.weights_sum_i(sigmas, *args, masks=masks, is_all=True)
+            if self._flag('soft_mask', False):
+                edit_mask = torch.sigmoid((masks - self._flag('conf_thr', 0.5)) * 100)
+                sigmas_fg = sigmas * edit_mask
+                sigmas_bg = sigmas * (1 - edit_mask)
+            else:
+                edit_mask = masks > 0.5
+                sigmas_fg = torch.where(edit_mask, sigmas, torch.zeros_like(sigmas))
+                sigmas_bg = torch.where(edit_mask, torch.zeros_like(sigmas), sigmas)
+            results['sigma'] = sigmas
+            results['rgbs'] = rgbs
+            results['edit_mask'] = edit_mask
+            results['fg'] = self.weights_sum_i(sigmas_fg, *args, masks=masks, if_fg=True)
+            results['bg'] = self.weights_sum_i(sigmas_bg, *args, masks=masks)
+        else:
+            results = self.weights_sum_i(sigmas, *args, masks=None, is_all=True)
+        return results
+
+    def weights_sum_i(self, sigmas, sample_dist, z_vals, nears, fars, rgbs, prefix, masks=None, bg_color=None,
+                      if_fg=False, is_all=False):
+        if is_all and self._flag('detach_bg', False) and masks is not None:
+            # samples the mask head calls background contribute values but no gradient (:409-418)
+            edit_points = masks.mean(-1, keepdim=True) >= 0.5
+            sigmas = torch.where(edit_points, sigmas, sigmas.detach())
+            rgbs = torch.where(edit_points, rgbs, rgbs.detach())
+        deltas = torch.cat([z_vals[..., 1:] - z_vals[..., :-1], sample_dist], dim=-1)
+        alphas = 1 - torch.exp(-deltas * sigmas.squeeze(-1))
+        trans = torch.cumprod(torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1), dim=-1)
+        weights = alphas * trans[..., :-1]
+        weights_sum = weights.sum(dim=-1)
+        ori_z = ((z_vals - nears) / (fars - nears)).clamp(0, 1)
+        depth = torch.sum(weights * ori_z, dim=-1)
+        image = torch.sum(weights.unsqueeze(-1) * rgbs, dim=-2).view(*prefix, 3)
+        results = {}
+        if if_fg and bg_color is not None:
+            results['black_image'] = image
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        results['image'] = image
+        if self._flag('train_conf') and masks is not None:
+            w = weights.detach() if self._flag('detach_mask_from_field', False) else weights
+            results['render_mask'] = torch.sum(w.unsqueeze(-1) * masks, dim=-2).view(*prefix, -1)
+        results['depth'] = depth.view(*prefix)
+        results['weights_sum'] = weights_sum
+        results['weights'] = weights
+        results['mask'] = (nears < fars).reshape(*prefix)
+        return results
+
+    # ------------------------------------------------------------------------------------- occupancy path
+    def run_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024,
+                 T_thresh=1e-4, **kwargs):
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.cuda().contiguous().view(-1, 3)
+        rays_d = rays_d.cuda().contiguous().view(-1, 3)
+        N = rays_o.shape[0]
+        dev = rays_o.device
+        aabb = self.aabb_train if self.training else self.aabb_infer
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, aabb)    # min_near stays 0.2 here (Appendix B5)
+        results = {}
+        if self.training:
+            counter = self.step_counter[self.local_step % 16]
+            counter.zero_()
+            self.local_step += 1
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
+                self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps)
+            sigmas, rgbs, _ = self(xyzs, dirs)
+            rgbs = rgbs[..., :3]
+            weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs.float(), deltas, rays, T_thresh)
+        else:
+            weights_sum = torch.zeros(N, dtype=torch.float32, device=dev)
+            depth = torch.zeros(N, dtype=torch.float32, device=dev)
+            image = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+            rays_alive = torch.arange(N, dtype=torch.int32, device=dev)
+            rays_t = nears.clone()
+            step = 0
+            while step < max_steps:
+                n_alive = rays_alive.shape[0]
+                if n_alive <= 0:
+                    break
+                n_step = max(min(N // n_alive, 8), 1)
+                xyzs, dirs, deltas = raymarching.march_rays(
+                    n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, self.density_bitfield,
+                    self.cascade, self.grid_size, nears, fars, 128, perturb if step == 0 else False, dt_gamma, max_steps)
+                sigmas, rgbs, _ = self(xyzs, dirs)
+                rgbs = rgbs[..., :3]
+                raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum,
+                                           depth, image, T_thresh)
+                rays_alive = rays_alive[rays_alive >= 0]
+                step += n_step
+
+        bgc = self._flag('bg_color')
+        if bgc:
+            bg = torch.tensor([list(bgc)], dtype=torch.float32, device=dev)
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg
+        elif bg_color is not None:
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        results['image'] = image.view(*prefix, 3)
+        results['depth'] = depth.view(*prefix)
+        results['weights_sum'] = weights_sum.reshape(*prefix)
+        results['mask'] = (nears < fars).reshape(*prefix)
+        return results
+
+    # ------------------------------------------------------------------------------------- occupancy grid
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128):
+        if not self.cuda_ray:
+            return
+        dev = self.density_bitfield.device
+        G = self.grid_size
+        tmp_grid = -torch.ones_like(self.density_grid)
+        axis = torch.arange(G, dtype=torch.int32, device=dev)
+        for xs in axis.split(S):
+            for ys in axis.split(S):
+                for zs in axis.split(S):
+                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
+                    coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
+                    indices = raymarching.morton3D(coords).long()
+                    xyzs = 2 * coords.float() / (G - 1) - 1
+                    for cas in range(self.cascade):
+                        bound = min(2 ** cas, self.bound)
+                        half_grid_size = bound / G
+                        cas_xyzs = xyzs * (bound - half_grid_size)
+                        cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half_grid_size
+                        sigmas = self.density(cas_xyzs)['sigma'].reshape(-1).detach()
+                        tmp_grid[cas, indices] = sigmas.float()
+        valid = self.density_grid >= 0
+        self.density_grid[valid] = torch.maximum(self.density_grid[valid] * decay, tmp_grid[valid])
+        self.mean_density = torch.mean(self.density_grid[valid]).item()
+        self.iter_density += 1
+        density_thresh = min(self.mean_density, self.density_thresh)
+        self.density_bitfield = raymarching.packbits(self.density_grid, density_thresh, self.density_bitfield)
+        total_step = min(16, self.local_step)
+        if total_step > 0:
+            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        self.local_step = 0
+
+    def render(self, rays_o, rays_d, staged=False, max_ray_batch=2048, **kwargs):
+        if self.cuda_ray and 'neus' not in str(self._flag('backbone', 'grid')):
+            return self.run_cuda(rays_o, rays_d, **kwargs)
+        return self.run(rays_o, rays_d, **kwargs)

@@ -1,0 +1,151 @@
+/*
+ * nerf_b200.h -- C ABI of libnerf_b200.so: the B200 (sm_100a) replacement for CustomNeRF's two native
+ * extensions (gridencoder, raymarching) plus the field-network MLP the reference takes from tiny-cuda-nn.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer on the current device unless stated otherwise;
+ *   - the caller owns all memory; nothing here allocates (scratch is passed in) or retains pointers;
+ *   - sizes are uint32_t, scalars float, exactly as the reference's pybind entry points pass them;
+ *   - the last argument is the cudaStream_t to launch on (as void*; NULL = legacy default stream) --
+ *     the reference always launches on the legacy default stream;
+ *   - the return value is 0 on success, otherwise a cudaError_t (> 0) or one of NB200_E_* (< 0);
+ *     nb200_error_string() turns either into text.  The reference returns void and surfaces faults
+ *     asynchronously; its TORCH_CHECKs become NB200_E_* codes that the Python layer re-raises as
+ *     RuntimeError with the reference's wording.
+ *
+ * Each entry point names the reference function it replaces as file:line under /root/reference.
+ */
+#ifndef NERF_B200_H
+#define NERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* dtype tags for void* tensors */
+#define NB200_F32 0
+#define NB200_F16 1
+
+/* error codes (negative; positive values are cudaError_t) */
+#define NB200_E_BAD_DIM   (-1)   /* "GridEncoding: C must be 1, 2, 4, or 8." / D must be 2..5 (gridencoder.cu:380,397) */
+#define NB200_E_BAD_DTYPE (-2)   /* unsupported dtype tag (the reference's f64 instantiations are not built) */
+#define NB200_E_BAD_ARG   (-3)   /* null pointer / inconsistent sizes */
+#define NB200_E_SCRATCH   (-4)   /* scratch buffer too small */
+
+const char *nb200_error_string(int code);
+int nb200_version(void);
+
+/* ============================================================================================
+ * gridencoder  (reference: gridencoder/src/gridencoder.h:12-15, bindings.cpp:5-7)
+ * ========================================================================================== */
+
+/* Output layout of grid_encode_forward / input layout of grid_encode_backward's grad. */
+#define NB200_LAYOUT_LBC 0   /* [L, B, C]: the reference's native layout (gridencoder.cu:384-389)            */
+#define NB200_LAYOUT_BLC 1   /* [B, L*C]: what grid.py:63 / :81 produce with an extra permute copy; written
+                                directly here so the copy disappears                                        */
+
+/* Replaces grid_encode_forward (gridencoder.cu:447-470 -> kernel_grid :87-244).
+ *   inputs      f32 [B, D] in [0,1]            embeddings  emb_dtype [rows, C]
+ *   offsets     i32 [L+1]                      outputs     emb_dtype, layout per `layout`
+ *   dy_dx       emb_dtype [B, L*D*C] or NULL   S = log2(per_level_scale), H = base resolution
+ *   gridtype 0 = hash, 1 = tiled; interp 0 = linear, 1 = smoothstep.
+ * Levels >= max_level are not written (caller zero-fills, grid.py:52).
+ * fp16 mode accumulates in fp32 and rounds once (the reference rounds twice per corner). */
+int nb200_grid_encode_forward(const float *inputs, const void *embeddings, const int32_t *offsets, void *outputs,
+                              uint32_t B, uint32_t D, uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                              void *dy_dx, uint32_t gridtype, int align_corners, uint32_t interp,
+                              int emb_dtype, int layout, void *stream);
+
+/* Replaces grid_encode_backward (gridencoder.cu:472-502 -> kernel_grid_backward :247-339,
+ * kernel_input_backward :342-368).
+ *   grad             grad_dtype, layout per `layout`          grad_embeddings  f32 [rows, C], ACCUMULATED INTO
+ *   dy_dx            grad_dtype [B, L*D*C] or NULL            grad_inputs      grad_dtype [B, D] or NULL
+ * grad_embeddings is always fp32 (the reference scatters __half2 atomics under AMP); the caller zero-fills it
+ * (grid.py:83).  agg: 0 = one atomic per corner, 1 = warp-aggregated scatter (adjacent samples of a ray that share
+ * a cell are summed in registers and issue one atomic). */
+int nb200_grid_encode_backward(const void *grad, const float *inputs, const int32_t *offsets, float *grad_embeddings,
+                               uint32_t B, uint32_t D, uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                               const void *dy_dx, void *grad_inputs, uint32_t gridtype, int align_corners,
+                               uint32_t interp, int grad_dtype, int layout, int agg, void *stream);
+
+/* Replaces grad_total_variation (gridencoder.cu:638-644 -> kernel_grad_tv :505-609).  f32 only
+ * (grid.py:171 forces autocast off).  inputs f32 [B, D] in [0,1]; adds into grad f32 [rows, C]. */
+int nb200_grad_total_variation(const float *inputs, const float *embeddings, float *grad, const int32_t *offsets,
+                               float weight, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                               uint32_t gridtype, int align_corners, void *stream);
+
+/* scales[l] = exp2f(l * S) * H - 1.0f evaluated on the device (gridencoder.cu:138); test aid: lets the CPU
+ * oracle use the device's exp2f values.  scales f32 [L]. */
+int nb200_grid_level_scales(float *scales, uint32_t L, float S, uint32_t H, void *stream);
+
+/* fp32 -> fp16 copy of the table (the persistent half "shadow" that replaces grid.py:45-46's per-call cast). */
+int nb200_cast_f32_to_f16(const float *src, void *dst, uint64_t n, void *stream);
+
+/* ============================================================================================
+ * raymarching  (reference: raymarching/src/raymarching.h:7-22, bindings.cpp:5-20)
+ * ========================================================================================== */
+
+/* Replaces near_far_from_aabb (raymarching.cu:148-156 -> kernel :91-145). */
+int nb200_near_far_from_aabb(const float *rays_o, const float *rays_d, const float *aabb, uint32_t N, float min_near,
+                             float *nears, float *fars, void *stream);
+/* Replaces sph_from_ray (raymarching.cu:201-209 -> kernel :162-199). */
+int nb200_sph_from_ray(const float *rays_o, const float *rays_d, float radius, uint32_t N, float *coords, void *stream);
+/* Replaces morton3D / morton3D_invert (raymarching.cu:229-232, :257-260). */
+int nb200_morton3D(const int32_t *coords, uint32_t N, int32_t *indices, void *stream);
+int nb200_morton3D_invert(const int32_t *indices, uint32_t N, int32_t *coords, void *stream);
+/* Replaces packbits (raymarching.cu:292-300 -> kernel :267-289).  N = number of output bytes. */
+int nb200_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *bitfield, void *stream);
+
+/* march_rays_train (raymarching.cu:482-490 -> kernel :311-480), split in two so the caller can size the outputs
+ * exactly instead of allocating N*max_steps rows (raymarching.py:196-209):
+ *
+ *   nb200_march_rays_train_count : march every ray once, counts -> rays[n] = (n, offset, count) with offsets the
+ *       exclusive scan of the counts in ray-id order STARTING AT counter[0]'s entry value (one valid member of
+ *       the reference's atomicAdd-ordered output set); then counter[0] += sum, counter[1] += N.
+ *       scratch: i32, at least nb200_march_scratch_ints(N) entries.
+ *   nb200_march_rays_train_write : march again and write xyzs/dirs/deltas for rays whose segment fits in M
+ *       (raymarching.cu:415-416).  Rows not covered by a segment are left untouched (caller zero-fills,
+ *       raymarching.py:206-208).
+ *   nb200_march_rays_train       : both, back to back == the reference entry point. */
+uint32_t nb200_march_scratch_ints(uint32_t N);
+int nb200_march_rays_train_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                 const float *nears, const float *fars, const float *noises,
+                                 int32_t *rays, int32_t *counter, int32_t *scratch, void *stream);
+int nb200_march_rays_train_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                 const float *nears, const float *fars, const float *noises, const int32_t *rays,
+                                 float *xyzs, float *dirs, float *deltas, void *stream);
+int nb200_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                           uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
+                           const float *fars, float *xyzs, float *dirs, float *deltas, int32_t *rays, int32_t *counter,
+                           const float *noises, int32_t *scratch, void *stream);
+
+/* Replaces composite_rays_train_forward (+_sdf, byte-identical math) (raymarching.cu:660-679 -> kernel :500-577). */
+int nb200_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas, const int32_t *rays,
+                                       uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth,
+                                       float *image, void *stream);
+/* Replaces composite_rays_train_backward (+_sdf) (raymarching.cu:860-878 -> kernel :691-772).  Every row of a ray's
+ * segment is written (zeros after the early-out), rows outside any segment are left untouched. */
+int nb200_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_image, const float *sigmas,
+                                        const float *rgbs, const float *deltas, const int32_t *rays,
+                                        const float *weights_sum, const float *image, uint32_t M, uint32_t N,
+                                        float T_thresh, float *grad_sigmas, float *grad_rgbs, void *stream);
+
+/* Replaces march_rays (raymarching.cu:992-999 -> kernel :884-989).  Outputs must be zero-filled by the caller. */
+int nb200_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t,
+                     const float *rays_o, const float *rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                     uint32_t C, uint32_t H, const uint8_t *grid, const float *nears, const float *fars,
+                     float *xyzs, float *dirs, float *deltas, const float *noises, void *stream);
+/* Replaces composite_rays (raymarching.cu:1092-1098 -> kernel :1002-1089).  In-place on rays_alive / rays_t /
+ * weights_sum / depth / image. */
+int nb200_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t,
+                         const float *sigmas, const float *rgbs, const float *deltas, float *weights_sum, float *depth,
+                         float *image, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H */
