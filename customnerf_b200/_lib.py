@@ -33,7 +33,14 @@ def lib():
     return _lib
 
 
+# number of this library's kernel launches so far (bench.py reports it as gpu_launches)
+LAUNCHES = 0
+_LAUNCHES_PER_CALL = {"march_rays_train(count)": 3, "count": 3}
+
+
 def check(rc, what):
+    global LAUNCHES
+    LAUNCHES += _LAUNCHES_PER_CALL.get(what, 1)
     if rc != 0:
         msg = lib().nb200_error_string(C.c_int(rc)).decode()
         raise RuntimeError("%s failed: %s (code %d)" % (what, msg, rc))

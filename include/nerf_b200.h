@@ -145,6 +145,15 @@ int nb200_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int3
                          const float *sigmas, const float *rgbs, const float *deltas, float *weights_sum, float *depth,
                          float *image, void *stream);
 
+/* ============================================================================================
+ * tensor-core path self test (no reference counterpart): one-CTA tcgen05 GEMM D[128,N] = A[128,K] * B[N,K]^T with
+ * fp16 operands / fp32 accumulation, used by the tests to pin the UMMA descriptor conventions the fused MLP
+ * kernels rely on.  a_mn / b_mn select MN-major operand storage (A given as [K][128], B as [K][N]).
+ * status (device u32) is set to 1 if the MMA never signalled completion.
+ * ========================================================================================== */
+int nb200_umma_selftest(const void *A, const void *B, float *D, uint32_t N, uint32_t K, uint32_t a_mn, uint32_t b_mn,
+                        uint32_t *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,130 @@
+"""-m gpu: the whole hot path (march -> encode -> MLP -> composite, forward + backward) and the renderers built on it
+against the CPU oracle restatement (oracle/torch_ref.py) with identical weights.
+
+MLP numerics contract (tiny-cuda-nn is un-vendored: parity unpinned): fp16 operands, fp32 accumulation; the oracle
+emulates the operand rounding (half=True), so the remaining differences are accumulation order: abs 2e-3 / rel 1e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close
+from oracle import torch_ref
+
+pytestmark = pytest.mark.gpu
+ENC = dict(log2_hashmap_size=15, desired_resolution=512)
+
+
+def _pair(opt, scene=None):
+    from customnerf_b200.nerf import NeRFNetwork
+    torch.manual_seed(0)
+    net = NeRFNetwork(opt, encoding="hashgrid", **ENC).cuda()
+    with torch.no_grad():
+        net.pos_en.embeddings.uniform_(-0.5, 0.5)
+    ref = torch_ref.NeRFNetwork(opt, encoder_kwargs=dict(gridtype="hash", **ENC))
+    ref.pos_en.embeddings.data.copy_(net.pos_en.embeddings.detach().cpu())
+    for name in ("network", "density_network", "rgb_network"):
+        getattr(ref, name).params.data.copy_(getattr(net, name).params.detach().cpu())
+        getattr(ref, name).half = True
+    if scene is not None and opt.cuda_ray:
+        bf = torch.from_numpy(scene["bitfield"])
+        net.density_bitfield.copy_(bf.cuda())
+        ref.density_bitfield = bf
+    return net, ref
+
+
+def test_field_network_forward_and_density():
+    opt = torch_ref.default_opt(train_conf=0.01)
+    net, ref = _pair(opt)
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(4096, 3, generator=g) * 2 - 1) * 1.9
+    d = torch.randn(4096, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    sigma, rgba, _ = net(x.cuda(), d.cuda())
+    s0, c0, _ = ref(x, d)
+    assert rgba.shape == (4096, 4) and sigma.dtype == torch.float32
+    assert_close(rgba.float().detach().cpu().numpy(), c0.detach().numpy(), 1e-2, 2e-3, "radiances")
+    assert_close(sigma.detach().cpu().numpy(), s0.detach().numpy(), 2e-2, 1e-3, "sigma")
+    assert_close(net.density(x.cuda())["sigma"].detach().cpu().numpy(), s0.detach().numpy(), 2e-2, 1e-3, "density()")
+
+
+def test_cuda_ray_train_step_matches_oracle(scene):
+    opt = torch_ref.default_opt(cuda_ray=True, train_conf=0)
+    net, ref = _pair(opt, scene)
+    sel = slice(7000, 7512)
+    o, d = torch.from_numpy(scene["rays_o"][sel]), torch.from_numpy(scene["rays_d"][sel])
+    target = torch.rand(512, 3, generator=torch.Generator().manual_seed(2))
+    net.train(); ref.train()
+    out = net.render(o[None].cuda(), d[None].cuda(), perturb=False, force_all_rays=True)
+    out0 = ref.render(o[None], d[None], perturb=False, force_all_rays=True)
+    assert int(net.step_counter[0, 0]) == int(ref.step_counter[0, 0]) > 1000
+    assert_close(out["image"].detach().cpu().numpy(), out0["image"].detach().numpy(), 1e-2, 2e-3, "image")
+    assert_close(out["weights_sum"].detach().cpu().numpy(), out0["weights_sum"].detach().numpy(), 1e-2, 2e-3, "weights_sum")
+    assert_close(out["depth"].detach().cpu().numpy(), out0["depth"].detach().numpy(), 1e-2, 2e-3, "depth")
+    ((out["image"].reshape(-1, 3) - target.cuda()) ** 2).mean().backward()
+    ((out0["image"].reshape(-1, 3) - target) ** 2).mean().backward()
+    for name in ("network", "density_network", "rgb_network"):
+        g, g0 = getattr(net, name).params.grad.cpu().numpy(), getattr(ref, name).params.grad.numpy()
+        assert_close(g, g0, 5e-2, 2e-2 * np.abs(g0).max(), name + ".params.grad")
+    g, g0 = net.pos_en.embeddings.grad.cpu().numpy(), ref.pos_en.embeddings.grad.numpy()
+    assert_close(g, g0, 5e-2, 2e-2 * np.abs(g0).max(), "embeddings.grad")
+
+
+def test_cuda_ray_eval_matches_oracle(scene):
+    opt = torch_ref.default_opt(cuda_ray=True, train_conf=0)
+    net, ref = _pair(opt, scene)
+    sel = slice(7100, 7356)
+    o, d = torch.from_numpy(scene["rays_o"][sel]), torch.from_numpy(scene["rays_d"][sel])
+    net.eval(); ref.eval()
+    with torch.no_grad():
+        out = net.render(o[None].cuda(), d[None].cuda(), perturb=False)
+        out0 = ref.render(o[None], d[None], perturb=False)
+    assert_close(out["image"].cpu().numpy(), out0["image"].numpy(), 1e-2, 3e-3, "image")
+    assert_close(out["weights_sum"].cpu().numpy(), out0["weights_sum"].numpy(), 1e-2, 3e-3, "weights_sum")
+
+
+@pytest.mark.parametrize("soft_mask,detach_bg", [(False, False), (True, True)])
+def test_dense_lgie_render_matches_oracle(soft_mask, detach_bg):
+    """NeRFRenderer.run with the LGIE outputs (fg / bg / render_mask; renderer.py:383-403) at deterministic samples"""
+    from customnerf_b200 import synthetic as syn
+    opt = torch_ref.default_opt(cuda_ray=False, train_conf=0.01, soft_mask=soft_mask, detach_bg=detach_bg)
+    net, ref = _pair(opt)
+    o, d = syn.random_rays(256, seed=4)
+    net.eval(); ref.eval()           # eval => deterministic importance sampling (det=True), no perturbation
+    out = net.render(o[None].cuda(), d[None].cuda(), num_steps=32, upsample_steps=32, perturb=False)
+    out0 = ref.render(o[None], d[None], num_steps=32, upsample_steps=32, perturb=False)
+    for key in ("image", "render_mask", "weights_sum", "depth"):
+        assert_close(out[key].detach().cpu().numpy(), out0[key].detach().numpy(), 2e-2, 5e-3, key)
+    for part in ("fg", "bg"):
+        assert_close(out[part]["image"].detach().cpu().numpy(), out0[part]["image"].detach().numpy(), 2e-2, 5e-3,
+                     part + ".image")
+    loss = out["image"].mean() + out["render_mask"].mean() + out["fg"]["image"].mean()
+    loss.backward()
+    assert net.pos_en.embeddings.grad.abs().sum() > 0 and torch.isfinite(net.rgb_network.params.grad).all()
+
+
+def test_update_extra_state_builds_the_same_bitfield(scene):
+    """occupancy-grid update (renderer.py:1658-1715): EMA + mean + packbits on the GPU vs the oracle, same densities"""
+    from customnerf_b200 import raymarching as rm
+    opt = torch_ref.default_opt(cuda_ray=True, train_conf=0)
+    net, ref = _pair(opt, scene)
+    net.update_extra_state()
+    assert net.density_bitfield.dtype == torch.uint8 and net.iter_density == 1
+    grid = net.density_grid.cpu().numpy()
+    thr = min(net.mean_density, net.density_thresh)
+    from oracle import cpu_ops
+    assert np.array_equal(net.density_bitfield.cpu().numpy(), cpu_ops.packbits(grid, thr))
+    assert abs(net.mean_density - float(grid.mean())) < 1e-4 * max(1.0, abs(float(grid.mean())))
+    assert (grid >= 0).all()
+
+
+def test_train_step_harness_runs_and_reduces_loss(scene):
+    from customnerf_b200 import trainer, synthetic as syn
+    model = trainer.build_scene_model(torch.device("cuda"), log2_hashmap_size=15, desired_resolution=512)
+    ts = trainer.TrainStep(model, lr=5e-3)
+    o, d = syn.camera_rays(105, 142)
+    sel = torch.arange(6000, 10000)
+    o, d = o[sel].cuda(), d[sel].cuda()
+    target = syn.bear_color(o + d * 1.5)
+    losses = [float(ts.step(o, d, target)) for _ in range(30)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
