@@ -151,8 +151,17 @@ def test_grid_encoder_against_reference_kernels(scene, cfg, half):
     mine_g = enc.embeddings.grad.cpu().numpy()
     ref_g = gemb_ref.float().cpu().numpy()
     if half:
-        # the reference sums rounded __half2 atomics (gridencoder.cu:324-330); coarse cells receive thousands of
-        # adds, so its own error is the tolerance here: rel 1e-2 with the abs floor of north_star
-        assert_close(mine_g, ref_g, 1e-2, 2e-2 * np.abs(ref_g).max(), "grad fp16")
+        # The reference sums rounded __half2 atomics (gridencoder.cu:324-330): a coarse cell receives thousands of
+        # adds and its fp16 accumulator loses up to a few percent (measured: 2.2 % at the hottest cell of level 0),
+        # so against the reference the bound is its own error: rel 3e-2 with an abs floor of 2e-2 * max|g| ...
+        assert_close(mine_g, ref_g, 3e-2, 2e-2 * np.abs(ref_g).max(), "grad fp16 vs reference half atomics")
+        # ... while against the fp64-accumulated oracle this implementation (fp32 accumulation) meets the
+        # north_star bound (rel 1e-2) with room to spare
+        from customnerf_b200.gridencoder import level_scales
+        sc = level_scales(16, enc.per_level_scale, 16).cpu().numpy()
+        g0, _ = cpu_ops.grid_encode_backward(g.float().cpu().numpy(), x01.cpu().numpy(), tuple(enc.embeddings.shape),
+                                             enc.offsets.cpu().numpy(), enc.per_level_scale, 16,
+                                             gridtype=enc.gridtype_id, scales=sc)
+        assert_close(mine_g, g0, 1e-3, 1e-5 * np.abs(g0).max(), "grad fp16 path vs fp64 oracle")
     else:
         assert_close(mine_g, ref_g, 1e-4, 1e-5 * np.abs(ref_g).max(), "grad fp32")
