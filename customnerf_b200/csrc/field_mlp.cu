@@ -1,0 +1,663 @@
+// field_mlp.cu -- the fused density + colour field network on the sm_100a tensor cores (tcgen05 / TMEM).
+//
+// Replaces the three tiny-cuda-nn FullyFusedMLP launches of nerf/network_grid.py:159-177 (trunk 32-64-64-64, density
+// head 64-64-1, colour head 91(96)-64-4) plus the frequency embedder (nerf/base.py:42-77), the gaussian density bias
+// (network_grid.py:150-156), trunc_exp (provider_utils.py:16-29) and the concat -- one kernel, no activation ever
+// round-trips HBM between layers.
+//
+// Mapping: one CTA = 128 threads works on tiles of 128 points (UMMA M = 128).  Every operand tile in shared memory is
+// "128 rows x 128 bytes, 128B-swizzled" (umma.cuh): activations are K-major A operands, weights K-major B operands
+// resident for the CTA's lifetime (44 KB).  Each layer is: one elected thread issues K/16 tcgen05.mma into the TMEM
+// accumulator and commits to an mbarrier; all 128 threads (thread == row == TMEM lane) read their accumulator row with
+// tcgen05.ld, apply the activation, round to fp16 and store the row as the next layer's A tile.
+//
+// Numerics contract (tiny-cuda-nn is un-vendored: parity unpinned): fp16 operands, fp32 accumulation, hidden
+// activations rounded to fp16, heads evaluated in fp32.  Bias-free; input lanes 91..95 of the colour head are fed 1.0.
+//
+// K order of the colour head inside the kernel: [fea(64) | view_en(27) | ones(5)] -- a column permutation of the
+// reference's cat([view_en, fea]) that the weight packer applies to the flat tcnn-layout parameter vector.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+// ---- packed weight images (bytes) ---------------------------------------------------------------------
+// forward: B operand rows = output neuron n, cols = input k
+constexpr uint32_t F_W1V = 0;        // 64 rows: cols 0..31 trunk layer 0 (W1), cols 32..63 colour layer 0 view part
+constexpr uint32_t F_W2 = 8192;      // trunk layer 1   [64 x 64]
+constexpr uint32_t F_W3 = 16384;     // trunk layer 2   [64 x 64]
+constexpr uint32_t F_WD1 = 24576;    // density layer 0 [64 x 64]
+constexpr uint32_t F_WR1F = 32768;   // colour layer 0, fea part [64 x 64]
+constexpr uint32_t F_WD2 = 40960;    // density layer 1 [16 x 64]
+constexpr uint32_t F_WR2 = 43008;    // colour layer 1  [16 x 64]
+constexpr uint32_t F_BYTES = 45056;
+// backward (dgrad): B operand rows = input k, cols = output neuron n (transposes)
+constexpr uint32_t B_W1T = 0;        // [32 x 64]
+constexpr uint32_t B_W2T = 4096;     // [64 x 64]
+constexpr uint32_t B_W3T = 12288;
+constexpr uint32_t B_WD1T = 20480;
+constexpr uint32_t B_WR1FT = 28672;
+constexpr uint32_t B_W16T = 36864;   // 64 rows: cols 0..15 = Wr2^T, cols 16..31 = Wd2^T
+constexpr uint32_t B_BYTES = 45056;
+
+// flat tcnn-layout parameter offsets (elements)
+constexpr uint32_t T_W1 = 0, T_W2 = 64 * 32, T_W3 = 64 * 32 + 64 * 64;      // trunk:   [64x32][64x64][64x64]
+constexpr uint32_t D_W1 = 0, D_W2 = 64 * 64;                                 // density: [64x64][16x64]
+constexpr uint32_t R_W1 = 0, R_W2 = 64 * 96;                                 // colour:  [64x96][16x64]
+
+__device__ __forceinline__ void put(uint8_t *img, uint32_t row, uint32_t col, float v) {
+    *reinterpret_cast<__half *>(img + umma::sw128_offset(row, col >> 3) + (col & 7u) * 2) = __float2half_rn(v);
+}
+
+__global__ void k_pack_field_weights(const float *__restrict__ trunk, const float *__restrict__ density,
+                                     const float *__restrict__ rgb, uint8_t *__restrict__ fwd, uint8_t *__restrict__ bwd) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < (F_BYTES + B_BYTES) / 4; i += nth) {
+        if (i < F_BYTES / 4) reinterpret_cast<uint32_t *>(fwd)[i] = 0;
+        else reinterpret_cast<uint32_t *>(bwd)[i - F_BYTES / 4] = 0;
+    }
+    // the zero fill and the scattered puts below touch disjoint bytes only if ordered: do the puts in a second kernel
+}
+
+__global__ void k_pack_field_weights2(const float *__restrict__ trunk, const float *__restrict__ density,
+                                      const float *__restrict__ rgb, uint8_t *__restrict__ fwd, uint8_t *__restrict__ bwd) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < 64 * 64; i += nth) {
+        const uint32_t n = i >> 6, k = i & 63;
+        if (k < 32) {
+            const float w1 = trunk[T_W1 + n * 32 + k];
+            put(fwd + F_W1V, n, k, w1);
+            put(bwd + B_W1T, k, n, w1);
+            // colour layer 0, view part: internal col 32+j <- reference input lane j (j < 27) or 91 + (j - 27) (ones)
+            const uint32_t src = (k < 27) ? k : 91 + (k - 27);
+            put(fwd + F_W1V, n, 32 + k, rgb[R_W1 + n * 96 + src]);
+        }
+        const float w2 = trunk[T_W2 + n * 64 + k], w3 = trunk[T_W3 + n * 64 + k];
+        const float wd1 = density[D_W1 + n * 64 + k], wr1f = rgb[R_W1 + n * 96 + 27 + k];
+        put(fwd + F_W2, n, k, w2);     put(bwd + B_W2T, k, n, w2);
+        put(fwd + F_W3, n, k, w3);     put(bwd + B_W3T, k, n, w3);
+        put(fwd + F_WD1, n, k, wd1);   put(bwd + B_WD1T, k, n, wd1);
+        put(fwd + F_WR1F, n, k, wr1f); put(bwd + B_WR1FT, k, n, wr1f);
+        if (n < 16) {
+            const float wd2 = density[D_W2 + n * 64 + k], wr2 = rgb[R_W2 + n * 64 + k];
+            put(fwd + F_WD2, n, k, wd2);
+            put(fwd + F_WR2, n, k, wr2);
+            put(bwd + B_W16T, k, n, wr2);
+            put(bwd + B_W16T, k, 16 + n, wd2);
+        }
+    }
+}
+
+// ---- shared-memory map of the forward kernel ------------------------------------------------------------
+constexpr uint32_t S_W = 0;                       // weights, F_BYTES
+constexpr uint32_t S_XV = F_BYTES;                // cols 0..31 x_en, cols 32..63 [view_en(27) | ones(5)]
+constexpr uint32_t S_H0 = S_XV + 16384;
+constexpr uint32_t S_H1 = S_H0 + 16384;
+constexpr uint32_t S_FEA = S_H1 + 16384;
+constexpr uint32_t S_FWD_BYTES = S_FEA + 16384;   // 110592
+constexpr uint32_t kTmemCols = 64;
+
+struct FieldFwdArgs {
+    const __half *x_en;     // [M, 32]
+    const float *xyz;       // [M, 3]  (gaussian density bias)
+    const float *dirs;      // [M, 3]
+    const uint8_t *wimg;    // forward weight image
+    float *sigma;           // [M]
+    float *sigma_arg;       // [M] or null: raw + gaussian (the argument of trunc_exp), saved for backward
+    __half *rgba;           // [M, 4]
+    __half *act;            // [5, M, 64] or null: h1, h2, fea, hd, hr saved for backward
+    uint32_t M;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// K-major A/B descriptor of K-step ks (16 halves) inside a 64-wide swizzled tile
+__device__ __forceinline__ uint64_t kdesc(uint32_t tile_addr, uint32_t ks) {
+    return umma::make_desc(tile_addr + ks * 32, 16, 1024, umma::kLayoutSW128);
+}
+
+// accumulator row (64 fp32) -> optional ReLU -> fp16 -> row of a swizzled tile (+ optional global copy)
+template <bool kRelu>
+__device__ __forceinline__ void epilogue_row64(uint32_t tmem_row_addr, uint8_t *tile, uint32_t row, __half *gdst) {
+    uint32_t a[32], b[32];
+    umma::tmem_ld32(tmem_row_addr, a);
+    umma::tmem_ld32(tmem_row_addr + 32, b);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (uint32_t c = 0; c < 8; c++) {
+        uint32_t *src = (c < 4) ? (a + c * 8) : (b + (c - 4) * 8);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            v[j] = __uint_as_float(src[j]);
+            if (kRelu) v[j] = fmaxf(v[j], 0.0f);
+        }
+        const uint4 pk = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        *reinterpret_cast<uint4 *>(tile + umma::sw128_offset(row, c)) = pk;
+        if (gdst) *reinterpret_cast<uint4 *>(gdst + c * 8) = pk;
+    }
+}
+
+__global__ void __launch_bounds__(128, 2)
+k_field_forward(const FieldFwdArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t fail_s;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t ntiles = (p.M + 127) / 128;
+
+    // one-time: weights -> smem, TMEM, barrier
+    for (uint32_t i = tid; i < F_BYTES / 16; i += 128)
+        reinterpret_cast<uint4 *>(smem + S_W)[i] = __ldg(reinterpret_cast<const uint4 *>(p.wimg) + i);
+    if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemCols);
+    if (tid == 0) {
+        umma::mbar_init(&bar, 1);
+        umma::mbar_fence_init();
+        fail_s = 0;
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t trow = tmem + ((warp * 32u) << 16);      // this warp's TMEM lane quarter
+    const uint32_t sW = umma::smem_u32(smem + S_W), sXV = umma::smem_u32(smem + S_XV), sH0 = umma::smem_u32(smem + S_H0),
+                   sH1 = umma::smem_u32(smem + S_H1), sFEA = umma::smem_u32(smem + S_FEA);
+    constexpr uint32_t ID64 = umma::make_idesc_f16(128, 64, 0, 0), ID16 = umma::make_idesc_f16(128, 16, 0, 0);
+    uint32_t phase = 0;
+
+    // issue `nk` K-steps of A(tile a, first K-step ak) x B(tile b, first K-step bk)
+    auto mma_run = [&](uint32_t a, uint32_t ak, uint32_t b, uint32_t bk, uint32_t nk, uint32_t idesc, bool first) {
+        for (uint32_t k = 0; k < nk; k++)
+            umma::mma_f16_ss(tmem, kdesc(a, ak + k), kdesc(b, bk + k), idesc, !(first && k == 0));
+    };
+    // completion of everything issued so far -> all threads; returns after the accumulator is readable
+    auto sync_mma = [&]() {
+        if (tid == 0) umma::commit(&bar);
+        if (!umma::mbar_wait(&bar, phase)) fail_s = 1;
+        phase ^= 1;
+        umma::fence_after_sync();
+    };
+    // publish the smem tile just written by the epilogue to the async proxy and order the TMEM loads before the next MMA
+    auto publish = [&]() {
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+    };
+
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t g = tile * 128 + tid;
+        const bool valid = g < p.M;
+        // ---- inputs: x_en row and the direction encoding -> XV tile
+        {
+            uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, x2 = x0, x3 = x0;
+            float d0 = 0, d1 = 0, d2 = 0;
+            if (valid) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.x_en + (size_t)g * 32);
+                x0 = __ldg(src); x1 = __ldg(src + 1); x2 = __ldg(src + 2); x3 = __ldg(src + 3);
+                d0 = p.dirs[(size_t)g * 3]; d1 = p.dirs[(size_t)g * 3 + 1]; d2 = p.dirs[(size_t)g * 3 + 2];
+            }
+            uint8_t *xv = smem + S_XV;
+            *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 0)) = x0;
+            *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 1)) = x1;
+            *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 2)) = x2;
+            *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 3)) = x3;
+            float e[32];
+            e[0] = d0; e[1] = d1; e[2] = d2;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float f = (float)(1 << k);
+                float s0, c0, s1, c1, s2, c2;
+                sincosf(d0 * f, &s0, &c0); sincosf(d1 * f, &s1, &c1); sincosf(d2 * f, &s2, &c2);
+                e[3 + 6 * k] = s0; e[4 + 6 * k] = s1; e[5 + 6 * k] = s2;
+                e[6 + 6 * k] = c0; e[7 + 6 * k] = c1; e[8 + 6 * k] = c2;
+            }
+#pragma unroll
+            for (int j = 27; j < 32; j++) e[j] = 1.0f;
+#pragma unroll
+            for (uint32_t c = 0; c < 4; c++) {
+                const uint4 pk = make_uint4(pack_h2(e[c * 8], e[c * 8 + 1]), pack_h2(e[c * 8 + 2], e[c * 8 + 3]),
+                                            pack_h2(e[c * 8 + 4], e[c * 8 + 5]), pack_h2(e[c * 8 + 6], e[c * 8 + 7]));
+                *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 4 + c)) = pk;
+            }
+        }
+        publish();
+        __half *act = (p.act && valid) ? p.act + (size_t)g * 64 : nullptr;
+        const size_t act_stride = (size_t)p.M * 64;
+
+        // ---- trunk layer 0: h1 = relu(x_en W1^T), K = 32
+        if (tid == 0) mma_run(sXV, 0, sW + F_W1V, 0, 2, ID64, true);
+        sync_mma();
+        epilogue_row64<true>(trow, smem + S_H0, tid, act);
+        publish();
+        // ---- trunk layer 1: h2 = relu(h1 W2^T)
+        if (tid == 0) mma_run(sH0, 0, sW + F_W2, 0, 4, ID64, true);
+        sync_mma();
+        epilogue_row64<true>(trow, smem + S_H1, tid, act ? act + act_stride : nullptr);
+        publish();
+        // ---- trunk layer 2: fea = h2 W3^T (no activation)
+        if (tid == 0) mma_run(sH1, 0, sW + F_W3, 0, 4, ID64, true);
+        sync_mma();
+        epilogue_row64<false>(trow, smem + S_FEA, tid, act ? act + 2 * act_stride : nullptr);
+        publish();
+        // ---- density layer 0: hd = relu(fea Wd1^T)
+        if (tid == 0) mma_run(sFEA, 0, sW + F_WD1, 0, 4, ID64, true);
+        sync_mma();
+        epilogue_row64<true>(trow, smem + S_H0, tid, act ? act + 3 * act_stride : nullptr);
+        publish();
+        // ---- density layer 1: raw = hd Wd2^T (N = 16, lane 0 is the output); sigma = exp(raw + 5 exp(-|x|^2 / 0.08))
+        if (tid == 0) mma_run(sH0, 0, sW + F_WD2, 0, 4, ID16, true);
+        sync_mma();
+        {
+            uint32_t r[16];
+            umma::tmem_ld16(trow, r);
+            umma::tmem_ld_wait();
+            if (valid) {
+                const float x = p.xyz[(size_t)g * 3], y = p.xyz[(size_t)g * 3 + 1], z = p.xyz[(size_t)g * 3 + 2];
+                const float gauss = 5.0f * expf(-(x * x + y * y + z * z) / (2 * 0.2f * 0.2f));
+                const float arg = __uint_as_float(r[0]) + gauss;
+                p.sigma[g] = expf(arg);
+                if (p.sigma_arg) p.sigma_arg[g] = arg;
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        // ---- colour layer 0: hr = relu(fea Wr1f^T + [view|1] Wr1v^T), K = 64 + 32
+        if (tid == 0) {
+            mma_run(sFEA, 0, sW + F_WR1F, 0, 4, ID64, true);
+            mma_run(sXV, 2, sW + F_W1V, 2, 2, ID64, false);
+        }
+        sync_mma();
+        epilogue_row64<true>(trow, smem + S_H1, tid, act ? act + 4 * act_stride : nullptr);
+        publish();
+        // ---- colour layer 1: rgba = sigmoid(hr Wr2^T) (N = 16, lanes 0..3)
+        if (tid == 0) mma_run(sH1, 0, sW + F_WR2, 0, 4, ID16, true);
+        sync_mma();
+        {
+            uint32_t r[16];
+            umma::tmem_ld16(trow, r);
+            umma::tmem_ld_wait();
+            if (valid) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = 1.0f / (1.0f + expf(-__uint_as_float(r[j])));
+                *reinterpret_cast<uint2 *>(p.rgba + (size_t)g * 4) = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+    }
+
+    if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+    if (tid == 0 && fail_s) p.sigma[0] = __int_as_float(0x7fc00000);   // make a barrier time-out visible (NaN)
+}
+
+
+// =====================================================================================================
+// backward: dgrad chain + weight gradients, one kernel
+// =====================================================================================================
+// shared-memory map (bytes).  The four gradient tiles are consecutive so that an MN-major M = 128 A operand whose
+// first 64-row block is one tile finds its second block (LBO = 16384) in the next tile.
+constexpr uint32_t SB_W = 0;                        // transposed weights, B_BYTES
+constexpr uint32_t SB_T16 = B_BYTES;                // cols 0..15 dOr (colour head pre-sigmoid grads), 16..31 dOd
+constexpr uint32_t SB_GA = SB_T16 + 16384;          // dHR, later dH2
+constexpr uint32_t SB_GB = SB_GA + 16384;           // dHD, later dH1
+constexpr uint32_t SB_GC = SB_GB + 16384;           // dFEA
+constexpr uint32_t SB_XV = SB_GC + 16384;           // x_en | view
+constexpr uint32_t SB_H1 = SB_XV + 16384;
+constexpr uint32_t SB_H2 = SB_H1 + 16384;
+constexpr uint32_t SB_FEA = SB_H2 + 16384;
+constexpr uint32_t SB_HD = SB_FEA + 16384;
+constexpr uint32_t SB_HR = SB_HD + 16384;
+constexpr uint32_t S_BWD_BYTES = SB_HR + 16384;     // 45056 + 10 * 16384 = 208896
+// TMEM columns
+constexpr uint32_t C_DG = 0, C_W1 = 64, C_W2 = 96, C_W3 = 160, C_PAIR = 224, C_R1V = 288, C_D2 = 320, C_R2 = 384;
+constexpr uint32_t kTmemColsBwd = 512;
+
+struct FieldBwdArgs {
+    const float *d_sigma;     // [M]
+    const float *d_rgba;      // [M, 4]
+    const float *sigma_arg;   // [M]
+    const __half *rgba;       // [M, 4]
+    const __half *x_en;       // [M, 32]
+    const float *dirs;        // [M, 3]
+    const __half *act;        // [5, M, 64]
+    const uint8_t *wimg;      // backward weight image
+    __half *d_x_en;           // [M, 32]
+    float *g_trunk, *g_density, *g_rgb;   // flat fp32 parameter gradients, ACCUMULATED INTO
+    uint32_t M;
+};
+
+// MN-major descriptor of K-step ks (16 rows = 2 swizzle atoms) starting at column `col0` (multiple of 8 halves)
+__device__ __forceinline__ uint64_t mndesc(uint32_t tile_addr, uint32_t ks, uint32_t col0) {
+    return umma::make_desc(tile_addr + ks * 2048 + col0 * 2, 16384, 1024, umma::kLayoutSW128);
+}
+
+// dgrad epilogue: DG row (64 fp32) * relu'(activation row) -> fp16 -> gradient tile
+template <bool kMask>
+__device__ __forceinline__ void bwd_epilogue_row64(uint32_t tmem_row_addr, const uint8_t *act_tile, uint8_t *dst_tile,
+                                                   uint32_t row) {
+#pragma unroll
+    for (uint32_t h = 0; h < 2; h++) {
+        uint32_t a[32];
+        umma::tmem_ld32(tmem_row_addr + h * 32, a);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = __uint_as_float(a[c * 8 + j]);
+            if (kMask) {
+                const uint4 m = *reinterpret_cast<const uint4 *>(act_tile + umma::sw128_offset(row, h * 4 + c));
+                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    // fp16 activation after ReLU is > 0 iff its bit pattern is non-zero and not negative zero
+                    if ((mw[j] & 0x7fffu) == 0) v[2 * j] = 0.0f;
+                    if ((mw[j] & 0x7fff0000u) == 0) v[2 * j + 1] = 0.0f;
+                }
+            }
+            const uint4 pk = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+            *reinterpret_cast<uint4 *>(dst_tile + umma::sw128_offset(row, h * 4 + c)) = pk;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, 1)
+k_field_backward(const FieldBwdArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t ntiles = (p.M + 127) / 128;
+
+    for (uint32_t i = tid; i < B_BYTES / 16; i += 128)
+        reinterpret_cast<uint4 *>(smem + SB_W)[i] = __ldg(reinterpret_cast<const uint4 *>(p.wimg) + i);
+    // the T16 tile is only ever written in its first 4 chunks per row: clear the rest once
+    for (uint32_t i = tid; i < 16384 / 16; i += 128) reinterpret_cast<uint4 *>(smem + SB_T16)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemColsBwd);
+    if (tid == 0) {
+        umma::mbar_init(&bar, 1);
+        umma::mbar_fence_init();
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t trow = tmem + ((warp * 32u) << 16);
+    const uint32_t base = umma::smem_u32(smem);
+    const uint32_t sW = base + SB_W, sT16 = base + SB_T16, sGA = base + SB_GA, sGB = base + SB_GB, sGC = base + SB_GC,
+                   sXV = base + SB_XV, sH1 = base + SB_H1, sH2 = base + SB_H2, sFEA = base + SB_FEA, sHD = base + SB_HD,
+                   sHR = base + SB_HR;
+    constexpr uint32_t ID64 = umma::make_idesc_f16(128, 64, 0, 0), ID32 = umma::make_idesc_f16(128, 32, 0, 0);
+    constexpr uint32_t WG64 = umma::make_idesc_f16(128, 64, 1, 1), WG32 = umma::make_idesc_f16(128, 32, 1, 1);
+    uint32_t phase = 0;
+    bool first_tile = true;
+
+    auto dgrad = [&](uint32_t a, uint32_t ak, uint32_t b, uint32_t bk, uint32_t nk, uint32_t idesc, bool first) {
+        for (uint32_t k = 0; k < nk; k++)
+            umma::mma_f16_ss(tmem + C_DG, kdesc(a, ak + k), kdesc(b, bk + k), idesc, !(first && k == 0));
+    };
+    // D[cols] (+)= A_tile^T (M = 128: this tile and the next) x B_tile[:, col0 : col0 + N], contraction over the 128 points
+    auto wgrad = [&](uint32_t dcol, uint32_t a, uint32_t b, uint32_t bcol0, uint32_t idesc) {
+        for (uint32_t k = 0; k < 8; k++)
+            umma::mma_f16_ss(tmem + dcol, mndesc(a, k, 0), mndesc(b, k, bcol0), idesc, !(first_tile && k == 0));
+    };
+    auto sync_mma = [&]() {
+        if (tid == 0) umma::commit(&bar);
+        umma::mbar_wait(&bar, phase);
+        phase ^= 1;
+        umma::fence_after_sync();
+    };
+    auto publish = [&]() {
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+    };
+
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t g = tile * 128 + tid;
+        const bool valid = g < p.M;
+        const size_t act_stride = (size_t)p.M * 64;
+        // ---- load this point's rows: x_en | view, h1, h2, fea, hd, hr; build the head gradients (T16)
+        {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            uint8_t *tiles[5] = {smem + SB_H1, smem + SB_H2, smem + SB_FEA, smem + SB_HD, smem + SB_HR};
+#pragma unroll
+            for (int t = 0; t < 5; t++) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.act + t * act_stride + (size_t)g * 64);
+#pragma unroll
+                for (uint32_t c = 0; c < 8; c++)
+                    *reinterpret_cast<uint4 *>(tiles[t] + umma::sw128_offset(tid, c)) = valid ? __ldg(src + c) : z;
+            }
+            const uint4 *xs = reinterpret_cast<const uint4 *>(p.x_en + (size_t)g * 32);
+#pragma unroll
+            for (uint32_t c = 0; c < 4; c++)
+                *reinterpret_cast<uint4 *>(smem + SB_XV + umma::sw128_offset(tid, c)) = valid ? __ldg(xs + c) : z;
+            float d0 = 0, d1 = 0, d2 = 0;
+            if (valid) { d0 = p.dirs[(size_t)g * 3]; d1 = p.dirs[(size_t)g * 3 + 1]; d2 = p.dirs[(size_t)g * 3 + 2]; }
+            float e[32];
+            e[0] = d0; e[1] = d1; e[2] = d2;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float f = (float)(1 << k);
+                float s0, c0, s1, c1, s2, c2;
+                sincosf(d0 * f, &s0, &c0); sincosf(d1 * f, &s1, &c1); sincosf(d2 * f, &s2, &c2);
+                e[3 + 6 * k] = s0; e[4 + 6 * k] = s1; e[5 + 6 * k] = s2;
+                e[6 + 6 * k] = c0; e[7 + 6 * k] = c1; e[8 + 6 * k] = c2;
+            }
+#pragma unroll
+            for (int j = 27; j < 32; j++) e[j] = valid ? 1.0f : 0.0f;
+#pragma unroll
+            for (uint32_t c = 0; c < 4; c++) {
+                const uint4 pk = make_uint4(pack_h2(e[c * 8], e[c * 8 + 1]), pack_h2(e[c * 8 + 2], e[c * 8 + 3]),
+                                            pack_h2(e[c * 8 + 4], e[c * 8 + 5]), pack_h2(e[c * 8 + 6], e[c * 8 + 7]));
+                *reinterpret_cast<uint4 *>(smem + SB_XV + umma::sw128_offset(tid, 4 + c)) = valid ? pk : z;
+            }
+            // head gradients: colour = g * y (1 - y) (sigmoid), density = g * exp(clamp(arg, -15, 15)) (trunc_exp)
+            float go[4] = {0, 0, 0, 0}, gd = 0;
+            if (valid) {
+                const uint2 yy = *reinterpret_cast<const uint2 *>(p.rgba + (size_t)g * 4);
+                const float2 y01 = __half22float2(*reinterpret_cast<const __half2 *>(&yy.x));
+                const float2 y23 = __half22float2(*reinterpret_cast<const __half2 *>(&yy.y));
+                const float4 gr = *reinterpret_cast<const float4 *>(p.d_rgba + (size_t)g * 4);
+                go[0] = gr.x * y01.x * (1 - y01.x); go[1] = gr.y * y01.y * (1 - y01.y);
+                go[2] = gr.z * y23.x * (1 - y23.x); go[3] = gr.w * y23.y * (1 - y23.y);
+                gd = p.d_sigma[g] * expf(fminf(fmaxf(p.sigma_arg[g], -15.0f), 15.0f));
+            }
+            uint8_t *t16 = smem + SB_T16;
+            *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(tid, 0)) = make_uint4(pack_h2(go[0], go[1]), pack_h2(go[2], go[3]), 0, 0);
+            *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(tid, 1)) = z;
+            *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(tid, 2)) = make_uint4(pack_h2(gd, 0.0f), 0, 0, 0);
+            *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(tid, 3)) = z;
+        }
+        publish();
+
+        // ---- dHR = (dOr Wr2) * [hr > 0]
+        if (tid == 0) dgrad(sT16, 0, sW + B_W16T, 0, 1, ID64, true);
+        sync_mma();
+        bwd_epilogue_row64<true>(trow + C_DG, smem + SB_HR, smem + SB_GA, tid);
+        publish();
+        // ---- dHD = (dOd Wd2) * [hd > 0];   wgrad of the two heads (A = T16^T)
+        if (tid == 0) {
+            dgrad(sT16, 1, sW + B_W16T, 1, 1, ID64, true);
+            wgrad(C_R2, sT16, sHR, 0, WG64);
+            wgrad(C_D2, sT16, sHD, 0, WG64);
+        }
+        sync_mma();
+        bwd_epilogue_row64<true>(trow + C_DG, smem + SB_HD, smem + SB_GB, tid);
+        publish();
+        // ---- dFEA = dHR Wr1f + dHD Wd1;   wgrad Wr1f | Wd1 (A = [dHR | dHD]^T, B = fea), Wr1v (A = dHR^T, B = view)
+        if (tid == 0) {
+            dgrad(sGA, 0, sW + B_WR1FT, 0, 4, ID64, true);
+            dgrad(sGB, 0, sW + B_WD1T, 0, 4, ID64, false);
+            wgrad(C_PAIR, sGA, sFEA, 0, WG64);
+            wgrad(C_R1V, sGA, sXV, 32, WG32);
+        }
+        sync_mma();
+        bwd_epilogue_row64<false>(trow + C_DG, nullptr, smem + SB_GC, tid);
+        publish();
+        // ---- dH2 = (dFEA W3) * [h2 > 0];   wgrad W3 (A = dFEA^T, B = h2)
+        if (tid == 0) {
+            dgrad(sGC, 0, sW + B_W3T, 0, 4, ID64, true);
+            wgrad(C_W3, sGC, sH2, 0, WG64);
+        }
+        sync_mma();
+        bwd_epilogue_row64<true>(trow + C_DG, smem + SB_H2, smem + SB_GA, tid);
+        publish();
+        // ---- dH1 = (dH2 W2) * [h1 > 0];   wgrad W2 (A = dH2^T, B = h1)
+        if (tid == 0) {
+            dgrad(sGA, 0, sW + B_W2T, 0, 4, ID64, true);
+            wgrad(C_W2, sGA, sH1, 0, WG64);
+        }
+        sync_mma();
+        bwd_epilogue_row64<true>(trow + C_DG, smem + SB_H1, smem + SB_GB, tid);
+        publish();
+        // ---- dX = dH1 W1 (N = 32) -> global;   wgrad W1 (A = dH1^T, B = x_en)
+        if (tid == 0) {
+            dgrad(sGB, 0, sW + B_W1T, 0, 4, ID32, true);
+            wgrad(C_W1, sGB, sXV, 0, WG32);
+        }
+        sync_mma();                                   // also drains every wgrad MMA that still reads this tile's smem
+        {
+            uint32_t a[32];
+            umma::tmem_ld32(trow + C_DG, a);
+            umma::tmem_ld_wait();
+            if (valid) {
+                uint4 *dst = reinterpret_cast<uint4 *>(p.d_x_en + (size_t)g * 32);
+#pragma unroll
+                for (uint32_t c = 0; c < 4; c++)
+                    dst[c] = make_uint4(pack_h2(__uint_as_float(a[c * 8]), __uint_as_float(a[c * 8 + 1])),
+                                        pack_h2(__uint_as_float(a[c * 8 + 2]), __uint_as_float(a[c * 8 + 3])),
+                                        pack_h2(__uint_as_float(a[c * 8 + 4]), __uint_as_float(a[c * 8 + 5])),
+                                        pack_h2(__uint_as_float(a[c * 8 + 6]), __uint_as_float(a[c * 8 + 7])));
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        first_tile = false;
+    }
+
+    // ---- flush the weight-gradient accumulators: thread == TMEM lane == output neuron (row of dW)
+    if (!first_tile) {
+        const uint32_t n = tid;
+        auto flush = [&](uint32_t col, uint32_t ncols, float *dst, uint32_t ld, uint32_t coff, bool on) {
+            for (uint32_t c0 = 0; c0 < ncols; c0 += 16) {
+                uint32_t r[16];
+                umma::tmem_ld16(trow + col + c0, r);
+                umma::tmem_ld_wait();
+                if (on) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) atomicAdd(dst + (size_t)ld * 0 + coff + c0 + j, __uint_as_float(r[j]));
+                }
+            }
+        };
+        // trunk
+        flush(C_W1, 32, p.g_trunk + T_W1 + n * 32, 0, 0, n < 64);
+        flush(C_W2, 64, p.g_trunk + T_W2 + n * 64, 0, 0, n < 64);
+        flush(C_W3, 64, p.g_trunk + T_W3 + n * 64, 0, 0, n < 64);
+        // pair: rows 0..63 = colour layer 0 (fea columns 27..90), rows 64..127 = density layer 0
+        flush(C_PAIR, 64, n < 64 ? p.g_rgb + R_W1 + n * 96 + 27 : p.g_density + D_W1 + (n - 64) * 64, 0, 0, true);
+        // colour layer 0, view columns: internal col j -> lane j (j < 27) or 91 + (j - 27)
+        for (uint32_t c0 = 0; c0 < 32; c0 += 16) {
+            uint32_t r[16];
+            umma::tmem_ld16(trow + C_R1V + c0, r);
+            umma::tmem_ld_wait();
+            if (n < 64) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint32_t col = c0 + j, src = (col < 27) ? col : 91 + (col - 27);
+                    atomicAdd(p.g_rgb + R_W1 + n * 96 + src, __uint_as_float(r[j]));
+                }
+            }
+        }
+        // heads: A = T16, rows 0..15 = colour outputs, rows 16..31 = density outputs
+        flush(C_R2, 64, p.g_rgb + R_W2 + n * 64, 0, 0, n < 16);
+        flush(C_D2, 64, p.g_density + D_W2 + (n >= 16 ? n - 16 : 0) * 64, 0, 0, n >= 16 && n < 32);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, kTmemColsBwd);
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t nb200_field_weight_image_bytes(void) { return F_BYTES; }
+
+int nb200_field_pack_weights(const float *trunk, const float *density, const float *rgb, void *fwd_img, void *bwd_img,
+                             void *stream) {
+    if (!trunk || !density || !rgb || !fwd_img || !bwd_img) return NB200_E_BAD_ARG;
+    cudaStream_t st = nb_stream(stream);
+    k_pack_field_weights<<<32, 256, 0, st>>>(trunk, density, rgb, (uint8_t *)fwd_img, (uint8_t *)bwd_img);
+    k_pack_field_weights2<<<16, 256, 0, st>>>(trunk, density, rgb, (uint8_t *)fwd_img, (uint8_t *)bwd_img);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, const void *fwd_img, float *sigma,
+                        float *sigma_arg, void *rgba, void *act, uint32_t M, void *stream) {
+    if (M == 0) return 0;
+    if (!x_en || !xyz || !dirs || !fwd_img || !sigma || !rgba) return NB200_E_BAD_ARG;
+    static int configured = 0;
+    const int smem = (int)S_FWD_BYTES + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_field_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = 1;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    FieldFwdArgs a;
+    a.x_en = (const __half *)x_en; a.xyz = xyz; a.dirs = dirs; a.wimg = (const uint8_t *)fwd_img;
+    a.sigma = sigma; a.sigma_arg = sigma_arg; a.rgba = (__half *)rgba; a.act = (__half *)act; a.M = M;
+    const uint32_t ntiles = (M + 127) / 128;
+    const uint32_t grid = ntiles < (uint32_t)(2 * sms) ? ntiles : (uint32_t)(2 * sms);
+    k_field_forward<<<grid, 128, smem, nb_stream(stream)>>>(a);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,
+                         const void *x_en, const float *dirs, const void *act, const void *bwd_img, void *d_x_en,
+                         float *g_trunk, float *g_density, float *g_rgb, uint32_t M, void *stream) {
+    if (M == 0) return 0;
+    if (!d_sigma || !d_rgba || !sigma_arg || !rgba || !x_en || !dirs || !act || !bwd_img || !d_x_en || !g_trunk ||
+        !g_density || !g_rgb)
+        return NB200_E_BAD_ARG;
+    static int configured = 0;
+    const int smem = (int)S_BWD_BYTES + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_field_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = 1;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    FieldBwdArgs a;
+    a.d_sigma = d_sigma; a.d_rgba = d_rgba; a.sigma_arg = sigma_arg; a.rgba = (const __half *)rgba;
+    a.x_en = (const __half *)x_en; a.dirs = dirs; a.act = (const __half *)act; a.wimg = (const uint8_t *)bwd_img;
+    a.d_x_en = (__half *)d_x_en; a.g_trunk = g_trunk; a.g_density = g_density; a.g_rgb = g_rgb; a.M = M;
+    const uint32_t ntiles = (M + 127) / 128;
+    const uint32_t grid = ntiles < (uint32_t)sms ? ntiles : (uint32_t)sms;
+    k_field_backward<<<grid, 128, smem, nb_stream(stream)>>>(a);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

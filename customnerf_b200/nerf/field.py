@@ -11,6 +11,7 @@ from torch.amp import custom_bwd, custom_fwd
 
 from ..gridencoder import GridEncoder
 from .mlp import Network
+from .fused_field import fused_field, _PackedWeights
 from .rendering import NeRFRenderer
 
 
@@ -73,6 +74,10 @@ class NeRFNetwork(NeRFRenderer):
         n_out = 3 + (1 if getattr(opt, 'train_conf', 0) else 0)
         self.rgb_network = Network(self.input_ch_views + 64, n_out, _mlp_cfg("Sigmoid", 1), seed=1339)
         self.bg_net = None
+        # one fused tcgen05 kernel for trunk + heads when the shapes are the reference's (32 -> 64 ... -> 1 | 3(+1));
+        # the per-layer library path (mlp.Network.forward) stays available through use_fused_field = False
+        self.use_fused_field = self.pos_en_dim == 32
+        self._packed = _PackedWeights()
 
     def background(self, d):
         return torch.zeros(d.size(), dtype=d.dtype, device=d.device)
@@ -81,7 +86,16 @@ class NeRFNetwork(NeRFRenderer):
         """density blob at the scene centre (network_grid.py:150-156)"""
         return 5 * torch.exp(-(x ** 2).sum(-1) / (2 * 0.2 ** 2))
 
+    def _fused(self, x, d):
+        x_en = self.pos_en(x, bound=self.opt.bound)
+        sigma, rgba = fused_field(x_en, x, d, self.network.params, self.density_network.params,
+                                  self.rgb_network.params, self._packed)
+        return sigma, rgba[:, :self.rgb_network.n_output_dims]
+
     def forward(self, x, d, l=None, ratio=1, shading='albedo'):
+        if self.use_fused_field:
+            sigma, radiances = self._fused(x, d)
+            return sigma, radiances, None
         x_en = self.pos_en(x, bound=self.opt.bound)
         fea = self.network(x_en)
         sigma = self.density_network(fea)
@@ -91,6 +105,9 @@ class NeRFNetwork(NeRFRenderer):
         return sigma, radiances, None
 
     def density(self, x):
+        if self.use_fused_field:
+            sigma, _ = self._fused(x, torch.zeros_like(x))
+            return {'sigma': sigma}
         x_en = self.pos_en(x, bound=self.opt.bound)
         fea = self.network(x_en)
         sigma = self.density_network(fea)

@@ -1,0 +1,78 @@
+"""Fused field network (trunk + density head + colour head + embedder + trunc_exp) on the tcgen05 kernels of
+csrc/field_mlp.cu, as one autograd node.  Same math and the same flat tcnn-layout parameters as the three
+``Network`` modules of ``NeRFNetwork`` (nerf/network_grid.py:98-139, :159-177)."""
+import torch
+from torch.autograd import Function
+
+from .. import _lib as L
+
+
+def _image_bytes():
+    return int(L.lib().nb200_field_weight_image_bytes())
+
+
+class _PackedWeights:
+    """fp16 pre-swizzled operand images of the three parameter vectors, re-packed only when a vector changed."""
+
+    def __init__(self):
+        self.key = None
+        self.fwd = self.bwd = None
+
+    def get(self, trunk, density, rgb):
+        key = (trunk.data_ptr(), trunk._version, density.data_ptr(), density._version, rgb.data_ptr(), rgb._version)
+        if key != self.key or self.fwd is None or self.fwd.device != trunk.device:
+            n = _image_bytes()
+            if self.fwd is None or self.fwd.device != trunk.device:
+                self.fwd = torch.empty(n, dtype=torch.uint8, device=trunk.device)
+                self.bwd = torch.empty(n, dtype=torch.uint8, device=trunk.device)
+            L.check(L.lib().nb200_field_pack_weights(L.ptr(trunk.detach()), L.ptr(density.detach()), L.ptr(rgb.detach()),
+                                                     L.ptr(self.fwd), L.ptr(self.bwd), L.stream()), "field_pack_weights")
+            self.key = key
+        return self.fwd, self.bwd
+
+
+class _FusedField(Function):
+    @staticmethod
+    def forward(ctx, x_en, xyz, dirs, trunk, density, rgb, packed, save):
+        M = x_en.shape[0]
+        dev = x_en.device
+        x_en = x_en.half().contiguous()
+        xyz = xyz.float().contiguous()
+        dirs = dirs.float().contiguous()
+        fwd_img, bwd_img = packed.get(trunk, density, rgb)
+        sigma = torch.empty(M, dtype=torch.float32, device=dev)
+        rgba = torch.empty(M, 4, dtype=torch.half, device=dev)
+        sigma_arg = torch.empty(M, dtype=torch.float32, device=dev) if save else None
+        act = torch.empty(5, M, 64, dtype=torch.half, device=dev) if save else None
+        L.check(L.lib().nb200_field_forward(L.ptr(x_en), L.ptr(xyz), L.ptr(dirs), L.ptr(fwd_img), L.ptr(sigma),
+                                            L.ptr(sigma_arg), L.ptr(rgba), L.ptr(act), L.u32(M), L.stream()),
+                "field_forward")
+        if save:
+            ctx.save_for_backward(x_en, dirs, sigma_arg, rgba, act, bwd_img)
+            ctx.shapes = (trunk.numel(), density.numel(), rgb.numel())
+        return sigma, rgba
+
+    @staticmethod
+    def backward(ctx, d_sigma, d_rgba):
+        x_en, dirs, sigma_arg, rgba, act, bwd_img = ctx.saved_tensors
+        M = x_en.shape[0]
+        dev = x_en.device
+        d_sigma = (torch.zeros(M, device=dev) if d_sigma is None else d_sigma.float()).contiguous()
+        d_rgba = (torch.zeros(M, 4, device=dev) if d_rgba is None else d_rgba.float()).contiguous()
+        nt, nd, nr = ctx.shapes
+        g_trunk = torch.zeros(nt, dtype=torch.float32, device=dev)
+        g_density = torch.zeros(nd, dtype=torch.float32, device=dev)
+        g_rgb = torch.zeros(nr, dtype=torch.float32, device=dev)
+        d_x_en = torch.empty(M, 32, dtype=torch.half, device=dev)
+        L.check(L.lib().nb200_field_backward(L.ptr(d_sigma), L.ptr(d_rgba), L.ptr(sigma_arg), L.ptr(rgba), L.ptr(x_en),
+                                             L.ptr(dirs), L.ptr(act), L.ptr(bwd_img), L.ptr(d_x_en), L.ptr(g_trunk),
+                                             L.ptr(g_density), L.ptr(g_rgb), L.u32(M), L.stream()), "field_backward")
+        return d_x_en, None, None, g_trunk, g_density, g_rgb, None, None
+
+
+def fused_field(x_en, xyz, dirs, trunk, density, rgb, packed):
+    """-> (sigma f32 [M], rgba f16 [M, 4]).  x_en: grid encoding [M, 32]."""
+    if not x_en.is_cuda:
+        raise RuntimeError("customnerf_b200 fused field network runs on CUDA only (no CPU fallback)")
+    save = torch.is_grad_enabled() and any(t.requires_grad for t in (x_en, trunk, density, rgb))
+    return _FusedField.apply(x_en, xyz, dirs, trunk, density, rgb, packed, save)

@@ -146,6 +146,29 @@ int nb200_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int3
                          float *image, void *stream);
 
 /* ============================================================================================
+ * field network: replaces the three tinycudann.Network (FullyFusedMLP) modules of nerf/network_grid.py:98-139 and the
+ * torch glue of NeRFNetwork.forward / density (:159-193): trunk 32-64-64-64 -> density head 64-64-1 -> trunc_exp with
+ * the gaussian bias; [view_en(27) | fea(64)] -> colour head 96-64-(3+1) sigmoid.  One fused tcgen05 kernel per
+ * direction.  Parameters are the three flat fp32 tcnn-layout vectors (row-major [out_padded, in_padded] per layer).
+ * ========================================================================================== */
+uint32_t nb200_field_weight_image_bytes(void);
+/* fp32 flat params -> fp16 pre-swizzled operand images (forward and transposed/backward), each
+ * nb200_field_weight_image_bytes() long and 16-byte aligned.  Run once per optimiser step. */
+int nb200_field_pack_weights(const float *trunk, const float *density, const float *rgb, void *fwd_img, void *bwd_img,
+                             void *stream);
+/* x_en f16 [M,32] (grid encoding), xyz f32 [M,3], dirs f32 [M,3] -> sigma f32 [M], rgba f16 [M,4].
+ * Optional (training): sigma_arg f32 [M] (argument of trunc_exp) and act f16 [5,M,64] (h1, h2, fea, hd, hr). */
+int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, const void *fwd_img, float *sigma,
+                        float *sigma_arg, void *rgba, void *act, uint32_t M, void *stream);
+
+/* Backward of nb200_field_forward.  d_sigma f32 [M], d_rgba f32 [M,4] are the upstream gradients; sigma_arg, rgba, act
+ * are what the forward saved.  Writes d_x_en f16 [M,32] (gradient of the grid encoding, input of
+ * nb200_grid_encode_backward) and ACCUMULATES the three flat fp32 parameter gradients (tcnn layout). */
+int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,
+                         const void *x_en, const float *dirs, const void *act, const void *bwd_img, void *d_x_en,
+                         float *g_trunk, float *g_density, float *g_rgb, uint32_t M, void *stream);
+
+/* ============================================================================================
  * tensor-core path self test (no reference counterpart): one-CTA tcgen05 GEMM D[128,N] = A[128,K] * B[N,K]^T with
  * fp16 operands / fp32 accumulation, used by the tests to pin the UMMA descriptor conventions the fused MLP
  * kernels rely on.  a_mn / b_mn select MN-major operand storage (A given as [K][128], B as [K][N]).
