@@ -217,8 +217,31 @@ def op_breakdown(model, rays_o, rays_d, reps=20):
     out["composite_train_backward"] = timeit(lambda: L.check(lib.nb200_composite_rays_train_backward(
         L.ptr(gws), L.ptr(gim), L.ptr(sig), L.ptr(rgb), L.ptr(deltas), L.ptr(rays), L.ptr(ws), L.ptr(im), L.u32(M), L.u32(N),
         L.f32(1e-4), L.ptr(gs), L.ptr(gc), L.stream()), "cb"))
+    # fused tcgen05 field network (trunk + heads), forward with activations saved, and backward
+    from customnerf_b200.nerf.fused_field import _image_bytes
+    nb = _image_bytes()
+    fimg = torch.empty(nb, dtype=torch.uint8, device=dev); bimg = torch.empty(nb, dtype=torch.uint8, device=dev)
+    tp, dp_, rp = model.network.params.detach(), model.density_network.params.detach(), model.rgb_network.params.detach()
+    L.check(lib.nb200_field_pack_weights(L.ptr(tp), L.ptr(dp_), L.ptr(rp), L.ptr(fimg), L.ptr(bimg), L.stream()), "pack")
+    sigma = torch.empty(M, device=dev); sarg = torch.empty(M, device=dev)
+    rgba = torch.empty(M, 4, dtype=torch.half, device=dev); act = torch.empty(5, M, 64, dtype=torch.half, device=dev)
+    enc_fwd()
+    out["field_forward_tcgen05"] = timeit(lambda: L.check(lib.nb200_field_forward(
+        L.ptr(feat), L.ptr(xyzs), L.ptr(dirs), L.ptr(fimg), L.ptr(sigma), L.ptr(sarg), L.ptr(rgba), L.ptr(act), L.u32(M),
+        L.stream()), "ff"))
+    out["field_forward_tcgen05_nosave"] = timeit(lambda: L.check(lib.nb200_field_forward(
+        L.ptr(feat), L.ptr(xyzs), L.ptr(dirs), L.ptr(fimg), L.ptr(sigma), L.ptr(None), L.ptr(rgba), L.ptr(None), L.u32(M),
+        L.stream()), "ff"))
+    dsig = torch.randn(M, device=dev) * 0.01; drgba = torch.randn(M, 4, device=dev)
+    dx = torch.empty(M, 32, dtype=torch.half, device=dev)
+    gt, gd_, gr = torch.zeros_like(tp), torch.zeros_like(dp_), torch.zeros_like(rp)
+    out["field_backward_tcgen05"] = timeit(lambda: L.check(lib.nb200_field_backward(
+        L.ptr(dsig), L.ptr(drgba), L.ptr(sarg), L.ptr(rgba), L.ptr(feat), L.ptr(dirs), L.ptr(act), L.ptr(bimg), L.ptr(dx),
+        L.ptr(gt), L.ptr(gd_), L.ptr(gr), L.u32(M), L.stream()), "fb"))
+    model.use_fused_field = False
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
-        out["field_mlp_forward(torch/cuBLAS)"] = timeit(lambda: model(xyzs, dirs))
+        out["field_forward(torch/cuBLAS per-layer path)"] = timeit(lambda: model(xyzs, dirs))
+    model.use_fused_field = True
     samples = int(counter[0])
     return out, samples, M
 
@@ -231,6 +254,10 @@ def roofline_from(breakdown, samples, peaks):
         "composite_train_forward": 24.0,
         "composite_train_backward": 40.0,
         "march_write": 32.0,
+        # field network: HBM bytes per point (x_en 64 + xyz/dirs 24 + outputs 12 + saved activations 644)
+        "field_forward_tcgen05": 744.0,
+        # reads activations 640 + x_en 64 + dirs 12 + grads/outputs 36, writes d_x_en 64
+        "field_backward_tcgen05": 816.0,
     }
     mine = {k: v for k, v in breakdown.items() if k in per_unit}
     top = max(mine, key=mine.get)
