@@ -347,7 +347,7 @@ def run_b200(args):
                         "h2d_bytes_per_step": int(3 * n_rays * 3 * 4), "d2h_bytes_per_step": 4,
                         "ms_per_step": sec_e2e / args.steps * 1e3},
                 "gpu_launches": int(launches), "clocks": clk}
-        if world == 1:
+        if world == 1 and not args.no_breakdown:
             bd, samples, M = op_breakdown(model, o_d, d_d)
             line["kernel_us"] = {k: round(v, 2) for k, v in bd.items()}
             line["samples_per_step"] = samples
@@ -365,6 +365,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-breakdown", action="store_true",
+                    help="skip the per-kernel breakdown and the CPU baseline (profiling runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -10,7 +10,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnerf_b200.so")
 
-F32, F16 = 0, 1
+F32, F16, F32_AS_F16 = 0, 1, 2
 LAYOUT_LBC, LAYOUT_BLC = 0, 1
 
 _lib = None

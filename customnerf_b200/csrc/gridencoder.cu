@@ -327,10 +327,15 @@ template <> struct Vec2<__half> { using type = __half2; };
 __device__ __forceinline__ float2 ge_ld2(const float *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
 __device__ __forceinline__ float2 ge_ld2(const __half *p) { return __half22float2(__ldg(reinterpret_cast<const __half2 *>(p))); }
 
-// one thread per point; outputs [B, L*2]
-template <typename T>
+// fp32 master table read as if it had been cast to fp16 first (the autocast path of grid.py:45-46 without the copy)
+__device__ __forceinline__ float2 ge_ld2_round_half(const float *p) {
+    return __half22float2(__float22half2_rn(__ldg(reinterpret_cast<const float2 *>(p))));
+}
+
+// one thread per point; outputs [B, L*2].  TE = table storage type, T = value / output type.
+template <typename TE, typename T>
 __global__ void __launch_bounds__(256)
-k_grid_fwd_d3c2(const float *__restrict__ inputs, const T *__restrict__ grid, const int32_t *__restrict__ offsets,
+k_grid_fwd_d3c2(const float *__restrict__ inputs, const TE *__restrict__ grid, const int32_t *__restrict__ offsets,
                 T *__restrict__ outputs, uint32_t B, uint32_t L, uint32_t max_level, float S, uint32_t H,
                 uint32_t gridtype, bool align_corners, uint32_t interp) {
     __shared__ LevelInfo info[kMaxFastLevels];
@@ -355,12 +360,13 @@ k_grid_fwd_d3c2(const float *__restrict__ inputs, const T *__restrict__ grid, co
                 const uint32_t g0 = (uint32_t)floorf(p0), g1 = (uint32_t)floorf(p1), g2 = (uint32_t)floorf(p2);
                 p0 -= (float)g0; p1 -= (float)g1; p2 -= (float)g2;
                 if (interp == 1) { p0 = ge_smoothstep(p0); p1 = ge_smoothstep(p1); p2 = ge_smoothstep(p2); }
-                const T *lg = grid + (size_t)li.offset * 2;
+                const TE *lg = grid + (size_t)li.offset * 2;
                 float2 v[8];
 #pragma unroll
                 for (uint32_t idx = 0; idx < 8; idx++) {
                     const uint32_t row = ge_row_d3(li, g0 + (idx & 1u), g1 + ((idx >> 1) & 1u), g2 + ((idx >> 2) & 1u));
-                    v[idx] = ge_ld2(lg + (size_t)row * 2);
+                    if constexpr (sizeof(TE) == 4 && sizeof(T) == 2) v[idx] = ge_ld2_round_half(lg + (size_t)row * 2);
+                    else v[idx] = ge_ld2(lg + (size_t)row * 2);
                 }
 #pragma unroll
                 for (uint32_t idx = 0; idx < 8; idx++) {
@@ -506,7 +512,7 @@ int launch_fwd(const float *inputs, const T *emb, const int32_t *offsets, T *out
                uint32_t L, uint32_t max_level, float S, uint32_t H, T *dy_dx, uint32_t gridtype, bool ac,
                uint32_t interp, int layout, cudaStream_t st) {
     if (D == 3 && C == 2 && layout == NB200_LAYOUT_BLC && !dy_dx && L <= kMaxFastLevels) {
-        k_grid_fwd_d3c2<T><<<nb_div_up(B, 256), 256, 0, st>>>(inputs, emb, offsets, out, B, L, max_level, S, H, gridtype, ac, interp);
+        k_grid_fwd_d3c2<T, T><<<nb_div_up(B, 256), 256, 0, st>>>(inputs, emb, offsets, out, B, L, max_level, S, H, gridtype, ac, interp);
         return 0;
     }
     switch (D) {
@@ -589,7 +595,14 @@ int nb200_grid_encode_forward(const float *inputs, const void *embeddings, const
     else if (emb_dtype == NB200_F16)
         rc = launch_fwd<__half>(inputs, (const __half *)embeddings, offsets, (__half *)outputs, B, D, C, L, max_level, S,
                                 H, (__half *)dy_dx, gridtype, align_corners != 0, interp, layout, nb_stream(stream));
-    else
+    else if (emb_dtype == NB200_F32_AS_F16) {
+        // fast path only: fp32 table, values rounded to fp16 on load, fp16 outputs
+        if (!(D == 3 && C == 2 && layout == NB200_LAYOUT_BLC && !dy_dx && L <= kMaxFastLevels)) return NB200_E_BAD_DTYPE;
+        k_grid_fwd_d3c2<float, __half><<<nb_div_up(B, 256), 256, 0, nb_stream(stream)>>>(
+            inputs, (const float *)embeddings, offsets, (__half *)outputs, B, L, max_level, S, H, gridtype,
+            align_corners != 0, interp);
+        rc = 0;
+    } else
         return NB200_E_BAD_DTYPE;
     if (rc) return rc;
     NB_LAUNCH_CHECK();

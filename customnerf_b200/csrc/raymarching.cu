@@ -28,9 +28,11 @@ __device__ __forceinline__ int rm_mip_level(float mx, int Cm1) {
 struct RayCtx {
     float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
     float sx, sy, sz;          // 0.5f * sign(d)
-    float rH, H3, Hf, Hm1f, bound, dt_gamma, dt_min, dt_max;
+    float rH, H3, Hf, Hm1f, bound, rbound, dt_gamma, dt_min, dt_max;
+    float halfH;               // 0.5f * H when H is a power of two (then the fp64 product of :374 is an exact fp32 one), else 0
     double Hd;
     int Cm1;
+    int level_dt;              // mip_from_dt of the constant step when dt_gamma == 0, else -1
     const uint8_t *grid;
 };
 
@@ -45,9 +47,16 @@ __device__ __forceinline__ void rm_setup(RayCtx &r, const float *__restrict__ o,
     r.H3 = (float)(H * H * H);
     r.Hf = (float)H; r.Hm1f = (float)(H - 1); r.Hd = (double)H;
     r.bound = bound; r.dt_gamma = dt_gamma;
+    r.rbound = __fdiv_rn(1.0f, bound);
+    r.halfH = ((H & (H - 1)) == 0) ? 0.5f * (float)H : 0.0f;
     r.dt_min = __fdiv_rn(2 * kSqrt3, (float)max_steps);                                   // :345
     r.dt_max = __fdiv_rn(__fmul_rn(2 * kSqrt3, (float)(1 << (C - 1))), (float)H);          // :346
     r.Cm1 = (int)C - 1;
+    r.level_dt = -1;
+    if (dt_gamma == 0.0f) {
+        const float dt = rm_clamp(0.0f, r.dt_min, r.dt_max);                               // t * 0 == 0 for every finite t
+        r.level_dt = rm_mip_level(__fmul_rn(__fmul_rn(dt, r.Hf), 0.5f), r.Cm1);
+    }
     r.grid = grid;
 }
 
@@ -55,10 +64,21 @@ __device__ __forceinline__ float rm_dt(const RayCtx &r, float t) {
     return rm_clamp(__fmul_rn(t, r.dt_gamma), r.dt_min, r.dt_max);
 }
 
-// (int) clamp(0.5 * (p * mip_rbound + 1) * H, 0, H-1): fp64 product because the literal is a double (:374-376)
+// (int) clamp(0.5 * (p * mip_rbound + 1) * H, 0, H-1): fp64 product because the literal is a double (:374-376).
+// When H is a power of two, 0.5 * f * H only changes f's exponent, so the fp64 product rounded to fp32 equals the
+// single fp32 product f * (0.5 * H) bit for bit (no overflow / underflow is possible for f in [0, 2]).
 __device__ __forceinline__ int rm_cell(const RayCtx &r, float p, float mip_rbound) {
-    const double v = __dmul_rn(__dmul_rn(0.5, (double)__fmaf_rn(p, mip_rbound, 1.0f)), r.Hd);
-    return __float2int_rz(rm_clamp(__double2float_rn(v), 0.0f, r.Hm1f));
+    const float f = __fmaf_rn(p, mip_rbound, 1.0f);
+    float v;
+    if (r.halfH != 0.0f) v = __fmul_rn(f, r.halfH);
+    else v = __double2float_rn(__dmul_rn(__dmul_rn(0.5, (double)f), r.Hd));
+    return __float2int_rz(rm_clamp(v, 0.0f, r.Hm1f));
+}
+
+// do { t += dt; } while (t < tt);   (:396-398)
+__device__ __forceinline__ float rm_advance(const RayCtx &r, float t, float tt) {
+    do { t = __fadd_rn(t, rm_dt(r, t)); } while (t < tt);
+    return t;
 }
 
 __device__ __forceinline__ float rm_exit(float n, float s, float rH, float mip_bound, float p, float rd) {
@@ -76,9 +96,12 @@ __device__ __forceinline__ bool rm_step(const RayCtx &r, float &t, float &x, flo
     z = rm_clamp(__fmaf_rn(t, r.dz, r.oz), -r.bound, r.bound);
     dt = rm_dt(r, t);
     const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-    const int level = max(rm_mip_level(mx, r.Cm1), rm_mip_level(__fmul_rn(__fmul_rn(dt, r.Hf), 0.5f), r.Cm1));
-    const float mip_bound = fminf(__int_as_float((127 + level) << 23), r.bound);           // scalbnf(1, level)
-    const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    const int level_dt = r.level_dt >= 0 ? r.level_dt : rm_mip_level(__fmul_rn(__fmul_rn(dt, r.Hf), 0.5f), r.Cm1);
+    const int level = max(rm_mip_level(mx, r.Cm1), level_dt);
+    const float pw = __int_as_float((127 + level) << 23);                                   // scalbnf(1, level)
+    const bool capped = pw > r.bound;
+    const float mip_bound = capped ? r.bound : pw;                                          // fminf(2^level, bound)
+    const float mip_rbound = capped ? r.rbound : __int_as_float((127 - level) << 23);       // 1 / mip_bound, exact
     const int nx = rm_cell(r, x, mip_rbound);
     const int ny = rm_cell(r, y, mip_rbound);
     const int nz = rm_cell(r, z, mip_rbound);
@@ -89,9 +112,7 @@ __device__ __forceinline__ bool rm_step(const RayCtx &r, float &t, float &x, flo
     const float ty = rm_exit((float)ny, r.sy, r.rH, mip_bound, y, r.rdy);
     const float tz = rm_exit((float)nz, r.sz, r.rH, mip_bound, z, r.rdz);
     const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
-    do {
-        t = __fadd_rn(t, rm_dt(r, t));
-    } while (t < tt);
+    t = rm_advance(r, t, tt);
     return false;
 }
 
@@ -171,7 +192,7 @@ __global__ void k_packbits(const float *__restrict__ grid, uint32_t N, float thr
 // ------------------------------------------------------------------------------------------------
 // march_rays_train: count -> scan -> write
 // ------------------------------------------------------------------------------------------------
-constexpr int kMarchBlock = 256;
+constexpr int kMarchBlock = 32;    // one warp per block: ~15 k rays are only ~470 warps, spread them over all SMs
 
 // pass 1 (:353-400): counts, block-local exclusive offsets (warp shuffles), per-block sums
 __global__ void __launch_bounds__(kMarchBlock)

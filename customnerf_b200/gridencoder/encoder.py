@@ -5,8 +5,8 @@ autocast behaviour; what changed underneath (reference file:line in brackets):
 
   * outputs are written by the kernel directly as [B, L*C]  [grid.py:49,63: [L,B,C] + permute copy];
   * the backward reads ``grad`` as [B, L*C] directly        [grid.py:81: view/permute/contiguous copy];
-  * under autocast the fp16 table is a cached "shadow" that is re-cast only when ``embeddings`` changed
-    (``_version`` bump from the optimiser)                  [grid.py:45-46: full-table cast every call];
+  * under autocast the kernel reads the fp32 master table and rounds every entry to fp16 as it loads it
+    (bit-identical to gathering from a half copy)           [grid.py:45-46: full-table fp32->fp16 copy every call];
   * ``grad_embeddings`` is accumulated in fp32 by a warp-aggregated scatter and returned as fp32
                                                             [gridencoder.cu:324-337: __half2 atomics].
 """
@@ -21,17 +21,8 @@ from .. import _lib as L
 _gridtype_to_id = {'hash': 0, 'tiled': 1}
 _interp_to_id = {'linear': 0, 'smoothstep': 1}
 
-def _half_table(embeddings):
-    """fp16 shadow of an fp32 table, refreshed only when the fp32 master was modified in place.
-    The shadow rides on the tensor object itself, so it is freed with it."""
-    ent = getattr(embeddings, "_nb200_half_shadow", None)
-    if ent is not None and ent[0] == embeddings._version and ent[1].device == embeddings.device:
-        return ent[1]
-    src = embeddings.detach()
-    dst = torch.empty(src.shape, dtype=torch.half, device=src.device)
-    L.check(L.lib().nb200_cast_f32_to_f16(L.ptr(src), L.ptr(dst), L.u64(src.numel()), L.stream()), "cast_f32_to_f16")
-    embeddings._nb200_half_shadow = (embeddings._version, dst)
-    return dst
+def _fast_shape(D, C, Lv, calc_grad_inputs):
+    return D == 3 and C == 2 and Lv <= 32 and not calc_grad_inputs
 
 
 def _check_inputs(inputs, embeddings, offsets):
@@ -66,26 +57,35 @@ class _grid_encode(Function):
         max_level = Lv if max_level is None else min(max_level, Lv)
 
         master = embeddings
+        tag = None
+        out_dtype = embeddings.dtype
         if torch.is_autocast_enabled() and C % 2 == 0 and embeddings.dtype == torch.float32:
-            embeddings = _half_table(master)
+            # manual autocast (grid.py:43-46): half-precision table values, fp32 coordinates
+            out_dtype = torch.half
+            if _fast_shape(D, C, Lv, calc_grad_inputs):
+                tag = L.F32_AS_F16            # the kernel rounds each fp32 entry to fp16 as it loads it: no table copy
+            else:
+                embeddings = embeddings.to(torch.half)
         _check_inputs(inputs, embeddings, offsets)
         if D not in (2, 3, 4, 5) or C not in (1, 2, 4, 8):
             raise RuntimeError("GridEncoding: C must be 1, 2, 4, or 8.")
+        if tag is None:
+            tag = L.dtype_tag(embeddings)
 
         if max_level < Lv:
-            outputs = torch.zeros(B, Lv * C, device=inputs.device, dtype=embeddings.dtype)
+            outputs = torch.zeros(B, Lv * C, device=inputs.device, dtype=out_dtype)
         else:
-            outputs = torch.empty(B, Lv * C, device=inputs.device, dtype=embeddings.dtype)
+            outputs = torch.empty(B, Lv * C, device=inputs.device, dtype=out_dtype)
         if calc_grad_inputs:
             alloc = torch.zeros if max_level < Lv else torch.empty
-            dy_dx = alloc(B, Lv * D * C, device=inputs.device, dtype=embeddings.dtype)
+            dy_dx = alloc(B, Lv * D * C, device=inputs.device, dtype=out_dtype)
         else:
             dy_dx = None
 
         L.check(L.lib().nb200_grid_encode_forward(
             L.ptr(inputs), L.ptr(embeddings), L.ptr(offsets), L.ptr(outputs), L.u32(B), L.u32(D), L.u32(C), L.u32(Lv),
             L.u32(max_level), L.f32(S), L.u32(H), L.ptr(dy_dx), L.u32(gridtype), L.i32(int(align_corners)),
-            L.u32(interpolation), L.i32(L.dtype_tag(embeddings)), L.i32(L.LAYOUT_BLC), L.stream()),
+            L.u32(interpolation), L.i32(tag), L.i32(L.LAYOUT_BLC), L.stream()),
             "grid_encode_forward")
 
         ctx.save_for_backward(inputs, offsets, dy_dx)

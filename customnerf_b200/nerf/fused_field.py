@@ -12,22 +12,20 @@ def _image_bytes():
 
 
 class _PackedWeights:
-    """fp16 pre-swizzled operand images of the three parameter vectors, re-packed only when a vector changed."""
+    """fp16 pre-swizzled operand images of the three parameter vectors.  Re-packed on every call (two tiny launches):
+    in-place optimiser kernels such as torch's fused Adam do not bump tensor versions, so nothing cheaper is safe."""
 
     def __init__(self):
-        self.key = None
         self.fwd = self.bwd = None
 
     def get(self, trunk, density, rgb):
-        key = (trunk.data_ptr(), trunk._version, density.data_ptr(), density._version, rgb.data_ptr(), rgb._version)
-        if key != self.key or self.fwd is None or self.fwd.device != trunk.device:
-            n = _image_bytes()
-            if self.fwd is None or self.fwd.device != trunk.device:
-                self.fwd = torch.empty(n, dtype=torch.uint8, device=trunk.device)
-                self.bwd = torch.empty(n, dtype=torch.uint8, device=trunk.device)
-            L.check(L.lib().nb200_field_pack_weights(L.ptr(trunk.detach()), L.ptr(density.detach()), L.ptr(rgb.detach()),
-                                                     L.ptr(self.fwd), L.ptr(self.bwd), L.stream()), "field_pack_weights")
-            self.key = key
+        n = _image_bytes()
+        if self.fwd is None or self.fwd.device != trunk.device or torch.is_grad_enabled():
+            # a fresh pair while autograd may still hold the previous one for a pending backward
+            self.fwd = torch.empty(n, dtype=torch.uint8, device=trunk.device)
+            self.bwd = torch.empty(n, dtype=torch.uint8, device=trunk.device)
+        L.check(L.lib().nb200_field_pack_weights(L.ptr(trunk.detach()), L.ptr(density.detach()), L.ptr(rgb.detach()),
+                                                 L.ptr(self.fwd), L.ptr(self.bwd), L.stream()), "field_pack_weights")
         return self.fwd, self.bwd
 
 

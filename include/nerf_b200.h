@@ -27,6 +27,8 @@ extern "C" {
 /* dtype tags for void* tensors */
 #define NB200_F32 0
 #define NB200_F16 1
+#define NB200_F32_AS_F16 2   /* grid_encode_forward fast path only: fp32 table, every value rounded to fp16 as it is
+                                loaded, fp16 outputs -- autocast semantics of grid.py:45-46 without the table copy */
 
 /* error codes (negative; positive values are cudaError_t) */
 #define NB200_E_BAD_DIM   (-1)   /* "GridEncoding: C must be 1, 2, 4, or 8." / D must be 2..5 (gridencoder.cu:380,397) */
