@@ -11,7 +11,7 @@ With N GPUs every rank renders its own view of the scene (weak scaling) and the 
 the MLPs are all-reduced once per step (NCCL).
 
 A "step" = one full train step over one image: near/far -> march -> encode -> MLP -> composite -> loss ->
-backward (composite, MLP, encode scatter) -> Adam.
+backward (composite, MLP, encode scatter) -> Adam, replayed as one CUDA graph (customnerf_b200/fused_trainer.py).
   value : rays/s with the ray batch already resident in HBM (device-timed with CUDA events, L2 flushed between
           steps outside the event pairs, max over ranks)
   e2e   : rays/s through the public API with HOST (pinned) ray / target buffers: H2D copies and the D2H read of
@@ -138,141 +138,55 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-def op_breakdown(model, rays_o, rays_d, reps=20):
-    """Device time of every native kernel of one step, each timed alone with CUDA events (L2 flushed in between)."""
-    import numpy as np
-    import torch
-    from customnerf_b200 import raymarching as rm, _lib as L
-    dev = rays_o.device
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def timeit(fn):
-        ts = []
-        for _ in range(reps):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b) * 1e3)
-        ts.sort()
-        return ts[len(ts) // 2]
-
-    out = {}
-    N = rays_o.shape[0]
-    nears, fars = rm.near_far_from_aabb(rays_o, rays_d, model.aabb_train)
-    out["near_far_from_aabb"] = timeit(lambda: rm.near_far_from_aabb(rays_o, rays_d, model.aabb_train))
-    counter = torch.zeros(2, dtype=torch.int32, device=dev)
-    noises = torch.rand(N, device=dev)
-    xyzs, dirs, deltas, rays = rm.march_rays_train(rays_o, rays_d, model.bound, model.density_bitfield, model.cascade,
-                                                   model.grid_size, nears, fars, counter, -1, True, 128, True, 0, 1024,
-                                                   noises=noises)
-    M = xyzs.shape[0]
-    scratch = torch.empty(int(L.lib().nb200_march_scratch_ints(L.u32(N))), dtype=torch.int32, device=dev)
-    lib = L.lib()
-
-    def march_count():
-        counter.zero_()
-        L.check(lib.nb200_march_rays_train_count(L.ptr(rays_o), L.ptr(rays_d), L.ptr(model.density_bitfield),
-                L.f32(model.bound), L.f32(0), L.u32(1024), L.u32(N), L.u32(model.cascade), L.u32(model.grid_size),
-                L.ptr(nears), L.ptr(fars), L.ptr(noises), L.ptr(rays), L.ptr(counter), L.ptr(scratch), L.stream()), "count")
-
-    def march_write():
-        L.check(lib.nb200_march_rays_train_write(L.ptr(rays_o), L.ptr(rays_d), L.ptr(model.density_bitfield),
-                L.f32(model.bound), L.f32(0), L.u32(1024), L.u32(N), L.u32(model.cascade), L.u32(model.grid_size), L.u32(M),
-                L.ptr(nears), L.ptr(fars), L.ptr(noises), L.ptr(rays), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas), L.stream()), "write")
-    out["march_count(+scan)"] = timeit(march_count)
-    out["march_write"] = timeit(march_write)
-
-    enc = model.pos_en
-    emb16 = enc.embeddings.detach().half()
-    x01 = ((xyzs + model.bound) / (2 * model.bound)).contiguous()
-    feat = torch.empty(M, 32, dtype=torch.half, device=dev)
-    S = float(np.log2(enc.per_level_scale))
-
-    def enc_fwd():
-        L.check(lib.nb200_grid_encode_forward(L.ptr(x01), L.ptr(emb16), L.ptr(enc.offsets), L.ptr(feat), L.u32(M), L.u32(3),
-                L.u32(2), L.u32(16), L.u32(16), L.f32(S), L.u32(16), L.ptr(None), L.u32(enc.gridtype_id), L.i32(0), L.u32(0),
-                L.i32(L.F16), L.i32(L.LAYOUT_BLC), L.stream()), "fwd")
-    gfeat = torch.randn(M, 32, device=dev).half()
-    gemb = torch.zeros_like(enc.embeddings)
-
-    def enc_bwd(agg):
-        def f():
-            L.check(lib.nb200_grid_encode_backward(L.ptr(gfeat), L.ptr(x01), L.ptr(enc.offsets), L.ptr(gemb), L.u32(M),
-                    L.u32(3), L.u32(2), L.u32(16), L.u32(16), L.f32(S), L.u32(16), L.ptr(None), L.ptr(None),
-                    L.u32(enc.gridtype_id), L.i32(0), L.u32(0), L.i32(L.F16), L.i32(L.LAYOUT_BLC), L.i32(agg), L.stream()), "bwd")
-        return f
-    out["grid_encode_forward_f16"] = timeit(enc_fwd)
-    out["grid_encode_backward_f16_agg"] = timeit(enc_bwd(1))
-    out["grid_encode_backward_f16_noagg"] = timeit(enc_bwd(0))
-
-    sig = (torch.rand(M, device=dev) * 50).requires_grad_()
-    rgb = torch.rand(M, 3, device=dev).requires_grad_()
-    ws = torch.empty(N, device=dev); dp = torch.empty(N, device=dev); im = torch.empty(N, 3, device=dev)
-    gs = torch.empty(M, device=dev); gc = torch.empty(M, 3, device=dev)
-    gws = torch.randn(N, device=dev); gim = torch.randn(N, 3, device=dev)
-    out["composite_train_forward"] = timeit(lambda: L.check(lib.nb200_composite_rays_train_forward(
-        L.ptr(sig), L.ptr(rgb), L.ptr(deltas), L.ptr(rays), L.u32(M), L.u32(N), L.f32(1e-4), L.ptr(ws), L.ptr(dp), L.ptr(im),
-        L.stream()), "cf"))
-    out["composite_train_backward"] = timeit(lambda: L.check(lib.nb200_composite_rays_train_backward(
-        L.ptr(gws), L.ptr(gim), L.ptr(sig), L.ptr(rgb), L.ptr(deltas), L.ptr(rays), L.ptr(ws), L.ptr(im), L.u32(M), L.u32(N),
-        L.f32(1e-4), L.ptr(gs), L.ptr(gc), L.stream()), "cb"))
-    # fused tcgen05 field network (trunk + heads), forward with activations saved, and backward
-    from customnerf_b200.nerf.fused_field import _image_bytes
-    nb = _image_bytes()
-    fimg = torch.empty(nb, dtype=torch.uint8, device=dev); bimg = torch.empty(nb, dtype=torch.uint8, device=dev)
-    tp, dp_, rp = model.network.params.detach(), model.density_network.params.detach(), model.rgb_network.params.detach()
-    L.check(lib.nb200_field_pack_weights(L.ptr(tp), L.ptr(dp_), L.ptr(rp), L.ptr(fimg), L.ptr(bimg), L.stream()), "pack")
-    sigma = torch.empty(M, device=dev); sarg = torch.empty(M, device=dev)
-    rgba = torch.empty(M, 4, dtype=torch.half, device=dev); act = torch.empty(5, M, 64, dtype=torch.half, device=dev)
-    enc_fwd()
-    out["field_forward_tcgen05"] = timeit(lambda: L.check(lib.nb200_field_forward(
-        L.ptr(feat), L.ptr(xyzs), L.ptr(dirs), L.ptr(fimg), L.ptr(sigma), L.ptr(sarg), L.ptr(rgba), L.ptr(act), L.u32(M),
-        L.stream()), "ff"))
-    out["field_forward_tcgen05_nosave"] = timeit(lambda: L.check(lib.nb200_field_forward(
-        L.ptr(feat), L.ptr(xyzs), L.ptr(dirs), L.ptr(fimg), L.ptr(sigma), L.ptr(None), L.ptr(rgba), L.ptr(None), L.u32(M),
-        L.stream()), "ff"))
-    dsig = torch.randn(M, device=dev) * 0.01; drgba = torch.randn(M, 4, device=dev)
-    dx = torch.empty(M, 32, dtype=torch.half, device=dev)
-    gt, gd_, gr = torch.zeros_like(tp), torch.zeros_like(dp_), torch.zeros_like(rp)
-    out["field_backward_tcgen05"] = timeit(lambda: L.check(lib.nb200_field_backward(
-        L.ptr(dsig), L.ptr(drgba), L.ptr(sarg), L.ptr(rgba), L.ptr(feat), L.ptr(dirs), L.ptr(act), L.ptr(bimg), L.ptr(dx),
-        L.ptr(gt), L.ptr(gd_), L.ptr(gr), L.u32(M), L.stream()), "fb"))
-    model.use_fused_field = False
-    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
-        out["field_forward(torch/cuBLAS per-layer path)"] = timeit(lambda: model(xyzs, dirs))
-    model.use_fused_field = True
-    samples = int(counter[0])
-    return out, samples, M
+# Algorithmic bytes per sample of every stage (DESIGN.md "Kernels"): what the stage must move if every
+# byte were touched exactly once.  fp16 features / activations, fp32 table master and gradients.
+BYTES_PER_SAMPLE = {
+    "march_write": 32.0,                    # xyz 12 + dir 12 + deltas 8 written
+    "grid_encode_forward": 12.0 + 16 * 8 * 8 + 64.0,       # coords + 128 corner float2 gathers (fp32 master) + 64 B features
+    "field_forward": 64.0 + 24.0 + 4 + 4 + 8 + 640.0,      # x_en + xyz/dirs + sigma + sigma_arg + rgba + 5 saved activations
+    "composite_forward": 4.0 + 8 + 8,                      # sigma + rgba(f16x4) + deltas
+    "composite_backward": 4.0 + 8 + 8 + 4 + 16,            # same reads + d_sigma + d_rgba(float4)
+    "field_backward": 640.0 + 64 + 12 + 4 + 16 + 4 + 8 + 64,   # activations, x_en, dirs, d_sigma, d_rgba, sigma_arg, rgba; d_x_en out
+    "grid_encode_backward": 12.0 + 64 + 2 * 16 * 8 * 8,    # coords + feature grads + 128 float2 atomic read-modify-writes
+}
+BYTES_PER_PARAM = {"adam": 32.0}            # p, g, m, v read; p, m, v, g written (16 + 16)
 
 
-def roofline_from(breakdown, samples, peaks):
-    """Dominant native kernel of the step and its achieved algorithmic bandwidth (SURVEY.md 8(d) per-unit bytes)."""
-    per_unit = {  # bytes per sample
-        "grid_encode_forward_f16": 588.0,      # 12 B coords + 16*8 corners * 4 B + 64 B out
-        "grid_encode_backward_f16_agg": 1100.0 + 1024.0,   # 12 + 64 B grad + fp32 atomics RMW 2*8*16*8 B
-        "composite_train_forward": 24.0,
-        "composite_train_backward": 40.0,
-        "march_write": 32.0,
-        # field network: HBM bytes per point (x_en 64 + xyz/dirs 24 + outputs 12 + saved activations 644)
-        "field_forward_tcgen05": 744.0,
-        # reads activations 640 + x_en 64 + dirs 12 + grads/outputs 36, writes d_x_en 64
-        "field_backward_tcgen05": 816.0,
-    }
-    mine = {k: v for k, v in breakdown.items() if k in per_unit}
-    top = max(mine, key=mine.get)
-    us = mine[top]
-    achieved = per_unit[top] * samples / (us * 1e-6) / 1e9
+def rooflines(stage_us, samples, n_params, peaks):
+    """achieved algorithmic GB/s of every bandwidth-bound stage, and the dominant one as the headline roofline"""
     peak = peaks.get("hbm_gbs", 6650.0)
-    return {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "us_per_launch": us, "bytes_per_unit": per_unit[top], "units_per_launch": samples,
-            "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"}
+    src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    per = {}
+    for k, us in stage_us.items():
+        if k in BYTES_PER_SAMPLE:
+            units, bpu = samples, BYTES_PER_SAMPLE[k]
+        elif k in BYTES_PER_PARAM:
+            units, bpu = n_params, BYTES_PER_PARAM[k]
+        else:
+            continue
+        ach = bpu * units / (us * 1e-6) / 1e9
+        per[k] = {"us": round(us, 2), "bytes_per_unit": bpu, "units": units, "achieved_gbs": round(ach, 1),
+                  "frac_of_hbm_peak": round(ach / peak, 4)}
+    top = max(per, key=lambda k: per[k]["us"])
+    t = per[top]
+    # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture, when one exists
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top)
+    except Exception:
+        pass
+    head = {"kernel": top, "bound": "hbm", "achieved": t["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": t["achieved_gbs"] / peak, "traffic": traffic, "us_per_launch": t["us"],
+            "bytes_per_unit": t["bytes_per_unit"], "units_per_launch": t["units"], "peak_source": src,
+            "how": "CUDA events recorded between the stages of real train steps on the launching stream (L2 flushed "
+                   "between steps), mean over the profiled steps"}
+    return head, per
 
 
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from customnerf_b200 import parallel, synthetic as syn, trainer, _lib as L
+    from customnerf_b200 import parallel, synthetic as syn, trainer, fused_trainer, _lib as L
 
     rank, local_rank, world = parallel.init_from_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (use --impl reference for the CPU arm)"
@@ -281,13 +195,12 @@ def run_b200(args):
     L.lib()   # fail loudly if the native library is missing
 
     model = trainer.build_scene_model(dev)
-    sync = parallel.FlatGradSync([p for g in model.get_params(5e-4) for p in g["params"]]) if world > 1 else None
-    ts = trainer.TrainStep(model, lr=5e-4, fp16=True, world_size=world, grad_sync=sync)
     o, d = syn.camera_rays(IMG_H, IMG_W, view=rank)           # weak scaling: one image per rank
     target = syn.bear_color(o + d * 1.5)
     n_rays = o.shape[0]
+    sync = (lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM)) if world > 1 else None
+    fs = fused_trainer.FusedTrainStep(model, n_rays, lr=5e-4, world_size=world, grad_sync=sync, use_graph=not args.no_graph)
     o_h, d_h, t_h = o.pin_memory(), d.pin_memory(), target.pin_memory()
-    o_d, d_d, t_d = o.to(dev), d.to(dev), target.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -302,18 +215,20 @@ def run_b200(args):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             if host_inputs:
-                ro, rd, tg = o_h.to(dev, non_blocking=True), d_h.to(dev, non_blocking=True), t_h.to(dev, non_blocking=True)
-                loss = ts.step(ro, rd, tg, n_total=n_rays * world)
-                _ = loss.item()                                # D2H read of the step's result
+                fs.step(o_h, d_h, t_h)                         # H2D of the batch (pinned) + the step
+                fs.last_stats()                                # D2H read of loss / sample count (16 B) + sync
             else:
-                ts.step(o_d, d_d, t_d, n_total=n_rays * world)
+                fs.step()                                      # batch already resident in HBM
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs) / 1e3    # seconds of device time
 
+    fs.step(o_h, d_h, t_h)
     for _ in range(max(args.warmup, 3)):
-        ts.step(o_d, d_d, t_d, n_total=n_rays * world)
+        fs.step()
+    _, samples, used = fs.last_stats()
+    assert used == samples, "sample buffers overflowed during warm-up (%d > %d)" % (samples, fs.m_cap)
     clocks = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -325,6 +240,7 @@ def run_b200(args):
     sec_e2e = timed(args.steps, host_inputs=True)
     barrier()
     clk = clocks.stop() if rank == 0 else None
+    loss, samples, used = fs.last_stats()
     if world > 1:
         t = torch.tensor([sec, sec_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -341,17 +257,22 @@ def run_b200(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": n_rays, "parallelism": "ray-sharded dp%d" % world,
+                           "step": "one CUDA-graph replay: near/far, march, encode, field MLP, composite, MSE, backward, "
+                                   "fused Adam" + (", NCCL all-reduce of the flat gradient" if world > 1 else ""),
+                           "sample_rows_capacity": fs.m_cap,
                            "l2": "256 MB memset between steps, outside the per-step CUDA-event pairs",
                            "timing": "sum of per-step CUDA-event intervals, max over ranks"},
                 "e2e": {"value": total_rays / sec_e2e, "unit": UNIT,
-                        "h2d_bytes_per_step": int(3 * n_rays * 3 * 4), "d2h_bytes_per_step": 4,
-                        "ms_per_step": sec_e2e / args.steps * 1e3},
-                "gpu_launches": int(launches), "clocks": clk}
+                        "h2d_bytes_per_step": int(3 * n_rays * 3 * 4), "d2h_bytes_per_step": 16,
+                        "ms_per_step": sec_e2e / args.steps * 1e3,
+                        "api": "FusedTrainStep.step(rays_o, rays_d, target) with pinned host tensors + last_stats()"},
+                "gpu_launches": int(launches), "clocks": clk, "samples_per_step": samples, "final_loss": loss}
         if world == 1 and not args.no_breakdown:
-            bd, samples, M = op_breakdown(model, o_d, d_d)
-            line["kernel_us"] = {k: round(v, 2) for k, v in bd.items()}
-            line["samples_per_step"] = samples
-            line["roofline"] = roofline_from(bd, samples, peaks)
+            fs.use_graph = False
+            stage_us = fs.profile_stages(10, flush=flush.zero_)
+            fs.use_graph = not args.no_graph
+            line["kernel_us"] = {k: round(v, 2) for k, v in stage_us.items()}
+            line["roofline"], line["stage_rooflines"] = rooflines(stage_us, samples, fs.params_flat.numel(), peaks)
             n_cpu = 2048
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(3, 1, n_cpu).items() if k != "ms_per_step"}
         print(json.dumps(line), flush=True)
@@ -365,6 +286,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--no-breakdown", action="store_true",
                     help="skip the per-kernel breakdown and the CPU baseline (profiling runs under ncu)")
     args = ap.parse_args()

@@ -106,7 +106,8 @@ struct FieldFwdArgs {
     float *sigma_arg;       // [M] or null: raw + gaussian (the argument of trunc_exp), saved for backward
     __half *rgba;           // [M, 4]
     __half *act;            // [5, M, 64] or null: h1, h2, fea, hd, hr saved for backward
-    uint32_t M;
+    uint32_t M;             // rows allocated (the stride of `act` planes)
+    const int32_t *count_dev;   // when non-null only rows < min(M, *count_dev) are evaluated
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -149,7 +150,9 @@ k_field_forward(const FieldFwdArgs p) {
     __shared__ uint32_t fail_s;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t ntiles = (p.M + 127) / 128;
+    const uint32_t Mrows = p.count_dev ? min(p.M, (uint32_t)max(*p.count_dev, 0)) : p.M;
+    const uint32_t ntiles = (Mrows + 127) / 128;
+    if (blockIdx.x >= ntiles) return;
 
     // one-time: weights -> smem, TMEM, barrier
     for (uint32_t i = tid; i < F_BYTES / 16; i += 128)
@@ -193,7 +196,7 @@ k_field_forward(const FieldFwdArgs p) {
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t g = tile * 128 + tid;
-        const bool valid = g < p.M;
+        const bool valid = g < Mrows;
         // ---- inputs: x_en row and the direction encoding -> XV tile
         {
             uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, x2 = x0, x3 = x0;
@@ -333,7 +336,8 @@ struct FieldBwdArgs {
     const uint8_t *wimg;      // backward weight image
     __half *d_x_en;           // [M, 32]
     float *g_trunk, *g_density, *g_rgb;   // flat fp32 parameter gradients, ACCUMULATED INTO
-    uint32_t M;
+    uint32_t M;               // rows allocated (the stride of `act` planes)
+    const int32_t *count_dev; // when non-null only rows < min(M, *count_dev) are processed
 };
 
 // MN-major descriptor of K-step ks (16 rows = 2 swizzle atoms) starting at column `col0` (multiple of 8 halves)
@@ -378,7 +382,9 @@ k_field_backward(const FieldBwdArgs p) {
     __shared__ uint32_t tmem_base_s;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t ntiles = (p.M + 127) / 128;
+    const uint32_t Mrows = p.count_dev ? min(p.M, (uint32_t)max(*p.count_dev, 0)) : p.M;
+    const uint32_t ntiles = (Mrows + 127) / 128;
+    if (blockIdx.x >= ntiles) return;
 
     for (uint32_t i = tid; i < B_BYTES / 16; i += 128)
         reinterpret_cast<uint4 *>(smem + SB_W)[i] = __ldg(reinterpret_cast<const uint4 *>(p.wimg) + i);
@@ -428,7 +434,7 @@ k_field_backward(const FieldBwdArgs p) {
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t g = tile * 128 + tid;
-        const bool valid = g < p.M;
+        const bool valid = g < Mrows;
         const size_t act_stride = (size_t)p.M * 64;
         // ---- load this point's rows: x_en | view, h1, h2, fea, hd, hr; build the head gradients (T16)
         {
@@ -609,7 +615,7 @@ int nb200_field_pack_weights(const float *trunk, const float *density, const flo
 }
 
 int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, const void *fwd_img, float *sigma,
-                        float *sigma_arg, void *rgba, void *act, uint32_t M, void *stream) {
+                        float *sigma_arg, void *rgba, void *act, uint32_t M, const int32_t *count_dev, void *stream) {
     if (M == 0) return 0;
     if (!x_en || !xyz || !dirs || !fwd_img || !sigma || !rgba) return NB200_E_BAD_ARG;
     static int configured = 0;
@@ -625,6 +631,7 @@ int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, c
     FieldFwdArgs a;
     a.x_en = (const __half *)x_en; a.xyz = xyz; a.dirs = dirs; a.wimg = (const uint8_t *)fwd_img;
     a.sigma = sigma; a.sigma_arg = sigma_arg; a.rgba = (__half *)rgba; a.act = (__half *)act; a.M = M;
+    a.count_dev = count_dev;
     const uint32_t ntiles = (M + 127) / 128;
     const uint32_t grid = ntiles < (uint32_t)(2 * sms) ? ntiles : (uint32_t)(2 * sms);
     k_field_forward<<<grid, 128, smem, nb_stream(stream)>>>(a);
@@ -634,7 +641,8 @@ int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, c
 
 int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,
                          const void *x_en, const float *dirs, const void *act, const void *bwd_img, void *d_x_en,
-                         float *g_trunk, float *g_density, float *g_rgb, uint32_t M, void *stream) {
+                         float *g_trunk, float *g_density, float *g_rgb, uint32_t M, const int32_t *count_dev,
+                         void *stream) {
     if (M == 0) return 0;
     if (!d_sigma || !d_rgba || !sigma_arg || !rgba || !x_en || !dirs || !act || !bwd_img || !d_x_en || !g_trunk ||
         !g_density || !g_rgb)
@@ -653,6 +661,7 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
     a.d_sigma = d_sigma; a.d_rgba = d_rgba; a.sigma_arg = sigma_arg; a.rgba = (const __half *)rgba;
     a.x_en = (const __half *)x_en; a.dirs = dirs; a.act = (const __half *)act; a.wimg = (const uint8_t *)bwd_img;
     a.d_x_en = (__half *)d_x_en; a.g_trunk = g_trunk; a.g_density = g_density; a.g_rgb = g_rgb; a.M = M;
+    a.count_dev = count_dev;
     const uint32_t ntiles = (M + 127) / 128;
     const uint32_t grid = ntiles < (uint32_t)sms ? ntiles : (uint32_t)sms;
     k_field_backward<<<grid, 128, smem, nb_stream(stream)>>>(a);

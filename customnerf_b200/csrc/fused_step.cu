@@ -1,0 +1,128 @@
+// fused_step.cu -- one reconstruction train step of the occupancy (cuda_ray) path as a fixed sequence of launches on
+// one stream, driven by a plan of device pointers.
+//
+// Replaces, for the training hot loop, the Python glue of the reference between its native ops:
+//   NeRFRenderer.run_cuda            nerf/renderer.py:597-650   near/far -> march -> field -> composite
+//   NeRFNetwork.forward              nerf/network_grid.py:159-177
+//   _grid_encode / _composite autograd Functions  gridencoder/grid.py:27-95, raymarching/raymarching.py:239-292
+//   MSE loss + scaler + optimiser    nerf/utils_init_nerf.py:224-234, 612-629
+//
+// Nothing here synchronises with the host or allocates: the sample count of the step stays on the device
+// (`m_eff`), every buffer has a fixed capacity (`M_cap` rows) and the kernels bound their work by the device-side
+// count, so the whole step can be captured once into a CUDA graph and replayed (the reference blocks on
+// counter[0].item() every step, raymarching.py:225).  Rays whose samples do not fit in M_cap rows are dropped
+// exactly as the reference drops them when its mean_count budget overflows (raymarching.cu:415-416); the caller
+// watches counter[0] against M_cap and grows the buffers.
+#include "common.cuh"
+
+namespace {
+struct StageTimer {
+    cudaEvent_t fb[NB200_FB_STAGES + 1];
+    cudaEvent_t up[NB200_UP_STAGES + 1];
+    bool fb_done, up_done;
+};
+inline void tick(cudaEvent_t *ev, int i, cudaStream_t st) { if (ev) cudaEventRecord(ev[i], st); }
+}  // namespace
+
+extern "C" {
+
+int nb200_stage_timer_create(void **timer) {
+    if (!timer) return NB200_E_BAD_ARG;
+    StageTimer *t = new StageTimer();
+    t->fb_done = t->up_done = false;
+    for (auto &e : t->fb) { cudaError_t rc = cudaEventCreate(&e); if (rc != cudaSuccess) return (int)rc; }
+    for (auto &e : t->up) { cudaError_t rc = cudaEventCreate(&e); if (rc != cudaSuccess) return (int)rc; }
+    *timer = t;
+    return 0;
+}
+
+int nb200_stage_timer_destroy(void *timer) {
+    StageTimer *t = (StageTimer *)timer;
+    if (!t) return 0;
+    for (auto &e : t->fb) cudaEventDestroy(e);
+    for (auto &e : t->up) cudaEventDestroy(e);
+    delete t;
+    return 0;
+}
+
+int nb200_stage_timer_read(void *timer, float *out_us) {
+    StageTimer *t = (StageTimer *)timer;
+    if (!t || !out_us || !t->fb_done || !t->up_done) return NB200_E_BAD_ARG;
+    cudaError_t rc = cudaEventSynchronize(t->up[NB200_UP_STAGES]);
+    if (rc != cudaSuccess) return (int)rc;
+    for (int i = 0; i < NB200_FB_STAGES; i++) {
+        float ms = 0; cudaEventElapsedTime(&ms, t->fb[i], t->fb[i + 1]); out_us[i] = ms * 1e3f;
+    }
+    for (int i = 0; i < NB200_UP_STAGES; i++) {
+        float ms = 0; cudaEventElapsedTime(&ms, t->up[i], t->up[i + 1]); out_us[NB200_FB_STAGES + i] = ms * 1e3f;
+    }
+    return 0;
+}
+
+
+int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
+    if (!p) return NB200_E_BAD_ARG;
+    cudaStream_t st = nb_stream(stream);
+    int rc;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(p->counter, 0, 2 * sizeof(int32_t), st)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(p->loss, 0, sizeof(float), st)) != cudaSuccess) return (int)e;
+    StageTimer *tm = (StageTimer *)p->timer;
+    cudaEvent_t *ev = tm ? tm->fb : nullptr;
+    int k = 0;
+    tick(ev, k++, st);
+    if ((rc = nb200_near_far_from_aabb(p->rays_o, p->rays_d, p->aabb, p->N, p->min_near, p->nears, p->fars, stream))) return rc;
+    tick(ev, k++, st);
+    if ((rc = nb200_fs_march_count(p->rays_o, p->rays_d, p->bitfield, p->bound, p->dt_gamma, p->max_steps, p->N, p->C,
+                                   p->H, p->M_cap, p->nears, p->fars, p->noises, p->rays, p->counter, p->m_eff,
+                                   p->scratch, stream))) return rc;
+    tick(ev, k++, st);
+    if ((rc = nb200_fs_march_write(p->rays_o, p->rays_d, p->bitfield, p->bound, p->dt_gamma, p->max_steps, p->N, p->C,
+                                   p->H, p->M_cap, p->nears, p->fars, p->noises, p->rays, p->xyzs, p->dirs, p->deltas,
+                                   p->m_eff, stream))) return rc;
+    tick(ev, k++, st);
+    if ((rc = nb200_fs_encode_forward(p->xyzs, p->bound, p->table, p->offsets, p->x_en, p->M_cap, p->L, p->S, p->base_res,
+                                      p->gridtype, 0, 0, p->m_eff, stream))) return rc;
+    tick(ev, k++, st);
+    if ((rc = nb200_field_forward(p->x_en, p->xyzs, p->dirs, p->w_fwd, p->sigma, p->sigma_arg, p->rgba, p->act, p->M_cap,
+                                  p->m_eff, stream))) return rc;
+    tick(ev, k++, st);
+    if ((rc = nb200_fs_composite_forward(p->sigma, p->rgba, p->deltas, p->rays, p->M_cap, p->N, p->T_thresh,
+                                         p->weights_sum, p->depth, p->image, stream))) return rc;
+    tick(ev, k++, st);
+    if ((rc = nb200_mse_loss_grad(p->image, p->target, p->N, p->inv_n_total, p->loss_scale, p->loss, p->g_image, stream))) return rc;
+    tick(ev, k++, st);
+    if ((rc = nb200_fs_composite_backward(p->g_weights_sum, p->g_image, p->sigma, p->rgba, p->deltas, p->rays,
+                                          p->weights_sum, p->image, p->M_cap, p->N, p->T_thresh, p->d_sigma, p->d_rgba,
+                                          stream))) return rc;
+    tick(ev, k++, st);
+    if ((rc = nb200_field_backward(p->d_sigma, p->d_rgba, p->sigma_arg, p->rgba, p->x_en, p->dirs, p->act, p->w_bwd,
+                                   p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, stream))) return rc;
+    tick(ev, k++, st);
+    if ((rc = nb200_fs_encode_backward(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
+                                       p->base_res, p->gridtype, 0, 0, p->m_eff, stream))) return rc;
+    tick(ev, k++, st);
+    if (tm) tm->fb_done = true;
+    return 0;
+}
+
+int nb200_train_update(const nb200_train_plan *p, void *stream) {
+    if (!p) return NB200_E_BAD_ARG;
+    int rc;
+    cudaStream_t st = nb_stream(stream);
+    StageTimer *tm = (StageTimer *)p->timer;
+    cudaEvent_t *ev = tm ? tm->up : nullptr;
+    tick(ev, 0, st);
+    if ((rc = nb200_adam_hyper(p->step, p->sched, p->hyper, stream))) return rc;
+    if ((rc = nb200_fused_adam(p->params_flat, p->grads_flat, p->exp_avg, p->exp_avg_sq, p->n_params, p->n_table_params,
+                               p->hyper, 1, stream))) return rc;
+    tick(ev, 1, st);
+    if ((rc = nb200_field_pack_weights(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, stream))) return rc;
+    tick(ev, 2, st);
+    if (tm) tm->up_done = true;
+    return 0;
+}
+
+uint32_t nb200_train_plan_bytes(void) { return (uint32_t)sizeof(nb200_train_plan); }
+
+}  // extern "C"

@@ -281,6 +281,15 @@ k_grad_tv(const float *__restrict__ inputs, const float *__restrict__ grid, floa
 constexpr uint32_t kMaxFastLevels = 32;
 constexpr uint32_t P1 = 2654435761u, P2 = 805459861u;
 
+// optional input transform and device-side row count of the fused train step (nb200_fs_*): x01 = (x + add) * mul is
+// what GridEncoder.forward's `(inputs + bound) / (2 * bound)` evaluates to in torch (a tensor / python-scalar division
+// is a multiplication by the fp32 reciprocal), fused here so the normalised copy of the sample positions never exists.
+struct InXform {
+    float add, mul;                 // mul == 0: identity (inputs are already in [0, 1])
+    const int32_t *count_dev;       // when non-null only rows < min(B, *count_dev) are processed
+    __device__ __forceinline__ float operator()(float x) const { return mul != 0.0f ? __fmul_rn(__fadd_rn(x, add), mul) : x; }
+};
+
 struct LevelInfo {
     uint32_t offset;     // first row of the level
     uint32_t size;       // rows in the level (hashmap_size)
@@ -337,13 +346,15 @@ template <typename TE, typename T>
 __global__ void __launch_bounds__(256)
 k_grid_fwd_d3c2(const float *__restrict__ inputs, const TE *__restrict__ grid, const int32_t *__restrict__ offsets,
                 T *__restrict__ outputs, uint32_t B, uint32_t L, uint32_t max_level, float S, uint32_t H,
-                uint32_t gridtype, bool align_corners, uint32_t interp) {
+                uint32_t gridtype, bool align_corners, uint32_t interp, InXform xf) {
     __shared__ LevelInfo info[kMaxFastLevels];
+    if (xf.count_dev) B = min(B, (uint32_t)max(*xf.count_dev, 0));
+    if (blockIdx.x * blockDim.x >= B) return;
     ge_fill_level_info(info, offsets, max_level, S, H, gridtype, align_corners);
     __syncthreads();
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    const float x0 = inputs[(size_t)b * 3], x1 = inputs[(size_t)b * 3 + 1], x2 = inputs[(size_t)b * 3 + 2];
+    const float x0 = xf(inputs[(size_t)b * 3]), x1 = xf(inputs[(size_t)b * 3 + 1]), x2 = xf(inputs[(size_t)b * 3 + 2]);
     const bool oob = (x0 < 0 || x0 > 1) || (x1 < 0 || x1 > 1) || (x2 < 0 || x2 > 1);
     T *out = outputs + (size_t)b * L * 2;
     const float half_off = align_corners ? 0.0f : 0.5f;
@@ -408,15 +419,17 @@ template <typename T, bool kAgg>
 __global__ void __launch_bounds__(256)
 k_grid_bwd_d3c2(const T *__restrict__ grad, const float *__restrict__ inputs, const int32_t *__restrict__ offsets,
                 float *__restrict__ grad_grid, uint32_t B, uint32_t L, uint32_t max_level, float S, uint32_t H,
-                uint32_t gridtype, bool align_corners, uint32_t interp) {
+                uint32_t gridtype, bool align_corners, uint32_t interp, InXform xf) {
     __shared__ LevelInfo info[kMaxFastLevels];
+    if (xf.count_dev) B = min(B, (uint32_t)max(*xf.count_dev, 0));
+    if (blockIdx.x * blockDim.x >= B) return;
     ge_fill_level_info(info, offsets, max_level, S, H, gridtype, align_corners);
     __syncthreads();
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = nb_lane();
     const bool inb = b < B;            // keep whole warps alive for the shuffles
     float x0 = -1.0f, x1 = -1.0f, x2 = -1.0f;
-    if (inb) { x0 = inputs[(size_t)b * 3]; x1 = inputs[(size_t)b * 3 + 1]; x2 = inputs[(size_t)b * 3 + 2]; }
+    if (inb) { x0 = xf(inputs[(size_t)b * 3]); x1 = xf(inputs[(size_t)b * 3 + 1]); x2 = xf(inputs[(size_t)b * 3 + 2]); }
     const bool oob = (x0 < 0 || x0 > 1) || (x1 < 0 || x1 > 1) || (x2 < 0 || x2 > 1);   // !inb => oob
     const T *g = grad + (size_t)(inb ? b : 0) * L * 2;
     const float half_off = align_corners ? 0.0f : 0.5f;
@@ -512,7 +525,7 @@ int launch_fwd(const float *inputs, const T *emb, const int32_t *offsets, T *out
                uint32_t L, uint32_t max_level, float S, uint32_t H, T *dy_dx, uint32_t gridtype, bool ac,
                uint32_t interp, int layout, cudaStream_t st) {
     if (D == 3 && C == 2 && layout == NB200_LAYOUT_BLC && !dy_dx && L <= kMaxFastLevels) {
-        k_grid_fwd_d3c2<T, T><<<nb_div_up(B, 256), 256, 0, st>>>(inputs, emb, offsets, out, B, L, max_level, S, H, gridtype, ac, interp);
+        k_grid_fwd_d3c2<T, T><<<nb_div_up(B, 256), 256, 0, st>>>(inputs, emb, offsets, out, B, L, max_level, S, H, gridtype, ac, interp, InXform{0.0f, 0.0f, nullptr});
         return 0;
     }
     switch (D) {
@@ -546,8 +559,8 @@ int launch_bwd(const T *grad, const float *inputs, const int32_t *offsets, float
     int rc = 0;
     if (D == 3 && C == 2 && layout == NB200_LAYOUT_BLC && L <= kMaxFastLevels) {
         const uint32_t nblk = nb_div_up(B, 256);
-        if (agg) k_grid_bwd_d3c2<T, true><<<nblk, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, max_level, S, H, gridtype, ac, interp);
-        else k_grid_bwd_d3c2<T, false><<<nblk, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, max_level, S, H, gridtype, ac, interp);
+        if (agg) k_grid_bwd_d3c2<T, true><<<nblk, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, max_level, S, H, gridtype, ac, interp, InXform{0.0f, 0.0f, nullptr});
+        else k_grid_bwd_d3c2<T, false><<<nblk, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, max_level, S, H, gridtype, ac, interp, InXform{0.0f, 0.0f, nullptr});
     } else {
         switch (D) {
             case 2: rc = launch_bwd_c<T, 2>(grad, inputs, offsets, gg, B, C, L, max_level, S, H, gridtype, ac, interp, layout, st); break;
@@ -600,7 +613,7 @@ int nb200_grid_encode_forward(const float *inputs, const void *embeddings, const
         if (!(D == 3 && C == 2 && layout == NB200_LAYOUT_BLC && !dy_dx && L <= kMaxFastLevels)) return NB200_E_BAD_DTYPE;
         k_grid_fwd_d3c2<float, __half><<<nb_div_up(B, 256), 256, 0, nb_stream(stream)>>>(
             inputs, (const float *)embeddings, offsets, (__half *)outputs, B, L, max_level, S, H, gridtype,
-            align_corners != 0, interp);
+            align_corners != 0, interp, InXform{0.0f, 0.0f, nullptr});
         rc = 0;
     } else
         return NB200_E_BAD_DTYPE;
@@ -628,6 +641,32 @@ int nb200_grid_encode_backward(const void *grad, const float *inputs, const int3
     else
         return NB200_E_BAD_DTYPE;
     if (rc) return rc;
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+// fused train step (D = 3, C = 2): raw sample positions in [-bound, bound], fp32 master table rounded to fp16 per load,
+// fp16 [M, L*2] features / feature gradients, rows limited by a device-side count
+int nb200_fs_encode_forward(const float *xyz, float bound, const float *table, const int32_t *offsets, void *x_en,
+                            uint32_t M_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                            uint32_t interp, const int32_t *count_dev, void *stream) {
+    if (M_cap == 0 || L == 0) return 0;
+    if (!xyz || !table || !offsets || !x_en || L > kMaxFastLevels || !(bound > 0.0f)) return NB200_E_BAD_ARG;
+    const InXform xf{bound, 1.0f / (2.0f * bound), count_dev};
+    k_grid_fwd_d3c2<float, __half><<<nb_div_up(M_cap, 256), 256, 0, nb_stream(stream)>>>(
+        xyz, table, offsets, (__half *)x_en, M_cap, L, L, S, H, gridtype, align_corners != 0, interp, xf);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_fs_encode_backward(const void *d_x_en, const float *xyz, float bound, const int32_t *offsets, float *grad_table,
+                             uint32_t M_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                             uint32_t interp, const int32_t *count_dev, void *stream) {
+    if (M_cap == 0 || L == 0) return 0;
+    if (!d_x_en || !xyz || !offsets || !grad_table || L > kMaxFastLevels || !(bound > 0.0f)) return NB200_E_BAD_ARG;
+    const InXform xf{bound, 1.0f / (2.0f * bound), count_dev};
+    k_grid_bwd_d3c2<__half, true><<<nb_div_up(M_cap, 256), 256, 0, nb_stream(stream)>>>(
+        (const __half *)d_x_en, xyz, offsets, grad_table, M_cap, L, L, S, H, gridtype, align_corners != 0, interp, xf);
     NB_LAUNCH_CHECK();
     return 0;
 }

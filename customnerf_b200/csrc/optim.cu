@@ -1,0 +1,151 @@
+// optim.cu -- the table-wide passes of a train step, fused.
+//
+// The reference trains with torch.optim.Adam(betas=(0.9, 0.99), eps=1e-15) under a GradScaler (main.py:182,
+// nerf/utils_init_nerf.py:100,612-629): per step that is a zero-fill of every gradient (grid.py:83), an unscale
+// pass, an inf check with a D2H sync, and the Adam pass -- four sweeps over the 12.2 M-entry hash table
+// (~0.6 GB of traffic at BASELINE.json configs[1]).  Here it is ONE sweep: read p, g, m, v; write p, m, v and
+// g = 0 (32 B per parameter), with the loss-scale reciprocal folded into the gradient load.
+//
+// Arithmetic follows torch's fused Adam (aten/src/ATen/native/cuda/fused_adam_utils.cuh, non-amsgrad, no weight
+// decay): m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2; p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps).
+#include "common.cuh"
+
+namespace {
+
+struct AdamHyper {          // 8 floats per parameter group, written by the host before every step
+    float lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale, pad;
+};
+
+__device__ __forceinline__ void adam1(float &p, float &g, float &m, float &v, const AdamHyper &h) {
+    const float gr = g * h.grad_scale;
+    m = m + (1.0f - h.beta1) * (gr - m);                // torch lerp(m, g, w) for w < 0.5
+    v = h.beta2 * v + (1.0f - h.beta2) * gr * gr;
+    const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
+    p -= (h.lr / h.bc1) * m / denom;
+}
+
+// n4 = number of float4 groups; elements [0, split) use group 0, [split, n) group 1.  split % 4 == 0 is required
+// when vectorised (the launcher checks).
+__global__ void __launch_bounds__(256)
+k_fused_adam(float4 *__restrict__ param, float4 *__restrict__ grad, float4 *__restrict__ exp_avg,
+             float4 *__restrict__ exp_avg_sq, uint64_t n4, uint64_t split4, const AdamHyper *__restrict__ hyper,
+             int zero_grad) {
+    const AdamHyper h0 = hyper[0], h1 = hyper[1];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const AdamHyper &h = i < split4 ? h0 : h1;
+        float4 p = param[i], g = grad[i], m = exp_avg[i], v = exp_avg_sq[i];
+        adam1(p.x, g.x, m.x, v.x, h); adam1(p.y, g.y, m.y, v.y, h);
+        adam1(p.z, g.z, m.z, v.z, h); adam1(p.w, g.w, m.w, v.w, h);
+        param[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
+        if (zero_grad) grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_fused_adam_tail(float *__restrict__ param, float *__restrict__ grad, float *__restrict__ exp_avg,
+                  float *__restrict__ exp_avg_sq, uint64_t begin, uint64_t n, uint64_t split,
+                  const AdamHyper *__restrict__ hyper, int zero_grad) {
+    const uint64_t i = begin + threadIdx.x;
+    if (i >= n) return;
+    const AdamHyper h = hyper[i < split ? 0 : 1];
+    float p = param[i], g = grad[i], m = exp_avg[i], v = exp_avg_sq[i];
+    adam1(p, g, m, v, h);
+    param[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
+    if (zero_grad) grad[i] = 0.0f;
+}
+
+// Per-step hyper-parameters computed on the device so that a captured step never reads host memory that the host may
+// already have advanced: t = ++(*step); lr_g = lr0_g * decay_base^min((t-1)/decay_iters, 1)  (the LambdaLR of
+// main.py:189 evaluated before this optimiser step); bias corrections in double precision as torch computes them.
+// sched = {lr0 group 0, lr0 group 1, beta1, beta2, eps, grad_scale, decay_base, decay_iters}
+__global__ void k_adam_hyper(int32_t *__restrict__ step, const float *__restrict__ sched, AdamHyper *__restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int32_t t = *step + 1;
+    *step = t;
+    const double b1 = sched[2], b2 = sched[3];
+    double decay = 1.0;
+    if (sched[7] > 0.0f) decay = pow((double)sched[6], fmin((double)(t - 1) / (double)sched[7], 1.0));
+    const float bc1 = (float)(1.0 - pow(b1, (double)t)), bc2s = (float)sqrt(1.0 - pow(b2, (double)t));
+    for (int g = 0; g < 2; g++) {
+        AdamHyper h;
+        h.lr = (float)((double)sched[g] * decay);
+        h.beta1 = sched[2]; h.beta2 = sched[3]; h.eps = sched[4];
+        h.bc1 = bc1; h.bc2_sqrt = bc2s; h.grad_scale = sched[5]; h.pad = 0.0f;
+        out[g] = h;
+    }
+}
+
+// loss = sum (image - target)^2 * inv_n ; g_image = 2 (image - target) * inv_n * loss_scale     (one thread per ray)
+__global__ void __launch_bounds__(256)
+k_mse_loss_grad(const float *__restrict__ image, const float *__restrict__ target, uint32_t N, float inv_n,
+                float loss_scale, float *__restrict__ loss, float *__restrict__ g_image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.0f;
+    if (n < N) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float d = image[n * 3 + c] - target[n * 3 + c];
+            acc += d * d;
+            g_image[n * 3 + c] = 2.0f * d * inv_n * loss_scale;
+        }
+    }
+    acc = nb_warp_sum(acc);
+    __shared__ float part[8];
+    if (nb_lane() == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float v = part[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+        if (threadIdx.x == 0) atomicAdd(loss, v * inv_n);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int nb200_fused_adam(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, uint64_t split,
+                     const float *hyper, int zero_grad, void *stream) {
+    if (n == 0) return 0;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || split > n) return NB200_E_BAD_ARG;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+                         reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq);
+    if ((al & 15u) || (split & 3u)) return NB200_E_BAD_ARG;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t n4 = n / 4;
+    cudaStream_t st = nb_stream(stream);
+    if (n4) {
+        const uint32_t want = nb_div_up(n4, 256);
+        const uint32_t grid = want < (uint32_t)sms * 8 ? want : (uint32_t)sms * 8;
+        k_fused_adam<<<grid, 256, 0, st>>>((float4 *)param, (float4 *)grad, (float4 *)exp_avg, (float4 *)exp_avg_sq, n4,
+                                           split / 4, (const AdamHyper *)hyper, zero_grad);
+        NB_LAUNCH_CHECK();
+    }
+    if (n4 * 4 < n) {
+        k_fused_adam_tail<<<1, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n4 * 4, n, split, (const AdamHyper *)hyper,
+                                             zero_grad);
+        NB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int nb200_adam_hyper(int32_t *step, const float *sched, float *hyper, void *stream) {
+    if (!step || !sched || !hyper) return NB200_E_BAD_ARG;
+    k_adam_hyper<<<1, 32, 0, nb_stream(stream)>>>(step, sched, (AdamHyper *)hyper);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_mse_loss_grad(const float *image, const float *target, uint32_t N, float inv_n, float loss_scale, float *loss,
+                        float *g_image, void *stream) {
+    if (N == 0) return 0;
+    if (!image || !target || !loss || !g_image) return NB200_E_BAD_ARG;
+    k_mse_loss_grad<<<nb_div_up(N, 256), 256, 0, nb_stream(stream)>>>(image, target, N, inv_n, loss_scale, loss, g_image);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

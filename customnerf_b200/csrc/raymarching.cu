@@ -232,7 +232,7 @@ k_march_count(const float *__restrict__ rays_o, const float *__restrict__ rays_d
 // single block: exclusive scan of the block sums starting at counter[0]; counter += (sum, N)  (:405-406)
 __global__ void __launch_bounds__(1024)
 k_march_scan(const int32_t *__restrict__ block_sums, int32_t *__restrict__ block_prefix, uint32_t nb, uint32_t N,
-             int32_t *__restrict__ counter) {
+             int32_t *__restrict__ counter, uint32_t M_cap, int32_t *__restrict__ m_eff) {
     __shared__ int warp_tot[32];
     __shared__ int carry_s, chunk_total_s;
     if (threadIdx.x == 0) carry_s = counter[0];
@@ -259,6 +259,9 @@ k_march_scan(const int32_t *__restrict__ block_sums, int32_t *__restrict__ block
     if (threadIdx.x == 0) {
         counter[0] = carry_s;
         counter[1] += (int32_t)N;
+        // rows the downstream kernels of the fused step may touch: every segment below this row is complete
+        // (k_march_write lowers it to the offset of the first ray that does not fit in M_cap rows)
+        if (m_eff) *m_eff = (int32_t)min((uint32_t)max(carry_s, 0), M_cap);
     }
 }
 
@@ -274,13 +277,16 @@ k_march_write(const float *__restrict__ rays_o, const float *__restrict__ rays_d
               float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
               const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
               const int32_t *__restrict__ rays, float *__restrict__ xyzs, float *__restrict__ dirs,
-              float *__restrict__ deltas) {
+              float *__restrict__ deltas, int32_t *__restrict__ m_eff) {
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     if (n >= N) return;
     const uint32_t point_index = (uint32_t)rays[n * 3 + 1];
     const uint32_t num_steps = (uint32_t)rays[n * 3 + 2];
     if (num_steps == 0) return;
-    if (point_index + num_steps > M) return;
+    if (point_index + num_steps > M) {
+        if (m_eff) atomicMin(m_eff, (int32_t)min(point_index, M));
+        return;
+    }
     RayCtx r;
     rm_setup(r, rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H);
     const float far = fars[n];
@@ -323,8 +329,22 @@ __device__ __forceinline__ float warp_incl_sum(float p) {
 
 constexpr int kCompBlock = 256;   // 8 rays per block
 
+// colour of sample s: float [M,3] (the reference layout) or half [M,4] (rgb + mask, straight from the field kernel)
+template <typename TC>
+__device__ __forceinline__ void ld_rgb(const TC *__restrict__ rgbs, size_t s, float &c0, float &c1, float &c2) {
+    if constexpr (sizeof(TC) == 2) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(rgbs) + s);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
+        c0 = a.x; c1 = a.y; c2 = b.x;
+    } else {
+        c0 = __ldg(rgbs + s * 3); c1 = __ldg(rgbs + s * 3 + 1); c2 = __ldg(rgbs + s * 3 + 2);
+    }
+}
+
+template <typename TC>
 __global__ void __launch_bounds__(kCompBlock)
-k_composite_train_fwd(const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
+k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ rgbs, const float *__restrict__ deltas,
                       const int32_t *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
                       float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image) {
     const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
@@ -343,7 +363,7 @@ k_composite_train_fwd(const float *__restrict__ sigmas, const float *__restrict_
                 sigma = __ldg(sigmas + s);
                 const float2 dl = __ldg(reinterpret_cast<const float2 *>(deltas) + s);
                 d0 = dl.x; d1 = dl.y;
-                c0 = __ldg(rgbs + s * 3); c1 = __ldg(rgbs + s * 3 + 1); c2 = __ldg(rgbs + s * 3 + 2);
+                ld_rgb<TC>(rgbs, s, c0, c1, c2);
             }
             const float alpha = valid ? 1.0f - __expf(-sigma * d0) : 0.0f;
             const float pin = warp_incl_prod(1.0f - alpha);
@@ -370,9 +390,11 @@ k_composite_train_fwd(const float *__restrict__ sigmas, const float *__restrict_
     }
 }
 
+// GS = row stride of grad_rgbs: 3 (reference layout) or 4 (float4 rows [g_r, g_g, g_b, 0] for the field backward)
+template <typename TC, int GS>
 __global__ void __launch_bounds__(kCompBlock)
 k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *__restrict__ grad_image,
-                      const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
+                      const float *__restrict__ sigmas, const TC *__restrict__ rgbs, const float *__restrict__ deltas,
                       const int32_t *__restrict__ rays, const float *__restrict__ weights_sum,
                       const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
                       float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs) {
@@ -397,7 +419,7 @@ k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *_
             if (valid) {
                 sigma = __ldg(sigmas + s);
                 d0 = __ldg(deltas + s * 2);
-                c0 = __ldg(rgbs + s * 3); c1 = __ldg(rgbs + s * 3 + 1); c2 = __ldg(rgbs + s * 3 + 2);
+                ld_rgb<TC>(rgbs, s, c0, c1, c2);
             }
             const float alpha = valid ? 1.0f - __expf(-sigma * d0) : 0.0f;
             const float pin = warp_incl_prod(1.0f - alpha);
@@ -424,7 +446,11 @@ k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *_
         }
         if (valid) {   // rows after the early-out get explicit zeros (raymarching.py:284-285 zero-fills instead)
             grad_sigmas[s] = gs;
-            grad_rgbs[s * 3] = gr0; grad_rgbs[s * 3 + 1] = gr1; grad_rgbs[s * 3 + 2] = gr2;
+            if constexpr (GS == 4) {
+                reinterpret_cast<float4 *>(grad_rgbs)[s] = make_float4(gr0, gr1, gr2, 0.0f);
+            } else {
+                grad_rgbs[s * 3] = gr0; grad_rgbs[s * 3 + 1] = gr1; grad_rgbs[s * 3 + 2] = gr2;
+            }
         }
     }
 }
@@ -537,10 +563,11 @@ int nb200_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t 
 
 uint32_t nb200_march_scratch_ints(uint32_t N) { return 2 * nb_div_up(N, kMarchBlock) + 8; }
 
-int nb200_march_rays_train_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
-                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
-                                 const float *nears, const float *fars, const float *noises,
-                                 int32_t *rays, int32_t *counter, int32_t *scratch, void *stream) {
+static int march_count_impl(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                            const float *nears, const float *fars, const float *noises,
+                            int32_t *rays, int32_t *counter, int32_t *scratch, uint32_t M_cap, int32_t *m_eff,
+                            void *stream) {
     if (N == 0) return 0;
     if (!scratch || !rays || !counter) return NB200_E_BAD_ARG;
     const uint32_t nb = nb_div_up(N, kMarchBlock);
@@ -549,9 +576,41 @@ int nb200_march_rays_train_count(const float *rays_o, const float *rays_d, const
     k_march_count<<<nb, kMarchBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
                                               noises, rays, block_sums);
     NB_LAUNCH_CHECK();
-    k_march_scan<<<1, 1024, 0, st>>>(block_sums, block_prefix, nb, N, counter);
+    k_march_scan<<<1, 1024, 0, st>>>(block_sums, block_prefix, nb, N, counter, M_cap, m_eff);
     NB_LAUNCH_CHECK();
     k_march_fixup<<<nb_div_up(N, 256), 256, 0, st>>>(rays, block_prefix, N);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_march_rays_train_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                 const float *nears, const float *fars, const float *noises,
+                                 int32_t *rays, int32_t *counter, int32_t *scratch, void *stream) {
+    return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter,
+                            scratch, 0, nullptr, stream);
+}
+
+// fused train step: count + scan, then write, into buffers of M_cap rows; *m_eff = rows covered by complete segments
+int nb200_fs_march_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, const float *nears,
+                         const float *fars, const float *noises, int32_t *rays, int32_t *counter, int32_t *m_eff,
+                         int32_t *scratch, void *stream) {
+    if (N == 0) return 0;
+    if (!m_eff) return NB200_E_BAD_ARG;
+    return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays,
+                            counter, scratch, M_cap, m_eff, stream);
+}
+
+int nb200_fs_march_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, const float *nears,
+                         const float *fars, const float *noises, const int32_t *rays, float *xyzs, float *dirs,
+                         float *deltas, int32_t *m_eff, void *stream) {
+    if (N == 0) return 0;
+    if (!m_eff) return NB200_E_BAD_ARG;
+    k_march_write<<<nb_div_up(N, kMarchBlock), kMarchBlock, 0, nb_stream(stream)>>>(
+        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M_cap, nears, fars, noises, rays, xyzs, dirs, deltas,
+        m_eff);
     NB_LAUNCH_CHECK();
     return 0;
 }
@@ -562,7 +621,8 @@ int nb200_march_rays_train_write(const float *rays_o, const float *rays_d, const
                                  float *xyzs, float *dirs, float *deltas, void *stream) {
     if (N == 0) return 0;
     k_march_write<<<nb_div_up(N, kMarchBlock), kMarchBlock, 0, nb_stream(stream)>>>(
-        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, noises, rays, xyzs, dirs, deltas);
+        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, noises, rays, xyzs, dirs, deltas,
+        nullptr);
     NB_LAUNCH_CHECK();
     return 0;
 }
@@ -582,8 +642,31 @@ int nb200_composite_rays_train_forward(const float *sigmas, const float *rgbs, c
                                        uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth,
                                        float *image, void *stream) {
     if (N == 0) return 0;
-    k_composite_train_fwd<<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
+    k_composite_train_fwd<float><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
         sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+// fused train step: colours are the field kernel's half [M,4] rows; grad_rgba rows are float4 [g_r, g_g, g_b, 0]
+int nb200_fs_composite_forward(const float *sigmas, const void *rgba, const float *deltas, const int32_t *rays,
+                               uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image,
+                               void *stream) {
+    if (N == 0) return 0;
+    k_composite_train_fwd<__half><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
+        sigmas, (const __half *)rgba, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_fs_composite_backward(const float *grad_weights_sum, const float *grad_image, const float *sigmas,
+                                const void *rgba, const float *deltas, const int32_t *rays, const float *weights_sum,
+                                const float *image, uint32_t M, uint32_t N, float T_thresh, float *grad_sigmas,
+                                float *grad_rgba, void *stream) {
+    if (N == 0) return 0;
+    k_composite_train_bwd<__half, 4><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
+        grad_weights_sum, grad_image, sigmas, (const __half *)rgba, deltas, rays, weights_sum, image, M, N, T_thresh,
+        grad_sigmas, grad_rgba);
     NB_LAUNCH_CHECK();
     return 0;
 }
@@ -593,7 +676,7 @@ int nb200_composite_rays_train_backward(const float *grad_weights_sum, const flo
                                         const float *weights_sum, const float *image, uint32_t M, uint32_t N,
                                         float T_thresh, float *grad_sigmas, float *grad_rgbs, void *stream) {
     if (N == 0) return 0;
-    k_composite_train_bwd<<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
+    k_composite_train_bwd<float, 3><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
         grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas,
         grad_rgbs);
     NB_LAUNCH_CHECK();

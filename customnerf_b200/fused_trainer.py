@@ -1,0 +1,319 @@
+"""FusedTrainStep: the reconstruction train step of the occupancy (cuda_ray) path as ONE replayable CUDA graph.
+
+Same computation as ``trainer.TrainStep`` (the autograd composition of the drop-in ops, i.e. what
+``Trainer_Nerf.train_step_pretrain`` + ``train_one_epoch`` do around ``model.render``,
+nerf/utils_init_nerf.py:194-241, 599-629), restructured for the B200:
+
+  * no host synchronisation inside the step: the step's sample count stays on the device (the reference blocks on
+    ``counter[0].item()`` every step, raymarching/raymarching.py:225); buffers have a fixed capacity ``m_cap`` rows
+    and every kernel bounds its work by the device-side count;
+  * no autograd graph, no allocator traffic: fixed buffers, the backward kernels are called directly
+    (csrc/fused_step.cu: nb200_train_forward_backward / nb200_train_update);
+  * one flat fp32 vector holds [hash table | trunk | density head | colour head]; the module's Parameters are views
+    into it, so state-dict names are unchanged and the gradient all-reduce of the ray-sharded
+    multi-GPU step is a single NCCL call on ``grads_flat``;
+  * zero-grad + unscale + Adam are one pass over that vector (csrc/optim.cu) with the reference's hyper-parameters
+    (Adam betas (0.9, 0.99), eps 1e-15, table at 10x LR: main.py:182, network_grid.py:196-206);
+  * the whole sequence is captured once and replayed; per-step scalars (step count, learning rate, bias corrections)
+    are computed on the device, so a replay reads no host memory.
+
+Capacity: rays whose samples do not fit in ``m_cap`` rows are dropped for that step exactly as the reference drops
+them when its ``mean_count`` budget overflows (raymarching.cu:415-416).  ``last_stats()`` returns the step's true
+sample count; ``step()`` grows the buffers (and re-captures) when a step overflowed, so at most one step per growth
+sees dropped rays.  The default capacity is 1.25x the count measured on the first batch.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+LOSS_SCALE = 128.0
+# this library's kernels in one step: near/far, march count + scan + fixup + write, encode, field, composite, loss,
+# composite^T, field^T, encode^T, adam hyper, adam, weight pack x2
+KERNELS_PER_STEP = 16
+STAGES = ["near_far_from_aabb", "march_count", "march_write", "grid_encode_forward", "field_forward",
+          "composite_forward", "mse_loss", "composite_backward", "field_backward", "grid_encode_backward",
+          "adam", "pack_weights"]
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed: %s (code %d)" % (what, L.lib().nb200_error_string(C.c_int(rc)).decode(), rc))
+
+
+class TrainPlan(C.Structure):
+    """mirror of nb200_train_plan (include/nerf_b200.h)"""
+    _u32 = ["N", "M_cap", "C", "H", "L", "base_res", "gridtype", "max_steps"]
+    _f32 = ["bound", "dt_gamma", "S", "T_thresh", "min_near", "loss_scale", "inv_n_total", "pad0"]
+    _u64 = ["n_params", "n_table_params"]
+    _ptr = ["rays_o", "rays_d", "target", "aabb", "noises", "bitfield",
+            "params_flat", "grads_flat", "exp_avg", "exp_avg_sq", "hyper", "sched", "step",
+            "table", "trunk", "density", "rgb", "offsets",
+            "g_table", "g_trunk", "g_density", "g_rgb", "w_fwd", "w_bwd",
+            "nears", "fars", "weights_sum", "depth", "image", "g_weights_sum", "g_image", "loss",
+            "rays", "counter", "m_eff", "scratch",
+            "xyzs", "dirs", "deltas", "sigma", "sigma_arg", "d_sigma", "d_rgba",
+            "x_en", "rgba", "act", "d_x_en", "timer"]
+    _fields_ = ([(n, C.c_uint32) for n in _u32] + [(n, C.c_float) for n in _f32] + [(n, C.c_uint64) for n in _u64] +
+                [(n, C.c_void_p) for n in _ptr])
+
+
+def flatten_parameters(model):
+    """Move the four parameter tensors of ``model`` (NeRFNetwork) into one flat fp32 vector
+    [table | trunk | density | rgb]; the Parameters become views.  Returns (flat, [(name, offset, numel)])."""
+    named = [("pos_en.embeddings", model.pos_en.embeddings), ("network.params", model.network.params),
+             ("density_network.params", model.density_network.params), ("rgb_network.params", model.rgb_network.params)]
+    total = sum(p.numel() for _, p in named)
+    dev = named[0][1].device
+    flat = torch.empty(total, dtype=torch.float32, device=dev)
+    layout, off = [], 0
+    for name, p in named:
+        n = p.numel()
+        if n % 4:
+            raise RuntimeError("parameter %s: numel %d is not a multiple of 4" % (name, n))
+        flat[off:off + n].copy_(p.detach().reshape(-1))
+        p.data = flat[off:off + n].view(p.shape)
+        layout.append((name, off, n))
+        off += n
+    return flat, layout
+
+
+class FusedTrainStep:
+    def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
+                 betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
+                 lr_decay_iters=0):
+        if not model.cuda_ray:
+            raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
+        if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
+            raise RuntimeError("FusedTrainStep needs the reference field shape (D=3, 16 levels x 2 features)")
+        self.model = model
+        self.lib = L.lib()
+        self.dev = model.pos_en.embeddings.device
+        self.N = int(n_rays)
+        self.lr = float(lr)
+        self.betas, self.eps = betas, float(eps)
+        self.world_size = world_size
+        self.grad_sync = grad_sync          # callable(flat fp32 grad tensor) -> None (sums across ranks in place)
+        self.use_graph = use_graph
+        self.perturb = perturb
+        self.T_thresh, self.dt_gamma, self.max_steps = float(T_thresh), float(dt_gamma), int(max_steps)
+        self.graph = None
+        self.overflows = 0
+        model.train()
+
+        dev = self.dev
+        self.params_flat, self.layout = flatten_parameters(model)
+        self.grads_flat = torch.zeros_like(self.params_flat)
+        self.exp_avg = torch.zeros_like(self.params_flat)
+        self.exp_avg_sq = torch.zeros_like(self.params_flat)
+        self.hyper = torch.zeros(16, dtype=torch.float32, device=dev)
+        # {lr0 table (10x, network_grid.py:199), lr0 MLPs, beta1, beta2, eps, 1/loss_scale, LambdaLR base, iters (main.py:189)}
+        self.sched = torch.tensor([self.lr * 10.0, self.lr, betas[0], betas[1], self.eps, 1.0 / LOSS_SCALE,
+                                   float(lr_decay_base), float(lr_decay_iters)], dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        nb = int(self.lib.nb200_field_weight_image_bytes())
+        self.w_fwd = torch.empty(nb, dtype=torch.uint8, device=dev)
+        self.w_bwd = torch.empty(nb, dtype=torch.uint8, device=dev)
+
+        N = self.N
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.rays_o = torch.zeros(N, 3, **f32)
+        self.rays_d = torch.zeros(N, 3, **f32)
+        self.target = torch.zeros(N, 3, **f32)
+        self.noises = torch.zeros(N, **f32)
+        self.nears, self.fars = torch.empty(N, **f32), torch.empty(N, **f32)
+        self.weights_sum, self.depth = torch.empty(N, **f32), torch.empty(N, **f32)
+        self.image, self.g_image = torch.empty(N, 3, **f32), torch.empty(N, 3, **f32)
+        self.g_weights_sum = torch.zeros(N, **f32)
+        self.rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+        self.scratch = torch.empty(int(self.lib.nb200_march_scratch_ints(L.u32(N))), dtype=torch.int32, device=dev)
+        # [counter0, counter1, m_eff, loss bits]: one 16-byte D2H returns everything the host wants to know
+        self.stats = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.stats_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.n_total = N * world_size
+        self._pack()
+        self.m_cap = 0
+        self._alloc_samples(int(m_cap) if m_cap else 0)
+
+    # ------------------------------------------------------------------------------------------ setup
+    def _pack(self):
+        m = self.model
+        with torch.cuda.device(self.dev):
+            L.check(self.lib.nb200_field_pack_weights(L.ptr(m.network.params.detach()), L.ptr(m.density_network.params.detach()),
+                                                      L.ptr(m.rgb_network.params.detach()), L.ptr(self.w_fwd),
+                                                      L.ptr(self.w_bwd), L.stream()), "field_pack_weights")
+
+    def _alloc_samples(self, m_cap):
+        dev = self.dev
+        self.graph = None
+        self.m_cap = m_cap
+        if m_cap == 0:
+            return
+        f32 = dict(dtype=torch.float32, device=dev)
+        f16 = dict(dtype=torch.float16, device=dev)
+        M = m_cap
+        self.xyzs, self.dirs, self.deltas = torch.zeros(M, 3, **f32), torch.zeros(M, 3, **f32), torch.zeros(M, 2, **f32)
+        self.sigma, self.sigma_arg, self.d_sigma = torch.zeros(M, **f32), torch.zeros(M, **f32), torch.zeros(M, **f32)
+        self.d_rgba = torch.zeros(M, 4, **f32)
+        self.x_en, self.d_x_en = torch.zeros(M, 32, **f16), torch.zeros(M, 32, **f16)
+        self.rgba = torch.zeros(M, 4, **f16)
+        self.act = torch.zeros(5, M, 64, **f16)
+        self._fill_plan()
+
+    def _fill_plan(self):
+        m, enc = self.model, self.model.pos_en
+        p = TrainPlan()
+        p.N, p.M_cap, p.C, p.H = self.N, self.m_cap, m.cascade, m.grid_size
+        p.L, p.base_res, p.gridtype, p.max_steps = enc.num_levels, int(enc.base_resolution), enc.gridtype_id, self.max_steps
+        p.bound, p.dt_gamma = float(m.bound), self.dt_gamma
+        p.S = float(np.log2(enc.per_level_scale))
+        p.T_thresh, p.min_near = self.T_thresh, 0.2          # run_cuda leaves min_near at its default (Appendix B5)
+        p.loss_scale, p.inv_n_total = LOSS_SCALE, 1.0 / (3.0 * self.n_total)
+        p.n_params, p.n_table_params = self.params_flat.numel(), self.layout[0][2]
+
+        def a(t):
+            return None if t is None else t.data_ptr()
+        p.rays_o, p.rays_d, p.target, p.aabb = a(self.rays_o), a(self.rays_d), a(self.target), a(m.aabb_train)
+        p.noises = a(self.noises) if self.perturb else None
+        p.bitfield = a(m.density_bitfield)
+        p.params_flat, p.grads_flat, p.exp_avg, p.exp_avg_sq = a(self.params_flat), a(self.grads_flat), a(self.exp_avg), a(self.exp_avg_sq)
+        p.hyper, p.sched, p.step = a(self.hyper), a(self.sched), a(self.step_count)
+        es = 4
+        base, gbase = self.params_flat.data_ptr(), self.grads_flat.data_ptr()
+        offs = {name: off for name, off, _ in self.layout}
+        p.table, p.g_table = base + es * offs["pos_en.embeddings"], gbase + es * offs["pos_en.embeddings"]
+        p.trunk, p.g_trunk = base + es * offs["network.params"], gbase + es * offs["network.params"]
+        p.density, p.g_density = base + es * offs["density_network.params"], gbase + es * offs["density_network.params"]
+        p.rgb, p.g_rgb = base + es * offs["rgb_network.params"], gbase + es * offs["rgb_network.params"]
+        p.offsets = a(enc.offsets)
+        p.w_fwd, p.w_bwd = a(self.w_fwd), a(self.w_bwd)
+        p.nears, p.fars, p.weights_sum, p.depth, p.image = a(self.nears), a(self.fars), a(self.weights_sum), a(self.depth), a(self.image)
+        p.g_weights_sum, p.g_image = a(self.g_weights_sum), a(self.g_image)
+        sp = self.stats.data_ptr()
+        p.counter, p.m_eff, p.loss = sp, sp + 8, sp + 12
+        p.rays, p.scratch = a(self.rays), a(self.scratch)
+        p.xyzs, p.dirs, p.deltas = a(self.xyzs), a(self.dirs), a(self.deltas)
+        p.sigma, p.sigma_arg, p.d_sigma, p.d_rgba = a(self.sigma), a(self.sigma_arg), a(self.d_sigma), a(self.d_rgba)
+        p.x_en, p.rgba, p.act, p.d_x_en = a(self.x_en), a(self.rgba), a(self.act), a(self.d_x_en)
+        assert C.sizeof(p) == int(self.lib.nb200_train_plan_bytes()), "nb200_train_plan layout mismatch"
+        self.plan = p
+
+    def measure_samples(self, rays_o, rays_d):
+        """Samples the occupancy grid yields for this ray batch (one synchronous count pass; used to size m_cap)."""
+        from . import raymarching as rm
+        m = self.model
+        o, d = rays_o.to(self.dev).float().contiguous(), rays_d.to(self.dev).float().contiguous()
+        nears, fars = rm.near_far_from_aabb(o, d, m.aabb_train)
+        counter = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        rays = torch.empty(o.shape[0], 3, dtype=torch.int32, device=self.dev)
+        L.check(self.lib.nb200_march_rays_train_count(
+            L.ptr(o), L.ptr(d), L.ptr(m.density_bitfield), L.f32(m.bound), L.f32(self.dt_gamma), L.u32(self.max_steps),
+            L.u32(o.shape[0]), L.u32(m.cascade), L.u32(m.grid_size), L.ptr(nears), L.ptr(fars), L.ptr(None), L.ptr(rays),
+            L.ptr(counter), L.ptr(self.scratch), L.stream()), "count")
+        return int(counter[0].item())
+
+    @staticmethod
+    def _round_cap(samples):
+        return max(4096, int(math.ceil(samples * 1.25 / 4096.0)) * 4096)
+
+    # ------------------------------------------------------------------------------------------ the step
+    def _launch(self):
+        """every device-side action of one step, on the current stream (this is what the graph captures)"""
+        st = L.stream()
+        if self.perturb:
+            self.noises.uniform_()
+        _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), st), "train_forward_backward")
+        if self.grad_sync is not None:
+            self.grad_sync(self.grads_flat)
+        _check(self.lib.nb200_train_update(C.byref(self.plan), st), "train_update")
+        self.stats_host.copy_(self.stats, non_blocking=True)
+
+    def _capture(self):
+        """warm up on a side stream (first-call cudaFuncSetAttribute, allocator, RNG registration), capture one step,
+        then restore the optimiser state the warm-up steps advanced"""
+        state = (self.params_flat, self.exp_avg, self.exp_avg_sq, self.step_count)
+        keep = [t.clone() for t in state]
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._launch()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        # thread_local: NCCL's watchdog thread may touch the CUDA API while the all-reduce of a sharded step is captured
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self._launch()
+        for t, k in zip(state, keep):
+            t.copy_(k)
+        self.grads_flat.zero_()
+        self._pack()
+        self.graph = g
+
+    def forward_backward(self):
+        """forward + backward only, not captured (tests): gradients accumulate into ``grads_flat``"""
+        with torch.cuda.device(self.dev):
+            if self.perturb:
+                self.noises.uniform_()
+            _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
+            self.stats_host.copy_(self.stats, non_blocking=True)
+
+    def profile_stages(self, n_steps=10, flush=None):
+        """Device time of every stage of ``n_steps`` real (non-captured) train steps, measured with CUDA events recorded
+        between the stages on the launching stream.  Returns {stage: mean microseconds}.  ``flush``: optional callable
+        run before each step (e.g. an L2-flushing memset)."""
+        timer = C.c_void_p()
+        _check(self.lib.nb200_stage_timer_create(C.byref(timer)), "stage_timer_create")
+        out = (C.c_float * len(STAGES))()
+        acc = np.zeros(len(STAGES))
+        try:
+            self.plan.timer = timer.value
+            with torch.cuda.device(self.dev):
+                for _ in range(n_steps):
+                    if flush is not None:
+                        flush()
+                    self._launch()
+                    L.LAUNCHES += KERNELS_PER_STEP
+                    _check(self.lib.nb200_stage_timer_read(timer, out), "stage_timer_read")
+                    acc += np.array(list(out))
+        finally:
+            self.plan.timer = None
+            self.lib.nb200_stage_timer_destroy(timer)
+        return {k: float(v / n_steps) for k, v in zip(STAGES, acc)}
+
+    def set_batch(self, rays_o, rays_d, target):
+        """copy one ray batch (host -- ideally pinned -- or device tensors) into the step's static input buffers"""
+        self.rays_o.copy_(rays_o.reshape(-1, 3), non_blocking=True)
+        self.rays_d.copy_(rays_d.reshape(-1, 3), non_blocking=True)
+        self.target.copy_(target.reshape(-1, 3), non_blocking=True)
+
+    def step(self, rays_o=None, rays_d=None, target=None):
+        """One train step on the current stream.  Never synchronises; ``last_stats()`` reads the result back."""
+        with torch.cuda.device(self.dev):
+            if self.m_cap == 0:
+                self._alloc_samples(self._round_cap(self.measure_samples(rays_o if rays_o is not None else self.rays_o,
+                                                                         rays_d if rays_d is not None else self.rays_d)))
+            if rays_o is not None:
+                self.set_batch(rays_o, rays_d, target)
+            if self.use_graph:
+                if self.graph is None:
+                    self._capture()
+                self.graph.replay()
+            else:
+                self._launch()
+            L.LAUNCHES += KERNELS_PER_STEP
+
+    def last_stats(self):
+        """(loss, samples, rows_used) of the most recent step -- synchronises with the device.  Grows the sample
+        buffers (and drops the captured graph) when that step overflowed ``m_cap``."""
+        torch.cuda.current_stream(self.dev).synchronize()
+        s = self.stats_host
+        loss = float(s[3:4].view(torch.float32)[0])
+        samples, used = int(s[0]), int(s[2])
+        if samples > self.m_cap:
+            self.overflows += 1
+            self._alloc_samples(self._round_cap(samples))
+        return loss, samples, used

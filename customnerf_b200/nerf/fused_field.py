@@ -43,7 +43,8 @@ class _FusedField(Function):
         sigma_arg = torch.empty(M, dtype=torch.float32, device=dev) if save else None
         act = torch.empty(5, M, 64, dtype=torch.half, device=dev) if save else None
         L.check(L.lib().nb200_field_forward(L.ptr(x_en), L.ptr(xyz), L.ptr(dirs), L.ptr(fwd_img), L.ptr(sigma),
-                                            L.ptr(sigma_arg), L.ptr(rgba), L.ptr(act), L.u32(M), L.stream()),
+                                            L.ptr(sigma_arg), L.ptr(rgba), L.ptr(act), L.u32(M), L.ptr(None),
+                                            L.stream()),
                 "field_forward")
         if save:
             ctx.save_for_backward(x_en, dirs, sigma_arg, rgba, act, bwd_img)
@@ -64,7 +65,8 @@ class _FusedField(Function):
         d_x_en = torch.empty(M, 32, dtype=torch.half, device=dev)
         L.check(L.lib().nb200_field_backward(L.ptr(d_sigma), L.ptr(d_rgba), L.ptr(sigma_arg), L.ptr(rgba), L.ptr(x_en),
                                              L.ptr(dirs), L.ptr(act), L.ptr(bwd_img), L.ptr(d_x_en), L.ptr(g_trunk),
-                                             L.ptr(g_density), L.ptr(g_rgb), L.u32(M), L.stream()), "field_backward")
+                                             L.ptr(g_density), L.ptr(g_rgb), L.u32(M), L.ptr(None), L.stream()),
+                "field_backward")
         return d_x_en, None, None, g_trunk, g_density, g_rgb, None, None
 
 

@@ -40,9 +40,10 @@ def build_scene_model(device, log2_hashmap_size=19, desired_resolution=2048, enc
 
 
 class TrainStep:
-    def __init__(self, model, lr=5e-4, fp16=True, world_size=1, grad_sync=None):
+    def __init__(self, model, lr=5e-4, fp16=True, world_size=1, grad_sync=None, perturb=True):
         self.model = model
         self.fp16 = fp16
+        self.perturb = perturb
         self.world_size = world_size
         self.grad_sync = grad_sync            # callable(list of params) -> None, sums gradients across ranks
         self.optimizer = torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True)
@@ -55,7 +56,7 @@ class TrainStep:
         for p in self.params:
             p.grad = None
         with torch.autocast('cuda', dtype=torch.float16, enabled=self.fp16):
-            out = model.render(rays_o[None], rays_d[None], staged=False, perturb=True, force_all_rays=True,
+            out = model.render(rays_o[None], rays_d[None], staged=False, perturb=self.perturb, force_all_rays=True,
                                **vars(model.opt))
             pred = out['image'].reshape(-1, 3)
             n_local = pred.shape[0]

@@ -159,16 +159,115 @@ uint32_t nb200_field_weight_image_bytes(void);
 int nb200_field_pack_weights(const float *trunk, const float *density, const float *rgb, void *fwd_img, void *bwd_img,
                              void *stream);
 /* x_en f16 [M,32] (grid encoding), xyz f32 [M,3], dirs f32 [M,3] -> sigma f32 [M], rgba f16 [M,4].
- * Optional (training): sigma_arg f32 [M] (argument of trunc_exp) and act f16 [5,M,64] (h1, h2, fea, hd, hr). */
+ * Optional (training): sigma_arg f32 [M] (argument of trunc_exp) and act f16 [5,M,64] (h1, h2, fea, hd, hr).
+ * count_dev (device i32, may be NULL): when given only rows < min(M, *count_dev) are evaluated. */
 int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, const void *fwd_img, float *sigma,
-                        float *sigma_arg, void *rgba, void *act, uint32_t M, void *stream);
+                        float *sigma_arg, void *rgba, void *act, uint32_t M, const int32_t *count_dev, void *stream);
 
 /* Backward of nb200_field_forward.  d_sigma f32 [M], d_rgba f32 [M,4] are the upstream gradients; sigma_arg, rgba, act
  * are what the forward saved.  Writes d_x_en f16 [M,32] (gradient of the grid encoding, input of
  * nb200_grid_encode_backward) and ACCUMULATES the three flat fp32 parameter gradients (tcnn layout). */
 int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,
                          const void *x_en, const float *dirs, const void *act, const void *bwd_img, void *d_x_en,
-                         float *g_trunk, float *g_density, float *g_rgb, uint32_t M, void *stream);
+                         float *g_trunk, float *g_density, float *g_rgb, uint32_t M, const int32_t *count_dev,
+                         void *stream);
+
+/* ============================================================================================
+ * fused train step (no single reference counterpart: replaces the Python glue between the ops --
+ * NeRFRenderer.run_cuda nerf/renderer.py:597-650, NeRFNetwork.forward nerf/network_grid.py:159-177, the autograd
+ * Functions of gridencoder/grid.py:27-95 and raymarching/raymarching.py:239-292, and the loss / GradScaler / Adam
+ * sequence of nerf/utils_init_nerf.py:224-234,612-629).  No host synchronisation, no allocation: capturable in a
+ * CUDA graph.  The nb200_fs_* entry points are the individual stages; nb200_train_* run them from a plan.
+ * ========================================================================================== */
+
+/* count + scan (nb200_march_rays_train_count) and write (nb200_march_rays_train_write) into buffers of M_cap rows.
+ * counter[0] += total samples, counter[1] += N as the reference; *m_eff (device i32) = number of leading rows covered
+ * by complete ray segments (= min(total, offset of the first ray that does not fit)): the row bound of every later
+ * stage.  _count initialises it, _write lowers it. */
+int nb200_fs_march_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, const float *nears,
+                         const float *fars, const float *noises, int32_t *rays, int32_t *counter, int32_t *m_eff,
+                         int32_t *scratch, void *stream);
+int nb200_fs_march_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, const float *nears,
+                         const float *fars, const float *noises, const int32_t *rays, float *xyzs, float *dirs,
+                         float *deltas, int32_t *m_eff, void *stream);
+/* grid encode of raw positions xyz in [-bound, bound] (GridEncoder.forward's normalisation grid.py:156 fused in),
+ * D = 3, C = 2, fp32 master table rounded to fp16 per load (autocast semantics of grid.py:45-46), x_en f16 [M_cap, 2L]. */
+int nb200_fs_encode_forward(const float *xyz, float bound, const float *table, const int32_t *offsets, void *x_en,
+                            uint32_t M_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                            uint32_t interp, const int32_t *count_dev, void *stream);
+/* scatter of d_x_en f16 [M_cap, 2L] into grad_table f32 [rows, 2] (accumulated; warp-aggregated fp32 atomics). */
+int nb200_fs_encode_backward(const void *d_x_en, const float *xyz, float bound, const int32_t *offsets, float *grad_table,
+                             uint32_t M_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                             uint32_t interp, const int32_t *count_dev, void *stream);
+/* composite_rays_train forward / backward reading the field kernel's rgba f16 [M,4] rows directly (the reference
+ * slices [..., :3] and casts to float, renderer.py:510,635) and writing grad_rgba as float4 rows [g_r, g_g, g_b, 0]. */
+int nb200_fs_composite_forward(const float *sigmas, const void *rgba, const float *deltas, const int32_t *rays,
+                               uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image,
+                               void *stream);
+int nb200_fs_composite_backward(const float *grad_weights_sum, const float *grad_image, const float *sigmas,
+                                const void *rgba, const float *deltas, const int32_t *rays, const float *weights_sum,
+                                const float *image, uint32_t M, uint32_t N, float T_thresh, float *grad_sigmas,
+                                float *grad_rgba, void *stream);
+/* loss[0] += sum((image - target)^2) * inv_n ;  g_image = 2 (image - target) * inv_n * loss_scale.
+ * (F.mse_loss of utils_init_nerf.py:224 with inv_n = 1 / (3 * N_total), and its gradient times the loss scale.) */
+int nb200_mse_loss_grad(const float *image, const float *target, uint32_t N, float inv_n, float loss_scale, float *loss,
+                        float *g_image, void *stream);
+/* One pass of Adam over a flat fp32 parameter vector with two hyper-parameter groups (elements [0, split) and
+ * [split, n)): gradient unscale, moment update, parameter update and (zero_grad) gradient reset, 32 B per parameter.
+ * hyper: device f32 [2][8] = {lr, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale, 0} per group.
+ * Same arithmetic as torch.optim.Adam (main.py:182).  All pointers 16-byte aligned, split % 4 == 0. */
+int nb200_fused_adam(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, uint64_t split,
+                     const float *hyper, int zero_grad, void *stream);
+
+/* t = ++(*step) and the two hyper groups for optimiser step t, computed on the device (so a replayed graph never
+ * depends on host memory): sched f32[8] = {lr0 group 0, lr0 group 1, beta1, beta2, eps, grad_scale, decay_base,
+ * decay_iters}; lr = lr0 * decay_base^min((t-1)/decay_iters, 1) (LambdaLR of main.py:189; decay_iters <= 0: constant). */
+int nb200_adam_hyper(int32_t *step, const float *sched, float *hyper, void *stream);
+
+typedef struct nb200_train_plan {
+    /* sizes and scalars */
+    uint32_t N, M_cap, C, H, L, base_res, gridtype, max_steps;
+    float bound, dt_gamma, S, T_thresh, min_near, loss_scale, inv_n_total, pad0;
+    uint64_t n_params, n_table_params;
+    /* inputs (device) */
+    const float *rays_o, *rays_d, *target, *aabb, *noises;      /* noises may be NULL (perturb off) */
+    const uint8_t *bitfield;
+    /* parameters: one flat fp32 vector [table | trunk | density | rgb]; the four pointers below alias into it */
+    float *params_flat, *grads_flat, *exp_avg, *exp_avg_sq;
+    float *hyper;                                                /* f32 [16], rewritten by every nb200_train_update */
+    const float *sched;                                          /* f32 [8], see nb200_adam_hyper */
+    int32_t *step;                                               /* optimiser step count (device) */
+    const float *table, *trunk, *density, *rgb;
+    const int32_t *offsets;
+    float *g_table, *g_trunk, *g_density, *g_rgb;
+    void *w_fwd, *w_bwd;                                         /* packed fp16 operand images of the MLP weights */
+    /* per-ray work buffers [N ...] */
+    float *nears, *fars, *weights_sum, *depth, *image, *g_weights_sum, *g_image, *loss;
+    int32_t *rays, *counter, *m_eff, *scratch;
+    /* per-sample work buffers [M_cap ...] */
+    float *xyzs, *dirs, *deltas, *sigma, *sigma_arg, *d_sigma, *d_rgba;
+    void *x_en, *rgba, *act, *d_x_en;
+    void *timer;                                                 /* nb200_stage_timer or NULL */
+} nb200_train_plan;
+
+/* Per-stage device timing of a (non-captured) step: when plan->timer is set, nb200_train_forward_backward records an
+ * event before its first kernel and after each of its NB200_FB_STAGES stages, nb200_train_update after each of its
+ * NB200_UP_STAGES stages.  nb200_stage_timer_read synchronises on the last event and returns the stage durations in
+ * microseconds: out_us[NB200_FB_STAGES + NB200_UP_STAGES] (host memory). */
+#define NB200_FB_STAGES 10   /* near_far, march_count, march_write, encode, field, composite, loss, composite^T, field^T, encode^T */
+#define NB200_UP_STAGES 2    /* adam (hyper + sweep), weight pack */
+int nb200_stage_timer_create(void **timer);
+int nb200_stage_timer_destroy(void *timer);
+int nb200_stage_timer_read(void *timer, float *out_us);
+
+uint32_t nb200_train_plan_bytes(void);
+/* near/far -> march -> encode -> field -> composite -> MSE -> composite^T -> field^T -> encode^T (gradients
+ * accumulated into grads_flat).  Resets counter and loss first. */
+int nb200_train_forward_backward(const nb200_train_plan *plan, void *stream);
+/* fused Adam over params_flat (zeroing grads_flat) and re-pack of the MLP operand images. */
+int nb200_train_update(const nb200_train_plan *plan, void *stream);
 
 /* ============================================================================================
  * tensor-core path self test (no reference counterpart): one-CTA tcgen05 GEMM D[128,N] = A[128,K] * B[N,K]^T with

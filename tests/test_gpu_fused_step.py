@@ -1,0 +1,137 @@
+"""-m gpu: the fused, graph-captured train step (customnerf_b200/fused_trainer.py, csrc/fused_step.cu, csrc/optim.cu)
+against the autograd composition of the drop-in ops (trainer.TrainStep) and against torch.optim.Adam.
+
+Tolerances: gradients come out of the same kernels in both paths (fp16 activations, fp32 atomics whose order differs
+run to run), so loss rel 1e-5, gradients rel 1e-2 of the largest entry (SURVEY.md Appendix D, fp16 grid grads).
+The Adam kernel is compared with torch.optim.Adam on identical gradients: rel 1e-5.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+N_RAYS = 2048
+
+
+def _models():
+    from customnerf_b200 import trainer
+    a = trainer.build_scene_model(torch.device("cuda"), log2_hashmap_size=15, desired_resolution=512, seed=3)
+    b = trainer.build_scene_model(torch.device("cuda"), log2_hashmap_size=15, desired_resolution=512, seed=3)
+    with torch.no_grad():
+        a.pos_en.embeddings.uniform_(-0.5, 0.5)
+        b.pos_en.embeddings.copy_(a.pos_en.embeddings)
+    return a, b
+
+
+def _batch():
+    from customnerf_b200 import synthetic as syn
+    o, d = syn.camera_rays(105, 142)
+    sel = torch.arange(5000, 5000 + N_RAYS)
+    o, d = o[sel].contiguous(), d[sel].contiguous()
+    return o.cuda(), d.cuda(), syn.bear_color(o + d * 1.5).cuda()
+
+
+def test_forward_backward_matches_autograd_path():
+    from customnerf_b200 import trainer, fused_trainer
+    ma, mb = _models()
+    o, d, tgt = _batch()
+    ref = trainer.TrainStep(ma, perturb=False)
+    loss_ref = ref.forward_backward(o, d, tgt)
+    fs = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False, use_graph=False)
+    fs.m_cap or fs._alloc_samples(fs._round_cap(fs.measure_samples(o, d)))
+    fs.set_batch(o, d, tgt)
+    fs.forward_backward()
+    loss, samples, used = fs.last_stats()
+    assert samples == used == int(ma.step_counter[0, 0]) > 1000
+    assert abs(loss - float(loss_ref)) <= 1e-5 * abs(float(loss_ref)) + 1e-7
+    for name, off, n in fs.layout:
+        mod, attr = name.split(".")
+        g_ref = getattr(getattr(ma, mod), attr).grad.reshape(-1).float().cpu().numpy()
+        g = fs.grads_flat[off:off + n].cpu().numpy()
+        scale = np.abs(g_ref).max()
+        assert scale > 0
+        assert np.abs(g - g_ref).max() <= 1e-2 * scale, (name, np.abs(g - g_ref).max(), scale)
+
+
+def test_capacity_overflow_drops_whole_rays_and_recovers():
+    from customnerf_b200 import fused_trainer
+    _, mb = _models()
+    o, d, tgt = _batch()
+    fs = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False, use_graph=False, m_cap=4096)
+    fs.set_batch(o, d, tgt)
+    fs.forward_backward()
+    torch.cuda.synchronize()
+    rays = fs.rays.cpu().numpy()
+    loss, samples, used = fs.last_stats()          # grows the buffers
+    assert samples > 4096 and used <= 4096 and np.isfinite(loss)
+    fits = rays[:, 1] + rays[:, 2] <= 4096
+    assert used == (rays[fits, 1] + rays[fits, 2]).max()      # complete segments only
+    assert fs.m_cap >= samples and fs.overflows == 1
+    fs.grads_flat.zero_()
+    fs.set_batch(o, d, tgt)
+    fs.forward_backward()
+    _, samples2, used2 = fs.last_stats()
+    assert samples2 == used2 == samples
+
+
+def test_fused_adam_matches_torch_adam():
+    from customnerf_b200 import _lib as L
+    lib = L.lib()
+    torch.manual_seed(0)
+    n, split = 40000 + 8, 30000
+    p0 = torch.randn(n, device="cuda")
+    p = p0.clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    ref_a = torch.nn.Parameter(p0[:split].clone())
+    ref_b = torch.nn.Parameter(p0[split:].clone())
+    opt = torch.optim.Adam([{"params": [ref_a], "lr": 5e-3}, {"params": [ref_b], "lr": 5e-4}], betas=(0.9, 0.99), eps=1e-15)
+    sched = torch.tensor([5e-3, 5e-4, 0.9, 0.99, 1e-15, 1.0 / 128.0, 0.1, 100.0], device="cuda")
+    lam = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 0.1 ** min(it / 100.0, 1))
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    hyper = torch.zeros(16, device="cuda")
+    for it in range(5):
+        g = torch.randn(n, device="cuda") * (10.0 ** (-it))
+        g[::7] = 0.0
+        ref_a.grad, ref_b.grad = g[:split].clone(), g[split:].clone()
+        opt.step(); lam.step()
+        gs = (g * 128.0).contiguous()
+        L.check(lib.nb200_adam_hyper(L.ptr(step), L.ptr(sched), L.ptr(hyper), L.stream()), "hyper")
+        L.check(lib.nb200_fused_adam(L.ptr(p), L.ptr(gs), L.ptr(m), L.ptr(v), C.c_uint64(n), C.c_uint64(split),
+                                     L.ptr(hyper), C.c_int(1), L.stream()), "adam")
+        assert float(gs.abs().max()) == 0.0
+        ref = torch.cat([ref_a.detach(), ref_b.detach()])
+        err = (p - ref).abs().max().item()
+        assert err <= 1e-5 * 5e-3 * (it + 1) + 1e-7, (it, err)
+    assert int(step) == 5
+
+
+def test_graph_replay_trains_and_matches_eager_launches():
+    from customnerf_b200 import fused_trainer
+    ma, mb = _models()
+    o, d, tgt = _batch()
+    eager = fused_trainer.FusedTrainStep(ma, N_RAYS, perturb=False, use_graph=False)
+    graph = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False, use_graph=True)
+    losses_e, losses_g = [], []
+    for _ in range(6):
+        eager.step(o, d, tgt); losses_e.append(eager.last_stats()[0])
+        graph.step(o, d, tgt); losses_g.append(graph.last_stats()[0])
+    assert losses_e[-1] < losses_e[0]                  # it trains
+    assert int(graph.step_count) == int(eager.step_count) == 6
+    np.testing.assert_allclose(losses_g, losses_e, rtol=2e-2)
+    # parameters stay views of the flat vector (state-dict names unchanged)
+    assert mb.pos_en.embeddings.data_ptr() == graph.params_flat.data_ptr()
+    assert set(k for k in mb.state_dict() if "params" in k or "embeddings" in k) == {
+        "pos_en.embeddings", "network.params", "density_network.params", "rgb_network.params"}
+
+
+def test_stage_profile_reports_every_stage():
+    from customnerf_b200 import fused_trainer
+    _, mb = _models()
+    o, d, tgt = _batch()
+    fs = fused_trainer.FusedTrainStep(mb, N_RAYS, use_graph=False)
+    fs.step(o, d, tgt)
+    prof = fs.profile_stages(3)
+    assert list(prof) == fused_trainer.STAGES
+    assert all(v > 0 for v in prof.values())
