@@ -273,8 +273,9 @@ def run_b200(args):
             fs.use_graph = not args.no_graph
             line["kernel_us"] = {k: round(v, 2) for k, v in stage_us.items()}
             line["roofline"], line["stage_rooflines"] = rooflines(stage_us, samples, fs.params_flat.numel(), peaks)
-            n_cpu = 2048
-            line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(3, 1, n_cpu).items() if k != "ms_per_step"}
+            if not args.no_cpu:
+                n_cpu = 2048
+                line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(3, 1, n_cpu).items() if k != "ms_per_step"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -287,6 +288,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (kernel tuning runs)")
     ap.add_argument("--no-breakdown", action="store_true",
                     help="skip the per-kernel breakdown and the CPU baseline (profiling runs under ncu)")
     args = ap.parse_args()

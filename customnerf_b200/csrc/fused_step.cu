@@ -79,7 +79,7 @@ int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
     tick(ev, k++, st);
     if ((rc = nb200_fs_march_write(p->rays_o, p->rays_d, p->bitfield, p->bound, p->dt_gamma, p->max_steps, p->N, p->C,
                                    p->H, p->M_cap, p->nears, p->fars, p->noises, p->rays, p->xyzs, p->dirs, p->deltas,
-                                   p->m_eff, stream))) return rc;
+                                   p->m_eff, p->scratch, stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_fs_encode_forward(p->xyzs, p->bound, p->table, p->offsets, p->x_en, p->M_cap, p->L, p->S, p->base_res,
                                       p->gridtype, 0, 0, p->m_eff, stream))) return rc;

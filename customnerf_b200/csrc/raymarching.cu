@@ -12,6 +12,7 @@
 // are integers that must match the reference bit-exactly.
 #include "common.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -33,6 +34,7 @@ struct RayCtx {
     double Hd;
     int Cm1;
     int level_dt;              // mip_from_dt of the constant step when dt_gamma == 0, else -1
+    float dt_min_c;            // that constant step
     const uint8_t *grid;
 };
 
@@ -53,9 +55,11 @@ __device__ __forceinline__ void rm_setup(RayCtx &r, const float *__restrict__ o,
     r.dt_max = __fdiv_rn(__fmul_rn(2 * kSqrt3, (float)(1 << (C - 1))), (float)H);          // :346
     r.Cm1 = (int)C - 1;
     r.level_dt = -1;
+    r.dt_min_c = 0.0f;
     if (dt_gamma == 0.0f) {
         const float dt = rm_clamp(0.0f, r.dt_min, r.dt_max);                               // t * 0 == 0 for every finite t
         r.level_dt = rm_mip_level(__fmul_rn(__fmul_rn(dt, r.Hf), 0.5f), r.Cm1);
+        r.dt_min_c = dt;
     }
     r.grid = grid;
 }
@@ -76,7 +80,40 @@ __device__ __forceinline__ int rm_cell(const RayCtx &r, float p, float mip_rboun
 }
 
 // do { t += dt; } while (t < tt);   (:396-398)
+//
+// With dt_gamma == 0 the step is the constant dt_min, and while t stays inside one binade [2^e, 2^(e+1)) every
+// rounded addition t + dt advances t by the SAME multiple c of the binade's ulp u (t = T u, dt = q u + r with
+// 0 <= r < u; the sum rounds to (T + q) u or (T + q + 1) u depending only on r, unless r == u / 2 where ties-to-even
+// looks at T's parity).  So the loop's result is t + n c for the smallest n >= 1 with t + n c >= tt, evaluated exactly
+// by one FMA (the value is a multiple of u below 2^24 u) -- bit-identical to the serial loop, without the loop.
+// Ties, a binade crossing, or t outside the normal range fall back to the serial loop.
 __device__ __forceinline__ float rm_advance(const RayCtx &r, float t, float tt) {
+    if (r.level_dt >= 0) {                                          // dt_gamma == 0: dt is a constant
+        const float dt = r.dt_min_c;
+        const uint32_t eb = __float_as_uint(t) & 0x7f800000u;
+        if (eb > (24u << 23) && eb < (253u << 23) && t >= dt) {     // t >= dt: the differences below are exact (Sterbenz)
+            const float u = __uint_as_float(eb - (23u << 23));
+            const float top = __uint_as_float(eb + (1u << 23));
+            const float c = __fsub_rn(__fadd_rn(t, dt), t);
+            const float tn = __fadd_rn(t, u);
+            const float c2 = __fsub_rn(__fadd_rn(tn, dt), tn);      // the other parity of T: differs from c only on a tie
+            if (c == c2 && c > 0.0f) {
+                float nf = fmaxf(ceilf(__fdividef(__fsub_rn(tt, t), c)), 1.0f);
+                if (nf < 65536.0f) {
+                    float t1 = __fmaf_rn(nf, c, t), t0 = __fmaf_rn(nf - 1.0f, c, t);
+                    if (t1 < tt) { nf += 1.0f; t0 = t1; t1 = __fmaf_rn(nf, c, t); }              // estimate one short
+                    else if (nf > 1.0f && t0 >= tt) { nf -= 1.0f; t1 = t0; t0 = __fmaf_rn(nf - 1.0f, c, t); }   // one long
+                    // accept only a verified answer: n minimal, and every point before the last inside the binade
+                    // (t0 = t + (n-1) c < top makes all of them exact multiples of u reached by constant steps)
+                    if (t1 >= tt && (nf == 1.0f || t0 < tt) && t0 < top) {
+                        if (t1 < top) return t1;
+                        t = __fadd_rn(t0, dt);          // the last step crosses the binade: rounded with the new ulp
+                        if (t >= tt) return t;          // (else keep stepping serially from here)
+                    }
+                }
+            }
+        }
+    }
     do { t = __fadd_rn(t, rm_dt(r, t)); } while (t < tt);
     return t;
 }
@@ -190,43 +227,61 @@ __global__ void k_packbits(const float *__restrict__ grid, uint32_t N, float thr
 }
 
 // ------------------------------------------------------------------------------------------------
-// march_rays_train: count -> scan -> write
+// march_rays_train: count (+ record) -> scan -> expand
 // ------------------------------------------------------------------------------------------------
-constexpr int kMarchBlock = 32;    // one warp per block: ~15 k rays are only ~470 warps, spread them over all SMs
+// The traversal is a serial dependent chain per ray (~300 voxel visits of ~100 dependent instructions each) and an
+// image is only ~15 k rays, i.e. < 1 warp per SM scheduler when 32 rays share a warp: the kernel is latency bound with
+// most issue slots empty.  So (1) a warp carries only `rpw` rays (lanes >= rpw idle): 32 / rpw times more warps in
+// flight to hide the chain's latency, and less divergence inside a warp; (2) every ray is traversed ONCE: the count
+// pass records the parameter t of each sample it would emit (up to `tcap` per ray) and the second pass only expands
+// those records into xyzs / dirs / deltas with one warp per ray and coalesced stores (a ray with more than `tcap`
+// samples is re-marched by one lane, as the reference does for every ray, raymarching.cu:418-479).
+constexpr int kMarchBlock = 32;    // one warp per block
 
-// pass 1 (:353-400): counts, block-local exclusive offsets (warp shuffles), per-block sums
+__host__ __device__ __forceinline__ uint32_t march_tcap(uint32_t N) { return N <= (1u << 16) ? 128u : (N <= (1u << 20) ? 64u : 32u); }
+static uint32_t march_rpw(uint32_t N) {
+    static int env = -1;
+    if (env < 0) { const char *e = getenv("NB200_MARCH_RPW"); env = e ? atoi(e) : 0; }
+    if (env == 1 || env == 2 || env == 4 || env == 8 || env == 16 || env == 32) return (uint32_t)env;
+    uint32_t r = 32;                                   // aim at >= ~6 warps per SM scheduler (148 x 4 of them)
+    while (r > 4 && (uint64_t)N / r < 148ull * 4 * 6) r >>= 1;
+    return r;
+}
+
+// pass 1 (:353-400): counts, sample records, block-local exclusive offsets (warp shuffles), per-block sums
 __global__ void __launch_bounds__(kMarchBlock)
 k_march_count(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
               float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
               const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
-              int32_t *__restrict__ rays, int32_t *__restrict__ block_sums) {
-    __shared__ int warp_tot[kMarchBlock / 32];
-    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+              int32_t *__restrict__ rays, int32_t *__restrict__ block_sums, uint32_t rpw, float *__restrict__ trec,
+              uint32_t tcap) {
+    const uint32_t lane = threadIdx.x;
+    const uint32_t n = blockIdx.x * rpw + lane;
+    const bool live = lane < rpw && n < N;
     int num_steps = 0;
-    if (n < N) {
+    if (live) {
         RayCtx r;
         rm_setup(r, rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H);
         const float far = fars[n];
         float t = nears[n];
         t = __fmaf_rn(rm_dt(r, t), noises ? noises[n] : 0.0f, t);      // :351
+        float *rec = trec ? trec + (size_t)n * tcap : nullptr;
         float x, y, z, dt;
         while (t < far && (uint32_t)num_steps < max_steps) {
-            if (rm_step(r, t, x, y, z, dt)) { num_steps++; t = __fadd_rn(t, dt); }
+            if (rm_step(r, t, x, y, z, dt)) {
+                if (rec && (uint32_t)num_steps < tcap) rec[num_steps] = t;
+                num_steps++;
+                t = __fadd_rn(t, dt);
+            }
         }
     }
     const int incl = nb_warp_incl_scan(num_steps);
-    const uint32_t w = threadIdx.x >> 5;
-    if (nb_lane() == 31) warp_tot[w] = incl;
-    __syncthreads();
-    int base = 0;
-#pragma unroll
-    for (int i = 0; i < kMarchBlock / 32; i++) base += (i < (int)w) ? warp_tot[i] : 0;
-    if (n < N) {
+    if (live) {
         rays[n * 3] = (int32_t)n;
-        rays[n * 3 + 1] = base + incl - num_steps;      // block-local exclusive offset, globalised by k_march_fixup
+        rays[n * 3 + 1] = incl - num_steps;             // block-local exclusive offset, globalised by k_march_fixup
         rays[n * 3 + 2] = num_steps;
     }
-    if (threadIdx.x == kMarchBlock - 1) block_sums[blockIdx.x] = base + incl;
+    if (lane == 31) block_sums[blockIdx.x] = incl;
 }
 
 // single block: exclusive scan of the block sums starting at counter[0]; counter += (sum, N)  (:405-406)
@@ -260,39 +315,62 @@ k_march_scan(const int32_t *__restrict__ block_sums, int32_t *__restrict__ block
         counter[0] = carry_s;
         counter[1] += (int32_t)N;
         // rows the downstream kernels of the fused step may touch: every segment below this row is complete
-        // (k_march_write lowers it to the offset of the first ray that does not fit in M_cap rows)
+        // (k_march_expand lowers it to the offset of the first ray that does not fit in M_cap rows)
         if (m_eff) *m_eff = (int32_t)min((uint32_t)max(carry_s, 0), M_cap);
     }
 }
 
-__global__ void k_march_fixup(int32_t *__restrict__ rays, const int32_t *__restrict__ block_prefix, uint32_t N) {
+__global__ void k_march_fixup(int32_t *__restrict__ rays, const int32_t *__restrict__ block_prefix, uint32_t N,
+                              uint32_t rpw) {
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     if (n >= N) return;
-    rays[n * 3 + 1] += block_prefix[n / kMarchBlock];
+    rays[n * 3 + 1] += block_prefix[n / rpw];
 }
 
-// pass 2 (:418-479)
-__global__ void __launch_bounds__(kMarchBlock)
-k_march_write(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
-              float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
-              const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
-              const int32_t *__restrict__ rays, float *__restrict__ xyzs, float *__restrict__ dirs,
-              float *__restrict__ deltas, int32_t *__restrict__ m_eff) {
-    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+// pass 2 (:418-479): one warp per ray.  Lane i of trip k owns sample 32 k + i of the ray: the sample position is
+// recomputed from its recorded t with the same FMA / clamp as the traversal, deltas[:,1] from the previous record.
+constexpr int kExpandBlock = 256;
+__global__ void __launch_bounds__(kExpandBlock)
+k_march_expand(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+               float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+               const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
+               const int32_t *__restrict__ rays, float *__restrict__ xyzs, float *__restrict__ dirs,
+               float *__restrict__ deltas, int32_t *__restrict__ m_eff, const float *__restrict__ trec, uint32_t tcap) {
+    const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
     if (n >= N) return;
+    const uint32_t lane = nb_lane();
     const uint32_t point_index = (uint32_t)rays[n * 3 + 1];
     const uint32_t num_steps = (uint32_t)rays[n * 3 + 2];
     if (num_steps == 0) return;
     if (point_index + num_steps > M) {
-        if (m_eff) atomicMin(m_eff, (int32_t)min(point_index, M));
+        if (m_eff && lane == 0) atomicMin(m_eff, (int32_t)min(point_index, M));
         return;
     }
     RayCtx r;
     rm_setup(r, rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H);
-    const float far = fars[n];
     float t = nears[n];
     t = __fmaf_rn(rm_dt(r, t), noises ? noises[n] : 0.0f, t);
     float *px = xyzs + (size_t)point_index * 3, *pd = dirs + (size_t)point_index * 3, *pl = deltas + (size_t)point_index * 2;
+    if (trec && num_steps <= tcap) {
+        const float *rec = trec + (size_t)n * tcap;
+        for (uint32_t base = 0; base < num_steps; base += 32) {
+            const uint32_t i = base + lane;
+            if (i < num_steps) {
+                const float ti = rec[i];
+                float last_t = t;                                   // the ray's (perturbed) start for its first sample
+                if (i > 0) { const float tp = rec[i - 1]; last_t = __fadd_rn(tp, rm_dt(r, tp)); }
+                const float dt = rm_dt(r, ti);
+                px[i * 3] = rm_clamp(__fmaf_rn(ti, r.dx, r.ox), -r.bound, r.bound);
+                px[i * 3 + 1] = rm_clamp(__fmaf_rn(ti, r.dy, r.oy), -r.bound, r.bound);
+                px[i * 3 + 2] = rm_clamp(__fmaf_rn(ti, r.dz, r.oz), -r.bound, r.bound);
+                pd[i * 3] = r.dx; pd[i * 3 + 1] = r.dy; pd[i * 3 + 2] = r.dz;
+                *reinterpret_cast<float2 *>(pl + i * 2) = make_float2(dt, __fsub_rn(__fadd_rn(ti, dt), last_t));
+            }
+        }
+        return;
+    }
+    if (lane != 0) return;                  // more samples than records: re-march this ray serially
+    const float far = fars[n];
     float last_t = t, x, y, z, dt;
     uint32_t step = 0;
     while (t < far && step < num_steps) {
@@ -561,7 +639,13 @@ int nb200_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t 
     return 0;
 }
 
-uint32_t nb200_march_scratch_ints(uint32_t N) { return 2 * nb_div_up(N, kMarchBlock) + 8; }
+// scratch layout (int32 units): [block sums: nb4][block prefixes: nb4][8 spare][sample records: N * tcap floats],
+// nb4 = ceil(N / 4) (the smallest rays-per-warp the launcher ever picks)
+static inline uint32_t march_nb_max(uint32_t N) { return nb_div_up(N, 4); }
+uint32_t nb200_march_scratch_ints(uint32_t N) { return 2 * march_nb_max(N) + 8 + N * march_tcap(N); }
+static inline float *march_trec(int32_t *scratch, uint32_t N) {
+    return reinterpret_cast<float *>(scratch + 2 * march_nb_max(N) + 8);
+}
 
 static int march_count_impl(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
                             float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
@@ -570,15 +654,29 @@ static int march_count_impl(const float *rays_o, const float *rays_d, const uint
                             void *stream) {
     if (N == 0) return 0;
     if (!scratch || !rays || !counter) return NB200_E_BAD_ARG;
-    const uint32_t nb = nb_div_up(N, kMarchBlock);
-    int32_t *block_sums = scratch, *block_prefix = scratch + nb;
+    const uint32_t rpw = march_rpw(N);
+    const uint32_t nb = nb_div_up(N, rpw);
+    int32_t *block_sums = scratch, *block_prefix = scratch + march_nb_max(N);
     cudaStream_t st = nb_stream(stream);
     k_march_count<<<nb, kMarchBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
-                                              noises, rays, block_sums);
+                                              noises, rays, block_sums, rpw, march_trec(scratch, N), march_tcap(N));
     NB_LAUNCH_CHECK();
     k_march_scan<<<1, 1024, 0, st>>>(block_sums, block_prefix, nb, N, counter, M_cap, m_eff);
     NB_LAUNCH_CHECK();
-    k_march_fixup<<<nb_div_up(N, 256), 256, 0, st>>>(rays, block_prefix, N);
+    k_march_fixup<<<nb_div_up(N, 256), 256, 0, st>>>(rays, block_prefix, N, rpw);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int march_expand_impl(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                             uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
+                             const float *fars, const float *noises, const int32_t *rays, float *xyzs, float *dirs,
+                             float *deltas, int32_t *m_eff, const int32_t *scratch, void *stream) {
+    if (N == 0) return 0;
+    const float *trec = scratch ? march_trec(const_cast<int32_t *>(scratch), N) : nullptr;
+    k_march_expand<<<nb_div_up((uint64_t)N * 32, kExpandBlock), kExpandBlock, 0, nb_stream(stream)>>>(
+        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, noises, rays, xyzs, dirs, deltas,
+        m_eff, trec, march_tcap(N));
     NB_LAUNCH_CHECK();
     return 0;
 }
@@ -591,7 +689,7 @@ int nb200_march_rays_train_count(const float *rays_o, const float *rays_d, const
                             scratch, 0, nullptr, stream);
 }
 
-// fused train step: count + scan, then write, into buffers of M_cap rows; *m_eff = rows covered by complete segments
+// fused train step: count + scan, then expand, into buffers of M_cap rows; *m_eff = rows covered by complete segments
 int nb200_fs_march_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, const float *nears,
                          const float *fars, const float *noises, int32_t *rays, int32_t *counter, int32_t *m_eff,
@@ -605,26 +703,20 @@ int nb200_fs_march_count(const float *rays_o, const float *rays_d, const uint8_t
 int nb200_fs_march_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, const float *nears,
                          const float *fars, const float *noises, const int32_t *rays, float *xyzs, float *dirs,
-                         float *deltas, int32_t *m_eff, void *stream) {
+                         float *deltas, int32_t *m_eff, const int32_t *scratch, void *stream) {
     if (N == 0) return 0;
     if (!m_eff) return NB200_E_BAD_ARG;
-    k_march_write<<<nb_div_up(N, kMarchBlock), kMarchBlock, 0, nb_stream(stream)>>>(
-        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M_cap, nears, fars, noises, rays, xyzs, dirs, deltas,
-        m_eff);
-    NB_LAUNCH_CHECK();
-    return 0;
+    return march_expand_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M_cap, nears, fars, noises, rays,
+                             xyzs, dirs, deltas, m_eff, scratch, stream);
 }
 
+// scratch: the buffer nb200_march_rays_train_count filled for the same rays (its sample records), or NULL to re-march
 int nb200_march_rays_train_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
                                  float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                                  const float *nears, const float *fars, const float *noises, const int32_t *rays,
-                                 float *xyzs, float *dirs, float *deltas, void *stream) {
-    if (N == 0) return 0;
-    k_march_write<<<nb_div_up(N, kMarchBlock), kMarchBlock, 0, nb_stream(stream)>>>(
-        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, noises, rays, xyzs, dirs, deltas,
-        nullptr);
-    NB_LAUNCH_CHECK();
-    return 0;
+                                 float *xyzs, float *dirs, float *deltas, const int32_t *scratch, void *stream) {
+    return march_expand_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, noises, rays,
+                             xyzs, dirs, deltas, nullptr, scratch, stream);
 }
 
 int nb200_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
@@ -635,7 +727,7 @@ int nb200_march_rays_train(const float *rays_o, const float *rays_d, const uint8
                                           rays, counter, scratch, stream);
     if (rc) return rc;
     return nb200_march_rays_train_write(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars,
-                                        noises, rays, xyzs, dirs, deltas, stream);
+                                        noises, rays, xyzs, dirs, deltas, scratch, stream);
 }
 
 int nb200_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas, const int32_t *rays,

@@ -31,7 +31,7 @@ def shard_rays(n_rays, rank, world_size, mode="interleaved"):
     if mode == "interleaved":
         return torch.arange(rank, n_rays, world_size)
     per = (n_rays + world_size - 1) // world_size
-    return torch.arange(rank * per, min(n_rays, (rank + 1) * per))
+    return torch.arange(min(n_rays, rank * per), min(n_rays, (rank + 1) * per))
 
 
 class FlatGradSync:

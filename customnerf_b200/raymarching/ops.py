@@ -7,9 +7,10 @@ backward.  All ops run on the CURRENT stream of the tensors' device -- the refer
 default stream.
 
 What is different underneath:
-  * ``march_rays_train`` counts first (one kernel + scan), reads the total back (the same single D2H sync the
-    reference has at :225), then allocates ``m`` rounded up by the reference's rule and writes -- instead of
-    zero-filling N*max_steps rows (:196-209) and slicing.  ``rays`` comes out in ray-id order with scan
+  * ``march_rays_train`` traverses every ray ONCE (count kernel that also records each sample's t, + scan), reads the
+    total back (the same single D2H sync the reference has at :225), allocates ``m`` rounded up by the reference's
+    rule and expands the records with one warp per ray -- instead of zero-filling N*max_steps rows (:196-209),
+    marching every ray twice and slicing.  ``rays`` comes out in ray-id order with scan
     offsets (deterministic; a valid member of the reference's atomics-ordered output set).
   * no ``torch.cuda.empty_cache()`` on the hot path (:232).
 """
@@ -158,7 +159,7 @@ def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
         L.check(lib.nb200_march_rays_train_write(
             L.ptr(rays_o), L.ptr(rays_d), L.ptr(density_bitfield), L.f32(bound), L.f32(dt_gamma), L.u32(max_steps),
             L.u32(N), L.u32(C), L.u32(H), L.u32(M), L.ptr(nears), L.ptr(fars), L.ptr(noises), L.ptr(rays), L.ptr(xyzs),
-            L.ptr(dirs), L.ptr(deltas), L.stream()), "march_rays_train(write)")
+            L.ptr(dirs), L.ptr(deltas), L.ptr(scratch), L.stream()), "march_rays_train(write)")
     return xyzs, dirs, deltas, rays
 
 

@@ -107,9 +107,11 @@ int nb200_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t 
  *       exclusive scan of the counts in ray-id order STARTING AT counter[0]'s entry value (one valid member of
  *       the reference's atomicAdd-ordered output set); then counter[0] += sum, counter[1] += N.
  *       scratch: i32, at least nb200_march_scratch_ints(N) entries.
- *   nb200_march_rays_train_write : march again and write xyzs/dirs/deltas for rays whose segment fits in M
- *       (raymarching.cu:415-416).  Rows not covered by a segment are left untouched (caller zero-fills,
- *       raymarching.py:206-208).
+ *       The count pass also records the parameter t of every sample (up to a per-ray cap) in `scratch`.
+ *   nb200_march_rays_train_write : write xyzs/dirs/deltas for rays whose segment fits in M (raymarching.cu:415-416)
+ *       by expanding the records of the count pass (`scratch` = the same buffer, same rays; one warp per ray,
+ *       coalesced stores), or by marching again when scratch is NULL / a ray has more samples than records.
+ *       Rows not covered by a segment are left untouched (caller zero-fills, raymarching.py:206-208).
  *   nb200_march_rays_train       : both, back to back == the reference entry point. */
 uint32_t nb200_march_scratch_ints(uint32_t N);
 int nb200_march_rays_train_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
@@ -119,7 +121,7 @@ int nb200_march_rays_train_count(const float *rays_o, const float *rays_d, const
 int nb200_march_rays_train_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
                                  float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                                  const float *nears, const float *fars, const float *noises, const int32_t *rays,
-                                 float *xyzs, float *dirs, float *deltas, void *stream);
+                                 float *xyzs, float *dirs, float *deltas, const int32_t *scratch, void *stream);
 int nb200_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
                            uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
                            const float *fars, float *xyzs, float *dirs, float *deltas, int32_t *rays, int32_t *counter,
@@ -191,7 +193,7 @@ int nb200_fs_march_count(const float *rays_o, const float *rays_d, const uint8_t
 int nb200_fs_march_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, const float *nears,
                          const float *fars, const float *noises, const int32_t *rays, float *xyzs, float *dirs,
-                         float *deltas, int32_t *m_eff, void *stream);
+                         float *deltas, int32_t *m_eff, const int32_t *scratch, void *stream);
 /* grid encode of raw positions xyz in [-bound, bound] (GridEncoder.forward's normalisation grid.py:156 fused in),
  * D = 3, C = 2, fp32 master table rounded to fp16 per load (autocast semantics of grid.py:45-46), x_en f16 [M_cap, 2L]. */
 int nb200_fs_encode_forward(const float *xyz, float bound, const float *table, const int32_t *offsets, void *x_en,

@@ -3,7 +3,7 @@ against the autograd composition of the drop-in ops (trainer.TrainStep) and agai
 
 Tolerances: gradients come out of the same kernels in both paths (fp16 activations, fp32 atomics whose order differs
 run to run), so loss rel 1e-5, gradients rel 1e-2 of the largest entry (SURVEY.md Appendix D, fp16 grid grads).
-The Adam kernel is compared with torch.optim.Adam on identical gradients: rel 1e-5.
+The Adam kernel is compared with torch.optim.Adam on identical gradients: abs 1e-6 on O(1) parameters (2-4 ulp).
 """
 import ctypes as C
 
@@ -103,7 +103,7 @@ def test_fused_adam_matches_torch_adam():
         assert float(gs.abs().max()) == 0.0
         ref = torch.cat([ref_a.detach(), ref_b.detach()])
         err = (p - ref).abs().max().item()
-        assert err <= 1e-5 * 5e-3 * (it + 1) + 1e-7, (it, err)
+        assert err <= 1e-6, (it, err)      # parameters are O(1): one fp32 ulp is 2.4e-7 .. 4.8e-7
     assert int(step) == 5
 
 
