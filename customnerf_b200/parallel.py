@@ -29,7 +29,7 @@ def shard_rays(n_rays, rank, world_size, mode="interleaved"):
     interleaved (default): ray i -> rank i % world.  Neighbouring pixels have similar sample counts, so a strided
     split balances the per-rank sample totals far better than contiguous image rows (SURVEY.md 8(e) caveat)."""
     if mode == "interleaved":
-        return torch.arange(rank, n_rays, world_size)
+        return torch.arange(min(rank, n_rays), n_rays, world_size)
     per = (n_rays + world_size - 1) // world_size
     return torch.arange(min(n_rays, rank * per), min(n_rays, (rank + 1) * per))
 
