@@ -87,34 +87,68 @@ __device__ __forceinline__ int rm_cell(const RayCtx &r, float p, float mip_rboun
 // looks at T's parity).  So the loop's result is t + n c for the smallest n >= 1 with t + n c >= tt, evaluated exactly
 // by one FMA (the value is a multiple of u below 2^24 u) -- bit-identical to the serial loop, without the loop.
 // Ties, a binade crossing, or t outside the normal range fall back to the serial loop.
-__device__ __forceinline__ float rm_advance(const RayCtx &r, float t, float tt) {
+// constant step c of the binade of t (see above); false when the closed form does not apply (tie, range)
+__device__ __forceinline__ bool rm_binade_step(float t, float dt, float &c, float &top) {
+    const uint32_t eb = __float_as_uint(t) & 0x7f800000u;
+    if (!(eb > (24u << 23) && eb < (253u << 23) && t >= dt)) return false;   // t >= dt: the differences are exact (Sterbenz)
+    const float u = __uint_as_float(eb - (23u << 23));
+    top = __uint_as_float(eb + (1u << 23));
+    c = __fsub_rn(__fadd_rn(t, dt), t);
+    const float tn = __fadd_rn(t, u);
+    const float c2 = __fsub_rn(__fadd_rn(tn, dt), tn);          // the other parity of T: differs from c only on a tie
+    return c == c2 && c > 0.0f;
+}
+
+// returns the advanced t; nsteps = number of additions the loop performed
+__device__ __forceinline__ float rm_advance(const RayCtx &r, float t, float tt, uint32_t &nsteps) {
+    uint32_t n = 0;
     if (r.level_dt >= 0) {                                          // dt_gamma == 0: dt is a constant
         const float dt = r.dt_min_c;
-        const uint32_t eb = __float_as_uint(t) & 0x7f800000u;
-        if (eb > (24u << 23) && eb < (253u << 23) && t >= dt) {     // t >= dt: the differences below are exact (Sterbenz)
-            const float u = __uint_as_float(eb - (23u << 23));
-            const float top = __uint_as_float(eb + (1u << 23));
-            const float c = __fsub_rn(__fadd_rn(t, dt), t);
-            const float tn = __fadd_rn(t, u);
-            const float c2 = __fsub_rn(__fadd_rn(tn, dt), tn);      // the other parity of T: differs from c only on a tie
-            if (c == c2 && c > 0.0f) {
-                float nf = fmaxf(ceilf(__fdividef(__fsub_rn(tt, t), c)), 1.0f);
-                if (nf < 65536.0f) {
-                    float t1 = __fmaf_rn(nf, c, t), t0 = __fmaf_rn(nf - 1.0f, c, t);
-                    if (t1 < tt) { nf += 1.0f; t0 = t1; t1 = __fmaf_rn(nf, c, t); }              // estimate one short
-                    else if (nf > 1.0f && t0 >= tt) { nf -= 1.0f; t1 = t0; t0 = __fmaf_rn(nf - 1.0f, c, t); }   // one long
-                    // accept only a verified answer: n minimal, and every point before the last inside the binade
-                    // (t0 = t + (n-1) c < top makes all of them exact multiples of u reached by constant steps)
-                    if (t1 >= tt && (nf == 1.0f || t0 < tt) && t0 < top) {
-                        if (t1 < top) return t1;
-                        t = __fadd_rn(t0, dt);          // the last step crosses the binade: rounded with the new ulp
-                        if (t >= tt) return t;          // (else keep stepping serially from here)
-                    }
+        float c, top;
+        if (rm_binade_step(t, dt, c, top)) {
+            float nf = fmaxf(ceilf(__fdividef(__fsub_rn(tt, t), c)), 1.0f);
+            if (nf < 65536.0f) {
+                float t1 = __fmaf_rn(nf, c, t), t0 = __fmaf_rn(nf - 1.0f, c, t);
+                if (t1 < tt) { nf += 1.0f; t0 = t1; t1 = __fmaf_rn(nf, c, t); }              // estimate one short
+                else if (nf > 1.0f && t0 >= tt) { nf -= 1.0f; t1 = t0; t0 = __fmaf_rn(nf - 1.0f, c, t); }   // one long
+                // accept only a verified answer: n minimal, and every point before the last inside the binade
+                // (t0 = t + (n-1) c < top makes all of them exact multiples of u reached by constant steps)
+                if (t1 >= tt && (nf == 1.0f || t0 < tt) && t0 < top) {
+                    n = (uint32_t)nf;
+                    if (t1 < top) { nsteps = n; return t1; }
+                    t = __fadd_rn(t0, dt);          // the last step crosses the binade: rounded with the new ulp
+                    if (t >= tt) { nsteps = n; return t; }          // (else keep stepping serially from here)
                 }
             }
         }
     }
-    do { t = __fadd_rn(t, rm_dt(r, t)); } while (t < tt);
+    do { t = __fadd_rn(t, rm_dt(r, t)); n++; } while (t < tt);
+    nsteps = n;
+    return t;
+}
+
+// t after n additions of the constant step dt (dt_gamma == 0): binade by binade with the constant-step closed form,
+// the crossing addition done for real.  Bit-identical to n serial additions.
+__device__ __forceinline__ float rm_lattice_jump(float t, float dt, uint32_t n) {
+    while (n > 0) {
+        float c, top;
+        if (rm_binade_step(t, dt, c, top)) {
+            // largest j with t + j c < top
+            float jf = fmaxf(ceilf(__fdividef(__fsub_rn(top, t), c)) - 1.0f, 0.0f);
+            if (jf < 16777216.0f) {
+                if (__fmaf_rn(jf, c, t) >= top) jf -= 1.0f;                              // estimate one long
+                else if (__fmaf_rn(jf + 1.0f, c, t) < top) jf += 1.0f;                   // one short
+                if (jf >= 0.0f && __fmaf_rn(jf, c, t) < top && __fmaf_rn(jf + 1.0f, c, t) >= top) {
+                    const uint32_t j = min(n, (uint32_t)jf);
+                    t = __fmaf_rn((float)j, c, t);
+                    n -= j;
+                    if (n == 0) break;
+                }
+            }
+        }
+        t = __fadd_rn(t, dt);       // the crossing step (or a step the closed form does not cover)
+        n -= 1;
+    }
     return t;
 }
 
@@ -125,9 +159,9 @@ __device__ __forceinline__ float rm_exit(float n, float s, float rH, float mip_b
     return __fmul_rn(__fmaf_rn(__fmaf_rn(b, 2.0f, -1.0f), mip_bound, -p), rd);
 }
 
-// One iteration of the marching loop (:359-399).  Returns true when the cell at t is occupied: x,y,z,dt are the
-// sample; the caller emits it and advances t by dt.  Otherwise t has been advanced past the empty voxel.
-__device__ __forceinline__ bool rm_step(const RayCtx &r, float &t, float &x, float &y, float &z, float &dt) {
+// Occupancy probe of the marching loop (:359-387) at parameter t: x,y,z,dt are the would-be sample; when the cell is
+// empty, tt is the parameter at which the ray leaves the voxel (:388-394).
+__device__ __forceinline__ bool rm_probe(const RayCtx &r, float t, float &x, float &y, float &z, float &dt, float &tt) {
     x = rm_clamp(__fmaf_rn(t, r.dx, r.ox), -r.bound, r.bound);
     y = rm_clamp(__fmaf_rn(t, r.dy, r.oy), -r.bound, r.bound);
     z = rm_clamp(__fmaf_rn(t, r.dz, r.oz), -r.bound, r.bound);
@@ -148,8 +182,17 @@ __device__ __forceinline__ bool rm_step(const RayCtx &r, float &t, float &x, flo
     const float tx = rm_exit((float)nx, r.sx, r.rH, mip_bound, x, r.rdx);
     const float ty = rm_exit((float)ny, r.sy, r.rH, mip_bound, y, r.rdy);
     const float tz = rm_exit((float)nz, r.sz, r.rH, mip_bound, z, r.rdz);
-    const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
-    t = rm_advance(r, t, tt);
+    tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    return false;
+}
+
+// One iteration of the marching loop (:359-399).  Returns true when the cell at t is occupied: x,y,z,dt are the
+// sample; the caller emits it and advances t by dt.  Otherwise t has been advanced past the empty voxel.
+__device__ __forceinline__ bool rm_step(const RayCtx &r, float &t, float &x, float &y, float &z, float &dt) {
+    float tt;
+    if (rm_probe(r, t, x, y, z, dt, tt)) return true;
+    uint32_t n;
+    t = rm_advance(r, t, tt, n);
     return false;
 }
 
@@ -238,7 +281,8 @@ __global__ void k_packbits(const float *__restrict__ grid, uint32_t N, float thr
 // samples is re-marched by one lane, as the reference does for every ray, raymarching.cu:418-479).
 constexpr int kMarchBlock = 32;    // one warp per block
 
-__host__ __device__ __forceinline__ uint32_t march_tcap(uint32_t N) { return N <= (1u << 16) ? 128u : (N <= (1u << 20) ? 64u : 32u); }
+// sample records kept per ray: all of them (max_steps <= 1024) while that stays under ~1 GB
+__host__ __device__ __forceinline__ uint32_t march_tcap(uint32_t N) { return N <= (1u << 18) ? 1024u : (N <= (1u << 21) ? 256u : 64u); }
 static uint32_t march_rpw(uint32_t N) {
     static int env = -1;
     if (env < 0) { const char *e = getenv("NB200_MARCH_RPW"); env = e ? atoi(e) : 0; }
@@ -282,6 +326,131 @@ k_march_count(const float *__restrict__ rays_o, const float *__restrict__ rays_d
         rays[n * 3 + 2] = num_steps;
     }
     if (lane == 31) block_sums[blockIdx.x] = incl;
+}
+
+// ---- pass 1 for the constant-step case (dt_gamma == 0): one WARP per ray, speculative segments -----------------
+// With a constant step every parameter the loop can visit lies on the lattice T(0) = t0, T(k+1) = fl(T(k) + dt), and
+// T(k) is available in closed form (rm_lattice_jump).  The loop is a chain over lattice indices:
+//     k occupied -> emit, k + 1;      k empty -> the first j > k with T(j) >= voxel exit.
+// The chain is serial, but its restriction to a window of indices depends only on where it ENTERS the window.  So the
+// warp cuts a window of 32 * seg indices into 32 segments; lane s marches segment s speculating that its first index
+// a_s is visited, recording the samples it would emit and where it lands beyond the segment.  A cheap sequential pass
+// then threads the true chain through the segments: the entry e of segment s (the landing of the last valid segment)
+// must be a_s itself or the first point lane s moved to (v1) -- both lie on lane s's chain, so everything lane s did
+// from e on IS the true chain (a sample speculatively emitted AT a_s is dropped when e = v1).  In the rare case where
+// e is neither, lane s re-marches its segment from e.  Samples are therefore identical to the serial loop's by
+// construction, never by tolerance; the critical path drops from the whole ray (~500 dependent voxel visits) to one
+// segment (<= 64 lattice points).
+constexpr int kSegWarps = 4;            // rays per block
+constexpr int kSegMax = 64;             // lattice indices per lane and round
+constexpr int kSegMin = 8;
+constexpr int kRecStride = kSegMax + 1; // +1: lanes write their own rows, keep them on different banks
+
+struct SegResult { uint32_t cnt, v1, land; float tland; bool occ_a; };
+
+__device__ __forceinline__ SegResult rm_march_segment(const RayCtx &r, uint32_t k, float t, uint32_t b, float far,
+                                                      float *__restrict__ rec) {
+    SegResult o;
+    o.cnt = 0; o.v1 = 0xffffffffu; o.occ_a = false;
+    const uint32_t a = k;
+    float x, y, z, dt, tt;
+    while (k < b && t < far) {
+        if (rm_probe(r, t, x, y, z, dt, tt)) {
+            rec[o.cnt++] = t;
+            if (k == a) o.occ_a = true;
+            k += 1;
+            t = __fadd_rn(t, dt);
+        } else {
+            uint32_t n;
+            t = rm_advance(r, t, tt, n);
+            k += n;
+        }
+        if (o.v1 == 0xffffffffu) o.v1 = k;
+    }
+    o.land = k; o.tland = t;
+    return o;
+}
+
+__global__ void __launch_bounds__(kSegWarps * 32)
+k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
+                  float bound, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                  const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
+                  int32_t *__restrict__ rays, int32_t *__restrict__ block_sums, float *__restrict__ trec, uint32_t tcap) {
+    __shared__ float rec_s[kSegWarps][32][kRecStride];
+    __shared__ int ray_tot[kSegWarps];
+    const uint32_t lane = nb_lane(), w = threadIdx.x >> 5;
+    const uint32_t n = blockIdx.x * kSegWarps + w;
+    uint32_t total = 0;
+    if (n < N) {
+        RayCtx r;
+        rm_setup(r, rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, 0.0f, max_steps, C, H);
+        const float far = fars[n], dt = r.dt_min_c;
+        float t0 = nears[n];
+        t0 = __fmaf_rn(rm_dt(r, t0), noises ? noises[n] : 0.0f, t0);      // :351
+        float *rec = rec_s[w][lane];
+        float *out = trec ? trec + (size_t)n * tcap : nullptr;
+        if (t0 < far) {
+            const float kest = fminf(__fdividef(far - t0, dt) + 2.0f, 1.0e9f);
+            const uint32_t seg = (uint32_t)min(max((int)ceilf(kest * (1.0f / 32.0f)), kSegMin), kSegMax);
+            uint32_t K0 = 0;            // first index of the window == the chain's entry into it (exact for lane 0)
+            float tK0 = t0;
+            bool ended = false;
+            while (!ended) {
+                const uint32_t a = K0 + lane * seg, b = a + seg;
+                const float ta = rm_lattice_jump(tK0, dt, lane * seg);
+                SegResult sr = rm_march_segment(r, a, ta, b, far, rec);
+                // ---- thread the true chain through the segments
+                uint32_t e = K0, drop = 0, valid = 0;
+                float te = tK0;
+                for (uint32_t sgm = 0; sgm < 32; sgm++) {
+                    const uint32_t as = K0 + sgm * seg, bs = as + seg;
+                    if (e >= bs) continue;                                  // the chain jumps over this segment
+                    const uint32_t v1s = __shfl_sync(0xffffffffu, sr.v1, sgm);
+                    const bool occs = __shfl_sync(0xffffffffu, (int)sr.occ_a, sgm) != 0;
+                    uint32_t dr;
+                    if (e == as) dr = 0;
+                    else if (e == v1s) dr = occs ? 1u : 0u;
+                    else {                                                  // mis-speculation: re-march from the true entry
+                        if (lane == sgm) sr = rm_march_segment(r, e, te, b, far, rec);
+                        dr = 0;
+                    }
+                    if (lane == sgm) { drop = dr; valid = sr.cnt - dr; }
+                    e = __shfl_sync(0xffffffffu, sr.land, sgm);
+                    te = __shfl_sync(0xffffffffu, sr.tland, sgm);
+                    if (!(te < far)) { ended = true; break; }
+                }
+                // ---- compact this round's samples behind the ray's earlier ones (max_steps caps the ray, :359)
+                const uint32_t incl = (uint32_t)nb_warp_incl_scan((int)valid);
+                const uint32_t round_total = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t first = total + incl - valid;
+                if (out) {
+                    for (uint32_t i = 0; i < valid; i++) {
+                        const uint32_t idx = first + i;
+                        if (idx < max_steps && idx < tcap) out[idx] = rec[drop + i];
+                    }
+                }
+                total += round_total;
+                if (total >= max_steps) { total = max_steps; ended = true; }
+                K0 = e; tK0 = te;
+            }
+        }
+    }
+    if (lane == 0) ray_tot[w] = (int)total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+#pragma unroll
+        for (int i = 0; i < kSegWarps; i++) {
+            const uint32_t ni = blockIdx.x * kSegWarps + i;
+            if (ni < N) {
+                rays[ni * 3] = (int32_t)ni;
+                rays[ni * 3 + 1] = run;             // block-local exclusive offset, globalised by k_march_fixup
+                rays[ni * 3 + 2] = ray_tot[i];
+            }
+            run += ray_tot[i];
+        }
+        block_sums[blockIdx.x] = run;
+    }
 }
 
 // single block: exclusive scan of the block sums starting at counter[0]; counter += (sum, N)  (:405-406)
@@ -654,12 +823,19 @@ static int march_count_impl(const float *rays_o, const float *rays_d, const uint
                             void *stream) {
     if (N == 0) return 0;
     if (!scratch || !rays || !counter) return NB200_E_BAD_ARG;
-    const uint32_t rpw = march_rpw(N);
+    static int serial_env = -1;
+    if (serial_env < 0) { const char *e = getenv("NB200_MARCH_SERIAL"); serial_env = (e && atoi(e)) ? 1 : 0; }
+    const bool seg = dt_gamma == 0.0f && !serial_env;
+    const uint32_t rpw = seg ? (uint32_t)kSegWarps : march_rpw(N);
     const uint32_t nb = nb_div_up(N, rpw);
     int32_t *block_sums = scratch, *block_prefix = scratch + march_nb_max(N);
     cudaStream_t st = nb_stream(stream);
-    k_march_count<<<nb, kMarchBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
-                                              noises, rays, block_sums, rpw, march_trec(scratch, N), march_tcap(N));
+    if (seg)
+        k_march_count_seg<<<nb, kSegWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, max_steps, N, C, H, nears, fars,
+                                                        noises, rays, block_sums, march_trec(scratch, N), march_tcap(N));
+    else
+        k_march_count<<<nb, kMarchBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
+                                                  noises, rays, block_sums, rpw, march_trec(scratch, N), march_tcap(N));
     NB_LAUNCH_CHECK();
     k_march_scan<<<1, 1024, 0, st>>>(block_sums, block_prefix, nb, N, counter, M_cap, m_eff);
     NB_LAUNCH_CHECK();
