@@ -122,7 +122,7 @@ __device__ __forceinline__ uint64_t kdesc(uint32_t tile_addr, uint32_t ks) {
 
 // accumulator row (64 fp32) -> optional ReLU -> fp16 -> row of a swizzled tile (+ optional global copy)
 template <bool kRelu>
-__device__ __forceinline__ void epilogue_row64(uint32_t tmem_row_addr, uint8_t *tile, uint32_t row, __half *gdst) {
+__device__ __noinline__ void epilogue_row64(uint32_t tmem_row_addr, uint8_t *tile, uint32_t row, __half *gdst) {
     uint32_t a[32], b[32];
     umma::tmem_ld32(tmem_row_addr, a);
     umma::tmem_ld32(tmem_row_addr + 32, b);
@@ -139,6 +139,47 @@ __device__ __forceinline__ void epilogue_row64(uint32_t tmem_row_addr, uint8_t *
         const uint4 pk = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
         *reinterpret_cast<uint4 *>(tile + umma::sw128_offset(row, c)) = pk;
         if (gdst) *reinterpret_cast<uint4 *>(gdst + c * 8) = pk;
+    }
+}
+
+// direction encoding get_embedder(4) of one row: [d, sin(2^k d), cos(2^k d)] (27) then five 1.0 lanes (the padded
+// inputs 91..95 of the colour head), written as chunks 4..7 of row `row` of the XV tile
+__device__ __noinline__ void write_view_chunks(uint8_t *xv, uint32_t row, float d0, float d1, float d2, bool valid) {
+    float e[32];
+    e[0] = d0; e[1] = d1; e[2] = d2;
+    // sin / cos of 2^k d: one sincosf per component, then the double-angle identities (three doublings add < 1e-6 of
+    // error, far below the fp16 rounding of the operand; one sincosf body instead of twelve in the instruction stream)
+    float s0, c0, s1, c1, s2, c2;
+    sincosf(d0, &s0, &c0); sincosf(d1, &s1, &c1); sincosf(d2, &s2, &c2);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        e[3 + 6 * k] = s0; e[4 + 6 * k] = s1; e[5 + 6 * k] = s2;
+        e[6 + 6 * k] = c0; e[7 + 6 * k] = c1; e[8 + 6 * k] = c2;
+        const float t0 = 2.0f * s0 * c0, t1 = 2.0f * s1 * c1, t2 = 2.0f * s2 * c2;
+        c0 = 1.0f - 2.0f * s0 * s0; c1 = 1.0f - 2.0f * s1 * s1; c2 = 1.0f - 2.0f * s2 * s2;
+        s0 = t0; s1 = t1; s2 = t2;
+    }
+#pragma unroll
+    for (int j = 27; j < 32; j++) e[j] = 1.0f;
+#pragma unroll
+    for (uint32_t c = 0; c < 4; c++) {
+        uint4 pk = make_uint4(pack_h2(e[c * 8], e[c * 8 + 1]), pack_h2(e[c * 8 + 2], e[c * 8 + 3]),
+                              pack_h2(e[c * 8 + 4], e[c * 8 + 5]), pack_h2(e[c * 8 + 6], e[c * 8 + 7]));
+        if (!valid) pk = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(row, 4 + c)) = pk;
+    }
+}
+
+// swizzled smem tile (128 rows x 128 B) -> rows [row0, row0 + 128) of a row-major [M, 64] half plane.  Consecutive
+// lanes take consecutive 16-byte chunks, so every store instruction of a warp writes 4 complete 128-byte lines
+// (the per-row stores of the epilogue would write 32 quarter-lines instead).
+__device__ __noinline__ void copy_tile_out(const uint8_t *tile, __half *plane, uint32_t row0, uint32_t Mrows, uint32_t tid) {
+#pragma unroll
+    for (uint32_t i = 0; i < 8; i++) {
+        const uint32_t q = i * 128 + tid, row = q >> 3, ch = q & 7u, g = row0 + row;
+        if (g < Mrows)
+            *reinterpret_cast<uint4 *>(plane + (size_t)g * 64 + ch * 8) =
+                *reinterpret_cast<const uint4 *>(tile + umma::sw128_offset(row, ch));
     }
 }
 
@@ -194,76 +235,75 @@ k_field_forward(const FieldFwdArgs p) {
         umma::fence_after_sync();
     };
 
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // this thread's input row of the NEXT tile, prefetched into registers while the current tile is in flight
+    uint4 nx0, nx1, nx2, nx3;
+    float nd0, nd1, nd2, npx, npy, npz;
+    auto prefetch_inputs = [&](uint32_t tile) {
         const uint32_t g = tile * 128 + tid;
-        const bool valid = g < Mrows;
-        // ---- inputs: x_en row and the direction encoding -> XV tile
-        {
-            uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, x2 = x0, x3 = x0;
-            float d0 = 0, d1 = 0, d2 = 0;
-            if (valid) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(p.x_en + (size_t)g * 32);
-                x0 = __ldg(src); x1 = __ldg(src + 1); x2 = __ldg(src + 2); x3 = __ldg(src + 3);
-                d0 = p.dirs[(size_t)g * 3]; d1 = p.dirs[(size_t)g * 3 + 1]; d2 = p.dirs[(size_t)g * 3 + 2];
-            }
-            uint8_t *xv = smem + S_XV;
-            *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 0)) = x0;
-            *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 1)) = x1;
-            *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 2)) = x2;
-            *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 3)) = x3;
-            float e[32];
-            e[0] = d0; e[1] = d1; e[2] = d2;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float f = (float)(1 << k);
-                float s0, c0, s1, c1, s2, c2;
-                sincosf(d0 * f, &s0, &c0); sincosf(d1 * f, &s1, &c1); sincosf(d2 * f, &s2, &c2);
-                e[3 + 6 * k] = s0; e[4 + 6 * k] = s1; e[5 + 6 * k] = s2;
-                e[6 + 6 * k] = c0; e[7 + 6 * k] = c1; e[8 + 6 * k] = c2;
-            }
-#pragma unroll
-            for (int j = 27; j < 32; j++) e[j] = 1.0f;
-#pragma unroll
-            for (uint32_t c = 0; c < 4; c++) {
-                const uint4 pk = make_uint4(pack_h2(e[c * 8], e[c * 8 + 1]), pack_h2(e[c * 8 + 2], e[c * 8 + 3]),
-                                            pack_h2(e[c * 8 + 4], e[c * 8 + 5]), pack_h2(e[c * 8 + 6], e[c * 8 + 7]));
-                *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 4 + c)) = pk;
-            }
+        nx0 = nx1 = nx2 = nx3 = make_uint4(0, 0, 0, 0);
+        nd0 = nd1 = nd2 = npx = npy = npz = 0.0f;
+        if (tile < ntiles && g < Mrows) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.x_en + (size_t)g * 32);
+            nx0 = __ldg(src); nx1 = __ldg(src + 1); nx2 = __ldg(src + 2); nx3 = __ldg(src + 3);
+            nd0 = __ldg(p.dirs + (size_t)g * 3); nd1 = __ldg(p.dirs + (size_t)g * 3 + 1); nd2 = __ldg(p.dirs + (size_t)g * 3 + 2);
+            npx = __ldg(p.xyz + (size_t)g * 3); npy = __ldg(p.xyz + (size_t)g * 3 + 1); npz = __ldg(p.xyz + (size_t)g * 3 + 2);
         }
-        publish();
-        __half *act = (p.act && valid) ? p.act + (size_t)g * 64 : nullptr;
+    };
+    auto write_xv = [&](bool valid) {
+        uint8_t *xv = smem + S_XV;
+        *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 0)) = nx0;
+        *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 1)) = nx1;
+        *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 2)) = nx2;
+        *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 3)) = nx3;
+        write_view_chunks(xv, tid, nd0, nd1, nd2, true);
+        (void)valid;
+    };
+
+    prefetch_inputs(blockIdx.x);
+    write_xv(true);
+    float px = npx, py = npy, pz = npz;                     // this tile's sample position (gaussian density bias)
+    publish();
+
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t g = tile * 128 + tid, row0 = tile * 128;
+        const bool valid = g < Mrows;
+        const bool save = p.act != nullptr;
         const size_t act_stride = (size_t)p.M * 64;
 
         // ---- trunk layer 0: h1 = relu(x_en W1^T), K = 32
         if (tid == 0) mma_run(sXV, 0, sW + F_W1V, 0, 2, ID64, true);
+        prefetch_inputs(tile + gridDim.x);                  // loads complete behind the next layers
         sync_mma();
-        epilogue_row64<true>(trow, smem + S_H0, tid, act);
+        epilogue_row64<true>(trow, smem + S_H0, tid, nullptr);
         publish();
         // ---- trunk layer 1: h2 = relu(h1 W2^T)
         if (tid == 0) mma_run(sH0, 0, sW + F_W2, 0, 4, ID64, true);
+        if (save) copy_tile_out(smem + S_H0, p.act, row0, Mrows, tid);
         sync_mma();
-        epilogue_row64<true>(trow, smem + S_H1, tid, act ? act + act_stride : nullptr);
+        epilogue_row64<true>(trow, smem + S_H1, tid, nullptr);
         publish();
         // ---- trunk layer 2: fea = h2 W3^T (no activation)
         if (tid == 0) mma_run(sH1, 0, sW + F_W3, 0, 4, ID64, true);
+        if (save) copy_tile_out(smem + S_H1, p.act + act_stride, row0, Mrows, tid);
         sync_mma();
-        epilogue_row64<false>(trow, smem + S_FEA, tid, act ? act + 2 * act_stride : nullptr);
+        epilogue_row64<false>(trow, smem + S_FEA, tid, nullptr);
         publish();
         // ---- density layer 0: hd = relu(fea Wd1^T)
         if (tid == 0) mma_run(sFEA, 0, sW + F_WD1, 0, 4, ID64, true);
+        if (save) copy_tile_out(smem + S_FEA, p.act + 2 * act_stride, row0, Mrows, tid);
         sync_mma();
-        epilogue_row64<true>(trow, smem + S_H0, tid, act ? act + 3 * act_stride : nullptr);
+        epilogue_row64<true>(trow, smem + S_H0, tid, nullptr);
         publish();
         // ---- density layer 1: raw = hd Wd2^T (N = 16, lane 0 is the output); sigma = exp(raw + 5 exp(-|x|^2 / 0.08))
         if (tid == 0) mma_run(sH0, 0, sW + F_WD2, 0, 4, ID16, true);
+        if (save) copy_tile_out(smem + S_H0, p.act + 3 * act_stride, row0, Mrows, tid);
         sync_mma();
         {
             uint32_t r[16];
             umma::tmem_ld16(trow, r);
             umma::tmem_ld_wait();
             if (valid) {
-                const float x = p.xyz[(size_t)g * 3], y = p.xyz[(size_t)g * 3 + 1], z = p.xyz[(size_t)g * 3 + 2];
-                const float gauss = 5.0f * expf(-(x * x + y * y + z * z) / (2 * 0.2f * 0.2f));
+                const float gauss = 5.0f * expf(-(px * px + py * py + pz * pz) / (2 * 0.2f * 0.2f));
                 const float arg = __uint_as_float(r[0]) + gauss;
                 p.sigma[g] = expf(arg);
                 if (p.sigma_arg) p.sigma_arg[g] = arg;
@@ -278,10 +318,15 @@ k_field_forward(const FieldFwdArgs p) {
             mma_run(sXV, 2, sW + F_W1V, 2, 2, ID64, false);
         }
         sync_mma();
-        epilogue_row64<true>(trow, smem + S_H1, tid, act ? act + 4 * act_stride : nullptr);
+        // the XV tile is free from here on: stage the next tile's inputs (published by the barriers below)
+        write_xv(true);
+        px = npx; py = npy; pz = npz;
+        // note: px/py/pz of THIS tile were consumed by the density head above
+        epilogue_row64<true>(trow, smem + S_H1, tid, nullptr);
         publish();
         // ---- colour layer 1: rgba = sigmoid(hr Wr2^T) (N = 16, lanes 0..3)
         if (tid == 0) mma_run(sH1, 0, sW + F_WR2, 0, 4, ID16, true);
+        if (save) copy_tile_out(smem + S_H1, p.act + 4 * act_stride, row0, Mrows, tid);
         sync_mma();
         {
             uint32_t r[16];
@@ -294,6 +339,7 @@ k_field_forward(const FieldFwdArgs p) {
                 *reinterpret_cast<uint2 *>(p.rgba + (size_t)g * 4) = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
             }
         }
+        umma::fence_proxy_async();          // the XV rows written after colour layer 0 feed the next tile's first MMA
         umma::fence_before_sync();
         __syncthreads();
         umma::fence_after_sync();
@@ -320,7 +366,8 @@ constexpr uint32_t SB_H2 = SB_H1 + 16384;
 constexpr uint32_t SB_FEA = SB_H2 + 16384;
 constexpr uint32_t SB_HD = SB_FEA + 16384;
 constexpr uint32_t SB_HR = SB_HD + 16384;
-constexpr uint32_t S_BWD_BYTES = SB_HR + 16384;     // 45056 + 10 * 16384 = 208896
+constexpr uint32_t SB_XV2 = SB_HR + 16384;          // second x_en | view buffer (tiles alternate)
+constexpr uint32_t S_BWD_BYTES = SB_XV2 + 16384;    // 45056 + 11 * 16384 = 225280
 // TMEM columns
 constexpr uint32_t C_DG = 0, C_W1 = 64, C_W2 = 96, C_W3 = 160, C_PAIR = 224, C_R1V = 288, C_D2 = 320, C_R2 = 384;
 constexpr uint32_t kTmemColsBwd = 512;
@@ -345,51 +392,94 @@ __device__ __forceinline__ uint64_t mndesc(uint32_t tile_addr, uint32_t ks, uint
     return umma::make_desc(tile_addr + ks * 2048 + col0 * 2, 16384, 1024, umma::kLayoutSW128);
 }
 
-// dgrad epilogue: DG row (64 fp32) * relu'(activation row) -> fp16 -> gradient tile
-template <bool kMask>
-__device__ __forceinline__ void bwd_epilogue_row64(uint32_t tmem_row_addr, const uint8_t *act_tile, uint8_t *dst_tile,
-                                                   uint32_t row) {
+// The backward CTA has 8 warps: warp w owns the TMEM lane quarter 32 (w % 4) (a hardware restriction of tcgen05.ld) and
+// the column half (w / 4) of every 64-wide accumulator, so each epilogue is split over twice the warps of the forward
+// kernel and twice as many warps are in flight to hide the TMEM / shared-memory / barrier latencies between the MMAs.
+constexpr uint32_t kBwdThreads = 256;
+
+// dgrad epilogue of one row and one column half: DG (32 fp32) * relu'(activation) -> fp16 -> gradient tile.
+// Deliberately not inlined: five call sites per tile, and the kernel's instruction footprint matters (one CTA per SM).
+__device__ __noinline__ void bwd_epilogue_half(uint32_t taddr, const uint8_t *act_tile, uint8_t *dst_tile, uint32_t row,
+                                               uint32_t half) {
+    uint32_t a[32];
+    umma::tmem_ld32(taddr, a);
+    umma::tmem_ld_wait();
 #pragma unroll
-    for (uint32_t h = 0; h < 2; h++) {
-        uint32_t a[32];
-        umma::tmem_ld32(tmem_row_addr + h * 32, a);
-        umma::tmem_ld_wait();
+    for (uint32_t c = 0; c < 4; c++) {
+        float v[8];
 #pragma unroll
-        for (uint32_t c = 0; c < 4; c++) {
-            float v[8];
+        for (int j = 0; j < 8; j++) v[j] = __uint_as_float(a[c * 8 + j]);
+        if (act_tile) {
+            const uint4 m = *reinterpret_cast<const uint4 *>(act_tile + umma::sw128_offset(row, half * 4 + c));
+            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = __uint_as_float(a[c * 8 + j]);
-            if (kMask) {
-                const uint4 m = *reinterpret_cast<const uint4 *>(act_tile + umma::sw128_offset(row, h * 4 + c));
-                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    // fp16 activation after ReLU is > 0 iff its bit pattern is non-zero and not negative zero
-                    if ((mw[j] & 0x7fffu) == 0) v[2 * j] = 0.0f;
-                    if ((mw[j] & 0x7fff0000u) == 0) v[2 * j + 1] = 0.0f;
-                }
+            for (int j = 0; j < 4; j++) {
+                // fp16 activation after ReLU is > 0 iff its bit pattern is non-zero and not negative zero
+                if ((mw[j] & 0x7fffu) == 0) v[2 * j] = 0.0f;
+                if ((mw[j] & 0x7fff0000u) == 0) v[2 * j + 1] = 0.0f;
             }
-            const uint4 pk = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-            *reinterpret_cast<uint4 *>(dst_tile + umma::sw128_offset(row, h * 4 + c)) = pk;
         }
+        const uint4 pk = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        *reinterpret_cast<uint4 *>(dst_tile + umma::sw128_offset(row, half * 4 + c)) = pk;
     }
 }
 
-__global__ void __launch_bounds__(128, 1)
+// 16 accumulator columns of one weight-gradient row -> fp32 atomics on the flat parameter gradient
+__device__ __noinline__ void bwd_flush16(uint32_t taddr, float *dst, bool on) {
+    uint32_t r[16];
+    umma::tmem_ld16(taddr, r);
+    umma::tmem_ld_wait();
+    if (on) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) atomicAdd(dst + j, __uint_as_float(r[j]));
+    }
+}
+
+// ---- asynchronous global -> shared copies (LDGSTS): the activation tiles of the NEXT tile stream in behind the MMAs
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src, bool valid) {
+    const uint32_t sz = valid ? 16u : 0u;                   // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// rows [row0, row0 + 128) of a row-major [M, 64] half plane -> swizzled tile; a warp's copy covers 4 complete lines
+__device__ __forceinline__ void load_tile_async(uint32_t tile_smem, const __half *plane, uint32_t row0, uint32_t Mrows,
+                                                uint32_t tid) {
+#pragma unroll
+    for (uint32_t i = 0; i < 1024 / kBwdThreads; i++) {
+        const uint32_t q = i * kBwdThreads + tid, row = q >> 3, ch = q & 7u, g = row0 + row;
+        const bool ok = g < Mrows;
+        cp_async16(tile_smem + umma::sw128_offset(row, ch), plane + (ok ? (size_t)g * 64 + ch * 8 : 0), ok);
+    }
+}
+// rows of the [M, 32] half encoding -> chunks 0..3 of the XV tile
+__device__ __forceinline__ void load_xen_async(uint32_t tile_smem, const __half *x_en, uint32_t row0, uint32_t Mrows,
+                                               uint32_t tid) {
+#pragma unroll
+    for (uint32_t i = 0; i < 512 / kBwdThreads; i++) {
+        const uint32_t q = i * kBwdThreads + tid, row = q >> 2, ch = q & 3u, g = row0 + row;
+        const bool ok = g < Mrows;
+        cp_async16(tile_smem + umma::sw128_offset(row, ch), x_en + (ok ? (size_t)g * 32 + ch * 8 : 0), ok);
+    }
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
 k_field_backward(const FieldBwdArgs p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t half = warp >> 2, row = (warp & 3u) * 32u + (tid & 31u);     // column half and tile row of this thread
     const uint32_t Mrows = p.count_dev ? min(p.M, (uint32_t)max(*p.count_dev, 0)) : p.M;
     const uint32_t ntiles = (Mrows + 127) / 128;
     if (blockIdx.x >= ntiles) return;
 
-    for (uint32_t i = tid; i < B_BYTES / 16; i += 128)
+    for (uint32_t i = tid; i < B_BYTES / 16; i += kBwdThreads)
         reinterpret_cast<uint4 *>(smem + SB_W)[i] = __ldg(reinterpret_cast<const uint4 *>(p.wimg) + i);
     // the T16 tile is only ever written in its first 4 chunks per row: clear the rest once
-    for (uint32_t i = tid; i < 16384 / 16; i += 128) reinterpret_cast<uint4 *>(smem + SB_T16)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < 16384 / 16; i += kBwdThreads) reinterpret_cast<uint4 *>(smem + SB_T16)[i] = make_uint4(0, 0, 0, 0);
     if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemColsBwd);
     if (tid == 0) {
         umma::mbar_init(&bar, 1);
@@ -400,7 +490,7 @@ k_field_backward(const FieldBwdArgs p) {
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t trow = tmem + ((warp * 32u) << 16);
+    const uint32_t trow = tmem + (((warp & 3u) * 32u) << 16);
     const uint32_t base = umma::smem_u32(smem);
     const uint32_t sW = base + SB_W, sT16 = base + SB_T16, sGA = base + SB_GA, sGB = base + SB_GB, sGC = base + SB_GC,
                    sXV = base + SB_XV, sH1 = base + SB_H1, sH2 = base + SB_H2, sFEA = base + SB_FEA, sHD = base + SB_HD,
@@ -409,6 +499,7 @@ k_field_backward(const FieldBwdArgs p) {
     constexpr uint32_t WG64 = umma::make_idesc_f16(128, 64, 1, 1), WG32 = umma::make_idesc_f16(128, 32, 1, 1);
     uint32_t phase = 0;
     bool first_tile = true;
+    const size_t act_stride = (size_t)p.M * 64;
 
     auto dgrad = [&](uint32_t a, uint32_t ak, uint32_t b, uint32_t bk, uint32_t nk, uint32_t idesc, bool first) {
         for (uint32_t k = 0; k < nk; k++)
@@ -419,8 +510,7 @@ k_field_backward(const FieldBwdArgs p) {
         for (uint32_t k = 0; k < 8; k++)
             umma::mma_f16_ss(tmem + dcol, mndesc(a, k, 0), mndesc(b, k, bcol0), idesc, !(first_tile && k == 0));
     };
-    auto sync_mma = [&]() {
-        if (tid == 0) umma::commit(&bar);
+    auto wait_mma = [&]() {                 // completion of everything committed by the issuing thread so far
         umma::mbar_wait(&bar, phase);
         phase ^= 1;
         umma::fence_after_sync();
@@ -431,153 +521,199 @@ k_field_backward(const FieldBwdArgs p) {
         __syncthreads();
         umma::fence_after_sync();
     };
+    auto epilogue = [&](const uint8_t *mask_tile, uint32_t dst_off) {
+        bwd_epilogue_half(trow + C_DG + 32 * half, mask_tile, smem + dst_off, row, half);
+    };
+
+    // ---- per-row inputs prefetched one tile ahead into registers: the warps of column half 0 build the head
+    //      gradients of their row (T16), the warps of half 1 its direction encoding (XV chunks 4..7)
+    uint2 n_rgba = make_uint2(0, 0); float4 n_drgba = make_float4(0, 0, 0, 0);
+    float n_dsig = 0, n_sarg = 0, n_d0 = 0, n_d1 = 0, n_d2 = 0;
+    auto prefetch_row = [&](uint32_t tile) {
+        const uint32_t g = tile * 128 + row;
+        const bool ok = tile < ntiles && g < Mrows;
+        if (half == 0) {
+            n_rgba = make_uint2(0, 0); n_drgba = make_float4(0, 0, 0, 0); n_dsig = 0; n_sarg = 0;
+            if (ok) {
+                n_rgba = __ldg(reinterpret_cast<const uint2 *>(p.rgba + (size_t)g * 4));
+                n_drgba = __ldg(reinterpret_cast<const float4 *>(p.d_rgba + (size_t)g * 4));
+                n_dsig = __ldg(p.d_sigma + g); n_sarg = __ldg(p.sigma_arg + g);
+            }
+        } else {
+            n_d0 = n_d1 = n_d2 = 0;
+            if (ok) {
+                n_d0 = __ldg(p.dirs + (size_t)g * 3); n_d1 = __ldg(p.dirs + (size_t)g * 3 + 1); n_d2 = __ldg(p.dirs + (size_t)g * 3 + 2);
+            }
+        }
+    };
+    // head gradients of a row: colour = g * y (1 - y) (sigmoid), density = g * exp(clamp(arg, -15, 15)) (trunc_exp)
+    auto write_t16 = [&]() {
+        if (half != 0) return;
+        const float2 y01 = __half22float2(*reinterpret_cast<const __half2 *>(&n_rgba.x));
+        const float2 y23 = __half22float2(*reinterpret_cast<const __half2 *>(&n_rgba.y));
+        const float go0 = n_drgba.x * y01.x * (1 - y01.x), go1 = n_drgba.y * y01.y * (1 - y01.y);
+        const float go2 = n_drgba.z * y23.x * (1 - y23.x), go3 = n_drgba.w * y23.y * (1 - y23.y);
+        const float gd = n_dsig * expf(fminf(fmaxf(n_sarg, -15.0f), 15.0f));
+        uint8_t *t16 = smem + SB_T16;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(row, 0)) = make_uint4(pack_h2(go0, go1), pack_h2(go2, go3), 0, 0);
+        *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(row, 1)) = z;
+        *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(row, 2)) = make_uint4(pack_h2(gd, 0.0f), 0, 0, 0);
+        *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(row, 3)) = z;
+    };
+
+    // Order of one stage: the issuing thread launches the stage's dgrad MMAs, commits, then launches the stage's weight-
+    // gradient MMAs WITHOUT a commit.  The epilogue warps wake on the dgrad commit and work while the tensor pipe runs
+    // the weight gradients; tcgen05 MMAs complete in issue order, so the NEXT stage's commit also covers them -- which
+    // is when their operands (a gradient tile, an activation tile) may be overwritten / refilled.
+    //
+    // cp.async groups per tile, in commit order: G1 = {HR, HD, x_en of the next XV buffer}, G2 = {FEA}, G3 = {H2}, G4 = {H1}
+    {
+        const uint32_t row0 = blockIdx.x * 128;
+        load_tile_async(sHR, p.act + 4 * act_stride, row0, Mrows, tid);
+        load_tile_async(sHD, p.act + 3 * act_stride, row0, Mrows, tid);
+        load_xen_async(sXV, p.x_en, row0, Mrows, tid);
+        cp_async_commit();
+        load_tile_async(sFEA, p.act + 2 * act_stride, row0, Mrows, tid);
+        cp_async_commit();
+        load_tile_async(sH2, p.act + act_stride, row0, Mrows, tid);
+        cp_async_commit();
+        load_tile_async(sH1, p.act, row0, Mrows, tid);
+        cp_async_commit();
+        prefetch_row(blockIdx.x);
+        if (half == 1) write_view_chunks(smem + SB_XV, row, n_d0, n_d1, n_d2, row0 + row < Mrows);
+    }
+    const bool issuer_warp = warp == 0;
+    uint32_t xv_sel = 0;                   // which XV buffer the current tile uses
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t g = tile * 128 + tid;
+        const uint32_t g = tile * 128 + row;
         const bool valid = g < Mrows;
-        const size_t act_stride = (size_t)p.M * 64;
-        // ---- load this point's rows: x_en | view, h1, h2, fea, hd, hr; build the head gradients (T16)
-        {
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            uint8_t *tiles[5] = {smem + SB_H1, smem + SB_H2, smem + SB_FEA, smem + SB_HD, smem + SB_HR};
-#pragma unroll
-            for (int t = 0; t < 5; t++) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(p.act + t * act_stride + (size_t)g * 64);
-#pragma unroll
-                for (uint32_t c = 0; c < 8; c++)
-                    *reinterpret_cast<uint4 *>(tiles[t] + umma::sw128_offset(tid, c)) = valid ? __ldg(src + c) : z;
-            }
-            const uint4 *xs = reinterpret_cast<const uint4 *>(p.x_en + (size_t)g * 32);
-#pragma unroll
-            for (uint32_t c = 0; c < 4; c++)
-                *reinterpret_cast<uint4 *>(smem + SB_XV + umma::sw128_offset(tid, c)) = valid ? __ldg(xs + c) : z;
-            float d0 = 0, d1 = 0, d2 = 0;
-            if (valid) { d0 = p.dirs[(size_t)g * 3]; d1 = p.dirs[(size_t)g * 3 + 1]; d2 = p.dirs[(size_t)g * 3 + 2]; }
-            float e[32];
-            e[0] = d0; e[1] = d1; e[2] = d2;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float f = (float)(1 << k);
-                float s0, c0, s1, c1, s2, c2;
-                sincosf(d0 * f, &s0, &c0); sincosf(d1 * f, &s1, &c1); sincosf(d2 * f, &s2, &c2);
-                e[3 + 6 * k] = s0; e[4 + 6 * k] = s1; e[5 + 6 * k] = s2;
-                e[6 + 6 * k] = c0; e[7 + 6 * k] = c1; e[8 + 6 * k] = c2;
-            }
-#pragma unroll
-            for (int j = 27; j < 32; j++) e[j] = valid ? 1.0f : 0.0f;
-#pragma unroll
-            for (uint32_t c = 0; c < 4; c++) {
-                const uint4 pk = make_uint4(pack_h2(e[c * 8], e[c * 8 + 1]), pack_h2(e[c * 8 + 2], e[c * 8 + 3]),
-                                            pack_h2(e[c * 8 + 4], e[c * 8 + 5]), pack_h2(e[c * 8 + 6], e[c * 8 + 7]));
-                *reinterpret_cast<uint4 *>(smem + SB_XV + umma::sw128_offset(tid, 4 + c)) = valid ? pk : z;
-            }
-            // head gradients: colour = g * y (1 - y) (sigmoid), density = g * exp(clamp(arg, -15, 15)) (trunc_exp)
-            float go[4] = {0, 0, 0, 0}, gd = 0;
-            if (valid) {
-                const uint2 yy = *reinterpret_cast<const uint2 *>(p.rgba + (size_t)g * 4);
-                const float2 y01 = __half22float2(*reinterpret_cast<const __half2 *>(&yy.x));
-                const float2 y23 = __half22float2(*reinterpret_cast<const __half2 *>(&yy.y));
-                const float4 gr = *reinterpret_cast<const float4 *>(p.d_rgba + (size_t)g * 4);
-                go[0] = gr.x * y01.x * (1 - y01.x); go[1] = gr.y * y01.y * (1 - y01.y);
-                go[2] = gr.z * y23.x * (1 - y23.x); go[3] = gr.w * y23.y * (1 - y23.y);
-                gd = p.d_sigma[g] * expf(fminf(fmaxf(p.sigma_arg[g], -15.0f), 15.0f));
-            }
-            uint8_t *t16 = smem + SB_T16;
-            *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(tid, 0)) = make_uint4(pack_h2(go[0], go[1]), pack_h2(go[2], go[3]), 0, 0);
-            *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(tid, 1)) = z;
-            *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(tid, 2)) = make_uint4(pack_h2(gd, 0.0f), 0, 0, 0);
-            *reinterpret_cast<uint4 *>(t16 + umma::sw128_offset(tid, 3)) = z;
-        }
+        const uint32_t next = tile + gridDim.x;
+        const bool has_next = next < ntiles;
+        const uint32_t nrow0 = next * 128;
+        const uint32_t sXVc = xv_sel ? base + SB_XV2 : sXV, sXVn = xv_sel ? sXV : base + SB_XV2;
+        uint8_t *xv_next = smem + (xv_sel ? SB_XV : SB_XV2);
+
+        write_t16();                       // from the registers prefetched one tile ago
+        prefetch_row(next);                // consumed by the refill below (view chunks) and by the next write_t16
+        cp_async_wait<3>();                // G1 landed (this thread's part); the barrier below covers the other threads
         publish();
 
-        // ---- dHR = (dOr Wr2) * [hr > 0]
-        if (tid == 0) dgrad(sT16, 0, sW + B_W16T, 0, 1, ID64, true);
-        sync_mma();
-        bwd_epilogue_row64<true>(trow + C_DG, smem + SB_HR, smem + SB_GA, tid);
+        // ---- stage 1: dHR = (dOr Wr2) * [hr > 0]
+        if (issuer_warp && umma::elect_one()) {
+            dgrad(sT16, 0, sW + B_W16T, 0, 1, ID64, true);
+            umma::commit(&bar);
+        }
+        wait_mma();
+        epilogue(smem + SB_HR, SB_GA);
         publish();
-        // ---- dHD = (dOd Wd2) * [hd > 0];   wgrad of the two heads (A = T16^T)
-        if (tid == 0) {
+        // ---- stage 2: dHD = (dOd Wd2) * [hd > 0];   wgrad of the two heads (A = T16^T)
+        if (issuer_warp && umma::elect_one()) {
             dgrad(sT16, 1, sW + B_W16T, 1, 1, ID64, true);
+            umma::commit(&bar);
             wgrad(C_R2, sT16, sHR, 0, WG64);
             wgrad(C_D2, sT16, sHD, 0, WG64);
         }
-        sync_mma();
-        bwd_epilogue_row64<true>(trow + C_DG, smem + SB_HD, smem + SB_GB, tid);
+        wait_mma();
+        epilogue(smem + SB_HD, SB_GB);
+        cp_async_wait<2>();                // G2: FEA (and G1's x_en) for the weight gradients of stage 3
         publish();
-        // ---- dFEA = dHR Wr1f + dHD Wd1;   wgrad Wr1f | Wd1 (A = [dHR | dHD]^T, B = fea), Wr1v (A = dHR^T, B = view)
-        if (tid == 0) {
+        // ---- stage 3: dFEA = dHR Wr1f + dHD Wd1;   wgrad Wr1f | Wd1 (A = [dHR | dHD]^T, B = fea), Wr1v (A = dHR^T, B = view)
+        if (issuer_warp && umma::elect_one()) {
             dgrad(sGA, 0, sW + B_WR1FT, 0, 4, ID64, true);
             dgrad(sGB, 0, sW + B_WD1T, 0, 4, ID64, false);
+            umma::commit(&bar);
             wgrad(C_PAIR, sGA, sFEA, 0, WG64);
-            wgrad(C_R1V, sGA, sXV, 32, WG32);
+            wgrad(C_R1V, sGA, sXVc, 32, WG32);
         }
-        sync_mma();
-        bwd_epilogue_row64<false>(trow + C_DG, nullptr, smem + SB_GC, tid);
+        wait_mma();                        // ... which also means the head weight gradients of stage 2 are done:
+        if (has_next) {                    // HR / HD and the other XV buffer are free, refill them for the next tile
+            load_tile_async(sHR, p.act + 4 * act_stride, nrow0, Mrows, tid);
+            load_tile_async(sHD, p.act + 3 * act_stride, nrow0, Mrows, tid);
+            load_xen_async(sXVn, p.x_en, nrow0, Mrows, tid);
+        }
+        cp_async_commit();                 // G1'
+        if (half == 1) write_view_chunks(xv_next, row, n_d0, n_d1, n_d2, has_next && nrow0 + row < Mrows);
+        epilogue(nullptr, SB_GC);
+        cp_async_wait<2>();                // G3: H2
         publish();
-        // ---- dH2 = (dFEA W3) * [h2 > 0];   wgrad W3 (A = dFEA^T, B = h2)
-        if (tid == 0) {
+        // ---- stage 4: dH2 = (dFEA W3) * [h2 > 0];   wgrad W3 (A = dFEA^T, B = h2)
+        if (issuer_warp && umma::elect_one()) {
             dgrad(sGC, 0, sW + B_W3T, 0, 4, ID64, true);
+            umma::commit(&bar);
             wgrad(C_W3, sGC, sH2, 0, WG64);
         }
-        sync_mma();
-        bwd_epilogue_row64<true>(trow + C_DG, smem + SB_H2, smem + SB_GA, tid);
+        wait_mma();                        // stage-3 weight gradients done: FEA is free
+        if (has_next) load_tile_async(sFEA, p.act + 2 * act_stride, nrow0, Mrows, tid);
+        cp_async_commit();                 // G2'
+        epilogue(smem + SB_H2, SB_GA);
+        cp_async_wait<2>();                // G4: H1
         publish();
-        // ---- dH1 = (dH2 W2) * [h1 > 0];   wgrad W2 (A = dH2^T, B = h1)
-        if (tid == 0) {
+        // ---- stage 5: dH1 = (dH2 W2) * [h1 > 0];   wgrad W2 (A = dH2^T, B = h1)
+        if (issuer_warp && umma::elect_one()) {
             dgrad(sGA, 0, sW + B_W2T, 0, 4, ID64, true);
+            umma::commit(&bar);
             wgrad(C_W2, sGA, sH1, 0, WG64);
         }
-        sync_mma();
-        bwd_epilogue_row64<true>(trow + C_DG, smem + SB_H1, smem + SB_GB, tid);
+        wait_mma();                        // stage-4 weight gradients done: H2 is free
+        if (has_next) load_tile_async(sH2, p.act + act_stride, nrow0, Mrows, tid);
+        cp_async_commit();                 // G3'
+        epilogue(smem + SB_H1, SB_GB);
         publish();
-        // ---- dX = dH1 W1 (N = 32) -> global;   wgrad W1 (A = dH1^T, B = x_en)
-        if (tid == 0) {
+        // ---- stage 6: dX = dH1 W1 (N = 32) -> global;   wgrad W1 (A = dH1^T, B = x_en)
+        if (issuer_warp && umma::elect_one()) {
             dgrad(sGB, 0, sW + B_W1T, 0, 4, ID32, true);
-            wgrad(C_W1, sGB, sXV, 0, WG32);
+            umma::commit(&bar);
+            wgrad(C_W1, sGB, sXVc, 0, WG32);
         }
-        sync_mma();                                   // also drains every wgrad MMA that still reads this tile's smem
+        wait_mma();                        // stage-5 weight gradients done: H1 is free
+        if (has_next) load_tile_async(sH1, p.act, nrow0, Mrows, tid);
+        cp_async_commit();                 // G4'
         {
-            uint32_t a[32];
-            umma::tmem_ld32(trow + C_DG, a);
+            uint32_t a[16];
+            umma::tmem_ld16(trow + C_DG + 16 * half, a);
             umma::tmem_ld_wait();
             if (valid) {
-                uint4 *dst = reinterpret_cast<uint4 *>(p.d_x_en + (size_t)g * 32);
+                uint4 *dst = reinterpret_cast<uint4 *>(p.d_x_en + (size_t)g * 32) + half * 2;
 #pragma unroll
-                for (uint32_t c = 0; c < 4; c++)
+                for (uint32_t c = 0; c < 2; c++)
                     dst[c] = make_uint4(pack_h2(__uint_as_float(a[c * 8]), __uint_as_float(a[c * 8 + 1])),
                                         pack_h2(__uint_as_float(a[c * 8 + 2]), __uint_as_float(a[c * 8 + 3])),
                                         pack_h2(__uint_as_float(a[c * 8 + 4]), __uint_as_float(a[c * 8 + 5])),
                                         pack_h2(__uint_as_float(a[c * 8 + 6]), __uint_as_float(a[c * 8 + 7])));
             }
         }
+        // (the W1 weight gradient may still be running: nothing it reads -- GB, this tile's XV buffer -- is written
+        //  before the next tile's stage-1 commit has completed)
         umma::fence_before_sync();
         __syncthreads();
         umma::fence_after_sync();
         first_tile = false;
+        xv_sel ^= 1u;
     }
+    cp_async_wait<0>();
+    // drain the last weight-gradient MMAs before reading their accumulators
+    if (issuer_warp && umma::elect_one()) umma::commit(&bar);
+    wait_mma();
 
-    // ---- flush the weight-gradient accumulators: thread == TMEM lane == output neuron (row of dW)
+    // ---- flush the weight-gradient accumulators: TMEM lane == output neuron n (row of dW); the two column halves of
+    //      every accumulator go to the two warps that own the lane quarter
     if (!first_tile) {
-        const uint32_t n = tid;
-        auto flush = [&](uint32_t col, uint32_t ncols, float *dst, uint32_t ld, uint32_t coff, bool on) {
-            for (uint32_t c0 = 0; c0 < ncols; c0 += 16) {
-                uint32_t r[16];
-                umma::tmem_ld16(trow + col + c0, r);
-                umma::tmem_ld_wait();
-                if (on) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) atomicAdd(dst + (size_t)ld * 0 + coff + c0 + j, __uint_as_float(r[j]));
-                }
-            }
+        const uint32_t n = row;
+        auto flush = [&](uint32_t col, uint32_t ncols, float *dst, bool on) {
+            const uint32_t hc = ncols / 2;
+            for (uint32_t c0 = half * hc; c0 < (half + 1) * hc; c0 += 16) bwd_flush16(trow + col + c0, dst + c0, on);
         };
         // trunk
-        flush(C_W1, 32, p.g_trunk + T_W1 + n * 32, 0, 0, n < 64);
-        flush(C_W2, 64, p.g_trunk + T_W2 + n * 64, 0, 0, n < 64);
-        flush(C_W3, 64, p.g_trunk + T_W3 + n * 64, 0, 0, n < 64);
+        flush(C_W1, 32, p.g_trunk + T_W1 + n * 32, n < 64);
+        flush(C_W2, 64, p.g_trunk + T_W2 + n * 64, n < 64);
+        flush(C_W3, 64, p.g_trunk + T_W3 + n * 64, n < 64);
         // pair: rows 0..63 = colour layer 0 (fea columns 27..90), rows 64..127 = density layer 0
-        flush(C_PAIR, 64, n < 64 ? p.g_rgb + R_W1 + n * 96 + 27 : p.g_density + D_W1 + (n - 64) * 64, 0, 0, true);
+        flush(C_PAIR, 64, n < 64 ? p.g_rgb + R_W1 + n * 96 + 27 : p.g_density + D_W1 + (n - 64) * 64, true);
         // colour layer 0, view columns: internal col j -> lane j (j < 27) or 91 + (j - 27)
-        for (uint32_t c0 = 0; c0 < 32; c0 += 16) {
+        {
+            const uint32_t c0 = half * 16;
             uint32_t r[16];
             umma::tmem_ld16(trow + C_R1V + c0, r);
             umma::tmem_ld_wait();
@@ -590,8 +726,8 @@ k_field_backward(const FieldBwdArgs p) {
             }
         }
         // heads: A = T16, rows 0..15 = colour outputs, rows 16..31 = density outputs
-        flush(C_R2, 64, p.g_rgb + R_W2 + n * 64, 0, 0, n < 16);
-        flush(C_D2, 64, p.g_density + D_W2 + (n >= 16 ? n - 16 : 0) * 64, 0, 0, n >= 16 && n < 32);
+        flush(C_R2, 64, p.g_rgb + R_W2 + n * 64, n < 16);
+        flush(C_D2, 64, p.g_density + D_W2 + (n >= 16 ? n - 16 : 0) * 64, n >= 16 && n < 32);
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -664,7 +800,7 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
     a.count_dev = count_dev;
     const uint32_t ntiles = (M + 127) / 128;
     const uint32_t grid = ntiles < (uint32_t)sms ? ntiles : (uint32_t)sms;
-    k_field_backward<<<grid, 128, smem, nb_stream(stream)>>>(a);
+    k_field_backward<<<grid, kBwdThreads, smem, nb_stream(stream)>>>(a);
     NB_LAUNCH_CHECK();
     return 0;
 }

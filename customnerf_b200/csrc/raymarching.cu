@@ -328,6 +328,85 @@ k_march_count(const float *__restrict__ rays_o, const float *__restrict__ rays_d
     if (lane == 31) block_sums[blockIdx.x] = incl;
 }
 
+// ---- occupied-region bounds: rays that cannot meet an occupied cell are not marched at all ------------------------
+// obounds[level][6] = {max(x + 1), max(y + 1), max(z + 1), max(H - x), max(H - y), max(H - z)} over the set cells of a
+// cascade level (all zero = level empty; the buffer is zero-filled before the launch).
+__global__ void __launch_bounds__(256)
+k_occ_bounds(const uint8_t *__restrict__ grid, uint32_t C, uint32_t H, int32_t *__restrict__ obounds) {
+    const uint32_t H3 = H * H * H, wpl = H3 / 32;                    // 32-cell words per level
+    // one level at a time so that the six running maxima stay in registers; one warp reduction + 6 atomics per level
+    for (uint32_t level = 0; level < C; level++) {
+        int m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0;
+        for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < wpl; wi += gridDim.x * blockDim.x) {
+            uint32_t bits = __ldg(reinterpret_cast<const uint32_t *>(grid) + level * wpl + wi);
+            while (bits) {
+                const uint32_t b = (uint32_t)__ffs((int)bits) - 1u;
+                bits &= bits - 1u;
+                const uint32_t m = wi * 32 + b;
+                const int x = (int)nb_morton3D_invert(m), y = (int)nb_morton3D_invert(m >> 1), z = (int)nb_morton3D_invert(m >> 2);
+                m0 = max(m0, x + 1); m1 = max(m1, y + 1); m2 = max(m2, z + 1);
+                m3 = max(m3, (int)H - x); m4 = max(m4, (int)H - y); m5 = max(m5, (int)H - z);
+            }
+        }
+        m0 = __reduce_max_sync(0xffffffffu, m0); m1 = __reduce_max_sync(0xffffffffu, m1);
+        m2 = __reduce_max_sync(0xffffffffu, m2); m3 = __reduce_max_sync(0xffffffffu, m3);
+        m4 = __reduce_max_sync(0xffffffffu, m4); m5 = __reduce_max_sync(0xffffffffu, m5);
+        if (nb_lane() == 0 && m0 > 0) {
+            int32_t *o = obounds + level * 6;
+            atomicMax(o + 0, m0); atomicMax(o + 1, m1); atomicMax(o + 2, m2);
+            atomicMax(o + 3, m3); atomicMax(o + 4, m4); atomicMax(o + 5, m5);
+        }
+    }
+}
+
+// Can the ray segment t in [t0, far] come within one cell of an occupied cell of any level?  Conservative by
+// construction: each level's box of occupied cells is dilated by a full cell (>= 1/64 of the scene, five orders of
+// magnitude above the rounding of position and cell index, raymarching.cu:361-376) and the slab intervals by 1e-3, so a
+// "no" proves that every cell the marching loop would probe is empty and the ray emits nothing.  All lanes of a warp
+// evaluate the same ray: the result is warp-uniform.
+__device__ __forceinline__ bool rm_may_hit(const RayCtx &r, const int32_t *__restrict__ obounds, uint32_t C, uint32_t H,
+                                           float t0, float far) {
+    if (!obounds) return true;
+    // positions are clamped to the scene box (:361-363): only argue about rays whose whole range lies inside it
+    {
+        const float e0 = fmaf(t0, r.dx, r.ox), e1 = fmaf(t0, r.dy, r.oy), e2 = fmaf(t0, r.dz, r.oz);
+        const float f0 = fmaf(far, r.dx, r.ox), f1 = fmaf(far, r.dy, r.oy), f2 = fmaf(far, r.dz, r.oz);
+        const float lim = r.bound + 1e-3f;
+        const float m = fmaxf(fmaxf(fmaxf(fabsf(e0), fabsf(e1)), fabsf(e2)), fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fabsf(f2)));
+        if (!(m <= lim)) return true;           // (also catches NaN / inf)
+    }
+    for (uint32_t level = 0; level < C; level++) {
+        const int32_t *o = obounds + level * 6;
+        const int hx = __ldg(o + 0), hy = __ldg(o + 1), hz = __ldg(o + 2);
+        if (hx <= 0) continue;                                       // no occupied cell at this level
+        const int lx = (int)H - __ldg(o + 3), ly = (int)H - __ldg(o + 4), lz = (int)H - __ldg(o + 5);
+        const float mb = fminf(__int_as_float((127 + (int)level) << 23), r.bound);
+        const float cs = 2.0f * mb / (float)H;
+        // occupied cells [l, h) per axis, dilated by one cell
+        const float bx0 = (float)(lx - 1) * cs - mb, bx1 = (float)(hx + 1) * cs - mb;
+        const float by0 = (float)(ly - 1) * cs - mb, by1 = (float)(hy + 1) * cs - mb;
+        const float bz0 = (float)(lz - 1) * cs - mb, bz1 = (float)(hz + 1) * cs - mb;
+        float tn = t0 - 1e-3f, tf = far + 1e-3f;
+        bool miss = false;
+        const float oo[3] = {r.ox, r.oy, r.oz}, dd[3] = {r.dx, r.dy, r.dz};
+        const float b0[3] = {bx0, by0, bz0}, b1[3] = {bx1, by1, bz1};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (fabsf(dd[a]) < 1e-12f) {
+                if (oo[a] < b0[a] || oo[a] > b1[a]) miss = true;     // parallel to the slab and outside it
+            } else {
+                const float inv = 1.0f / dd[a];
+                float ta = (b0[a] - oo[a]) * inv, tb = (b1[a] - oo[a]) * inv;
+                if (ta > tb) { const float tmp = ta; ta = tb; tb = tmp; }
+                tn = fmaxf(tn, ta - 1e-3f);
+                tf = fminf(tf, tb + 1e-3f);
+            }
+        }
+        if (!miss && tn <= tf) return true;
+    }
+    return false;
+}
+
 // ---- pass 1 for the constant-step case (dt_gamma == 0): one WARP per ray, speculative segments -----------------
 // With a constant step every parameter the loop can visit lies on the lattice T(0) = t0, T(k+1) = fl(T(k) + dt), and
 // T(k) is available in closed form (rm_lattice_jump).  The loop is a chain over lattice indices:
@@ -375,7 +454,8 @@ __global__ void __launch_bounds__(kSegWarps * 32)
 k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
                   float bound, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                   const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
-                  int32_t *__restrict__ rays, int32_t *__restrict__ block_sums, float *__restrict__ trec, uint32_t tcap) {
+                  int32_t *__restrict__ rays, int32_t *__restrict__ block_sums, float *__restrict__ trec, uint32_t tcap,
+                  const int32_t *__restrict__ obounds) {
     __shared__ float rec_s[kSegWarps][32][kRecStride];
     __shared__ int ray_tot[kSegWarps];
     const uint32_t lane = nb_lane(), w = threadIdx.x >> 5;
@@ -389,7 +469,7 @@ k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ ra
         t0 = __fmaf_rn(rm_dt(r, t0), noises ? noises[n] : 0.0f, t0);      // :351
         float *rec = rec_s[w][lane];
         float *out = trec ? trec + (size_t)n * tcap : nullptr;
-        if (t0 < far) {
+        if (t0 < far && rm_may_hit(r, obounds, C, H, t0, far)) {
             const float kest = fminf(__fdividef(far - t0, dt) + 2.0f, 1.0e9f);
             const uint32_t seg = (uint32_t)min(max((int)ceilf(kest * (1.0f / 32.0f)), kSegMin), kSegMax);
             uint32_t K0 = 0;            // first index of the window == the chain's entry into it (exact for lane 0)
@@ -808,12 +888,14 @@ int nb200_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t 
     return 0;
 }
 
-// scratch layout (int32 units): [block sums: nb4][block prefixes: nb4][8 spare][sample records: N * tcap floats],
-// nb4 = ceil(N / 4) (the smallest rays-per-warp the launcher ever picks)
+// scratch layout (int32 units): [block sums: nb4][block prefixes: nb4][occupied bounds: 8 levels x 6 + 16 spare]
+// [sample records: N * tcap floats], nb4 = ceil(N / 4) (the smallest rays-per-warp the launcher ever picks)
+constexpr uint32_t kScratchFixed = 64;
 static inline uint32_t march_nb_max(uint32_t N) { return nb_div_up(N, 4); }
-uint32_t nb200_march_scratch_ints(uint32_t N) { return 2 * march_nb_max(N) + 8 + N * march_tcap(N); }
+uint32_t nb200_march_scratch_ints(uint32_t N) { return 2 * march_nb_max(N) + kScratchFixed + N * march_tcap(N); }
+static inline int32_t *march_obounds(int32_t *scratch, uint32_t N) { return scratch + 2 * march_nb_max(N); }
 static inline float *march_trec(int32_t *scratch, uint32_t N) {
-    return reinterpret_cast<float *>(scratch + 2 * march_nb_max(N) + 8);
+    return reinterpret_cast<float *>(scratch + 2 * march_nb_max(N) + kScratchFixed);
 }
 
 static int march_count_impl(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
@@ -830,9 +912,21 @@ static int march_count_impl(const float *rays_o, const float *rays_d, const uint
     const uint32_t nb = nb_div_up(N, rpw);
     int32_t *block_sums = scratch, *block_prefix = scratch + march_nb_max(N);
     cudaStream_t st = nb_stream(stream);
-    if (seg)
+    if (seg) {
+        static int nocull_env = -1;
+        if (nocull_env < 0) { const char *e = getenv("NB200_MARCH_CULL"); nocull_env = (e && atoi(e)) ? 0 : 1; }
+        int32_t *obounds = nullptr;
+        if (!nocull_env && C <= 8 && (H * H * H) % 32 == 0 && (reinterpret_cast<uintptr_t>(grid) & 3u) == 0) {
+            obounds = march_obounds(scratch, N);
+            cudaError_t e = cudaMemsetAsync(obounds, 0, 48 * sizeof(int32_t), st);
+            if (e != cudaSuccess) return (int)e;
+            k_occ_bounds<<<148, 256, 0, st>>>(grid, C, H, obounds);
+            NB_LAUNCH_CHECK();
+        }
         k_march_count_seg<<<nb, kSegWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, max_steps, N, C, H, nears, fars,
-                                                        noises, rays, block_sums, march_trec(scratch, N), march_tcap(N));
+                                                        noises, rays, block_sums, march_trec(scratch, N), march_tcap(N),
+                                                        obounds);
+    }
     else
         k_march_count<<<nb, kMarchBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
                                                   noises, rays, block_sums, rpw, march_trec(scratch, N), march_tcap(N));

@@ -205,9 +205,13 @@ class NeRFRenderer(nn.Module):
             xyzs, dirs, deltas, rays = raymarching.march_rays_train(
                 rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
                 self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps)
-            sigmas, rgbs, _ = self(xyzs, dirs)
-            rgbs = rgbs[..., :3]
-            weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs.float(), deltas, rays, T_thresh)
+            sigmas, rgba, _ = self(xyzs, dirs)
+            rgbs = rgba[..., :3].float()
+            if self._flag('train_conf') and rgba.shape[-1] > 3:
+                results.update(self._lgie_composites(sigmas, rgbs, rgba[..., 3:].float(), deltas, rays, T_thresh, prefix))
+                weights_sum, depth, image = results.pop('_all')
+            else:
+                weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
         else:
             weights_sum = torch.zeros(N, dtype=torch.float32, device=dev)
             depth = torch.zeros(N, dtype=torch.float32, device=dev)
@@ -241,6 +245,45 @@ class NeRFRenderer(nn.Module):
         results['weights_sum'] = weights_sum.reshape(*prefix)
         results['mask'] = (nears < fars).reshape(*prefix)
         return results
+
+    def _lgie_composites(self, sigmas, rgbs, masks, deltas, rays, T_thresh, prefix):
+        """LGIE outputs on the occupancy path: the same quantities NeRFRenderer.run builds with weights_sum_i
+        (reference :383-403, :407-474) -- all / fg / bg composites over the SAME samples, the rendered mask, soft or
+        hard edit mask, detach_bg -- composed from composite_rays_train.  The reference's run_cuda never produces them
+        although its trainer requires them; sample-level formulas are the dense path's."""
+        comp = raymarching.composite_rays_train
+        m1 = masks[..., :1]
+        sig_all, rgb_all = sigmas, rgbs
+        if self._flag('detach_bg', False):
+            # samples the mask head calls background contribute values but no gradient to the "all" image (:409-418)
+            edit_points = masks.mean(-1) >= 0.5
+            sig_all = torch.where(edit_points, sigmas, sigmas.detach())
+            rgb_all = torch.where(edit_points.unsqueeze(-1), rgbs, rgbs.detach())
+        out = {'_all': comp(sig_all, rgb_all, deltas, rays, T_thresh)}
+        if self._flag('soft_mask', False):
+            edit_mask = torch.sigmoid((m1 - self._flag('conf_thr', 0.5)) * 100)
+            sig_fg = sigmas * edit_mask.squeeze(-1)
+            sig_bg = sigmas * (1 - edit_mask.squeeze(-1))
+        else:
+            edit_mask = m1 > 0.5
+            sig_fg = torch.where(edit_mask.squeeze(-1), sigmas, torch.zeros_like(sigmas))
+            sig_bg = torch.where(edit_mask.squeeze(-1), torch.zeros_like(sigmas), sigmas)
+
+        def render_mask(sig):
+            # sum_i w_i * mask_i: the compositing kernel with the mask as (replicated) colour; optionally with
+            # detached weights (detach_mask_from_field, :460-463)
+            s = sig.detach() if self._flag('detach_mask_from_field', False) else sig
+            return comp(s, m1.expand(-1, 3).contiguous(), deltas, rays, T_thresh)[2][..., :1]
+
+        def pack(sig, rgb, with_all=None):
+            ws, depth, image = with_all if with_all is not None else comp(sig, rgb, deltas, rays, T_thresh)
+            return {'image': image.view(*prefix, 3), 'depth': depth.view(*prefix), 'weights_sum': ws.reshape(*prefix),
+                    'render_mask': render_mask(sig).view(*prefix, 1)}
+        out['render_mask'] = render_mask(sig_all).view(*prefix, 1)
+        out['sigma'], out['rgbs'], out['edit_mask'] = sigmas, rgbs, edit_mask
+        out['fg'] = pack(sig_fg, rgbs)
+        out['bg'] = pack(sig_bg, rgbs)
+        return out
 
     # ------------------------------------------------------------------------------------- occupancy grid
     @torch.no_grad()

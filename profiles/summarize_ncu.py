@@ -65,6 +65,37 @@ for rep in sorted(glob.glob(os.path.join(root, "gpurun_out", tag + "_k_*.ncu-rep
         for i in hits:
             out.append("  %-75s %s %s" % (m, vals[i], units[i]))
 
+# ---- dram traffic per launch of each captured kernel -> profiles/ncu_traffic.json (bench.py's roofline.traffic)
+STAGE_OF = {"k_field_backward": "field_backward", "k_field_forward": "field_forward", "k_grid_bwd_d3c2": "grid_encode_backward",
+            "k_grid_fwd_d3c2": "grid_encode_forward", "k_march_count_seg": "march_count", "k_march_count": "march_count",
+            "k_march_expand": "march_write", "k_fused_adam": "adam", "k_composite_train_fwd": "composite_forward",
+            "k_composite_train_bwd": "composite_backward"}
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+traffic = {}
+for rep in sorted(glob.glob(os.path.join(root, "gpurun_out", tag + "_k_*.ncu-rep"))):
+    kname = os.path.basename(rep)[len(tag) + 1:-len(".ncu-rep")]
+    try:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, timeout=300).stdout
+        rdr = list(csv.reader(txt.splitlines()))
+        hdr, units, vals = rdr[0], rdr[1], rdr[2]
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            tot += float(vals[i].replace(",", "")) * UNIT.get(units[i], 1.0)
+        if kname in STAGE_OF:
+            traffic[STAGE_OF[kname]] = tot
+    except Exception as e:
+        out.append("## traffic of %s unavailable: %s" % (kname, e))
+if traffic:
+    import json
+    tp = os.path.join(here, "ncu_traffic.json")
+    old = {}
+    if os.path.isfile(tp):
+        old = json.load(open(tp))
+    old.update(traffic)
+    old["_source"] = "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full captures tagged " + tag
+    json.dump(old, open(tp, "w"), indent=1, sort_keys=True)
+
 dst = os.path.join(here, tag + "_ncu_summary.txt")
 open(dst, "w").write("\n".join(out) + "\n")
 print("\n".join(out))

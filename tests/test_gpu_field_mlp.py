@@ -33,7 +33,7 @@ def _inputs(M, seed=1):
     return x.cuda(), d.cuda()
 
 
-@pytest.mark.parametrize("M", [1, 127, 128, 129, 5000, 40000])
+@pytest.mark.parametrize("M", [1, 127, 128, 129, 5000, 40000, 100003])
 def test_fused_forward_matches_library_path_and_oracle(M):
     net, opt = _net()
     x, d = _inputs(M)
@@ -56,7 +56,7 @@ def test_fused_forward_matches_library_path_and_oracle(M):
     assert_close(s1.cpu().numpy(), sr.numpy(), 2e-2, 1e-3, "sigma fused vs oracle")
 
 
-@pytest.mark.parametrize("M", [300, 20000])
+@pytest.mark.parametrize("M", [300, 20000, 70001])
 def test_fused_backward_matches_library_path(M):
     net, opt = _net()
     x, d = _inputs(M, seed=3)

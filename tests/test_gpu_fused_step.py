@@ -135,3 +135,28 @@ def test_stage_profile_reports_every_stage():
     prof = fs.profile_stages(3)
     assert list(prof) == fused_trainer.STAGES
     assert all(v > 0 for v in prof.values())
+
+
+def test_graph_capture_includes_nccl_allreduce():
+    """The sharded step's only collective (all-reduce of the flat gradient) is captured inside the step's CUDA graph.
+    A one-rank NCCL group exercises exactly that capture path on a single GPU; with one rank the sum is the identity,
+    so the losses must follow the un-synchronised run."""
+    import socket
+    import torch.distributed as dist
+    from customnerf_b200 import fused_trainer
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
+    try:
+        ma, mb = _models()
+        o, d, tgt = _batch()
+        plain = fused_trainer.FusedTrainStep(ma, N_RAYS, perturb=False, use_graph=True)
+        synced = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False, use_graph=True,
+                                              grad_sync=lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM))
+        la, lb = [], []
+        for _ in range(4):
+            plain.step(o, d, tgt); la.append(plain.last_stats()[0])
+            synced.step(o, d, tgt); lb.append(synced.last_stats()[0])
+        np.testing.assert_allclose(lb, la, rtol=2e-2)
+        assert lb[-1] < lb[0]
+    finally:
+        dist.destroy_process_group()

@@ -149,3 +149,50 @@ def test_train_step_harness_runs_and_reduces_loss(scene):
     after = eval_loss()
     assert np.isfinite(losses).all()
     assert after < 0.9 * before, (before, after)
+
+
+@pytest.mark.parametrize("soft", [False, True])
+def test_lgie_composites_on_cuda_path_match_dense_formulas(soft):
+    """all / fg / bg composites, rendered mask, soft | hard edit mask and detach_bg on the occupancy path against the
+    dense path's sample-level formulas (nerf/renderer.py:383-474) evaluated in fp64 on the same samples.
+    Tolerance abs 2e-4 (T_thresh = 1e-4 early-out + __expf)."""
+    from customnerf_b200.nerf import NeRFNetwork
+    opt = torch_ref.default_opt(cuda_ray=True, train_conf=0.01, soft_mask=soft, detach_bg=True, conf_thr=0.5)
+    net = NeRFNetwork(opt, encoding="hashgrid", **ENC).cuda()
+    g = torch.Generator().manual_seed(11)
+    counts = torch.randint(0, 70, (300,), generator=g)
+    counts[::17] = 0
+    offs = torch.cumsum(counts, 0) - counts
+    M = int(counts.sum())
+    rays = torch.stack([torch.arange(300), offs, counts], -1).int().cuda()
+    sig = (torch.rand(M, generator=g) * 40).cuda().requires_grad_()
+    rgb = torch.rand(M, 3, generator=g).cuda().requires_grad_()
+    msk = torch.rand(M, 1, generator=g).cuda()
+    deltas = torch.stack([torch.full((M,), 0.0034), torch.rand(M, generator=g) * 0.02 + 0.0034], -1).cuda()
+    out = net._lgie_composites(sig, rgb, msk, deltas, rays, 1e-4, (300,))
+    ws_all, _, img_all = out['_all']
+
+    s64, c64, m64, d64 = (t.detach().double().cpu() for t in (sig, rgb, msk, deltas))
+    em = torch.sigmoid((m64 - 0.5) * 100) if soft else (m64 > 0.5).double()
+
+    def dense(sg):
+        img, ws, rm = torch.zeros(300, 3, dtype=torch.float64), torch.zeros(300, dtype=torch.float64), torch.zeros(300, dtype=torch.float64)
+        for r in range(300):
+            o, n = int(offs[r]), int(counts[r])
+            a = 1 - torch.exp(-sg[o:o + n] * d64[o:o + n, 0])
+            T = torch.cumprod(torch.cat([torch.ones(1, dtype=torch.float64), 1 - a]), 0)[:-1]
+            w = a * T
+            img[r], ws[r], rm[r] = (w[:, None] * c64[o:o + n]).sum(0), w.sum(), (w * m64[o:o + n, 0]).sum()
+        return img, ws, rm
+    for name, sg, got in (("all", s64, (img_all, ws_all, out['render_mask'])),
+                          ("fg", s64 * em[:, 0], (out['fg']['image'], out['fg']['weights_sum'], out['fg']['render_mask'])),
+                          ("bg", s64 * (1 - em[:, 0]), (out['bg']['image'], out['bg']['weights_sum'], out['bg']['render_mask']))):
+        img, ws, rm = dense(sg)
+        assert_close(got[0].detach().cpu().numpy(), img.numpy(), 0, 2e-4, name + " image")
+        assert_close(got[1].detach().cpu().numpy(), ws.numpy(), 0, 2e-4, name + " weights_sum")
+        assert_close(got[2].detach().cpu().numpy().reshape(-1), rm.numpy(), 0, 2e-4, name + " render_mask")
+    # detach_bg: background samples (mask < 0.5) get no gradient from the "all" image, foreground samples do
+    img_all.sum().backward()
+    bgs = (msk[:, 0] < 0.5)
+    assert float(sig.grad[bgs].abs().max()) == 0.0 and float(rgb.grad[bgs].abs().max()) == 0.0
+    assert float(sig.grad[~bgs].abs().max()) > 0.0
