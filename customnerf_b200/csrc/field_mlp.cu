@@ -44,6 +44,8 @@ constexpr uint32_t B_BYTES = 45056;
 constexpr uint32_t T_W1 = 0, T_W2 = 64 * 32, T_W3 = 64 * 32 + 64 * 64;      // trunk:   [64x32][64x64][64x64]
 constexpr uint32_t D_W1 = 0, D_W2 = 64 * 64;                                 // density: [64x64][16x64]
 constexpr uint32_t R_W1 = 0, R_W2 = 64 * 96;                                 // colour:  [64x96][16x64]
+constexpr uint32_t kTrunkFloats = 64 * 32 + 2 * 64 * 64, kDensityFloats = 64 * 64 + 16 * 64, kRgbFloats = 64 * 96 + 16 * 64;
+constexpr uint32_t kWgradFloats = kTrunkFloats + kDensityFloats + kRgbFloats;   // 22528: one slab = [trunk | density | rgb]
 
 __device__ __forceinline__ void put(uint8_t *img, uint32_t row, uint32_t col, float v) {
     *reinterpret_cast<__half *>(img + umma::sw128_offset(row, col >> 3) + (col & 7u) * 2) = __float2half_rn(v);
@@ -147,10 +149,11 @@ __device__ __noinline__ void epilogue_row64(uint32_t tmem_row_addr, uint8_t *til
 __device__ __noinline__ void write_view_chunks(uint8_t *xv, uint32_t row, float d0, float d1, float d2, bool valid) {
     float e[32];
     e[0] = d0; e[1] = d1; e[2] = d2;
-    // sin / cos of 2^k d: one sincosf per component, then the double-angle identities (three doublings add < 1e-6 of
+    // sin / cos of 2^k d: one __sincosf per component (|d| <= 1 for unit directions: abs error < 4e-7, three orders
+    // below the fp16 rounding of the operand), then the double-angle identities (three doublings add < 1e-6 of
     // error, far below the fp16 rounding of the operand; one sincosf body instead of twelve in the instruction stream)
     float s0, c0, s1, c1, s2, c2;
-    sincosf(d0, &s0, &c0); sincosf(d1, &s1, &c1); sincosf(d2, &s2, &c2);
+    __sincosf(d0, &s0, &c0); __sincosf(d1, &s1, &c1); __sincosf(d2, &s2, &c2);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         e[3 + 6 * k] = s0; e[4 + 6 * k] = s1; e[5 + 6 * k] = s2;
@@ -383,6 +386,7 @@ struct FieldBwdArgs {
     const uint8_t *wimg;      // backward weight image
     __half *d_x_en;           // [M, 32]
     float *g_trunk, *g_density, *g_rgb;   // flat fp32 parameter gradients, ACCUMULATED INTO
+    float *slabs;                         // [gridDim.x][kWgradFloats] per-CTA partial sums, or null (atomics)
     uint32_t M;               // rows allocated (the stride of `act` planes)
     const int32_t *count_dev; // when non-null only rows < min(M, *count_dev) are processed
 };
@@ -424,14 +428,22 @@ __device__ __noinline__ void bwd_epilogue_half(uint32_t taddr, const uint8_t *ac
     }
 }
 
-// 16 accumulator columns of one weight-gradient row -> fp32 atomics on the flat parameter gradient
-__device__ __noinline__ void bwd_flush16(uint32_t taddr, float *dst, bool on) {
+// 16 accumulator columns of one weight-gradient row -> this CTA's private partial-sum slab (plain 16-byte stores; a
+// second small kernel adds the slabs into the flat parameter gradient), or, without a slab, fp32 atomics straight on the
+// gradient (every CTA then hits the same 22 k addresses at the same time: ~25 % of the kernel in the r01e profile)
+__device__ __noinline__ void bwd_flush16(uint32_t taddr, float *dst, bool on, bool slab) {
     uint32_t r[16];
     umma::tmem_ld16(taddr, r);
     umma::tmem_ld_wait();
     if (on) {
+        if (slab) {
 #pragma unroll
-        for (int j = 0; j < 16; j++) atomicAdd(dst + j, __uint_as_float(r[j]));
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<uint4 *>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) atomicAdd(dst + j, __uint_as_float(r[j]));
+        }
     }
 }
 
@@ -701,16 +713,37 @@ k_field_backward(const FieldBwdArgs p) {
     //      every accumulator go to the two warps that own the lane quarter
     if (!first_tile) {
         const uint32_t n = row;
+        const bool slab = p.slabs != nullptr;
+        float *gt = p.g_trunk, *gd = p.g_density, *gr = p.g_rgb;
+        if (slab) {
+            gt = p.slabs + (size_t)blockIdx.x * kWgradFloats;
+            gd = gt + kTrunkFloats;
+            gr = gd + kDensityFloats;
+        }
         auto flush = [&](uint32_t col, uint32_t ncols, float *dst, bool on) {
             const uint32_t hc = ncols / 2;
-            for (uint32_t c0 = half * hc; c0 < (half + 1) * hc; c0 += 16) bwd_flush16(trow + col + c0, dst + c0, on);
+            for (uint32_t c0 = half * hc; c0 < (half + 1) * hc; c0 += 16) bwd_flush16(trow + col + c0, dst + c0, on, slab);
         };
         // trunk
-        flush(C_W1, 32, p.g_trunk + T_W1 + n * 32, n < 64);
-        flush(C_W2, 64, p.g_trunk + T_W2 + n * 64, n < 64);
-        flush(C_W3, 64, p.g_trunk + T_W3 + n * 64, n < 64);
-        // pair: rows 0..63 = colour layer 0 (fea columns 27..90), rows 64..127 = density layer 0
-        flush(C_PAIR, 64, n < 64 ? p.g_rgb + R_W1 + n * 96 + 27 : p.g_density + D_W1 + (n - 64) * 64, true);
+        flush(C_W1, 32, gt + T_W1 + n * 32, n < 64);
+        flush(C_W2, 64, gt + T_W2 + n * 64, n < 64);
+        flush(C_W3, 64, gt + T_W3 + n * 64, n < 64);
+        // pair: rows 0..63 = colour layer 0 (fea columns 27..90), rows 64..127 = density layer 0.  Columns 27..90 of a
+        // 96-float row are not 16-byte aligned: scalar stores / atomics
+        {
+            float *dst = n < 64 ? gr + R_W1 + n * 96 + 27 : gd + D_W1 + (n - 64) * 64;
+            for (uint32_t c0 = half * 32; c0 < (half + 1) * 32; c0 += 16) {
+                if (n >= 64) { bwd_flush16(trow + C_PAIR + c0, dst + c0, true, slab); continue; }
+                uint32_t r[16];
+                umma::tmem_ld16(trow + C_PAIR + c0, r);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if (slab) dst[c0 + j] = __uint_as_float(r[j]);
+                    else atomicAdd(dst + c0 + j, __uint_as_float(r[j]));
+                }
+            }
+        }
         // colour layer 0, view columns: internal col j -> lane j (j < 27) or 91 + (j - 27)
         {
             const uint32_t c0 = half * 16;
@@ -721,22 +754,56 @@ k_field_backward(const FieldBwdArgs p) {
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     const uint32_t col = c0 + j, src = (col < 27) ? col : 91 + (col - 27);
-                    atomicAdd(p.g_rgb + R_W1 + n * 96 + src, __uint_as_float(r[j]));
+                    if (slab) gr[R_W1 + n * 96 + src] = __uint_as_float(r[j]);
+                    else atomicAdd(gr + R_W1 + n * 96 + src, __uint_as_float(r[j]));
                 }
             }
         }
-        // heads: A = T16, rows 0..15 = colour outputs, rows 16..31 = density outputs
-        flush(C_R2, 64, p.g_rgb + R_W2 + n * 64, n < 16);
-        flush(C_D2, 64, p.g_density + D_W2 + (n >= 16 ? n - 16 : 0) * 64, n >= 16 && n < 32);
+        // heads: A = T16, rows 0..15 = colour outputs (4 real), rows 16..31 = density outputs (1 real)
+        flush(C_R2, 64, gr + R_W2 + n * 64, n < 4);
+        flush(C_D2, 64, gd + D_W2, n == 16);
     }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, kTmemColsBwd);
 }
 
+// slabs [nslab][kWgradFloats] -> += into the three flat gradients.  Padded output rows of the two heads (tcnn pads 1 -> 16
+// and 4 -> 16 outputs) are never written by the flush and never read here.  256 threads = 64 parameters x 4 slab groups.
+__global__ void __launch_bounds__(256)
+k_field_wgrad_reduce(const float *__restrict__ slabs, uint32_t grid, uint32_t M, const int32_t *__restrict__ count_dev,
+                     float *__restrict__ g_trunk, float *__restrict__ g_density, float *__restrict__ g_rgb) {
+    __shared__ float part[4][64];
+    const uint32_t Mrows = count_dev ? min(M, (uint32_t)max(*count_dev, 0)) : M;
+    const uint32_t nslab = min(grid, (Mrows + 127) / 128);
+    const uint32_t pl = threadIdx.x & 63u, cg = threadIdx.x >> 6, i = blockIdx.x * 64 + pl;
+    float acc = 0.0f;
+    if (i < kWgradFloats)
+        for (uint32_t c = cg; c < nslab; c += 4) acc += __ldg(slabs + (size_t)c * kWgradFloats + i);
+    part[cg][pl] = acc;
+    __syncthreads();
+    if (cg != 0 || i >= kWgradFloats || nslab == 0) return;
+    const float sum = (part[0][pl] + part[1][pl]) + (part[2][pl] + part[3][pl]);
+    if (i < kTrunkFloats) { g_trunk[i] += sum; return; }
+    uint32_t j = i - kTrunkFloats;
+    if (j < kDensityFloats) {
+        if (j < D_W2 || j < D_W2 + 64) g_density[j] += sum;            // layer 0, and row 0 of the padded head
+        return;
+    }
+    j -= kDensityFloats;
+    if (j < R_W2 || j < R_W2 + 4 * 64) g_rgb[j] += sum;                // layer 0, and rows 0..3 of the padded head
+}
+
 }  // namespace
 
 extern "C" {
+
+uint32_t nb200_field_wgrad_scratch_bytes(void) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (uint32_t)sms * kWgradFloats * (uint32_t)sizeof(float);
+}
 
 uint32_t nb200_field_weight_image_bytes(void) { return F_BYTES; }
 
@@ -778,7 +845,7 @@ int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, c
 int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,
                          const void *x_en, const float *dirs, const void *act, const void *bwd_img, void *d_x_en,
                          float *g_trunk, float *g_density, float *g_rgb, uint32_t M, const int32_t *count_dev,
-                         void *stream) {
+                         float *wg_scratch, void *stream) {
     if (M == 0) return 0;
     if (!d_sigma || !d_rgba || !sigma_arg || !rgba || !x_en || !dirs || !act || !bwd_img || !d_x_en || !g_trunk ||
         !g_density || !g_rgb)
@@ -798,10 +865,17 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
     a.x_en = (const __half *)x_en; a.dirs = dirs; a.act = (const __half *)act; a.wimg = (const uint8_t *)bwd_img;
     a.d_x_en = (__half *)d_x_en; a.g_trunk = g_trunk; a.g_density = g_density; a.g_rgb = g_rgb; a.M = M;
     a.count_dev = count_dev;
+    a.slabs = wg_scratch;
     const uint32_t ntiles = (M + 127) / 128;
     const uint32_t grid = ntiles < (uint32_t)sms ? ntiles : (uint32_t)sms;
+    if (wg_scratch && (reinterpret_cast<uintptr_t>(wg_scratch) & 15u)) return NB200_E_BAD_ARG;
     k_field_backward<<<grid, kBwdThreads, smem, nb_stream(stream)>>>(a);
     NB_LAUNCH_CHECK();
+    if (wg_scratch) {
+        k_field_wgrad_reduce<<<nb_div_up(kWgradFloats, 64), 256, 0, nb_stream(stream)>>>(wg_scratch, grid, M, count_dev, g_trunk,
+                                                                                  g_density, g_rgb);
+        NB_LAUNCH_CHECK();
+    }
     return 0;
 }
 

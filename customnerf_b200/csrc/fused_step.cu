@@ -97,7 +97,7 @@ int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
                                           stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_field_backward(p->d_sigma, p->d_rgba, p->sigma_arg, p->rgba, p->x_en, p->dirs, p->act, p->w_bwd,
-                                   p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, stream))) return rc;
+                                   p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_fs_encode_backward(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
                                        p->base_res, p->gridtype, 0, 0, p->m_eff, stream))) return rc;

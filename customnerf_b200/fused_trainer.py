@@ -32,8 +32,8 @@ from . import _lib as L
 
 LOSS_SCALE = 128.0
 # this library's kernels in one step: near/far, march count + scan + fixup + write, encode, field, composite, loss,
-# composite^T, field^T, encode^T, adam hyper, adam, weight pack x2
-KERNELS_PER_STEP = 16
+# composite^T, field^T + weight-gradient reduce, encode^T, adam hyper, adam, weight pack x2
+KERNELS_PER_STEP = 17
 STAGES = ["near_far_from_aabb", "march_count", "march_write", "grid_encode_forward", "field_forward",
           "composite_forward", "mse_loss", "composite_backward", "field_backward", "grid_encode_backward",
           "adam", "pack_weights"]
@@ -56,7 +56,7 @@ class TrainPlan(C.Structure):
             "nears", "fars", "weights_sum", "depth", "image", "g_weights_sum", "g_image", "loss",
             "rays", "counter", "m_eff", "scratch",
             "xyzs", "dirs", "deltas", "sigma", "sigma_arg", "d_sigma", "d_rgba",
-            "x_en", "rgba", "act", "d_x_en", "timer"]
+            "x_en", "rgba", "act", "d_x_en", "wg_scratch", "timer"]
     _fields_ = ([(n, C.c_uint32) for n in _u32] + [(n, C.c_float) for n in _f32] + [(n, C.c_uint64) for n in _u64] +
                 [(n, C.c_void_p) for n in _ptr])
 
@@ -117,6 +117,8 @@ class FusedTrainStep:
         nb = int(self.lib.nb200_field_weight_image_bytes())
         self.w_fwd = torch.empty(nb, dtype=torch.uint8, device=dev)
         self.w_bwd = torch.empty(nb, dtype=torch.uint8, device=dev)
+        self.lib.nb200_field_wgrad_scratch_bytes.restype = C.c_uint32
+        self.wg_scratch = torch.empty(int(self.lib.nb200_field_wgrad_scratch_bytes()) // 4, dtype=torch.float32, device=dev)
 
         N = self.N
         f32 = dict(dtype=torch.float32, device=dev)
@@ -198,6 +200,7 @@ class FusedTrainStep:
         p.xyzs, p.dirs, p.deltas = a(self.xyzs), a(self.dirs), a(self.deltas)
         p.sigma, p.sigma_arg, p.d_sigma, p.d_rgba = a(self.sigma), a(self.sigma_arg), a(self.d_sigma), a(self.d_rgba)
         p.x_en, p.rgba, p.act, p.d_x_en = a(self.x_en), a(self.rgba), a(self.act), a(self.d_x_en)
+        p.wg_scratch = a(self.wg_scratch)
         assert C.sizeof(p) == int(self.lib.nb200_train_plan_bytes()), "nb200_train_plan layout mismatch"
         self.plan = p
 

@@ -29,6 +29,18 @@ class _PackedWeights:
         return self.fwd, self.bwd
 
 
+_wg = {}
+
+
+def _wg_scratch(dev):
+    """per-device scratch for the backward kernel's per-CTA partial weight-gradient sums"""
+    key = (dev.type, dev.index)
+    if key not in _wg:
+        L.lib().nb200_field_wgrad_scratch_bytes.restype = L.u32
+        _wg[key] = torch.empty(int(L.lib().nb200_field_wgrad_scratch_bytes()) // 4, dtype=torch.float32, device=dev)
+    return _wg[key]
+
+
 class _FusedField(Function):
     @staticmethod
     def forward(ctx, x_en, xyz, dirs, trunk, density, rgb, packed, save):
@@ -65,7 +77,8 @@ class _FusedField(Function):
         d_x_en = torch.empty(M, 32, dtype=torch.half, device=dev)
         L.check(L.lib().nb200_field_backward(L.ptr(d_sigma), L.ptr(d_rgba), L.ptr(sigma_arg), L.ptr(rgba), L.ptr(x_en),
                                              L.ptr(dirs), L.ptr(act), L.ptr(bwd_img), L.ptr(d_x_en), L.ptr(g_trunk),
-                                             L.ptr(g_density), L.ptr(g_rgb), L.u32(M), L.ptr(None), L.stream()),
+                                             L.ptr(g_density), L.ptr(g_rgb), L.u32(M), L.ptr(None), L.ptr(_wg_scratch(dev)),
+                                             L.stream()),
                 "field_backward")
         return d_x_en, None, None, g_trunk, g_density, g_rgb, None, None
 

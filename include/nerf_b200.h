@@ -172,7 +172,10 @@ int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, c
 int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,
                          const void *x_en, const float *dirs, const void *act, const void *bwd_img, void *d_x_en,
                          float *g_trunk, float *g_density, float *g_rgb, uint32_t M, const int32_t *count_dev,
-                         void *stream);
+                         float *wg_scratch, void *stream);
+/* wg_scratch: nb200_field_wgrad_scratch_bytes() bytes (16-byte aligned) of per-CTA partial weight-gradient sums that a
+ * second small kernel adds into g_* (deterministic, no contended atomics); NULL = fp32 atomics straight on g_*. */
+uint32_t nb200_field_wgrad_scratch_bytes(void);
 
 /* ============================================================================================
  * fused train step (no single reference counterpart: replaces the Python glue between the ops --
@@ -251,6 +254,7 @@ typedef struct nb200_train_plan {
     /* per-sample work buffers [M_cap ...] */
     float *xyzs, *dirs, *deltas, *sigma, *sigma_arg, *d_sigma, *d_rgba;
     void *x_en, *rgba, *act, *d_x_en;
+    float *wg_scratch;                                           /* nb200_field_wgrad_scratch_bytes() or NULL */
     void *timer;                                                 /* nb200_stage_timer or NULL */
 } nb200_train_plan;
 
