@@ -18,6 +18,7 @@
 // reference's cat([view_en, fea]) that the weight packer applies to the flat tcnn-layout parameter vector.
 #include "common.cuh"
 #include "umma.cuh"
+#include <string.h>
 
 namespace {
 
@@ -173,21 +174,8 @@ __device__ __noinline__ void write_view_chunks(uint8_t *xv, uint32_t row, float 
     }
 }
 
-// swizzled smem tile (128 rows x 128 B) -> rows [row0, row0 + 128) of a row-major [M, 64] half plane.  Consecutive
-// lanes take consecutive 16-byte chunks, so every store instruction of a warp writes 4 complete 128-byte lines
-// (the per-row stores of the epilogue would write 32 quarter-lines instead).
-__device__ __noinline__ void copy_tile_out(const uint8_t *tile, __half *plane, uint32_t row0, uint32_t Mrows, uint32_t tid) {
-#pragma unroll
-    for (uint32_t i = 0; i < 8; i++) {
-        const uint32_t q = i * 128 + tid, row = q >> 3, ch = q & 7u, g = row0 + row;
-        if (g < Mrows)
-            *reinterpret_cast<uint4 *>(plane + (size_t)g * 64 + ch * 8) =
-                *reinterpret_cast<const uint4 *>(tile + umma::sw128_offset(row, ch));
-    }
-}
-
 __global__ void __launch_bounds__(128, 2)
-k_field_forward(const FieldFwdArgs p) {
+k_field_forward(const FieldFwdArgs p, const __grid_constant__ CUtensorMap act_map) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -238,6 +226,20 @@ k_field_forward(const FieldFwdArgs p) {
         umma::fence_after_sync();
     };
 
+    // saved activations leave through the TMA unit: after a tile has been published, thread 0 hands it to a bulk tensor
+    // store (plane `pl` of the [5][M][64] activation tensor, rows row0..row0+127, clipped at M by the tensor map) and the
+    // copy proceeds behind the next layers.  Before a barrier that lets a later epilogue overwrite a tile, thread 0 makes
+    // sure the stores that still read it have finished reading (at most `kPending` younger stores may be in flight).
+    const bool save = p.act != nullptr;
+    auto store_tile = [&](uint32_t tile_smem, uint32_t pl, uint32_t row0) {
+        if (save && tid == 0) {
+            umma::tma_store_3d(&act_map, tile_smem, 0, (int32_t)row0, (int32_t)pl);
+            umma::tma_store_commit();
+        }
+    };
+    auto drain1 = [&]() { if (save && tid == 0) umma::tma_store_wait_read<1>(); };
+    auto drain0 = [&]() { if (save && tid == 0) umma::tma_store_wait_read<0>(); };
+
     // this thread's input row of the NEXT tile, prefetched into registers while the current tile is in flight
     uint4 nx0, nx1, nx2, nx3;
     float nd0, nd1, nd2, npx, npy, npz;
@@ -270,36 +272,38 @@ k_field_forward(const FieldFwdArgs p) {
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t g = tile * 128 + tid, row0 = tile * 128;
         const bool valid = g < Mrows;
-        const bool save = p.act != nullptr;
-        const size_t act_stride = (size_t)p.M * 64;
 
         // ---- trunk layer 0: h1 = relu(x_en W1^T), K = 32
         if (tid == 0) mma_run(sXV, 0, sW + F_W1V, 0, 2, ID64, true);
         prefetch_inputs(tile + gridDim.x);                  // loads complete behind the next layers
         sync_mma();
         epilogue_row64<true>(trow, smem + S_H0, tid, nullptr);
+        drain0();                                           // (the previous tile's hr store has left H1)
         publish();
         // ---- trunk layer 1: h2 = relu(h1 W2^T)
         if (tid == 0) mma_run(sH0, 0, sW + F_W2, 0, 4, ID64, true);
-        if (save) copy_tile_out(smem + S_H0, p.act, row0, Mrows, tid);
+        store_tile(sH0, 0, row0);
         sync_mma();
         epilogue_row64<true>(trow, smem + S_H1, tid, nullptr);
+        drain1();
         publish();
         // ---- trunk layer 2: fea = h2 W3^T (no activation)
         if (tid == 0) mma_run(sH1, 0, sW + F_W3, 0, 4, ID64, true);
-        if (save) copy_tile_out(smem + S_H1, p.act + act_stride, row0, Mrows, tid);
+        store_tile(sH1, 1, row0);
         sync_mma();
         epilogue_row64<false>(trow, smem + S_FEA, tid, nullptr);
+        drain1();                                           // the h1 store has left H0 before hd overwrites it
         publish();
         // ---- density layer 0: hd = relu(fea Wd1^T)
         if (tid == 0) mma_run(sFEA, 0, sW + F_WD1, 0, 4, ID64, true);
-        if (save) copy_tile_out(smem + S_FEA, p.act + 2 * act_stride, row0, Mrows, tid);
+        store_tile(sFEA, 2, row0);
         sync_mma();
         epilogue_row64<true>(trow, smem + S_H0, tid, nullptr);
+        drain1();                                           // the h2 store has left H1 before hr overwrites it
         publish();
         // ---- density layer 1: raw = hd Wd2^T (N = 16, lane 0 is the output); sigma = exp(raw + 5 exp(-|x|^2 / 0.08))
         if (tid == 0) mma_run(sH0, 0, sW + F_WD2, 0, 4, ID16, true);
-        if (save) copy_tile_out(smem + S_H0, p.act + 3 * act_stride, row0, Mrows, tid);
+        store_tile(sH0, 3, row0);
         sync_mma();
         {
             uint32_t r[16];
@@ -312,6 +316,7 @@ k_field_forward(const FieldFwdArgs p) {
                 if (p.sigma_arg) p.sigma_arg[g] = arg;
             }
         }
+        drain1();
         umma::fence_before_sync();
         __syncthreads();
         umma::fence_after_sync();
@@ -324,12 +329,12 @@ k_field_forward(const FieldFwdArgs p) {
         // the XV tile is free from here on: stage the next tile's inputs (published by the barriers below)
         write_xv(true);
         px = npx; py = npy; pz = npz;
-        // note: px/py/pz of THIS tile were consumed by the density head above
         epilogue_row64<true>(trow, smem + S_H1, tid, nullptr);
+        drain1();
         publish();
         // ---- colour layer 1: rgba = sigmoid(hr Wr2^T) (N = 16, lanes 0..3)
         if (tid == 0) mma_run(sH1, 0, sW + F_WR2, 0, 4, ID16, true);
-        if (save) copy_tile_out(smem + S_H1, p.act + 4 * act_stride, row0, Mrows, tid);
+        store_tile(sH1, 4, row0);
         sync_mma();
         {
             uint32_t r[16];
@@ -342,11 +347,13 @@ k_field_forward(const FieldFwdArgs p) {
                 *reinterpret_cast<uint2 *>(p.rgba + (size_t)g * 4) = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
             }
         }
+        drain1();                           // the hd store has left H0 before the next tile's h1 overwrites it
         umma::fence_proxy_async();          // the XV rows written after colour layer 0 feed the next tile's first MMA
         umma::fence_before_sync();
         __syncthreads();
         umma::fence_after_sync();
     }
+    if (save && tid == 0) umma::tma_store_wait<0>();
 
     if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
     if (tid == 0 && fail_s) p.sigma[0] = __int_as_float(0x7fc00000);   // make a barrier time-out visible (NaN)
@@ -817,6 +824,33 @@ int nb200_field_pack_weights(const float *trunk, const float *density, const flo
     return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+// the saved activations as a rank-3 tensor [5 planes][M rows][64 halves], boxes of 128 rows, 128B swizzle
+static int make_act_map(CUtensorMap *map, void *act, uint32_t M) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return NB200_E_BAD_ARG;
+    const cuuint64_t dims[3] = {64, M, 5};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)M * 128};
+    const cuuint32_t box[3] = {64, 128, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, act, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : NB200_E_BAD_ARG;
+}
+
 int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, const void *fwd_img, float *sigma,
                         float *sigma_arg, void *rgba, void *act, uint32_t M, const int32_t *count_dev, void *stream) {
     if (M == 0) return 0;
@@ -837,7 +871,14 @@ int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, c
     a.count_dev = count_dev;
     const uint32_t ntiles = (M + 127) / 128;
     const uint32_t grid = ntiles < (uint32_t)(2 * sms) ? ntiles : (uint32_t)(2 * sms);
-    k_field_forward<<<grid, 128, smem, nb_stream(stream)>>>(a);
+    CUtensorMap act_map;
+    memset(&act_map, 0, sizeof(act_map));
+    if (act) {
+        if (reinterpret_cast<uintptr_t>(act) & 15u) return NB200_E_BAD_ARG;
+        const int rc = make_act_map(&act_map, act, M);
+        if (rc) return rc;
+    }
+    k_field_forward<<<grid, 128, smem, nb_stream(stream)>>>(a, act_map);
     NB_LAUNCH_CHECK();
     return 0;
 }

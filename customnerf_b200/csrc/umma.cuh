@@ -126,6 +126,21 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, uint32
     return false;
 }
 
+// ---- TMA (bulk tensor) stores: smem tile -> global through a CUtensorMap, asynchronous, issued by ONE thread ------------
+// The 128B-swizzled tile layout below (sw128_offset) is exactly CU_TENSOR_MAP_SWIZZLE_128B's, so a UMMA operand tile can
+// be handed to the TMA unit as it is.
+__device__ __forceinline__ void tma_store_3d(const void *tmap, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap), "r"(smem_src),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's most recent store groups may still be READING their shared-memory source
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- operand tile placement -----------------------------------------------------------------------------
 // A tile is stored as rows of 128 bytes (64 halves); 8 rows form a 1024-byte swizzle atom; the 16-byte chunk c of row
 // r sits at chunk position c ^ (r & 7) (the 128B swizzle: address bits [4,7) ^= bits [7,10)).  The tile base must be
