@@ -19,6 +19,7 @@
 // Index arithmetic is uint32 with wrap-around exactly as gridencoder.cu:50-84; scale is computed on the
 // device with the reference's expression exp2f(level * S) * H - 1.0f so fine-level positions are identical.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -419,7 +420,7 @@ template <typename T, bool kAgg>
 __global__ void __launch_bounds__(256)
 k_grid_bwd_d3c2(const T *__restrict__ grad, const float *__restrict__ inputs, const int32_t *__restrict__ offsets,
                 float *__restrict__ grad_grid, uint32_t B, uint32_t L, uint32_t max_level, float S, uint32_t H,
-                uint32_t gridtype, bool align_corners, uint32_t interp, InXform xf) {
+                uint32_t gridtype, bool align_corners, uint32_t interp, InXform xf, uint32_t agg_max_heads) {
     __shared__ LevelInfo info[kMaxFastLevels];
     if (xf.count_dev) B = min(B, (uint32_t)max(*xf.count_dev, 0));
     if (blockIdx.x * blockDim.x >= B) return;
@@ -459,11 +460,12 @@ k_grid_bwd_d3c2(const T *__restrict__ grad, const float *__restrict__ inputs, co
             const bool poob = __shfl_up_sync(0xffffffffu, (int)oob, 1) != 0;
             const bool head = (lane == 0) || oob || poob || (q0 != c0) || (q1 != c1) || (q2 != c2);
             const uint32_t heads = __ballot_sync(0xffffffffu, head);
-            if (__popc(heads) <= 16) {                       // warp-uniform: at least half of the atomics disappear
+            if ((uint32_t)__popc(heads) <= agg_max_heads) {     // warp-uniform: enough atomics disappear to pay for the shuffles
                 const uint32_t nh = (lane == 31) ? 0u : (heads >> (lane + 1));
                 const uint32_t run_last = nh ? lane + (uint32_t)__ffs(nh) - 1u : 31u;
-#pragma unroll
-                for (uint32_t o = 1; o < 32; o <<= 1) {
+                // log-step segmented reduction, only as many rounds as the longest run of this warp needs
+                const uint32_t max_run = __reduce_max_sync(0xffffffffu, head ? run_last - lane + 1u : 0u);
+                for (uint32_t o = 1; o < max_run; o <<= 1) {
                     const bool take = (lane + o) <= run_last;
 #pragma unroll
                     for (uint32_t idx = 0; idx < 8; idx++) {
@@ -502,6 +504,13 @@ __global__ void k_cast_f32_f16(const float *__restrict__ src, __half *__restrict
     } else {
         for (uint64_t j = i; j < n; j++) dst[j] = __float2half_rn(src[j]);
     }
+}
+
+// warp-aggregate a level only when at most this many of the 32 lanes start a new cell run (tunable: NB200_GE_AGG_MAXHEADS)
+static uint32_t ge_agg_max_heads() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("NB200_GE_AGG_MAXHEADS"); v = e ? atoi(e) : 32; if (v < 0 || v > 32) v = 32; }
+    return (uint32_t)v;
 }
 
 // ---- dispatch helpers ------------------------------------------------------------------------------
@@ -559,8 +568,8 @@ int launch_bwd(const T *grad, const float *inputs, const int32_t *offsets, float
     int rc = 0;
     if (D == 3 && C == 2 && layout == NB200_LAYOUT_BLC && L <= kMaxFastLevels) {
         const uint32_t nblk = nb_div_up(B, 256);
-        if (agg) k_grid_bwd_d3c2<T, true><<<nblk, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, max_level, S, H, gridtype, ac, interp, InXform{0.0f, 0.0f, nullptr});
-        else k_grid_bwd_d3c2<T, false><<<nblk, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, max_level, S, H, gridtype, ac, interp, InXform{0.0f, 0.0f, nullptr});
+        if (agg) k_grid_bwd_d3c2<T, true><<<nblk, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, max_level, S, H, gridtype, ac, interp, InXform{0.0f, 0.0f, nullptr}, ge_agg_max_heads());
+        else k_grid_bwd_d3c2<T, false><<<nblk, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, max_level, S, H, gridtype, ac, interp, InXform{0.0f, 0.0f, nullptr}, 0);
     } else {
         switch (D) {
             case 2: rc = launch_bwd_c<T, 2>(grad, inputs, offsets, gg, B, C, L, max_level, S, H, gridtype, ac, interp, layout, st); break;
@@ -666,7 +675,8 @@ int nb200_fs_encode_backward(const void *d_x_en, const float *xyz, float bound, 
     if (!d_x_en || !xyz || !offsets || !grad_table || L > kMaxFastLevels || !(bound > 0.0f)) return NB200_E_BAD_ARG;
     const InXform xf{bound, 1.0f / (2.0f * bound), count_dev};
     k_grid_bwd_d3c2<__half, true><<<nb_div_up(M_cap, 256), 256, 0, nb_stream(stream)>>>(
-        (const __half *)d_x_en, xyz, offsets, grad_table, M_cap, L, L, S, H, gridtype, align_corners != 0, interp, xf);
+        (const __half *)d_x_en, xyz, offsets, grad_table, M_cap, L, L, S, H, gridtype, align_corners != 0, interp, xf,
+        ge_agg_max_heads());
     NB_LAUNCH_CHECK();
     return 0;
 }
