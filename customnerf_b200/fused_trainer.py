@@ -301,9 +301,16 @@ class FusedTrainStep:
                                                                          rays_d if rays_d is not None else self.rays_d)))
             if rays_o is not None:
                 self.set_batch(rays_o, rays_d, target)
-            if self.use_graph:
-                if self.graph is None:
+            if self.use_graph and self.graph is None:
+                try:
                     self._capture()
+                except Exception as e:      # e.g. a collective that cannot be captured on this NCCL build
+                    import warnings
+                    warnings.warn("FusedTrainStep: CUDA-graph capture failed (%s); launching the step's kernels "
+                                  "directly instead" % (e,))
+                    self.use_graph, self.graph = False, None
+                    torch.cuda.synchronize(self.dev)
+            if self.use_graph:
                 self.graph.replay()
             else:
                 self._launch()
