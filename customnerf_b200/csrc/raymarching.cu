@@ -71,10 +71,13 @@ __device__ __forceinline__ float rm_dt(const RayCtx &r, float t) {
 // (int) clamp(0.5 * (p * mip_rbound + 1) * H, 0, H-1): fp64 product because the literal is a double (:374-376).
 // When H is a power of two, 0.5 * f * H only changes f's exponent, so the fp64 product rounded to fp32 equals the
 // single fp32 product f * (0.5 * H) bit for bit (no overflow / underflow is possible for f in [0, 2]).
+// kFast (here and below): the caller guarantees dt_gamma == 0 and H a power of two, so the constant-step and the
+// single-fp32-product paths are selected at compile time instead of being predicated into every probe.
+template <bool kFast = false>
 __device__ __forceinline__ int rm_cell(const RayCtx &r, float p, float mip_rbound) {
     const float f = __fmaf_rn(p, mip_rbound, 1.0f);
     float v;
-    if (r.halfH != 0.0f) v = __fmul_rn(f, r.halfH);
+    if (kFast || r.halfH != 0.0f) v = __fmul_rn(f, r.halfH);
     else v = __double2float_rn(__dmul_rn(__dmul_rn(0.5, (double)f), r.Hd));
     return __float2int_rz(rm_clamp(v, 0.0f, r.Hm1f));
 }
@@ -100,9 +103,10 @@ __device__ __forceinline__ bool rm_binade_step(float t, float dt, float &c, floa
 }
 
 // returns the advanced t; nsteps = number of additions the loop performed
+template <bool kFast = false>
 __device__ __forceinline__ float rm_advance(const RayCtx &r, float t, float tt, uint32_t &nsteps) {
     uint32_t n = 0;
-    if (r.level_dt >= 0) {                                          // dt_gamma == 0: dt is a constant
+    if (kFast || r.level_dt >= 0) {                                 // dt_gamma == 0: dt is a constant
         const float dt = r.dt_min_c;
         float c, top;
         if (rm_binade_step(t, dt, c, top)) {
@@ -122,7 +126,7 @@ __device__ __forceinline__ float rm_advance(const RayCtx &r, float t, float tt, 
             }
         }
     }
-    do { t = __fadd_rn(t, rm_dt(r, t)); n++; } while (t < tt);
+    do { t = __fadd_rn(t, kFast ? r.dt_min_c : rm_dt(r, t)); n++; } while (t < tt);
     nsteps = n;
     return t;
 }
@@ -161,21 +165,22 @@ __device__ __forceinline__ float rm_exit(float n, float s, float rH, float mip_b
 
 // Occupancy probe of the marching loop (:359-387) at parameter t: x,y,z,dt are the would-be sample; when the cell is
 // empty, tt is the parameter at which the ray leaves the voxel (:388-394).
+template <bool kFast = false>
 __device__ __forceinline__ bool rm_probe(const RayCtx &r, float t, float &x, float &y, float &z, float &dt, float &tt) {
     x = rm_clamp(__fmaf_rn(t, r.dx, r.ox), -r.bound, r.bound);
     y = rm_clamp(__fmaf_rn(t, r.dy, r.oy), -r.bound, r.bound);
     z = rm_clamp(__fmaf_rn(t, r.dz, r.oz), -r.bound, r.bound);
-    dt = rm_dt(r, t);
+    dt = kFast ? r.dt_min_c : rm_dt(r, t);
     const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-    const int level_dt = r.level_dt >= 0 ? r.level_dt : rm_mip_level(__fmul_rn(__fmul_rn(dt, r.Hf), 0.5f), r.Cm1);
+    const int level_dt = (kFast || r.level_dt >= 0) ? r.level_dt : rm_mip_level(__fmul_rn(__fmul_rn(dt, r.Hf), 0.5f), r.Cm1);
     const int level = max(rm_mip_level(mx, r.Cm1), level_dt);
     const float pw = __int_as_float((127 + level) << 23);                                   // scalbnf(1, level)
     const bool capped = pw > r.bound;
     const float mip_bound = capped ? r.bound : pw;                                          // fminf(2^level, bound)
     const float mip_rbound = capped ? r.rbound : __int_as_float((127 - level) << 23);       // 1 / mip_bound, exact
-    const int nx = rm_cell(r, x, mip_rbound);
-    const int ny = rm_cell(r, y, mip_rbound);
-    const int nz = rm_cell(r, z, mip_rbound);
+    const int nx = rm_cell<kFast>(r, x, mip_rbound);
+    const int ny = rm_cell<kFast>(r, y, mip_rbound);
+    const int nz = rm_cell<kFast>(r, z, mip_rbound);
     const uint32_t index = __float2uint_rz(__fmaf_rn((float)level, r.H3, (float)nb_morton3D(nx, ny, nz)));   // :378
     const bool occ = (__ldg(r.grid + (index >> 3)) >> (index & 7u)) & 1u;
     if (occ) return true;
@@ -434,14 +439,14 @@ __device__ __forceinline__ SegResult rm_march_segment(const RayCtx &r, uint32_t 
     const uint32_t a = k;
     float x, y, z, dt, tt;
     while (k < b && t < far) {
-        if (rm_probe(r, t, x, y, z, dt, tt)) {
+        if (rm_probe<true>(r, t, x, y, z, dt, tt)) {
             rec[o.cnt++] = t;
             if (k == a) o.occ_a = true;
             k += 1;
             t = __fadd_rn(t, dt);
         } else {
             uint32_t n;
-            t = rm_advance(r, t, tt, n);
+            t = rm_advance<true>(r, t, tt, n);
             k += n;
         }
         if (o.v1 == 0xffffffffu) o.v1 = k;
@@ -454,10 +459,9 @@ __global__ void __launch_bounds__(kSegWarps * 32)
 k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
                   float bound, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                   const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
-                  int32_t *__restrict__ rays, int32_t *__restrict__ block_sums, float *__restrict__ trec, uint32_t tcap,
+                  int32_t *__restrict__ counts, float *__restrict__ trec, uint32_t tcap,
                   const int32_t *__restrict__ obounds) {
     __shared__ float rec_s[kSegWarps][32][kRecStride];
-    __shared__ int ray_tot[kSegWarps];
     const uint32_t lane = nb_lane(), w = threadIdx.x >> 5;
     const uint32_t n = blockIdx.x * kSegWarps + w;
     uint32_t total = 0;
@@ -482,22 +486,41 @@ k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ ra
                 // ---- thread the true chain through the segments
                 uint32_t e = K0, drop = 0, valid = 0;
                 float te = tK0;
-                for (uint32_t sgm = 0; sgm < 32; sgm++) {
-                    const uint32_t as = K0 + sgm * seg, bs = as + seg;
-                    if (e >= bs) continue;                                  // the chain jumps over this segment
-                    const uint32_t v1s = __shfl_sync(0xffffffffu, sr.v1, sgm);
-                    const bool occs = __shfl_sync(0xffffffffu, (int)sr.occ_a, sgm) != 0;
-                    uint32_t dr;
-                    if (e == as) dr = 0;
-                    else if (e == v1s) dr = occs ? 1u : 0u;
-                    else {                                                  // mis-speculation: re-march from the true entry
-                        if (lane == sgm) sr = rm_march_segment(r, e, te, b, far, rec);
-                        dr = 0;
+                // common case, checked in parallel: every segment up to the one where the ray ends is entered at its
+                // own first index or at the first point its lane moved to, i.e. lane s-1 landed on a_s or on v1_s
+                {
+                    const uint32_t pl = __shfl_up_sync(0xffffffffu, sr.land, 1);
+                    const bool ok = lane == 0 || pl == a || pl == sr.v1;
+                    const uint32_t endm = __ballot_sync(0xffffffffu, !(sr.tland < far));
+                    const uint32_t last = endm ? (uint32_t)__ffs((int)endm) - 1u : 31u;      // segment in which the chain ends
+                    const uint32_t bad = __ballot_sync(0xffffffffu, !ok) & (last == 31u ? 0xffffffffu : ((2u << last) - 1u));
+                    if (bad == 0) {
+                        if (lane <= last) {
+                            drop = (lane != 0 && pl != a && sr.occ_a) ? 1u : 0u;
+                            valid = sr.cnt - drop;
+                        }
+                        e = __shfl_sync(0xffffffffu, sr.land, last);
+                        te = __shfl_sync(0xffffffffu, sr.tland, last);
+                        ended = endm != 0;
+                    } else {
+                        for (uint32_t sgm = 0; sgm < 32; sgm++) {
+                            const uint32_t as = K0 + sgm * seg, bs = as + seg;
+                            if (e >= bs) continue;                                  // the chain jumps over this segment
+                            const uint32_t v1s = __shfl_sync(0xffffffffu, sr.v1, sgm);
+                            const bool occs = __shfl_sync(0xffffffffu, (int)sr.occ_a, sgm) != 0;
+                            uint32_t dr;
+                            if (e == as) dr = 0;
+                            else if (e == v1s) dr = occs ? 1u : 0u;
+                            else {                                                  // mis-speculation: re-march from the true entry
+                                if (lane == sgm) sr = rm_march_segment(r, e, te, b, far, rec);
+                                dr = 0;
+                            }
+                            if (lane == sgm) { drop = dr; valid = sr.cnt - dr; }
+                            e = __shfl_sync(0xffffffffu, sr.land, sgm);
+                            te = __shfl_sync(0xffffffffu, sr.tland, sgm);
+                            if (!(te < far)) { ended = true; break; }
+                        }
                     }
-                    if (lane == sgm) { drop = dr; valid = sr.cnt - dr; }
-                    e = __shfl_sync(0xffffffffu, sr.land, sgm);
-                    te = __shfl_sync(0xffffffffu, sr.tland, sgm);
-                    if (!(te < far)) { ended = true; break; }
                 }
                 // ---- compact this round's samples behind the ray's earlier ones (max_steps caps the ray, :359)
                 const uint32_t incl = (uint32_t)nb_warp_incl_scan((int)valid);
@@ -515,21 +538,50 @@ k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ ra
             }
         }
     }
-    if (lane == 0) ray_tot[w] = (int)total;
+    if (lane == 0 && n < N) counts[n] = (int32_t)total;
+}
+
+// single block: rays[n] = (n, exclusive prefix of the per-ray counts starting at counter[0], count); counter += (sum, N)
+// (:405-413 with scan-ordered instead of atomically reserved offsets).  Each thread owns 8 consecutive rays per trip.
+__global__ void __launch_bounds__(1024)
+k_march_scan_rays(const int32_t *__restrict__ counts, int32_t *__restrict__ rays, uint32_t N, int32_t *__restrict__ counter,
+                  uint32_t M_cap, int32_t *__restrict__ m_eff) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s, chunk_total_s;
+    if (threadIdx.x == 0) carry_s = counter[0];
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
+    for (uint32_t base = 0; base < N; base += 8192) {
+        const uint32_t i0 = base + threadIdx.x * 8;
+        int c[8], v = 0;
 #pragma unroll
-        for (int i = 0; i < kSegWarps; i++) {
-            const uint32_t ni = blockIdx.x * kSegWarps + i;
-            if (ni < N) {
-                rays[ni * 3] = (int32_t)ni;
-                rays[ni * 3 + 1] = run;             // block-local exclusive offset, globalised by k_march_fixup
-                rays[ni * 3 + 2] = ray_tot[i];
-            }
-            run += ray_tot[i];
+        for (int j = 0; j < 8; j++) { c[j] = (i0 + j < N) ? counts[i0 + j] : 0; v += c[j]; }
+        const int incl = nb_warp_incl_scan(v);
+        if (nb_lane() == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int wt = warp_tot[threadIdx.x];
+            const int wi = nb_warp_incl_scan(wt);
+            warp_tot[threadIdx.x] = wi - wt;            // exclusive warp offsets
+            if (threadIdx.x == 31) chunk_total_s = wi;
         }
-        block_sums[blockIdx.x] = run;
+        __syncthreads();
+        int off = carry_s + warp_tot[threadIdx.x >> 5] + incl - v;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t n = i0 + j;
+            if (n < N) { rays[n * 3] = (int32_t)n; rays[n * 3 + 1] = off; rays[n * 3 + 2] = c[j]; }
+            off += c[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += chunk_total_s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        counter[0] = carry_s;
+        counter[1] += (int32_t)N;
+        // rows the downstream kernels of the fused step may touch: every segment below this row is complete
+        // (k_march_expand lowers it to the offset of the first ray that does not fit in M_cap rows)
+        if (m_eff) *m_eff = (int32_t)min((uint32_t)max(carry_s, 0), M_cap);
     }
 }
 
@@ -888,14 +940,15 @@ int nb200_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t 
     return 0;
 }
 
-// scratch layout (int32 units): [block sums: nb4][block prefixes: nb4][occupied bounds: 8 levels x 6 + 16 spare]
-// [sample records: N * tcap floats], nb4 = ceil(N / 4) (the smallest rays-per-warp the launcher ever picks)
+// scratch layout (int32 units): [per-ray counts: N + 8  (serial kernel: block sums nb4 | block prefixes nb4)]
+// [occupied bounds: 8 levels x 6 + 16 spare][sample records: N * tcap floats], nb4 = ceil(N / 4)
 constexpr uint32_t kScratchFixed = 64;
 static inline uint32_t march_nb_max(uint32_t N) { return nb_div_up(N, 4); }
-uint32_t nb200_march_scratch_ints(uint32_t N) { return 2 * march_nb_max(N) + kScratchFixed + N * march_tcap(N); }
-static inline int32_t *march_obounds(int32_t *scratch, uint32_t N) { return scratch + 2 * march_nb_max(N); }
+static inline uint32_t march_hdr(uint32_t N) { return N + 8; }      // per-ray counts (or 2 x nb4 block sums / prefixes)
+uint32_t nb200_march_scratch_ints(uint32_t N) { return march_hdr(N) + kScratchFixed + N * march_tcap(N); }
+static inline int32_t *march_obounds(int32_t *scratch, uint32_t N) { return scratch + march_hdr(N); }
 static inline float *march_trec(int32_t *scratch, uint32_t N) {
-    return reinterpret_cast<float *>(scratch + 2 * march_nb_max(N) + kScratchFixed);
+    return reinterpret_cast<float *>(scratch + march_hdr(N) + kScratchFixed);
 }
 
 static int march_count_impl(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
@@ -907,7 +960,7 @@ static int march_count_impl(const float *rays_o, const float *rays_d, const uint
     if (!scratch || !rays || !counter) return NB200_E_BAD_ARG;
     static int serial_env = -1;
     if (serial_env < 0) { const char *e = getenv("NB200_MARCH_SERIAL"); serial_env = (e && atoi(e)) ? 1 : 0; }
-    const bool seg = dt_gamma == 0.0f && !serial_env;
+    const bool seg = dt_gamma == 0.0f && (H & (H - 1)) == 0 && !serial_env;   // k_march_count_seg's compile-time fast paths
     const uint32_t rpw = seg ? (uint32_t)kSegWarps : march_rpw(N);
     const uint32_t nb = nb_div_up(N, rpw);
     int32_t *block_sums = scratch, *block_prefix = scratch + march_nb_max(N);
@@ -924,12 +977,14 @@ static int march_count_impl(const float *rays_o, const float *rays_d, const uint
             NB_LAUNCH_CHECK();
         }
         k_march_count_seg<<<nb, kSegWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, max_steps, N, C, H, nears, fars,
-                                                        noises, rays, block_sums, march_trec(scratch, N), march_tcap(N),
-                                                        obounds);
+                                                        noises, scratch, march_trec(scratch, N), march_tcap(N), obounds);
+        NB_LAUNCH_CHECK();
+        k_march_scan_rays<<<1, 1024, 0, st>>>(scratch, rays, N, counter, M_cap, m_eff);
+        NB_LAUNCH_CHECK();
+        return 0;
     }
-    else
-        k_march_count<<<nb, kMarchBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
-                                                  noises, rays, block_sums, rpw, march_trec(scratch, N), march_tcap(N));
+    k_march_count<<<nb, kMarchBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
+                                              noises, rays, block_sums, rpw, march_trec(scratch, N), march_tcap(N));
     NB_LAUNCH_CHECK();
     k_march_scan<<<1, 1024, 0, st>>>(block_sums, block_prefix, nb, N, counter, M_cap, m_eff);
     NB_LAUNCH_CHECK();

@@ -239,22 +239,25 @@ class FusedTrainStep:
         then restore the optimiser state the warm-up steps advanced"""
         state = (self.params_flat, self.exp_avg, self.exp_avg_sq, self.step_count)
         keep = [t.clone() for t in state]
-        s = torch.cuda.Stream(device=self.dev)
-        s.wait_stream(torch.cuda.current_stream(self.dev))
-        with torch.cuda.stream(s):
-            for _ in range(2):
+        try:
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._launch()
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            # thread_local: NCCL's watchdog thread may touch the CUDA API while the all-reduce of a sharded step is captured
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._launch()
-        torch.cuda.current_stream(self.dev).wait_stream(s)
-        torch.cuda.synchronize(self.dev)
-        g = torch.cuda.CUDAGraph()
-        # thread_local: NCCL's watchdog thread may touch the CUDA API while the all-reduce of a sharded step is captured
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
-            self._launch()
-        for t, k in zip(state, keep):
-            t.copy_(k)
-        self.grads_flat.zero_()
-        self._pack()
-        self.graph = g
+            self.graph = g
+        finally:
+            torch.cuda.synchronize(self.dev)
+            for t, k in zip(state, keep):
+                t.copy_(k)
+            self.grads_flat.zero_()
+            self._pack()
 
     def forward_backward(self):
         """forward + backward only, not captured (tests): gradients accumulate into ``grads_flat``"""
