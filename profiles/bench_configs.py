@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Timings of the BASELINE.json configs that are NOT the bench line (configs[1] is bench.py): run on the GPU box,
+prints one JSON object per config.  usage: python profiles/bench_configs.py > gpurun_out/configs.jsonl"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from customnerf_b200 import trainer, fused_trainer, synthetic as syn, raymarching  # noqa: E402
+
+dev = torch.device("cuda")
+
+
+def timeit(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def c0_dense_path():
+    """configs[0] on the GPU: 4096 rays through the dense (non-cuda_ray) renderer, forward + backward + Adam"""
+    opt = trainer.make_opt(cuda_ray=False)
+    model = trainer.build_scene_model(dev, opt=opt)
+    ts = trainer.TrainStep(model)
+    o, d = syn.random_rays(4096, seed=1)
+    o, d = o.to(dev), d.to(dev)
+    tgt = syn.bear_color(o + d * 1.5)
+    orig = model.render
+    model.render = lambda ro, rd, **kw: orig(ro, rd, **{**kw, "num_steps": 64, "upsample_steps": 64})
+    ms = timeit(lambda: ts.step(o, d, tgt), 10)
+    return {"config": "configs[0] dense renderer, 4096 rays, 64+64 samples, fwd+bwd+Adam (autograd over the drop-in ops)",
+            "ms_per_step": ms, "rays_per_s": 4096 / ms * 1e3}
+
+
+def c2_inference():
+    """configs[2]: full 248x184 image through march_rays / composite_rays (n_step loop) + one occupancy-grid update"""
+    model = trainer.build_scene_model(dev)
+    model.eval()
+    o, d = syn.camera_rays(184, 248)
+    o, d = o.to(dev), d.to(dev)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        ms = timeit(lambda: model.render(o[None], d[None], perturb=False), 5, warm=1)
+        model.train()
+        t0 = time.perf_counter(); model.update_extra_state(); torch.cuda.synchronize(); upd = (time.perf_counter() - t0) * 1e3
+    return {"config": "configs[2] inference 248x184 (45632 rays), n_step loop; occupancy update of 2x128^3 cells",
+            "ms_per_frame": ms, "rays_per_s": o.shape[0] / ms * 1e3, "update_extra_state_ms": upd}
+
+
+def c4_scale(n_rays=1 << 20, log2_T=22):
+    """configs[4] on one GPU: 2^22 table, 1 M rays per step (fused graph step)"""
+    model = trainer.build_scene_model(dev, log2_hashmap_size=log2_T)
+    o, d = syn.random_rays(n_rays, seed=2)
+    tgt = syn.bear_color(o + d * 1.5)
+    fs = fused_trainer.FusedTrainStep(model, n_rays)
+    fs.step(o.to(dev), d.to(dev), tgt.to(dev))
+    loss, samples, used = fs.last_stats()
+    ms = timeit(lambda: fs.step(), 5, warm=2)
+    loss, samples, used = fs.last_stats()
+    fs.use_graph = False
+    stages = fs.profile_stages(3)
+    return {"config": "configs[4] at 1 GPU: 2^%d table, %d rays/step" % (log2_T, n_rays), "ms_per_step": ms,
+            "rays_per_s": n_rays / ms * 1e3, "samples_per_step": samples, "rows_used": used,
+            "stage_us": {k: round(v, 1) for k, v in stages.items()}}
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c0", "c2", "c4"]
+    for name, fn in (("c0", c0_dense_path), ("c2", c2_inference), ("c4", c4_scale)):
+        if name in which:
+            try:
+                print(json.dumps(fn()), flush=True)
+            except Exception as e:                       # keep going: one config failing must not hide the others
+                print(json.dumps({"config": name, "error": repr(e)}), flush=True)
+            torch.cuda.empty_cache()

@@ -160,3 +160,22 @@ def test_graph_capture_includes_nccl_allreduce():
         assert lb[-1] < lb[0]
     finally:
         dist.destroy_process_group()
+
+
+def test_fused_step_at_scale_config_shapes():
+    """BASELINE.json configs[4] shapes in miniature: 2^22-entry hash table (79 M parameters, 302 MB fp32) and a
+    150 k-ray batch (~2.7 M samples): exercises 64-bit indexing, the multi-trip ray scan and the TMA activation stores."""
+    from customnerf_b200 import trainer, fused_trainer, synthetic as syn
+    model = trainer.build_scene_model(torch.device("cuda"), log2_hashmap_size=22, desired_resolution=2048, seed=1)
+    assert model.pos_en.embeddings.shape[0] == 39625280
+    n = 150000
+    o, d = syn.random_rays(n, seed=5)
+    tgt = syn.bear_color(o + d * 1.5)
+    fs = fused_trainer.FusedTrainStep(model, n, use_graph=True)
+    losses = []
+    for _ in range(4):
+        fs.step(o.cuda(), d.cuda(), tgt.cuda())
+        loss, samples, used = fs.last_stats()
+        assert samples == used > 500000 and np.isfinite(loss)
+        losses.append(loss)
+    assert losses[-1] < losses[0]
