@@ -52,17 +52,8 @@ __device__ __forceinline__ void put(uint8_t *img, uint32_t row, uint32_t col, fl
     *reinterpret_cast<__half *>(img + umma::sw128_offset(row, col >> 3) + (col & 7u) * 2) = __float2half_rn(v);
 }
 
+// every byte of both images that a descriptor can reach is written here (no separate zero fill)
 __global__ void k_pack_field_weights(const float *__restrict__ trunk, const float *__restrict__ density,
-                                     const float *__restrict__ rgb, uint8_t *__restrict__ fwd, uint8_t *__restrict__ bwd) {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (uint32_t i = tid; i < (F_BYTES + B_BYTES) / 4; i += nth) {
-        if (i < F_BYTES / 4) reinterpret_cast<uint32_t *>(fwd)[i] = 0;
-        else reinterpret_cast<uint32_t *>(bwd)[i - F_BYTES / 4] = 0;
-    }
-    // the zero fill and the scattered puts below touch disjoint bytes only if ordered: do the puts in a second kernel
-}
-
-__global__ void k_pack_field_weights2(const float *__restrict__ trunk, const float *__restrict__ density,
                                       const float *__restrict__ rgb, uint8_t *__restrict__ fwd, uint8_t *__restrict__ bwd) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (uint32_t i = tid; i < 64 * 64; i += nth) {
@@ -87,6 +78,8 @@ __global__ void k_pack_field_weights2(const float *__restrict__ trunk, const flo
             put(fwd + F_WR2, n, k, wr2);
             put(bwd + B_W16T, k, n, wr2);
             put(bwd + B_W16T, k, 16 + n, wd2);
+        } else if (n >= 32) {
+            put(bwd + B_W16T, k, n, 0.0f);          // columns 32..63 of the head tile: never read, kept finite
         }
     }
 }
@@ -818,8 +811,7 @@ int nb200_field_pack_weights(const float *trunk, const float *density, const flo
                              void *stream) {
     if (!trunk || !density || !rgb || !fwd_img || !bwd_img) return NB200_E_BAD_ARG;
     cudaStream_t st = nb_stream(stream);
-    k_pack_field_weights<<<32, 256, 0, st>>>(trunk, density, rgb, (uint8_t *)fwd_img, (uint8_t *)bwd_img);
-    k_pack_field_weights2<<<16, 256, 0, st>>>(trunk, density, rgb, (uint8_t *)fwd_img, (uint8_t *)bwd_img);
+    k_pack_field_weights<<<16, 256, 0, st>>>(trunk, density, rgb, (uint8_t *)fwd_img, (uint8_t *)bwd_img);
     NB_LAUNCH_CHECK();
     return 0;
 }

@@ -71,11 +71,9 @@ int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
     cudaEvent_t *ev = tm ? tm->fb : nullptr;
     int k = 0;
     tick(ev, k++, st);
-    if ((rc = nb200_near_far_from_aabb(p->rays_o, p->rays_d, p->aabb, p->N, p->min_near, p->nears, p->fars, stream))) return rc;
-    tick(ev, k++, st);
     if ((rc = nb200_fs_march_count(p->rays_o, p->rays_d, p->bitfield, p->bound, p->dt_gamma, p->max_steps, p->N, p->C,
                                    p->H, p->M_cap, p->nears, p->fars, p->noises, p->rays, p->counter, p->m_eff,
-                                   p->scratch, stream))) return rc;
+                                   p->scratch, p->aabb, p->min_near, stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_fs_march_write(p->rays_o, p->rays_d, p->bitfield, p->bound, p->dt_gamma, p->max_steps, p->N, p->C,
                                    p->H, p->M_cap, p->nears, p->fars, p->noises, p->rays, p->xyzs, p->dirs, p->deltas,
@@ -88,9 +86,8 @@ int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
                                   p->m_eff, stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_fs_composite_forward(p->sigma, p->rgba, p->deltas, p->rays, p->M_cap, p->N, p->T_thresh,
-                                         p->weights_sum, p->depth, p->image, stream))) return rc;
-    tick(ev, k++, st);
-    if ((rc = nb200_mse_loss_grad(p->image, p->target, p->N, p->inv_n_total, p->loss_scale, p->loss, p->g_image, stream))) return rc;
+                                         p->weights_sum, p->depth, p->image, p->target, p->inv_n_total, p->loss_scale,
+                                         p->loss, p->g_image, stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_fs_composite_backward(p->g_weights_sum, p->g_image, p->sigma, p->rgba, p->deltas, p->rays,
                                           p->weights_sum, p->image, p->M_cap, p->N, p->T_thresh, p->d_sigma, p->d_rgba,

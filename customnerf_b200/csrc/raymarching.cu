@@ -204,6 +204,25 @@ __device__ __forceinline__ bool rm_step(const RayCtx &r, float &t, float &x, flo
 // ------------------------------------------------------------------------------------------------
 // utils
 // ------------------------------------------------------------------------------------------------
+// slab test of raymarching.cu:108-144 on precomputed reciprocal directions; a miss gives near = far = FLT_MAX
+__device__ __forceinline__ void rm_near_far(float ox, float oy, float oz, float rdx, float rdy, float rdz,
+                                            const float *__restrict__ aabb, float min_near, float &near, float &far) {
+    float tmp;
+    near = __fmul_rn(__fsub_rn(aabb[0], ox), rdx); far = __fmul_rn(__fsub_rn(aabb[3], ox), rdx);
+    if (near > far) { tmp = near; near = far; far = tmp; }
+    float near_y = __fmul_rn(__fsub_rn(aabb[1], oy), rdy), far_y = __fmul_rn(__fsub_rn(aabb[4], oy), rdy);
+    if (near_y > far_y) { tmp = near_y; near_y = far_y; far_y = tmp; }
+    if (near > far_y || near_y > far) { near = far = FLT_MAX; return; }
+    if (near_y > near) near = near_y;
+    if (far_y < far) far = far_y;
+    float near_z = __fmul_rn(__fsub_rn(aabb[2], oz), rdz), far_z = __fmul_rn(__fsub_rn(aabb[5], oz), rdz);
+    if (near_z > far_z) { tmp = near_z; near_z = far_z; far_z = tmp; }
+    if (near > far_z || near_z > far) { near = far = FLT_MAX; return; }
+    if (near_z > near) near = near_z;
+    if (far_z < far) far = far_z;
+    if (near < min_near) near = min_near;
+}
+
 __global__ void k_near_far_from_aabb(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
                                      const float *__restrict__ aabb, uint32_t N, float min_near,
                                      float *__restrict__ nears, float *__restrict__ fars) {
@@ -212,19 +231,8 @@ __global__ void k_near_far_from_aabb(const float *__restrict__ rays_o, const flo
     const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
     const float rdx = __fdiv_rn(1.0f, rays_d[n * 3]), rdy = __fdiv_rn(1.0f, rays_d[n * 3 + 1]),
                 rdz = __fdiv_rn(1.0f, rays_d[n * 3 + 2]);
-    float near = __fmul_rn(__fsub_rn(aabb[0], ox), rdx), far = __fmul_rn(__fsub_rn(aabb[3], ox), rdx), tmp;
-    if (near > far) { tmp = near; near = far; far = tmp; }
-    float near_y = __fmul_rn(__fsub_rn(aabb[1], oy), rdy), far_y = __fmul_rn(__fsub_rn(aabb[4], oy), rdy);
-    if (near_y > far_y) { tmp = near_y; near_y = far_y; far_y = tmp; }
-    if (near > far_y || near_y > far) { nears[n] = fars[n] = FLT_MAX; return; }
-    if (near_y > near) near = near_y;
-    if (far_y < far) far = far_y;
-    float near_z = __fmul_rn(__fsub_rn(aabb[2], oz), rdz), far_z = __fmul_rn(__fsub_rn(aabb[5], oz), rdz);
-    if (near_z > far_z) { tmp = near_z; near_z = far_z; far_z = tmp; }
-    if (near > far_z || near_z > far) { nears[n] = fars[n] = FLT_MAX; return; }
-    if (near_z > near) near = near_z;
-    if (far_z < far) far = far_z;
-    if (near < min_near) near = min_near;
+    float near, far;
+    rm_near_far(ox, oy, oz, rdx, rdy, rdz, aabb, min_near, near, far);
     nears[n] = near;
     fars[n] = far;
 }
@@ -458,9 +466,9 @@ __device__ __forceinline__ SegResult rm_march_segment(const RayCtx &r, uint32_t 
 __global__ void __launch_bounds__(kSegWarps * 32)
 k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
                   float bound, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
-                  const float *__restrict__ nears, const float *__restrict__ fars, const float *__restrict__ noises,
+                  float *__restrict__ nears, float *__restrict__ fars, const float *__restrict__ noises,
                   int32_t *__restrict__ counts, float *__restrict__ trec, uint32_t tcap,
-                  const int32_t *__restrict__ obounds) {
+                  const int32_t *__restrict__ obounds, const float *__restrict__ aabb, float min_near) {
     __shared__ float rec_s[kSegWarps][32][kRecStride];
     const uint32_t lane = nb_lane(), w = threadIdx.x >> 5;
     const uint32_t n = blockIdx.x * kSegWarps + w;
@@ -468,8 +476,14 @@ k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ ra
     if (n < N) {
         RayCtx r;
         rm_setup(r, rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, 0.0f, max_steps, C, H);
-        const float far = fars[n], dt = r.dt_min_c;
-        float t0 = nears[n];
+        float far, t0;
+        if (aabb) {         // near_far_from_aabb fused in (same reciprocals, same operation order: bit-identical)
+            rm_near_far(r.ox, r.oy, r.oz, r.rdx, r.rdy, r.rdz, aabb, min_near, t0, far);
+            if (lane == 0) { nears[n] = t0; fars[n] = far; }
+        } else {
+            far = fars[n]; t0 = nears[n];
+        }
+        const float dt = r.dt_min_c;
         t0 = __fmaf_rn(rm_dt(r, t0), noises ? noises[n] : 0.0f, t0);      // :351
         float *rec = rec_s[w][lane];
         float *out = trec ? trec + (size_t)n * tcap : nullptr;
@@ -721,14 +735,29 @@ __device__ __forceinline__ void ld_rgb(const TC *__restrict__ rgbs, size_t s, fl
     }
 }
 
+// optional fused MSE (fused train step): loss[0] += sum (image - target)^2 * inv_n, g_image = 2 (image - target) inv_n scale
+struct MseArgs { const float *target; float *loss, *g_image; float inv_n, scale; };
+
 template <typename TC>
 __global__ void __launch_bounds__(kCompBlock)
 k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ rgbs, const float *__restrict__ deltas,
                       const int32_t *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
-                      float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image) {
+                      float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image, MseArgs mse) {
+    __shared__ float loss_part[kCompBlock / 32];
     const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
-    if (n >= N) return;
     const uint32_t lane = nb_lane();
+    if (mse.target) {                       // whole block stays alive for the block-level loss reduction
+        if (lane == 0) loss_part[threadIdx.x >> 5] = 0.0f;
+        if (n >= N) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float v = 0.0f;
+                for (int i = 0; i < kCompBlock / 32; i++) v += loss_part[i];
+                if (v != 0.0f) atomicAdd(mse.loss, v * mse.inv_n);
+            }
+            return;
+        }
+    } else if (n >= N) return;
     const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
     float r = 0, g = 0, b = 0, ws = 0, d = 0;
     if (num_steps != 0 && offset + num_steps <= M) {
@@ -766,6 +795,20 @@ k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ r
         weights_sum[index] = ws;
         depth[index] = d;
         image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+    }
+    if (mse.target) {
+        if (lane == 0) {
+            const float d0 = r - mse.target[index * 3], d1 = g - mse.target[index * 3 + 1], d2 = b - mse.target[index * 3 + 2];
+            const float k = 2.0f * mse.inv_n * mse.scale;
+            mse.g_image[index * 3] = d0 * k; mse.g_image[index * 3 + 1] = d1 * k; mse.g_image[index * 3 + 2] = d2 * k;
+            loss_part[threadIdx.x >> 5] = d0 * d0 + d1 * d1 + d2 * d2;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float v = 0.0f;
+            for (int i = 0; i < kCompBlock / 32; i++) v += loss_part[i];
+            atomicAdd(mse.loss, v * mse.inv_n);
+        }
     }
 }
 
@@ -953,9 +996,9 @@ static inline float *march_trec(int32_t *scratch, uint32_t N) {
 
 static int march_count_impl(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
                             float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
-                            const float *nears, const float *fars, const float *noises,
+                            float *nears, float *fars, const float *noises,
                             int32_t *rays, int32_t *counter, int32_t *scratch, uint32_t M_cap, int32_t *m_eff,
-                            void *stream) {
+                            const float *aabb, float min_near, void *stream) {
     if (N == 0) return 0;
     if (!scratch || !rays || !counter) return NB200_E_BAD_ARG;
     static int serial_env = -1;
@@ -977,11 +1020,16 @@ static int march_count_impl(const float *rays_o, const float *rays_d, const uint
             NB_LAUNCH_CHECK();
         }
         k_march_count_seg<<<nb, kSegWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, max_steps, N, C, H, nears, fars,
-                                                        noises, scratch, march_trec(scratch, N), march_tcap(N), obounds);
+                                                        noises, scratch, march_trec(scratch, N), march_tcap(N), obounds,
+                                                        aabb, min_near);
         NB_LAUNCH_CHECK();
         k_march_scan_rays<<<1, 1024, 0, st>>>(scratch, rays, N, counter, M_cap, m_eff);
         NB_LAUNCH_CHECK();
         return 0;
+    }
+    if (aabb) {             // the serial kernel reads nears / fars: produce them first
+        k_near_far_from_aabb<<<nb_div_up(N, 128), 128, 0, st>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+        NB_LAUNCH_CHECK();
     }
     k_march_count<<<nb, kMarchBlock, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
                                               noises, rays, block_sums, rpw, march_trec(scratch, N), march_tcap(N));
@@ -1010,19 +1058,19 @@ int nb200_march_rays_train_count(const float *rays_o, const float *rays_d, const
                                  float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                  const float *nears, const float *fars, const float *noises,
                                  int32_t *rays, int32_t *counter, int32_t *scratch, void *stream) {
-    return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter,
-                            scratch, 0, nullptr, stream);
+    return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, const_cast<float *>(nears),
+                            const_cast<float *>(fars), noises, rays, counter, scratch, 0, nullptr, nullptr, 0.0f, stream);
 }
 
 // fused train step: count + scan, then expand, into buffers of M_cap rows; *m_eff = rows covered by complete segments
 int nb200_fs_march_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
-                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, const float *nears,
-                         const float *fars, const float *noises, int32_t *rays, int32_t *counter, int32_t *m_eff,
-                         int32_t *scratch, void *stream) {
+                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, float *nears,
+                         float *fars, const float *noises, int32_t *rays, int32_t *counter, int32_t *m_eff,
+                         int32_t *scratch, const float *aabb, float min_near, void *stream) {
     if (N == 0) return 0;
-    if (!m_eff) return NB200_E_BAD_ARG;
+    if (!m_eff || !nears || !fars) return NB200_E_BAD_ARG;
     return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays,
-                            counter, scratch, M_cap, m_eff, stream);
+                            counter, scratch, M_cap, m_eff, aabb, min_near, stream);
 }
 
 int nb200_fs_march_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
@@ -1060,7 +1108,7 @@ int nb200_composite_rays_train_forward(const float *sigmas, const float *rgbs, c
                                        float *image, void *stream) {
     if (N == 0) return 0;
     k_composite_train_fwd<float><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
-        sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+        sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image, MseArgs{nullptr, nullptr, nullptr, 0.0f, 0.0f});
     NB_LAUNCH_CHECK();
     return 0;
 }
@@ -1068,10 +1116,13 @@ int nb200_composite_rays_train_forward(const float *sigmas, const float *rgbs, c
 // fused train step: colours are the field kernel's half [M,4] rows; grad_rgba rows are float4 [g_r, g_g, g_b, 0]
 int nb200_fs_composite_forward(const float *sigmas, const void *rgba, const float *deltas, const int32_t *rays,
                                uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image,
+                               const float *target, float inv_n, float loss_scale, float *loss, float *g_image,
                                void *stream) {
     if (N == 0) return 0;
+    if (target && (!loss || !g_image)) return NB200_E_BAD_ARG;
     k_composite_train_fwd<__half><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
-        sigmas, (const __half *)rgba, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+        sigmas, (const __half *)rgba, deltas, rays, M, N, T_thresh, weights_sum, depth, image,
+        MseArgs{target, loss, g_image, inv_n, loss_scale});
     NB_LAUNCH_CHECK();
     return 0;
 }

@@ -31,12 +31,11 @@ import torch
 from . import _lib as L
 
 LOSS_SCALE = 128.0
-# this library's kernels in one step: near/far, march count + scan + fixup + write, encode, field, composite, loss,
-# composite^T, field^T + weight-gradient reduce, encode^T, adam hyper, adam, weight pack x2
-KERNELS_PER_STEP = 17
-STAGES = ["near_far_from_aabb", "march_count", "march_write", "grid_encode_forward", "field_forward",
-          "composite_forward", "mse_loss", "composite_backward", "field_backward", "grid_encode_backward",
-          "adam", "pack_weights"]
+# this library's kernels in one step: march count (+ near/far) + scan + expand, encode, field, composite (+ MSE),
+# composite^T, field^T + weight-gradient reduce, encode^T, adam hyper, adam, weight pack
+KERNELS_PER_STEP = 12
+STAGES = ["march_count", "march_write", "grid_encode_forward", "field_forward", "composite_forward",
+          "composite_backward", "field_backward", "grid_encode_backward", "adam", "pack_weights"]
 
 
 def _check(rc, what):

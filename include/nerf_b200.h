@@ -188,11 +188,12 @@ uint32_t nb200_field_wgrad_scratch_bytes(void);
 /* count + scan (nb200_march_rays_train_count) and write (nb200_march_rays_train_write) into buffers of M_cap rows.
  * counter[0] += total samples, counter[1] += N as the reference; *m_eff (device i32) = number of leading rows covered
  * by complete ray segments (= min(total, offset of the first ray that does not fit)): the row bound of every later
- * stage.  _count initialises it, _write lowers it. */
+ * stage.  _count initialises it, _write lowers it.  With aabb != NULL, _count also performs near_far_from_aabb
+ * (raymarching.cu:108-144; same arithmetic, bit-identical) and WRITES nears / fars instead of reading them. */
 int nb200_fs_march_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
-                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, const float *nears,
-                         const float *fars, const float *noises, int32_t *rays, int32_t *counter, int32_t *m_eff,
-                         int32_t *scratch, void *stream);
+                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, float *nears,
+                         float *fars, const float *noises, int32_t *rays, int32_t *counter, int32_t *m_eff,
+                         int32_t *scratch, const float *aabb, float min_near, void *stream);
 int nb200_fs_march_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M_cap, const float *nears,
                          const float *fars, const float *noises, const int32_t *rays, float *xyzs, float *dirs,
@@ -210,7 +211,8 @@ int nb200_fs_encode_backward(const void *d_x_en, const float *xyz, float bound, 
  * slices [..., :3] and casts to float, renderer.py:510,635) and writing grad_rgba as float4 rows [g_r, g_g, g_b, 0]. */
 int nb200_fs_composite_forward(const float *sigmas, const void *rgba, const float *deltas, const int32_t *rays,
                                uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image,
-                               void *stream);
+                               const float *target, float inv_n, float loss_scale, float *loss, float *g_image,
+                               void *stream);   /* target != NULL: nb200_mse_loss_grad fused in (per ray) */
 int nb200_fs_composite_backward(const float *grad_weights_sum, const float *grad_image, const float *sigmas,
                                 const void *rgba, const float *deltas, const int32_t *rays, const float *weights_sum,
                                 const float *image, uint32_t M, uint32_t N, float T_thresh, float *grad_sigmas,
@@ -262,7 +264,7 @@ typedef struct nb200_train_plan {
  * event before its first kernel and after each of its NB200_FB_STAGES stages, nb200_train_update after each of its
  * NB200_UP_STAGES stages.  nb200_stage_timer_read synchronises on the last event and returns the stage durations in
  * microseconds: out_us[NB200_FB_STAGES + NB200_UP_STAGES] (host memory). */
-#define NB200_FB_STAGES 10   /* near_far, march_count, march_write, encode, field, composite, loss, composite^T, field^T, encode^T */
+#define NB200_FB_STAGES 8    /* march_count (+ near/far), march_write, encode, field, composite (+ MSE), composite^T, field^T, encode^T */
 #define NB200_UP_STAGES 2    /* adam (hyper + sweep), weight pack */
 int nb200_stage_timer_create(void **timer);
 int nb200_stage_timer_destroy(void *timer);
