@@ -33,10 +33,12 @@ k_fused_adam(float4 *__restrict__ param, float4 *__restrict__ grad, float4 *__re
     const AdamHyper h0 = hyper[0], h1 = hyper[1];
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
         const AdamHyper &h = i < split4 ? h0 : h1;
-        float4 p = param[i], g = grad[i], m = exp_avg[i], v = exp_avg_sq[i];
+        // the moments are touched once per step: streaming loads / stores keep them from displacing the table and its
+        // gradient (both L2-resident between the encode kernels and this sweep)
+        float4 p = param[i], g = grad[i], m = __ldcs(exp_avg + i), v = __ldcs(exp_avg_sq + i);
         adam1(p.x, g.x, m.x, v.x, h); adam1(p.y, g.y, m.y, v.y, h);
         adam1(p.z, g.z, m.z, v.z, h); adam1(p.w, g.w, m.w, v.w, h);
-        param[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
+        param[i] = p; __stcs(exp_avg + i, m); __stcs(exp_avg_sq + i, v);
         if (zero_grad) grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
