@@ -463,6 +463,10 @@ __device__ __forceinline__ SegResult rm_march_segment(const RayCtx &r, uint32_t 
     return o;
 }
 
+// kLanes lanes cooperate on one ray (32 / kLanes rays per warp).  Fewer lanes per ray = longer segments: the per-lane
+// work evens out (a warp issues for its slowest lane) and the per-round overheads are shared by more lattice points,
+// at the price of fewer warps to hide the chain latency; 8 measured best at ~15 k rays (profiles/).
+template <int kLanes>
 __global__ void __launch_bounds__(kSegWarps * 32)
 k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
                   float bound, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
@@ -470,89 +474,113 @@ k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ ra
                   int32_t *__restrict__ counts, float *__restrict__ trec, uint32_t tcap,
                   const int32_t *__restrict__ obounds, const float *__restrict__ aabb, float min_near) {
     __shared__ float rec_s[kSegWarps][32][kRecStride];
+    constexpr uint32_t kFull = 0xffffffffu, kRaysPerWarp = 32 / kLanes, kGroupMask = kLanes == 32 ? kFull : ((1u << kLanes) - 1u);
     const uint32_t lane = nb_lane(), w = threadIdx.x >> 5;
-    const uint32_t n = blockIdx.x * kSegWarps + w;
+    const uint32_t li = lane % kLanes, gshift = lane - li;          // index inside the ray's lane group, group's first lane
+    const uint32_t n = (blockIdx.x * kSegWarps + w) * kRaysPerWarp + lane / kLanes;
     uint32_t total = 0;
+    RayCtx r;
+    float far = 0.0f, t0 = 0.0f, dt = 0.0f;
+    bool ended = true;
+    float *rec = rec_s[w][lane];
+    float *out = nullptr;
     if (n < N) {
-        RayCtx r;
         rm_setup(r, rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, 0.0f, max_steps, C, H);
-        float far, t0;
         if (aabb) {         // near_far_from_aabb fused in (same reciprocals, same operation order: bit-identical)
             rm_near_far(r.ox, r.oy, r.oz, r.rdx, r.rdy, r.rdz, aabb, min_near, t0, far);
-            if (lane == 0) { nears[n] = t0; fars[n] = far; }
+            if (li == 0) { nears[n] = t0; fars[n] = far; }
         } else {
             far = fars[n]; t0 = nears[n];
         }
-        const float dt = r.dt_min_c;
+        dt = r.dt_min_c;
         t0 = __fmaf_rn(rm_dt(r, t0), noises ? noises[n] : 0.0f, t0);      // :351
-        float *rec = rec_s[w][lane];
-        float *out = trec ? trec + (size_t)n * tcap : nullptr;
-        if (t0 < far && rm_may_hit(r, obounds, C, H, t0, far)) {
-            const float kest = fminf(__fdividef(far - t0, dt) + 2.0f, 1.0e9f);
-            const uint32_t seg = (uint32_t)min(max((int)ceilf(kest * (1.0f / 32.0f)), kSegMin), kSegMax);
-            uint32_t K0 = 0;            // first index of the window == the chain's entry into it (exact for lane 0)
-            float tK0 = t0;
-            bool ended = false;
-            while (!ended) {
-                const uint32_t a = K0 + lane * seg, b = a + seg;
-                const float ta = rm_lattice_jump(tK0, dt, lane * seg);
-                SegResult sr = rm_march_segment(r, a, ta, b, far, rec);
-                // ---- thread the true chain through the segments
-                uint32_t e = K0, drop = 0, valid = 0;
-                float te = tK0;
-                // common case, checked in parallel: every segment up to the one where the ray ends is entered at its
-                // own first index or at the first point its lane moved to, i.e. lane s-1 landed on a_s or on v1_s
-                {
-                    const uint32_t pl = __shfl_up_sync(0xffffffffu, sr.land, 1);
-                    const bool ok = lane == 0 || pl == a || pl == sr.v1;
-                    const uint32_t endm = __ballot_sync(0xffffffffu, !(sr.tland < far));
-                    const uint32_t last = endm ? (uint32_t)__ffs((int)endm) - 1u : 31u;      // segment in which the chain ends
-                    const uint32_t bad = __ballot_sync(0xffffffffu, !ok) & (last == 31u ? 0xffffffffu : ((2u << last) - 1u));
-                    if (bad == 0) {
-                        if (lane <= last) {
-                            drop = (lane != 0 && pl != a && sr.occ_a) ? 1u : 0u;
-                            valid = sr.cnt - drop;
-                        }
-                        e = __shfl_sync(0xffffffffu, sr.land, last);
-                        te = __shfl_sync(0xffffffffu, sr.tland, last);
-                        ended = endm != 0;
-                    } else {
-                        for (uint32_t sgm = 0; sgm < 32; sgm++) {
-                            const uint32_t as = K0 + sgm * seg, bs = as + seg;
-                            if (e >= bs) continue;                                  // the chain jumps over this segment
-                            const uint32_t v1s = __shfl_sync(0xffffffffu, sr.v1, sgm);
-                            const bool occs = __shfl_sync(0xffffffffu, (int)sr.occ_a, sgm) != 0;
-                            uint32_t dr;
-                            if (e == as) dr = 0;
-                            else if (e == v1s) dr = occs ? 1u : 0u;
-                            else {                                                  // mis-speculation: re-march from the true entry
-                                if (lane == sgm) sr = rm_march_segment(r, e, te, b, far, rec);
-                                dr = 0;
-                            }
-                            if (lane == sgm) { drop = dr; valid = sr.cnt - dr; }
-                            e = __shfl_sync(0xffffffffu, sr.land, sgm);
-                            te = __shfl_sync(0xffffffffu, sr.tland, sgm);
-                            if (!(te < far)) { ended = true; break; }
-                        }
-                    }
+        out = trec ? trec + (size_t)n * tcap : nullptr;
+        ended = !(t0 < far && rm_may_hit(r, obounds, C, H, t0, far));
+    }
+    const float kest = ended ? 0.0f : fminf(__fdividef(far - t0, dt) + 2.0f, 1.0e9f);
+    const uint32_t seg = (uint32_t)min(max((int)ceilf(kest * (1.0f / kLanes)), kSegMin), kSegMax);
+    uint32_t K0 = 0;            // first index of the window == the chain's entry into it (exact for the group's lane 0)
+    float tK0 = t0;
+    // groups of a warp finish at different times: the collectives below always run warp-wide, a finished group's lanes
+    // contribute values nobody uses
+    while (__any_sync(kFull, !ended)) {
+        uint32_t a = 0, b = 0;
+        SegResult sr;
+        sr.cnt = 0; sr.v1 = 0; sr.land = 0; sr.tland = 0.0f; sr.occ_a = false;
+        if (!ended) {
+            a = K0 + li * seg; b = a + seg;
+            const float ta = rm_lattice_jump(tK0, dt, li * seg);
+            sr = rm_march_segment(r, a, ta, b, far, rec);
+        }
+        // ---- thread the true chain through the group's segments
+        uint32_t e = K0, drop = 0, valid = 0;
+        float te = tK0;
+        bool now_ended = false;
+        // common case, checked in parallel: every segment up to the one where the ray ends is entered at its own first
+        // index or at the first point its lane moved to, i.e. lane s-1 landed on a_s or on v1_s
+        const uint32_t pl = __shfl_up_sync(kFull, sr.land, 1, kLanes);
+        const bool ok = li == 0 || pl == a || pl == sr.v1;
+        const uint32_t endm = (__ballot_sync(kFull, !(sr.tland < far)) >> gshift) & kGroupMask;
+        const uint32_t last = endm ? (uint32_t)__ffs((int)endm) - 1u : (uint32_t)kLanes - 1u;      // segment in which the chain ends
+        const uint32_t upto = last == 31u ? kFull : ((2u << last) - 1u);
+        const uint32_t bad = (__ballot_sync(kFull, !ok) >> gshift) & kGroupMask & upto;
+        {
+            const uint32_t land_l = __shfl_sync(kFull, sr.land, last, kLanes);
+            const float tland_l = __shfl_sync(kFull, sr.tland, last, kLanes);
+            if (bad == 0) {
+                if (li <= last) {
+                    drop = (li != 0 && pl != a && sr.occ_a) ? 1u : 0u;
+                    valid = sr.cnt - drop;
                 }
-                // ---- compact this round's samples behind the ray's earlier ones (max_steps caps the ray, :359)
-                const uint32_t incl = (uint32_t)nb_warp_incl_scan((int)valid);
-                const uint32_t round_total = __shfl_sync(0xffffffffu, incl, 31);
-                const uint32_t first = total + incl - valid;
-                if (out) {
-                    for (uint32_t i = 0; i < valid; i++) {
-                        const uint32_t idx = first + i;
-                        if (idx < max_steps && idx < tcap) out[idx] = rec[drop + i];
-                    }
-                }
-                total += round_total;
-                if (total >= max_steps) { total = max_steps; ended = true; }
-                K0 = e; tK0 = te;
+                e = land_l; te = tland_l;
+                now_ended = endm != 0;
             }
         }
+        if (__any_sync(kFull, bad != 0 && !ended)) {        // rare: some group must be threaded sequentially
+            const bool mine = bad != 0 && !ended;
+            bool stop = !mine;
+            for (uint32_t sgm = 0; sgm < (uint32_t)kLanes; sgm++) {
+                const uint32_t as = K0 + sgm * seg, bs = as + seg;
+                const uint32_t v1s = __shfl_sync(kFull, sr.v1, sgm, kLanes);
+                const bool occs = __shfl_sync(kFull, (int)sr.occ_a, sgm, kLanes) != 0;
+                const bool visit = !stop && e < bs;                     // (else the chain jumps over this segment)
+                uint32_t dr = 0;
+                if (visit && e != as) {
+                    if (e == v1s) dr = occs ? 1u : 0u;
+                    else if (li == sgm) sr = rm_march_segment(r, e, te, b, far, rec);   // mis-speculation: re-march
+                }
+                if (visit && li == sgm) { drop = dr; valid = sr.cnt - dr; }
+                const uint32_t land_s = __shfl_sync(kFull, sr.land, sgm, kLanes);
+                const float tland_s = __shfl_sync(kFull, sr.tland, sgm, kLanes);
+                if (visit) {
+                    e = land_s; te = tland_s;
+                    if (!(te < far)) { now_ended = true; stop = true; }
+                }
+            }
+        }
+        // ---- compact this round's samples behind the ray's earlier ones (max_steps caps the ray, :359)
+        uint32_t incl = valid;
+#pragma unroll
+        for (int o = 1; o < kLanes; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, incl, o, kLanes);
+            if ((int)li >= o) incl += t;
+        }
+        const uint32_t round_total = __shfl_sync(kFull, incl, kLanes - 1, kLanes);
+        if (!ended) {
+            const uint32_t first = total + incl - valid;
+            if (out) {
+                for (uint32_t i = 0; i < valid; i++) {
+                    const uint32_t idx = first + i;
+                    if (idx < max_steps && idx < tcap) out[idx] = rec[drop + i];
+                }
+            }
+            total += round_total;
+            if (total >= max_steps) { total = max_steps; now_ended = true; }
+            K0 = e; tK0 = te;
+            ended = now_ended;
+        }
     }
-    if (lane == 0 && n < N) counts[n] = (int32_t)total;
+    if (li == 0 && n < N) counts[n] = (int32_t)total;
 }
 
 // single block: rays[n] = (n, exclusive prefix of the per-ray counts starting at counter[0], count); counter += (sum, N)
@@ -1019,9 +1047,18 @@ static int march_count_impl(const float *rays_o, const float *rays_d, const uint
             k_occ_bounds<<<148, 256, 0, st>>>(grid, C, H, obounds);
             NB_LAUNCH_CHECK();
         }
-        k_march_count_seg<<<nb, kSegWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, max_steps, N, C, H, nears, fars,
-                                                        noises, scratch, march_trec(scratch, N), march_tcap(N), obounds,
-                                                        aabb, min_near);
+        static int lanes_env = -1;
+        if (lanes_env < 0) { const char *e = getenv("NB200_MARCH_LANES"); lanes_env = e ? atoi(e) : 0; }
+        uint32_t lanes = (lanes_env == 4 || lanes_env == 8 || lanes_env == 16 || lanes_env == 32) ? (uint32_t)lanes_env : 8u;
+        while (lanes < 32 && (uint64_t)N * lanes < 148ull * 4 * 32 * 4) lanes <<= 1;     // few rays: keep >= ~4 warps per scheduler
+        const uint32_t rays_per_block = kSegWarps * 32 / lanes, nbk = nb_div_up(N, rays_per_block);
+#define NB_SEG_LAUNCH(L) k_march_count_seg<L><<<nbk, kSegWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, max_steps, N, C, H, \
+        nears, fars, noises, scratch, march_trec(scratch, N), march_tcap(N), obounds, aabb, min_near)
+        if (lanes == 4) NB_SEG_LAUNCH(4);
+        else if (lanes == 8) NB_SEG_LAUNCH(8);
+        else if (lanes == 16) NB_SEG_LAUNCH(16);
+        else NB_SEG_LAUNCH(32);
+#undef NB_SEG_LAUNCH
         NB_LAUNCH_CHECK();
         k_march_scan_rays<<<1, 1024, 0, st>>>(scratch, rays, N, counter, M_cap, m_eff);
         NB_LAUNCH_CHECK();
