@@ -372,7 +372,7 @@ constexpr uint32_t SB_HR = SB_HD + 16384;
 constexpr uint32_t SB_XV2 = SB_HR + 16384;          // second x_en | view buffer (tiles alternate)
 constexpr uint32_t S_BWD_BYTES = SB_XV2 + 16384;    // 45056 + 11 * 16384 = 225280
 // TMEM columns
-constexpr uint32_t C_DG = 0, C_W1 = 64, C_W2 = 96, C_W3 = 160, C_PAIR = 224, C_R1V = 288, C_D2 = 320, C_R2 = 384;
+constexpr uint32_t C_DG = 0, C_W1 = 64, C_W2 = 96, C_W3 = 160, C_PAIR = 224, C_R1V = 288, C_D2 = 320, C_R2 = 384, C_DG2 = 448;
 constexpr uint32_t kTmemColsBwd = 512;
 
 struct FieldBwdArgs {
@@ -517,6 +517,10 @@ k_field_backward(const FieldBwdArgs p) {
         for (uint32_t k = 0; k < nk; k++)
             umma::mma_f16_ss(tmem + C_DG, kdesc(a, ak + k), kdesc(b, bk + k), idesc, !(first && k == 0));
     };
+    auto dgrad_to = [&](uint32_t dcol, uint32_t a, uint32_t ak, uint32_t b, uint32_t bk, uint32_t nk, uint32_t idesc) {
+        for (uint32_t k = 0; k < nk; k++)
+            umma::mma_f16_ss(tmem + dcol, kdesc(a, ak + k), kdesc(b, bk + k), idesc, k != 0);
+    };
     // D[cols] (+)= A_tile^T (M = 128: this tile and the next) x B_tile[:, col0 : col0 + N], contraction over the 128 points
     auto wgrad = [&](uint32_t dcol, uint32_t a, uint32_t b, uint32_t bcol0, uint32_t idesc) {
         for (uint32_t k = 0; k < 8; k++)
@@ -612,23 +616,18 @@ k_field_backward(const FieldBwdArgs p) {
         cp_async_wait<3>();                // G1 landed (this thread's part); the barrier below covers the other threads
         publish();
 
-        // ---- stage 1: dHR = (dOr Wr2) * [hr > 0]
+        // ---- stages 1 + 2: dHR = (dOr Wr2) * [hr > 0] and dHD = (dOd Wd2) * [hd > 0] are independent (both read only the
+        //      head gradients): one commit, one epilogue pass over two accumulators;  wgrad of the two heads (A = T16^T)
         if (issuer_warp && umma::elect_one()) {
-            dgrad(sT16, 0, sW + B_W16T, 0, 1, ID64, true);
-            umma::commit(&bar);
-        }
-        wait_mma();
-        epilogue(smem + SB_HR, SB_GA);
-        publish();
-        // ---- stage 2: dHD = (dOd Wd2) * [hd > 0];   wgrad of the two heads (A = T16^T)
-        if (issuer_warp && umma::elect_one()) {
-            dgrad(sT16, 1, sW + B_W16T, 1, 1, ID64, true);
+            dgrad_to(C_DG, sT16, 0, sW + B_W16T, 0, 1, ID64);
+            dgrad_to(C_DG2, sT16, 1, sW + B_W16T, 1, 1, ID64);
             umma::commit(&bar);
             wgrad(C_R2, sT16, sHR, 0, WG64);
             wgrad(C_D2, sT16, sHD, 0, WG64);
         }
         wait_mma();
-        epilogue(smem + SB_HD, SB_GB);
+        epilogue(smem + SB_HR, SB_GA);
+        bwd_epilogue_half(trow + C_DG2 + 32 * half, smem + SB_HD, smem + SB_GB, row, half);
         cp_async_wait<2>();                // G2: FEA (and G1's x_en) for the weight gradients of stage 3
         publish();
         // ---- stage 3: dFEA = dHR Wr1f + dHD Wd1;   wgrad Wr1f | Wd1 (A = [dHR | dHD]^T, B = fea), Wr1v (A = dHR^T, B = view)
