@@ -83,7 +83,7 @@ def flatten_parameters(model):
 class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
-                 lr_decay_iters=0):
+                 lr_decay_iters=0, allreduce_chunks=0, process_group=None):
         if not model.cuda_ray:
             raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
@@ -96,6 +96,10 @@ class FusedTrainStep:
         self.betas, self.eps = betas, float(eps)
         self.world_size = world_size
         self.grad_sync = grad_sync          # callable(flat fp32 grad tensor) -> None (sums across ranks in place)
+        # allreduce_chunks > 1: the flat gradient is all-reduced (torch.distributed, NCCL) in that many pieces and the
+        # Adam sweep of piece i runs while piece i+1 is still on the wire (replaces grad_sync)
+        self.allreduce_chunks = int(allreduce_chunks)
+        self.process_group = process_group
         self.use_graph = use_graph
         self.perturb = perturb
         self.T_thresh, self.dt_gamma, self.max_steps = float(T_thresh), float(dt_gamma), int(max_steps)
@@ -228,10 +232,33 @@ class FusedTrainStep:
         if self.perturb:
             self.noises.uniform_()
         _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), st), "train_forward_backward")
-        if self.grad_sync is not None:
-            self.grad_sync(self.grads_flat)
-        _check(self.lib.nb200_train_update(C.byref(self.plan), st), "train_update")
+        if self.allreduce_chunks > 1:
+            self._pipelined_allreduce_update(st)
+        else:
+            if self.grad_sync is not None:
+                self.grad_sync(self.grads_flat)
+            _check(self.lib.nb200_train_update(C.byref(self.plan), st), "train_update")
         self.stats_host.copy_(self.stats, non_blocking=True)
+
+    def _pipelined_allreduce_update(self, st):
+        """all-reduce(sum) of grads_flat in pieces on NCCL's stream, each piece's Adam sweep as soon as it has arrived"""
+        import torch.distributed as dist
+        n, n_table = self.params_flat.numel(), self.layout[0][2]
+        per = ((n + self.allreduce_chunks - 1) // self.allreduce_chunks + 1023) // 1024 * 1024
+        ranges = [(a, min(n, a + per)) for a in range(0, n, per)]
+        works = [dist.all_reduce(self.grads_flat[a:b], op=dist.ReduceOp.SUM, group=self.process_group, async_op=True)
+                 for a, b in ranges]
+        p = self.plan
+        _check(self.lib.nb200_adam_hyper(C.c_void_p(p.step), C.c_void_p(p.sched), C.c_void_p(p.hyper), st), "adam_hyper")
+        for (a, b), wk in zip(ranges, works):
+            wk.wait()                       # the current stream waits for this piece only
+            split = min(max(n_table - a, 0), b - a)
+            _check(self.lib.nb200_fused_adam(C.c_void_p(p.params_flat + 4 * a), C.c_void_p(p.grads_flat + 4 * a),
+                                             C.c_void_p(p.exp_avg + 4 * a), C.c_void_p(p.exp_avg_sq + 4 * a),
+                                             C.c_uint64(b - a), C.c_uint64(split), C.c_void_p(p.hyper), C.c_int(1), st),
+                   "fused_adam")
+        _check(self.lib.nb200_field_pack_weights(C.c_void_p(p.trunk), C.c_void_p(p.density), C.c_void_p(p.rgb),
+                                                 C.c_void_p(p.w_fwd), C.c_void_p(p.w_bwd), st), "field_pack_weights")
 
     def _capture(self):
         """warm up on a side stream (first-call cudaFuncSetAttribute, allocator, RNG registration), capture one step,

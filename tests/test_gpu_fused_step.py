@@ -152,12 +152,17 @@ def test_graph_capture_includes_nccl_allreduce():
         plain = fused_trainer.FusedTrainStep(ma, N_RAYS, perturb=False, use_graph=True)
         synced = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False, use_graph=True,
                                               grad_sync=lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM))
-        la, lb = [], []
+        mc, _ = _models()
+        piped = fused_trainer.FusedTrainStep(mc, N_RAYS, perturb=False, use_graph=True, allreduce_chunks=3)
+        la, lb, lc = [], [], []
         for _ in range(4):
             plain.step(o, d, tgt); la.append(plain.last_stats()[0])
             synced.step(o, d, tgt); lb.append(synced.last_stats()[0])
+            piped.step(o, d, tgt); lc.append(piped.last_stats()[0])     # chunked all-reduce pipelined with Adam
         np.testing.assert_allclose(lb, la, rtol=2e-2)
-        assert lb[-1] < lb[0]
+        np.testing.assert_allclose(lc, la, rtol=2e-2)
+        assert lb[-1] < lb[0] and lc[-1] < lc[0]
+        assert int(piped.step_count) == 4
     finally:
         dist.destroy_process_group()
 
