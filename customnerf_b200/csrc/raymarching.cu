@@ -967,6 +967,133 @@ k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *__r
     image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
 }
 
+// ------------------------------------------------------------------------------------------------
+// inference rounds driven from the device (no per-round host synchronisation)
+// ------------------------------------------------------------------------------------------------
+// The reference's eval loop (nerf/renderer.py:651-688) reads n_alive back every round to pick n_step and to compact
+// rays_alive with a boolean mask.  Here the round state lives on the device: state = {n_alive, n_step, step, samples}.
+// A round = plan -> march -> (encode, field) -> composite -> compact, every kernel launched for the worst case (N rays /
+// N + pad samples) and bounded by the state, so a round can be captured once in a CUDA graph and replayed; the host
+// only looks at n_alive every few rounds.  Per ray the samples and their order are those of the reference loop, so the
+// composited image is the same.
+__global__ void k_infer_plan(int32_t *__restrict__ state, uint32_t N, uint32_t max_steps) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n_alive = state[0];
+    const int step = state[2];
+    if (step >= (int)max_steps) n_alive = 0;                               // while step < max_steps   (:667)
+    const int n_step = n_alive > 0 ? max(min((int)N / n_alive, 8), 1) : 0;   // :676
+    state[0] = n_alive;
+    state[1] = n_step;
+    state[3] = n_alive * n_step;                                           // sample rows of this round
+}
+
+__global__ void __launch_bounds__(128)
+k_march_rays_dev(const int32_t *__restrict__ state, const int32_t *__restrict__ rays_alive, const float *__restrict__ rays_t,
+                 const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, float dt_gamma,
+                 uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *__restrict__ grid,
+                 const float *__restrict__ fars, float *__restrict__ xyzs, float *__restrict__ dirs,
+                 float *__restrict__ deltas, const float *__restrict__ noises) {
+    const uint32_t n_alive = (uint32_t)state[0], n_step = (uint32_t)state[1];
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int32_t index = rays_alive[n];
+    RayCtx r;
+    rm_setup(r, rays_o + (size_t)index * 3, rays_d + (size_t)index * 3, grid, bound, dt_gamma, max_steps, C, H);
+    float *px = xyzs + (size_t)n * n_step * 3, *pd = dirs + (size_t)n * n_step * 3, *pl = deltas + (size_t)n * n_step * 2;
+    float t = rays_t[index];
+    const float far = fars[index];
+    t = __fmaf_rn(rm_dt(r, t), (noises && state[2] == 0) ? noises[n] : 0.0f, t);      // perturb in the first round only (:677)
+    float last_t = t, x, y, z, dt;
+    uint32_t step = 0;
+    while (t < far && step < n_step) {
+        if (rm_step(r, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t = __fadd_rn(t, dt);
+            pl[0] = dt; pl[1] = __fsub_rn(t, last_t);
+            last_t = t;
+            px += 3; pd += 3; pl += 2; step++;
+        }
+    }
+    for (; step < n_step; step++) {          // unused slots read as "ray finished" (the reference zero-fills, raymarching.py:391-393)
+        px[0] = px[1] = px[2] = 0.0f; pd[0] = pd[1] = pd[2] = 0.0f; pl[0] = pl[1] = 0.0f;
+        px += 3; pd += 3; pl += 2;
+    }
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(128)
+k_composite_rays_dev(const int32_t *__restrict__ state, float T_thresh, int32_t *__restrict__ rays_alive,
+                     float *__restrict__ rays_t, const float *__restrict__ sigmas, const TC *__restrict__ rgbs,
+                     const float *__restrict__ deltas, float *__restrict__ weights_sum, float *__restrict__ depth,
+                     float *__restrict__ image) {
+    const uint32_t n_alive = (uint32_t)state[0], n_step = (uint32_t)state[1];
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int32_t index = rays_alive[n];
+    size_t s = (size_t)n * n_step;
+    float t = rays_t[index];
+    float weight_sum = weights_sum[index], d = depth[index];
+    float r = image[index * 3], g = image[index * 3 + 1], b = image[index * 3 + 2];
+    uint32_t step = 0;
+    while (step < n_step) {
+        const float d0 = deltas[s * 2], d1 = deltas[s * 2 + 1];
+        if (d0 == 0) break;                                      // :1042
+        const float alpha = 1.0f - __expf(-sigmas[s] * d0);
+        const float T = 1 - weight_sum;                          // :1052
+        const float weight = alpha * T;
+        float c0, c1, c2;
+        ld_rgb<TC>(rgbs, s, c0, c1, c2);
+        weight_sum += weight;
+        t += d1;
+        d = fmaf(weight, t, d);
+        r = fmaf(weight, c0, r); g = fmaf(weight, c1, g); b = fmaf(weight, c2, b);
+        if (T < T_thresh) break;                                 // :1066
+        s++; step++;
+    }
+    if (step < n_step) rays_alive[n] = -1; else rays_t[index] = t;   // :1078-1082
+    weights_sum[index] = weight_sum; depth[index] = d;
+    image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+}
+
+// ordered compaction rays_alive[rays_alive >= 0] (:685) by one block; state: n_alive = survivors, step += n_step
+__global__ void __launch_bounds__(1024)
+k_compact_alive(int32_t *__restrict__ state, const int32_t *__restrict__ alive_in, int32_t *__restrict__ alive_out) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s, chunk_total_s;
+    const uint32_t n_alive = (uint32_t)state[0];
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_alive; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const int32_t v = (i < n_alive) ? alive_in[i] : -1;
+        const int keep = v >= 0 ? 1 : 0;
+        const int incl = nb_warp_incl_scan(keep);
+        if (nb_lane() == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int wt = warp_tot[threadIdx.x];
+            const int wi = nb_warp_incl_scan(wt);
+            warp_tot[threadIdx.x] = wi - wt;
+            if (threadIdx.x == 31) chunk_total_s = wi;
+        }
+        __syncthreads();
+        if (keep) alive_out[carry_s + warp_tot[threadIdx.x >> 5] + incl - 1] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += chunk_total_s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        state[2] += state[1];
+        state[0] = carry_s;
+    }
+}
+
+__global__ void k_copy_alive(const int32_t *__restrict__ state, const int32_t *__restrict__ src, int32_t *__restrict__ dst) {
+    const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i < (uint32_t)state[0]) dst[i] = src[i];
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1208,6 +1335,48 @@ int nb200_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int3
     k_composite_rays<<<nb_div_up(n_alive, 128), 128, 0, nb_stream(stream)>>>(n_alive, n_step, T_thresh, rays_alive,
                                                                             rays_t, sigmas, rgbs, deltas, weights_sum,
                                                                             depth, image);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- device-driven inference rounds (see k_infer_plan) --------------------------------------------------------------
+int nb200_infer_plan(int32_t *state, uint32_t N, uint32_t max_steps, void *stream) {
+    if (!state) return NB200_E_BAD_ARG;
+    k_infer_plan<<<1, 32, 0, nb_stream(stream)>>>(state, N, max_steps);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_march_rays_dev(const int32_t *state, uint32_t N, const int32_t *rays_alive, const float *rays_t,
+                         const float *rays_o, const float *rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                         uint32_t C, uint32_t H, const uint8_t *grid, const float *fars, float *xyzs, float *dirs,
+                         float *deltas, const float *noises, void *stream) {
+    if (N == 0) return 0;
+    if (!state) return NB200_E_BAD_ARG;
+    k_march_rays_dev<<<nb_div_up(N, 128), 128, 0, nb_stream(stream)>>>(state, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma,
+                                                                       max_steps, C, H, grid, fars, xyzs, dirs, deltas, noises);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_composite_rays_dev(const int32_t *state, uint32_t N, float T_thresh, int32_t *rays_alive, float *rays_t,
+                             const float *sigmas, const void *rgba, const float *deltas, float *weights_sum, float *depth,
+                             float *image, void *stream) {
+    if (N == 0) return 0;
+    if (!state) return NB200_E_BAD_ARG;
+    k_composite_rays_dev<__half><<<nb_div_up(N, 128), 128, 0, nb_stream(stream)>>>(state, T_thresh, rays_alive, rays_t, sigmas,
+                                                                                  (const __half *)rgba, deltas, weights_sum,
+                                                                                  depth, image);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_compact_alive(int32_t *state, uint32_t N, int32_t *rays_alive, int32_t *tmp, void *stream) {
+    if (N == 0) return 0;
+    if (!state || !rays_alive || !tmp) return NB200_E_BAD_ARG;
+    k_compact_alive<<<1, 1024, 0, nb_stream(stream)>>>(state, rays_alive, tmp);
+    NB_LAUNCH_CHECK();
+    k_copy_alive<<<nb_div_up(N, 256), 256, 0, nb_stream(stream)>>>(state, tmp, rays_alive);
     NB_LAUNCH_CHECK();
     return 0;
 }

@@ -78,6 +78,10 @@ class NeRFNetwork(NeRFRenderer):
         # the per-layer library path (mlp.Network.forward) stays available through use_fused_field = False
         self.use_fused_field = self.pos_en_dim == 32
         self._packed = _PackedWeights()
+        # eval on the occupancy path: device-driven rounds in a CUDA graph (fused_infer.py) instead of the reference's
+        # host-driven n_step loop; set False to run the loop of NeRFRenderer.run_cuda
+        self.fast_inference = True
+        self._infer = None
 
     def background(self, d):
         return torch.zeros(d.size(), dtype=d.dtype, device=d.device)
@@ -112,6 +116,29 @@ class NeRFNetwork(NeRFRenderer):
         fea = self.network(x_en)
         sigma = self.density_network(fea)
         return {'sigma': trunc_exp(sigma.squeeze(-1) + self.gaussian(x))}
+
+    def run_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024,
+                 T_thresh=1e-4, **kwargs):
+        if self.training or not (self.fast_inference and self.use_fused_field and torch.is_autocast_enabled()):
+            return super().run_cuda(rays_o, rays_d, dt_gamma=dt_gamma, bg_color=bg_color, perturb=perturb,
+                                    force_all_rays=force_all_rays, max_steps=max_steps, T_thresh=T_thresh, **kwargs)
+        from ..fused_infer import FusedInference
+        prefix = rays_o.shape[:-1]
+        N = rays_o.reshape(-1, 3).shape[0]
+        inf = self._infer
+        if (inf is None or inf.N != N or inf.T_thresh != float(T_thresh) or inf.dt_gamma != float(dt_gamma)
+                or inf.max_steps != int(max_steps)):
+            inf = self._infer = FusedInference(self, N, T_thresh=T_thresh, dt_gamma=dt_gamma, max_steps=max_steps)
+        weights_sum, depth, image, nears, fars = inf.render(rays_o.cuda().float(), rays_d.cuda().float(), perturb=perturb)
+        weights_sum, depth, image = weights_sum.clone(), depth.clone(), image.clone()
+        bgc = self._flag('bg_color')
+        if bgc:
+            bg = torch.tensor([list(bgc)], dtype=torch.float32, device=image.device)
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg
+        elif bg_color is not None:
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        return {'image': image.view(*prefix, 3), 'depth': depth.view(*prefix), 'weights_sum': weights_sum.reshape(*prefix),
+                'mask': (nears < fars).reshape(*prefix)}
 
     def get_params(self, lr):
         return [

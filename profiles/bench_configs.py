@@ -51,10 +51,13 @@ def c2_inference():
     o, d = o.to(dev), d.to(dev)
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         ms = timeit(lambda: model.render(o[None], d[None], perturb=False), 5, warm=1)
+        model.fast_inference = False
+        ms_loop = timeit(lambda: model.render(o[None], d[None], perturb=False), 3, warm=1)
+        model.fast_inference = True
         model.train()
         t0 = time.perf_counter(); model.update_extra_state(); torch.cuda.synchronize(); upd = (time.perf_counter() - t0) * 1e3
     return {"config": "configs[2] inference 248x184 (45632 rays), n_step loop; occupancy update of 2x128^3 cells",
-            "ms_per_frame": ms, "rays_per_s": o.shape[0] / ms * 1e3, "update_extra_state_ms": upd}
+            "ms_per_frame": ms, "rays_per_s": o.shape[0] / ms * 1e3, "ms_per_frame_host_loop": ms_loop, "update_extra_state_ms": upd}
 
 
 def c4_scale(n_rays=1 << 20, log2_T=22):

@@ -196,3 +196,25 @@ def test_lgie_composites_on_cuda_path_match_dense_formulas(soft):
     bgs = (msk[:, 0] < 0.5)
     assert float(sig.grad[bgs].abs().max()) == 0.0 and float(rgb.grad[bgs].abs().max()) == 0.0
     assert float(sig.grad[~bgs].abs().max()) > 0.0
+
+
+def test_device_driven_inference_matches_the_host_loop(scene):
+    """FusedInference (device-side round state, CUDA-graph rounds) against the reference-shaped host loop of
+    NeRFRenderer.run_cuda: per ray the same samples are composited in the same order, so the frames must be identical."""
+    opt = torch_ref.default_opt(cuda_ray=True, train_conf=0)
+    net, _ = _pair(opt, scene)
+    net.eval()
+    sel = slice(3000, 3000 + 4096)
+    o, d = torch.from_numpy(scene["rays_o"][sel]).cuda(), torch.from_numpy(scene["rays_d"][sel]).cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        net.fast_inference = False
+        slow = net.render(o[None], d[None], perturb=False)
+        net.fast_inference = True
+        fast = net.render(o[None], d[None], perturb=False)
+        again = net.render(o[None], d[None], perturb=False)           # graph replay on a re-used instance
+    assert net._infer is not None and net._infer.rounds >= 8
+    assert float(slow["weights_sum"].sum()) > 100
+    for k in ("image", "depth", "weights_sum"):
+        assert torch.equal(fast[k], slow[k]), k
+        assert torch.equal(again[k], slow[k]), k
+    assert torch.equal(fast["mask"], slow["mask"])
