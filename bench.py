@@ -193,6 +193,36 @@ BYTES_PER_SAMPLE = {
 BYTES_PER_PARAM = {"adam": 32.0}            # p, g, m, v read; p, m, v, g written (16 + 16)
 
 
+def l2_probe(dev):
+    """L2 read bandwidth of this GPU measured in place (MEASURED_PEAKS.json has no L2 figure): a coalesced
+    stream over a 32 MB buffer, and random 8-byte gathers over a 4 MB (2^19 x 8 B: one hashed level) and a 32 MB region."""
+    import ctypes as C
+    import torch
+    from customnerf_b200 import _lib as L
+    lib = L.lib()
+    buf = torch.zeros(32 << 20, dtype=torch.uint8, device=dev)
+    sink = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def t(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps * 1e-3
+    reps = 20
+    s_stream = t(lambda: L.check(lib.nb200_l2_stream_probe(L.ptr(buf), C.c_uint64(32 << 20), L.u32(reps), L.ptr(sink), L.stream()), "l2s"))
+    out = {"stream_32MB_gbs": round((32 << 20) * reps / s_stream / 1e9, 1)}
+    nthr, per = 148 * 2048, 64
+    for name, words in (("gather_4MB", 1 << 19), ("gather_32MB", 1 << 22)):
+        s_g = t(lambda: L.check(lib.nb200_l2_gather_probe(L.ptr(buf), L.u32(words), L.u32(nthr), L.u32(per), L.ptr(sink), L.stream()), "l2g"))
+        out[name + "_gsectors_per_s"] = round(nthr * per / s_g / 1e9, 2)
+        out[name + "_sector_gbs"] = round(nthr * per * 32 / s_g / 1e9, 1)
+    out["how"] = "ld.global.cg (L1 bypassed); stream: float4 per thread; gather: 8-byte words at LCG-hashed positions, 32-byte sectors"
+    return out
+
+
 def rooflines(stage_us, samples, n_params, peaks):
     """achieved algorithmic GB/s of every bandwidth-bound stage, and the dominant one as the headline roofline"""
     peak = peaks.get("hbm_gbs", 6650.0)
@@ -316,6 +346,15 @@ def run_b200(args):
             fs.use_graph = not args.no_graph
             line["kernel_us"] = {k: round(v, 2) for k, v in stage_us.items()}
             line["roofline"], line["stage_rooflines"] = rooflines(stage_us, samples, fs.params_flat.numel(), peaks)
+            try:
+                l2 = l2_probe(dev)
+                # the encoder against the L2: 128 corner gathers per sample (forward), 128 reductions (backward)
+                l2["grid_encode_forward_gsectors_per_s"] = round(samples * 128 / (stage_us["grid_encode_forward"] * 1e-6) / 1e9, 2)
+                l2["grid_encode_forward_frac_of_gather_32MB"] = round(l2["grid_encode_forward_gsectors_per_s"] / l2["gather_32MB_gsectors_per_s"], 3)
+                l2["grid_encode_backward_gatomics_per_s"] = round(samples * 128 / (stage_us["grid_encode_backward"] * 1e-6) / 1e9, 2)
+                line["l2_probe"] = l2
+            except Exception as e:
+                line["l2_probe"] = {"error": repr(e)}
             if not args.no_cpu:
                 n_cpu = 2048
                 line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(3, 1, n_cpu).items() if k != "ms_per_step"}

@@ -151,3 +151,49 @@ int nb200_mse_loss_grad(const float *image, const float *target, uint32_t N, flo
 }
 
 }  // extern "C"
+
+// ---- L2 bandwidth probes (measurement aid: MEASURED_PEAKS.json has no L2 figure) -------------------
+namespace {
+// every thread streams float4s of a small (L2-resident) buffer `reps` times
+__global__ void __launch_bounds__(256)
+k_l2_stream(const float4 *__restrict__ buf, uint64_t n4, uint32_t reps, float *__restrict__ sink) {
+    float acc = 0.0f;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint32_t r = 0; r < reps; r++)
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            const float4 v = __ldcg(buf + i);           // .cg: L2 only, the L1 never serves these
+            acc += v.x + v.y + v.z + v.w;
+        }
+    if (acc == 123456.789f) *sink = acc;                // keep the loads alive
+}
+// every thread gathers 8-byte words at hashed positions (one 32-byte sector per request, like a hashed grid level)
+__global__ void __launch_bounds__(256)
+k_l2_gather(const float2 *__restrict__ buf, uint32_t mask, uint32_t per_thread, float *__restrict__ sink) {
+    float acc = 0.0f;
+    uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+#pragma unroll 8
+    for (uint32_t j = 0; j < per_thread; j++) {
+        h = h * 1664525u + 1013904223u;
+        const float2 v = __ldcg(buf + ((h >> 7) & mask));
+        acc += v.x + v.y;
+    }
+    if (acc == 123456.789f) *sink = acc;
+}
+}  // namespace
+
+extern "C" {
+// streams `bytes` (16-byte aligned, should fit the L2) `reps` times; returns after enqueueing.  bytes_moved = bytes * reps
+int nb200_l2_stream_probe(const void *buf, uint64_t bytes, uint32_t reps, float *sink, void *stream) {
+    if (!buf || !sink || (bytes & 15u)) return NB200_E_BAD_ARG;
+    k_l2_stream<<<148 * 8, 256, 0, nb_stream(stream)>>>((const float4 *)buf, bytes / 16, reps, sink);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+// n_threads x per_thread random 8-byte gathers over the first `words` (power of two) float2 words of buf
+int nb200_l2_gather_probe(const void *buf, uint32_t words, uint32_t n_threads, uint32_t per_thread, float *sink, void *stream) {
+    if (!buf || !sink || (words & (words - 1)) || n_threads == 0) return NB200_E_BAD_ARG;
+    k_l2_gather<<<nb_div_up(n_threads, 256), 256, 0, nb_stream(stream)>>>((const float2 *)buf, words - 1, per_thread, sink);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+}  // extern "C"

@@ -296,6 +296,12 @@ int nb200_train_forward_backward(const nb200_train_plan *plan, void *stream);
 /* fused Adam over params_flat (zeroing grads_flat) and re-pack of the MLP operand images. */
 int nb200_train_update(const nb200_train_plan *plan, void *stream);
 
+/* L2 bandwidth probes (measurement aid, no reference counterpart): MEASURED_PEAKS.json carries no L2 figure, so bench.py
+ * measures (a) a coalesced float4 stream over an L2-resident buffer and (b) random 8-byte gathers (one 32-byte sector
+ * each, the access pattern of a hashed grid level) and reports the encoder's rates next to them. */
+int nb200_l2_stream_probe(const void *buf, uint64_t bytes, uint32_t reps, float *sink, void *stream);
+int nb200_l2_gather_probe(const void *buf, uint32_t words, uint32_t n_threads, uint32_t per_thread, float *sink, void *stream);
+
 /* ============================================================================================
  * tensor-core path self test (no reference counterpart): one-CTA tcgen05 GEMM D[128,N] = A[128,K] * B[N,K]^T with
  * fp16 operands / fp32 accumulation, used by the tests to pin the UMMA descriptor conventions the fused MLP
