@@ -410,21 +410,20 @@ __device__ __noinline__ void bwd_epilogue_half(uint32_t taddr, const uint8_t *ac
     umma::tmem_ld_wait();
 #pragma unroll
     for (uint32_t c = 0; c < 4; c++) {
-        float v[8];
+        uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = __uint_as_float(a[c * 8 + j]);
+        for (int j = 0; j < 4; j++) pk[j] = pack_h2(__uint_as_float(a[c * 8 + 2 * j]), __uint_as_float(a[c * 8 + 2 * j + 1]));
         if (act_tile) {
+            // relu'(x) on packed halves: (act > 0) as a 0xffff / 0 lane mask ANDed onto the packed gradient
             const uint4 m = *reinterpret_cast<const uint4 *>(act_tile + umma::sw128_offset(row, half * 4 + c));
             const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+            const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                // fp16 activation after ReLU is > 0 iff its bit pattern is non-zero and not negative zero
-                if ((mw[j] & 0x7fffu) == 0) v[2 * j] = 0.0f;
-                if ((mw[j] & 0x7fff0000u) == 0) v[2 * j + 1] = 0.0f;
+                pk[j] &= __hgt2_mask(*reinterpret_cast<const __half2 *>(&mw[j]), zero);
             }
         }
-        const uint4 pk = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-        *reinterpret_cast<uint4 *>(dst_tile + umma::sw128_offset(row, half * 4 + c)) = pk;
+        *reinterpret_cast<uint4 *>(dst_tile + umma::sw128_offset(row, half * 4 + c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
 }
 
@@ -488,8 +487,9 @@ k_field_backward(const FieldBwdArgs p) {
     const uint32_t ntiles = (Mrows + 127) / 128;
     if (blockIdx.x >= ntiles) return;
 
+    // the weight image streams in asynchronously with the first tile's activations (part of cp.async group G1 below)
     for (uint32_t i = tid; i < B_BYTES / 16; i += kBwdThreads)
-        reinterpret_cast<uint4 *>(smem + SB_W)[i] = __ldg(reinterpret_cast<const uint4 *>(p.wimg) + i);
+        cp_async16(umma::smem_u32(smem + SB_W) + i * 16, p.wimg + (size_t)i * 16, true);
     // the T16 tile is only ever written in its first 4 chunks per row: clear the rest once
     for (uint32_t i = tid; i < 16384 / 16; i += kBwdThreads) reinterpret_cast<uint4 *>(smem + SB_T16)[i] = make_uint4(0, 0, 0, 0);
     if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemColsBwd);
