@@ -111,6 +111,14 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// ---- asynchronous global -> shared copies (LDGSTS): the activation tiles of the NEXT tile stream in behind the MMAs
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src, bool valid) {
+    const uint32_t sz = valid ? 16u : 0u;                   // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // K-major A/B descriptor of K-step ks (16 halves) inside a 64-wide swizzled tile
 __device__ __forceinline__ uint64_t kdesc(uint32_t tile_addr, uint32_t ks) {
     return umma::make_desc(tile_addr + ks * 32, 16, 1024, umma::kLayoutSW128);
@@ -126,13 +134,16 @@ __device__ __noinline__ void epilogue_row64(uint32_t tmem_row_addr, uint8_t *til
 #pragma unroll
     for (uint32_t c = 0; c < 8; c++) {
         uint32_t *src = (c < 4) ? (a + c * 8) : (b + (c - 4) * 8);
-        float v[8];
+        uint32_t q[4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            v[j] = __uint_as_float(src[j]);
-            if (kRelu) v[j] = fmaxf(v[j], 0.0f);
+        for (int j = 0; j < 4; j++) {
+            q[j] = pack_h2(__uint_as_float(src[2 * j]), __uint_as_float(src[2 * j + 1]));
+            if (kRelu) {        // ReLU on the packed pair (rounding is monotone and max(., 0) drops NaN: same result as before rounding)
+                const __half2 r2 = __hmax2(*reinterpret_cast<const __half2 *>(&q[j]), __float2half2_rn(0.0f));
+                q[j] = *reinterpret_cast<const uint32_t *>(&r2);
+            }
         }
-        const uint4 pk = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        const uint4 pk = make_uint4(q[0], q[1], q[2], q[3]);
         *reinterpret_cast<uint4 *>(tile + umma::sw128_offset(row, c)) = pk;
         if (gdst) *reinterpret_cast<uint4 *>(gdst + c * 8) = pk;
     }
@@ -179,9 +190,10 @@ k_field_forward(const FieldFwdArgs p, const __grid_constant__ CUtensorMap act_ma
     const uint32_t ntiles = (Mrows + 127) / 128;
     if (blockIdx.x >= ntiles) return;
 
-    // one-time: weights -> smem, TMEM, barrier
+    // one-time: weights -> smem (asynchronously, behind the first tile's input loads), TMEM, barrier
     for (uint32_t i = tid; i < F_BYTES / 16; i += 128)
-        reinterpret_cast<uint4 *>(smem + S_W)[i] = __ldg(reinterpret_cast<const uint4 *>(p.wimg) + i);
+        cp_async16(umma::smem_u32(smem + S_W) + i * 16, p.wimg + (size_t)i * 16, true);
+    cp_async_commit();
     if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemCols);
     if (tid == 0) {
         umma::mbar_init(&bar, 1);
@@ -260,6 +272,7 @@ k_field_forward(const FieldFwdArgs p, const __grid_constant__ CUtensorMap act_ma
     prefetch_inputs(blockIdx.x);
     write_xv(true);
     float px = npx, py = npy, pz = npz;                     // this tile's sample position (gaussian density bias)
+    cp_async_wait<0>();                                     // the weight image
     publish();
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -445,14 +458,6 @@ __device__ __noinline__ void bwd_flush16(uint32_t taddr, float *dst, bool on, bo
         }
     }
 }
-
-// ---- asynchronous global -> shared copies (LDGSTS): the activation tiles of the NEXT tile stream in behind the MMAs
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src, bool valid) {
-    const uint32_t sz = valid ? 16u : 0u;                   // src-size 0: the 16 bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // rows [row0, row0 + 128) of a row-major [M, 64] half plane -> swizzled tile; a warp's copy covers 4 complete lines
 __device__ __forceinline__ void load_tile_async(uint32_t tile_smem, const __half *plane, uint32_t row0, uint32_t Mrows,
