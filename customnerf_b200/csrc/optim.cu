@@ -16,12 +16,20 @@ struct AdamHyper {          // 8 floats per parameter group, written by the host
     float lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale, pad;
 };
 
-__device__ __forceinline__ void adam1(float &p, float &g, float &m, float &v, const AdamHyper &h) {
+// per-group constants hoisted out of the sweep (two of the three divisions of the update are per-step constants)
+struct AdamConst {
+    float grad_scale, w1, beta2, w2, inv_bc2_sqrt, eps, step_size;
+    __device__ __forceinline__ explicit AdamConst(const AdamHyper &h)
+        : grad_scale(h.grad_scale), w1(1.0f - h.beta1), beta2(h.beta2), w2(1.0f - h.beta2),
+          inv_bc2_sqrt(1.0f / h.bc2_sqrt), eps(h.eps), step_size(h.lr / h.bc1) {}
+};
+
+__device__ __forceinline__ void adam1(float &p, float &g, float &m, float &v, const AdamConst &h) {
     const float gr = g * h.grad_scale;
-    m = m + (1.0f - h.beta1) * (gr - m);                // torch lerp(m, g, w) for w < 0.5
-    v = h.beta2 * v + (1.0f - h.beta2) * gr * gr;
-    const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
-    p -= (h.lr / h.bc1) * m / denom;
+    m = m + h.w1 * (gr - m);                            // torch lerp(m, g, w) for w < 0.5
+    v = h.beta2 * v + h.w2 * gr * gr;
+    const float denom = sqrtf(v) * h.inv_bc2_sqrt + h.eps;
+    p -= h.step_size * m / denom;
 }
 
 // n4 = number of float4 groups; elements [0, split) use group 0, [split, n) group 1.  split % 4 == 0 is required
@@ -30,9 +38,9 @@ __global__ void __launch_bounds__(256)
 k_fused_adam(float4 *__restrict__ param, float4 *__restrict__ grad, float4 *__restrict__ exp_avg,
              float4 *__restrict__ exp_avg_sq, uint64_t n4, uint64_t split4, const AdamHyper *__restrict__ hyper,
              int zero_grad) {
-    const AdamHyper h0 = hyper[0], h1 = hyper[1];
+    const AdamConst h0(hyper[0]), h1(hyper[1]);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
-        const AdamHyper &h = i < split4 ? h0 : h1;
+        const AdamConst &h = i < split4 ? h0 : h1;
         // the moments are touched once per step: streaming loads / stores keep them from displacing the table and its
         // gradient (both L2-resident between the encode kernels and this sweep)
         float4 p = param[i], g = grad[i], m = __ldcs(exp_avg + i), v = __ldcs(exp_avg_sq + i);
@@ -49,7 +57,7 @@ k_fused_adam_tail(float *__restrict__ param, float *__restrict__ grad, float *__
                   const AdamHyper *__restrict__ hyper, int zero_grad) {
     const uint64_t i = begin + threadIdx.x;
     if (i >= n) return;
-    const AdamHyper h = hyper[i < split ? 0 : 1];
+    const AdamConst h(hyper[i < split ? 0 : 1]);
     float p = param[i], g = grad[i], m = exp_avg[i], v = exp_avg_sq[i];
     adam1(p, g, m, v, h);
     param[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
