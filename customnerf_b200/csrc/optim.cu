@@ -29,7 +29,7 @@ __device__ __forceinline__ void adam1(float &p, float &g, float &m, float &v, co
     m = m + h.w1 * (gr - m);                            // torch lerp(m, g, w) for w < 0.5
     v = h.beta2 * v + h.w2 * gr * gr;
     const float denom = sqrtf(v) * h.inv_bc2_sqrt + h.eps;
-    p -= h.step_size * m / denom;
+    p -= h.step_size * __fdividef(m, denom);          // 2-ulp division: the update is <= lr, its error ~1e-10
 }
 
 // n4 = number of float4 groups; elements [0, split) use group 0, [split, n) group 1.  split % 4 == 0 is required

@@ -243,7 +243,9 @@ int nb200_mse_loss_grad(const float *image, const float *target, uint32_t N, flo
 /* One pass of Adam over a flat fp32 parameter vector with two hyper-parameter groups (elements [0, split) and
  * [split, n)): gradient unscale, moment update, parameter update and (zero_grad) gradient reset, 32 B per parameter.
  * hyper: device f32 [2][8] = {lr, beta1, beta2, eps, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale, 0} per group.
- * Same arithmetic as torch.optim.Adam (main.py:182).  All pointers 16-byte aligned, split % 4 == 0. */
+ * The arithmetic of torch.optim.Adam (main.py:182); the last division m / denom is the 2-ulp fast form (the update is
+ * bounded by lr, so its error is ~1e-10 absolute; tests/test_gpu_fused_step.py bounds the drift against torch at 1e-6).
+ * All pointers 16-byte aligned, split % 4 == 0. */
 int nb200_fused_adam(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, uint64_t split,
                      const float *hyper, int zero_grad, void *stream);
 
