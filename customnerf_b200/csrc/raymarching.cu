@@ -435,7 +435,7 @@ __device__ __forceinline__ bool rm_may_hit(const RayCtx &r, const int32_t *__res
 // segment (<= 64 lattice points).
 constexpr int kSegWarps = 4;            // rays per block
 constexpr int kSegMax = 64;             // lattice indices per lane and round
-constexpr int kSegMin = 8;
+constexpr int kSegMin = 4;
 constexpr int kRecStride = kSegMax + 1; // +1: lanes write their own rows, keep them on different banks
 
 struct SegResult { uint32_t cnt, v1, land; float tland; bool occ_a; };
@@ -463,10 +463,12 @@ __device__ __forceinline__ SegResult rm_march_segment(const RayCtx &r, uint32_t 
     return o;
 }
 
-// kLanes lanes cooperate on one ray (32 / kLanes rays per warp).  Fewer lanes per ray = longer segments: the per-lane
-// work evens out (a warp issues for its slowest lane) and the per-round overheads are shared by more lattice points,
-// at the price of fewer warps to hide the chain latency; 8 measured best at ~15 k rays (profiles/).
-template <int kLanes>
+// kLanes lanes cooperate on one ray (32 / kLanes rays per warp), and every lane marches kChunks segments that lie a
+// quarter (1 / kChunks) of the window apart BEFORE the warp synchronises to thread the chain through them.  A warp
+// issues for its slowest lane: one contiguous segment per lane leaves the lanes inside the object marching several
+// times longer than the lanes in empty space (measured: 3-4x more probes issued than a balanced warp would need), while
+// the sum of segments spread over the ray evens out.
+template <int kLanes, int kChunks>
 __global__ void __launch_bounds__(kSegWarps * 32)
 k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
                   float bound, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
@@ -475,6 +477,7 @@ k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ ra
                   const int32_t *__restrict__ obounds, const float *__restrict__ aabb, float min_near) {
     __shared__ float rec_s[kSegWarps][32][kRecStride];
     constexpr uint32_t kFull = 0xffffffffu, kRaysPerWarp = 32 / kLanes, kGroupMask = kLanes == 32 ? kFull : ((1u << kLanes) - 1u);
+    constexpr int kSegCap = kSegMax / kChunks;                      // a lane's kChunks segments share its record row
     const uint32_t lane = nb_lane(), w = threadIdx.x >> 5;
     const uint32_t li = lane % kLanes, gshift = lane - li;          // index inside the ray's lane group, group's first lane
     const uint32_t n = (blockIdx.x * kSegWarps + w) * kRaysPerWarp + lane / kLanes;
@@ -498,84 +501,108 @@ k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ ra
         ended = !(t0 < far && rm_may_hit(r, obounds, C, H, t0, far));
     }
     const float kest = ended ? 0.0f : fminf(__fdividef(far - t0, dt) + 2.0f, 1.0e9f);
-    const uint32_t seg = (uint32_t)min(max((int)ceilf(kest * (1.0f / kLanes)), kSegMin), kSegMax);
+    const uint32_t seg = (uint32_t)min(max((int)ceilf(kest * (1.0f / (kLanes * kChunks))), kSegMin), kSegCap);
     uint32_t K0 = 0;            // first index of the window == the chain's entry into it (exact for the group's lane 0)
     float tK0 = t0;
     // groups of a warp finish at different times: the collectives below always run warp-wide, a finished group's lanes
     // contribute values nobody uses
     while (__any_sync(kFull, !ended)) {
-        uint32_t a = 0, b = 0;
-        SegResult sr;
-        sr.cnt = 0; sr.v1 = 0; sr.land = 0; sr.tland = 0.0f; sr.occ_a = false;
-        if (!ended) {
-            a = K0 + li * seg; b = a + seg;
-            const float ta = rm_lattice_jump(tK0, dt, li * seg);
-            sr = rm_march_segment(r, a, ta, b, far, rec);
+        // ---- march: chunk c of the window is lattice [K0 + c kLanes seg, K0 + (c + 1) kLanes seg), this lane's piece of
+        //      it starts li seg further; no warp-level synchronisation between a lane's pieces
+        uint32_t a[kChunks];
+        SegResult sr[kChunks];
+        {
+            uint32_t kprev = K0;
+            float tprev = tK0;
+#pragma unroll
+            for (int c = 0; c < kChunks; c++) {
+                a[c] = 0;
+                sr[c].cnt = 0; sr[c].v1 = 0; sr[c].land = 0; sr[c].tland = 0.0f; sr[c].occ_a = false;
+                if (!ended) {
+                    a[c] = K0 + ((uint32_t)c * kLanes + li) * seg;
+                    const float ta = rm_lattice_jump(tprev, dt, a[c] - kprev);
+                    sr[c] = rm_march_segment(r, a[c], ta, a[c] + seg, far, rec + c * seg);
+                    kprev = a[c]; tprev = ta;
+                }
+            }
         }
-        // ---- thread the true chain through the group's segments
-        uint32_t e = K0, drop = 0, valid = 0;
+        // ---- thread the true chain through the chunks, one after the other
+        uint32_t e = K0;
         float te = tK0;
         bool now_ended = false;
-        // common case, checked in parallel: every segment up to the one where the ray ends is entered at its own first
-        // index or at the first point its lane moved to, i.e. lane s-1 landed on a_s or on v1_s
-        const uint32_t pl = __shfl_up_sync(kFull, sr.land, 1, kLanes);
-        const bool ok = li == 0 || pl == a || pl == sr.v1;
-        const uint32_t endm = (__ballot_sync(kFull, !(sr.tland < far)) >> gshift) & kGroupMask;
-        const uint32_t last = endm ? (uint32_t)__ffs((int)endm) - 1u : (uint32_t)kLanes - 1u;      // segment in which the chain ends
-        const uint32_t upto = last == 31u ? kFull : ((2u << last) - 1u);
-        const uint32_t bad = (__ballot_sync(kFull, !ok) >> gshift) & kGroupMask & upto;
-        {
-            const uint32_t land_l = __shfl_sync(kFull, sr.land, last, kLanes);
-            const float tland_l = __shfl_sync(kFull, sr.tland, last, kLanes);
+#pragma unroll
+        for (int c = 0; c < kChunks; c++) {
+            const bool live = !ended && !now_ended;         // this group still follows the chain into chunk c
+            uint32_t drop = 0, valid = 0;
+            // common case, checked in parallel: every segment up to the one where the ray ends is entered at its own
+            // first index or at the first point its lane moved to, i.e. the previous segment landed on a_s or on v1_s
+            uint32_t pl = __shfl_up_sync(kFull, sr[c].land, 1, kLanes);
+            if (li == 0) pl = e;
+            const bool ok = pl == a[c] || pl == sr[c].v1;
+            const uint32_t endm = (__ballot_sync(kFull, !(sr[c].tland < far)) >> gshift) & kGroupMask;
+            const uint32_t last = endm ? (uint32_t)__ffs((int)endm) - 1u : (uint32_t)kLanes - 1u;      // segment in which the chain ends
+            const uint32_t upto = last == 31u ? kFull : ((2u << last) - 1u);
+            const uint32_t bad = (__ballot_sync(kFull, !ok) >> gshift) & kGroupMask & upto;
+            const uint32_t land_l = __shfl_sync(kFull, sr[c].land, last, kLanes);
+            const float tland_l = __shfl_sync(kFull, sr[c].tland, last, kLanes);
+            uint32_t e2 = e;
+            float te2 = te;
+            bool end2 = false;
             if (bad == 0) {
                 if (li <= last) {
-                    drop = (li != 0 && pl != a && sr.occ_a) ? 1u : 0u;
-                    valid = sr.cnt - drop;
+                    drop = (pl != a[c] && sr[c].occ_a) ? 1u : 0u;
+                    valid = sr[c].cnt - drop;
                 }
-                e = land_l; te = tland_l;
-                now_ended = endm != 0;
+                e2 = land_l; te2 = tland_l;
+                end2 = endm != 0;
             }
-        }
-        if (__any_sync(kFull, bad != 0 && !ended)) {        // rare: some group must be threaded sequentially
-            const bool mine = bad != 0 && !ended;
-            bool stop = !mine;
-            for (uint32_t sgm = 0; sgm < (uint32_t)kLanes; sgm++) {
-                const uint32_t as = K0 + sgm * seg, bs = as + seg;
-                const uint32_t v1s = __shfl_sync(kFull, sr.v1, sgm, kLanes);
-                const bool occs = __shfl_sync(kFull, (int)sr.occ_a, sgm, kLanes) != 0;
-                const bool visit = !stop && e < bs;                     // (else the chain jumps over this segment)
-                uint32_t dr = 0;
-                if (visit && e != as) {
-                    if (e == v1s) dr = occs ? 1u : 0u;
-                    else if (li == sgm) sr = rm_march_segment(r, e, te, b, far, rec);   // mis-speculation: re-march
-                }
-                if (visit && li == sgm) { drop = dr; valid = sr.cnt - dr; }
-                const uint32_t land_s = __shfl_sync(kFull, sr.land, sgm, kLanes);
-                const float tland_s = __shfl_sync(kFull, sr.tland, sgm, kLanes);
-                if (visit) {
-                    e = land_s; te = tland_s;
-                    if (!(te < far)) { now_ended = true; stop = true; }
+            if (__any_sync(kFull, bad != 0 && live)) {        // rare: some group must be threaded sequentially
+                const bool mine = bad != 0 && live;
+                bool stop = !mine;
+                for (uint32_t sgm = 0; sgm < (uint32_t)kLanes; sgm++) {
+                    const uint32_t as = K0 + ((uint32_t)c * kLanes + sgm) * seg, bs = as + seg;
+                    const uint32_t v1s = __shfl_sync(kFull, sr[c].v1, sgm, kLanes);
+                    const bool occs = __shfl_sync(kFull, (int)sr[c].occ_a, sgm, kLanes) != 0;
+                    const bool visit = !stop && e2 < bs;                    // (else the chain jumps over this segment)
+                    uint32_t dr = 0;
+                    if (visit && e2 != as) {
+                        if (e2 == v1s) dr = occs ? 1u : 0u;
+                        else if (li == sgm) sr[c] = rm_march_segment(r, e2, te2, bs, far, rec + c * seg);   // mis-speculation: re-march
+                    }
+                    if (visit && li == sgm) { drop = dr; valid = sr[c].cnt - dr; }
+                    const uint32_t land_s = __shfl_sync(kFull, sr[c].land, sgm, kLanes);
+                    const float tland_s = __shfl_sync(kFull, sr[c].tland, sgm, kLanes);
+                    if (visit) {
+                        e2 = land_s; te2 = tland_s;
+                        if (!(te2 < far)) { end2 = true; stop = true; }
+                    }
                 }
             }
-        }
-        // ---- compact this round's samples behind the ray's earlier ones (max_steps caps the ray, :359)
-        uint32_t incl = valid;
+            if (!live) { valid = 0; drop = 0; }
+            // ---- compact this chunk's samples behind the ray's earlier ones (max_steps caps the ray, :359)
+            uint32_t incl = valid;
 #pragma unroll
-        for (int o = 1; o < kLanes; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, incl, o, kLanes);
-            if ((int)li >= o) incl += t;
-        }
-        const uint32_t round_total = __shfl_sync(kFull, incl, kLanes - 1, kLanes);
-        if (!ended) {
-            const uint32_t first = total + incl - valid;
-            if (out) {
-                for (uint32_t i = 0; i < valid; i++) {
-                    const uint32_t idx = first + i;
-                    if (idx < max_steps && idx < tcap) out[idx] = rec[drop + i];
-                }
+            for (int o = 1; o < kLanes; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, incl, o, kLanes);
+                if ((int)li >= o) incl += t;
             }
-            total += round_total;
-            if (total >= max_steps) { total = max_steps; now_ended = true; }
+            const uint32_t chunk_total = __shfl_sync(kFull, incl, kLanes - 1, kLanes);
+            if (live) {
+                const uint32_t first = total + incl - valid;
+                if (out) {
+                    const float *src = rec + c * seg + drop;
+                    for (uint32_t i = 0; i < valid; i++) {
+                        const uint32_t idx = first + i;
+                        if (idx < max_steps && idx < tcap) out[idx] = src[i];
+                    }
+                }
+                total += chunk_total;
+                e = e2; te = te2;
+                if (end2) now_ended = true;
+                if (total >= max_steps) { total = max_steps; now_ended = true; }
+            }
+        }
+        if (!ended) {
             K0 = e; tK0 = te;
             ended = now_ended;
         }
@@ -1179,12 +1206,17 @@ static int march_count_impl(const float *rays_o, const float *rays_d, const uint
         uint32_t lanes = (lanes_env == 4 || lanes_env == 8 || lanes_env == 16 || lanes_env == 32) ? (uint32_t)lanes_env : 8u;
         while (lanes < 32 && (uint64_t)N * lanes < 148ull * 4 * 32 * 4) lanes <<= 1;     // few rays: keep >= ~4 warps per scheduler
         const uint32_t rays_per_block = kSegWarps * 32 / lanes, nbk = nb_div_up(N, rays_per_block);
-#define NB_SEG_LAUNCH(L) k_march_count_seg<L><<<nbk, kSegWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, max_steps, N, C, H, \
+        static int chunks_env = -1;
+        if (chunks_env < 0) { const char *e = getenv("NB200_MARCH_CHUNKS"); chunks_env = e ? atoi(e) : 0; }
+        const int chunks = (chunks_env == 1 || chunks_env == 2 || chunks_env == 4) ? chunks_env : 2;   // 2 measured best (profiles/)
+#define NB_SEG_LAUNCH(L, R) k_march_count_seg<L, R><<<nbk, kSegWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, max_steps, N, C, H, \
         nears, fars, noises, scratch, march_trec(scratch, N), march_tcap(N), obounds, aabb, min_near)
-        if (lanes == 4) NB_SEG_LAUNCH(4);
-        else if (lanes == 8) NB_SEG_LAUNCH(8);
-        else if (lanes == 16) NB_SEG_LAUNCH(16);
-        else NB_SEG_LAUNCH(32);
+#define NB_SEG_LANES(R) do { if (lanes == 8) NB_SEG_LAUNCH(8, R); else if (lanes == 16) NB_SEG_LAUNCH(16, R); else NB_SEG_LAUNCH(32, R); } while (0)
+        if (lanes == 4) lanes = 8;
+        if (chunks == 1) NB_SEG_LANES(1);
+        else if (chunks == 2) NB_SEG_LANES(2);
+        else NB_SEG_LANES(4);
+#undef NB_SEG_LANES
 #undef NB_SEG_LAUNCH
         NB_LAUNCH_CHECK();
         k_march_scan_rays<<<1, 1024, 0, st>>>(scratch, rays, N, counter, M_cap, m_eff);
