@@ -51,12 +51,7 @@ class ClockSampler:
         self.sm, self.mx, self.reasons, self.nvml = [], None, set(), None
 
     def _poll(self):
-        n = self.nvml
-        h = n.nvmlDeviceGetHandleByIndex(self.index)
-        try:
-            self.mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
-        except Exception:
-            self.mx = None
+        n, h = self.nvml, self.handle
         names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
         while not self.stop_flag:
             try:
@@ -70,14 +65,19 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def start(self):
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nvml = pynvml
-            # CUDA_VISIBLE_DEVICES may renumber devices: map through the UUID-free simple case (same order)
+            # handle and max clock are fetched here (blocking, before the timed region) so the thread only polls
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            try:
+                self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            except Exception:
+                self.mx = None
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
             return

@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(kSegWarps * 32)
 k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ grid,
                   float bound, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                   float *__restrict__ nears, float *__restrict__ fars, const float *__restrict__ noises,
-                  int32_t *__restrict__ counts, float *__restrict__ trec, uint32_t tcap,
+                  int32_t *__restrict__ counts, int32_t *__restrict__ group_sums, float *__restrict__ trec, uint32_t tcap,
                   const int32_t *__restrict__ obounds, const float *__restrict__ aabb, float min_near) {
     __shared__ float rec_s[kSegWarps][32][kRecStride];
     constexpr uint32_t kFull = 0xffffffffu, kRaysPerWarp = 32 / kLanes, kGroupMask = kLanes == 32 ? kFull : ((1u << kLanes) - 1u);
@@ -607,51 +607,23 @@ k_march_count_seg(const float *__restrict__ rays_o, const float *__restrict__ ra
             ended = now_ended;
         }
     }
-    if (li == 0 && n < N) counts[n] = (int32_t)total;
+    if (li == 0 && n < N) {
+        counts[n] = (int32_t)total;
+        if (total) atomicAdd(group_sums + (n >> 5), (int32_t)total);        // 32-ray groups: scanned by k_march_scan
+    }
 }
 
-// single block: rays[n] = (n, exclusive prefix of the per-ray counts starting at counter[0], count); counter += (sum, N)
-// (:405-413 with scan-ordered instead of atomically reserved offsets).  Each thread owns 8 consecutive rays per trip.
-__global__ void __launch_bounds__(1024)
-k_march_scan_rays(const int32_t *__restrict__ counts, int32_t *__restrict__ rays, uint32_t N, int32_t *__restrict__ counter,
-                  uint32_t M_cap, int32_t *__restrict__ m_eff) {
-    __shared__ int warp_tot[32];
-    __shared__ int carry_s, chunk_total_s;
-    if (threadIdx.x == 0) carry_s = counter[0];
-    __syncthreads();
-    for (uint32_t base = 0; base < N; base += 8192) {
-        const uint32_t i0 = base + threadIdx.x * 8;
-        int c[8], v = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) { c[j] = (i0 + j < N) ? counts[i0 + j] : 0; v += c[j]; }
-        const int incl = nb_warp_incl_scan(v);
-        if (nb_lane() == 31) warp_tot[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const int wt = warp_tot[threadIdx.x];
-            const int wi = nb_warp_incl_scan(wt);
-            warp_tot[threadIdx.x] = wi - wt;            // exclusive warp offsets
-            if (threadIdx.x == 31) chunk_total_s = wi;
-        }
-        __syncthreads();
-        int off = carry_s + warp_tot[threadIdx.x >> 5] + incl - v;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint32_t n = i0 + j;
-            if (n < N) { rays[n * 3] = (int32_t)n; rays[n * 3 + 1] = off; rays[n * 3 + 2] = c[j]; }
-            off += c[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s += chunk_total_s;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        counter[0] = carry_s;
-        counter[1] += (int32_t)N;
-        // rows the downstream kernels of the fused step may touch: every segment below this row is complete
-        // (k_march_expand lowers it to the offset of the first ray that does not fit in M_cap rows)
-        if (m_eff) *m_eff = (int32_t)min((uint32_t)max(carry_s, 0), M_cap);
-    }
+// rays[n] = (n, prefix of its 32-ray group + exclusive prefix inside the group, count): one thread per ray, coalesced
+__global__ void __launch_bounds__(256)
+k_march_finalize(const int32_t *__restrict__ counts, const int32_t *__restrict__ group_prefix, int32_t *__restrict__ rays,
+                 uint32_t N) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    const int c = n < N ? counts[n] : 0;
+    const int incl = nb_warp_incl_scan(c);
+    if (n >= N) return;
+    rays[n * 3] = (int32_t)n;
+    rays[n * 3 + 1] = group_prefix[n >> 5] + incl - c;
+    rays[n * 3 + 2] = c;
 }
 
 // single block: exclusive scan of the block sums starting at counter[0]; counter += (sum, N)  (:405-406)
@@ -1169,7 +1141,9 @@ int nb200_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t 
 // [occupied bounds: 8 levels x 6 + 16 spare][sample records: N * tcap floats], nb4 = ceil(N / 4)
 constexpr uint32_t kScratchFixed = 64;
 static inline uint32_t march_nb_max(uint32_t N) { return nb_div_up(N, 4); }
-static inline uint32_t march_hdr(uint32_t N) { return N + 8; }      // per-ray counts (or 2 x nb4 block sums / prefixes)
+// per-ray counts [N + 8] then 32-ray group sums and prefixes [2 x (N / 32 + 8)]  (serial kernel: 2 x nb4 block sums / prefixes)
+static inline uint32_t march_groups(uint32_t N) { return nb_div_up(N, 32) + 8; }
+static inline uint32_t march_hdr(uint32_t N) { return N + 8 + 2 * march_groups(N); }
 uint32_t nb200_march_scratch_ints(uint32_t N) { return march_hdr(N) + kScratchFixed + N * march_tcap(N); }
 static inline int32_t *march_obounds(int32_t *scratch, uint32_t N) { return scratch + march_hdr(N); }
 static inline float *march_trec(int32_t *scratch, uint32_t N) {
@@ -1206,11 +1180,16 @@ static int march_count_impl(const float *rays_o, const float *rays_d, const uint
         uint32_t lanes = (lanes_env == 4 || lanes_env == 8 || lanes_env == 16 || lanes_env == 32) ? (uint32_t)lanes_env : 8u;
         while (lanes < 32 && (uint64_t)N * lanes < 148ull * 4 * 32 * 4) lanes <<= 1;     // few rays: keep >= ~4 warps per scheduler
         const uint32_t rays_per_block = kSegWarps * 32 / lanes, nbk = nb_div_up(N, rays_per_block);
+        int32_t *gsum = scratch + N + 8, *gprefix = gsum + march_groups(N);
+        {
+            cudaError_t e = cudaMemsetAsync(gsum, 0, (size_t)march_groups(N) * sizeof(int32_t), st);
+            if (e != cudaSuccess) return (int)e;
+        }
         static int chunks_env = -1;
         if (chunks_env < 0) { const char *e = getenv("NB200_MARCH_CHUNKS"); chunks_env = e ? atoi(e) : 0; }
         const int chunks = (chunks_env == 1 || chunks_env == 2 || chunks_env == 4) ? chunks_env : 2;   // 2 measured best (profiles/)
 #define NB_SEG_LAUNCH(L, R) k_march_count_seg<L, R><<<nbk, kSegWarps * 32, 0, st>>>(rays_o, rays_d, grid, bound, max_steps, N, C, H, \
-        nears, fars, noises, scratch, march_trec(scratch, N), march_tcap(N), obounds, aabb, min_near)
+        nears, fars, noises, scratch, gsum, march_trec(scratch, N), march_tcap(N), obounds, aabb, min_near)
 #define NB_SEG_LANES(R) do { if (lanes == 8) NB_SEG_LAUNCH(8, R); else if (lanes == 16) NB_SEG_LAUNCH(16, R); else NB_SEG_LAUNCH(32, R); } while (0)
         if (lanes == 4) lanes = 8;
         if (chunks == 1) NB_SEG_LANES(1);
@@ -1219,7 +1198,9 @@ static int march_count_impl(const float *rays_o, const float *rays_d, const uint
 #undef NB_SEG_LANES
 #undef NB_SEG_LAUNCH
         NB_LAUNCH_CHECK();
-        k_march_scan_rays<<<1, 1024, 0, st>>>(scratch, rays, N, counter, M_cap, m_eff);
+        k_march_scan<<<1, 1024, 0, st>>>(gsum, gprefix, nb_div_up(N, 32), N, counter, M_cap, m_eff);
+        NB_LAUNCH_CHECK();
+        k_march_finalize<<<nb_div_up(N, 256), 256, 0, st>>>(scratch, gprefix, rays, N);
         NB_LAUNCH_CHECK();
         return 0;
     }
