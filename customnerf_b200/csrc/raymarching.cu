@@ -1055,42 +1055,33 @@ k_composite_rays_dev(const int32_t *__restrict__ state, float T_thresh, int32_t 
     image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
 }
 
-// ordered compaction rays_alive[rays_alive >= 0] (:685) by one block; state: n_alive = survivors, step += n_step
-__global__ void __launch_bounds__(1024)
+// compaction rays_alive[rays_alive >= 0] (:685), all SMs: warp ballots + one atomic per warp.  The survivors' ORDER is
+// not the reference's (it is whatever order the warps' atomics land in) -- it only decides which slot of the next
+// round's sample buffers a ray uses, never what is accumulated for the ray.  state[4] counts the survivors.
+__global__ void __launch_bounds__(256)
 k_compact_alive(int32_t *__restrict__ state, const int32_t *__restrict__ alive_in, int32_t *__restrict__ alive_out) {
-    __shared__ int warp_tot[32];
-    __shared__ int carry_s, chunk_total_s;
     const uint32_t n_alive = (uint32_t)state[0];
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n_alive; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const int32_t v = (i < n_alive) ? alive_in[i] : -1;
-        const int keep = v >= 0 ? 1 : 0;
-        const int incl = nb_warp_incl_scan(keep);
-        if (nb_lane() == 31) warp_tot[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const int wt = warp_tot[threadIdx.x];
-            const int wi = nb_warp_incl_scan(wt);
-            warp_tot[threadIdx.x] = wi - wt;
-            if (threadIdx.x == 31) chunk_total_s = wi;
-        }
-        __syncthreads();
-        if (keep) alive_out[carry_s + warp_tot[threadIdx.x >> 5] + incl - 1] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s += chunk_total_s;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        state[2] += state[1];
-        state[0] = carry_s;
-    }
+    const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
+    const int32_t v = (i < n_alive) ? alive_in[i] : -1;
+    const bool keep = v >= 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (m == 0) return;
+    int base = 0;
+    if (nb_lane() == 0) base = atomicAdd(state + 4, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) alive_out[base + __popc(m & ((1u << nb_lane()) - 1u))] = v;
 }
 
 __global__ void k_copy_alive(const int32_t *__restrict__ state, const int32_t *__restrict__ src, int32_t *__restrict__ dst) {
     const uint32_t i = threadIdx.x + blockIdx.x * blockDim.x;
-    if (i < (uint32_t)state[0]) dst[i] = src[i];
+    if (i < (uint32_t)state[4]) dst[i] = src[i];
+}
+
+__global__ void k_infer_commit(int32_t *__restrict__ state) {        // n_alive = survivors, step += n_step
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    state[0] = state[4];
+    state[2] += state[1];
+    state[4] = 0;
 }
 
 }  // namespace
@@ -1387,9 +1378,11 @@ int nb200_composite_rays_dev(const int32_t *state, uint32_t N, float T_thresh, i
 int nb200_compact_alive(int32_t *state, uint32_t N, int32_t *rays_alive, int32_t *tmp, void *stream) {
     if (N == 0) return 0;
     if (!state || !rays_alive || !tmp) return NB200_E_BAD_ARG;
-    k_compact_alive<<<1, 1024, 0, nb_stream(stream)>>>(state, rays_alive, tmp);
+    k_compact_alive<<<nb_div_up(N, 256), 256, 0, nb_stream(stream)>>>(state, rays_alive, tmp);
     NB_LAUNCH_CHECK();
     k_copy_alive<<<nb_div_up(N, 256), 256, 0, nb_stream(stream)>>>(state, tmp, rays_alive);
+    NB_LAUNCH_CHECK();
+    k_infer_commit<<<1, 32, 0, nb_stream(stream)>>>(state);
     NB_LAUNCH_CHECK();
     return 0;
 }

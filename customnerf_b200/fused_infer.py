@@ -43,8 +43,8 @@ class FusedInference:
         self.xyzs, self.dirs, self.deltas = torch.zeros(M, 3, **f32), torch.zeros(M, 3, **f32), torch.zeros(M, 2, **f32)
         self.x_en, self.rgba, self.sigma = torch.zeros(M, 32, **f16), torch.zeros(M, 4, **f16), torch.zeros(M, **f32)
         self.weights_sum, self.depth, self.image = torch.zeros(N, **f32), torch.zeros(N, **f32), torch.zeros(N, 3, **f32)
-        self.state = torch.zeros(4, **i32)
-        self.state_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.state = torch.zeros(8, **i32)
+        self.state_host = torch.zeros(8, dtype=torch.int32).pin_memory()
         nb = int(self.lib.nb200_field_weight_image_bytes())
         self.w_fwd = torch.empty(nb, dtype=torch.uint8, device=dev)
         self.w_bwd = torch.empty(nb, dtype=torch.uint8, device=dev)
@@ -74,7 +74,7 @@ class FusedInference:
                                             p(self.rays_t), p(self.sigma), p(self.rgba), p(self.deltas), p(self.weights_sum),
                                             p(self.depth), p(self.image), st), "composite_rays_dev")
         _check(lib.nb200_compact_alive(p(self.state), L.u32(self.N), p(self.rays_alive), p(self.tmp), st), "compact_alive")
-        L.LAUNCHES += 7
+        L.LAUNCHES += 8
 
     def _capture(self):
         keep = [t.clone() for t in (self.state, self.rays_alive, self.rays_t, self.weights_sum, self.depth, self.image)]
@@ -108,7 +108,7 @@ class FusedInference:
             self.weights_sum.zero_(); self.depth.zero_(); self.image.zero_()
             self.rays_alive.copy_(torch.arange(self.N, dtype=torch.int32, device=self.dev))
             self.rays_t.copy_(self.nears)
-            self.state.copy_(torch.tensor([self.N, 0, 0, 0], dtype=torch.int32), non_blocking=True)
+            self.state.copy_(torch.tensor([self.N, 0, 0, 0, 0, 0, 0, 0], dtype=torch.int32), non_blocking=True)
             if perturb != self.use_noise:
                 self.use_noise, self.graph = bool(perturb), None
             if perturb:
@@ -120,7 +120,7 @@ class FusedInference:
                 for _ in range(self.rounds_per_check):
                     if self.use_graph:
                         self.graph.replay()
-                        L.LAUNCHES += 7
+                        L.LAUNCHES += 8
                     else:
                         self._round()
                 self.rounds += self.rounds_per_check

@@ -150,13 +150,14 @@ int nb200_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int3
                          float *image, void *stream);
 
 /* Device-driven inference rounds: the eval loop of nerf/renderer.py:651-688 without its per-round host read-back.
- * state (device i32[4]) = {n_alive, n_step, step, n_alive * n_step}.  One round:
+ * state (device i32[8]) = {n_alive, n_step, step, n_alive * n_step, survivor count of the running compaction, ...}.  One round:
  *   nb200_infer_plan          n_step = max(min(N / n_alive, 8), 1) (:676); n_alive = 0 once step >= max_steps (:667)
  *   nb200_march_rays_dev      nb200_march_rays for the state's n_alive / n_step (launched for N rays; unused sample
  *                             slots are zero-filled by the kernel; noises only applied while step == 0)
  *   nb200_fs_encode_forward + nb200_field_forward with count_dev = &state[3]
  *   nb200_composite_rays_dev  nb200_composite_rays reading the field kernel's rgba f16 [M,4] rows
- *   nb200_compact_alive       rays_alive = rays_alive[rays_alive >= 0] in order (:685); n_alive, step += n_step
+ *   nb200_compact_alive       rays_alive = rays_alive[rays_alive >= 0] (:685; survivors in arbitrary order, which only
+ *                             decides their buffer slots in the next round); n_alive, step += n_step
  * Every kernel is bounded by the state, so a round can be captured in a CUDA graph and replayed. */
 int nb200_infer_plan(int32_t *state, uint32_t N, uint32_t max_steps, void *stream);
 int nb200_march_rays_dev(const int32_t *state, uint32_t N, const int32_t *rays_alive, const float *rays_t,
