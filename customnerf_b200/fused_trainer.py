@@ -125,9 +125,13 @@ class FusedTrainStep:
 
         N = self.N
         f32 = dict(dtype=torch.float32, device=dev)
-        self.rays_o = torch.zeros(N, 3, **f32)
-        self.rays_d = torch.zeros(N, 3, **f32)
-        self.target = torch.zeros(N, 3, **f32)
+        # the batch lives in ONE device buffer [rays_o | rays_d | target] mirrored by one pinned host staging buffer:
+        # a loader that writes into pinned_batch() hands a step its inputs with a single H2D copy, which is the first
+        # node of the captured "staged" graph (no per-tensor copy calls on the host)
+        self.batch_dev = torch.zeros(3, N, 3, **f32)
+        self.batch_host = torch.zeros(3, N, 3, dtype=torch.float32).pin_memory()
+        self.rays_o, self.rays_d, self.target = self.batch_dev[0], self.batch_dev[1], self.batch_dev[2]
+        self.graph_staged = None
         self.noises = torch.zeros(N, **f32)
         self.nears, self.fars = torch.empty(N, **f32), torch.empty(N, **f32)
         self.weights_sum, self.depth = torch.empty(N, **f32), torch.empty(N, **f32)
@@ -153,7 +157,7 @@ class FusedTrainStep:
 
     def _alloc_samples(self, m_cap):
         dev = self.dev
-        self.graph = None
+        self.graph = self.graph_staged = None
         self.m_cap = m_cap
         if m_cap == 0:
             return
@@ -226,9 +230,16 @@ class FusedTrainStep:
         return max(4096, int(math.ceil(samples * 1.25 / 4096.0)) * 4096)
 
     # ------------------------------------------------------------------------------------------ the step
-    def _launch(self):
+    def pinned_batch(self):
+        """(rays_o, rays_d, target): [N,3] views of the pinned host staging buffer.  Fill them in place and call
+        ``step(*pinned_batch())``: the step then starts with one H2D copy of the whole batch inside its graph."""
+        return self.batch_host[0], self.batch_host[1], self.batch_host[2]
+
+    def _launch(self, staged=False):
         """every device-side action of one step, on the current stream (this is what the graph captures)"""
         st = L.stream()
+        if staged:
+            self.batch_dev.copy_(self.batch_host, non_blocking=True)
         if self.perturb:
             self.noises.uniform_()
         _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), st), "train_forward_backward")
@@ -260,7 +271,7 @@ class FusedTrainStep:
         _check(self.lib.nb200_field_pack_weights(C.c_void_p(p.trunk), C.c_void_p(p.density), C.c_void_p(p.rgb),
                                                  C.c_void_p(p.w_fwd), C.c_void_p(p.w_bwd), st), "field_pack_weights")
 
-    def _capture(self):
+    def _capture(self, staged=False):
         """warm up on a side stream (first-call cudaFuncSetAttribute, allocator, RNG registration), capture one step,
         then restore the optimiser state the warm-up steps advanced"""
         state = (self.params_flat, self.exp_avg, self.exp_avg_sq, self.step_count)
@@ -270,14 +281,17 @@ class FusedTrainStep:
             s.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    self._launch()
+                    self._launch(staged)
             torch.cuda.current_stream(self.dev).wait_stream(s)
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             # thread_local: NCCL's watchdog thread may touch the CUDA API while the all-reduce of a sharded step is captured
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._launch()
-            self.graph = g
+                self._launch(staged)
+            if staged:
+                self.graph_staged = g
+            else:
+                self.graph = g
         finally:
             torch.cuda.synchronize(self.dev)
             for t, k in zip(state, keep):
@@ -328,21 +342,25 @@ class FusedTrainStep:
             if self.m_cap == 0:
                 self._alloc_samples(self._round_cap(self.measure_samples(rays_o if rays_o is not None else self.rays_o,
                                                                          rays_d if rays_d is not None else self.rays_d)))
-            if rays_o is not None:
+            # a batch handed over in the pinned staging buffer is copied by the graph itself (one H2D node)
+            staged = (rays_o is not None and not rays_o.is_cuda and rays_o.data_ptr() == self.batch_host[0].data_ptr()
+                      and rays_d.data_ptr() == self.batch_host[1].data_ptr() and target.data_ptr() == self.batch_host[2].data_ptr())
+            if rays_o is not None and not staged:
                 self.set_batch(rays_o, rays_d, target)
-            if self.use_graph and self.graph is None:
+            have = self.graph_staged if staged else self.graph
+            if self.use_graph and have is None:
                 try:
-                    self._capture()
+                    self._capture(staged)
                 except Exception as e:      # e.g. a collective that cannot be captured on this NCCL build
                     import warnings
                     warnings.warn("FusedTrainStep: CUDA-graph capture failed (%s); launching the step's kernels "
                                   "directly instead" % (e,))
-                    self.use_graph, self.graph = False, None
+                    self.use_graph, self.graph, self.graph_staged = False, None, None
                     torch.cuda.synchronize(self.dev)
             if self.use_graph:
-                self.graph.replay()
+                (self.graph_staged if staged else self.graph).replay()
             else:
-                self._launch()
+                self._launch(staged)
             L.LAUNCHES += KERNELS_PER_STEP
 
     def last_stats(self):

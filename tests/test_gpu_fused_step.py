@@ -113,13 +113,20 @@ def test_graph_replay_trains_and_matches_eager_launches():
     o, d, tgt = _batch()
     eager = fused_trainer.FusedTrainStep(ma, N_RAYS, perturb=False, use_graph=False)
     graph = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False, use_graph=True)
-    losses_e, losses_g = [], []
+    mc, _ = _models()
+    staged = fused_trainer.FusedTrainStep(mc, N_RAYS, perturb=False, use_graph=True)
+    ho, hd, ht = staged.pinned_batch()                 # batch handed over in the pinned staging buffer:
+    ho.copy_(o.cpu()); hd.copy_(d.cpu()); ht.copy_(tgt.cpu())     # the H2D copy is a node of the step's graph
+    losses_e, losses_g, losses_s = [], [], []
     for _ in range(6):
         eager.step(o, d, tgt); losses_e.append(eager.last_stats()[0])
         graph.step(o, d, tgt); losses_g.append(graph.last_stats()[0])
+        staged.step(ho, hd, ht); losses_s.append(staged.last_stats()[0])
+    assert staged.graph_staged is not None and staged.graph is None
     assert losses_e[-1] < losses_e[0]                  # it trains
-    assert int(graph.step_count) == int(eager.step_count) == 6
+    assert int(graph.step_count) == int(eager.step_count) == int(staged.step_count) == 6
     np.testing.assert_allclose(losses_g, losses_e, rtol=2e-2)
+    np.testing.assert_allclose(losses_s, losses_e, rtol=2e-2)
     # parameters stay views of the flat vector (state-dict names unchanged)
     assert mb.pos_en.embeddings.data_ptr() == graph.params_flat.data_ptr()
     assert set(k for k in mb.state_dict() if "params" in k or "embeddings" in k) == {
