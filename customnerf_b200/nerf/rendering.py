@@ -294,13 +294,19 @@ class NeRFRenderer(nn.Module):
         G = self.grid_size
         tmp_grid = -torch.ones_like(self.density_grid)
         axis = torch.arange(G, dtype=torch.int32, device=dev)
+        cache = getattr(self, '_occ_cells', None)            # (morton index, cell-centre coordinate) of every cell: constant
         for xs in axis.split(S):
             for ys in axis.split(S):
                 for zs in axis.split(S):
-                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
-                    coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
-                    indices = raymarching.morton3D(coords).long()
-                    xyzs = 2 * coords.float() / (G - 1) - 1
+                    if S >= G and cache is not None and cache[0].device == dev and cache[0].numel() == G ** 3:
+                        indices, xyzs = cache
+                    else:
+                        xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
+                        coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
+                        indices = raymarching.morton3D(coords).long()
+                        xyzs = 2 * coords.float() / (G - 1) - 1
+                        if S >= G:
+                            self._occ_cells = (indices, xyzs)
                     for cas in range(self.cascade):
                         bound = min(2 ** cas, self.bound)
                         half_grid_size = bound / G
@@ -308,9 +314,12 @@ class NeRFRenderer(nn.Module):
                         cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half_grid_size
                         sigmas = self.density(cas_xyzs)['sigma'].reshape(-1).detach()
                         tmp_grid[cas, indices] = sigmas.float()
+        # EMA-max update where the grid is valid (:1701-1703), written with where() instead of boolean-mask indexing
+        # (no nonzero() synchronisation); the buffer is updated in place, captured graphs keep pointing at it
         valid = self.density_grid >= 0
-        self.density_grid[valid] = torch.maximum(self.density_grid[valid] * decay, tmp_grid[valid])
-        self.mean_density = torch.mean(self.density_grid[valid]).item()
+        self.density_grid.copy_(torch.where(valid, torch.maximum(self.density_grid * decay, tmp_grid), self.density_grid))
+        n_valid = valid.sum()
+        self.mean_density = (torch.where(valid, self.density_grid, torch.zeros_like(self.density_grid)).sum() / n_valid).item()
         self.iter_density += 1
         density_thresh = min(self.mean_density, self.density_thresh)
         self.density_bitfield = raymarching.packbits(self.density_grid, density_thresh, self.density_bitfield)
