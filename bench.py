@@ -272,7 +272,8 @@ def run_b200(args):
     # N > 1: ONE all-reduce of the flat gradient per step (measured at N = 2: 0.67 ms/step; splitting it into 4 pieces
     # pipelined with Adam -- FusedTrainStep(allreduce_chunks=4) -- was slower, 0.77 ms: per-collective latency dominates)
     sync = (lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM)) if world > 1 else None
-    fs = fused_trainer.FusedTrainStep(model, n_rays, lr=5e-4, world_size=world, grad_sync=sync, use_graph=not args.no_graph)
+    fs = fused_trainer.FusedTrainStep(model, n_rays, lr=5e-4, world_size=world, grad_sync=sync, use_graph=not args.no_graph,
+                                      pipeline_update=not args.no_pipeline)
     # the batch is handed over the way a loader would: written into the trainer's pinned staging buffer, from where each
     # step's graph copies it to the device (one H2D node of 537 KB inside the timed step)
     o_h, d_h, t_h = fs.pinned_batch()
@@ -334,7 +335,9 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": n_rays, "parallelism": "ray-sharded dp%d" % world,
                            "step": "one CUDA-graph replay: near/far, march, encode, field MLP, composite, MSE, backward, "
-                                   "fused Adam" + (", NCCL all-reduce of the flat gradient" if world > 1 else ""),
+                                   "fused Adam" + (", NCCL all-reduce of the flat gradient" if world > 1 else "") +
+                                   ("; the update of step k runs on a second stream next to the march of step k+1 (every "
+                                    "replay contains exactly one update and one forward/backward)" if not args.no_pipeline else ""),
                            "sample_rows_capacity": fs.m_cap,
                            "l2": "256 MB memset between steps, outside the per-step CUDA-event pairs",
                            "timing": "sum of per-step CUDA-event intervals, max over ranks"},
@@ -345,9 +348,10 @@ def run_b200(args):
                                "at the head of the step's graph) + last_stats() (16-byte D2H + sync)"},
                 "gpu_launches": int(launches), "clocks": clk, "samples_per_step": samples, "final_loss": loss}
         if world == 1 and not args.no_breakdown:
-            fs.use_graph = False
+            fs.flush()
+            fs.use_graph, fs.pipeline_update = False, False      # stage times: one stream, one kernel at a time
             stage_us = fs.profile_stages(10, flush=flush.zero_)
-            fs.use_graph = not args.no_graph
+            fs.use_graph, fs.pipeline_update = not args.no_graph, not args.no_pipeline
             line["kernel_us"] = {k: round(v, 2) for k, v in stage_us.items()}
             line["roofline"], line["stage_rooflines"] = rooflines(stage_us, samples, fs.params_flat.numel(), peaks)
             try:
@@ -382,6 +386,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying a CUDA graph")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="run each step's optimiser update before the next step starts instead of next to its ray march")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (kernel tuning runs)")
     ap.add_argument("--no-breakdown", action="store_true",
                     help="skip the per-kernel breakdown and the CPU baseline (profiling runs under ncu)")

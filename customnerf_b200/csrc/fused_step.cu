@@ -60,16 +60,19 @@ int nb200_stage_timer_read(void *timer, float *out_us) {
 }
 
 
-int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
+// phases: NB200_PHASE_MARCH = near/far + march (reads only the rays, the noises and the occupancy bit field -- nothing the
+// optimiser writes, so it may run concurrently with the previous step's nb200_train_update), NB200_PHASE_REST = encode ..
+// encode^T.  nb200_train_forward_backward = both.
+int nb200_train_phase(const nb200_train_plan *p, int phases, void *stream) {
     if (!p) return NB200_E_BAD_ARG;
     cudaStream_t st = nb_stream(stream);
     int rc;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(p->counter, 0, 2 * sizeof(int32_t), st)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(p->loss, 0, sizeof(float), st)) != cudaSuccess) return (int)e;
     StageTimer *tm = (StageTimer *)p->timer;
     cudaEvent_t *ev = tm ? tm->fb : nullptr;
     int k = 0;
+    if (!(phases & NB200_PHASE_MARCH)) { k = 2; goto rest; }
+    if ((e = cudaMemsetAsync(p->counter, 0, 2 * sizeof(int32_t), st)) != cudaSuccess) return (int)e;
     tick(ev, k++, st);
     if ((rc = nb200_fs_march_count(p->rays_o, p->rays_d, p->bitfield, p->bound, p->dt_gamma, p->max_steps, p->N, p->C,
                                    p->H, p->M_cap, p->nears, p->fars, p->noises, p->rays, p->counter, p->m_eff,
@@ -78,6 +81,9 @@ int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
     if ((rc = nb200_fs_march_write(p->rays_o, p->rays_d, p->bitfield, p->bound, p->dt_gamma, p->max_steps, p->N, p->C,
                                    p->H, p->M_cap, p->nears, p->fars, p->noises, p->rays, p->xyzs, p->dirs, p->deltas,
                                    p->m_eff, p->scratch, stream))) return rc;
+rest:
+    if (!(phases & NB200_PHASE_REST)) return 0;
+    if ((e = cudaMemsetAsync(p->loss, 0, sizeof(float), st)) != cudaSuccess) return (int)e;
     tick(ev, k++, st);
     if ((rc = nb200_fs_encode_forward(p->xyzs, p->bound, p->table, p->offsets, p->x_en, p->M_cap, p->L, p->S, p->base_res,
                                       p->gridtype, 0, 0, p->m_eff, stream))) return rc;
@@ -101,6 +107,10 @@ int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
     tick(ev, k++, st);
     if (tm) tm->fb_done = true;
     return 0;
+}
+
+int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
+    return nb200_train_phase(p, NB200_PHASE_MARCH | NB200_PHASE_REST, stream);
 }
 
 int nb200_train_update(const nb200_train_plan *p, void *stream) {

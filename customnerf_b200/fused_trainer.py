@@ -83,7 +83,7 @@ def flatten_parameters(model):
 class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
-                 lr_decay_iters=0, allreduce_chunks=0, process_group=None):
+                 lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False):
         if not model.cuda_ray:
             raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
@@ -100,6 +100,14 @@ class FusedTrainStep:
         # Adam sweep of piece i runs while piece i+1 is still on the wire (replaces grad_sync)
         self.allreduce_chunks = int(allreduce_chunks)
         self.process_group = process_group
+        # pipeline_update: the optimiser update of step k (all-reduce, Adam, weight re-pack) runs on a second stream
+        # CONCURRENTLY with the ray march of step k + 1, which reads nothing the update writes -- a memory-bound sweep next
+        # to an issue-bound traversal, and at N > 1 the all-reduce hides behind the march.  The parameters then lag one
+        # update behind the last step() until flush() (call it before reading the model: eval, update_extra_state,
+        # checkpoints).  Same arithmetic, same order per tensor: results equal the unpipelined step's.
+        self.pipeline_update = bool(pipeline_update)
+        self._pending_update = False
+        self._side = None
         self.use_graph = use_graph
         self.perturb = perturb
         self.T_thresh, self.dt_gamma, self.max_steps = float(T_thresh), float(dt_gamma), int(max_steps)
@@ -235,6 +243,14 @@ class FusedTrainStep:
         ``step(*pinned_batch())``: the step then starts with one H2D copy of the whole batch inside its graph."""
         return self.batch_host[0], self.batch_host[1], self.batch_host[2]
 
+    def _update(self, st):
+        if self.allreduce_chunks > 1:
+            self._pipelined_allreduce_update(st)
+        else:
+            if self.grad_sync is not None:
+                self.grad_sync(self.grads_flat)
+            _check(self.lib.nb200_train_update(C.byref(self.plan), st), "train_update")
+
     def _launch(self, staged=False):
         """every device-side action of one step, on the current stream (this is what the graph captures)"""
         st = L.stream()
@@ -242,14 +258,28 @@ class FusedTrainStep:
             self.batch_dev.copy_(self.batch_host, non_blocking=True)
         if self.perturb:
             self.noises.uniform_()
-        _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), st), "train_forward_backward")
-        if self.allreduce_chunks > 1:
-            self._pipelined_allreduce_update(st)
+        if not self.pipeline_update:
+            _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), st), "train_forward_backward")
+            self._update(st)
         else:
-            if self.grad_sync is not None:
-                self.grad_sync(self.grads_flat)
-            _check(self.lib.nb200_train_update(C.byref(self.plan), st), "train_update")
+            # [update of the previous step] on the side stream  ||  [march of this step] here, then join
+            main = torch.cuda.current_stream(self.dev)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self._update(L.stream())
+            _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(1), st), "train_phase(march)")
+            main.wait_stream(self._side)
+            _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(2), st), "train_phase(rest)")
         self.stats_host.copy_(self.stats, non_blocking=True)
+
+    def flush(self):
+        """pipeline_update: apply the update of the last step() now, so that the parameters are current"""
+        if self.pipeline_update and self._pending_update:
+            with torch.cuda.device(self.dev):
+                self._update(L.stream())
+            self._pending_update = False
 
     def _pipelined_allreduce_update(self, st):
         """all-reduce(sum) of grads_flat in pieces on NCCL's stream, each piece's Adam sweep as soon as it has arrived"""
@@ -275,6 +305,8 @@ class FusedTrainStep:
         """warm up on a side stream (first-call cudaFuncSetAttribute, allocator, RNG registration), capture one step,
         then restore the optimiser state the warm-up steps advanced"""
         state = (self.params_flat, self.exp_avg, self.exp_avg_sq, self.step_count)
+        if self.pipeline_update:            # the gradient of the step before is still waiting for its update: keep it
+            state = state + (self.grads_flat,)
         keep = [t.clone() for t in state]
         try:
             s = torch.cuda.Stream(device=self.dev)
@@ -296,7 +328,8 @@ class FusedTrainStep:
             torch.cuda.synchronize(self.dev)
             for t, k in zip(state, keep):
                 t.copy_(k)
-            self.grads_flat.zero_()
+            if not self.pipeline_update:
+                self.grads_flat.zero_()
             self._pack()
 
     def forward_backward(self):
@@ -347,6 +380,17 @@ class FusedTrainStep:
                       and rays_d.data_ptr() == self.batch_host[1].data_ptr() and target.data_ptr() == self.batch_host[2].data_ptr())
             if rays_o is not None and not staged:
                 self.set_batch(rays_o, rays_d, target)
+            if self.pipeline_update and not self._pending_update:
+                # first step of a pipelined run: nothing to update yet -- forward + backward only, launched directly
+                if staged:
+                    self.batch_dev.copy_(self.batch_host, non_blocking=True)
+                if self.perturb:
+                    self.noises.uniform_()
+                _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
+                self.stats_host.copy_(self.stats, non_blocking=True)
+                self._pending_update = True
+                L.LAUNCHES += KERNELS_PER_STEP - 4
+                return
             have = self.graph_staged if staged else self.graph
             if self.use_graph and have is None:
                 try:

@@ -296,6 +296,12 @@ uint32_t nb200_train_plan_bytes(void);
 /* near/far -> march -> encode -> field -> composite -> MSE -> composite^T -> field^T -> encode^T (gradients
  * accumulated into grads_flat).  Resets counter and loss first. */
 int nb200_train_forward_backward(const nb200_train_plan *plan, void *stream);
+/* The same in two phases.  NB200_PHASE_MARCH (near/far + march) reads only rays, noises and the occupancy bit field --
+ * nothing the optimiser writes -- so a trainer may run it on a second stream concurrently with the PREVIOUS step's
+ * nb200_train_update (a memory-bound sweep next to an issue-bound traversal); NB200_PHASE_REST is encode .. encode^T. */
+#define NB200_PHASE_MARCH 1
+#define NB200_PHASE_REST  2
+int nb200_train_phase(const nb200_train_plan *plan, int phases, void *stream);
 /* fused Adam over params_flat (zeroing grads_flat) and re-pack of the MLP operand images. */
 int nb200_train_update(const nb200_train_plan *plan, void *stream);
 
