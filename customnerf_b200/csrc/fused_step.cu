@@ -93,11 +93,12 @@ rest:
     tick(ev, k++, st);
     if ((rc = nb200_fs_composite_forward(p->sigma, p->rgba, p->deltas, p->rays, p->M_cap, p->N, p->T_thresh,
                                          p->weights_sum, p->depth, p->image, p->target, p->inv_n_total, p->loss_scale,
-                                         p->loss, p->g_image, stream))) return rc;
+                                         p->loss, p->g_image, p->target_mask, p->mask_weight, p->render_mask,
+                                         p->g_render_mask, stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_fs_composite_backward(p->g_weights_sum, p->g_image, p->sigma, p->rgba, p->deltas, p->rays,
                                           p->weights_sum, p->image, p->M_cap, p->N, p->T_thresh, p->d_sigma, p->d_rgba,
-                                          stream))) return rc;
+                                          p->target_mask ? p->g_render_mask : nullptr, p->render_mask, stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_field_backward(p->d_sigma, p->d_rgba, p->sigma_arg, p->rgba, p->x_en, p->dirs, p->act, p->w_bwd,
                                    p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, stream))) return rc;

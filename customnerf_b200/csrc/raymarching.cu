@@ -751,19 +751,29 @@ constexpr int kCompBlock = 256;   // 8 rays per block
 
 // colour of sample s: float [M,3] (the reference layout) or half [M,4] (rgb + mask, straight from the field kernel)
 template <typename TC>
-__device__ __forceinline__ void ld_rgb(const TC *__restrict__ rgbs, size_t s, float &c0, float &c1, float &c2) {
+__device__ __forceinline__ void ld_rgba(const TC *__restrict__ rgbs, size_t s, float &c0, float &c1, float &c2, float &c3) {
     if constexpr (sizeof(TC) == 2) {
         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(rgbs) + s);
         const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
         const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
-        c0 = a.x; c1 = a.y; c2 = b.x;
+        c0 = a.x; c1 = a.y; c2 = b.x; c3 = b.y;                 // 4th channel: the mask head (train_conf)
     } else {
-        c0 = __ldg(rgbs + s * 3); c1 = __ldg(rgbs + s * 3 + 1); c2 = __ldg(rgbs + s * 3 + 2);
+        c0 = __ldg(rgbs + s * 3); c1 = __ldg(rgbs + s * 3 + 1); c2 = __ldg(rgbs + s * 3 + 2); c3 = 0.0f;
     }
+}
+template <typename TC>
+__device__ __forceinline__ void ld_rgb(const TC *__restrict__ rgbs, size_t s, float &c0, float &c1, float &c2) {
+    float c3;
+    ld_rgba<TC>(rgbs, s, c0, c1, c2, c3);
 }
 
 // optional fused MSE (fused train step): loss[0] += sum (image - target)^2 * inv_n, g_image = 2 (image - target) inv_n scale
-struct MseArgs { const float *target; float *loss, *g_image; float inv_n, scale; };
+// mask part (train_conf, utils_init_nerf.py:231-233): render_mask = sum w * mask (the 4th channel of the half rgba rows),
+// loss += mask_weight * mean (render_mask - target_mask)^2, g_render_mask its gradient
+struct MseArgs {
+    const float *target; float *loss, *g_image; float inv_n, scale;
+    const float *target_mask; float *render_mask, *g_render_mask; float mask_weight;
+};
 
 template <typename TC>
 __global__ void __launch_bounds__(kCompBlock)
@@ -786,19 +796,19 @@ k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ r
         }
     } else if (n >= N) return;
     const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
-    float r = 0, g = 0, b = 0, ws = 0, d = 0;
+    float r = 0, g = 0, b = 0, ws = 0, d = 0, mk = 0;
     if (num_steps != 0 && offset + num_steps <= M) {
         float T_carry = 1.0f, t_carry = 0.0f;
         for (uint32_t base = 0; base < num_steps; base += 32) {
             const uint32_t i = base + lane;
             const bool valid = i < num_steps;
             const size_t s = (size_t)offset + i;
-            float sigma = 0, d0 = 0, d1 = 0, c0 = 0, c1 = 0, c2 = 0;
+            float sigma = 0, d0 = 0, d1 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
             if (valid) {
                 sigma = __ldg(sigmas + s);
                 const float2 dl = __ldg(reinterpret_cast<const float2 *>(deltas) + s);
                 d0 = dl.x; d1 = dl.y;
-                ld_rgb<TC>(rgbs, s, c0, c1, c2);
+                ld_rgba<TC>(rgbs, s, c0, c1, c2, c3);
             }
             const float alpha = valid ? 1.0f - __expf(-sigma * d0) : 0.0f;
             const float pin = warp_incl_prod(1.0f - alpha);
@@ -810,6 +820,7 @@ k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ r
             const uint32_t last = term ? (uint32_t)(__ffs(term) - 1) : 31u;   // the breaking sample is included (:554-557)
             const float weight = (valid && lane <= last) ? alpha * (T_carry * pex) : 0.0f;
             r = fmaf(weight, c0, r); g = fmaf(weight, c1, g); b = fmaf(weight, c2, b);
+            mk = fmaf(weight, c3, mk);
             d = fmaf(weight, t_i, d);
             ws += weight;
             if (term) break;
@@ -817,18 +828,26 @@ k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ r
             t_carry = __shfl_sync(0xffffffffu, t_i, 31);
         }
         r = nb_warp_sum(r); g = nb_warp_sum(g); b = nb_warp_sum(b); ws = nb_warp_sum(ws); d = nb_warp_sum(d);
+        if (mse.render_mask) mk = nb_warp_sum(mk);
     }
     if (lane == 0) {
         weights_sum[index] = ws;
         depth[index] = d;
         image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+        if (mse.render_mask) mse.render_mask[index] = mk;
     }
     if (mse.target) {
         if (lane == 0) {
             const float d0 = r - mse.target[index * 3], d1 = g - mse.target[index * 3 + 1], d2 = b - mse.target[index * 3 + 2];
             const float k = 2.0f * mse.inv_n * mse.scale;
             mse.g_image[index * 3] = d0 * k; mse.g_image[index * 3 + 1] = d1 * k; mse.g_image[index * 3 + 2] = d2 * k;
-            loss_part[threadIdx.x >> 5] = d0 * d0 + d1 * d1 + d2 * d2;
+            float part = d0 * d0 + d1 * d1 + d2 * d2;
+            if (mse.target_mask) {          // mean over N x 1 entries = 3 x the per-element weight of the N x 3 image
+                const float dm = mk - mse.target_mask[index];
+                mse.g_render_mask[index] = 2.0f * dm * (3.0f * mse.inv_n) * mse.mask_weight * mse.scale;
+                part += 3.0f * mse.mask_weight * dm * dm;
+            }
+            loss_part[threadIdx.x >> 5] = part;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -846,12 +865,17 @@ k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *_
                       const float *__restrict__ sigmas, const TC *__restrict__ rgbs, const float *__restrict__ deltas,
                       const int32_t *__restrict__ rays, const float *__restrict__ weights_sum,
                       const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
-                      float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs) {
+                      float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs,
+                      const float *__restrict__ grad_render_mask, const float *__restrict__ render_mask) {
     const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
     if (n >= N) return;
     const uint32_t lane = nb_lane();
     const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
     if (num_steps == 0 || offset + num_steps > M) return;
+    // optional 4th composited channel (the rendered mask): same recurrences as a colour channel
+    const bool has_m = grad_render_mask != nullptr;
+    const float gm = has_m ? grad_render_mask[index] : 0.0f, m_final = has_m ? render_mask[index] : 0.0f;
+    float m_c = 0;
     const float gws = grad_weights_sum[index];
     const float gi0 = grad_image[index * 3], gi1 = grad_image[index * 3 + 1], gi2 = grad_image[index * 3 + 2];
     const float r_final = image[index * 3], g_final = image[index * 3 + 1], b_final = image[index * 3 + 2];
@@ -862,13 +886,13 @@ k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *_
         const uint32_t i = base + lane;
         const bool valid = i < num_steps;
         const size_t s = (size_t)offset + i;
-        float gs = 0, gr0 = 0, gr1 = 0, gr2 = 0;
+        float gs = 0, gr0 = 0, gr1 = 0, gr2 = 0, gr3 = 0;
         if (!done) {
-            float sigma = 0, d0 = 0, c0 = 0, c1 = 0, c2 = 0;
+            float sigma = 0, d0 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
             if (valid) {
                 sigma = __ldg(sigmas + s);
                 d0 = __ldg(deltas + s * 2);
-                ld_rgb<TC>(rgbs, s, c0, c1, c2);
+                ld_rgba<TC>(rgbs, s, c0, c1, c2, c3);
             }
             const float alpha = valid ? 1.0f - __expf(-sigma * d0) : 0.0f;
             const float pin = warp_incl_prod(1.0f - alpha);
@@ -882,21 +906,24 @@ k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *_
             const float r_i = r_c + warp_incl_sum(weight * c0);
             const float g_i = g_c + warp_incl_sum(weight * c1);
             const float b_i = b_c + warp_incl_sum(weight * c2);
+            float m_i = 0.0f;
+            if (has_m) m_i = m_c + warp_incl_sum(weight * c3);      // (warp-uniform branch)
             if (act) {
-                gr0 = gi0 * weight; gr1 = gi1 * weight; gr2 = gi2 * weight;
+                gr0 = gi0 * weight; gr1 = gi1 * weight; gr2 = gi2 * weight; gr3 = gm * weight;
                 gs = d0 * (gi0 * (T_after * c0 - (r_final - r_i)) + gi1 * (T_after * c1 - (g_final - g_i)) +
-                           gi2 * (T_after * c2 - (b_final - b_i)) + ws_term);             // :752-757
+                           gi2 * (T_after * c2 - (b_final - b_i)) + gm * (T_after * c3 - (m_final - m_i)) + ws_term);   // :752-757
             }
             if (term) done = true;
             T_carry = __shfl_sync(0xffffffffu, T_after, 31);
             r_c = __shfl_sync(0xffffffffu, r_i, 31);
             g_c = __shfl_sync(0xffffffffu, g_i, 31);
             b_c = __shfl_sync(0xffffffffu, b_i, 31);
+            if (has_m) m_c = __shfl_sync(0xffffffffu, m_i, 31);
         }
         if (valid) {   // rows after the early-out get explicit zeros (raymarching.py:284-285 zero-fills instead)
             grad_sigmas[s] = gs;
             if constexpr (GS == 4) {
-                reinterpret_cast<float4 *>(grad_rgbs)[s] = make_float4(gr0, gr1, gr2, 0.0f);
+                reinterpret_cast<float4 *>(grad_rgbs)[s] = make_float4(gr0, gr1, gr2, gr3);
             } else {
                 grad_rgbs[s * 3] = gr0; grad_rgbs[s * 3 + 1] = gr1; grad_rgbs[s * 3 + 2] = gr2;
             }
@@ -1276,7 +1303,7 @@ int nb200_composite_rays_train_forward(const float *sigmas, const float *rgbs, c
                                        float *image, void *stream) {
     if (N == 0) return 0;
     k_composite_train_fwd<float><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
-        sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image, MseArgs{nullptr, nullptr, nullptr, 0.0f, 0.0f});
+        sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image, MseArgs{nullptr, nullptr, nullptr, 0.0f, 0.0f, nullptr, nullptr, nullptr, 0.0f});
     NB_LAUNCH_CHECK();
     return 0;
 }
@@ -1285,12 +1312,14 @@ int nb200_composite_rays_train_forward(const float *sigmas, const float *rgbs, c
 int nb200_fs_composite_forward(const float *sigmas, const void *rgba, const float *deltas, const int32_t *rays,
                                uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image,
                                const float *target, float inv_n, float loss_scale, float *loss, float *g_image,
+                               const float *target_mask, float mask_weight, float *render_mask, float *g_render_mask,
                                void *stream) {
     if (N == 0) return 0;
     if (target && (!loss || !g_image)) return NB200_E_BAD_ARG;
+    if (target_mask && (!target || !render_mask || !g_render_mask)) return NB200_E_BAD_ARG;
     k_composite_train_fwd<__half><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
         sigmas, (const __half *)rgba, deltas, rays, M, N, T_thresh, weights_sum, depth, image,
-        MseArgs{target, loss, g_image, inv_n, loss_scale});
+        MseArgs{target, loss, g_image, inv_n, loss_scale, target_mask, render_mask, g_render_mask, mask_weight});
     NB_LAUNCH_CHECK();
     return 0;
 }
@@ -1298,11 +1327,12 @@ int nb200_fs_composite_forward(const float *sigmas, const void *rgba, const floa
 int nb200_fs_composite_backward(const float *grad_weights_sum, const float *grad_image, const float *sigmas,
                                 const void *rgba, const float *deltas, const int32_t *rays, const float *weights_sum,
                                 const float *image, uint32_t M, uint32_t N, float T_thresh, float *grad_sigmas,
-                                float *grad_rgba, void *stream) {
+                                float *grad_rgba, const float *grad_render_mask, const float *render_mask, void *stream) {
     if (N == 0) return 0;
+    if (grad_render_mask && !render_mask) return NB200_E_BAD_ARG;
     k_composite_train_bwd<__half, 4><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
         grad_weights_sum, grad_image, sigmas, (const __half *)rgba, deltas, rays, weights_sum, image, M, N, T_thresh,
-        grad_sigmas, grad_rgba);
+        grad_sigmas, grad_rgba, grad_render_mask, render_mask);
     NB_LAUNCH_CHECK();
     return 0;
 }
@@ -1314,7 +1344,7 @@ int nb200_composite_rays_train_backward(const float *grad_weights_sum, const flo
     if (N == 0) return 0;
     k_composite_train_bwd<float, 3><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
         grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas,
-        grad_rgbs);
+        grad_rgbs, nullptr, nullptr);
     NB_LAUNCH_CHECK();
     return 0;
 }

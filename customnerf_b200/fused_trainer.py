@@ -48,7 +48,9 @@ class TrainPlan(C.Structure):
     _u32 = ["N", "M_cap", "C", "H", "L", "base_res", "gridtype", "max_steps"]
     _f32 = ["bound", "dt_gamma", "S", "T_thresh", "min_near", "loss_scale", "inv_n_total", "pad0"]
     _u64 = ["n_params", "n_table_params"]
-    _ptr = ["rays_o", "rays_d", "target", "aabb", "noises", "bitfield",
+    _ptr0 = ["rays_o", "rays_d", "target", "aabb", "noises", "target_mask", "render_mask", "g_render_mask"]
+    _f32b = ["mask_weight", "pad1"]
+    _ptr = ["bitfield",
             "params_flat", "grads_flat", "exp_avg", "exp_avg_sq", "hyper", "sched", "step",
             "table", "trunk", "density", "rgb", "offsets",
             "g_table", "g_trunk", "g_density", "g_rgb", "w_fwd", "w_bwd",
@@ -57,7 +59,7 @@ class TrainPlan(C.Structure):
             "xyzs", "dirs", "deltas", "sigma", "sigma_arg", "d_sigma", "d_rgba",
             "x_en", "rgba", "act", "d_x_en", "wg_scratch", "timer"]
     _fields_ = ([(n, C.c_uint32) for n in _u32] + [(n, C.c_float) for n in _f32] + [(n, C.c_uint64) for n in _u64] +
-                [(n, C.c_void_p) for n in _ptr])
+                [(n, C.c_void_p) for n in _ptr0] + [(n, C.c_float) for n in _f32b] + [(n, C.c_void_p) for n in _ptr])
 
 
 def flatten_parameters(model):
@@ -83,7 +85,7 @@ def flatten_parameters(model):
 class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
-                 lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False):
+                 lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0):
         if not model.cuda_ray:
             raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
@@ -105,6 +107,9 @@ class FusedTrainStep:
         # to an issue-bound traversal, and at N > 1 the all-reduce hides behind the march.  The parameters then lag one
         # update behind the last step() until flush() (call it before reading the model: eval, update_extra_state,
         # checkpoints).  Same arithmetic, same order per tensor: results equal the unpipelined step's.
+        # mask_weight > 0: the reference's reconstruction loss with train_conf (utils_init_nerf.py:224-234):
+        # MSE(image, target) + mask_weight * MSE(render_mask, target_mask); render_mask composites the 4th field output
+        self.mask_weight = float(mask_weight)
         self.pipeline_update = bool(pipeline_update)
         self._pending_update = False
         self._side = None
@@ -140,6 +145,8 @@ class FusedTrainStep:
         self.batch_host = torch.zeros(3, N, 3, dtype=torch.float32).pin_memory()
         self.rays_o, self.rays_d, self.target = self.batch_dev[0], self.batch_dev[1], self.batch_dev[2]
         self.graph_staged = None
+        self.target_mask = torch.zeros(N, **f32)
+        self.render_mask, self.g_render_mask = torch.zeros(N, **f32), torch.zeros(N, **f32)
         self.noises = torch.zeros(N, **f32)
         self.nears, self.fars = torch.empty(N, **f32), torch.empty(N, **f32)
         self.weights_sum, self.depth = torch.empty(N, **f32), torch.empty(N, **f32)
@@ -195,6 +202,9 @@ class FusedTrainStep:
             return None if t is None else t.data_ptr()
         p.rays_o, p.rays_d, p.target, p.aabb = a(self.rays_o), a(self.rays_d), a(self.target), a(m.aabb_train)
         p.noises = a(self.noises) if self.perturb else None
+        use_mask = self.mask_weight > 0.0
+        p.target_mask = a(self.target_mask) if use_mask else None
+        p.render_mask, p.g_render_mask, p.mask_weight = a(self.render_mask), a(self.g_render_mask), self.mask_weight
         p.bitfield = a(m.density_bitfield)
         p.params_flat, p.grads_flat, p.exp_avg, p.exp_avg_sq = a(self.params_flat), a(self.grads_flat), a(self.exp_avg), a(self.exp_avg_sq)
         p.hyper, p.sched, p.step = a(self.hyper), a(self.sched), a(self.step_count)
@@ -363,13 +373,15 @@ class FusedTrainStep:
             self.lib.nb200_stage_timer_destroy(timer)
         return {k: float(v / n_steps) for k, v in zip(STAGES, acc)}
 
-    def set_batch(self, rays_o, rays_d, target):
+    def set_batch(self, rays_o, rays_d, target, target_mask=None):
         """copy one ray batch (host -- ideally pinned -- or device tensors) into the step's static input buffers"""
         self.rays_o.copy_(rays_o.reshape(-1, 3), non_blocking=True)
         self.rays_d.copy_(rays_d.reshape(-1, 3), non_blocking=True)
         self.target.copy_(target.reshape(-1, 3), non_blocking=True)
+        if target_mask is not None:
+            self.target_mask.copy_(target_mask.reshape(-1), non_blocking=True)
 
-    def step(self, rays_o=None, rays_d=None, target=None):
+    def step(self, rays_o=None, rays_d=None, target=None, target_mask=None):
         """One train step on the current stream.  Never synchronises; ``last_stats()`` reads the result back."""
         with torch.cuda.device(self.dev):
             if self.m_cap == 0:
@@ -379,7 +391,9 @@ class FusedTrainStep:
             staged = (rays_o is not None and not rays_o.is_cuda and rays_o.data_ptr() == self.batch_host[0].data_ptr()
                       and rays_d.data_ptr() == self.batch_host[1].data_ptr() and target.data_ptr() == self.batch_host[2].data_ptr())
             if rays_o is not None and not staged:
-                self.set_batch(rays_o, rays_d, target)
+                self.set_batch(rays_o, rays_d, target, target_mask)
+            elif target_mask is not None:
+                self.target_mask.copy_(target_mask.reshape(-1), non_blocking=True)
             if self.pipeline_update and not self._pending_update:
                 # first step of a pipelined run: nothing to update yet -- forward + backward only, launched directly
                 if staged:

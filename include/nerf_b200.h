@@ -232,11 +232,18 @@ int nb200_fs_encode_backward(const void *d_x_en, const float *xyz, float bound, 
 int nb200_fs_composite_forward(const float *sigmas, const void *rgba, const float *deltas, const int32_t *rays,
                                uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image,
                                const float *target, float inv_n, float loss_scale, float *loss, float *g_image,
-                               void *stream);   /* target != NULL: nb200_mse_loss_grad fused in (per ray) */
+                               const float *target_mask, float mask_weight, float *render_mask, float *g_render_mask,
+                               void *stream);
+/* target != NULL: nb200_mse_loss_grad fused in (per ray).  target_mask != NULL (the reference's train_conf term,
+ * utils_init_nerf.py:231-233): render_mask[n] = sum_i w_i * mask_i (mask = 4th channel of the rgba rows; what
+ * weights_sum_i renders on the dense path, renderer.py:460-463), loss += mask_weight * mean((render_mask - target_mask)^2),
+ * g_render_mask = its gradient times loss_scale. */
 int nb200_fs_composite_backward(const float *grad_weights_sum, const float *grad_image, const float *sigmas,
                                 const void *rgba, const float *deltas, const int32_t *rays, const float *weights_sum,
                                 const float *image, uint32_t M, uint32_t N, float T_thresh, float *grad_sigmas,
-                                float *grad_rgba, void *stream);
+                                float *grad_rgba, const float *grad_render_mask, const float *render_mask, void *stream);
+/* grad_render_mask / render_mask (both or neither): the rendered mask as a 4th composited channel; its gradient lands in
+ * grad_rgba[:, 3] and in grad_sigmas. */
 /* loss[0] += sum((image - target)^2) * inv_n ;  g_image = 2 (image - target) * inv_n * loss_scale.
  * (F.mse_loss of utils_init_nerf.py:224 with inv_n = 1 / (3 * N_total), and its gradient times the loss scale.) */
 int nb200_mse_loss_grad(const float *image, const float *target, uint32_t N, float inv_n, float loss_scale, float *loss,
@@ -262,6 +269,9 @@ typedef struct nb200_train_plan {
     uint64_t n_params, n_table_params;
     /* inputs (device) */
     const float *rays_o, *rays_d, *target, *aabb, *noises;      /* noises may be NULL (perturb off) */
+    const float *target_mask;                                    /* [N] or NULL: ground-truth mask of the train_conf loss term */
+    float *render_mask, *g_render_mask;                          /* [N] each (used when target_mask != NULL) */
+    float mask_weight, pad1;                                     /* train_conf */
     const uint8_t *bitfield;
     /* parameters: one flat fp32 vector [table | trunk | density | rgb]; the four pointers below alias into it */
     float *params_flat, *grads_flat, *exp_avg, *exp_avg_sq;

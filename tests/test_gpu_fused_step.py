@@ -216,3 +216,45 @@ def test_pipelined_update_matches_the_serial_step():
     assert close > 0.97, close
     piped.step(o, d, tgt)                                                  # primes again after a flush
     assert np.isfinite(piped.last_stats()[0])
+
+
+def test_mask_loss_term_matches_the_autograd_path():
+    """train_conf: loss = MSE(image, target) + w * MSE(render_mask, gt_mask) (nerf/utils_init_nerf.py:224-234) with
+    render_mask = sum_i w_i mask_i composited from the 4th field output.  Fused step (mask as a 4th composited channel)
+    against autograd over the drop-in ops (run_cuda + _lgie_composites): loss rel 1e-5, gradients 1e-2 of the largest."""
+    import torch.nn.functional as F
+    from customnerf_b200 import trainer, fused_trainer
+    w = 0.5
+    opt = trainer.make_opt(train_conf=w)
+    dev = torch.device("cuda")
+    ma = trainer.build_scene_model(dev, log2_hashmap_size=15, desired_resolution=512, opt=opt, seed=3)
+    mb = trainer.build_scene_model(dev, log2_hashmap_size=15, desired_resolution=512, opt=opt, seed=3)
+    with torch.no_grad():
+        ma.pos_en.embeddings.uniform_(-0.5, 0.5)
+        mb.pos_en.embeddings.copy_(ma.pos_en.embeddings)
+    o, d, tgt = _batch()
+    gt_mask = (torch.rand(N_RAYS, generator=torch.Generator().manual_seed(9)) > 0.5).float().cuda()
+    ma.train()
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = ma.render(o[None], d[None], staged=False, perturb=False, force_all_rays=True, **vars(opt))
+        loss_ref = (F.mse_loss(out["image"].reshape(-1, 3), tgt, reduction="sum") / (3.0 * N_RAYS)
+                    + w * F.mse_loss(out["render_mask"].reshape(-1), gt_mask, reduction="sum") / N_RAYS)
+    (loss_ref * fused_trainer.LOSS_SCALE).backward()
+    fs = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False, use_graph=False, mask_weight=w)
+    fs._alloc_samples(fs._round_cap(fs.measure_samples(o, d)))
+    fs.set_batch(o, d, tgt, gt_mask)
+    fs.forward_backward()
+    loss, samples, used = fs.last_stats()
+    assert samples == used > 1000
+    ref = float(loss_ref.detach())
+    assert abs(loss - ref) <= 1e-5 * abs(ref) + 1e-7, (loss, ref)
+    np.testing.assert_allclose(fs.render_mask.cpu().numpy(), out["render_mask"].reshape(-1).detach().float().cpu().numpy(), atol=2e-4)
+    for name, off, n in fs.layout:
+        mod, attr = name.split(".")
+        g_ref = getattr(getattr(ma, mod), attr).grad.reshape(-1).float().cpu().numpy()
+        g = fs.grads_flat[off:off + n].cpu().numpy()
+        scale = np.abs(g_ref).max()
+        assert np.abs(g - g_ref).max() <= 1e-2 * scale, (name, np.abs(g - g_ref).max(), scale)
+    # the mask head really receives gradient: rows 3 of the colour head's last layer
+    gr = fs.grads_flat[fs.layout[3][1]:].cpu().numpy()[64 * 96:].reshape(16, 64)
+    assert np.abs(gr[3]).sum() > 0
