@@ -31,11 +31,23 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+TRAIN_CONF = 0.01          # main.py:132 default: 4-output colour head, loss += train_conf * MSE(render_mask, gt_mask)
+
+
+def silhouette(o, d, n=48):
+    """synthetic ground-truth mask [N]: 1 where the ray meets the analytic bear (48 density probes along the ray)"""
+    import torch
+    from customnerf_b200 import synthetic as syn
+    t = torch.linspace(0.4, 2.8, n)
+    p = o[:, None, :] + d[:, None, :] * t[None, :, None]
+    return (syn.bear_density(p).max(dim=1).values > 1.0).float()
+
+
 METRIC = "train_rays_per_sec_fwd_bwd"
 UNIT = "rays/s"
 IMG_H, IMG_W = 105, 142
 WORKLOAD = "configs[1]: 142x105 image (14910 rays), bear scene, bound 2, 128^3x2 occupancy grid, hash 2^19 L16 F2, " \
-           "64-wide MLPs, cuda_ray path, fp16 autocast, Adam"
+           "64-wide MLPs (rgb + mask head), cuda_ray path, fp16 autocast, loss MSE(rgb) + 0.01 MSE(mask), Adam"
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -135,7 +147,7 @@ def cpu_reference_run(steps, warmup, n_rays):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    opt = torch_ref.default_opt(cuda_ray=False, train_conf=0)
+    opt = torch_ref.default_opt(cuda_ray=False, train_conf=TRAIN_CONF)      # the reference's default: mask head + mask loss
     net = torch_ref.NeRFNetwork(opt, encoder_kwargs=dict(log2_hashmap_size=19, desired_resolution=2048, gridtype="hash"))
     net.train()
     optim = torch.optim.Adam(net.get_params(5e-4), betas=(0.9, 0.99), eps=1e-15)
@@ -143,12 +155,14 @@ def cpu_reference_run(steps, warmup, n_rays):
     sel = torch.linspace(0, o.shape[0] - 1, n_rays).long()
     o, d = o[sel].contiguous(), d[sel].contiguous()
     target = syn.bear_color(o + d * 1.5)
+    gt_mask = silhouette(o, d)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         optim.zero_grad(set_to_none=True)
         out = net.render(o[None], d[None], num_steps=64, upsample_steps=64, perturb=True)
-        loss = ((out["image"].reshape(-1, 3) - target) ** 2).mean()
+        loss = ((out["image"].reshape(-1, 3) - target) ** 2).mean() \
+            + TRAIN_CONF * ((out["render_mask"].reshape(-1) - gt_mask) ** 2).mean()      # utils_init_nerf.py:224-234
         loss.backward()
         optim.step()
         dt = time.perf_counter() - t0
@@ -265,15 +279,17 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     L.lib()   # fail loudly if the native library is missing
 
-    model = trainer.build_scene_model(dev)
+    model = trainer.build_scene_model(dev, opt=trainer.make_opt(train_conf=TRAIN_CONF))
     o, d = syn.camera_rays(IMG_H, IMG_W, view=rank)           # weak scaling: one image per rank
     target = syn.bear_color(o + d * 1.5)
+    gt_mask = silhouette(o, d)
     n_rays = o.shape[0]
     # N > 1: ONE all-reduce of the flat gradient per step (measured at N = 2: 0.67 ms/step; splitting it into 4 pieces
     # pipelined with Adam -- FusedTrainStep(allreduce_chunks=4) -- was slower, 0.77 ms: per-collective latency dominates)
     sync = (lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM)) if world > 1 else None
     fs = fused_trainer.FusedTrainStep(model, n_rays, lr=5e-4, world_size=world, grad_sync=sync, use_graph=not args.no_graph,
-                                      pipeline_update=not args.no_pipeline)
+                                      pipeline_update=not args.no_pipeline, mask_weight=TRAIN_CONF)
+    fs.target_mask.copy_(gt_mask)     # [N] ground-truth mask: resident (59 KB; not part of the per-step H2D count)
     # the batch is handed over the way a loader would: written into the trainer's pinned staging buffer, from where each
     # step's graph copies it to the device (one H2D node of 537 KB inside the timed step)
     o_h, d_h, t_h = fs.pinned_batch()
