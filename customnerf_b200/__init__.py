@@ -6,6 +6,11 @@ Drop-in surface (same names, arguments and error behaviour as the reference):
                                                                       march_rays_train, composite_rays_train, ...)
     customnerf_b200.nerf          <->  nerf/network_grid.py + the hot-path half of nerf/renderer.py
 
+Beyond the drop-in surface (B200-first execution of the same computations):
+    customnerf_b200.fused_trainer.FusedTrainStep   the reconstruction train step as one replayable CUDA graph
+    customnerf_b200.fused_infer.FusedInference     full-image rendering with device-driven rounds (no per-round host sync)
+    customnerf_b200.parallel                       ray sharding + the single NCCL all-reduce of the flat gradient
+
 ``install_aliases()`` registers the two op packages under their reference names so that
 ``from gridencoder import GridEncoder`` (nerf/encoding.py:62) and ``import raymarching``
 (nerf/renderer.py:16) resolve to this implementation.  See INTEGRATION.md.
