@@ -284,11 +284,17 @@ def run_b200(args):
     target = syn.bear_color(o + d * 1.5)
     gt_mask = silhouette(o, d)
     n_rays = o.shape[0]
-    # N > 1: ONE all-reduce of the flat gradient per step (measured at N = 2: 0.67 ms/step; splitting it into 4 pieces
-    # pipelined with Adam -- FusedTrainStep(allreduce_chunks=4) -- was slower, 0.77 ms: per-collective latency dominates)
-    sync = (lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM)) if world > 1 else None
+    # N > 1, default: the update is ONE kernel over NVLink peer memory (csrc/peer_update.cu: every rank reduces + Adam-
+    # updates the slice it owns out of the peers' gradients and stores the new parameters into every replica) -- no NCCL
+    # call inside the step.  --update nccl: one NCCL all-reduce of the flat gradient + a full Adam sweep per rank (measured
+    # at N = 2: 0.67 ms/step; in 4 pieces pipelined with Adam -- allreduce_chunks=4 -- 0.77 ms).
+    peer, sync = None, None
+    if (world > 1 or args.peer_at_1) and args.update in ("peer", "nvls"):
+        peer = parallel.PeerMemory(fused_trainer.flat_parameter_count(model), dev, multicast=args.update == "nvls")
+    elif world > 1:
+        sync = (lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM))
     fs = fused_trainer.FusedTrainStep(model, n_rays, lr=5e-4, world_size=world, grad_sync=sync, use_graph=not args.no_graph,
-                                      pipeline_update=not args.no_pipeline, mask_weight=TRAIN_CONF)
+                                      pipeline_update=not args.no_pipeline, mask_weight=TRAIN_CONF, peer=peer)
     fs.target_mask.copy_(gt_mask)     # [N] ground-truth mask: resident (59 KB; not part of the per-step H2D count)
     # the batch is handed over the way a loader would: written into the trainer's pinned staging buffer, from where each
     # step's graph copies it to the device (one H2D node of 537 KB inside the timed step)
@@ -309,7 +315,7 @@ def run_b200(args):
             a.record()
             if host_inputs:
                 fs.step(o_h, d_h, t_h)                         # H2D of the batch (pinned) + the step
-                fs.last_stats()                                # D2H read of loss / sample count (16 B) + sync
+                fs.last_stats()                                # D2H read of loss / sample count (32 B) + sync
             else:
                 fs.step()                                      # batch already resident in HBM
             b.record()
@@ -334,10 +340,26 @@ def run_b200(args):
     barrier()
     clk = clocks.stop() if rank == 0 else None
     loss, samples, used = fs.last_stats()
+    update_us = None
     if world > 1:
-        t = torch.tensor([sec, sec_e2e], device=dev, dtype=torch.float64)
+        # the update alone (all ranks in lock step; the gradient is zero by now, which changes nothing about the traffic)
+        import ctypes as C
+        fs.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        reps = 20
+        with torch.cuda.device(dev):
+            fs._update(L.stream())
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            for _ in range(reps):
+                fs._update(L.stream())
+            eb.record()
+            torch.cuda.synchronize()
+        update_us = ea.elapsed_time(eb) / reps * 1e3
+        t = torch.tensor([sec, sec_e2e, update_us], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec, sec_e2e = float(t[0]), float(t[1])
+        sec, sec_e2e, update_us = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         peaks = {}
@@ -351,18 +373,30 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": n_rays, "parallelism": "ray-sharded dp%d" % world,
                            "step": "one CUDA-graph replay: near/far, march, encode, field MLP, composite, MSE, backward, "
-                                   "fused Adam" + (", NCCL all-reduce of the flat gradient" if world > 1 else "") +
+                                   "fused Adam" + (", NCCL all-reduce of the flat gradient" if sync is not None else "") +
+                                   ("; update = one reduce + Adam + broadcast kernel over NVLink peer memory%s (no NCCL call "
+                                    "in the step)" % (" through the NVSwitch multicast mapping" if args.update == "nvls" else "")
+                                    if peer is not None else "") +
                                    ("; the update of step k runs on a second stream next to the march of step k+1 (every "
                                     "replay contains exactly one update and one forward/backward)" if not args.no_pipeline else ""),
                            "sample_rows_capacity": fs.m_cap,
                            "l2": "256 MB memset between steps, outside the per-step CUDA-event pairs",
                            "timing": "sum of per-step CUDA-event intervals, max over ranks"},
                 "e2e": {"value": total_rays / sec_e2e, "unit": UNIT,
-                        "h2d_bytes_per_step": int(3 * n_rays * 3 * 4), "d2h_bytes_per_step": 16,
+                        "h2d_bytes_per_step": int(3 * n_rays * 3 * 4), "d2h_bytes_per_step": 32,
                         "ms_per_step": sec_e2e / args.steps * 1e3,
                         "api": "FusedTrainStep.step(*fs.pinned_batch()) (batch in the pinned staging buffer, one H2D copy node "
-                               "at the head of the step's graph) + last_stats() (16-byte D2H + sync)"},
+                               "at the head of the step's graph) + last_stats() (32-byte D2H + sync)"},
                 "gpu_launches": int(launches), "clocks": clk, "samples_per_step": samples, "final_loss": loss}
+        if update_us is not None:
+            nb = fs.params_flat.numel() * 4
+            wire = nb * (world - 1) / world          # bytes in (gradient slices read) = bytes out (parameters stored) per rank
+            line["update"] = {"kind": args.update, "us": round(update_us, 1),
+                              "what": "adam_hyper + " + ("k_peer_reduce_adam_bcast" if peer is not None else
+                                                        "ncclAllReduce(grads_flat) + k_fused_adam") + " + weight re-pack, "
+                                      "back to back on all ranks, max over ranks",
+                              "nvlink_bytes_each_way_per_rank": int(wire),
+                              "nvlink_gbs_each_way_per_rank": round(wire / (update_us * 1e-6) / 1e9, 1)}
         if world == 1 and not args.no_breakdown:
             fs.flush()
             fs.use_graph, fs.pipeline_update = False, False      # stage times: one stream, one kernel at a time
@@ -404,6 +438,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="run each step's optimiser update before the next step starts instead of next to its ray march")
+    ap.add_argument("--update", default="peer", choices=["peer", "nvls", "nccl"],
+                    help="N > 1: optimiser update as one NVLink peer-memory kernel (peer: P2P loads / stores, default; nvls: "
+                         "through the NVSwitch multicast mapping, reduced in the switch) or NCCL all-reduce + Adam")
+    ap.add_argument("--peer-at-1", action="store_true", help="N = 1: run the update through the peer-memory kernel too (tuning)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (kernel tuning runs)")
     ap.add_argument("--no-breakdown", action="store_true",
                     help="skip the per-kernel breakdown and the CPU baseline (profiling runs under ncu)")

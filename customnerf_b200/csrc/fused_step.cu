@@ -131,6 +131,24 @@ int nb200_train_update(const nb200_train_plan *p, void *stream) {
     return 0;
 }
 
+int nb200_train_update_peer(const nb200_train_plan *p, const nb200_peer_plan *peer, void *stream) {
+    if (!p || !peer) return NB200_E_BAD_ARG;
+    if (peer->n != p->n_params || peer->split != p->n_table_params || peer->params[peer->rank] != p->params_flat ||
+        peer->grads[peer->rank] != p->grads_flat) return NB200_E_BAD_ARG;
+    int rc;
+    cudaStream_t st = nb_stream(stream);
+    StageTimer *tm = (StageTimer *)p->timer;
+    cudaEvent_t *ev = tm ? tm->up : nullptr;
+    tick(ev, 0, st);
+    if ((rc = nb200_adam_hyper(p->step, p->sched, p->hyper, stream))) return rc;
+    if ((rc = nb200_peer_reduce_adam_bcast(peer, stream))) return rc;
+    tick(ev, 1, st);
+    if ((rc = nb200_field_pack_weights(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, stream))) return rc;
+    tick(ev, 2, st);
+    if (tm) tm->up_done = true;
+    return 0;
+}
+
 uint32_t nb200_train_plan_bytes(void) { return (uint32_t)sizeof(nb200_train_plan); }
 
 }  // extern "C"

@@ -8,29 +8,9 @@
 //
 // Arithmetic follows torch's fused Adam (aten/src/ATen/native/cuda/fused_adam_utils.cuh, non-amsgrad, no weight
 // decay): m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2; p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps).
-#include "common.cuh"
+#include "adam.cuh"
 
 namespace {
-
-struct AdamHyper {          // 8 floats per parameter group, written by the host before every step
-    float lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale, pad;
-};
-
-// per-group constants hoisted out of the sweep (two of the three divisions of the update are per-step constants)
-struct AdamConst {
-    float grad_scale, w1, beta2, w2, inv_bc2_sqrt, eps, step_size;
-    __device__ __forceinline__ explicit AdamConst(const AdamHyper &h)
-        : grad_scale(h.grad_scale), w1(1.0f - h.beta1), beta2(h.beta2), w2(1.0f - h.beta2),
-          inv_bc2_sqrt(1.0f / h.bc2_sqrt), eps(h.eps), step_size(h.lr / h.bc1) {}
-};
-
-__device__ __forceinline__ void adam1(float &p, float &g, float &m, float &v, const AdamConst &h) {
-    const float gr = g * h.grad_scale;
-    m = m + h.w1 * (gr - m);                            // torch lerp(m, g, w) for w < 0.5
-    v = h.beta2 * v + h.w2 * gr * gr;
-    const float denom = sqrtf(v) * h.inv_bc2_sqrt + h.eps;
-    p -= h.step_size * __fdividef(m, denom);          // 2-ulp division: the update is <= lr, its error ~1e-10
-}
 
 // n4 = number of float4 groups; elements [0, split) use group 0, [split, n) group 1.  split % 4 == 0 is required
 // when vectorised (the launcher checks).
@@ -187,9 +167,28 @@ k_l2_gather(const float2 *__restrict__ buf, uint32_t mask, uint32_t per_thread, 
     }
     if (acc == 123456.789f) *sink = acc;
 }
+// plain float4 copy, 4 groups in flight per thread: dst / src may be peer mappings (NVLink pull or push)
+__global__ void __launch_bounds__(256)
+k_stream_copy(float4 *__restrict__ dst, const float4 *__restrict__ src, uint64_t n4) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 a = __ldcg(src + i), b = __ldcg(src + i + stride), c = __ldcg(src + i + 2 * stride), d = __ldcg(src + i + 3 * stride);
+        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < n4; i += stride) dst[i] = __ldcg(src + i);
+}
 }  // namespace
 
 extern "C" {
+// SM-issued copy of `bytes` (16-byte aligned) on `ctas` CTAs of 256 threads; with one side a peer mapping this measures
+// what NVLink gives loads (pull) or stores (push) issued by SMs -- the roofline of the peer-memory update kernel
+int nb200_stream_copy_probe(void *dst, const void *src, uint64_t bytes, uint32_t ctas, void *stream) {
+    if (!dst || !src || (bytes & 15u) || ctas == 0) return NB200_E_BAD_ARG;
+    k_stream_copy<<<ctas, 256, 0, nb_stream(stream)>>>((float4 *)dst, (const float4 *)src, bytes / 16);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
 // streams `bytes` (16-byte aligned, should fit the L2) `reps` times; returns after enqueueing.  bytes_moved = bytes * reps
 int nb200_l2_stream_probe(const void *buf, uint64_t bytes, uint32_t reps, float *sink, void *stream) {
     if (!buf || !sink || (bytes & 15u)) return NB200_E_BAD_ARG;

@@ -62,14 +62,23 @@ class TrainPlan(C.Structure):
                 [(n, C.c_void_p) for n in _ptr0] + [(n, C.c_float) for n in _f32b] + [(n, C.c_void_p) for n in _ptr])
 
 
-def flatten_parameters(model):
+def flat_parameter_count(model):
+    return (model.pos_en.embeddings.numel() + model.network.params.numel() + model.density_network.params.numel() +
+            model.rgb_network.params.numel())
+
+
+def flatten_parameters(model, flat=None):
     """Move the four parameter tensors of ``model`` (NeRFNetwork) into one flat fp32 vector
-    [table | trunk | density | rgb]; the Parameters become views.  Returns (flat, [(name, offset, numel)])."""
+    [table | trunk | density | rgb] (``flat``: use this buffer, e.g. peer-visible memory); the Parameters become views.
+    Returns (flat, [(name, offset, numel)])."""
     named = [("pos_en.embeddings", model.pos_en.embeddings), ("network.params", model.network.params),
              ("density_network.params", model.density_network.params), ("rgb_network.params", model.rgb_network.params)]
     total = sum(p.numel() for _, p in named)
     dev = named[0][1].device
-    flat = torch.empty(total, dtype=torch.float32, device=dev)
+    if flat is None:
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+    elif flat.numel() != total or flat.dtype != torch.float32 or flat.device != dev:
+        raise RuntimeError("flatten_parameters: the buffer must be fp32 [%d] on %s" % (total, dev))
     layout, off = [], 0
     for name, p in named:
         n = p.numel()
@@ -85,7 +94,8 @@ def flatten_parameters(model):
 class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
-                 lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0):
+                 lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0,
+                 peer=None):
         if not model.cuda_ray:
             raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
@@ -102,6 +112,13 @@ class FusedTrainStep:
         # Adam sweep of piece i runs while piece i+1 is still on the wire (replaces grad_sync)
         self.allreduce_chunks = int(allreduce_chunks)
         self.process_group = process_group
+        # peer (parallel.PeerMemory): parameters and gradient live in NVLink peer-visible memory and the update of the
+        # sharded step is ONE kernel (csrc/peer_update.cu): every rank reduces and Adam-updates the slice it owns straight
+        # out of the peers' gradients and stores the new parameters into every replica.  Replaces grad_sync (no NCCL call
+        # in the step); the moments of slices a rank does not own stay untouched on that rank.
+        self.peer = peer
+        if peer is not None and (grad_sync is not None or allreduce_chunks > 1):
+            raise RuntimeError("FusedTrainStep: peer replaces grad_sync / allreduce_chunks")
         # pipeline_update: the optimiser update of step k (all-reduce, Adam, weight re-pack) runs on a second stream
         # CONCURRENTLY with the ray march of step k + 1, which reads nothing the update writes -- a memory-bound sweep next
         # to an issue-bound traversal, and at N > 1 the all-reduce hides behind the march.  The parameters then lag one
@@ -121,8 +138,8 @@ class FusedTrainStep:
         model.train()
 
         dev = self.dev
-        self.params_flat, self.layout = flatten_parameters(model)
-        self.grads_flat = torch.zeros_like(self.params_flat)
+        self.params_flat, self.layout = flatten_parameters(model, None if peer is None else peer.params)
+        self.grads_flat = torch.zeros_like(self.params_flat) if peer is None else peer.grads.zero_()
         self.exp_avg = torch.zeros_like(self.params_flat)
         self.exp_avg_sq = torch.zeros_like(self.params_flat)
         self.hyper = torch.zeros(16, dtype=torch.float32, device=dev)
@@ -154,9 +171,12 @@ class FusedTrainStep:
         self.g_weights_sum = torch.zeros(N, **f32)
         self.rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
         self.scratch = torch.empty(int(self.lib.nb200_march_scratch_ints(L.u32(N))), dtype=torch.int32, device=dev)
-        # [counter0, counter1, m_eff, loss bits]: one 16-byte D2H returns everything the host wants to know
-        self.stats = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.stats_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        # [counter0, counter1, m_eff, loss bits, peer-update status, 3 spare]: one 32-byte D2H returns everything the host
+        # wants to know
+        self.stats = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.stats_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self.peer_plan = None if peer is None else peer.plan(self.layout[0][2], self.exp_avg, self.exp_avg_sq, self.hyper,
+                                                             status=self.stats[4:5])
         self.n_total = N * world_size
         self._pack()
         self.m_cap = 0
@@ -257,6 +277,9 @@ class FusedTrainStep:
         if self.allreduce_chunks > 1:
             self._pipelined_allreduce_update(st)
         else:
+            if self.peer_plan is not None:
+                _check(self.lib.nb200_train_update_peer(C.byref(self.plan), C.byref(self.peer_plan), st), "train_update_peer")
+                return
             if self.grad_sync is not None:
                 self.grad_sync(self.grads_flat)
             _check(self.lib.nb200_train_update(C.byref(self.plan), st), "train_update")
@@ -428,6 +451,9 @@ class FusedTrainStep:
         s = self.stats_host
         loss = float(s[3:4].view(torch.float32)[0])
         samples, used = int(s[0]), int(s[2])
+        if int(s[4]):
+            raise RuntimeError("FusedTrainStep: the peer-memory update timed out waiting for another rank (status %d): "
+                               "a rank left the job or launched fewer steps" % int(s[4]))
         if samples > self.m_cap:
             self.overflows += 1
             self._alloc_samples(self._round_cap(samples))

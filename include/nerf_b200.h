@@ -315,11 +315,60 @@ int nb200_train_phase(const nb200_train_plan *plan, int phases, void *stream);
 /* fused Adam over params_flat (zeroing grads_flat) and re-pack of the MLP operand images. */
 int nb200_train_update(const nb200_train_plan *plan, void *stream);
 
+/* ============================================================================================
+ * Multi-GPU optimiser update over NVLink peer memory ("one all-reduce(sum) per step over a flat
+ * buffer ... then identical optimizer step on every rank"; reference anchors: the DDP wrap of nerf/utils_init_nerf.py:
+ * 76-78 and torch.optim.Adam of main.py:182).  One kernel replaces all-reduce + Adam: rank r owns slice r of the flat
+ * parameter vector, reads slice r of every rank's gradient out of the peers' memory, sums in rank order, runs Adam on
+ * the slice (moments are only kept where they are owned) and stores the new parameters into every replica; the local
+ * gradient is reset once the peers have read it.  csrc/peer_update.cu describes the flag barriers.
+ *
+ * Peer-visible memory: cudaIpc handles exist only for whole cudaMalloc allocations, so -- the one exception to "nothing
+ * here allocates" -- nb200_peer_alloc returns such an allocation (zero-filled) on the current device; export its handle
+ * (nb200_peer_handle_bytes() bytes of HOST memory), ship it to the other processes by any means, import there.
+ * ========================================================================================== */
+#define NB200_PEER_MAX 8
+typedef struct nb200_peer_plan {
+    uint32_t world, rank;
+    uint32_t grid;                        /* CTAs: nb200_peer_grid(n, world, sms) -- identical on every rank */
+    uint32_t pad;
+    uint64_t n, split;                    /* parameters; [0, split) hyper group 0, [split, n) group 1; both % 4 == 0 */
+    float *params[NB200_PEER_MAX];        /* every rank's parameter vector  ([rank] local, the others imported) */
+    float *grads[NB200_PEER_MAX];         /* every rank's gradient vector */
+    uint32_t *signals[NB200_PEER_MAX];    /* every rank's flag words, nb200_peer_signal_bytes(grid) each, zero-filled */
+    float *exp_avg, *exp_avg_sq;          /* local, indexed like params; only this rank's slice is touched */
+    const float *hyper;                   /* as nb200_fused_adam */
+    uint32_t *epoch;                      /* local u32 [grid], zero-filled before the first call */
+    uint32_t *status;                     /* local u32: set non-zero when a barrier timed out (a peer is gone) */
+    float *mc_params, *mc_grads;          /* NVSwitch multicast mappings of the same two vectors (both or neither; NULL:
+                                             plain peer loads / stores): multimem.ld_reduce sums the gradient inside the
+                                             switch, multimem.st delivers the parameters to every replica */
+} nb200_peer_plan;
+uint32_t nb200_peer_plan_bytes(void);
+uint32_t nb200_peer_handle_bytes(void);
+uint64_t nb200_peer_signal_bytes(uint32_t grid);
+uint32_t nb200_peer_grid(uint64_t n, uint32_t world, uint32_t sms);
+/* elements [lo, hi) of the flat vector that `rank` owns (host arithmetic only) */
+void nb200_peer_slice(uint64_t n, uint32_t world, uint32_t rank, uint64_t *lo, uint64_t *hi);
+int nb200_peer_alloc(void **ptr, uint64_t bytes);
+int nb200_peer_free(void *ptr);
+int nb200_peer_export(void *ptr, void *handle);
+int nb200_peer_import(const void *handle, void **ptr);
+int nb200_peer_release(void *ptr);
+/* Every rank must call this the same number of times (a CUDA-graph replay counts); world == 1 degenerates to
+ * nb200_fused_adam with zero_grad. */
+int nb200_peer_reduce_adam_bcast(const nb200_peer_plan *plan, void *stream);
+/* nb200_train_update with the Adam sweep replaced by nb200_peer_reduce_adam_bcast. */
+int nb200_train_update_peer(const nb200_train_plan *plan, const nb200_peer_plan *peer, void *stream);
+
 /* L2 bandwidth probes (measurement aid, no reference counterpart): MEASURED_PEAKS.json carries no L2 figure, so bench.py
  * measures (a) a coalesced float4 stream over an L2-resident buffer and (b) random 8-byte gathers (one 32-byte sector
  * each, the access pattern of a hashed grid level) and reports the encoder's rates next to them. */
 int nb200_l2_stream_probe(const void *buf, uint64_t bytes, uint32_t reps, float *sink, void *stream);
 int nb200_l2_gather_probe(const void *buf, uint32_t words, uint32_t n_threads, uint32_t per_thread, float *sink, void *stream);
+/* SM-issued float4 copy on `ctas` CTAs; with one side a peer mapping (nb200_peer_import) it measures the NVLink rate
+ * available to loads (pull) / stores (push) from kernels: the roofline of nb200_peer_reduce_adam_bcast. */
+int nb200_stream_copy_probe(void *dst, const void *src, uint64_t bytes, uint32_t ctas, void *stream);
 
 /* ============================================================================================
  * tensor-core path self test (no reference counterpart): one-CTA tcgen05 GEMM D[128,N] = A[128,K] * B[N,K]^T with

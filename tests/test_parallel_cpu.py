@@ -74,3 +74,69 @@ def test_shard_rays_partitions():
             parts = [parallel.shard_rays(n, r, w, mode) for r in range(w)]
             allidx = torch.cat(parts).sort().values
             assert torch.equal(allidx, torch.arange(n)), (n, w, mode)
+
+
+def test_peer_slices_partition_and_match_the_library():
+    """parallel.peer_slice == nb200_peer_slice (host arithmetic of csrc/peer_update.cu); slices tile [0, n)"""
+    import ctypes as C
+    from customnerf_b200 import parallel, _lib
+    lib = _lib.lib()
+    lib.nb200_peer_grid.restype = C.c_uint32
+    for n in (12262256, 4, 8, 1000036, 79250560 + 22528):
+        for w in range(1, 9):
+            end = 0
+            for r in range(w):
+                lo, hi = C.c_uint64(), C.c_uint64()
+                lib.nb200_peer_slice(C.c_uint64(n), C.c_uint32(w), C.c_uint32(r), C.byref(lo), C.byref(hi))
+                assert (lo.value, hi.value) == parallel.peer_slice(n, w, r)
+                assert lo.value == end and hi.value >= lo.value and lo.value % 4 == 0
+                end = hi.value
+            assert end == n
+            g = lib.nb200_peer_grid(C.c_uint64(n), C.c_uint32(w), C.c_uint32(148))
+            assert 1 <= g <= 148 * 8
+
+
+def _peer_schedule_worker(rank, world, port, out_dir):
+    """the schedule of k_peer_reduce_adam_bcast restated with gloo: owner sums slice r of every rank's gradient in rank
+    order, Adam on the slice, new parameters to every replica == all-reduce + Adam on every rank"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from customnerf_b200 import parallel
+    parallel.init_from_env(backend="gloo")
+    n = 1036
+    g0 = torch.Generator().manual_seed(1)
+    p_repl = torch.randn(n, generator=g0)
+    p_ref = p_repl.clone().requires_grad_()
+    opt = torch.optim.Adam([p_ref], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    lo, hi = parallel.peer_slice(n, world, rank)
+    m, v = torch.zeros(n), torch.zeros(n)
+    gr = torch.Generator().manual_seed(10 + rank)
+    for t in range(1, 4):
+        grad = torch.randn(n, generator=gr)
+        # reference: all-reduce + Adam everywhere
+        total = grad.clone()
+        dist.all_reduce(total)
+        p_ref.grad = total
+        opt.step()
+        # peer schedule: every rank exposes its gradient; the owner reduces its slice in rank order
+        everyone = [torch.zeros(n) for _ in range(world)]
+        dist.all_gather(everyone, grad)
+        gs = sum(e[lo:hi] for e in everyone[1:]) + everyone[0][lo:hi] if world > 1 else everyone[0][lo:hi]
+        m[lo:hi] = m[lo:hi] + 0.1 * (gs - m[lo:hi])
+        v[lo:hi] = 0.99 * v[lo:hi] + 0.01 * gs * gs
+        new = p_repl[lo:hi] - (1e-2 / (1 - 0.9 ** t)) * m[lo:hi] / (v[lo:hi].sqrt() / (1 - 0.99 ** t) ** 0.5 + 1e-15)
+        # broadcast: slices may be ragged, so ship (lo, hi, values)
+        parts = [None] * world
+        dist.all_gather_object(parts, (lo, hi, new))
+        for a, b, vals in parts:
+            p_repl[a:b] = vals
+        np.testing.assert_allclose(p_repl.numpy(), p_ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+    assert float(m[:lo].abs().sum()) == 0.0 and float(m[hi:].abs().sum()) == 0.0     # moments only where owned
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_peer_update_schedule_equals_allreduce_plus_adam(tmp_path):
+    port = _free_port()
+    mp.spawn(_peer_schedule_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
