@@ -7,8 +7,9 @@
 Workload (BASELINE.json configs[1]): single-B200 reconstruction step at train_resolution_level 7 -- one 142 x 105
 image (14 910 rays) of the synthetic bear scene, bound 2, 128^3 x 2 occupancy grid, ~270 k samples per step,
 16-level hash grid (2^19, F=2) + 64-wide MLPs, occupancy (cuda_ray) path, fp16 autocast, Adam.
-With N GPUs every rank renders its own view of the scene (weak scaling) and the gradients of the hash table and
-the MLPs are all-reduced once per step (NCCL).
+With N GPUs every rank renders its own view of the scene (weak scaling); the gradients of the hash table and the MLPs
+are summed and the optimiser step taken by ONE kernel over NVLink peer memory (csrc/peer_update.cu; --update nccl: NCCL
+all-reduce + Adam instead).  --config 4 runs BASELINE.json configs[4] (2^22 table, 1 M rays per step) the same way.
 
 A "step" = one full train step over one image: near/far -> march -> encode -> MLP -> composite -> loss ->
 backward (composite, MLP, encode scatter) -> Adam, replayed as one CUDA graph (customnerf_b200/fused_trainer.py).
@@ -279,10 +280,28 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     L.lib()   # fail loudly if the native library is missing
 
-    model = trainer.build_scene_model(dev, opt=trainer.make_opt(train_conf=TRAIN_CONF))
-    o, d = syn.camera_rays(IMG_H, IMG_W, view=rank)           # weak scaling: one image per rank
-    target = syn.bear_color(o + d * 1.5)
-    gt_mask = silhouette(o, d)
+    workload, scaling = WORKLOAD, "weak"
+    if args.config == 4:
+        # BASELINE.json configs[4] (not the driver's line): 2^22 table, 1 M random rays per step -- sharded over the ranks
+        # (strong scaling, as the config words it) or, with --weak, 1 M rays on EVERY rank
+        model = trainer.build_scene_model(dev, log2_hashmap_size=22, opt=trainer.make_opt(train_conf=TRAIN_CONF))
+        total = 1 << 20
+        if args.weak:
+            o, d = syn.random_rays(total, seed=2 + rank)
+        else:
+            o, d = syn.random_rays(total, seed=2)
+            idx = parallel.shard_rays(total, rank, world)
+            o, d, scaling = o[idx].contiguous(), d[idx].contiguous(), "strong"
+        target = syn.bear_color(o + d * 1.5)
+        gt_mask = torch.cat([silhouette(o[i:i + 65536], d[i:i + 65536]) for i in range(0, o.shape[0], 65536)])
+        workload = "configs[4]: 2^22 hash table, %d random rays per %s, bear scene, bound 2, 128^3x2 occupancy grid, L16 F2, " \
+                   "64-wide MLPs (rgb + mask head), cuda_ray path, fp16 autocast, loss MSE(rgb) + 0.01 MSE(mask), Adam" \
+                   % (total, "rank and step" if args.weak else "step, sharded over the ranks")
+    else:
+        model = trainer.build_scene_model(dev, opt=trainer.make_opt(train_conf=TRAIN_CONF))
+        o, d = syn.camera_rays(IMG_H, IMG_W, view=rank)           # weak scaling: one image per rank
+        target = syn.bear_color(o + d * 1.5)
+        gt_mask = silhouette(o, d)
     n_rays = o.shape[0]
     # N > 1, default: the update is ONE kernel over NVLink peer memory (csrc/peer_update.cu: every rank reduces + Adam-
     # updates the slice it owns out of the peers' gradients and stores the new parameters into every replica) -- no NCCL
@@ -370,8 +389,8 @@ def run_b200(args):
         total_rays = n_rays * world * args.steps
         line = {"metric": METRIC, "value": total_rays / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": n_rays, "parallelism": "ray-sharded dp%d" % world,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": {"workload": workload, "rays_per_gpu_per_step": n_rays, "parallelism": "ray-sharded dp%d" % world,
                            "step": "one CUDA-graph replay: near/far, march, encode, field MLP, composite, MSE, backward, "
                                    "fused Adam" + (", NCCL all-reduce of the flat gradient" if sync is not None else "") +
                                    ("; update = one reduce + Adam + broadcast kernel over NVLink peer memory%s (no NCCL call "
@@ -441,6 +460,9 @@ def main():
     ap.add_argument("--update", default="peer", choices=["peer", "nvls", "nccl"],
                     help="N > 1: optimiser update as one NVLink peer-memory kernel (peer: P2P loads / stores, default; nvls: "
                          "through the NVSwitch multicast mapping, reduced in the switch) or NCCL all-reduce + Adam")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 4],
+                    help="BASELINE.json configs[] index: 1 = the bench line (default); 4 = 2^22 table, 1 M rays per step")
+    ap.add_argument("--weak", action="store_true", help="--config 4: 1 M rays on every rank instead of 1 M sharded over the ranks")
     ap.add_argument("--peer-at-1", action="store_true", help="N = 1: run the update through the peer-memory kernel too (tuning)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (kernel tuning runs)")
     ap.add_argument("--no-breakdown", action="store_true",
