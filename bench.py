@@ -280,7 +280,7 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     L.lib()   # fail loudly if the native library is missing
 
-    workload, scaling = WORKLOAD, "weak"
+    workload, scaling, raygen, cam_pose = WORKLOAD, "weak", None, None
     if args.config == 4:
         # BASELINE.json configs[4] (not the driver's line): 2^22 table, 1 M random rays per step -- sharded over the ranks
         # (strong scaling, as the config words it) or, with --weak, 1 M rays on EVERY rank
@@ -302,6 +302,8 @@ def run_b200(args):
         o, d = syn.camera_rays(IMG_H, IMG_W, view=rank)           # weak scaling: one image per rank
         target = syn.bear_color(o + d * 1.5)
         gt_mask = silhouette(o, d)
+        cam_pose, cam_intr = syn.camera_pose(IMG_H, IMG_W, view=rank)      # the same camera in the loader's terms
+        raygen = dict(H=IMG_H, W=IMG_W, intrinsics=cam_intr)
     n_rays = o.shape[0]
     # N > 1, default: the update is ONE kernel over NVLink peer memory (csrc/peer_update.cu: every rank reduces + Adam-
     # updates the slice it owns out of the peers' gradients and stores the new parameters into every replica) -- no NCCL
@@ -313,7 +315,7 @@ def run_b200(args):
     elif world > 1:
         sync = (lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM))
     fs = fused_trainer.FusedTrainStep(model, n_rays, lr=5e-4, world_size=world, grad_sync=sync, use_graph=not args.no_graph,
-                                      pipeline_update=not args.no_pipeline, mask_weight=TRAIN_CONF, peer=peer)
+                                      pipeline_update=not args.no_pipeline, mask_weight=TRAIN_CONF, peer=peer, raygen=raygen)
     fs.target_mask.copy_(gt_mask)     # [N] ground-truth mask: resident (59 KB; not part of the per-step H2D count)
     # the batch is handed over the way a loader would: written into the trainer's pinned staging buffer, from where each
     # step's graph copies it to the device (one H2D node of 537 KB inside the timed step)
@@ -326,13 +328,20 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if raygen is not None:
+        p_h, _ = fs.pinned_pose_batch()
+        p_h.copy_(cam_pose)
+
     def timed(n_steps, host_inputs):
         evs = []
         for _ in range(n_steps):
             flush.zero_()                                      # L2 flush, outside the per-step event pair
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            if host_inputs:
+            if host_inputs == "pose":
+                fs.step(pose=p_h, target=t_h)                  # H2D of pose + target pixels, rays generated in the step
+                fs.last_stats()
+            elif host_inputs:
                 fs.step(o_h, d_h, t_h)                         # H2D of the batch (pinned) + the step
                 fs.last_stats()                                # D2H read of loss / sample count (32 B) + sync
             else:
@@ -357,6 +366,13 @@ def run_b200(args):
     barrier()
     sec_e2e = timed(args.steps, host_inputs=True)
     barrier()
+    sec_pose = None
+    if raygen is not None:
+        fs.step(pose=p_h, target=t_h)                          # captures the pose-driven graph
+        fs.last_stats()
+        barrier()
+        sec_pose = timed(args.steps, host_inputs="pose")
+        barrier()
     clk = clocks.stop() if rank == 0 else None
     loss, samples, used = fs.last_stats()
     update_us = None
@@ -376,9 +392,10 @@ def run_b200(args):
             eb.record()
             torch.cuda.synchronize()
         update_us = ea.elapsed_time(eb) / reps * 1e3
-        t = torch.tensor([sec, sec_e2e, update_us], device=dev, dtype=torch.float64)
+        t = torch.tensor([sec, sec_e2e, update_us, sec_pose or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec, sec_e2e, update_us = float(t[0]), float(t[1]), float(t[2])
+        sec_pose = float(t[3]) if sec_pose is not None else None
 
     if rank == 0:
         peaks = {}
@@ -407,6 +424,13 @@ def run_b200(args):
                         "api": "FusedTrainStep.step(*fs.pinned_batch()) (batch in the pinned staging buffer, one H2D copy node "
                                "at the head of the step's graph) + last_stats() (32-byte D2H + sync)"},
                 "gpu_launches": int(launches), "clocks": clk, "samples_per_step": samples, "final_loss": loss}
+        if sec_pose is not None:
+            # the same end-to-end step fed the way the reference's loader feeds it (provider.py:344-470 hands the trainer a
+            # pose; get_rays runs on the device): host inputs = 64 B of pose + the target pixels, rays generated by the
+            # first kernel of the step's graph (csrc/raygen.cu)
+            line["e2e_from_pose"] = {"value": total_rays / sec_pose, "unit": UNIT, "h2d_bytes_per_step": int(64 + n_rays * 3 * 4),
+                                     "d2h_bytes_per_step": 32, "ms_per_step": sec_pose / args.steps * 1e3,
+                                     "api": "FusedTrainStep.step(pose=, target=) with pinned_pose_batch() + last_stats()"}
         if update_us is not None:
             nb = fs.params_flat.numel() * 4
             wire = nb * (world - 1) / world          # bytes in (gradient slices read) = bytes out (parameters stored) per rank

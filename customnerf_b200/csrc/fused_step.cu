@@ -110,6 +110,40 @@ rest:
     return 0;
 }
 
+uint32_t nb200_lgie_plan_bytes(void) { return (uint32_t)sizeof(nb200_lgie_plan); }
+
+int nb200_train_lgie_forward(const nb200_train_plan *p, const nb200_lgie_plan *g, void *stream) {
+    if (!p || !g || !g->weights_sum || !g->depth || !g->image || !g->render_mask) return NB200_E_BAD_ARG;
+    int rc;
+    if ((rc = nb200_train_phase(p, NB200_PHASE_MARCH, stream))) return rc;
+    if ((rc = nb200_fs_encode_forward(p->xyzs, p->bound, p->table, p->offsets, p->x_en, p->M_cap, p->L, p->S, p->base_res,
+                                      p->gridtype, 0, 0, p->m_eff, stream))) return rc;
+    if ((rc = nb200_field_forward(p->x_en, p->xyzs, p->dirs, p->w_fwd, p->sigma, p->sigma_arg, p->rgba, p->act, p->M_cap,
+                                  p->m_eff, stream))) return rc;
+    const size_t N = p->N;
+    for (int v = 0; v < 3; v++)
+        if ((rc = nb200_fs_composite_lgie_forward(v, p->sigma, p->rgba, p->deltas, p->rays, p->M_cap, p->N, p->T_thresh,
+                                                  g->conf_thr, g->soft_mask, g->weights_sum + v * N, g->depth + v * N,
+                                                  g->image + v * N * 3, g->render_mask + v * N, stream))) return rc;
+    return 0;
+}
+
+int nb200_train_lgie_backward(const nb200_train_plan *p, const nb200_lgie_plan *g, void *stream) {
+    if (!p || !g || !g->g_weights_sum || !g->g_image || !g->g_render_mask) return NB200_E_BAD_ARG;
+    int rc;
+    const size_t N = p->N;
+    for (int v = 0; v < 3; v++)
+        if ((rc = nb200_fs_composite_lgie_backward(v, g->g_weights_sum + v * N, g->g_image + v * N * 3, g->g_render_mask + v * N,
+                                                   p->sigma, p->rgba, p->deltas, p->rays, g->weights_sum + v * N,
+                                                   g->image + v * N * 3, g->render_mask + v * N, p->M_cap, p->N, p->T_thresh,
+                                                   g->conf_thr, g->soft_mask, g->detach_bg, g->detach_mask_from_field,
+                                                   p->d_sigma, p->d_rgba, stream))) return rc;
+    if ((rc = nb200_field_backward(p->d_sigma, p->d_rgba, p->sigma_arg, p->rgba, p->x_en, p->dirs, p->act, p->w_bwd,
+                                   p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, stream))) return rc;
+    return nb200_fs_encode_backward(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
+                                    p->base_res, p->gridtype, 0, 0, p->m_eff, stream);
+}
+
 int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
     return nb200_train_phase(p, NB200_PHASE_MARCH | NB200_PHASE_REST, stream);
 }

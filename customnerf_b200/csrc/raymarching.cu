@@ -775,11 +775,33 @@ struct MseArgs {
     const float *target_mask; float *render_mask, *g_render_mask; float mask_weight;
 };
 
-template <typename TC>
+// LGIE composites (the editing render of nerf/renderer.py:383-474, on the occupancy path: rendering._lgie_composites):
+// the same samples composited three times with the density gated by the mask head's output m (the 4th rgba channel):
+//   V = 0 "all": sigma;   V = 1 "fg": sigma * e(m);   V = 2 "bg": sigma * (1 - e(m))
+//   e = sigmoid((m - conf_thr) * 100) (soft_mask, :421-426) or [m > 0.5] (hard)
+// V = -1 is the plain composite (no gate; identical code to before the LGIE variants existed).
+struct LgieArgs { float thr; int soft, detach_bg, detach_mask, accumulate; };
+template <int V>
+__device__ __forceinline__ float lgie_gate(float m, const LgieArgs &a, float &dgate_dm) {
+    dgate_dm = 0.0f;
+    if constexpr (V <= 0) return 1.0f;
+    float e;
+    if (a.soft) {
+        e = 1.0f / (1.0f + expf(-(m - a.thr) * 100.0f));
+        dgate_dm = 100.0f * e * (1.0f - e);
+    } else {
+        e = m > 0.5f ? 1.0f : 0.0f;
+    }
+    if constexpr (V == 2) { dgate_dm = -dgate_dm; return 1.0f - e; }
+    return e;
+}
+
+template <typename TC, int V = -1>
 __global__ void __launch_bounds__(kCompBlock)
 k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ rgbs, const float *__restrict__ deltas,
                       const int32_t *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
-                      float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image, MseArgs mse) {
+                      float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image, MseArgs mse,
+                      LgieArgs lg = LgieArgs{}) {
     __shared__ float loss_part[kCompBlock / 32];
     const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
     const uint32_t lane = nb_lane();
@@ -809,6 +831,7 @@ k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ r
                 const float2 dl = __ldg(reinterpret_cast<const float2 *>(deltas) + s);
                 d0 = dl.x; d1 = dl.y;
                 ld_rgba<TC>(rgbs, s, c0, c1, c2, c3);
+                if constexpr (V > 0) { float dg; sigma *= lgie_gate<V>(c3, lg, dg); }
             }
             const float alpha = valid ? 1.0f - __expf(-sigma * d0) : 0.0f;
             const float pin = warp_incl_prod(1.0f - alpha);
@@ -859,14 +882,19 @@ k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ r
 }
 
 // GS = row stride of grad_rgbs: 3 (reference layout) or 4 (float4 rows [g_r, g_g, g_b, 0] for the field backward)
-template <typename TC, int GS>
+// V >= 0 (LGIE, GS == 4): contributions of variant V to the per-sample gradients -- d sigma = gs * gate * a,
+// d m = g_mask * w + gs * sigma * d gate / d m, d rgb = a * g_rgb, with a = [m >= 0.5] for the "all" variant under
+// detach_bg (background samples give values but no gradient to the global image, :409-418) and 1 otherwise;
+// detach_mask: the rendered mask's weights are detached (:460-463), so its term leaves gs.  accumulate: add to the rows.
+template <typename TC, int GS, int V = -1>
 __global__ void __launch_bounds__(kCompBlock)
 k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *__restrict__ grad_image,
                       const float *__restrict__ sigmas, const TC *__restrict__ rgbs, const float *__restrict__ deltas,
                       const int32_t *__restrict__ rays, const float *__restrict__ weights_sum,
                       const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
                       float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs,
-                      const float *__restrict__ grad_render_mask, const float *__restrict__ render_mask) {
+                      const float *__restrict__ grad_render_mask, const float *__restrict__ render_mask,
+                      LgieArgs lg = LgieArgs{}) {
     const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
     if (n >= N) return;
     const uint32_t lane = nb_lane();
@@ -889,10 +917,12 @@ k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *_
         float gs = 0, gr0 = 0, gr1 = 0, gr2 = 0, gr3 = 0;
         if (!done) {
             float sigma = 0, d0 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            [[maybe_unused]] float sigma_raw = 0, gate = 1.0f, dgate = 0.0f;
             if (valid) {
                 sigma = __ldg(sigmas + s);
                 d0 = __ldg(deltas + s * 2);
                 ld_rgba<TC>(rgbs, s, c0, c1, c2, c3);
+                if constexpr (V >= 0) { sigma_raw = sigma; gate = lgie_gate<V>(c3, lg, dgate); sigma *= gate; }
             }
             const float alpha = valid ? 1.0f - __expf(-sigma * d0) : 0.0f;
             const float pin = warp_incl_prod(1.0f - alpha);
@@ -910,8 +940,16 @@ k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *_
             if (has_m) m_i = m_c + warp_incl_sum(weight * c3);      // (warp-uniform branch)
             if (act) {
                 gr0 = gi0 * weight; gr1 = gi1 * weight; gr2 = gi2 * weight; gr3 = gm * weight;
+                float mask_term = gm * (T_after * c3 - (m_final - m_i));
+                if constexpr (V >= 0) { if (lg.detach_mask) mask_term = 0.0f; }
                 gs = d0 * (gi0 * (T_after * c0 - (r_final - r_i)) + gi1 * (T_after * c1 - (g_final - g_i)) +
-                           gi2 * (T_after * c2 - (b_final - b_i)) + gm * (T_after * c3 - (m_final - m_i)) + ws_term);   // :752-757
+                           gi2 * (T_after * c2 - (b_final - b_i)) + mask_term + ws_term);   // :752-757
+                if constexpr (V >= 0) {
+                    const float a = (V == 0 && lg.detach_bg && !(c3 >= 0.5f)) ? 0.0f : 1.0f;
+                    gr0 *= a; gr1 *= a; gr2 *= a;
+                    gr3 += gs * sigma_raw * dgate;
+                    gs *= gate * a;
+                }
             }
             if (term) done = true;
             T_carry = __shfl_sync(0xffffffffu, T_after, 31);
@@ -921,6 +959,12 @@ k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *_
             if (has_m) m_c = __shfl_sync(0xffffffffu, m_i, 31);
         }
         if (valid) {   // rows after the early-out get explicit zeros (raymarching.py:284-285 zero-fills instead)
+            if constexpr (V >= 0 && GS == 4) {
+                if (lg.accumulate) {      // the same lane owns row s in every variant's launch: a plain read-modify-write
+                    const float4 q = reinterpret_cast<const float4 *>(grad_rgbs)[s];
+                    gs += grad_sigmas[s]; gr0 += q.x; gr1 += q.y; gr2 += q.z; gr3 += q.w;
+                }
+            }
             grad_sigmas[s] = gs;
             if constexpr (GS == 4) {
                 reinterpret_cast<float4 *>(grad_rgbs)[s] = make_float4(gr0, gr1, gr2, gr3);
@@ -1333,6 +1377,47 @@ int nb200_fs_composite_backward(const float *grad_weights_sum, const float *grad
     k_composite_train_bwd<__half, 4><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
         grad_weights_sum, grad_image, sigmas, (const __half *)rgba, deltas, rays, weights_sum, image, M, N, T_thresh,
         grad_sigmas, grad_rgba, grad_render_mask, render_mask);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+// LGIE composites of the fused editing step: variant 0 = all, 1 = fg, 2 = bg (see LgieArgs).  Per-ray outputs of the
+// forward and per-ray gradient inputs of the backward are per variant; the backward of variant 0 writes the per-sample rows,
+// variants 1 and 2 accumulate into them (launch them in that order on one stream).
+int nb200_fs_composite_lgie_forward(int variant, const float *sigmas, const void *rgba, const float *deltas,
+                                    const int32_t *rays, uint32_t M, uint32_t N, float T_thresh, float conf_thr,
+                                    int soft_mask, float *weights_sum, float *depth, float *image, float *render_mask,
+                                    void *stream) {
+    if (N == 0) return 0;
+    if (!render_mask || variant < 0 || variant > 2) return NB200_E_BAD_ARG;
+    const MseArgs mse{nullptr, nullptr, nullptr, 0.0f, 0.0f, nullptr, render_mask, nullptr, 0.0f};
+    const LgieArgs lg{conf_thr, soft_mask, 0, 0, 0};
+    const uint32_t grid = nb_div_up((uint64_t)N * 32, kCompBlock);
+    cudaStream_t st = nb_stream(stream);
+#define NB_LGIE_FWD(V) k_composite_train_fwd<__half, V><<<grid, kCompBlock, 0, st>>>(sigmas, (const __half *)rgba, deltas, rays, \
+        M, N, T_thresh, weights_sum, depth, image, mse, lg)
+    if (variant == 0) NB_LGIE_FWD(0); else if (variant == 1) NB_LGIE_FWD(1); else NB_LGIE_FWD(2);
+#undef NB_LGIE_FWD
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_fs_composite_lgie_backward(int variant, const float *grad_weights_sum, const float *grad_image,
+                                     const float *grad_render_mask, const float *sigmas, const void *rgba,
+                                     const float *deltas, const int32_t *rays, const float *weights_sum, const float *image,
+                                     const float *render_mask, uint32_t M, uint32_t N, float T_thresh, float conf_thr,
+                                     int soft_mask, int detach_bg, int detach_mask_from_field, float *grad_sigmas,
+                                     float *grad_rgba, void *stream) {
+    if (N == 0) return 0;
+    if (!grad_render_mask || !render_mask || variant < 0 || variant > 2) return NB200_E_BAD_ARG;
+    const LgieArgs lg{conf_thr, soft_mask, detach_bg, detach_mask_from_field, variant != 0};
+    const uint32_t grid = nb_div_up((uint64_t)N * 32, kCompBlock);
+    cudaStream_t st = nb_stream(stream);
+#define NB_LGIE_BWD(V) k_composite_train_bwd<__half, 4, V><<<grid, kCompBlock, 0, st>>>(grad_weights_sum, grad_image, sigmas, \
+        (const __half *)rgba, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgba, grad_render_mask,    \
+        render_mask, lg)
+    if (variant == 0) NB_LGIE_BWD(0); else if (variant == 1) NB_LGIE_BWD(1); else NB_LGIE_BWD(2);
+#undef NB_LGIE_BWD
     NB_LAUNCH_CHECK();
     return 0;
 }

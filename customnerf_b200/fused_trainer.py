@@ -95,7 +95,7 @@ class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
                  lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0,
-                 peer=None):
+                 peer=None, raygen=None):
         if not model.cuda_ray:
             raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
@@ -117,6 +117,12 @@ class FusedTrainStep:
         # out of the peers' gradients and stores the new parameters into every replica.  Replaces grad_sync (no NCCL call
         # in the step); the moments of slices a rank does not own stay untouched on that rank.
         self.peer = peer
+        # raygen = dict(H=, W=, intrinsics=(fx, fy, cx, cy)) with H * W == n_rays: step(pose=, target=) takes the camera
+        # pose instead of rays -- the rays are generated by the first kernel of the step (csrc/raygen.cu, get_rays of
+        # nerf/provider_utils.py:238-302), so a step's host inputs are 64 B of pose + the target pixels
+        self.raygen = raygen
+        if raygen is not None and int(raygen["H"]) * int(raygen["W"]) != int(n_rays):
+            raise RuntimeError("FusedTrainStep: raygen H x W must equal n_rays")
         if peer is not None and (grad_sync is not None or allreduce_chunks > 1):
             raise RuntimeError("FusedTrainStep: peer replaces grad_sync / allreduce_chunks")
         # pipeline_update: the optimiser update of step k (all-reduce, Adam, weight re-pack) runs on a second stream
@@ -161,7 +167,9 @@ class FusedTrainStep:
         self.batch_dev = torch.zeros(3, N, 3, **f32)
         self.batch_host = torch.zeros(3, N, 3, dtype=torch.float32).pin_memory()
         self.rays_o, self.rays_d, self.target = self.batch_dev[0], self.batch_dev[1], self.batch_dev[2]
-        self.graph_staged = None
+        self.graph_staged = self.graph_pose = None
+        self.pose_dev = torch.zeros(4, 4, **f32)
+        self.pose_host = torch.zeros(4, 4, dtype=torch.float32).pin_memory()
         self.target_mask = torch.zeros(N, **f32)
         self.render_mask, self.g_render_mask = torch.zeros(N, **f32), torch.zeros(N, **f32)
         self.noises = torch.zeros(N, **f32)
@@ -192,7 +200,7 @@ class FusedTrainStep:
 
     def _alloc_samples(self, m_cap):
         dev = self.dev
-        self.graph = self.graph_staged = None
+        self.graph = self.graph_staged = self.graph_pose = None
         self.m_cap = m_cap
         if m_cap == 0:
             return
@@ -273,6 +281,26 @@ class FusedTrainStep:
         ``step(*pinned_batch())``: the step then starts with one H2D copy of the whole batch inside its graph."""
         return self.batch_host[0], self.batch_host[1], self.batch_host[2]
 
+    def pinned_pose_batch(self):
+        """(pose [4,4], target [N,3]): views of the pinned host staging buffers for ``step(pose=, target=)``"""
+        return self.pose_host, self.batch_host[2]
+
+    def _generate_rays(self):
+        r = self.raygen
+        fx, fy, cx, cy = [float(v) for v in r["intrinsics"]]
+        L.check(self.lib.nb200_get_rays(L.ptr(self.pose_dev), L.f32(fx), L.f32(fy), L.f32(cx), L.f32(cy), L.u32(int(r["H"])),
+                                        L.u32(int(r["W"])), L.u32(1), L.u32(self.N), L.ptr(None), L.f32(0.5), L.f32(0.5),
+                                        L.ptr(self.rays_o), L.ptr(self.rays_d), L.stream()), "get_rays")
+
+    def _stage(self, staged):
+        """host -> device copies (and ray generation) that head a staged step; staged: False | True (rays) | 'pose' """
+        if staged == "pose":
+            self.pose_dev.copy_(self.pose_host, non_blocking=True)
+            self.batch_dev[2].copy_(self.batch_host[2], non_blocking=True)
+            self._generate_rays()
+        elif staged:
+            self.batch_dev.copy_(self.batch_host, non_blocking=True)
+
     def _update(self, st):
         if self.allreduce_chunks > 1:
             self._pipelined_allreduce_update(st)
@@ -287,8 +315,7 @@ class FusedTrainStep:
     def _launch(self, staged=False):
         """every device-side action of one step, on the current stream (this is what the graph captures)"""
         st = L.stream()
-        if staged:
-            self.batch_dev.copy_(self.batch_host, non_blocking=True)
+        self._stage(staged)
         if self.perturb:
             self.noises.uniform_()
         if not self.pipeline_update:
@@ -353,7 +380,9 @@ class FusedTrainStep:
             # thread_local: NCCL's watchdog thread may touch the CUDA API while the all-reduce of a sharded step is captured
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._launch(staged)
-            if staged:
+            if staged == "pose":
+                self.graph_pose = g
+            elif staged:
                 self.graph_staged = g
             else:
                 self.graph = g
@@ -404,23 +433,41 @@ class FusedTrainStep:
         if target_mask is not None:
             self.target_mask.copy_(target_mask.reshape(-1), non_blocking=True)
 
-    def step(self, rays_o=None, rays_d=None, target=None, target_mask=None):
-        """One train step on the current stream.  Never synchronises; ``last_stats()`` reads the result back."""
+    def step(self, rays_o=None, rays_d=None, target=None, target_mask=None, pose=None):
+        """One train step on the current stream.  Never synchronises; ``last_stats()`` reads the result back.
+        ``pose`` (needs ``raygen``): camera-to-world [4,4] instead of rays; with the tensors of ``pinned_pose_batch()`` the
+        copies and the ray generation are nodes of the step's graph."""
         with torch.cuda.device(self.dev):
+            pose_staged = False
+            if pose is not None:
+                if self.raygen is None:
+                    raise RuntimeError("FusedTrainStep.step(pose=...): construct the step with raygen=dict(H, W, intrinsics)")
+                pose_staged = (not pose.is_cuda and pose.data_ptr() == self.pose_host.data_ptr() and target is not None
+                               and target.data_ptr() == self.batch_host[2].data_ptr())
+                if not pose_staged:
+                    self.pose_dev.copy_(pose.reshape(4, 4), non_blocking=True)
+                    if target is not None:
+                        self.target.copy_(target.reshape(-1, 3), non_blocking=True)
+                    self._generate_rays()
+                    L.LAUNCHES += 1
+                elif self.m_cap == 0:
+                    self._stage("pose")       # the capacity measurement below needs this camera's rays
+                rays_o = rays_d = target = None
             if self.m_cap == 0:
                 self._alloc_samples(self._round_cap(self.measure_samples(rays_o if rays_o is not None else self.rays_o,
                                                                          rays_d if rays_d is not None else self.rays_d)))
             # a batch handed over in the pinned staging buffer is copied by the graph itself (one H2D node)
             staged = (rays_o is not None and not rays_o.is_cuda and rays_o.data_ptr() == self.batch_host[0].data_ptr()
                       and rays_d.data_ptr() == self.batch_host[1].data_ptr() and target.data_ptr() == self.batch_host[2].data_ptr())
+            if pose_staged:
+                staged = "pose"
             if rays_o is not None and not staged:
                 self.set_batch(rays_o, rays_d, target, target_mask)
             elif target_mask is not None:
                 self.target_mask.copy_(target_mask.reshape(-1), non_blocking=True)
             if self.pipeline_update and not self._pending_update:
                 # first step of a pipelined run: nothing to update yet -- forward + backward only, launched directly
-                if staged:
-                    self.batch_dev.copy_(self.batch_host, non_blocking=True)
+                self._stage(staged)
                 if self.perturb:
                     self.noises.uniform_()
                 _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
@@ -428,7 +475,7 @@ class FusedTrainStep:
                 self._pending_update = True
                 L.LAUNCHES += KERNELS_PER_STEP - 4
                 return
-            have = self.graph_staged if staged else self.graph
+            have = self.graph_pose if staged == "pose" else self.graph_staged if staged else self.graph
             if self.use_graph and have is None:
                 try:
                     self._capture(staged)
@@ -436,13 +483,13 @@ class FusedTrainStep:
                     import warnings
                     warnings.warn("FusedTrainStep: CUDA-graph capture failed (%s); launching the step's kernels "
                                   "directly instead" % (e,))
-                    self.use_graph, self.graph, self.graph_staged = False, None, None
+                    self.use_graph, self.graph, self.graph_staged, self.graph_pose = False, None, None, None
                     torch.cuda.synchronize(self.dev)
             if self.use_graph:
-                (self.graph_staged if staged else self.graph).replay()
+                (self.graph_pose if staged == "pose" else self.graph_staged if staged else self.graph).replay()
             else:
                 self._launch(staged)
-            L.LAUNCHES += KERNELS_PER_STEP
+            L.LAUNCHES += KERNELS_PER_STEP + (1 if staged == "pose" else 0)
 
     def last_stats(self):
         """(loss, samples, rows_used) of the most recent step -- synchronises with the device.  Grows the sample

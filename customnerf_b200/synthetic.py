@@ -96,6 +96,24 @@ def camera_rays(H, W, n_views=1, radius=1.5, fov_deg=62.0, seed=0, view=0, devic
     return o.to(device), d.contiguous().to(device)
 
 
+def camera_pose(H, W, radius=1.5, fov_deg=62.0, seed=0, view=0):
+    """The camera of ``camera_rays`` in the loader's terms: (pose [4,4] cam2world fp32, (fx, fy, cx, cy)) such that
+    get_rays(pose, intrinsics, H, W) (nerf/provider_utils.py:238-302) yields the same rays."""
+    g = torch.Generator().manual_seed(seed + 7919 * view)
+    theta = float(torch.rand(1, generator=g)) * 2 * math.pi
+    phi = (float(torch.rand(1, generator=g)) - 0.5) * 0.8
+    eye = torch.tensor([radius * math.cos(phi) * math.sin(theta), radius * math.sin(phi),
+                        radius * math.cos(phi) * math.cos(theta)], dtype=torch.float32)
+    fwd = -eye / eye.norm()
+    right = torch.linalg.cross(fwd, torch.tensor([0.0, 1.0, 0.0]))
+    right = right / right.norm()
+    upv = torch.linalg.cross(right, fwd)
+    pose = torch.eye(4, dtype=torch.float32)
+    pose[:3, 0], pose[:3, 1], pose[:3, 2], pose[:3, 3] = right, -upv, fwd, eye
+    focal = 0.5 * W / math.tan(0.5 * math.radians(fov_deg))
+    return pose, (focal, focal, 0.5 * W, 0.5 * H)
+
+
 def random_rays(N, radius=1.5, seed=0, device='cpu'):
     """N rays from random points on the camera sphere towards random points of the unit ball (config C1/C5)."""
     g = torch.Generator().manual_seed(seed)

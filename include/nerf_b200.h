@@ -292,6 +292,39 @@ typedef struct nb200_train_plan {
     void *timer;                                                 /* nb200_stage_timer or NULL */
 } nb200_train_plan;
 
+/* ---- LGIE editing step (BASELINE.json configs[3]; reference: the fg / bg / all renders of NeRFRenderer.run,
+ * nerf/renderer.py:383-474, that Trainer_Nerf.train_step_editing consumes, utils_init_nerf.py:243-265).  The same samples
+ * are composited three times -- variant 0 "all": sigma; 1 "fg": sigma * e(m); 2 "bg": sigma * (1 - e(m)) -- with the
+ * mask head's output m (4th rgba channel) as the edit mask: e = sigmoid((m - conf_thr) * 100) (soft_mask) or [m > 0.5];
+ * every variant also renders its mask sum w * m.  detach_bg: samples with m < 0.5 give values but no gradient to the
+ * "all" render (:409-418); detach_mask_from_field: the rendered masks' weights carry no gradient (:460-463).
+ * Per-ray outputs / gradient inputs are laid out [3 variants][N ...].  The loss lives with the caller (the reference's is
+ * the Stable-Diffusion guidance, out of scope): run nb200_train_lgie_forward, write the gradients of the loss with respect
+ * to the rendered outputs into g_*, run nb200_train_lgie_backward, then nb200_train_update[_peer]. */
+typedef struct nb200_lgie_plan {
+    float conf_thr;
+    int32_t soft_mask, detach_bg, detach_mask_from_field;
+    float *weights_sum, *depth, *image, *render_mask;            /* [3,N], [3,N], [3,N,3], [3,N] */
+    const float *g_weights_sum, *g_image, *g_render_mask;        /* [3,N], [3,N,3], [3,N] (depth has no gradient,
+                                                                    raymarching.py:274-289) */
+} nb200_lgie_plan;
+int nb200_fs_composite_lgie_forward(int variant, const float *sigmas, const void *rgba, const float *deltas,
+                                    const int32_t *rays, uint32_t M, uint32_t N, float T_thresh, float conf_thr,
+                                    int soft_mask, float *weights_sum, float *depth, float *image, float *render_mask,
+                                    void *stream);
+/* variant 0 writes grad_sigmas / grad_rgba (float4 rows [g_r, g_g, g_b, g_m]); variants 1, 2 accumulate into them */
+int nb200_fs_composite_lgie_backward(int variant, const float *grad_weights_sum, const float *grad_image,
+                                     const float *grad_render_mask, const float *sigmas, const void *rgba,
+                                     const float *deltas, const int32_t *rays, const float *weights_sum, const float *image,
+                                     const float *render_mask, uint32_t M, uint32_t N, float T_thresh, float conf_thr,
+                                     int soft_mask, int detach_bg, int detach_mask_from_field, float *grad_sigmas,
+                                     float *grad_rgba, void *stream);
+/* near/far -> march -> encode -> field -> the three composites */
+int nb200_train_lgie_forward(const nb200_train_plan *plan, const nb200_lgie_plan *lgie, void *stream);
+/* the three composites^T (summed per sample) -> field^T -> encode^T; gradients accumulate into grads_flat */
+int nb200_train_lgie_backward(const nb200_train_plan *plan, const nb200_lgie_plan *lgie, void *stream);
+uint32_t nb200_lgie_plan_bytes(void);
+
 /* Per-stage device timing of a (non-captured) step: when plan->timer is set, nb200_train_forward_backward records an
  * event before its first kernel and after each of its NB200_FB_STAGES stages, nb200_train_update after each of its
  * NB200_UP_STAGES stages.  nb200_stage_timer_read synchronises on the last event and returns the stage durations in
@@ -314,6 +347,16 @@ int nb200_train_forward_backward(const nb200_train_plan *plan, void *stream);
 int nb200_train_phase(const nb200_train_plan *plan, int phases, void *stream);
 /* fused Adam over params_flat (zeroing grads_flat) and re-pack of the MLP operand images. */
 int nb200_train_update(const nb200_train_plan *plan, void *stream);
+
+/* ============================================================================================
+ * Ray generation.  Replaces the direction / origin arithmetic of get_rays
+ * (nerf/provider_utils.py:238-302; the index sampling of :263-284 stays with the caller):
+ *   pixel p = inds[b, n] (or n when inds == NULL, which requires N == H * W) -> i = p % W + off_x, j = p / W + off_y
+ *   dir = safe_normalize((i - cx) / fx, (j - cy) / fy, 1)  (:125-126, :289-293);  rays_d = R dir, rays_o = t  (:294-297)
+ * poses f32 [B, 4, 4] row-major camera-to-world (device); inds i64 [B, N] (device) or NULL; outputs f32 [B, N, 3].
+ * ========================================================================================== */
+int nb200_get_rays(const float *poses, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W, uint32_t B,
+                   uint32_t N, const int64_t *inds, float off_x, float off_y, float *rays_o, float *rays_d, void *stream);
 
 /* ============================================================================================
  * Multi-GPU optimiser update over NVLink peer memory ("one all-reduce(sum) per step over a flat

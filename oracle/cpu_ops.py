@@ -260,3 +260,24 @@ def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, we
         assert a.dtype == dt and a.flags["C_CONTIGUOUS"]
     lib().orc_composite_rays(u32(n_alive), u32(n_step), f32(T_thresh), _p(rays_alive), _p(rays_t), _p(_f32(sigmas)),
                              _p(_f32(rgbs)), _p(_f32(deltas)), _p(weights_sum), _p(depth), _p(image))
+
+
+def get_rays(poses, intrinsics, H, W, inds=None, offset=(0.5, 0.5)):
+    """numpy restatement of the direction / origin arithmetic of get_rays (nerf/provider_utils.py:238-302): pixel
+    (i, j) = (p % W + off_x, p // W + off_y) (:258-260), dir = safe_normalize((i - cx) / fx, (j - cy) / fy, 1)
+    (:125-126, :289-293), rays_d = dir @ R^T, rays_o = t (:294-297).  poses [B,4,4]; inds [B,N] int or None (all pixels).
+    Returns rays_o, rays_d [B,N,3] float32."""
+    poses = np.asarray(poses, np.float32)
+    B = poses.shape[0]
+    fx, fy, cx, cy = [np.float32(v) for v in intrinsics]
+    if inds is None:
+        inds = np.broadcast_to(np.arange(H * W, dtype=np.int64), (B, H * W))
+    inds = np.asarray(inds, np.int64)
+    i = (inds % W).astype(np.float32) + np.float32(offset[0])
+    j = (inds // W).astype(np.float32) + np.float32(offset[1])
+    xs, ys = (i - cx) / fx, (j - cy) / fy
+    d = np.stack([xs, ys, np.ones_like(xs)], -1)
+    d = d / np.sqrt(np.maximum((d * d).sum(-1, keepdims=True, dtype=np.float32), np.float32(1e-20)))
+    rays_d = np.einsum("bnc,bkc->bnk", d, poses[:, :3, :3]).astype(np.float32)
+    rays_o = np.broadcast_to(poses[:, None, :3, 3], rays_d.shape).astype(np.float32)
+    return np.ascontiguousarray(rays_o), np.ascontiguousarray(rays_d)

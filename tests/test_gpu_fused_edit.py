@@ -1,0 +1,111 @@
+"""-m gpu: the fused LGIE editing step (customnerf_b200/fused_edit.py, nb200_train_lgie_forward/backward, the gated
+composite kernels) against the autograd composition of the drop-in ops (NeRFRenderer.run_cuda + _lgie_composites, the
+occupancy-path form of nerf/renderer.py:383-474).
+
+Tolerances: rendered outputs rel 1e-4 (same kernels, fp32 compositing); loss rel 1e-4; parameter gradients within 1e-2 of
+the largest entry (fp16 activations, fp32 atomics in another order), as tests/test_gpu_fused_step.py.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+N_RAYS = 2048
+
+
+def _models(**flags):
+    from customnerf_b200 import trainer
+    opt = dict(train_conf=0.01, **flags)
+    a = trainer.build_scene_model(torch.device("cuda"), log2_hashmap_size=15, desired_resolution=512, seed=3, opt=trainer.make_opt(**opt))
+    b = trainer.build_scene_model(torch.device("cuda"), log2_hashmap_size=15, desired_resolution=512, seed=3, opt=trainer.make_opt(**opt))
+    with torch.no_grad():
+        a.pos_en.embeddings.uniform_(-0.5, 0.5)
+        b.pos_en.embeddings.copy_(a.pos_en.embeddings)
+        # a freshly initialised mask head sits just below 0.5 everywhere (empty foreground): widen its output row so that
+        # the edit mask splits the samples into a real foreground and a real background
+        for m in (a, b):
+            m.rgb_network.params[-16 * 64:].view(16, 64)[3] *= 12.0
+    return a, b
+
+
+def _batch():
+    from customnerf_b200 import synthetic as syn
+    o, d = syn.camera_rays(105, 142)
+    sel = torch.arange(5000, 5000 + N_RAYS)
+    o, d = o[sel].contiguous(), d[sel].contiguous()
+    tgt = syn.bear_color(o + d * 1.5).cuda()
+    return o.cuda(), d.cuda(), tgt, (tgt.mean(-1, keepdim=True) > 0.5).float()
+
+
+def _make_loss(tgt, gt_mask):
+    def loss_fn(out):        # touches every rendered output that carries a gradient
+        return (F.mse_loss(out["image"].reshape(-1, 3).float(), tgt) +
+                F.mse_loss(out["fg"]["image"].reshape(-1, 3).float(), tgt * gt_mask) +
+                F.mse_loss(out["bg"]["image"].reshape(-1, 3).float(), tgt * (1 - gt_mask)) +
+                0.5 * F.mse_loss(out["render_mask"].reshape(-1, 1).float(), gt_mask) +
+                0.25 * F.mse_loss(out["fg"]["render_mask"].reshape(-1, 1).float(), gt_mask) +
+                0.1 * (out["bg"]["weights_sum"].reshape(-1).float() ** 2).mean() +
+                0.1 * (out["weights_sum"].reshape(-1).float() - 1).abs().mean())
+    return loss_fn
+
+
+@pytest.mark.parametrize("flags", [dict(soft_mask=True, detach_bg=True), dict(soft_mask=False, detach_bg=False),
+                                   dict(soft_mask=True, detach_bg=False, detach_mask_from_field=True)])
+def test_edit_step_matches_autograd_composition(flags):
+    from customnerf_b200 import trainer, fused_edit
+    ma, mb = _models(**flags)
+    o, d, tgt, gt_mask = _batch()
+    loss_fn = _make_loss(tgt, gt_mask)
+    # reference-shaped path: autograd over the drop-in ops
+    ma.train()
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = ma.render(o[None], d[None], staged=False, perturb=False, force_all_rays=True, **vars(ma.opt))
+        loss_ref = loss_fn(out)
+    (loss_ref * trainer.LOSS_SCALE).backward()
+    # fused path
+    fs = fused_edit.FusedEditStep(mb, N_RAYS, loss_fn, perturb=False, use_graph=False)
+    fs._alloc_samples(fs._round_cap(fs.measure_samples(o, d)))
+    fs.set_batch(o, d, tgt)
+    fs.forward_backward()
+    loss, samples, used = fs.last_stats()
+    assert samples == used > 1000
+    got = fs.outputs()
+    for name, ref_d, got_d in (("all", out, got), ("fg", out["fg"], got["fg"]), ("bg", out["bg"], got["bg"])):
+        for key in ("image", "weights_sum", "depth", "render_mask"):
+            r, g = ref_d[key].detach().float().cpu().numpy().reshape(-1), got_d[key].cpu().numpy().reshape(-1)
+            assert np.abs(g - r).max() <= 1e-4 * max(1.0, np.abs(r).max()), (name, key, np.abs(g - r).max())
+    assert float(got["fg"]["weights_sum"].sum()) > 1.0 and float(got["bg"]["weights_sum"].sum()) > 1.0   # both non-trivial
+    assert abs(loss - float(loss_ref)) <= 1e-4 * abs(float(loss_ref)) + 1e-7
+    for name, off, n in fs.layout:
+        mod, attr = name.split(".")
+        g_ref = getattr(getattr(ma, mod), attr).grad.reshape(-1).float().cpu().numpy()
+        g = fs.grads_flat[off:off + n].cpu().numpy()
+        scale = np.abs(g_ref).max()
+        assert scale > 0
+        assert np.abs(g - g_ref).max() <= 1e-2 * scale, (flags, name, np.abs(g - g_ref).max(), scale)
+
+
+def test_edit_step_graph_replay_trains():
+    from customnerf_b200 import fused_edit
+    _, mb = _models(soft_mask=True, detach_bg=True)
+    _, mc = _models(soft_mask=True, detach_bg=True)
+    o, d, tgt, gt_mask = _batch()
+    loss_fn = _make_loss(tgt, gt_mask)
+    runs = {}
+    for graph, model in ((True, mb), (False, mc)):
+        fs = fused_edit.FusedEditStep(model, N_RAYS, loss_fn, perturb=False, use_graph=graph)
+        ls = []
+        for it in range(8):
+            fs.step(o, d, tgt)
+            ls.append(fs.last_stats()[0])
+        runs[graph] = ls
+    np.testing.assert_allclose(runs[True], runs[False], rtol=2e-3)     # replayed graph == direct launches
+    assert runs[True][-1] < runs[True][0]
+
+
+def test_edit_step_needs_the_mask_head():
+    from customnerf_b200 import trainer, fused_edit
+    model = trainer.build_scene_model(torch.device("cuda"), log2_hashmap_size=15, desired_resolution=512)
+    with pytest.raises(RuntimeError):
+        fused_edit.FusedEditStep(model, 128, lambda out: out["image"].sum())
