@@ -10,8 +10,9 @@ nerf/utils_init_nerf.py:194-241, 599-629), restructured for the B200:
   * no autograd graph, no allocator traffic: fixed buffers, the backward kernels are called directly
     (csrc/fused_step.cu: nb200_train_forward_backward / nb200_train_update);
   * one flat fp32 vector holds [hash table | trunk | density head | colour head]; the module's Parameters are views
-    into it, so state-dict names are unchanged and the gradient all-reduce of the ray-sharded
-    multi-GPU step is a single NCCL call on ``grads_flat``;
+    into it, so state-dict names are unchanged and the gradient exchange of the ray-sharded
+    multi-GPU step works on one buffer, ``grads_flat``: by default ONE kernel over NVLink peer memory that also takes the
+    optimiser step (``peer=``, csrc/peer_update.cu), or a single NCCL all-reduce (``grad_sync=``);
   * zero-grad + unscale + Adam are one pass over that vector (csrc/optim.cu) with the reference's hyper-parameters
     (Adam betas (0.9, 0.99), eps 1e-15, table at 10x LR: main.py:182, network_grid.py:196-206);
   * the whole sequence is captured once and replayed; per-step scalars (step count, learning rate, bias corrections)

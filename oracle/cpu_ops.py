@@ -281,3 +281,54 @@ def get_rays(poses, intrinsics, H, W, inds=None, offset=(0.5, 0.5)):
     rays_d = np.einsum("bnc,bkc->bnk", d, poses[:, :3, :3]).astype(np.float32)
     rays_o = np.broadcast_to(poses[:, None, :3, 3], rays_d.shape).astype(np.float32)
     return np.ascontiguousarray(rays_o), np.ascontiguousarray(rays_d)
+
+
+# ---- LGIE composites on the occupancy path ---------------------------------------------------------------------------
+def lgie_gate(m, variant, soft_mask, conf_thr):
+    """(gate, d gate / d m) of composite variant 0 all / 1 fg / 2 bg for mask values m [M]: the edit mask of
+    nerf/renderer.py:421-426 (soft: sigmoid((m - conf_thr) * 100); hard: m > 0.5) and its complement."""
+    m = _f32(m)
+    if variant == 0:
+        return np.ones_like(m), np.zeros_like(m)
+    if soft_mask:
+        e = (1.0 / (1.0 + np.exp(-(m.astype(np.float64) - conf_thr) * 100.0))).astype(np.float32)
+        de = np.float32(100.0) * e * (1 - e)
+    else:
+        e, de = (m > 0.5).astype(np.float32), np.zeros_like(m)
+    return (e, de) if variant == 1 else (1 - e, -de)
+
+
+def composite_lgie_forward(variant, sigmas, rgbs, masks, deltas, rays, T_thresh=1e-4, soft_mask=True, conf_thr=0.5):
+    """One LGIE render (nerf/renderer.py:383-474 on the occupancy path, composed as rendering._lgie_composites does):
+    the composite of raymarching.py:239-270 over sigma * gate, plus the rendered mask sum w * m (the same composite with the
+    mask as colour).  Returns weights_sum, depth, image [N,3], render_mask [N]."""
+    gate, _ = lgie_gate(masks, variant, soft_mask, conf_thr)
+    sv = _f32(sigmas) * gate
+    ws, depth, image = composite_rays_train_forward(sv, rgbs, deltas, rays, T_thresh)
+    m3 = np.repeat(_f32(masks).reshape(-1, 1), 3, axis=1)
+    _, _, mimg = composite_rays_train_forward(sv, m3, deltas, rays, T_thresh)
+    return ws, depth, image, np.ascontiguousarray(mimg[:, 0])
+
+
+def composite_lgie_backward(variant, g_ws, g_image, g_mask, sigmas, rgbs, masks, deltas, rays, T_thresh=1e-4, soft_mask=True,
+                            conf_thr=0.5, detach_bg=False, detach_mask_from_field=False):
+    """Gradients of one LGIE render with respect to (sigma [M], rgb [M,3], mask [M]) given the gradients of the loss with
+    respect to its weights_sum / image / render_mask: the backward of raymarching.py:272-289 applied to the colour composite
+    and to the mask composite, chained through the gate; detach_bg (:409-418) and detach_mask_from_field (:460-463) as in
+    rendering._lgie_composites."""
+    sig, m = _f32(sigmas), _f32(masks)
+    gate, dgate = lgie_gate(m, variant, soft_mask, conf_thr)
+    sv = sig * gate
+    ws, _, image = composite_rays_train_forward(sv, rgbs, deltas, rays, T_thresh)
+    gs_c, g_rgb = composite_rays_train_backward(g_ws, g_image, sv, rgbs, deltas, rays, ws, image, T_thresh)
+    m3 = np.repeat(m.reshape(-1, 1), 3, axis=1)
+    ws_m, _, mimg = composite_rays_train_forward(sv, m3, deltas, rays, T_thresh)
+    gm3 = np.zeros_like(_f32(g_image))
+    gm3[:, 0] = _f32(g_mask)
+    gs_m, g_m3 = composite_rays_train_backward(np.zeros_like(_f32(g_ws)), gm3, sv, m3, deltas, rays, ws_m, mimg, T_thresh)
+    gs = gs_c + (0.0 if detach_mask_from_field else 1.0) * gs_m            # gradient w.r.t. the gated density
+    a = (m >= 0.5).astype(np.float32) if (variant == 0 and detach_bg) else np.ones_like(m)
+    d_sigma = gs * gate * a
+    d_rgb = g_rgb * a[:, None]
+    d_mask = g_m3[:, 0] + gs * sig * dgate
+    return d_sigma, d_rgb, d_mask

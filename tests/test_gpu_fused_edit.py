@@ -109,3 +109,54 @@ def test_edit_step_needs_the_mask_head():
     model = trainer.build_scene_model(torch.device("cuda"), log2_hashmap_size=15, desired_resolution=512)
     with pytest.raises(RuntimeError):
         fused_edit.FusedEditStep(model, 128, lambda out: out["image"].sum())
+
+
+def test_gated_composite_kernels_match_the_cpu_oracle():
+    """nb200_fs_composite_lgie_forward / _backward (C ABI) against oracle.cpu_ops.composite_lgie_* on ragged rays
+    (empty rays, a ray longer than one warp trip, early termination at T_thresh): fp32 rel 1e-4; the three variants'
+    backward launches accumulate into one set of per-sample rows."""
+    import ctypes as C
+    from customnerf_b200 import _lib as L
+    from oracle import cpu_ops
+    lib = L.lib()
+    rng = np.random.RandomState(11)
+    counts = np.array([40, 0, 3, 97, 1, 64, 0, 33], np.int32)
+    N = counts.size
+    offs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int32)
+    order = rng.permutation(N).astype(np.int32)                         # rays rows in any order: column 0 is the ray id
+    rays = np.stack([np.arange(N, dtype=np.int32), offs, counts], 1)[order]
+    M = int(counts.sum())
+    sig = rng.uniform(0, 60, M).astype(np.float32)
+    sig[offs[3]:offs[3] + 30] = 400.0                                    # ray 3 saturates: T < 1e-4 inside the segment
+    rgba_h = np.concatenate([rng.uniform(0, 1, (M, 3)), np.clip(rng.normal(0.5, 0.02, (M, 1)), 0, 1)], 1).astype(np.float16)
+    rgb, msk = rgba_h[:, :3].astype(np.float32), rgba_h[:, 3].astype(np.float32)
+    dl = np.stack([rng.uniform(0.002, 0.01, M), rng.uniform(0.002, 0.01, M)], 1).astype(np.float32)
+    g_ws, g_img, g_m = (rng.randn(3, N).astype(np.float32), rng.randn(3, N, 3).astype(np.float32), rng.randn(3, N).astype(np.float32))
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d_sig, d_rgba_t, d_dl, d_rays = cu(sig), cu(rgba_h), cu(dl), cu(rays)
+    for soft, dbg, dmf in ((1, 1, 0), (0, 0, 0), (1, 0, 1)):
+        ws, dp, img, rm = (torch.zeros(3, N, device="cuda"), torch.zeros(3, N, device="cuda"),
+                           torch.zeros(3, N, 3, device="cuda"), torch.zeros(3, N, device="cuda"))
+        for v in range(3):
+            L.check(lib.nb200_fs_composite_lgie_forward(C.c_int(v), L.ptr(d_sig), L.ptr(d_rgba_t), L.ptr(d_dl), L.ptr(d_rays), L.u32(M),
+                                                        L.u32(N), L.f32(1e-4), L.f32(0.5), C.c_int(soft), L.ptr(ws[v]), L.ptr(dp[v]),
+                                                        L.ptr(img[v]), L.ptr(rm[v]), L.stream()), "lgie_fwd")
+        gs, grgba = torch.full((M,), 7.0, device="cuda"), torch.full((M, 4), 7.0, device="cuda")    # variant 0 must overwrite
+        t_gws, t_gimg, t_gm = cu(g_ws), cu(g_img), cu(g_m)
+        for v in range(3):
+            L.check(lib.nb200_fs_composite_lgie_backward(C.c_int(v), L.ptr(t_gws[v]), L.ptr(t_gimg[v]), L.ptr(t_gm[v]), L.ptr(d_sig),
+                                                         L.ptr(d_rgba_t), L.ptr(d_dl), L.ptr(d_rays), L.ptr(ws[v]), L.ptr(img[v]),
+                                                         L.ptr(rm[v]), L.u32(M), L.u32(N), L.f32(1e-4), L.f32(0.5), C.c_int(soft),
+                                                         C.c_int(dbg), C.c_int(dmf), L.ptr(gs), L.ptr(grgba), L.stream()), "lgie_bwd")
+        want_s, want_c, want_m = np.zeros(M, np.float32), np.zeros((M, 3), np.float32), np.zeros(M, np.float32)
+        for v in range(3):
+            o_ws, o_dp, o_img, o_rm = cpu_ops.composite_lgie_forward(v, sig, rgb, msk, dl, rays, 1e-4, bool(soft), 0.5)
+            for got, want, what in ((ws[v], o_ws, "weights_sum"), (dp[v], o_dp, "depth"), (img[v], o_img, "image"), (rm[v], o_rm, "render_mask")):
+                got = got.cpu().numpy()
+                assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), (v, soft, what, np.abs(got - want).max())
+            a, b, c = cpu_ops.composite_lgie_backward(v, g_ws[v], g_img[v], g_m[v], sig, rgb, msk, dl, rays, 1e-4, bool(soft), 0.5,
+                                                      bool(dbg), bool(dmf))
+            want_s += a; want_c += b; want_m += c
+        got_s, got_q = gs.cpu().numpy(), grgba.cpu().numpy()
+        for got, want, what in ((got_s, want_s, "d_sigma"), (got_q[:, :3], want_c, "d_rgb"), (got_q[:, 3], want_m, "d_mask")):
+            assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), (soft, dbg, dmf, what, np.abs(got - want).max())

@@ -389,3 +389,53 @@ def test_occupancy_renderer_and_grid_update_cpu(scene):
     res_e = net.render(o[None], d[None], perturb=False)
     # train and eval paths composite the same samples (T_thresh early-out aside)
     assert_close(res_e["image"].numpy(), res["image"].detach().numpy(), 1e-3, 2e-4, "train vs eval image")
+
+
+def test_lgie_oracle_matches_torch_autograd_of_the_same_composition():
+    """oracle.cpu_ops.composite_lgie_* (the checker of the gated composite kernels) against torch autograd through a
+    plain-torch restatement of the composite (weights = alpha * exclusive cumprod(1 - alpha), no early termination at
+    T_thresh = 0) on ragged rays: fp32 rel 1e-4."""
+    import torch
+    from oracle import cpu_ops
+    rng = np.random.RandomState(5)
+    counts = np.array([7, 0, 33, 1, 20], np.int32)
+    offs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int32)
+    rays = np.stack([np.arange(5, dtype=np.int32), offs, counts], 1)
+    M = int(counts.sum())
+    sig = rng.uniform(0, 30, M).astype(np.float32)
+    rgb = rng.uniform(0, 1, (M, 3)).astype(np.float32)
+    msk = np.clip(rng.normal(0.5, 0.02, M), 0, 1).astype(np.float32)
+    dl = np.stack([rng.uniform(0.002, 0.01, M), rng.uniform(0.002, 0.01, M)], 1).astype(np.float32)
+    g_ws, g_img, g_m = rng.randn(5).astype(np.float32), rng.randn(5, 3).astype(np.float32), rng.randn(5).astype(np.float32)
+    for variant in (0, 1, 2):
+        for soft, dbg, dmf in ((True, True, False), (False, False, False), (True, False, True)):
+            ws, depth, img, rm = cpu_ops.composite_lgie_forward(variant, sig, rgb, msk, dl, rays, 0.0, soft, 0.5)
+            ds, dc, dm = cpu_ops.composite_lgie_backward(variant, g_ws, g_img, g_m, sig, rgb, msk, dl, rays, 0.0, soft, 0.5, dbg, dmf)
+            ts, tc, tm = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (sig, rgb, msk))
+            e = torch.sigmoid((tm - 0.5) * 100) if soft else (tm > 0.5).double()
+            gate = torch.ones_like(tm) if variant == 0 else e if variant == 1 else 1 - e
+            s_in, c_in = ts, tc
+            if variant == 0 and dbg:
+                ep = tm >= 0.5
+                s_in = torch.where(ep, ts, ts.detach())
+                c_in = torch.where(ep[:, None], tc, tc.detach())
+            sv = s_in * gate
+            loss = 0.0
+            for n, (o, c) in enumerate(zip(offs, counts)):
+                if c == 0:
+                    continue
+                sl = slice(int(o), int(o + c))
+                alpha = 1 - torch.exp(-sv[sl] * torch.tensor(dl[sl, 0], dtype=torch.float64))
+                T = torch.cumprod(torch.cat([torch.ones(1, dtype=torch.float64), 1 - alpha[:-1]]), 0)
+                w = alpha * T
+                wm = w.detach() if dmf else w
+                np.testing.assert_allclose(float(w.sum().detach()), ws[n], rtol=1e-4, atol=1e-6)
+                np.testing.assert_allclose((w[:, None] * tc[sl]).sum(0).detach().numpy(), img[n], rtol=1e-4, atol=1e-6)
+                np.testing.assert_allclose(float((w * tm[sl]).sum().detach()), rm[n], rtol=1e-4, atol=1e-6)
+                loss = loss + g_ws[n] * w.sum() + (torch.tensor(g_img[n], dtype=torch.float64) * (w[:, None] * c_in[sl]).sum(0)).sum() \
+                    + g_m[n] * (wm * tm[sl]).sum()
+            loss.backward()
+            for got, want, what in ((ds, ts.grad, "sigma"), (dc, tc.grad, "rgb"), (dm, tm.grad, "mask")):
+                want = want.numpy()
+                assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), (variant, soft, dbg, dmf, what,
+                                                                                           np.abs(got - want).max())
