@@ -281,7 +281,16 @@ def run_b200(args):
     L.lib()   # fail loudly if the native library is missing
 
     workload, scaling, raygen, cam_pose = WORKLOAD, "weak", None, None
-    if args.config == 4:
+    if args.config == 3:
+        model = trainer.build_scene_model(dev, opt=trainer.make_opt(train_conf=TRAIN_CONF, soft_mask=True, detach_bg=True))
+        o, d = syn.camera_rays(IMG_H, IMG_W, view=rank)
+        target = syn.bear_color(o + d * 1.5)
+        gt_mask = silhouette(o, d)
+        workload = "configs[3]: LGIE editing step (foreground-masked local render + background render + full-image global " \
+                   "render over the same samples, soft edit mask conf_thr 0.5, detach_bg), 142x105 image (14910 rays) per rank, " \
+                   "bear scene, hash 2^19 L16 F2, 64-wide MLPs (rgb + mask head), cuda_ray path, fp16 autocast, stand-in " \
+                   "per-pixel loss on all three renders + rendered mask (the SDS guidance is out of scope), Adam"
+    elif args.config == 4:
         # BASELINE.json configs[4] (not the driver's line): 2^22 table, 1 M random rays per step -- sharded over the ranks
         # (strong scaling, as the config words it) or, with --weak, 1 M rays on EVERY rank
         model = trainer.build_scene_model(dev, log2_hashmap_size=22, opt=trainer.make_opt(train_conf=TRAIN_CONF))
@@ -314,8 +323,27 @@ def run_b200(args):
         peer = parallel.PeerMemory(fused_trainer.flat_parameter_count(model), dev, multicast=args.update == "nvls")
     elif world > 1:
         sync = (lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM))
-    fs = fused_trainer.FusedTrainStep(model, n_rays, lr=5e-4, world_size=world, grad_sync=sync, use_graph=not args.no_graph,
-                                      pipeline_update=not args.no_pipeline, mask_weight=TRAIN_CONF, peer=peer, raygen=raygen)
+    if args.config == 3:
+        # BASELINE.json configs[3] (not the driver's line): the LGIE editing step -- fg / bg / all renders with the soft edit
+        # mask and detach_bg -- on the same image, ray-sharded like configs[1].  The Stable-Diffusion guidance that gives the
+        # reference its editing loss is out of scope (north_star): a per-pixel stand-in loss touches all three renders and
+        # the rendered mask, normalised by the global ray count like the reconstruction loss.
+        from customnerf_b200 import fused_edit
+        tgt_d, msk_d = target.to(dev), gt_mask.to(dev)[:, None]
+        inv = 1.0 / (n_rays * world)
+
+        def edit_loss(out):
+            return inv * (((out["image"].reshape(-1, 3) - tgt_d) ** 2).sum() / 3 +
+                          ((out["fg"]["image"].reshape(-1, 3) - tgt_d * msk_d) ** 2).sum() / 3 +
+                          ((out["bg"]["image"].reshape(-1, 3) - tgt_d * (1 - msk_d)) ** 2).sum() / 3 +
+                          TRAIN_CONF * ((out["render_mask"].reshape(-1, 1) - msk_d) ** 2).sum())
+        fs = fused_edit.FusedEditStep(model, n_rays, edit_loss, lr=5e-4, world_size=world, grad_sync=sync,
+                                      use_graph=not args.no_graph, peer=peer)
+        raygen = None
+        args.no_breakdown = True
+    else:
+        fs = fused_trainer.FusedTrainStep(model, n_rays, lr=5e-4, world_size=world, grad_sync=sync, use_graph=not args.no_graph,
+                                          pipeline_update=not args.no_pipeline, mask_weight=TRAIN_CONF, peer=peer, raygen=raygen)
     fs.target_mask.copy_(gt_mask)     # [N] ground-truth mask: resident (59 KB; not part of the per-step H2D count)
     # the batch is handed over the way a loader would: written into the trainer's pinned staging buffer, from where each
     # step's graph copies it to the device (one H2D node of 537 KB inside the timed step)
@@ -408,7 +436,9 @@ def run_b200(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
                 "scaling": scaling, "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": workload, "rays_per_gpu_per_step": n_rays, "parallelism": "ray-sharded dp%d" % world,
-                           "step": "one CUDA-graph replay: near/far, march, encode, field MLP, composite, MSE, backward, "
+                           "step": ("LGIE editing step -- 3 mask-gated composites forward / backward, stand-in loss through "
+                                    "autograd on the per-ray outputs; " if args.config == 3 else "") +
+                                   "one CUDA-graph replay: near/far, march, encode, field MLP, composite, MSE, backward, "
                                    "fused Adam" + (", NCCL all-reduce of the flat gradient" if sync is not None else "") +
                                    ("; update = one reduce + Adam + broadcast kernel over NVLink peer memory%s (no NCCL call "
                                     "in the step)" % (" through the NVSwitch multicast mapping" if args.update == "nvls" else "")
@@ -484,8 +514,9 @@ def main():
     ap.add_argument("--update", default="peer", choices=["peer", "nvls", "nccl"],
                     help="N > 1: optimiser update as one NVLink peer-memory kernel (peer: P2P loads / stores, default; nvls: "
                          "through the NVSwitch multicast mapping, reduced in the switch) or NCCL all-reduce + Adam")
-    ap.add_argument("--config", type=int, default=1, choices=[1, 4],
-                    help="BASELINE.json configs[] index: 1 = the bench line (default); 4 = 2^22 table, 1 M rays per step")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4],
+                    help="BASELINE.json configs[] index: 1 = the bench line (default); 3 = LGIE editing step; "
+                         "4 = 2^22 table, 1 M rays per step")
     ap.add_argument("--weak", action="store_true", help="--config 4: 1 M rays on every rank instead of 1 M sharded over the ranks")
     ap.add_argument("--peer-at-1", action="store_true", help="N = 1: run the update through the peer-memory kernel too (tuning)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (kernel tuning runs)")

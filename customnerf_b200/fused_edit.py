@@ -35,6 +35,8 @@ class LgiePlan(C.Structure):
 
 
 class FusedEditStep(FusedTrainStep):
+    kernels_per_step = FusedTrainStep.kernels_per_step + 4      # 3 + 3 gated composites instead of 1 + 1
+
     def __init__(self, model, n_rays, loss_fn, **kw):
         if kw.pop("pipeline_update", False):
             raise RuntimeError("FusedEditStep: pipeline_update is not supported (the loss sits between forward and backward)")

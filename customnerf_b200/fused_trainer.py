@@ -93,6 +93,8 @@ def flatten_parameters(model, flat=None):
 
 
 class FusedTrainStep:
+    kernels_per_step = KERNELS_PER_STEP     # this library's launches in one replay (bench.py: gpu_launches)
+
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
                  lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0,
@@ -490,7 +492,7 @@ class FusedTrainStep:
                 (self.graph_pose if staged == "pose" else self.graph_staged if staged else self.graph).replay()
             else:
                 self._launch(staged)
-            L.LAUNCHES += KERNELS_PER_STEP + (1 if staged == "pose" else 0)
+            L.LAUNCHES += self.kernels_per_step + (1 if staged == "pose" else 0)
 
     def last_stats(self):
         """(loss, samples, rows_used) of the most recent step -- synchronises with the device.  Grows the sample

@@ -101,7 +101,44 @@ def train_case(rank, world, dev):
     return keep
 
 
-def main():
+def edit_case(rank, world, dev):
+    """sharded FusedEditStep (LGIE editing step): peer update vs NCCL all-reduce, same rays, no perturbation"""
+    from customnerf_b200 import fused_edit
+    losses, keep = {}, []
+    for mode in ("nccl", "peer"):
+        model = trainer.build_scene_model(dev, log2_hashmap_size=15, desired_resolution=512, seed=3,
+                                          opt=trainer.make_opt(train_conf=0.01, soft_mask=True, detach_bg=True))
+        with torch.no_grad():
+            g = torch.Generator(device=dev).manual_seed(11)
+            model.pos_en.embeddings.copy_(torch.rand(model.pos_en.embeddings.shape, device=dev, generator=g) - 0.5)
+            model.rgb_network.params[-16 * 64:].view(16, 64)[3] *= 12.0        # a mask head that splits fg / bg
+        o, d = syn.camera_rays(105, 142)
+        idx = parallel.shard_rays(4096, rank, world) + 5000
+        o, d = o[idx].contiguous().to(dev), d[idx].contiguous().to(dev)
+        tgt = syn.bear_color(o.cpu() + d.cpu() * 1.5).to(dev)
+        inv = 1.0 / 4096
+
+        def loss_fn(out):
+            return inv * (((out["image"].reshape(-1, 3) - tgt) ** 2).sum() + ((out["fg"]["image"].reshape(-1, 3) - 0.5 * tgt) ** 2).sum() +
+                          ((out["bg"]["image"].reshape(-1, 3) - 0.5 * tgt) ** 2).sum() + ((out["render_mask"].reshape(-1) - 0.5) ** 2).sum())
+        peer = parallel.PeerMemory(fused_trainer.flat_parameter_count(model), dev) if mode == "peer" else None
+        sync = (lambda flat: dist.all_reduce(flat)) if mode == "nccl" else None
+        fs = fused_edit.FusedEditStep(model, o.shape[0], loss_fn, world_size=world, grad_sync=sync, peer=peer, perturb=False)
+        ls = []
+        for it in range(6):
+            fs.step(o, d, tgt)
+            ls.append(fs.last_stats()[0])
+        torch.cuda.synchronize()
+        dist.barrier()
+        losses[mode] = ls
+        keep.append((fs, peer))
+    a, b = np.array(losses["nccl"]), np.array(losses["peer"])
+    np.testing.assert_allclose(b, a, rtol=1e-3)
+    assert a[-1] < a[0], "the editing step did not reduce its loss"
+    return keep
+
+
+def main():def main():
     rank, local_rank, world = parallel.init_from_env()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -114,6 +151,7 @@ def main():
             raise
         nvls = "unavailable"
     keep.append(train_case(rank, world, dev))
+    keep.append(edit_case(rank, world, dev))
     dist.barrier()
     torch.cuda.synchronize()
     if rank == 0:
