@@ -138,7 +138,9 @@ def edit_case(rank, world, dev):
     return keep
 
 
-def main():def main():
+
+
+def main():
     rank, local_rank, world = parallel.init_from_env()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
