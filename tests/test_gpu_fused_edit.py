@@ -14,6 +14,32 @@ pytestmark = pytest.mark.gpu
 N_RAYS = 2048
 
 
+def _split_mask_head(model, spread=12.0):
+    """A freshly initialised mask head sits on one side of 0.5 everywhere (empty foreground or empty background).  Shift and
+    widen its output row -- w3 <- spread * (w3 - beta * 1), beta found by bisection so that the median mask over points of
+    the scene is 0.5 (sum_j h_j > 0 after the ReLU, so the median falls monotonically with beta) -- to get a real split."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    o, d = _batch()[:2]                      # points along the test's own rays: the head sees these view directions
+    o, d = o.repeat(4, 1), d.repeat(4, 1)
+    x = o + d * (0.7 + 1.6 * torch.rand(o.shape[0], 1, device="cuda", generator=g))
+    row = model.rgb_network.params[-16 * 64:].view(16, 64)[3]
+    w3 = row.detach().clone()
+
+    def median_mask(beta):
+        with torch.no_grad():
+            row.copy_(spread * (w3 - beta))
+            with torch.autocast("cuda", dtype=torch.float16):
+                out = model(x, d)
+            return float(out[1][:, 3].float().median())
+    lo, hi = -4.0, 4.0
+    assert median_mask(lo) > 0.5 > median_mask(hi)
+    for _ in range(30):
+        mid = 0.5 * (lo + hi)
+        lo, hi = (mid, hi) if median_mask(mid) > 0.5 else (lo, mid)
+    median_mask(0.5 * (lo + hi))
+    return row.detach().clone()
+
+
 def _models(**flags):
     from customnerf_b200 import trainer
     opt = dict(train_conf=0.01, **flags)
@@ -22,10 +48,8 @@ def _models(**flags):
     with torch.no_grad():
         a.pos_en.embeddings.uniform_(-0.5, 0.5)
         b.pos_en.embeddings.copy_(a.pos_en.embeddings)
-        # a freshly initialised mask head sits just below 0.5 everywhere (empty foreground): widen its output row so that
-        # the edit mask splits the samples into a real foreground and a real background
-        for m in (a, b):
-            m.rgb_network.params[-16 * 64:].view(16, 64)[3] *= 12.0
+        row = _split_mask_head(a)
+        b.rgb_network.params[-16 * 64:].view(16, 64)[3].copy_(row)
     return a, b
 
 
@@ -76,7 +100,8 @@ def test_edit_step_matches_autograd_composition(flags):
             r, g = ref_d[key].detach().float().cpu().numpy().reshape(-1), got_d[key].cpu().numpy().reshape(-1)
             assert np.abs(g - r).max() <= 1e-4 * max(1.0, np.abs(r).max()), (name, key, np.abs(g - r).max())
     assert float(got["fg"]["weights_sum"].sum()) > 1.0 and float(got["bg"]["weights_sum"].sum()) > 1.0   # both non-trivial
-    assert abs(loss - float(loss_ref)) <= 1e-4 * abs(float(loss_ref)) + 1e-7
+    ref = float(loss_ref.detach())
+    assert abs(loss - ref) <= 1e-4 * abs(ref) + 1e-7
     for name, off, n in fs.layout:
         mod, attr = name.split(".")
         g_ref = getattr(getattr(ma, mod), attr).grad.reshape(-1).float().cpu().numpy()
