@@ -16,7 +16,8 @@ backward (composite, MLP, encode scatter) -> Adam, replayed as one CUDA graph (c
   value : rays/s with the ray batch already resident in HBM (device-timed with CUDA events, L2 flushed between
           steps outside the event pairs, max over ranks)
   e2e   : rays/s through the public API with HOST (pinned) ray / target buffers: H2D copies and the D2H read of
-          the loss inside the timed region
+          every step's loss inside the timed region, in the asynchronous loop a trainer runs (the result of step k - 1 is
+          read while step k executes); e2e_sync is the same with the host waiting for every step before issuing the next
 The reference arm (--impl reference) times the CPU restatement of the reference's PyTorch render path
 (oracle/torch_ref.py, dense 64+64 sampler, fp32) on a bounded sample of the same image's rays.
 """
@@ -356,26 +357,38 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the second staging slot (a loader alternates the two when it issues steps without waiting for the one before)
+    slots = [(o_h, d_h, t_h), fs.pinned_batch(1)]
+    for dst, src in zip(slots[1], (o, d, target)):
+        dst.copy_(src)
+    pose_slots = None
     if raygen is not None:
-        p_h, _ = fs.pinned_pose_batch()
-        p_h.copy_(cam_pose)
+        pose_slots = [fs.pinned_pose_batch(0), fs.pinned_pose_batch(1)]
+        for p_h, _ in pose_slots:
+            p_h.copy_(cam_pose)
 
-    def timed(n_steps, host_inputs):
+    def timed(n_steps, host_inputs, lagged=False):
+        """host_inputs: False (batch resident in HBM) | True (host rays + target) | "pose" (host pose + target).
+        lagged: the result of step k - 1 is read while step k runs (previous_stats) instead of waiting for step k
+        (last_stats); every step's result is still read back exactly once, the last one after the loop."""
         evs = []
-        for _ in range(n_steps):
+        for k in range(n_steps):
             flush.zero_()                                      # L2 flush, outside the per-step event pair
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             if host_inputs == "pose":
-                fs.step(pose=p_h, target=t_h)                  # H2D of pose + target pixels, rays generated in the step
-                fs.last_stats()
+                p_h, tt_h = pose_slots[k & 1]
+                fs.step(pose=p_h, target=tt_h)                 # H2D of pose + target pixels, rays generated in the step
             elif host_inputs:
-                fs.step(o_h, d_h, t_h)                         # H2D of the batch (pinned) + the step
-                fs.last_stats()                                # D2H read of loss / sample count (32 B) + sync
+                fs.step(*slots[k & 1])                         # H2D of the batch (pinned) + the step
             else:
                 fs.step()                                      # batch already resident in HBM
+            if host_inputs:
+                fs.previous_stats() if lagged else fs.last_stats()   # D2H read of loss / sample count (32 B)
             b.record()
             evs.append((a, b))
+        if host_inputs and lagged:
+            fs.last_stats()                                    # the last step's result
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs) / 1e3    # seconds of device time
 
@@ -392,14 +405,21 @@ def run_b200(args):
     sec = timed(args.steps, host_inputs=False)
     launches = L.LAUNCHES
     barrier()
-    sec_e2e = timed(args.steps, host_inputs=True)
+    for sl in slots:                                           # captures the graph of either staging slot (outside the timing)
+        fs.step(*sl)
+    fs.last_stats()
+    barrier()
+    sec_e2e_sync = timed(args.steps, host_inputs=True)
+    barrier()
+    sec_e2e = timed(args.steps, host_inputs=True, lagged=True)
     barrier()
     sec_pose = None
     if raygen is not None:
-        fs.step(pose=p_h, target=t_h)                          # captures the pose-driven graph
+        for p_h, tt_h in pose_slots:                           # captures the pose-driven graphs
+            fs.step(pose=p_h, target=tt_h)
         fs.last_stats()
         barrier()
-        sec_pose = timed(args.steps, host_inputs="pose")
+        sec_pose = timed(args.steps, host_inputs="pose", lagged=True)
         barrier()
     clk = clocks.stop() if rank == 0 else None
     loss, samples, used = fs.last_stats()
@@ -420,9 +440,9 @@ def run_b200(args):
             eb.record()
             torch.cuda.synchronize()
         update_us = ea.elapsed_time(eb) / reps * 1e3
-        t = torch.tensor([sec, sec_e2e, update_us, sec_pose or 0.0], device=dev, dtype=torch.float64)
+        t = torch.tensor([sec, sec_e2e, update_us, sec_pose or 0.0, sec_e2e_sync], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec, sec_e2e, update_us = float(t[0]), float(t[1]), float(t[2])
+        sec, sec_e2e, update_us, sec_e2e_sync = float(t[0]), float(t[1]), float(t[2]), float(t[4])
         sec_pose = float(t[3]) if sec_pose is not None else None
 
     if rank == 0:
@@ -451,8 +471,14 @@ def run_b200(args):
                 "e2e": {"value": total_rays / sec_e2e, "unit": UNIT,
                         "h2d_bytes_per_step": int(3 * n_rays * 3 * 4), "d2h_bytes_per_step": 32,
                         "ms_per_step": sec_e2e / args.steps * 1e3,
-                        "api": "FusedTrainStep.step(*fs.pinned_batch()) (batch in the pinned staging buffer, one H2D copy node "
-                               "at the head of the step's graph) + last_stats() (32-byte D2H + sync)"},
+                        "api": "the asynchronous training loop: FusedTrainStep.step(*fs.pinned_batch(k % 2)) (batch in one of two "
+                               "pinned staging slots, one H2D copy node at the head of the step's graph), then previous_stats(): "
+                               "the 32-byte result of step k - 1 is read while step k runs; every step's result is read once, "
+                               "the last one after the loop"},
+                "e2e_sync": {"value": total_rays / sec_e2e_sync, "unit": UNIT, "h2d_bytes_per_step": int(3 * n_rays * 3 * 4),
+                             "d2h_bytes_per_step": 32, "ms_per_step": sec_e2e_sync / args.steps * 1e3,
+                             "api": "the same with last_stats() after every step: the host waits for step k before it issues "
+                                    "step k + 1 (launch latency, copies and the wake-up are exposed each step)"},
                 "gpu_launches": int(launches), "clocks": clk, "samples_per_step": samples, "final_loss": loss}
         if sec_pose is not None:
             # the same end-to-end step fed the way the reference's loader feeds it (provider.py:344-470 hands the trainer a
@@ -460,7 +486,7 @@ def run_b200(args):
             # first kernel of the step's graph (csrc/raygen.cu)
             line["e2e_from_pose"] = {"value": total_rays / sec_pose, "unit": UNIT, "h2d_bytes_per_step": int(64 + n_rays * 3 * 4),
                                      "d2h_bytes_per_step": 32, "ms_per_step": sec_pose / args.steps * 1e3,
-                                     "api": "FusedTrainStep.step(pose=, target=) with pinned_pose_batch() + last_stats()"}
+                                     "api": "FusedTrainStep.step(pose=, target=) with pinned_pose_batch(k % 2) + previous_stats() (asynchronous loop as e2e)"}
         if update_us is not None:
             nb = fs.params_flat.numel() * 4
             wire = nb * (world - 1) / world          # bytes in (gradient slices read) = bytes out (parameters stored) per rank

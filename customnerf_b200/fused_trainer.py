@@ -142,7 +142,7 @@ class FusedTrainStep:
         self.use_graph = use_graph
         self.perturb = perturb
         self.T_thresh, self.dt_gamma, self.max_steps = float(T_thresh), float(dt_gamma), int(max_steps)
-        self.graph = None
+        self.graphs = {}                    # captured steps by input mode: False | True | 'pose' (slot 0), 'rays1' | 'pose1' (slot 1)
         self.overflows = 0
         model.train()
 
@@ -168,11 +168,11 @@ class FusedTrainStep:
         # a loader that writes into pinned_batch() hands a step its inputs with a single H2D copy, which is the first
         # node of the captured "staged" graph (no per-tensor copy calls on the host)
         self.batch_dev = torch.zeros(3, N, 3, **f32)
-        self.batch_host = torch.zeros(3, N, 3, dtype=torch.float32).pin_memory()
+        # TWO staging slots: while the copy node of step k may still be reading slot k % 2, the loader fills the other
+        self.batch_host = torch.zeros(2, 3, N, 3, dtype=torch.float32).pin_memory()
         self.rays_o, self.rays_d, self.target = self.batch_dev[0], self.batch_dev[1], self.batch_dev[2]
-        self.graph_staged = self.graph_pose = None
         self.pose_dev = torch.zeros(4, 4, **f32)
-        self.pose_host = torch.zeros(4, 4, dtype=torch.float32).pin_memory()
+        self.pose_host = torch.zeros(2, 4, 4, dtype=torch.float32).pin_memory()
         self.target_mask = torch.zeros(N, **f32)
         self.render_mask, self.g_render_mask = torch.zeros(N, **f32), torch.zeros(N, **f32)
         self.noises = torch.zeros(N, **f32)
@@ -186,6 +186,11 @@ class FusedTrainStep:
         # wants to know
         self.stats = torch.zeros(8, dtype=torch.int32, device=dev)
         self.stats_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        # results of the last two steps, copied out after each step and fenced by an event each: previous_stats() reads step
+        # k - 1 while step k runs (no pipeline bubble between steps; last_stats() is the synchronous form)
+        self.stats_ring = torch.zeros(2, 8, dtype=torch.int32).pin_memory()
+        self._ring_events = [torch.cuda.Event(), torch.cuda.Event()]
+        self._steps_launched = 0
         self.peer_plan = None if peer is None else peer.plan(self.layout[0][2], self.exp_avg, self.exp_avg_sq, self.hyper,
                                                              status=self.stats[4:5])
         self.n_total = N * world_size
@@ -203,7 +208,7 @@ class FusedTrainStep:
 
     def _alloc_samples(self, m_cap):
         dev = self.dev
-        self.graph = self.graph_staged = self.graph_pose = None
+        self.graphs = {}
         self.m_cap = m_cap
         if m_cap == 0:
             return
@@ -279,14 +284,21 @@ class FusedTrainStep:
         return max(4096, int(math.ceil(samples * 1.25 / 4096.0)) * 4096)
 
     # ------------------------------------------------------------------------------------------ the step
-    def pinned_batch(self):
-        """(rays_o, rays_d, target): [N,3] views of the pinned host staging buffer.  Fill them in place and call
-        ``step(*pinned_batch())``: the step then starts with one H2D copy of the whole batch inside its graph."""
-        return self.batch_host[0], self.batch_host[1], self.batch_host[2]
+    # the captured graphs by their historical names (tests, bench teardown)
+    graph = property(lambda self: self.graphs.get(False), lambda self, v: self.graphs.clear() if v is None else self.graphs.__setitem__(False, v))
+    graph_staged = property(lambda self: self.graphs.get(True))
+    graph_pose = property(lambda self: self.graphs.get("pose"))
 
-    def pinned_pose_batch(self):
-        """(pose [4,4], target [N,3]): views of the pinned host staging buffers for ``step(pose=, target=)``"""
-        return self.pose_host, self.batch_host[2]
+    def pinned_batch(self, slot=0):
+        """(rays_o, rays_d, target): [N,3] views of pinned host staging slot ``slot`` (0 or 1).  Fill them in place and call
+        ``step(*pinned_batch(slot))``: the step then starts with one H2D copy of the whole batch inside its graph.
+        Alternate the slots when steps are issued without waiting for the one before (``previous_stats()``)."""
+        b = self.batch_host[slot]
+        return b[0], b[1], b[2]
+
+    def pinned_pose_batch(self, slot=0):
+        """(pose [4,4], target [N,3]): views of pinned host staging slot ``slot`` for ``step(pose=, target=)``"""
+        return self.pose_host[slot], self.batch_host[slot][2]
 
     def _generate_rays(self):
         r = self.raygen
@@ -297,12 +309,13 @@ class FusedTrainStep:
 
     def _stage(self, staged):
         """host -> device copies (and ray generation) that head a staged step; staged: False | True (rays) | 'pose' """
-        if staged == "pose":
-            self.pose_dev.copy_(self.pose_host, non_blocking=True)
-            self.batch_dev[2].copy_(self.batch_host[2], non_blocking=True)
+        slot = 1 if staged in ("rays1", "pose1") else 0
+        if staged in ("pose", "pose1"):
+            self.pose_dev.copy_(self.pose_host[slot], non_blocking=True)
+            self.batch_dev[2].copy_(self.batch_host[slot][2], non_blocking=True)
             self._generate_rays()
         elif staged:
-            self.batch_dev.copy_(self.batch_host, non_blocking=True)
+            self.batch_dev.copy_(self.batch_host[slot], non_blocking=True)
 
     def _update(self, st):
         if self.allreduce_chunks > 1:
@@ -383,12 +396,7 @@ class FusedTrainStep:
             # thread_local: NCCL's watchdog thread may touch the CUDA API while the all-reduce of a sharded step is captured
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._launch(staged)
-            if staged == "pose":
-                self.graph_pose = g
-            elif staged:
-                self.graph_staged = g
-            else:
-                self.graph = g
+            self.graphs[staged] = g
         finally:
             torch.cuda.synchronize(self.dev)
             for t, k in zip(state, keep):
@@ -445,8 +453,11 @@ class FusedTrainStep:
             if pose is not None:
                 if self.raygen is None:
                     raise RuntimeError("FusedTrainStep.step(pose=...): construct the step with raygen=dict(H, W, intrinsics)")
-                pose_staged = (not pose.is_cuda and pose.data_ptr() == self.pose_host.data_ptr() and target is not None
-                               and target.data_ptr() == self.batch_host[2].data_ptr())
+                pose_staged = False
+                for slot, name in ((0, "pose"), (1, "pose1")):
+                    if (not pose.is_cuda and pose.data_ptr() == self.pose_host[slot].data_ptr() and target is not None
+                            and target.data_ptr() == self.batch_host[slot][2].data_ptr()):
+                        pose_staged = name
                 if not pose_staged:
                     self.pose_dev.copy_(pose.reshape(4, 4), non_blocking=True)
                     if target is not None:
@@ -454,16 +465,21 @@ class FusedTrainStep:
                     self._generate_rays()
                     L.LAUNCHES += 1
                 elif self.m_cap == 0:
-                    self._stage("pose")       # the capacity measurement below needs this camera's rays
+                    self._stage(pose_staged)  # the capacity measurement below needs this camera's rays
                 rays_o = rays_d = target = None
             if self.m_cap == 0:
                 self._alloc_samples(self._round_cap(self.measure_samples(rays_o if rays_o is not None else self.rays_o,
                                                                          rays_d if rays_d is not None else self.rays_d)))
             # a batch handed over in the pinned staging buffer is copied by the graph itself (one H2D node)
-            staged = (rays_o is not None and not rays_o.is_cuda and rays_o.data_ptr() == self.batch_host[0].data_ptr()
-                      and rays_d.data_ptr() == self.batch_host[1].data_ptr() and target.data_ptr() == self.batch_host[2].data_ptr())
+            staged = False
+            if rays_o is not None and not rays_o.is_cuda:
+                for slot, name in ((0, True), (1, "rays1")):
+                    b = self.batch_host[slot]
+                    if (rays_o.data_ptr() == b[0].data_ptr() and rays_d.data_ptr() == b[1].data_ptr()
+                            and target.data_ptr() == b[2].data_ptr()):
+                        staged = name
             if pose_staged:
-                staged = "pose"
+                staged = pose_staged
             if rays_o is not None and not staged:
                 self.set_batch(rays_o, rays_d, target, target_mask)
             elif target_mask is not None:
@@ -477,8 +493,9 @@ class FusedTrainStep:
                 self.stats_host.copy_(self.stats, non_blocking=True)
                 self._pending_update = True
                 L.LAUNCHES += KERNELS_PER_STEP - 4
+                self._publish_stats()
                 return
-            have = self.graph_pose if staged == "pose" else self.graph_staged if staged else self.graph
+            have = self.graphs.get(staged)
             if self.use_graph and have is None:
                 try:
                     self._capture(staged)
@@ -486,24 +503,48 @@ class FusedTrainStep:
                     import warnings
                     warnings.warn("FusedTrainStep: CUDA-graph capture failed (%s); launching the step's kernels "
                                   "directly instead" % (e,))
-                    self.use_graph, self.graph, self.graph_staged, self.graph_pose = False, None, None, None
+                    self.use_graph = False
+                    self.graphs.clear()
                     torch.cuda.synchronize(self.dev)
             if self.use_graph:
-                (self.graph_pose if staged == "pose" else self.graph_staged if staged else self.graph).replay()
+                self.graphs[staged].replay()
             else:
                 self._launch(staged)
-            L.LAUNCHES += self.kernels_per_step + (1 if staged == "pose" else 0)
+            L.LAUNCHES += self.kernels_per_step + (1 if staged in ("pose", "pose1") else 0)
+            self._publish_stats()
+
+    def _publish_stats(self):
+        i = self._steps_launched & 1
+        self.stats_ring[i].copy_(self.stats, non_blocking=True)
+        self._ring_events[i].record()
+        self._steps_launched += 1
+
+    def _parse_stats(self, s):
+        if int(s[4]):
+            raise RuntimeError("FusedTrainStep: the peer-memory update timed out waiting for another rank (status %d): "
+                               "a rank left the job or launched fewer steps" % int(s[4]))
+        return float(s[3:4].view(torch.float32)[0]), int(s[0]), int(s[2])
+
+    def previous_stats(self):
+        """(loss, samples, rows_used) of the step BEFORE the most recent ``step()`` -- waits for that step only, so the
+        device never idles between steps (issue step k + 1, then read step k).  None before the second step.  A step that
+        overflowed ``m_cap`` is noticed one step late: the buffers grow before the next ``step()``."""
+        if self._steps_launched < 2:
+            return None
+        i = (self._steps_launched - 2) & 1
+        self._ring_events[i].synchronize()
+        out = self._parse_stats(self.stats_ring[i])
+        if out[1] > self.m_cap:
+            torch.cuda.current_stream(self.dev).synchronize()
+            self.overflows += 1
+            self._alloc_samples(self._round_cap(out[1]))
+        return out
 
     def last_stats(self):
         """(loss, samples, rows_used) of the most recent step -- synchronises with the device.  Grows the sample
         buffers (and drops the captured graph) when that step overflowed ``m_cap``."""
         torch.cuda.current_stream(self.dev).synchronize()
-        s = self.stats_host
-        loss = float(s[3:4].view(torch.float32)[0])
-        samples, used = int(s[0]), int(s[2])
-        if int(s[4]):
-            raise RuntimeError("FusedTrainStep: the peer-memory update timed out waiting for another rank (status %d): "
-                               "a rank left the job or launched fewer steps" % int(s[4]))
+        loss, samples, used = self._parse_stats(self.stats_host)
         if samples > self.m_cap:
             self.overflows += 1
             self._alloc_samples(self._round_cap(samples))

@@ -133,6 +133,34 @@ def test_graph_replay_trains_and_matches_eager_launches():
         "pos_en.embeddings", "network.params", "density_network.params", "rgb_network.params"}
 
 
+def test_async_loop_two_staging_slots_and_lagged_stats():
+    """the asynchronous loop: step k + 1 is issued from the other pinned staging slot before step k's result is read
+    (previous_stats): same losses, in the same order, as the synchronous loop"""
+    from customnerf_b200 import fused_trainer
+    ma, mb = _models()
+    o, d, tgt = _batch()
+    sync = fused_trainer.FusedTrainStep(ma, N_RAYS, perturb=False)
+    asyn = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False)
+    slots = [asyn.pinned_batch(0), asyn.pinned_batch(1)]
+    assert slots[0][0].data_ptr() != slots[1][0].data_ptr()
+    for ho, hd, ht in slots:
+        ho.copy_(o.cpu()); hd.copy_(d.cpu()); ht.copy_(tgt.cpu())
+    want, got = [], []
+    assert asyn.previous_stats() is None
+    for k in range(7):
+        sync.step(o, d, tgt); want.append(sync.last_stats()[0])
+        asyn.step(*slots[k & 1])
+        prev = asyn.previous_stats()
+        assert (prev is None) == (k == 0)
+        if prev is not None:
+            got.append(prev[0])
+            assert prev[1] == prev[2] > 1000
+    got.append(asyn.last_stats()[0])
+    assert set(asyn.graphs) == {True, "rays1"}                     # one captured graph per staging slot
+    np.testing.assert_allclose(got, want, rtol=2e-2)
+    assert got[-1] < got[0]
+
+
 def test_stage_profile_reports_every_stage():
     from customnerf_b200 import fused_trainer
     _, mb = _models()
