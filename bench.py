@@ -346,8 +346,8 @@ def run_b200(args):
         fs = fused_trainer.FusedTrainStep(model, n_rays, lr=5e-4, world_size=world, grad_sync=sync, use_graph=not args.no_graph,
                                           pipeline_update=not args.no_pipeline, mask_weight=TRAIN_CONF, peer=peer, raygen=raygen)
     fs.target_mask.copy_(gt_mask)     # [N] ground-truth mask: resident (59 KB; not part of the per-step H2D count)
-    # the batch is handed over the way a loader would: written into the trainer's pinned staging buffer, from where each
-    # step's graph copies it to the device (one H2D node of 537 KB inside the timed step)
+    # the batch is handed over the way a loader would: written into one of the trainer's two pinned staging slots, from where
+    # step() copies it to the device (one H2D copy of 537 KB per step, inside the timed region)
     o_h, d_h, t_h = fs.pinned_batch()
     o_h.copy_(o); d_h.copy_(d); t_h.copy_(target)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -472,7 +472,8 @@ def run_b200(args):
                         "h2d_bytes_per_step": int(3 * n_rays * 3 * 4), "d2h_bytes_per_step": 32,
                         "ms_per_step": sec_e2e / args.steps * 1e3,
                         "api": "the asynchronous training loop: FusedTrainStep.step(*fs.pinned_batch(k % 2)) (batch in one of two "
-                               "pinned staging slots, one H2D copy node at the head of the step's graph), then previous_stats(): "
+                               "pinned staging slots; one H2D copy per step on a copy stream into the matching device slot, which "
+                               "the step's graph waits for), then previous_stats(): "
                                "the 32-byte result of step k - 1 is read while step k runs; every step's result is read once, "
                                "the last one after the loop"},
                 "e2e_sync": {"value": total_rays / sec_e2e_sync, "unit": UNIT, "h2d_bytes_per_step": int(3 * n_rays * 3 * 4),

@@ -23,6 +23,7 @@ them when its ``mean_count`` budget overflows (raymarching.cu:415-416).  ``last_
 sample count; ``step()`` grows the buffers (and re-captures) when a step overflowed, so at most one step per growth
 sees dropped rays.  The default capacity is 1.25x the count measured on the first batch.
 """
+import contextlib
 import ctypes as C
 import math
 
@@ -164,13 +165,16 @@ class FusedTrainStep:
 
         N = self.N
         f32 = dict(dtype=torch.float32, device=dev)
-        # the batch lives in ONE device buffer [rays_o | rays_d | target] mirrored by one pinned host staging buffer:
-        # a loader that writes into pinned_batch() hands a step its inputs with a single H2D copy, which is the first
-        # node of the captured "staged" graph (no per-tensor copy calls on the host)
-        self.batch_dev = torch.zeros(3, N, 3, **f32)
-        # TWO staging slots: while the copy node of step k may still be reading slot k % 2, the loader fills the other
+        # a batch lives in ONE device buffer [rays_o | rays_d | target] mirrored by a pinned host staging buffer: a loader
+        # that writes into pinned_batch() hands a step its inputs with a single H2D copy (no per-tensor copy calls)
+        self.batch_dev = torch.zeros(2, 3, N, 3, **f32)
+        # TWO staging slots, host (pinned) and device: the H2D copy of step k + 1's batch runs on a copy stream while step k
+        # computes, and the loader fills the other host slot meanwhile
         self.batch_host = torch.zeros(2, 3, N, 3, dtype=torch.float32).pin_memory()
-        self.rays_o, self.rays_d, self.target = self.batch_dev[0], self.batch_dev[1], self.batch_dev[2]
+        self.rays_o, self.rays_d, self.target = self.batch_dev[0][0], self.batch_dev[0][1], self.batch_dev[0][2]
+        self._copy_stream = None
+        self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]     # H2D into device slot s has landed
+        self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]      # the last step that read device slot s has finished
         self.pose_dev = torch.zeros(4, 4, **f32)
         self.pose_host = torch.zeros(2, 4, 4, dtype=torch.float32).pin_memory()
         self.target_mask = torch.zeros(N, **f32)
@@ -286,13 +290,14 @@ class FusedTrainStep:
     # ------------------------------------------------------------------------------------------ the step
     # the captured graphs by their historical names (tests, bench teardown)
     graph = property(lambda self: self.graphs.get(False), lambda self, v: self.graphs.clear() if v is None else self.graphs.__setitem__(False, v))
-    graph_staged = property(lambda self: self.graphs.get(True))
+    graph_staged = property(lambda self: self.graphs.get("rays1"))
     graph_pose = property(lambda self: self.graphs.get("pose"))
 
     def pinned_batch(self, slot=0):
         """(rays_o, rays_d, target): [N,3] views of pinned host staging slot ``slot`` (0 or 1).  Fill them in place and call
-        ``step(*pinned_batch(slot))``: the step then starts with one H2D copy of the whole batch inside its graph.
-        Alternate the slots when steps are issued without waiting for the one before (``previous_stats()``)."""
+        ``step(*pinned_batch(slot))``: ONE H2D copy of the whole batch is issued on a copy stream into the matching device
+        slot (it overlaps whatever the device is still computing) and the step's graph waits for it.  Alternate the slots
+        when steps are issued without waiting for the one before (``previous_stats()``)."""
         b = self.batch_host[slot]
         return b[0], b[1], b[2]
 
@@ -309,13 +314,37 @@ class FusedTrainStep:
 
     def _stage(self, staged):
         """host -> device copies (and ray generation) that head a staged step; staged: False | True (rays) | 'pose' """
-        slot = 1 if staged in ("rays1", "pose1") else 0
-        if staged in ("pose", "pose1"):
+        if staged in ("pose", "pose1"):     # ray batches (True / 'rays1') are copied ahead of the step by _prefetch
+            slot = 1 if staged == "pose1" else 0
             self.pose_dev.copy_(self.pose_host[slot], non_blocking=True)
-            self.batch_dev[2].copy_(self.batch_host[slot][2], non_blocking=True)
+            self.target.copy_(self.batch_host[slot][2], non_blocking=True)
             self._generate_rays()
-        elif staged:
-            self.batch_dev.copy_(self.batch_host[slot], non_blocking=True)
+
+    def _prefetch(self, slot):
+        """H2D copy of pinned host slot -> device slot on the copy stream; the current stream waits for it"""
+        main = torch.cuda.current_stream(self.dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        cs = self._copy_stream
+        cs.wait_event(self._slot_free[slot])
+        with torch.cuda.stream(cs):
+            self.batch_dev[slot].copy_(self.batch_host[slot], non_blocking=True)
+            self._slot_ready[slot].record(cs)
+        main.wait_event(self._slot_ready[slot])
+
+    @contextlib.contextmanager
+    def _plan_slot(self, slot):
+        """the plan with its ray / target pointers on device slot ``slot`` (what a launch or a capture inside sees)"""
+        if slot == 0:
+            yield
+            return
+        p, b = self.plan, self.batch_dev[1]
+        keep = (p.rays_o, p.rays_d, p.target)
+        p.rays_o, p.rays_d, p.target = b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr()
+        try:
+            yield
+        finally:
+            p.rays_o, p.rays_d, p.target = keep
 
     def _update(self, st):
         if self.allreduce_chunks > 1:
@@ -484,34 +513,43 @@ class FusedTrainStep:
                 self.set_batch(rays_o, rays_d, target, target_mask)
             elif target_mask is not None:
                 self.target_mask.copy_(target_mask.reshape(-1), non_blocking=True)
-            if self.pipeline_update and not self._pending_update:
-                # first step of a pipelined run: nothing to update yet -- forward + backward only, launched directly
-                self._stage(staged)
-                if self.perturb:
-                    self.noises.uniform_()
-                _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
-                self.stats_host.copy_(self.stats, non_blocking=True)
-                self._pending_update = True
-                L.LAUNCHES += KERNELS_PER_STEP - 4
-                self._publish_stats()
-                return
-            have = self.graphs.get(staged)
-            if self.use_graph and have is None:
-                try:
-                    self._capture(staged)
-                except Exception as e:      # e.g. a collective that cannot be captured on this NCCL build
-                    import warnings
-                    warnings.warn("FusedTrainStep: CUDA-graph capture failed (%s); launching the step's kernels "
-                                  "directly instead" % (e,))
-                    self.use_graph = False
-                    self.graphs.clear()
-                    torch.cuda.synchronize(self.dev)
-            if self.use_graph:
-                self.graphs[staged].replay()
-            else:
-                self._launch(staged)
-            L.LAUNCHES += self.kernels_per_step + (1 if staged in ("pose", "pose1") else 0)
+            slot = -1
+            if staged is True or staged == "rays1":
+                slot = 1 if staged == "rays1" else 0
+                self._prefetch(slot)
+                staged = "rays1" if slot else False       # slot 0 is where the resident batch lives: same graph
+            with self._plan_slot(max(slot, 0)):
+                self._step_staged(staged)
+            if slot >= 0:
+                self._slot_free[slot].record()
             self._publish_stats()
+
+    def _step_staged(self, staged):
+        if self.pipeline_update and not self._pending_update:
+            # first step of a pipelined run: nothing to update yet -- forward + backward only, launched directly
+            self._stage(staged)
+            if self.perturb:
+                self.noises.uniform_()
+            _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
+            self.stats_host.copy_(self.stats, non_blocking=True)
+            self._pending_update = True
+            L.LAUNCHES += KERNELS_PER_STEP - 4
+            return
+        if self.use_graph and self.graphs.get(staged) is None:
+            try:
+                self._capture(staged)
+            except Exception as e:      # e.g. a collective that cannot be captured on this NCCL build
+                import warnings
+                warnings.warn("FusedTrainStep: CUDA-graph capture failed (%s); launching the step's kernels "
+                              "directly instead" % (e,))
+                self.use_graph = False
+                self.graphs.clear()
+                torch.cuda.synchronize(self.dev)
+        if self.use_graph:
+            self.graphs[staged].replay()
+        else:
+            self._launch(staged)
+        L.LAUNCHES += self.kernels_per_step + (1 if staged in ("pose", "pose1") else 0)
 
     def _publish_stats(self):
         i = self._steps_launched & 1
