@@ -367,6 +367,9 @@ def run_b200(args):
         for p_h, _ in pose_slots:
             p_h.copy_(cam_pose)
 
+    import ctypes as C_
+    lib_ = L.lib()
+
     def timed(n_steps, host_inputs, lagged=False):
         """host_inputs: False (batch resident in HBM) | True (host rays + target) | "pose" (host pose + target).
         lagged: the result of step k - 1 is read while step k runs (previous_stats) instead of waiting for step k
@@ -374,6 +377,10 @@ def run_b200(args):
         evs = []
         for k in range(n_steps):
             flush.zero_()                                      # L2 flush, outside the per-step event pair
+            if peer is not None and world > 1:
+                # N > 1: line the ranks up again after the flush (a one-CTA flag barrier over the peer memory), so that one
+                # rank's 256 MB memset is not billed to the step of a peer that waits for it inside the update kernel
+                L.check(lib_.nb200_peer_rank_barrier(C_.byref(fs.peer_plan), L.stream()), "peer_rank_barrier")
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             if host_inputs == "pose":
@@ -467,7 +474,9 @@ def run_b200(args):
                                     "replay contains exactly one update and one forward/backward)" if not args.no_pipeline else ""),
                            "sample_rows_capacity": fs.m_cap,
                            "l2": "256 MB memset between steps, outside the per-step CUDA-event pairs",
-                           "timing": "sum of per-step CUDA-event intervals, max over ranks"},
+                           "timing": "sum of per-step CUDA-event intervals, max over ranks" +
+                                     ("; the ranks are re-aligned by a one-CTA flag barrier after each L2 flush, outside the "
+                                      "event pairs" if peer is not None and world > 1 else "")},
                 "e2e": {"value": total_rays / sec_e2e, "unit": UNIT,
                         "h2d_bytes_per_step": int(3 * n_rays * 3 * 4), "d2h_bytes_per_step": 32,
                         "ms_per_step": sec_e2e / args.steps * 1e3,

@@ -45,7 +45,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-// signal words of one rank: [phase 2][CTA grid][writer NB200_PEER_MAX]
+// signal words of one rank: [phase 3][CTA grid][writer NB200_PEER_MAX]; phases 0 / 1 are the update kernel's start / end
+// barriers, phase 2 (CTA 0 only) belongs to the standalone rank barrier
 __device__ __forceinline__ uint32_t *signal_slot(uint32_t *base, uint32_t grid, uint32_t phase, uint32_t cta, uint32_t writer) {
     return base + ((size_t)(phase * grid + cta) * NB200_PEER_MAX + writer);
 }
@@ -164,6 +165,24 @@ k_peer_reduce_adam_bcast(const nb200_peer_plan pl) {
     if (threadIdx.x == 0) pl.epoch[blockIdx.x] = epoch;
 }
 
+// Standalone rank barrier: one CTA; returns when every rank's stream has reached its own call.  (bench.py aligns the ranks
+// with it after the L2 flush that sits between timed steps, so that one rank's flush is not billed to a peer's step.)
+__global__ void __launch_bounds__(32)
+k_peer_rank_barrier(const nb200_peer_plan pl) {
+    const uint32_t epoch = pl.epoch[pl.grid] + 1u;
+    if (threadIdx.x < pl.world) {
+        const uint32_t peer = threadIdx.x;
+        st_release_sys(signal_slot(pl.signals[peer], pl.grid, 2, 0, pl.rank), epoch);
+        const uint32_t *mine = signal_slot(pl.signals[pl.rank], pl.grid, 2, 0, peer);
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (globaltimer_ns() - t0 > kSpinTimeoutNs) { atomicOr(pl.status, 4u); break; }
+        }
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) pl.epoch[pl.grid] = epoch;
+}
+
 template <int W>
 int launch_peer(const nb200_peer_plan *pl, cudaStream_t st) {
     static int unroll_env = -1;         // float4 groups per thread and trip (tuning knob; default: W * U = 8 loads in flight)
@@ -192,7 +211,7 @@ extern "C" {
 
 uint32_t nb200_peer_plan_bytes(void) { return (uint32_t)sizeof(nb200_peer_plan); }
 uint32_t nb200_peer_handle_bytes(void) { return (uint32_t)sizeof(cudaIpcMemHandle_t); }
-uint64_t nb200_peer_signal_bytes(uint32_t grid) { return (uint64_t)2 * grid * NB200_PEER_MAX * sizeof(uint32_t); }
+uint64_t nb200_peer_signal_bytes(uint32_t grid) { return (uint64_t)3 * grid * NB200_PEER_MAX * sizeof(uint32_t); }
 
 // CTAs of the update kernel for n parameters on `world` ranks with `sms` SMs each: host arithmetic only, so that every
 // rank derives the same grid (the signal slots are per CTA)
@@ -236,6 +255,15 @@ int nb200_peer_import(const void *handle, void **ptr) {
     return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
 }
 int nb200_peer_release(void *ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : 0; }
+
+int nb200_peer_rank_barrier(const nb200_peer_plan *pl, void *stream) {
+    if (!pl || pl->world == 0 || pl->world > NB200_PEER_MAX || pl->rank >= pl->world || pl->grid == 0 || !pl->epoch || !pl->status)
+        return NB200_E_BAD_ARG;
+    for (uint32_t q = 0; q < pl->world; q++) if (!pl->signals[q]) return NB200_E_BAD_ARG;
+    k_peer_rank_barrier<<<1, 32, 0, nb_stream(stream)>>>(*pl);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
 
 int nb200_peer_reduce_adam_bcast(const nb200_peer_plan *pl, void *stream) {
     if (!pl || pl->world == 0 || pl->world > NB200_PEER_MAX || pl->rank >= pl->world || pl->grid == 0) return NB200_E_BAD_ARG;

@@ -145,7 +145,7 @@ class PeerMemory:
         self.bases = bases
         self.params = torch.as_tensor(_DevArray(self.base.value, self.n, "<f4", self), device=self.device)
         self.grads = torch.as_tensor(_DevArray(self.base.value + 4 * self.n, self.n, "<f4", self), device=self.device)
-        self.epoch = torch.zeros(self.grid, dtype=torch.int32, device=self.device)
+        self.epoch = torch.zeros(self.grid + 1, dtype=torch.int32, device=self.device)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         if self.world > 1:
             torch.cuda.synchronize(self.device)
@@ -165,7 +165,7 @@ class PeerMemory:
             self.bases = [int(p) for p in self._symm.buffer_ptrs]
             assert self.bases[self.rank] == self._symm_buf.data_ptr()
             self.params, self.grads = self._symm_buf[:self.n], self._symm_buf[self.n:2 * self.n]
-            self.epoch = torch.zeros(self.grid, dtype=torch.int32, device=self.device)
+            self.epoch = torch.zeros(self.grid + 1, dtype=torch.int32, device=self.device)
             self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
             got = [None] * self.world
             dist.all_gather_object(got, (self.grid, self.n), group=group)

@@ -381,7 +381,7 @@ typedef struct nb200_peer_plan {
     uint32_t *signals[NB200_PEER_MAX];    /* every rank's flag words, nb200_peer_signal_bytes(grid) each, zero-filled */
     float *exp_avg, *exp_avg_sq;          /* local, indexed like params; only this rank's slice is touched */
     const float *hyper;                   /* as nb200_fused_adam */
-    uint32_t *epoch;                      /* local u32 [grid], zero-filled before the first call */
+    uint32_t *epoch;                      /* local u32 [grid + 1], zero-filled before the first call */
     uint32_t *status;                     /* local u32: set non-zero when a barrier timed out (a peer is gone) */
     float *mc_params, *mc_grads;          /* NVSwitch multicast mappings of the same two vectors (both or neither; NULL:
                                              plain peer loads / stores): multimem.ld_reduce sums the gradient inside the
@@ -401,6 +401,9 @@ int nb200_peer_release(void *ptr);
 /* Every rank must call this the same number of times (a CUDA-graph replay counts); world == 1 degenerates to
  * nb200_fused_adam with zero_grad. */
 int nb200_peer_reduce_adam_bcast(const nb200_peer_plan *plan, void *stream);
+/* One-CTA barrier over the same flag words: returns when every rank's stream has reached its own call (every rank must
+ * call it the same number of times).  bench.py aligns the ranks with it between timed steps. */
+int nb200_peer_rank_barrier(const nb200_peer_plan *plan, void *stream);
 /* nb200_train_update with the Adam sweep replaced by nb200_peer_reduce_adam_bcast. */
 int nb200_train_update_peer(const nb200_train_plan *plan, const nb200_peer_plan *peer, void *stream);
 

@@ -43,6 +43,8 @@ def adam_case(rank, world, dev, multicast=False):
                                      L.ptr(hyper), C.c_int(1), L.stream()), "fused_adam")
         torch.cuda.synchronize()
         dist.barrier()
+        L.check(lib.nb200_peer_rank_barrier(C.byref(plan), L.stream()), "peer_rank_barrier")
+        torch.cuda.synchronize()
         assert int(peer.status[0]) == 0, "barrier timed out"
         assert float(peer.grads.abs().max()) == 0.0, "the local gradient was not reset"
         if world == 2 and not multicast:          # a + b is commutative: the two-rank sum equals NCCL's bit for bit

@@ -47,7 +47,12 @@ def test_world1_equals_fused_adam_bit_for_bit():
             assert int(peer.status[0]) == 0
             assert torch.equal(peer.params, p_ref) and torch.equal(m, m_ref) and torch.equal(v, v_ref)
             assert float(peer.grads.abs().max()) == 0.0
-        assert int(peer.epoch.min()) == int(peer.epoch.max()) == 3
+        assert int(peer.epoch[:peer.grid].min()) == int(peer.epoch[:peer.grid].max()) == 3
+        # the standalone rank barrier (its own flag words and epoch counter); world 1: returns at once
+        for k in range(1, 4):
+            L.check(lib.nb200_peer_rank_barrier(C.byref(plan), L.stream()), "peer_rank_barrier")
+            torch.cuda.synchronize()
+            assert int(peer.epoch[peer.grid]) == k and int(peer.status[0]) == 0
     finally:
         peer.close()
 
