@@ -578,6 +578,49 @@ class FusedTrainStep:
             self._alloc_samples(self._round_cap(out[1]))
         return out
 
+    # ------------------------------------------------------------------------------------------ checkpoints
+    def optimizer_state_dict(self):
+        """The optimiser state in ``torch.optim.Adam.state_dict()`` form for ``Adam(model.get_params(lr), betas, eps)`` --
+        the object the reference trains with and stores under ``state['optimizer']`` (main.py:182,
+        utils_init_nerf.py:795) -- so that its checkpoints carry over: four parameters in get_params order
+        (network_grid.py:196-206), 'step' / 'exp_avg' / 'exp_avg_sq' each.  Applies a pending pipelined update first; with
+        the peer-memory update (moments kept only where owned) the slices are gathered from the ranks (a collective call:
+        every rank must make it)."""
+        self.flush()
+        m, v = self.exp_avg, self.exp_avg_sq
+        if self.peer is not None and self.peer.world > 1:
+            from . import parallel
+            m, v = m.clone(), v.clone()
+            parallel.gather_owned_slices(m, self.peer.world, self.peer.rank, self.peer.group)
+            parallel.gather_owned_slices(v, self.peer.world, self.peer.rank, self.peer.group)
+        t = float(int(self.step_count))
+        params = dict(self.model.named_parameters())
+        state, groups = {}, []
+        for i, (name, off, n) in enumerate(self.layout):
+            shape = params[name].shape
+            state[i] = {"step": torch.tensor(t), "exp_avg": m[off:off + n].view(shape).clone(),
+                        "exp_avg_sq": v[off:off + n].view(shape).clone()}
+            groups.append({"lr": self.lr * (10.0 if i == 0 else 1.0), "betas": tuple(self.betas), "eps": self.eps,
+                           "weight_decay": 0, "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                           "differentiable": False, "fused": None, "decoupled_weight_decay": False, "params": [i]})
+        return {"state": state, "param_groups": groups}
+
+    def load_optimizer_state_dict(self, sd):
+        """inverse of ``optimizer_state_dict`` (also takes the state dict of the reference's own Adam)"""
+        self.flush()
+        steps = set()
+        for i, (name, off, n) in enumerate(self.layout):
+            st = sd["state"].get(i)
+            if st is None:                       # a parameter that never received a gradient: no state yet
+                self.exp_avg[off:off + n].zero_(); self.exp_avg_sq[off:off + n].zero_()
+                continue
+            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise RuntimeError("load_optimizer_state_dict: the parameters disagree on the step count: %r" % sorted(steps))
+        self.step_count.fill_(steps.pop() if steps else 0)
+
     def last_stats(self):
         """(loss, samples, rows_used) of the most recent step -- synchronises with the device.  Grows the sample
         buffers (and drops the captured graph) when that step overflowed ``m_cap``."""

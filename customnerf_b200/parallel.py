@@ -70,6 +70,24 @@ def peer_slice(n, world_size, rank):
     return lo * 4, min(lo + per, n4) * 4
 
 
+def gather_owned_slices(vec, world_size, rank, group=None):
+    """In place: every rank's copy of the flat vector ``vec`` receives slice r from rank r (the slices of peer_slice).
+    The peer-memory update keeps Adam's moments only where they are owned; a checkpoint wants the whole vectors."""
+    if world_size == 1:
+        return vec
+    n = vec.numel()
+    per = max(peer_slice(n, world_size, r)[1] - peer_slice(n, world_size, r)[0] for r in range(world_size))
+    lo, hi = peer_slice(n, world_size, rank)
+    mine = torch.zeros(per, dtype=vec.dtype, device=vec.device)
+    mine[:hi - lo].copy_(vec[lo:hi])
+    parts = [torch.empty_like(mine) for _ in range(world_size)]
+    dist.all_gather(parts, mine, group=group)
+    for r, part in enumerate(parts):
+        a, b = peer_slice(n, world_size, r)
+        vec[a:b].copy_(part[:b - a])
+    return vec
+
+
 class _DevArray:
     """a raw device allocation seen through __cuda_array_interface__ (torch.as_tensor wraps it without a copy)"""
 

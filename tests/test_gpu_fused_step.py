@@ -161,6 +161,38 @@ def test_async_loop_two_staging_slots_and_lagged_stats():
     assert got[-1] < got[0]
 
 
+def test_optimizer_state_round_trip_and_torch_adam_format():
+    """optimizer_state_dict() loads into the reference's optimiser object (torch.optim.Adam over get_params) and back:
+    a run resumed from it continues exactly like the uninterrupted one"""
+    from customnerf_b200 import fused_trainer
+    ma, mb = _models()
+    o, d, tgt = _batch()
+    a = fused_trainer.FusedTrainStep(ma, N_RAYS, perturb=False)
+    for _ in range(3):
+        a.step(o, d, tgt)
+    a.last_stats()
+    sd = a.optimizer_state_dict()
+    # the reference's optimiser accepts it (main.py:182) and hands the same state back
+    opt = torch.optim.Adam(ma.get_params(5e-4), betas=(0.9, 0.99), eps=1e-15)
+    opt.load_state_dict(sd)
+    sd2 = opt.state_dict()
+    assert [g["lr"] for g in sd2["param_groups"]] == [5e-3, 5e-4, 5e-4, 5e-4]
+    assert torch.equal(sd2["state"][0]["exp_avg"].reshape(-1), a.exp_avg[:a.layout[0][2]])
+    assert int(float(sd2["state"][3]["step"])) == 3
+    # resume in a fresh trainer: parameters + optimiser state -> identical continuation
+    with torch.no_grad():
+        for (_, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            pb.copy_(pa)
+    b = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False)
+    b.load_optimizer_state_dict(sd2)
+    la, lb = [], []
+    for _ in range(3):
+        a.step(o, d, tgt); la.append(a.last_stats()[0])
+        b.step(o, d, tgt); lb.append(b.last_stats()[0])
+    assert int(b.step_count) == 6
+    np.testing.assert_allclose(lb, la, rtol=1e-3)       # fp32 atomics order differs run to run; no drift beyond it
+
+
 def test_stage_profile_reports_every_stage():
     from customnerf_b200 import fused_trainer
     _, mb = _models()

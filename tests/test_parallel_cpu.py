@@ -140,3 +140,25 @@ def test_peer_update_schedule_equals_allreduce_plus_adam(tmp_path):
     port = _free_port()
     mp.spawn(_peer_schedule_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+def _gather_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from customnerf_b200 import parallel
+    parallel.init_from_env(backend="gloo")
+    for n in (1036, 8, 4):                      # ragged last slice; fewer float4 groups than ranks
+        full = torch.arange(n, dtype=torch.float32) + 1
+        lo, hi = parallel.peer_slice(n, world, rank)
+        vec = torch.zeros(n)
+        vec[lo:hi] = full[lo:hi]                 # every rank holds only what it owns
+        parallel.gather_owned_slices(vec, world, rank)
+        assert torch.equal(vec, full), (n, rank)
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_gather_owned_slices_rebuilds_the_full_vector(tmp_path):
+    port = _free_port()
+    mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
