@@ -197,9 +197,14 @@ int launch_peer(const nb200_peer_plan *pl, cudaStream_t st) {
         else if (U >= 2) k_peer_reduce_adam_bcast<W, 2, true><<<pl->grid, T, 0, st>>>(*pl);
         else k_peer_reduce_adam_bcast<W, 1, true><<<pl->grid, T, 0, st>>>(*pl);
     } else {
-        if (U >= 4 && W <= 4) k_peer_reduce_adam_bcast<W, 4, false><<<pl->grid, T, 0, st>>>(*pl);
-        else if (U >= 2) k_peer_reduce_adam_bcast<W, 2, false><<<pl->grid, T, 0, st>>>(*pl);
-        else k_peer_reduce_adam_bcast<W, 1, false><<<pl->grid, T, 0, st>>>(*pl);
+        bool done = false;
+        if constexpr (W <= 4) {             // W x 4 float4 gradient registers only fit for few ranks
+            if (U >= 4) { k_peer_reduce_adam_bcast<W, 4, false><<<pl->grid, T, 0, st>>>(*pl); done = true; }
+        }
+        if (!done) {
+            if (U >= 2) k_peer_reduce_adam_bcast<W, 2, false><<<pl->grid, T, 0, st>>>(*pl);
+            else k_peer_reduce_adam_bcast<W, 1, false><<<pl->grid, T, 0, st>>>(*pl);
+        }
     }
     NB_LAUNCH_CHECK();
     return 0;
