@@ -4,6 +4,7 @@ buffer holding every gradient (hash table + the three MLPs).  Nothing else is ex
 
 The reference's own DDP wrap is dead code (nerf/utils_init_nerf.py:76-78; init_process_group is never called).
 """
+import ctypes as _C
 import os
 
 import torch
@@ -95,6 +96,14 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 2, "strides": None}
         self._owner = owner         # keeps the allocation alive as long as a tensor made from this object lives
+
+
+class PeerPlan(_C.Structure):
+    """mirror of nb200_peer_plan (include/nerf_b200.h)"""
+    _fields_ = [("world", _C.c_uint32), ("rank", _C.c_uint32), ("grid", _C.c_uint32), ("pad", _C.c_uint32),
+                ("n", _C.c_uint64), ("split", _C.c_uint64), ("params", _C.c_void_p * 8), ("grads", _C.c_void_p * 8),
+                ("signals", _C.c_void_p * 8), ("exp_avg", _C.c_void_p), ("exp_avg_sq", _C.c_void_p), ("hyper", _C.c_void_p),
+                ("epoch", _C.c_void_p), ("status", _C.c_void_p), ("mc_params", _C.c_void_p), ("mc_grads", _C.c_void_p)]
 
 
 class PeerMemory:
@@ -194,13 +203,6 @@ class PeerMemory:
 
     def plan(self, n_table_params, exp_avg, exp_avg_sq, hyper, status=None):
         C = self.C
-        ptr8, u32 = C.c_void_p * 8, C.c_uint32
-
-        class PeerPlan(C.Structure):
-            _fields_ = [("world", u32), ("rank", u32), ("grid", u32), ("pad", u32), ("n", C.c_uint64), ("split", C.c_uint64),
-                        ("params", ptr8), ("grads", ptr8), ("signals", ptr8), ("exp_avg", C.c_void_p),
-                        ("exp_avg_sq", C.c_void_p), ("hyper", C.c_void_p), ("epoch", C.c_void_p), ("status", C.c_void_p),
-                        ("mc_params", C.c_void_p), ("mc_grads", C.c_void_p)]
         p = PeerPlan()
         p.world, p.rank, p.grid, p.n, p.split = self.world, self.rank, self.grid, self.n, int(n_table_params)
         for r, b in enumerate(self.bases):

@@ -50,3 +50,18 @@ def test_missing_library_fails_loudly(monkeypatch):
         assert "no CPU" in str(e)
     else:
         raise AssertionError("expected ImportError")
+
+
+def test_plan_structures_match_the_library_layout():
+    """the ctypes mirrors of the three plan structs have the size the library compiled (no GPU needed)"""
+    import ctypes as C
+    from customnerf_b200 import _lib, fused_trainer, fused_edit, parallel
+    lib = _lib.lib()
+    for fn in (lib.nb200_train_plan_bytes, lib.nb200_peer_plan_bytes, lib.nb200_lgie_plan_bytes, lib.nb200_peer_handle_bytes):
+        fn.restype = C.c_uint32
+    assert C.sizeof(fused_trainer.TrainPlan) == lib.nb200_train_plan_bytes()
+    assert C.sizeof(parallel.PeerPlan) == lib.nb200_peer_plan_bytes()
+    assert C.sizeof(fused_edit.LgiePlan) == lib.nb200_lgie_plan_bytes()
+    assert lib.nb200_peer_handle_bytes() == 64
+    lib.nb200_peer_signal_bytes.restype = C.c_uint64
+    assert lib.nb200_peer_signal_bytes(C.c_uint32(296)) == 3 * 296 * 8 * 4

@@ -162,3 +162,27 @@ def test_gather_owned_slices_rebuilds_the_full_vector(tmp_path):
     port = _free_port()
     mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+def test_peer_plan_is_filled_from_the_mapped_bases():
+    """PeerMemory.plan() on a stand-in object (no GPU, no IPC): pointers of every rank = base, base + 4n, base + 8n"""
+    import ctypes as C
+    from customnerf_b200 import parallel, _lib
+    pm = object.__new__(parallel.PeerMemory)
+    pm.C, pm.lib = C, _lib.lib()
+    pm.lib.nb200_peer_plan_bytes.restype = C.c_uint32
+    pm.world, pm.rank, pm.grid, pm.n = 4, 2, 296, 1000
+    pm.sig_off, pm.mc_base = 2 * pm.n * 4, 0
+    pm.bases = [0x10000000 * (r + 1) for r in range(4)]
+    pm.epoch, pm.status = torch.zeros(pm.grid + 1, dtype=torch.int32), torch.zeros(1, dtype=torch.int32)
+    m, v, h = torch.zeros(pm.n), torch.zeros(pm.n), torch.zeros(16)
+    p = pm.plan(600, m, v, h)
+    assert (p.world, p.rank, p.grid, p.n, p.split) == (4, 2, 296, 1000, 600)
+    for r in range(4):
+        assert (p.params[r], p.grads[r], p.signals[r]) == (pm.bases[r], pm.bases[r] + 4000, pm.bases[r] + 8000)
+    assert p.params[4] is None and p.mc_params is None and p.mc_grads is None
+    assert (p.exp_avg, p.exp_avg_sq, p.hyper, p.epoch, p.status) == (m.data_ptr(), v.data_ptr(), h.data_ptr(),
+                                                                      pm.epoch.data_ptr(), pm.status.data_ptr())
+    pm.mc_base = 0x7000000000
+    q = pm.plan(600, m, v, h, status=torch.zeros(1, dtype=torch.int32))
+    assert (q.mc_params, q.mc_grads) == (pm.mc_base, pm.mc_base + 4000) and q.status != p.status
