@@ -1,0 +1,113 @@
+"""Mint golden values from the reference's remaining pure-Python pieces of the hot path, imported UNMODIFIED on the CPU:
+
+  * get_embedder(4)            /root/reference/nerf/base.py:42-77        (view-direction frequency encoding, 27 dims)
+  * trunc_exp                  /root/reference/nerf/provider_utils.py:16-29   (forward and its clamped backward)
+  * GridEncoder.__init__       /root/reference/gridencoder/grid.py:103-146    (level table: offsets / n_params / output_dim)
+  * NeRFRenderer.update_extra_state   /root/reference/nerf/renderer.py:1658-1715  (occupancy-grid EMA update, thresholding,
+                                       mean_count) with the two native ops it calls -- raymarching.morton3D / packbits,
+                                       CUDA-only in the reference -- served by the CPU oracle (oracle/cpu_ops.py), so what
+                                       is pinned here is the reference's own torch logic around them.
+
+Absent top-level imports (trimesh, plyfile, skimage, torchtyping, the compiled extension modules) are stubbed; none is
+touched by the code exercised.  Run in the build container:  python tests/golden/make_golden_python.py
+    -> tests/golden/ref_python.npz
+"""
+import hashlib
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import cpu_ops  # noqa: E402
+from customnerf_b200 import synthetic as syn  # noqa: E402
+
+GRID_CONFIGS = [dict(num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19, desired_resolution=2048, gridtype="hash"),
+                dict(num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=21, desired_resolution=8192, gridtype="tiled"),
+                dict(num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=22, desired_resolution=2048, gridtype="hash"),
+                dict(num_levels=8, level_dim=4, base_resolution=8, log2_hashmap_size=15, desired_resolution=512, gridtype="hash",
+                     align_corners=True),
+                dict(input_dim=2, num_levels=4, level_dim=1, base_resolution=4, log2_hashmap_size=10, per_level_scale=2, gridtype="hash")]
+
+
+def stub_modules():
+    for name in ("trimesh", "plyfile", "skimage", "skimage.measure", "_gridencoder", "_raymarching"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    tt = types.ModuleType("torchtyping")
+    tt.TensorType = type("TensorType", (), {"__class_getitem__": classmethod(lambda cls, item: cls)})
+    sys.modules.setdefault("torchtyping", tt)
+    rm = types.ModuleType("raymarching")          # the two native ops update_extra_state calls, served by the CPU oracle
+    rm.morton3D = lambda coords: torch.from_numpy(cpu_ops.morton3D(coords.numpy()))
+    rm.packbits = lambda grid, thresh, bitfield=None: torch.from_numpy(cpu_ops.packbits(grid.numpy(), thresh))
+    sys.modules["raymarching"] = rm
+    pkg = types.ModuleType("nerf")
+    pkg.__path__ = ["/root/reference/nerf"]
+    sys.modules["nerf"] = pkg
+    gpk = types.ModuleType("gridencoder")
+    gpk.__path__ = ["/root/reference/gridencoder"]
+    sys.modules["gridencoder"] = gpk
+
+
+def scene_density(x):
+    return {"sigma": syn.bear_density(x)}
+
+
+def digest(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8).copy()
+
+
+def main():
+    stub_modules()
+    base = importlib.import_module("nerf.base")
+    pu = importlib.import_module("nerf.provider_utils")
+    renderer = importlib.import_module("nerf.renderer")
+    grid = importlib.import_module("gridencoder.grid")
+    rng = np.random.RandomState(20261017)
+    G = {}
+    # ---- frequency embedding of the view direction
+    d = rng.randn(64, 3).astype(np.float32)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    emb, out_dim = base.get_embedder(4)
+    G["embed_in"], G["embed_out"], G["embed_dim"] = d, emb(torch.from_numpy(d)).numpy(), np.int64(out_dim)
+    # ---- trunc_exp
+    x = np.concatenate([rng.uniform(-20, 20, 61), [-15.0, 15.0, 16.5]]).astype(np.float32)
+    tx = torch.from_numpy(x).requires_grad_()
+    y = pu.trunc_exp(tx)
+    g = rng.randn(64).astype(np.float32)
+    y.backward(torch.from_numpy(g))
+    G["texp_in"], G["texp_out"], G["texp_gout"], G["texp_gin"] = x, y.detach().numpy(), g, tx.grad.numpy()
+    # ---- level tables
+    for i, cfg in enumerate(GRID_CONFIGS):
+        enc = grid.GridEncoder(**cfg)
+        G["grid%d_offsets" % i] = enc.offsets.numpy().astype(np.int64)
+        G["grid%d_meta" % i] = np.array([enc.n_params, enc.output_dim, enc.embeddings.shape[0], enc.embeddings.shape[1]], np.int64)
+        G["grid%d_scale" % i] = np.float64(enc.per_level_scale)
+        G["grid%d_init_absmax" % i] = np.float32(enc.embeddings.detach().abs().max())
+    # ---- occupancy-grid update (two consecutive updates: fresh grid, then the EMA-max path), bound 2 -> 2 cascades
+    opt = types.SimpleNamespace(bound=2, cuda_ray=True, min_near=0.01, density_thresh=10)
+    r = renderer.NeRFRenderer(opt)
+    r.density = scene_density
+    torch.manual_seed(123)
+    r.local_step = 3
+    r.step_counter[:3, 0] = torch.tensor([100, 200, 301], dtype=torch.int32)
+    for k in range(2):
+        r.update_extra_state()
+        g_ = r.density_grid.numpy()
+        G["occ%d_grid_sha256" % k] = digest(g_)
+        G["occ%d_grid_sample" % k] = g_.reshape(-1)[::1009].copy()
+        G["occ%d_bitfield_sha256" % k] = digest(r.density_bitfield.numpy())
+        G["occ%d_bits_set" % k] = np.int64(np.unpackbits(r.density_bitfield.numpy()).sum())
+        G["occ%d_mean_density" % k] = np.float64(r.mean_density)
+        G["occ%d_mean_count" % k] = np.int64(r.mean_count)
+        G["occ%d_iter_local" % k] = np.array([r.iter_density, r.local_step], np.int64)
+    np.savez_compressed(os.path.join(HERE, "ref_python.npz"), **G)
+    print("wrote ref_python.npz:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in G.items() if "occ" in k or "meta" in k})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,80 @@
+"""Oracle (oracle/) and the product's host-side Python (customnerf_b200/) against golden values minted from the reference's
+own Python code, imported unmodified by tests/golden/make_golden_python.py: the view-direction frequency encoding
+(nerf/base.py:42-77), trunc_exp forward / backward (nerf/provider_utils.py:16-29), the GridEncoder level table
+(gridencoder/grid.py:103-146) and the occupancy-grid update (nerf/renderer.py:1658-1715).
+
+Tolerances: integer tables, bit fields and counters exact; fp32 values rel 1e-6 (same torch ops on the same CPU)."""
+import hashlib
+import os
+import types
+
+import numpy as np
+import torch
+
+from oracle import cpu_ops, torch_ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "ref_python.npz"))
+from golden.make_golden_python import GRID_CONFIGS  # noqa: E402  (the configurations the vectors were minted for)
+
+
+def test_frequency_embedding_matches_the_reference():
+    from customnerf_b200.nerf import freq_embed
+    d = torch.from_numpy(G["embed_in"])
+    assert int(G["embed_dim"]) == 27
+    for name, fn in (("oracle", torch_ref.freq_embed), ("product", freq_embed)):
+        out = fn(d).numpy()
+        assert out.shape == G["embed_out"].shape, name
+        np.testing.assert_allclose(out, G["embed_out"], rtol=1e-6, atol=1e-7, err_msg=name)
+
+
+def test_trunc_exp_forward_and_clamped_backward_match_the_reference():
+    from customnerf_b200.nerf import trunc_exp
+    for name, fn in (("oracle", torch_ref._trunc_exp.apply), ("product", trunc_exp)):
+        x = torch.from_numpy(G["texp_in"].copy()).requires_grad_()
+        y = fn(x)
+        y.backward(torch.from_numpy(G["texp_gout"]))
+        np.testing.assert_allclose(y.detach().numpy(), G["texp_out"], rtol=1e-6, err_msg=name)
+        np.testing.assert_allclose(x.grad.numpy(), G["texp_gin"], rtol=1e-6, err_msg=name)      # exp(clamp(x, -15, 15)) * g
+
+
+def test_level_tables_match_the_reference_encoder():
+    from customnerf_b200.gridencoder import GridEncoder
+    for i, cfg in enumerate(GRID_CONFIGS):
+        want = G["grid%d_offsets" % i]
+        n_params, out_dim, rows, C = [int(v) for v in G["grid%d_meta" % i]]
+        okw = {k: v for k, v in cfg.items() if k != "gridtype"}
+        offs, scale = cpu_ops.grid_offsets(**okw)
+        assert np.array_equal(offs.astype(np.int64), want), ("oracle", i)
+        assert abs(float(scale) - float(G["grid%d_scale" % i])) < 1e-12
+        enc = GridEncoder(**cfg)                                   # host-side construction: no kernel is launched
+        assert np.array_equal(enc.offsets.numpy().astype(np.int64), want), ("product", i)
+        assert (enc.n_params, enc.output_dim, tuple(enc.embeddings.shape)) == (n_params, out_dim, (rows, C)), i
+        assert abs(float(enc.per_level_scale) - float(G["grid%d_scale" % i])) < 1e-12
+        assert float(enc.embeddings.detach().abs().max()) <= 1e-4 and float(G["grid%d_init_absmax" % i]) <= 1e-4   # U(-1e-4, 1e-4)
+
+
+def _digest(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+def test_occupancy_update_matches_the_reference_renderer():
+    """two consecutive update_extra_state calls (fresh grid, then the EMA-max path) with the generator seeded as the
+    reference run was: grid, bit field, mean density, mean_count"""
+    from customnerf_b200 import synthetic as syn
+    net = torch_ref.NeRFNetwork(torch_ref.default_opt(cuda_ray=True), encoder_kwargs=dict(log2_hashmap_size=12, desired_resolution=64,
+                                                                                          gridtype="hash"))
+    net.density = lambda x: {"sigma": syn.bear_density(x)}
+    torch.manual_seed(123)
+    net.local_step = 3
+    net.step_counter[:3, 0] = torch.tensor([100, 200, 301], dtype=torch.int32)
+    for k in range(2):
+        net.update_extra_state()
+        grid, bits = net.density_grid.numpy(), net.density_bitfield.numpy()
+        np.testing.assert_allclose(grid.reshape(-1)[::1009], G["occ%d_grid_sample" % k], rtol=1e-6, atol=1e-7)
+        assert int(np.unpackbits(bits).sum()) == int(G["occ%d_bits_set" % k])
+        assert np.array_equal(_digest(bits), G["occ%d_bitfield_sha256" % k])
+        assert np.array_equal(_digest(grid), G["occ%d_grid_sha256" % k])
+        assert abs(net.mean_density - float(G["occ%d_mean_density" % k])) <= 1e-6 * float(G["occ%d_mean_density" % k])
+        assert int(net.mean_count) == int(G["occ%d_mean_count" % k])
+        assert [net.iter_density, net.local_step] == list(G["occ%d_iter_local" % k])
