@@ -3,6 +3,9 @@
   * get_embedder(4)            /root/reference/nerf/base.py:42-77        (view-direction frequency encoding, 27 dims)
   * trunc_exp                  /root/reference/nerf/provider_utils.py:16-29   (forward and its clamped backward)
   * GridEncoder.__init__       /root/reference/gridencoder/grid.py:103-146    (level table: offsets / n_params / output_dim)
+  * NeRFRenderer.run           /root/reference/nerf/renderer.py:278-405   (the dense 'non-cuda_ray' renderer -- the path the
+                                       CPU baseline of bench.py restates: stratified + importance sampling, sort / gather, LGIE
+                                       all / fg / bg composites) on an analytic field, eval and training mode
   * NeRFRenderer.update_extra_state   /root/reference/nerf/renderer.py:1658-1715  (occupancy-grid EMA update, thresholding,
                                        mean_count) with the two native ops it calls -- raymarching.morton3D / packbits,
                                        CUDA-only in the reference -- served by the CPU oracle (oracle/cpu_ops.py), so what
@@ -44,6 +47,11 @@ def stub_modules():
     rm = types.ModuleType("raymarching")          # the two native ops update_extra_state calls, served by the CPU oracle
     rm.morton3D = lambda coords: torch.from_numpy(cpu_ops.morton3D(coords.numpy()))
     rm.packbits = lambda grid, thresh, bitfield=None: torch.from_numpy(cpu_ops.packbits(grid.numpy(), thresh))
+
+    def near_far(rays_o, rays_d, aabb, min_near=0.2):
+        n, f = cpu_ops.near_far_from_aabb(rays_o.numpy(), rays_d.numpy(), aabb.numpy(), min_near)
+        return torch.from_numpy(n), torch.from_numpy(f)
+    rm.near_far_from_aabb = near_far
     sys.modules["raymarching"] = rm
     pkg = types.ModuleType("nerf")
     pkg.__path__ = ["/root/reference/nerf"]
@@ -55,6 +63,23 @@ def stub_modules():
 
 def scene_density(x):
     return {"sigma": syn.bear_density(x)}
+
+
+def field_forward(x, d):
+    """analytic stand-in for NeRFNetwork.forward: sigma [M], (rgb | mask) [M,4], no normals"""
+    mask = torch.sigmoid(4.0 * x[:, :1] + d[:, 1:2])
+    return syn.bear_density(x), torch.cat([syn.bear_color(x), mask], -1), None
+
+
+RUN_OPT = dict(bound=2, cuda_ray=False, min_near=0.01, density_thresh=10, train_conf=0.01, soft_mask=True, conf_thr=0.5,
+               detach_bg=True, detach_mask_from_field=False)
+RUN_KEYS = ("image", "depth", "weights_sum", "render_mask")
+
+
+def run_rays():
+    o, d = syn.camera_rays(12, 16)
+    sel = torch.arange(40, 40 + 48)
+    return o[sel].contiguous()[None], d[sel].contiguous()[None]
 
 
 def digest(a):
@@ -88,6 +113,20 @@ def main():
         G["grid%d_meta" % i] = np.array([enc.n_params, enc.output_dim, enc.embeddings.shape[0], enc.embeddings.shape[1]], np.int64)
         G["grid%d_scale" % i] = np.float64(enc.per_level_scale)
         G["grid%d_init_absmax" % i] = np.float32(enc.embeddings.detach().abs().max())
+    # ---- the dense renderer on an analytic field: eval (deterministic importance sampling) and training (perturbed, random)
+    rr = renderer.NeRFRenderer(types.SimpleNamespace(**RUN_OPT))
+    rr.density = scene_density
+    rr.forward = field_forward
+    o, d = run_rays()
+    for mode in ("eval", "train"):
+        rr.train(mode == "train")
+        torch.manual_seed(5)
+        res = rr.run(o, d, num_steps=16, upsample_steps=16, perturb=(mode == "train"))
+        for key in RUN_KEYS:
+            G["run_%s_%s" % (mode, key)] = res[key].detach().numpy()
+            G["run_%s_fg_%s" % (mode, key)] = res["fg"][key].detach().numpy()
+            G["run_%s_bg_%s" % (mode, key)] = res["bg"][key].detach().numpy()
+        G["run_%s_edit_mask" % mode] = res["edit_mask"].detach().numpy()
     # ---- occupancy-grid update (two consecutive updates: fresh grid, then the EMA-max path), bound 2 -> 2 cascades
     opt = types.SimpleNamespace(bound=2, cuda_ray=True, min_near=0.01, density_thresh=10)
     r = renderer.NeRFRenderer(opt)

@@ -78,3 +78,28 @@ def test_occupancy_update_matches_the_reference_renderer():
         assert abs(net.mean_density - float(G["occ%d_mean_density" % k])) <= 1e-6 * float(G["occ%d_mean_density" % k])
         assert int(net.mean_count) == int(G["occ%d_mean_count" % k])
         assert [net.iter_density, net.local_step] == list(G["occ%d_iter_local" % k])
+
+
+def test_dense_renderer_run_matches_the_reference_renderer():
+    """oracle/torch_ref.py NeRFNetwork.run -- the restatement bench.py times as the CPU baseline -- against the reference's
+    NeRFRenderer.run (renderer.py:278-405) on the same analytic field: eval mode (deterministic importance sampling) and
+    training mode (perturbed strata, random importance samples; the reference draws torch.randn(3) for its unused light
+    direction first, :303, so the generator is advanced by the same draw here)."""
+    import types
+    from golden.make_golden_python import RUN_OPT, RUN_KEYS, field_forward, scene_density, run_rays
+    opt = torch_ref.default_opt(**RUN_OPT)
+    net = torch_ref.NeRFNetwork(opt, encoder_kwargs=dict(log2_hashmap_size=12, desired_resolution=64, gridtype="hash"))
+    net.density = scene_density
+    net.forward = field_forward
+    o, d = run_rays()
+    for mode in ("eval", "train"):
+        net.train(mode == "train")
+        torch.manual_seed(5)
+        torch.randn(3)                                    # the reference's light_d draw (renderer.py:303)
+        res = net.run(o, d, num_steps=16, upsample_steps=16, perturb=(mode == "train"))
+        for key in RUN_KEYS:
+            for sub, r in (("", res), ("fg_", res["fg"]), ("bg_", res["bg"])):
+                want = G["run_%s_%s%s" % (mode, sub, key)]
+                np.testing.assert_allclose(r[key].detach().numpy().reshape(want.shape), want, rtol=1e-5, atol=1e-6,
+                                           err_msg="%s %s%s" % (mode, sub, key))
+        np.testing.assert_allclose(res["edit_mask"].detach().numpy(), G["run_%s_edit_mask" % mode], rtol=1e-5, atol=1e-6)
