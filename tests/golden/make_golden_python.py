@@ -3,6 +3,9 @@
   * get_embedder(4)            /root/reference/nerf/base.py:42-77        (view-direction frequency encoding, 27 dims)
   * trunc_exp                  /root/reference/nerf/provider_utils.py:16-29   (forward and its clamped backward)
   * GridEncoder.__init__       /root/reference/gridencoder/grid.py:103-146    (level table: offsets / n_params / output_dim)
+  * GridEncoder.forward + _grid_encode   /root/reference/gridencoder/grid.py:24-99,151-168  (the autograd wrapper: [-bound, bound]
+                                       -> [0, 1] mapping, prefix shapes, [L,B,C] <-> [B,L*C] permutes, max_level, input gradients)
+                                       with the two native entry points it calls served by the C oracle
   * NeRFRenderer.run           /root/reference/nerf/renderer.py:278-405   (the dense 'non-cuda_ray' renderer -- the path the
                                        CPU baseline of bench.py restates: stratified + importance sampling, sort / gather, LGIE
                                        all / fg / bg composites) on an analytic field, eval and training mode
@@ -82,6 +85,30 @@ def run_rays():
     return o[sel].contiguous()[None], d[sel].contiguous()[None]
 
 
+ENC_CFG = dict(input_dim=3, num_levels=8, level_dim=2, base_resolution=8, log2_hashmap_size=12, desired_resolution=128,
+               gridtype="hash")
+
+
+def install_grid_backend(grid):
+    """grid._backend.grid_encode_forward / _backward (bindings.cpp:5-7) on CPU tensors through oracle/cpu_ops.py"""
+    def fwd(inputs, embeddings, offsets, outputs, B, D, C, L, max_level, S, H, dy_dx, gridtype, align_corners, interp):
+        out, dd = cpu_ops.grid_encode_forward(inputs.detach().numpy(), embeddings.detach().numpy(), offsets.numpy(), 2.0 ** S, H,
+                                              dy_dx is not None, gridtype, align_corners, interp, max_level)
+        outputs.copy_(torch.from_numpy(np.ascontiguousarray(out.reshape(B, L, C).transpose(1, 0, 2))))
+        if dy_dx is not None:
+            dy_dx.copy_(torch.from_numpy(dd))
+
+    def bwd(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, max_level, S, H, dy_dx, grad_inputs, gridtype,
+            align_corners, interp):
+        g = np.ascontiguousarray(grad.numpy().transpose(1, 0, 2)).reshape(B, L * C)
+        ge, gi = cpu_ops.grid_encode_backward(g, inputs.detach().numpy(), tuple(embeddings.shape), offsets.numpy(), 2.0 ** S, H,
+                                              None if dy_dx is None else dy_dx.numpy(), gridtype, align_corners, interp, max_level)
+        grad_embeddings.copy_(torch.from_numpy(ge))
+        if grad_inputs is not None:
+            grad_inputs.copy_(torch.from_numpy(gi))
+    grid._backend.grid_encode_forward, grid._backend.grid_encode_backward = fwd, bwd
+
+
 def digest(a):
     return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8).copy()
 
@@ -113,6 +140,22 @@ def main():
         G["grid%d_meta" % i] = np.array([enc.n_params, enc.output_dim, enc.embeddings.shape[0], enc.embeddings.shape[1]], np.int64)
         G["grid%d_scale" % i] = np.float64(enc.per_level_scale)
         G["grid%d_init_absmax" % i] = np.float32(enc.embeddings.detach().abs().max())
+    # ---- the encoder's autograd wrapper (native entry points served by the C oracle)
+    install_grid_backend(grid)
+    enc = grid.GridEncoder(**ENC_CFG)
+    emb = rng.uniform(-1, 1, tuple(enc.embeddings.shape)).astype(np.float32)
+    enc.embeddings.data.copy_(torch.from_numpy(emb))
+    xin = rng.uniform(-2, 2, (2, 5, 3)).astype(np.float32)
+    gout = rng.randn(2, 5, enc.output_dim).astype(np.float32)
+    G["enc_embeddings"], G["enc_inputs"], G["enc_gout"] = emb, xin, gout
+    tx = torch.from_numpy(xin.copy()).requires_grad_()
+    out = enc(tx, bound=2)
+    out.backward(torch.from_numpy(gout))
+    G["enc_out"], G["enc_grad_inputs"], G["enc_grad_embeddings"] = out.detach().numpy(), tx.grad.numpy(), enc.embeddings.grad.numpy().copy()
+    enc.embeddings.grad = None
+    out5 = enc(torch.from_numpy(xin.copy()), bound=2, max_level=5)             # levels >= 5 stay zero, no input gradient
+    out5.backward(torch.from_numpy(gout))
+    G["enc_out_max5"], G["enc_grad_embeddings_max5"] = out5.detach().numpy(), enc.embeddings.grad.numpy().copy()
     # ---- the dense renderer on an analytic field: eval (deterministic importance sampling) and training (perturbed, random)
     rr = renderer.NeRFRenderer(types.SimpleNamespace(**RUN_OPT))
     rr.density = scene_density

@@ -103,3 +103,31 @@ def test_dense_renderer_run_matches_the_reference_renderer():
                 np.testing.assert_allclose(r[key].detach().numpy().reshape(want.shape), want, rtol=1e-5, atol=1e-6,
                                            err_msg="%s %s%s" % (mode, sub, key))
         np.testing.assert_allclose(res["edit_mask"].detach().numpy(), G["run_%s_edit_mask" % mode], rtol=1e-5, atol=1e-6)
+
+
+def test_encoder_wrapper_matches_the_reference_autograd_function():
+    """oracle/torch_ref.py GridEncoder (a pure-torch encoder differentiated by autograd) against the reference's own
+    GridEncoder.forward + _grid_encode Function (gridencoder/grid.py:24-99, 151-168) whose two native entry points were
+    served by the C oracle when the vectors were minted: world -> [0,1] mapping, prefix shapes, level-major permutes,
+    max_level, gradients w.r.t. embeddings and inputs.  Two independent fp32 implementations of the kernel: rel 1e-4 with an
+    absolute floor of 3e-5 on O(1) features (a position is x * scale + 0.5 with scale up to 128, so one ulp of x moves the
+    interpolation weights by ~1e-5)."""
+    from golden.make_golden_python import ENC_CFG
+    enc = torch_ref.GridEncoder(**ENC_CFG)
+    enc.embeddings.data.copy_(torch.from_numpy(G["enc_embeddings"]))
+    x = torch.from_numpy(G["enc_inputs"].copy()).requires_grad_()
+    out = enc(x, bound=2)
+    assert tuple(out.shape) == G["enc_out"].shape
+    out.backward(torch.from_numpy(G["enc_gout"]))
+    np.testing.assert_allclose(out.detach().numpy(), G["enc_out"], rtol=1e-4, atol=3e-5)
+    np.testing.assert_allclose(enc.embeddings.grad.numpy(), G["enc_grad_embeddings"], rtol=1e-4, atol=3e-5)
+    gi, want = x.grad.numpy(), G["enc_grad_inputs"]
+    # d/d(world x) = d/d(x01) / (2 bound): the reference's kernel differentiates w.r.t. the [0,1] input and its wrapper
+    # returns that gradient for the [0,1] tensor autograd then chains through (inputs + bound) / (2 bound)
+    np.testing.assert_allclose(gi, want, rtol=1e-3, atol=1e-4 * np.abs(want).max())
+    enc.embeddings.grad = None
+    out5 = enc(torch.from_numpy(G["enc_inputs"].copy()), bound=2, max_level=5)
+    out5.backward(torch.from_numpy(G["enc_gout"]))
+    np.testing.assert_allclose(out5.detach().numpy(), G["enc_out_max5"], rtol=1e-4, atol=3e-5)
+    assert float(np.abs(out5.detach().numpy().reshape(-1, 8, 2)[:, 5:]).max()) == 0.0
+    np.testing.assert_allclose(enc.embeddings.grad.numpy(), G["enc_grad_embeddings_max5"], rtol=1e-4, atol=3e-5)
