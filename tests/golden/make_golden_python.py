@@ -6,6 +6,11 @@
   * GridEncoder.forward + _grid_encode   /root/reference/gridencoder/grid.py:24-99,151-168  (the autograd wrapper: [-bound, bound]
                                        -> [0, 1] mapping, prefix shapes, [L,B,C] <-> [B,L*C] permutes, max_level, input gradients)
                                        with the two native entry points it calls served by the C oracle
+  * NeRFNetwork.__init__ / forward / density   /root/reference/nerf/network_grid.py:70-193 (+ encoding.py:51-69): the field
+                                       network's composition -- tiled 2^21 -> 8192 encoder, trunk, density head + gaussian blob +
+                                       trunc_exp, [view embedding | features] -> colour + mask head -- with ``tinycudann.Network``
+                                       (absent, un-vendored, unpinned) served by the oracle's MLP restatement and the
+                                       encoder's native entry points by the C oracle: what is pinned is the WIRING
   * NeRFRenderer.run           /root/reference/nerf/renderer.py:278-405   (the dense 'non-cuda_ray' renderer -- the path the
                                        CPU baseline of bench.py restates: stratified + importance sampling, sort / gather, LGIE
                                        all / fg / bg composites) on an analytic field, eval and training mode
@@ -109,6 +114,17 @@ def install_grid_backend(grid):
     grid._backend.grid_encode_forward, grid._backend.grid_encode_backward = fwd, bwd
 
 
+def table_fill(rows, C):
+    """deterministic table values in [-1, 1) from the entry index (the 2^21 table is too large to store)"""
+    i = np.arange(rows * C, dtype=np.uint64)
+    h = (i * np.uint64(2654435761) + np.uint64(12345)) & np.uint64(0xFFFFFFFF)
+    return (((h >> np.uint64(8)).astype(np.float64) / float(1 << 23)) - 1.0).astype(np.float32).reshape(rows, C)
+
+
+FIELD_OPT = dict(bound=2, cuda_ray=False, min_near=0.01, density_thresh=10, train_conf=0.01, detach_mask_from_field=False,
+                 mask_no_dir=False)
+
+
 def digest(a):
     return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8).copy()
 
@@ -156,6 +172,31 @@ def main():
     out5 = enc(torch.from_numpy(xin.copy()), bound=2, max_level=5)             # levels >= 5 stay zero, no input gradient
     out5.backward(torch.from_numpy(gout))
     G["enc_out_max5"], G["enc_grad_embeddings_max5"] = out5.detach().numpy(), enc.embeddings.grad.numpy().copy()
+    # ---- the field network's wiring (tcnn.Network served by the oracle MLP)
+    from oracle import torch_ref
+    tc = types.ModuleType("tinycudann")
+    tc.Network = torch_ref.Network
+    sys.modules["tinycudann"] = tc
+    sys.modules["gridencoder"].GridEncoder = grid.GridEncoder          # what gridencoder/__init__.py:1 exports
+    ng = importlib.import_module("nerf.network_grid")
+    net = ng.NeRFNetwork(types.SimpleNamespace(**FIELD_OPT))
+    assert (net.pos_en.gridtype, net.pos_en_dim, tuple(net.pos_en.embeddings.shape)) == ("tiled", 32, (23967296, 2))
+    net.pos_en.embeddings.data.copy_(torch.from_numpy(table_fill(*net.pos_en.embeddings.shape)))
+    for name in ("network", "density_network", "rgb_network"):
+        m = getattr(net, name)
+        w = (rng.uniform(-1, 1, m.params.numel()) * 0.35).astype(np.float32)
+        m.params.data.copy_(torch.from_numpy(w))
+        G["field_params_" + name] = w
+    fx = rng.uniform(-1.6, 1.6, (200, 3)).astype(np.float32)
+    fx[:20] *= 0.1                                                  # points inside the gaussian blob at the centre
+    fd = rng.randn(200, 3).astype(np.float32)
+    fd /= np.linalg.norm(fd, axis=-1, keepdims=True)
+    with torch.no_grad():
+        sig, rad, _ = net(torch.from_numpy(fx), torch.from_numpy(fd))
+        dens = net.density(torch.from_numpy(fx))["sigma"]
+    G["field_x"], G["field_d"], G["field_sigma"], G["field_radiances"], G["field_density"] = fx, fd, sig.numpy(), rad.numpy(), dens.numpy()
+    G["field_param_group_lrs"] = np.array([g["lr"] for g in net.get_params(5e-4)], np.float64)
+    del net
     # ---- the dense renderer on an analytic field: eval (deterministic importance sampling) and training (perturbed, random)
     rr = renderer.NeRFRenderer(types.SimpleNamespace(**RUN_OPT))
     rr.density = scene_density

@@ -131,3 +131,38 @@ def test_encoder_wrapper_matches_the_reference_autograd_function():
     np.testing.assert_allclose(out5.detach().numpy(), G["enc_out_max5"], rtol=1e-4, atol=3e-5)
     assert float(np.abs(out5.detach().numpy().reshape(-1, 8, 2)[:, 5:]).max()) == 0.0
     np.testing.assert_allclose(enc.embeddings.grad.numpy(), G["enc_grad_embeddings_max5"], rtol=1e-4, atol=3e-5)
+
+
+def test_field_network_wiring_matches_the_reference_network_grid():
+    """oracle/torch_ref.py NeRFNetwork.forward / density against the reference's NeRFNetwork (nerf/network_grid.py:70-193)
+    run with its real tiled 2^21 -> 8192 encoder; tinycudann.Network (absent, unpinned) was served by the oracle's MLP
+    restatement when the vectors were minted, so what this pins is the wiring: which features feed which network, the
+    gaussian blob + trunc_exp on the density head, [view embedding | trunk features] into the colour + mask head, and
+    the parameter groups / learning rates of get_params.  fp32 rel 1e-4 (abs 3e-5: see the encoder wrapper test)."""
+    from golden.make_golden_python import FIELD_OPT, table_fill
+    opt = torch_ref.default_opt(**FIELD_OPT)
+    net = torch_ref.NeRFNetwork(opt)                       # default encoder = network_grid.py:89-96
+    assert tuple(net.pos_en.embeddings.shape) == (23967296, 2) and net.pos_en.gridtype == "tiled"
+    with torch.no_grad():
+        net.pos_en.embeddings.copy_(torch.from_numpy(table_fill(*net.pos_en.embeddings.shape)))
+        for name in ("network", "density_network", "rgb_network"):
+            getattr(net, name).params.copy_(torch.from_numpy(G["field_params_" + name]))
+        x, d = torch.from_numpy(G["field_x"]), torch.from_numpy(G["field_d"])
+        sigma, rad, _ = net(x, d)
+        dens = net.density(x)["sigma"]
+    assert tuple(rad.shape) == (200, 4)
+    np.testing.assert_allclose(rad.numpy(), G["field_radiances"], rtol=1e-4, atol=3e-5)
+    # sigma = exp(head + blob): a relative tolerance on the exponent's argument (values reach 360)
+    np.testing.assert_allclose(np.log(sigma.numpy()), np.log(G["field_sigma"]), rtol=0, atol=2e-4)
+    np.testing.assert_allclose(np.log(dens.numpy()), np.log(G["field_density"]), rtol=0, atol=2e-4)
+    assert [g["lr"] for g in net.get_params(5e-4)] == list(G["field_param_group_lrs"])
+    # the product's module has the same parameter groups and state-dict names (constructed on the CPU: no kernel runs)
+    from customnerf_b200.nerf import NeRFNetwork
+    from customnerf_b200 import trainer
+    prod = NeRFNetwork(trainer.make_opt(cuda_ray=False, train_conf=0.01), encoding="tiledgrid", log2_hashmap_size=12,
+                       desired_resolution=64)
+    assert [g["lr"] for g in prod.get_params(5e-4)] == list(G["field_param_group_lrs"])
+    assert {k for k in prod.state_dict() if "params" in k or "embeddings" in k} == {
+        "pos_en.embeddings", "network.params", "density_network.params", "rgb_network.params"}
+    for name in ("network", "density_network", "rgb_network"):
+        assert getattr(prod, name).params.numel() == G["field_params_" + name].size, name
