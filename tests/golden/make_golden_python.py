@@ -14,6 +14,10 @@
   * NeRFRenderer.run           /root/reference/nerf/renderer.py:278-405   (the dense 'non-cuda_ray' renderer -- the path the
                                        CPU baseline of bench.py restates: stratified + importance sampling, sort / gather, LGIE
                                        all / fg / bg composites) on an analytic field, eval and training mode
+  * NeRFRenderer.run_cuda, training branch   /root/reference/nerf/renderer.py:597-640,688-716  (the occupancy renderer's glue:
+                                       near/far with the default min_near, the step_counter ring, march -> field -> composite,
+                                       result dict) with its native ops served by the C oracle and ``Tensor.cuda()`` made the
+                                       identity for the duration of the call (the method moves its inputs to the GPU, :603-604)
   * NeRFRenderer.update_extra_state   /root/reference/nerf/renderer.py:1658-1715  (occupancy-grid EMA update, thresholding,
                                        mean_count) with the two native ops it calls -- raymarching.morton3D / packbits,
                                        CUDA-only in the reference -- served by the CPU oracle (oracle/cpu_ops.py), so what
@@ -60,6 +64,17 @@ def stub_modules():
         n, f = cpu_ops.near_far_from_aabb(rays_o.numpy(), rays_d.numpy(), aabb.numpy(), min_near)
         return torch.from_numpy(n), torch.from_numpy(f)
     rm.near_far_from_aabb = near_far
+
+    def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None, mean_count=-1,
+                         perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024):
+        assert not perturb                   # the wrapper would draw torch.rand(N) on the GPU (raymarching.py:214-217)
+        cnt = step_counter.numpy()
+        out = cpu_ops.march_rays_train(rays_o.numpy(), rays_d.numpy(), bound, density_bitfield.numpy(), C, H, nears.numpy(),
+                                       fars.numpy(), cnt, mean_count, None, align, force_all_rays, dt_gamma, max_steps)
+        return tuple(torch.from_numpy(a) for a in out)
+    rm.march_rays_train = march_rays_train
+    from oracle import torch_ref as _tr
+    rm.composite_rays_train = _tr.composite_rays_train
     sys.modules["raymarching"] = rm
     pkg = types.ModuleType("nerf")
     pkg.__path__ = ["/root/reference/nerf"]
@@ -211,6 +226,25 @@ def main():
             G["run_%s_fg_%s" % (mode, key)] = res["fg"][key].detach().numpy()
             G["run_%s_bg_%s" % (mode, key)] = res["bg"][key].detach().numpy()
         G["run_%s_edit_mask" % mode] = res["edit_mask"].detach().numpy()
+    # ---- the occupancy renderer's training branch on the bear bit field
+    grid_d = syn.density_grid(2, 128)
+    thr = min(float(grid_d.mean()), 10.0)
+    rc = renderer.NeRFRenderer(types.SimpleNamespace(bound=2, cuda_ray=True, min_near=0.01, density_thresh=10, bg_color=None,
+                                                     if_smooth=False))
+    rc.density_bitfield = torch.from_numpy(cpu_ops.packbits(grid_d.numpy(), thr))
+    rc.forward = lambda x, d, *a, **k: (syn.bear_density(x), syn.bear_color(x) * (0.5 + 0.5 * d[:, :1].abs()), None)
+    rc.train()
+    o, d = run_rays()
+    keep_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for it in range(2):                       # two calls: the step_counter ring advances
+            res = rc.run_cuda(o, d, perturb=False, force_all_rays=True)
+            for key in ("image", "depth", "weights_sum", "mask"):
+                G["runcuda%d_%s" % (it, key)] = res[key].detach().numpy()
+        G["runcuda_step_counter"], G["runcuda_local_step"] = rc.step_counter.numpy().copy(), np.int64(rc.local_step)
+    finally:
+        torch.Tensor.cuda = keep_cuda
     # ---- occupancy-grid update (two consecutive updates: fresh grid, then the EMA-max path), bound 2 -> 2 cascades
     opt = types.SimpleNamespace(bound=2, cuda_ray=True, min_near=0.01, density_thresh=10)
     r = renderer.NeRFRenderer(opt)

@@ -166,3 +166,24 @@ def test_field_network_wiring_matches_the_reference_network_grid():
         "pos_en.embeddings", "network.params", "density_network.params", "rgb_network.params"}
     for name in ("network", "density_network", "rgb_network"):
         assert getattr(prod, name).params.numel() == G["field_params_" + name].size, name
+
+
+def test_occupancy_renderer_training_branch_matches_the_reference_run_cuda():
+    """oracle/torch_ref.py NeRFNetwork.run_cuda (training branch) against the reference's NeRFRenderer.run_cuda
+    (renderer.py:597-640, 688-716) run on the CPU with its native ops served by the C oracle: near/far with the default
+    min_near, the step_counter ring over two calls, march -> field -> composite, the result dict."""
+    from customnerf_b200 import synthetic as syn
+    from golden.make_golden_python import run_rays
+    net = torch_ref.NeRFNetwork(torch_ref.default_opt(cuda_ray=True), encoder_kwargs=dict(log2_hashmap_size=12, desired_resolution=64,
+                                                                                          gridtype="hash"))
+    grid = syn.density_grid(2, 128)
+    net.density_bitfield = torch.from_numpy(cpu_ops.packbits(grid.numpy(), min(float(grid.mean()), 10.0)))
+    net.forward = lambda x, d: (syn.bear_density(x), syn.bear_color(x) * (0.5 + 0.5 * d[:, :1].abs()), None)
+    net.train()
+    o, d = run_rays()
+    for it in range(2):
+        res = net.run_cuda(o, d, perturb=False, force_all_rays=True)
+        for key in ("image", "depth", "weights_sum"):
+            np.testing.assert_allclose(res[key].detach().numpy(), G["runcuda%d_%s" % (it, key)], rtol=1e-5, atol=1e-6, err_msg=key)
+        assert np.array_equal(res["mask"].numpy(), G["runcuda%d_mask" % it])
+    assert np.array_equal(net.step_counter.numpy(), G["runcuda_step_counter"]) and net.local_step == int(G["runcuda_local_step"])
