@@ -126,7 +126,12 @@ def install_grid_backend(grid):
         grad_embeddings.copy_(torch.from_numpy(ge))
         if grad_inputs is not None:
             grad_inputs.copy_(torch.from_numpy(gi))
+    def tv(inputs, embeddings, grad, offsets, weight, B, D, C, L, S, H, gridtype, align_corners):
+        out = cpu_ops.grad_total_variation(inputs.detach().numpy(), embeddings.detach().numpy(), grad.numpy(), offsets.numpy(), weight,
+                                           2.0 ** S, H, gridtype, align_corners)
+        grad.copy_(torch.from_numpy(out))
     grid._backend.grid_encode_forward, grid._backend.grid_encode_backward = fwd, bwd
+    grid._backend.grad_total_variation = tv
 
 
 def table_fill(rows, C):
@@ -187,6 +192,20 @@ def main():
     out5 = enc(torch.from_numpy(xin.copy()), bound=2, max_level=5)             # levels >= 5 stay zero, no input gradient
     out5.backward(torch.from_numpy(gout))
     G["enc_out_max5"], G["enc_grad_embeddings_max5"] = out5.detach().numpy(), enc.embeddings.grad.numpy().copy()
+    # ---- total-variation gradient wrapper (grid.py:171-192): explicit locations in [-bound, bound], then random ones
+    enc.embeddings.grad = torch.zeros_like(enc.embeddings)
+    tv_x = rng.uniform(-2, 2, (300, 3)).astype(np.float32)
+    enc.grad_total_variation(weight=1e-2, inputs=torch.from_numpy(tv_x), bound=2)
+    G["tv_inputs"], G["tv_grad_explicit"] = tv_x, enc.embeddings.grad.numpy().copy()
+    torch.manual_seed(11)
+    enc.grad_total_variation(weight=1e-2, B=500)                  # accumulates on top; draws torch.rand(B, 3)
+    G["tv_grad_then_random"] = enc.embeddings.grad.numpy().copy()
+    try:
+        enc.embeddings.grad = None
+        enc.grad_total_variation()
+        G["tv_raises_without_grad"] = np.int64(0)
+    except ValueError:
+        G["tv_raises_without_grad"] = np.int64(1)
     # ---- the field network's wiring (tcnn.Network served by the oracle MLP)
     from oracle import torch_ref
     tc = types.ModuleType("tinycudann")

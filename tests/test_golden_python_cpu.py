@@ -138,7 +138,9 @@ def test_field_network_wiring_matches_the_reference_network_grid():
     run with its real tiled 2^21 -> 8192 encoder; tinycudann.Network (absent, unpinned) was served by the oracle's MLP
     restatement when the vectors were minted, so what this pins is the wiring: which features feed which network, the
     gaussian blob + trunc_exp on the density head, [view embedding | trunk features] into the colour + mask head, and
-    the parameter groups / learning rates of get_params.  fp32 rel 1e-4 (abs 3e-5: see the encoder wrapper test)."""
+    the parameter groups / learning rates of get_params.  Two independent fp32 encoders meet here at resolution 8192 (one ulp
+    of a [0,1] coordinate is 5e-4 of a finest-level cell), followed by three layers: outputs abs 2e-4, the density's exponent
+    abs 1e-3 (0.1 % of sigma) -- a wrong wiring moves these by O(1)."""
     from golden.make_golden_python import FIELD_OPT, table_fill
     opt = torch_ref.default_opt(**FIELD_OPT)
     net = torch_ref.NeRFNetwork(opt)                       # default encoder = network_grid.py:89-96
@@ -151,10 +153,10 @@ def test_field_network_wiring_matches_the_reference_network_grid():
         sigma, rad, _ = net(x, d)
         dens = net.density(x)["sigma"]
     assert tuple(rad.shape) == (200, 4)
-    np.testing.assert_allclose(rad.numpy(), G["field_radiances"], rtol=1e-4, atol=3e-5)
+    np.testing.assert_allclose(rad.numpy(), G["field_radiances"], rtol=1e-4, atol=2e-4)
     # sigma = exp(head + blob): a relative tolerance on the exponent's argument (values reach 360)
-    np.testing.assert_allclose(np.log(sigma.numpy()), np.log(G["field_sigma"]), rtol=0, atol=2e-4)
-    np.testing.assert_allclose(np.log(dens.numpy()), np.log(G["field_density"]), rtol=0, atol=2e-4)
+    np.testing.assert_allclose(np.log(sigma.numpy()), np.log(G["field_sigma"]), rtol=0, atol=1e-3)
+    np.testing.assert_allclose(np.log(dens.numpy()), np.log(G["field_density"]), rtol=0, atol=1e-3)
     assert [g["lr"] for g in net.get_params(5e-4)] == list(G["field_param_group_lrs"])
     # the product's module has the same parameter groups and state-dict names (constructed on the CPU: no kernel runs)
     from customnerf_b200.nerf import NeRFNetwork
@@ -187,3 +189,20 @@ def test_occupancy_renderer_training_branch_matches_the_reference_run_cuda():
             np.testing.assert_allclose(res[key].detach().numpy(), G["runcuda%d_%s" % (it, key)], rtol=1e-5, atol=1e-6, err_msg=key)
         assert np.array_equal(res["mask"].numpy(), G["runcuda%d_mask" % it])
     assert np.array_equal(net.step_counter.numpy(), G["runcuda_step_counter"]) and net.local_step == int(G["runcuda_local_step"])
+
+
+def test_total_variation_wrapper_matches_the_reference():
+    """oracle grad_total_variation against the reference's GridEncoder.grad_total_variation (grid.py:171-192) run on the CPU with
+    its native entry point served by the C oracle: the [-bound, bound] -> [0,1] mapping of explicit locations, accumulation into
+    .grad, the torch.rand(B, D) draw of the default path, the ValueError without a gradient.  Exact (same C arithmetic)."""
+    from golden.make_golden_python import ENC_CFG
+    assert int(G["tv_raises_without_grad"]) == 1
+    offs, scale = cpu_ops.grid_offsets(**{k: v for k, v in ENC_CFG.items() if k != "gridtype"})
+    emb = G["enc_embeddings"]
+    grad = np.zeros_like(emb)
+    x01 = (G["tv_inputs"] + np.float32(2)) / np.float32(4)
+    grad = cpu_ops.grad_total_variation(x01, emb, grad, offs, 1e-2, scale, ENC_CFG["base_resolution"])
+    assert np.array_equal(grad, G["tv_grad_explicit"]) and float(np.abs(grad).max()) > 0
+    torch.manual_seed(11)
+    grad = cpu_ops.grad_total_variation(torch.rand(500, 3).numpy(), emb, grad, offs, 1e-2, scale, ENC_CFG["base_resolution"])
+    assert np.array_equal(grad, G["tv_grad_then_random"])
