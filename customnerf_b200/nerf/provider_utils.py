@@ -27,27 +27,29 @@ def ray_kernel(poses, fx, fy, cx, cy, H, W, inds=None, offset=(0.5, 0.5), rays_o
     return rays_o, rays_d
 
 
+def _sample_pixels(B, H, W, N, error_map, device):
+    """Pixel indices [B, N] of a training batch, and the coarse cells they came from (None without an error map).
+    Same draws, in the same order, as the reference (:263-284): uniform with replacement -- one index set shared by the
+    batch -- or, with a 128 x 128 error map, cells drawn without replacement by error and a uniform jitter inside each."""
+    if error_map is None:
+        return torch.randint(0, H * W, size=[N], device=device).expand([B, N]), None
+    cells = torch.multinomial(error_map.to(device), N, replacement=False)
+    cell_h, cell_w = H / 128, W / 128
+    rows = ((cells // 128) * cell_h + torch.rand(B, N, device=device) * cell_h).long().clamp(max=H - 1)
+    cols = ((cells % 128) * cell_w + torch.rand(B, N, device=device) * cell_w).long().clamp(max=W - 1)
+    return rows * W + cols, cells
+
+
 @torch.no_grad()
 def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, offset=(0.5, 0.5)):
     """poses [B,4,4] cam2world, intrinsics (fx, fy, cx, cy) -> {'rays_o', 'rays_d' [B,N,3], 'inds' [B,N] when N > 0,
     'inds_coarse' with an error map}"""
-    device = poses.device
-    B = poses.shape[0]
     fx, fy, cx, cy = [float(v) for v in intrinsics]
-    results = {}
-    inds = None
+    results, inds = {}, None
     if N > 0:
-        N = min(N, H * W)
-        if error_map is None:
-            inds = torch.randint(0, H * W, size=[N], device=device).expand([B, N])          # may duplicate (:266)
-        else:
-            inds_coarse = torch.multinomial(error_map.to(device), N, replacement=False)     # [B, N] in [0, 128*128)
-            inds_x, inds_y = inds_coarse // 128, inds_coarse % 128
-            sx, sy = H / 128, W / 128
-            inds_x = (inds_x * sx + torch.rand(B, N, device=device) * sx).long().clamp(max=H - 1)
-            inds_y = (inds_y * sy + torch.rand(B, N, device=device) * sy).long().clamp(max=W - 1)
-            inds = inds_x * W + inds_y
-            results['inds_coarse'] = inds_coarse
+        inds, cells = _sample_pixels(poses.shape[0], H, W, min(N, H * W), error_map, poses.device)
+        if cells is not None:
+            results['inds_coarse'] = cells      # the trainer updates the error map through these
         results['inds'] = inds
     results['rays_o'], results['rays_d'] = ray_kernel(poses, fx, fy, cx, cy, H, W, inds, offset)
     return results

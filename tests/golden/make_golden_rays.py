@@ -54,6 +54,17 @@ def main():
         G[name + "_rays_d"] = out["rays_d"].contiguous().numpy()
         if "inds" in out:
             G[name + "_inds"] = out["inds"].contiguous().numpy()
+    # the pixel sampling of a training batch (:263-284): uniform, and error-map importance sampling; seeded CPU generator
+    H, W, B, N = 105, 142, 2, 300
+    poses = torch.from_numpy(np.stack([pose(1.0, 0.4, 1.5), pose(1.3, 2.0, 1.6)]))
+    intr = np.array([120.0, 120.0, W / 2, H / 2], np.float32)
+    em = torch.rand(B, 128 * 128, generator=torch.Generator().manual_seed(9))
+    torch.manual_seed(4)
+    out = ref.get_rays(poses, intr, H, W, N, error_map=em)
+    G["sample_error_map"], G["sample_em_inds"], G["sample_em_coarse"] = em.numpy(), out["inds"].numpy(), out["inds_coarse"].numpy()
+    torch.manual_seed(5)
+    G["sample_uniform_inds"] = ref.get_rays(poses, intr, H, W, N)["inds"].contiguous().numpy()
+    G["sample_HWBN"] = np.array([H, W, B, N], np.int64)
     np.savez_compressed(os.path.join(HERE, "ref_get_rays.npz"), **G)
     print("wrote", os.path.join(HERE, "ref_get_rays.npz"), {k: v.shape for k, v in G.items()})
 
