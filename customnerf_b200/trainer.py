@@ -39,6 +39,24 @@ def build_scene_model(device, log2_hashmap_size=19, desired_resolution=2048, enc
     return model
 
 
+def pretrain_loss(outputs, rgbs, mask, opt):
+    """The reconstruction loss of ``Trainer_Nerf.train_step_pretrain`` (nerf/utils_init_nerf.py:219-239) on a render result:
+    train_rgb * MSE(image, rgbs) [+ train_conf * MSE(render_mask, mask) with the mask head].  Returns what the reference's
+    step returns after rendering: (pred_rgb, mask_volume, loss, loss_dict); mask_volume is weights_sum clamped to
+    [1e-5, 1 - 1e-5].  FusedTrainStep(mask_weight=train_conf) computes the same loss inside the compositing kernel
+    (train_rgb is 1 in every shipped configuration, main.py)."""
+    pred_rgb = outputs['image']
+    B, N = pred_rgb.shape[:2]
+    mask_volume = torch.clamp(outputs['weights_sum'].reshape(B, N), 1e-5, 1 - 1e-5)
+    loss_c = getattr(opt, 'train_rgb', 1.0) * F.mse_loss(pred_rgb.reshape(-1, 3), rgbs.reshape(-1, 3).float(), reduction='mean')
+    loss, loss_dict = loss_c, {'loss_c': loss_c.item()}
+    if getattr(opt, 'train_conf', 0):
+        loss_m = opt.train_conf * F.mse_loss(outputs['render_mask'].reshape(-1), mask.reshape(-1).float(), reduction='mean')
+        loss = loss + loss_m
+        loss_dict['loss_m'] = loss_m.item()
+    return pred_rgb, mask_volume, loss, loss_dict
+
+
 class TrainStep:
     def __init__(self, model, lr=5e-4, fp16=True, world_size=1, grad_sync=None, perturb=True):
         self.model = model

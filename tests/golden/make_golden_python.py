@@ -18,6 +18,9 @@
                                        near/far with the default min_near, the step_counter ring, march -> field -> composite,
                                        result dict) with its native ops served by the C oracle and ``Tensor.cuda()`` made the
                                        identity for the duration of the call (the method moves its inputs to the GPU, :603-604)
+  * Trainer_Nerf.train_step_pretrain   /root/reference/nerf/utils_init_nerf.py:194-241  (the reconstruction loss: train_rgb * MSE
+                                       + train_conf * MSE of the rendered mask, the clamped mask volume) on a canned render result,
+                                       with the guidance modules it imports (nerf.sd, nerf.clip, clip, tensorboardX, imageio) stubbed
   * NeRFRenderer.update_extra_state   /root/reference/nerf/renderer.py:1658-1715  (occupancy-grid EMA update, thresholding,
                                        mean_count) with the two native ops it calls -- raymarching.morton3D / packbits,
                                        CUDA-only in the reference -- served by the CPU oracle (oracle/cpu_ops.py), so what
@@ -264,6 +267,34 @@ def main():
         G["runcuda_step_counter"], G["runcuda_local_step"] = rc.step_counter.numpy().copy(), np.int64(rc.local_step)
     finally:
         torch.Tensor.cuda = keep_cuda
+    # ---- the reconstruction loss of the trainer
+    for name in ("imageio", "tensorboardX", "clip"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sd_stub, clip_stub = types.ModuleType("nerf.sd"), types.ModuleType("nerf.clip")
+    sd_stub.StableDiffusion, clip_stub.CLIP = object, object
+    sys.modules["nerf.sd"], sys.modules["nerf.clip"] = sd_stub, clip_stub
+    utils = importlib.import_module("nerf.utils_init_nerf")
+    Npx = 96
+    canned = {"image": torch.from_numpy(rng.uniform(0, 1, (1, Npx, 3)).astype(np.float32)).requires_grad_(),
+              "weights_sum": torch.from_numpy(np.concatenate([[0.0, 1.0], rng.uniform(0, 1, Npx - 2)]).astype(np.float32)),
+              "render_mask": torch.from_numpy(rng.uniform(0, 1, (1, Npx, 1)).astype(np.float32)).requires_grad_()}
+    gt_rgb, gt_mask = rng.uniform(0, 1, (Npx, 3)).astype(np.float32), (rng.uniform(0, 1, (Npx, 1)) > 0.5).astype(np.float32)
+    for tag, tconf in (("conf", 0.01), ("noconf", 0)):
+        topt = types.SimpleNamespace(batch_rays=0, train_rgb=1.0, train_conf=tconf)
+        me = types.SimpleNamespace(device="cpu", opt=topt, model=types.SimpleNamespace(render=lambda *a, **k: canned))
+        for t in (canned["image"], canned["render_mask"]):
+            t.grad = None
+        data = (torch.from_numpy(gt_rgb), torch.from_numpy(gt_mask), torch.zeros(Npx, 3), torch.zeros(Npx, 3), 8, 12, "img")
+        pred, mvol, loss, ld = utils.Trainer_Nerf.train_step_pretrain(me, data)
+        loss.backward()
+        G["loss_%s_value" % tag], G["loss_%s_mask_volume" % tag] = np.float64(loss.item()), mvol.detach().numpy()
+        G["loss_%s_dict" % tag] = np.array([ld["loss_c"], ld.get("loss_m", -1.0)], np.float64)
+        G["loss_%s_grad_image" % tag] = canned["image"].grad.numpy().copy()
+        G["loss_%s_grad_mask" % tag] = (canned["render_mask"].grad if canned["render_mask"].grad is not None
+                                        else torch.zeros_like(canned["render_mask"])).numpy().copy()
+    for k in ("image", "weights_sum", "render_mask"):
+        G["loss_in_" + k] = canned[k].detach().numpy()
+    G["loss_in_rgb"], G["loss_in_gtmask"] = gt_rgb, gt_mask
     # ---- occupancy-grid update (two consecutive updates: fresh grid, then the EMA-max path), bound 2 -> 2 cascades
     opt = types.SimpleNamespace(bound=2, cuda_ray=True, min_near=0.01, density_thresh=10)
     r = renderer.NeRFRenderer(opt)

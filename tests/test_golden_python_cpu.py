@@ -206,3 +206,30 @@ def test_total_variation_wrapper_matches_the_reference():
     torch.manual_seed(11)
     grad = cpu_ops.grad_total_variation(torch.rand(500, 3).numpy(), emb, grad, offs, 1e-2, scale, ENC_CFG["base_resolution"])
     assert np.array_equal(grad, G["tv_grad_then_random"])
+
+
+def test_reconstruction_loss_matches_the_reference_trainer():
+    """customnerf_b200/trainer.py: pretrain_loss against the reference's Trainer_Nerf.train_step_pretrain
+    (utils_init_nerf.py:194-241) run on a canned render result: loss, its parts, the clamped mask volume, and the gradients
+    with respect to the rendered image and mask (what FusedTrainStep's compositing kernel produces as g_image /
+    g_render_mask).  Same torch ops: rel 1e-6."""
+    import types
+    from customnerf_b200 import trainer
+    for tag, tconf in (("conf", 0.01), ("noconf", 0)):
+        out = {"image": torch.from_numpy(G["loss_in_image"].copy()).requires_grad_(),
+               "weights_sum": torch.from_numpy(G["loss_in_weights_sum"]),
+               "render_mask": torch.from_numpy(G["loss_in_render_mask"].copy()).requires_grad_()}
+        opt = types.SimpleNamespace(train_rgb=1.0, train_conf=tconf)
+        pred, mvol, loss, ld = trainer.pretrain_loss(out, torch.from_numpy(G["loss_in_rgb"]), torch.from_numpy(G["loss_in_gtmask"]), opt)
+        loss.backward()
+        assert abs(loss.item() - float(G["loss_%s_value" % tag])) <= 1e-6 * float(G["loss_%s_value" % tag])
+        want_c, want_m = G["loss_%s_dict" % tag]
+        assert abs(ld["loss_c"] - want_c) <= 1e-6 * want_c and (("loss_m" in ld) == (want_m >= 0))
+        if want_m >= 0:
+            assert abs(ld["loss_m"] - want_m) <= 1e-6 * want_m
+        np.testing.assert_allclose(mvol.numpy(), G["loss_%s_mask_volume" % tag], rtol=1e-6)
+        assert mvol.min() >= 1e-5 and mvol.max() <= 1 - 1e-5
+        np.testing.assert_allclose(out["image"].grad.numpy(), G["loss_%s_grad_image" % tag], rtol=1e-6, atol=1e-9)
+        gm = out["render_mask"].grad
+        np.testing.assert_allclose((gm if gm is not None else torch.zeros_like(out["render_mask"])).numpy(),
+                                   G["loss_%s_grad_mask" % tag], rtol=1e-6, atol=1e-9)
