@@ -1,0 +1,68 @@
+"""-m gpu, OPT-IN (NB200_RUN_UNVERIFIED=1): the product's GPU paths against the golden vectors minted from the reference's own
+Python code (tests/golden/ref_python.npz, ref_wrappers.npz).  These vectors were minted after round 1's GPU budget had ended,
+so the tests below have never run on a B200; they stay opt-in until a first run has confirmed their tolerances (the oracle
+and the product's host-side Python are already pinned to the same vectors on the CPU, and the product is pinned to the oracle by
+the other GPU tests).  Enable with NB200_RUN_UNVERIFIED=1 and fold them into the default suite once green."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get("NB200_RUN_UNVERIFIED"), reason="opt-in: never run on a GPU yet (see module docstring)")]
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_dense_renderer_eval_mode_matches_the_reference_run():
+    """customnerf_b200/nerf/rendering.py NeRFRenderer.run (torch ops + the CUDA near/far op) in eval mode (deterministic
+    importance sampling) on the analytic field the vectors were minted with: fp32 rel 1e-4 (near/far differs from the C
+    oracle's by fp32 rounding of a division at most)."""
+    from customnerf_b200 import trainer
+    from customnerf_b200.nerf import NeRFNetwork
+    from golden.make_golden_python import RUN_OPT, RUN_KEYS, field_forward, scene_density, run_rays
+    G = np.load(os.path.join(HERE, "golden", "ref_python.npz"))
+    net = NeRFNetwork(trainer.make_opt(**RUN_OPT), encoding="hashgrid", log2_hashmap_size=12, desired_resolution=64).cuda()
+    net.density = lambda x: {k: v.cuda() for k, v in scene_density(x.cpu()).items()}
+    net.forward = lambda x, d: tuple(None if t is None else t.cuda() for t in field_forward(x.cpu(), d.cpu()))
+    net.eval()
+    o, d = run_rays()
+    with torch.no_grad():
+        res = net.run(o.cuda(), d.cuda(), num_steps=16, upsample_steps=16, perturb=False)
+    for key in RUN_KEYS:
+        for sub, r in (("", res), ("fg_", res["fg"]), ("bg_", res["bg"])):
+            want = G["run_eval_%s%s" % (sub, key)]
+            np.testing.assert_allclose(r[key].cpu().numpy().reshape(want.shape), want, rtol=1e-4, atol=1e-5, err_msg=sub + key)
+
+
+def test_raymarching_wrappers_match_the_reference_wrappers():
+    """customnerf_b200/raymarching ops against the reference's wrappers (ref_wrappers.npz): sizes incl. the alignment quirk,
+    counters and per-ray (id, count) exact; samples fp32-identical per ray segment (the product's offsets are scan-ordered,
+    one valid member of the reference's atomics-ordered set, so segments are compared after sorting rays by id)."""
+    from customnerf_b200 import raymarching as rm
+    from golden.make_golden_wrappers import scene
+    G = np.load(os.path.join(HERE, "golden", "ref_wrappers.npz"))
+    grid, thr, o, d = scene()
+    o, d = o.cuda(), d.cuda()
+    aabb = torch.tensor([-2, -2, -2, 2, 2, 2], dtype=torch.float32, device="cuda")
+    n0, f0 = rm.near_far_from_aabb(o, d, aabb)
+    np.testing.assert_allclose(torch.stack([n0, f0]).cpu().numpy(), G["nf_default"], rtol=1e-6)
+    bits = rm.packbits(grid.cuda(), thr)
+    assert np.array_equal(bits.cpu().numpy()[:4096], G["packbits_head"])
+    ind = rm.morton3D(torch.from_numpy(G["morton_coords"]).cuda())
+    assert np.array_equal(ind.cpu().numpy(), G["morton_indices"])
+    for tag, kw in (("all", dict(mean_count=-1, perturb=False, align=128, force_all_rays=True)),
+                    ("budget", dict(mean_count=1000, perturb=False, align=128, force_all_rays=False))):
+        counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+        n_ref, f_ref = torch.from_numpy(G["nf_default"][0]).cuda(), torch.from_numpy(G["nf_default"][1]).cuda()
+        xyzs, dirs, deltas, rays = rm.march_rays_train(o, d, 2, bits, 2, 128, n_ref, f_ref, counter, kw["mean_count"], kw["perturb"],
+                                                       kw["align"], kw["force_all_rays"], 0, 1024)
+        assert tuple(xyzs.shape) == G["mt_%s_xyzs" % tag].shape, tag
+        want_rays, got_rays = G["mt_%s_rays" % tag], rays.cpu().numpy()
+        if tag == "all":
+            assert np.array_equal(counter.cpu().numpy(), G["mt_all_counter"])
+            w, g = want_rays[np.argsort(want_rays[:, 0])], got_rays[np.argsort(got_rays[:, 0])]
+            assert np.array_equal(w[:, [0, 2]], g[:, [0, 2]])
+            X, Xw = xyzs.cpu().numpy(), G["mt_all_xyzs"]
+            for (rid, off_w, cnt), (_, off_g, _) in zip(w, g):
+                assert np.array_equal(X[off_g:off_g + cnt], Xw[off_w:off_w + cnt]), rid
