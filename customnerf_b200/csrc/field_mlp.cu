@@ -149,14 +149,14 @@ __device__ __noinline__ void epilogue_row64(uint32_t tmem_row_addr, uint8_t *til
     }
 }
 
-// direction encoding get_embedder(4) of one row: [d, sin(2^k d), cos(2^k d)] (27) then five 1.0 lanes (the padded
-// inputs 91..95 of the colour head), written as chunks 4..7 of row `row` of the XV tile
-__device__ __noinline__ void write_view_chunks(uint8_t *xv, uint32_t row, float d0, float d1, float d2, bool valid) {
-    float e[32];
+// direction encoding get_embedder(4) of one row (nerf/base.py:42-77): e = [d, sin(2^k d), cos(2^k d)] (27 lanes, input
+// first, then per frequency sin then cos) followed by five 1.0 lanes (the padded inputs 91..95 of the colour head).
+// sin / cos of 2^k d: one __sincosf per component (|d| <= 1 for unit directions: abs error < 4e-7), then the double-angle
+// identities (three doublings; the compounded error stays below 2e-6, asserted against sin/cos(2^k d) through
+// nb200_freq_embed in tests/test_gpu_field_mlp.py -- three orders below the fp16 rounding of the operand); one sincosf
+// body instead of twelve in the instruction stream.
+__device__ __forceinline__ void view_embed32(float d0, float d1, float d2, float (&e)[32]) {
     e[0] = d0; e[1] = d1; e[2] = d2;
-    // sin / cos of 2^k d: one __sincosf per component (|d| <= 1 for unit directions: abs error < 4e-7, three orders
-    // below the fp16 rounding of the operand), then the double-angle identities (three doublings add < 1e-6 of
-    // error, far below the fp16 rounding of the operand; one sincosf body instead of twelve in the instruction stream)
     float s0, c0, s1, c1, s2, c2;
     __sincosf(d0, &s0, &c0); __sincosf(d1, &s1, &c1); __sincosf(d2, &s2, &c2);
 #pragma unroll
@@ -169,6 +169,12 @@ __device__ __noinline__ void write_view_chunks(uint8_t *xv, uint32_t row, float 
     }
 #pragma unroll
     for (int j = 27; j < 32; j++) e[j] = 1.0f;
+}
+
+// ... written as chunks 4..7 of row `row` of the XV tile
+__device__ __noinline__ void write_view_chunks(uint8_t *xv, uint32_t row, float d0, float d1, float d2, bool valid) {
+    float e[32];
+    view_embed32(d0, d1, d2, e);
 #pragma unroll
     for (uint32_t c = 0; c < 4; c++) {
         uint4 pk = make_uint4(pack_h2(e[c * 8], e[c * 8 + 1]), pack_h2(e[c * 8 + 2], e[c * 8 + 3]),
@@ -176,6 +182,18 @@ __device__ __noinline__ void write_view_chunks(uint8_t *xv, uint32_t row, float 
         if (!valid) pk = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(row, 4 + c)) = pk;
     }
+}
+
+// the embedding as the field kernels compute it, fp32 [M, 27] (get_embedder(4) as a device op; also the test hook that
+// pins the double-angle evaluation above)
+__global__ void __launch_bounds__(256)
+k_freq_embed(const float *__restrict__ dirs, float *__restrict__ out, uint32_t M) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= M) return;
+    float e[32];
+    view_embed32(dirs[(size_t)g * 3], dirs[(size_t)g * 3 + 1], dirs[(size_t)g * 3 + 2], e);
+#pragma unroll
+    for (int j = 0; j < 27; j++) out[(size_t)g * 27 + j] = e[j];
 }
 
 __global__ void __launch_bounds__(128, 2)
@@ -810,6 +828,14 @@ uint32_t nb200_field_wgrad_scratch_bytes(void) {
 }
 
 uint32_t nb200_field_weight_image_bytes(void) { return F_BYTES; }
+
+int nb200_freq_embed(const float *dirs, float *out, uint32_t M, void *stream) {
+    if (M == 0) return 0;
+    if (!dirs || !out) return NB200_E_BAD_ARG;
+    k_freq_embed<<<nb_div_up(M, 256), 256, 0, nb_stream(stream)>>>(dirs, out, M);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
 
 int nb200_field_pack_weights(const float *trunk, const float *density, const float *rgb, void *fwd_img, void *bwd_img,
                              void *stream) {

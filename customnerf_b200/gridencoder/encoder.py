@@ -122,12 +122,19 @@ grid_encode = _grid_encode.apply
 
 def level_offsets(input_dim, num_levels, per_level_scale, base_resolution, max_params, align_corners=False):
     """Row offset of every level, int32 [L+1] (reference layout rule, grid.py:124-134): level i has
-    min(max_params, (ceil(H * s^i) + 1)^D) rows (no +1 with align_corners), rounded up to a multiple of 8."""
-    res = np.ceil(base_resolution * np.power(float(per_level_scale), np.arange(num_levels))).astype(np.int64)
-    side = res if align_corners else res + 1
-    rows = np.minimum(max_params, side ** input_dim)
-    rows = (np.ceil(rows / 8) * 8).astype(np.int64)
-    return np.concatenate([[0], np.cumsum(rows)]).astype(np.int32)
+    min(max_params, (ceil(H * s^i) + 1)^D) rows (no +1 with align_corners), rounded up to a multiple of 8.
+    Evaluated per level on Python scalars like the reference does (scalar ``**``: libm pow and arbitrary-precision integer
+    powers), so that the table -- and with it checkpoint compatibility -- cannot differ by a vectorised-pow ulp or an
+    int64 overflow at D = 5."""
+    offsets, offset = [], 0
+    for i in range(num_levels):
+        resolution = int(np.ceil(base_resolution * per_level_scale ** i))
+        rows = min(int(max_params), (resolution if align_corners else resolution + 1) ** input_dim)
+        rows = int(np.ceil(rows / 8) * 8)
+        offsets.append(offset)
+        offset += rows
+    offsets.append(offset)
+    return np.array(offsets, dtype=np.int32)
 
 
 class GridEncoder(nn.Module):

@@ -135,8 +135,9 @@ class NeRFNetwork(NeRFRenderer):
         if bgc:
             bg = torch.tensor([list(bgc)], dtype=torch.float32, device=image.device)
             image = image + (1 - weights_sum).unsqueeze(-1) * bg
-        elif bg_color is not None:
-            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        # (the ``bg_color`` argument is accepted and ignored, as in the reference: its blend is commented out at
+        #  renderer.py:700, only ``opt.bg_color`` is honoured -- the editing trainer passes a random colour here,
+        #  utils_init_nerf.py:358-365, which must not reach the image)
         return {'image': image.view(*prefix, 3), 'depth': depth.view(*prefix), 'weights_sum': weights_sum.reshape(*prefix),
                 'mask': (nears < fars).reshape(*prefix)}
 

@@ -238,8 +238,9 @@ class NeRFRenderer(nn.Module):
         if bgc:
             bg = torch.tensor([list(bgc)], dtype=torch.float32, device=dev)
             image = image + (1 - weights_sum).unsqueeze(-1) * bg
-        elif bg_color is not None:
-            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        # (the ``bg_color`` argument is accepted and ignored, as in the reference: its blend is commented out at
+        #  renderer.py:700, only ``opt.bg_color`` is honoured -- the editing trainer passes a random colour here,
+        #  utils_init_nerf.py:358-365, which must not reach the image)
         results['image'] = image.view(*prefix, 3)
         results['depth'] = depth.view(*prefix)
         results['weights_sum'] = weights_sum.reshape(*prefix)

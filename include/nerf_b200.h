@@ -196,6 +196,9 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
 /* wg_scratch: nb200_field_wgrad_scratch_bytes() bytes (16-byte aligned) of per-CTA partial weight-gradient sums that a
  * second small kernel adds into g_* (deterministic, no contended atomics); NULL = fp32 atomics straight on g_*. */
 uint32_t nb200_field_wgrad_scratch_bytes(void);
+/* get_embedder(4) of nerf/base.py:42-77 exactly as the field kernels evaluate it: dirs f32 [M,3] -> out f32 [M,27] =
+ * [d, sin d, cos d, sin 2d, cos 2d, sin 4d, cos 4d, sin 8d, cos 8d] (one sincos + three angle doublings per component). */
+int nb200_freq_embed(const float *dirs, float *out, uint32_t M, void *stream);
 
 /* ============================================================================================
  * fused train step (no single reference counterpart: replaces the Python glue between the ops --

@@ -1,16 +1,12 @@
-"""-m gpu, OPT-IN (NB200_RUN_UNVERIFIED=1): the product's GPU paths against the golden vectors minted from the reference's own
-Python code (tests/golden/ref_python.npz, ref_wrappers.npz).  These vectors were minted after round 1's GPU budget had ended,
-so the tests below have never run on a B200; they stay opt-in until a first run has confirmed their tolerances (the oracle
-and the product's host-side Python are already pinned to the same vectors on the CPU, and the product is pinned to the oracle by
-the other GPU tests).  Enable with NB200_RUN_UNVERIFIED=1 and fold them into the default suite once green."""
+"""-m gpu: the product's GPU paths against the golden vectors minted from the reference's own Python code run on the CPU
+(tests/golden/ref_python.npz, ref_wrappers.npz; scripts tests/golden/make_golden_{python,wrappers}.py)."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("NB200_RUN_UNVERIFIED"), reason="opt-in: never run on a GPU yet (see module docstring)")]
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 

@@ -124,6 +124,44 @@ def test_update_extra_state_builds_the_same_bitfield(scene):
     assert (grid >= 0).all()
 
 
+def test_update_extra_state_reproduces_the_reference_bitfield(monkeypatch):
+    """NeRFRenderer.update_extra_state on the GPU against the reference's own update_extra_state (renderer.py:1658-1715, run
+    on the CPU by tests/golden/make_golden_python.py): same analytic density (evaluated on the host so that its values are the
+    reference run's bit for bit), same jitter (the reference's torch.rand_like draws, replayed from the same CPU generator
+    state), two consecutive updates (fresh grid, then the EMA-max path).  The grid must be bit-identical (SHA-256); the bit
+    field too, except for cells that sit within one part in 10^6 of the threshold (the mean is summed in a different order on
+    the device) -- none on this scene."""
+    import hashlib
+    import os
+    from customnerf_b200 import synthetic as syn, trainer
+    from customnerf_b200.nerf import NeRFNetwork
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_python.npz"))
+    net = NeRFNetwork(trainer.make_opt(bound=2, cuda_ray=True, min_near=0.01, density_thresh=10), encoding="hashgrid",
+                      log2_hashmap_size=12, desired_resolution=64).cuda()
+    net.density = lambda x: {"sigma": syn.bear_density(x.cpu()).cuda()}
+    monkeypatch.setattr(torch, "rand_like", lambda t, **kw: torch.rand(t.shape, dtype=t.dtype).to(t.device))
+    torch.manual_seed(123)
+    net.local_step = 3
+    net.step_counter[:3, 0] = torch.tensor([100, 200, 301], dtype=torch.int32, device="cuda")
+
+    def digest(a):
+        return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+    for k in range(2):
+        net.update_extra_state()
+        grid, bits = net.density_grid.cpu().numpy(), net.density_bitfield.cpu().numpy()
+        np.testing.assert_allclose(grid.reshape(-1)[::1009], G["occ%d_grid_sample" % k], rtol=0, atol=0)
+        assert np.array_equal(digest(grid), G["occ%d_grid_sha256" % k]), "density grid differs from the reference's"
+        md = float(G["occ%d_mean_density" % k])
+        assert abs(float(net.mean_density) - md) <= 1e-6 * md
+        thr = min(md, 10.0)
+        borderline = int((np.abs(grid - thr) <= 1e-6 * thr).sum())
+        if borderline == 0:
+            assert np.array_equal(digest(bits), G["occ%d_bitfield_sha256" % k]), "bit field differs from the reference's"
+        assert abs(int(np.unpackbits(bits).sum()) - int(G["occ%d_bits_set" % k])) <= borderline
+        assert int(net.mean_count) == int(G["occ%d_mean_count" % k])
+        assert [net.iter_density, net.local_step] == list(G["occ%d_iter_local" % k])
+
+
 def test_train_step_harness_runs_and_reduces_loss(scene):
     """30 Adam steps on rays that hit the bear: the loss over those pixels goes down (evaluated without perturbation)"""
     from customnerf_b200 import trainer, synthetic as syn
