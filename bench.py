@@ -178,16 +178,22 @@ def cpu_reference_run(steps, warmup, n_rays):
 
 
 def run_reference_arm(args):
+    """--impl reference: the CPU restatement, EXACTLY args.steps timed steps after args.warmup warm-up steps (what the line
+    prints is what ran).  A step is a bounded sample of the workload: ``n_rays`` of the image's rays, sized from the step
+    count so that the whole run stays within a few minutes on the box's host cores (~0.7 s per 2048-ray step on 16 cores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_rays = 2048
-    res = cpu_reference_run(max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)), n_rays)
-    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    budget_rays = 2048 * 60                        # ~40 s of CPU work in total at the measured ~3 k rays/s
+    n_rays = int(min(2048, max(128, budget_rays // (steps + warmup))))
+    res = cpu_reference_run(steps, warmup, n_rays)
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference's dense PyTorch render path on "
-                       "a %d-ray sample of the image; rank 0 only" % n_rays},
+                       "a %d-ray sample of the image per step; %d timed + %d warm-up steps really run; rank 0 only"
+                       % (n_rays, steps, warmup)},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -239,10 +245,22 @@ def l2_probe(dev):
     return out
 
 
-def rooflines(stage_us, samples, n_params, peaks):
-    """achieved algorithmic GB/s of every bandwidth-bound stage, and the dominant one as the headline roofline"""
-    peak = peaks.get("hbm_gbs", 6650.0)
+# what bounds each stage: the encoder's 23-47 MB table and its gradient stay in the 126 MB L2 (ncu: the
+# scatter touches DRAM for 8 % of its algorithmic bytes), so the encode kernels are measured against the L2 rates probed in
+# this run; the field kernels stream activations from / to HBM and run the only dense contraction (tensor pipe); the
+# composites and Adam stream HBM; the march is issue / latency bound (samples/s reported).
+STAGE_BOUND = {"grid_encode_forward": "l2", "grid_encode_backward": "l2", "composite_forward": "l2", "composite_backward": "l2",
+               "field_forward": "hbm", "field_backward": "hbm", "adam": "hbm", "march_write": "hbm"}
+FLOPS_PER_SAMPLE = {"field_forward": 2.0 * 20480, "field_backward": 4.0 * 20480}     # useful MACs x 2; backward = dgrad + wgrad
+
+
+def rooflines(stage_us, samples, n_params, peaks, l2=None):
+    """achieved algorithmic GB/s of every stage against the roofline that bounds it; the dominant stage is the headline"""
+    hbm = peaks.get("hbm_gbs", 6650.0)
     src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1370.0))
+    l2_stream = (l2 or {}).get("stream_32MB_gbs")
+    l2_sector = (l2 or {}).get("gather_32MB_sector_gbs")
     per = {}
     for k, us in stage_us.items():
         if k in BYTES_PER_SAMPLE:
@@ -252,9 +270,25 @@ def rooflines(stage_us, samples, n_params, peaks):
         else:
             continue
         ach = bpu * units / (us * 1e-6) / 1e9
-        per[k] = {"us": round(us, 2), "bytes_per_unit": bpu, "units": units, "achieved_gbs": round(ach, 1),
-                  "frac_of_hbm_peak": round(ach / peak, 4)}
-    top = max(per, key=lambda k: per[k]["us"])
+        bound = STAGE_BOUND.get(k, "hbm")
+        if bound == "l2" and not l2_stream:
+            bound = "hbm"
+        peak = l2_stream if bound == "l2" else hbm
+        row = {"us": round(us, 2), "bytes_per_unit": bpu, "units": units, "bound": bound, "achieved_gbs": round(ach, 1),
+               "peak_gbs": peak, "frac": round(ach / peak, 4), "frac_of_hbm_peak": round(ach / hbm, 4)}
+        if bound == "l2":
+            row["frac_of_l2_random_sector_rate"] = round(ach / l2_sector, 4) if l2_sector else None
+        if k in FLOPS_PER_SAMPLE:
+            tfs = FLOPS_PER_SAMPLE[k] * units / (us * 1e-6) / 1e12
+            row["tensor"] = {"achieved_tflops": round(tfs, 1), "peak_tflops": tf, "frac": round(tfs / tf, 4),
+                             "flops_per_unit": FLOPS_PER_SAMPLE[k]}
+        per[k] = row
+    if "march_count" in stage_us:
+        us = stage_us["march_count"] + stage_us.get("march_write", 0.0)
+        per["march"] = {"us": round(us, 2), "bound": "issue/latency", "samples_per_s": round(samples / (us * 1e-6), 1),
+                        "units": samples}
+    timed = {k: v for k, v in per.items() if "achieved_gbs" in v}
+    top = max(timed, key=lambda k: timed[k]["us"])
     t = per[top]
     # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture, when one exists
     traffic = None
@@ -262,11 +296,23 @@ def rooflines(stage_us, samples, n_params, peaks):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top)
     except Exception:
         pass
-    head = {"kernel": top, "bound": "hbm", "achieved": t["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": t["achieved_gbs"] / peak, "traffic": traffic, "us_per_launch": t["us"],
-            "bytes_per_unit": t["bytes_per_unit"], "units_per_launch": t["units"], "peak_source": src,
-            "how": "CUDA events recorded between the stages of real train steps on the launching stream (L2 flushed "
-                   "between steps), mean over the profiled steps"}
+    head = {"kernel": top, "bound": t["bound"], "achieved": t["achieved_gbs"], "peak": t["peak_gbs"], "unit": "GB/s",
+            "frac": t["achieved_gbs"] / t["peak_gbs"], "traffic": traffic, "us_per_launch": t["us"],
+            "bytes_per_unit": t["bytes_per_unit"], "units_per_launch": t["units"],
+            "peak_source": ("L2 read stream over a 32 MB resident buffer measured in this run (l2_probe.stream_32MB_gbs; "
+                            "MEASURED_PEAKS.json has no L2 figure)" if t["bound"] == "l2" else src),
+            "frac_of_hbm_peak": t["frac_of_hbm_peak"],
+            "how": "achieved = bytes_per_unit x units_per_launch / us_per_launch; CUDA events recorded between the stages of "
+                   "real train steps on the launching stream (L2 flushed between steps), mean over the profiled steps"}
+    if t["bound"] == "l2":
+        head["frac_of_l2_random_sector_rate"] = t.get("frac_of_l2_random_sector_rate")
+    # the field network against the tensor pipe (the only dense contraction): forward + backward together
+    if "field_forward" in per and "field_backward" in per:
+        us = per["field_forward"]["us"] + per["field_backward"]["us"]
+        fl = (FLOPS_PER_SAMPLE["field_forward"] + FLOPS_PER_SAMPLE["field_backward"]) * samples
+        head["mlp_tensor"] = {"bound": "tensor", "achieved": round(fl / (us * 1e-6) / 1e12, 1), "peak": tf, "unit": "TFLOP/s",
+                              "frac": round(fl / (us * 1e-6) / 1e12 / tf, 4), "us": round(us, 2),
+                              "flops": fl, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a step)"}
     return head, per
 
 
@@ -499,7 +545,9 @@ def run_b200(args):
                                      "api": "FusedTrainStep.step(pose=, target=) with pinned_pose_batch(k % 2) + previous_stats() (asynchronous loop as e2e)"}
         if update_us is not None:
             nb = fs.params_flat.numel() * 4
-            wire = nb * (world - 1) / world          # bytes in (gradient slices read) = bytes out (parameters stored) per rank
+            # per rank and link direction: IN = the peers' gradient slices it reads (read responses) + the parameters the
+            # peers store into it; OUT = the same two streams the other way round: 2 x 4 B x n x (W - 1) / W each way
+            wire = 2 * nb * (world - 1) / world
             line["update"] = {"kind": args.update, "us": round(update_us, 1),
                               "what": "adam_hyper + " + ("k_peer_reduce_adam_bcast" if peer is not None else
                                                         "ncclAllReduce(grads_flat) + k_fused_adam") + " + weight re-pack, "
@@ -512,16 +560,20 @@ def run_b200(args):
             stage_us = fs.profile_stages(10, flush=flush.zero_)
             fs.use_graph, fs.pipeline_update = not args.no_graph, not args.no_pipeline
             line["kernel_us"] = {k: round(v, 2) for k, v in stage_us.items()}
-            line["roofline"], line["stage_rooflines"] = rooflines(stage_us, samples, fs.params_flat.numel(), peaks)
+            l2 = None
             try:
                 l2 = l2_probe(dev)
                 # the encoder against the L2: 128 corner gathers per sample (forward), 128 reductions (backward)
                 l2["grid_encode_forward_gsectors_per_s"] = round(samples * 128 / (stage_us["grid_encode_forward"] * 1e-6) / 1e9, 2)
                 l2["grid_encode_forward_frac_of_gather_32MB"] = round(l2["grid_encode_forward_gsectors_per_s"] / l2["gather_32MB_gsectors_per_s"], 3)
-                l2["grid_encode_backward_gatomics_per_s"] = round(samples * 128 / (stage_us["grid_encode_backward"] * 1e-6) / 1e9, 2)
+                # 128 ALGORITHMIC corner reductions per sample; the atomics actually issued after the warp aggregation are
+                # fewer (ncu lts__t_requests_srcunit_tex_op_red per launch: profiles/r02_encode_bwd_atomics.txt)
+                l2["grid_encode_backward_algorithmic_greductions_per_s"] = round(samples * 128 / (stage_us["grid_encode_backward"] * 1e-6) / 1e9, 2)
                 line["l2_probe"] = l2
             except Exception as e:
                 line["l2_probe"] = {"error": repr(e)}
+                l2 = None
+            line["roofline"], line["stage_rooflines"] = rooflines(stage_us, samples, fs.params_flat.numel(), peaks, l2)
             if not args.no_cpu:
                 n_cpu = 2048
                 line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(3, 1, n_cpu).items() if k != "ms_per_step"}

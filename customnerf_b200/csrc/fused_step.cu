@@ -22,6 +22,28 @@ struct StageTimer {
     bool fb_done, up_done;
 };
 inline void tick(cudaEvent_t *ev, int i, cudaStream_t st) { if (ev) cudaEventRecord(ev[i], st); }
+
+// grid encode + field network forward of the step: two launches, or ONE (NB200_PLAN_FUSED_FORWARD: the gather runs in
+// producer warps of the field kernel, csrc/field_fused.cu; x_en is still written once, for the backward pass)
+int fs_encode_field_forward(const nb200_train_plan *p, void *stream, cudaEvent_t *ev, int *k) {
+    cudaStream_t st = nb_stream(stream);
+    int rc;
+    if (p->flags & NB200_PLAN_FUSED_FORWARD) {
+        if (k) tick(ev, (*k)++, st);            // the encode stage is empty
+        if ((rc = nb200_field_fused_forward(p->xyzs, p->dirs, p->bound, p->table, p->offsets, p->L, p->S, p->base_res, p->gridtype,
+                                            0, 0, p->w_fwd, p->sigma, p->sigma_arg, p->rgba, p->x_en, p->act, p->M_cap, p->m_eff,
+                                            stream))) return rc;
+        if (k) tick(ev, (*k)++, st);
+        return 0;
+    }
+    if ((rc = nb200_fs_encode_forward(p->xyzs, p->bound, p->table, p->offsets, p->x_en, p->M_cap, p->L, p->S, p->base_res,
+                                      p->gridtype, 0, 0, p->m_eff, stream))) return rc;
+    if (k) tick(ev, (*k)++, st);
+    if ((rc = nb200_field_forward(p->x_en, p->xyzs, p->dirs, p->w_fwd, p->sigma, p->sigma_arg, p->rgba, p->act, p->M_cap,
+                                  p->m_eff, stream))) return rc;
+    if (k) tick(ev, (*k)++, st);
+    return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -85,12 +107,7 @@ rest:
     if (!(phases & NB200_PHASE_REST)) return 0;
     if ((e = cudaMemsetAsync(p->loss, 0, sizeof(float), st)) != cudaSuccess) return (int)e;
     tick(ev, k++, st);
-    if ((rc = nb200_fs_encode_forward(p->xyzs, p->bound, p->table, p->offsets, p->x_en, p->M_cap, p->L, p->S, p->base_res,
-                                      p->gridtype, 0, 0, p->m_eff, stream))) return rc;
-    tick(ev, k++, st);
-    if ((rc = nb200_field_forward(p->x_en, p->xyzs, p->dirs, p->w_fwd, p->sigma, p->sigma_arg, p->rgba, p->act, p->M_cap,
-                                  p->m_eff, stream))) return rc;
-    tick(ev, k++, st);
+    if ((rc = fs_encode_field_forward(p, stream, ev, &k))) return rc;
     if ((rc = nb200_fs_composite_forward(p->sigma, p->rgba, p->deltas, p->rays, p->M_cap, p->N, p->T_thresh,
                                          p->weights_sum, p->depth, p->image, p->target, p->inv_n_total, p->loss_scale,
                                          p->loss, p->g_image, p->target_mask, p->mask_weight, p->render_mask,
@@ -116,10 +133,7 @@ int nb200_train_lgie_forward(const nb200_train_plan *p, const nb200_lgie_plan *g
     if (!p || !g || !g->weights_sum || !g->depth || !g->image || !g->render_mask) return NB200_E_BAD_ARG;
     int rc;
     if ((rc = nb200_train_phase(p, NB200_PHASE_MARCH, stream))) return rc;
-    if ((rc = nb200_fs_encode_forward(p->xyzs, p->bound, p->table, p->offsets, p->x_en, p->M_cap, p->L, p->S, p->base_res,
-                                      p->gridtype, 0, 0, p->m_eff, stream))) return rc;
-    if ((rc = nb200_field_forward(p->x_en, p->xyzs, p->dirs, p->w_fwd, p->sigma, p->sigma_arg, p->rgba, p->act, p->M_cap,
-                                  p->m_eff, stream))) return rc;
+    if ((rc = fs_encode_field_forward(p, stream, nullptr, nullptr))) return rc;
     const size_t N = p->N;
     for (int v = 0; v < 3; v++)
         if ((rc = nb200_fs_composite_lgie_forward(v, p->sigma, p->rgba, p->deltas, p->rays, p->M_cap, p->N, p->T_thresh,

@@ -19,14 +19,12 @@
 // Index arithmetic is uint32 with wrap-around exactly as gridencoder.cu:50-84; scale is computed on the
 // device with the reference's expression exp2f(level * S) * H - 1.0f so fine-level positions are identical.
 #include "common.cuh"
+#include "grid_d3c2.cuh"
 #include <stdlib.h>
 
 namespace {
 
 
-__device__ __forceinline__ float ge_level_scale(uint32_t level, float S, uint32_t H) {
-    return exp2f(level * S) * H - 1.0f;      // gridencoder.cu:138 (same expression => same FFMA contraction)
-}
 
 template <uint32_t D>
 __device__ __forceinline__ uint32_t ge_fast_hash(const uint32_t pos_grid[D]) {
@@ -51,8 +49,6 @@ __device__ __forceinline__ uint32_t ge_grid_row(uint32_t gridtype, bool align_co
     return index % hashmap_size;
 }
 
-__device__ __forceinline__ float ge_smoothstep(float v) { return v * v * (3.0f - 2.0f * v); }
-__device__ __forceinline__ float ge_smoothstep_d(float v) { return 6 * v * (1.0f - v); }
 
 // ------------------------------------------------------------------------------------------------
 // generic forward: gridencoder.cu:87-244
@@ -276,72 +272,6 @@ k_grad_tv(const float *__restrict__ inputs, const float *__restrict__ grid, floa
     for (uint32_t ch = 0; ch < C; ch++) atomicAdd(&grad[index + ch], w * results[ch] * rsqrtf(idelta[ch] + 1e-9f));
 }
 
-// ------------------------------------------------------------------------------------------------
-// d3c2 fast path
-// ------------------------------------------------------------------------------------------------
-constexpr uint32_t kMaxFastLevels = 32;
-constexpr uint32_t P1 = 2654435761u, P2 = 805459861u;
-
-// optional input transform and device-side row count of the fused train step (nb200_fs_*): x01 = (x + add) * mul is
-// what GridEncoder.forward's `(inputs + bound) / (2 * bound)` evaluates to in torch (a tensor / python-scalar division
-// is a multiplication by the fp32 reciprocal), fused here so the normalised copy of the sample positions never exists.
-struct InXform {
-    float add, mul;                 // mul == 0: identity (inputs are already in [0, 1])
-    const int32_t *count_dev;       // when non-null only rows < min(B, *count_dev) are processed
-    __device__ __forceinline__ float operator()(float x) const { return mul != 0.0f ? __fmul_rn(__fadd_rn(x, add), mul) : x; }
-};
-
-struct LevelInfo {
-    uint32_t offset;     // first row of the level
-    uint32_t size;       // rows in the level (hashmap_size)
-    uint32_t m1, m2;     // dense strides of y and z (0 when the reference's stride loop has stopped)
-    uint32_t mask;       // size-1 when size is a power of two, else 0
-    uint32_t use_hash;
-    float scale;
-    uint32_t pad;
-};
-
-__device__ __forceinline__ void ge_fill_level_info(LevelInfo *info, const int32_t *__restrict__ offsets, uint32_t nlev,
-                                                   float S, uint32_t H, uint32_t gridtype, bool align_corners) {
-    for (uint32_t l = threadIdx.x; l < nlev; l += blockDim.x) {
-        LevelInfo li;
-        li.offset = (uint32_t)offsets[l];
-        li.size = (uint32_t)(offsets[l + 1] - offsets[l]);
-        li.scale = ge_level_scale(l, S, H);
-        const uint32_t resolution = (uint32_t)ceilf(li.scale) + 1;
-        const uint32_t r1 = align_corners ? resolution : resolution + 1;
-        // replay of the stride loop of get_grid_index (gridencoder.cu:71-75) for D = 3
-        uint32_t stride = 1;
-        stride *= r1;                                   // d = 0 always executes (1 <= size)
-        li.m1 = 0; li.m2 = 0;
-        if (stride <= li.size) {
-            li.m1 = stride; stride *= r1;
-            if (stride <= li.size) { li.m2 = stride; stride *= r1; }
-        }
-        li.use_hash = (gridtype == 0 && stride > li.size) ? 1u : 0u;
-        li.mask = ((li.size & (li.size - 1)) == 0) ? li.size - 1 : 0u;
-        li.pad = 0;
-        info[l] = li;
-    }
-}
-
-__device__ __forceinline__ uint32_t ge_row_d3(const LevelInfo &li, uint32_t x, uint32_t y, uint32_t z) {
-    uint32_t raw = li.use_hash ? (x ^ (y * P1) ^ (z * P2)) : (x + y * li.m1 + z * li.m2);
-    if (li.mask) return raw & li.mask;
-    return raw < li.size ? raw : raw % li.size;
-}
-
-template <typename T> struct Vec2;
-template <> struct Vec2<float> { using type = float2; };
-template <> struct Vec2<__half> { using type = __half2; };
-__device__ __forceinline__ float2 ge_ld2(const float *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
-__device__ __forceinline__ float2 ge_ld2(const __half *p) { return __half22float2(__ldg(reinterpret_cast<const __half2 *>(p))); }
-
-// fp32 master table read as if it had been cast to fp16 first (the autocast path of grid.py:45-46 without the copy)
-__device__ __forceinline__ float2 ge_ld2_round_half(const float *p) {
-    return __half22float2(__float22half2_rn(__ldg(reinterpret_cast<const float2 *>(p))));
-}
-
 // one thread per point; outputs [B, L*2].  TE = table storage type, T = value / output type.
 template <typename TE, typename T>
 __global__ void __launch_bounds__(256)
@@ -366,30 +296,8 @@ k_grid_fwd_d3c2(const float *__restrict__ inputs, const TE *__restrict__ grid, c
         for (uint32_t j = 0; j < 4; j++) {
             const uint32_t l = l0 + j;
             float r0 = 0.0f, r1 = 0.0f;
-            if (l < max_level && !oob) {
-                const LevelInfo li = info[l];
-                float p0 = x0 * li.scale + half_off, p1 = x1 * li.scale + half_off, p2 = x2 * li.scale + half_off;
-                const uint32_t g0 = (uint32_t)floorf(p0), g1 = (uint32_t)floorf(p1), g2 = (uint32_t)floorf(p2);
-                p0 -= (float)g0; p1 -= (float)g1; p2 -= (float)g2;
-                if (interp == 1) { p0 = ge_smoothstep(p0); p1 = ge_smoothstep(p1); p2 = ge_smoothstep(p2); }
-                const TE *lg = grid + (size_t)li.offset * 2;
-                float2 v[8];
-#pragma unroll
-                for (uint32_t idx = 0; idx < 8; idx++) {
-                    const uint32_t row = ge_row_d3(li, g0 + (idx & 1u), g1 + ((idx >> 1) & 1u), g2 + ((idx >> 2) & 1u));
-                    if constexpr (sizeof(TE) == 4 && sizeof(T) == 2) v[idx] = ge_ld2_round_half(lg + (size_t)row * 2);
-                    else v[idx] = ge_ld2(lg + (size_t)row * 2);
-                }
-#pragma unroll
-                for (uint32_t idx = 0; idx < 8; idx++) {
-                    float w = 1;
-                    w *= (idx & 1u) ? p0 : 1 - p0;
-                    w *= (idx & 2u) ? p1 : 1 - p1;
-                    w *= (idx & 4u) ? p2 : 1 - p2;
-                    r0 += w * v[idx].x;
-                    r1 += w * v[idx].y;
-                }
-            }
+            if (l < max_level && !oob)
+                ge_level_gather<TE, (sizeof(TE) == 4 && sizeof(T) == 2)>(info[l], grid, x0, x1, x2, half_off, interp, r0, r1);
             res[j * 2] = r0; res[j * 2 + 1] = r1;
         }
         // rows are (L*2) elements; L*2*sizeof(T) is a multiple of 16 bytes only when L % 4 == 0 (f16) / L % 2 == 0 (f32)

@@ -41,7 +41,7 @@ class FusedInference:
         self.rays_alive, self.tmp = torch.zeros(N, **i32), torch.zeros(N, **i32)
         M = N + 128
         self.xyzs, self.dirs, self.deltas = torch.zeros(M, 3, **f32), torch.zeros(M, 3, **f32), torch.zeros(M, 2, **f32)
-        self.x_en, self.rgba, self.sigma = torch.zeros(M, 32, **f16), torch.zeros(M, 4, **f16), torch.zeros(M, **f32)
+        self.rgba, self.sigma = torch.zeros(M, 4, **f16), torch.zeros(M, **f32)
         self.weights_sum, self.depth, self.image = torch.zeros(N, **f32), torch.zeros(N, **f32), torch.zeros(N, 3, **f32)
         self.state = torch.zeros(8, **i32)
         self.state_host = torch.zeros(8, dtype=torch.int32).pin_memory()
@@ -54,7 +54,7 @@ class FusedInference:
         self.rounds = 0
 
     def _round(self):
-        """one round on the current stream: plan -> march -> encode -> field -> composite -> compact"""
+        """one round on the current stream: plan -> march -> encode + field (one kernel) -> composite -> compact"""
         m, enc, lib, st = self.model, self.model.pos_en, self.lib, L.stream()
         p = L.ptr
         cnt = C.c_void_p(self.state.data_ptr() + 12)
@@ -64,17 +64,17 @@ class FusedInference:
                                         L.u32(m.cascade), L.u32(m.grid_size), p(m.density_bitfield), p(self.fars),
                                         p(self.xyzs), p(self.dirs), p(self.deltas),
                                         p(self.noises if self.use_noise else None), st), "march_rays_dev")
-        _check(lib.nb200_fs_encode_forward(p(self.xyzs), L.f32(m.bound), p(enc.embeddings.detach()), p(enc.offsets), p(self.x_en),
-                                           L.u32(self.M_cap), L.u32(enc.num_levels), L.f32(float(np.log2(enc.per_level_scale))),
-                                           L.u32(int(enc.base_resolution)), L.u32(enc.gridtype_id), L.i32(0), L.u32(0), cnt, st),
-               "fs_encode_forward")
-        _check(lib.nb200_field_forward(p(self.x_en), p(self.xyzs), p(self.dirs), p(self.w_fwd), p(self.sigma), p(None),
-                                       p(self.rgba), p(None), L.u32(self.M_cap), cnt, st), "field_forward")
+        # grid gather + field network in one launch: the features never exist in HBM (csrc/field_fused.cu)
+        _check(lib.nb200_field_fused_forward(p(self.xyzs), p(self.dirs), L.f32(m.bound), p(enc.embeddings.detach()), p(enc.offsets),
+                                             L.u32(enc.num_levels), L.f32(float(np.log2(enc.per_level_scale))),
+                                             L.u32(int(enc.base_resolution)), L.u32(enc.gridtype_id), L.i32(int(enc.align_corners)),
+                                             L.u32(enc.interp_id), p(self.w_fwd), p(self.sigma), p(None), p(self.rgba), p(None), p(None),
+                                             L.u32(self.M_cap), cnt, st), "field_fused_forward")
         _check(lib.nb200_composite_rays_dev(p(self.state), L.u32(self.N), L.f32(self.T_thresh), p(self.rays_alive),
                                             p(self.rays_t), p(self.sigma), p(self.rgba), p(self.deltas), p(self.weights_sum),
                                             p(self.depth), p(self.image), st), "composite_rays_dev")
         _check(lib.nb200_compact_alive(p(self.state), L.u32(self.N), p(self.rays_alive), p(self.tmp), st), "compact_alive")
-        L.LAUNCHES += 8
+        L.LAUNCHES += 7
 
     def _capture(self):
         keep = [t.clone() for t in (self.state, self.rays_alive, self.rays_t, self.weights_sum, self.depth, self.image)]
@@ -120,7 +120,7 @@ class FusedInference:
                 for _ in range(self.rounds_per_check):
                     if self.use_graph:
                         self.graph.replay()
-                        L.LAUNCHES += 8
+                        L.LAUNCHES += 7
                     else:
                         self._round()
                 self.rounds += self.rounds_per_check

@@ -48,7 +48,8 @@ def _check(rc, what):
 class TrainPlan(C.Structure):
     """mirror of nb200_train_plan (include/nerf_b200.h)"""
     _u32 = ["N", "M_cap", "C", "H", "L", "base_res", "gridtype", "max_steps"]
-    _f32 = ["bound", "dt_gamma", "S", "T_thresh", "min_near", "loss_scale", "inv_n_total", "pad0"]
+    _f32 = ["bound", "dt_gamma", "S", "T_thresh", "min_near", "loss_scale", "inv_n_total"]
+    _flags = ["flags"]
     _u64 = ["n_params", "n_table_params"]
     _ptr0 = ["rays_o", "rays_d", "target", "aabb", "noises", "target_mask", "render_mask", "g_render_mask"]
     _f32b = ["mask_weight", "pad1"]
@@ -60,7 +61,8 @@ class TrainPlan(C.Structure):
             "rays", "counter", "m_eff", "scratch",
             "xyzs", "dirs", "deltas", "sigma", "sigma_arg", "d_sigma", "d_rgba",
             "x_en", "rgba", "act", "d_x_en", "wg_scratch", "timer"]
-    _fields_ = ([(n, C.c_uint32) for n in _u32] + [(n, C.c_float) for n in _f32] + [(n, C.c_uint64) for n in _u64] +
+    _fields_ = ([(n, C.c_uint32) for n in _u32] + [(n, C.c_float) for n in _f32] + [(n, C.c_uint32) for n in _flags] +
+                [(n, C.c_uint64) for n in _u64] +
                 [(n, C.c_void_p) for n in _ptr0] + [(n, C.c_float) for n in _f32b] + [(n, C.c_void_p) for n in _ptr])
 
 
@@ -99,7 +101,7 @@ class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
                  lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0,
-                 peer=None, raygen=None):
+                 peer=None, raygen=None, fused_forward=True):
         if not model.cuda_ray:
             raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
@@ -137,6 +139,10 @@ class FusedTrainStep:
         # mask_weight > 0: the reference's reconstruction loss with train_conf (utils_init_nerf.py:224-234):
         # MSE(image, target) + mask_weight * MSE(render_mask, target_mask); render_mask composites the 4th field output
         self.mask_weight = float(mask_weight)
+        # fused_forward: grid gather + field network forward as ONE kernel (csrc/field_fused.cu: the features are gathered by
+        # producer warps straight into the tensor-core operand tile); False: two launches (encode, then field)
+        self.fused_forward = bool(fused_forward) and model.pos_en.num_levels == 16
+        self.kernels_per_step = KERNELS_PER_STEP - (1 if self.fused_forward else 0)
         self.pipeline_update = bool(pipeline_update)
         self._pending_update = False
         self._side = None
@@ -236,6 +242,7 @@ class FusedTrainStep:
         p.S = float(np.log2(enc.per_level_scale))
         p.T_thresh, p.min_near = self.T_thresh, 0.2          # run_cuda leaves min_near at its default (Appendix B5)
         p.loss_scale, p.inv_n_total = LOSS_SCALE, 1.0 / (3.0 * self.n_total)
+        p.flags = 1 if self.fused_forward else 0
         p.n_params, p.n_table_params = self.params_flat.numel(), self.layout[0][2]
 
         def a(t):
@@ -457,7 +464,7 @@ class FusedTrainStep:
                     if flush is not None:
                         flush()
                     self._launch()
-                    L.LAUNCHES += KERNELS_PER_STEP
+                    L.LAUNCHES += self.kernels_per_step
                     _check(self.lib.nb200_stage_timer_read(timer, out), "stage_timer_read")
                     acc += np.array(list(out))
         finally:
@@ -533,7 +540,7 @@ class FusedTrainStep:
             _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
             self.stats_host.copy_(self.stats, non_blocking=True)
             self._pending_update = True
-            L.LAUNCHES += KERNELS_PER_STEP - 4
+            L.LAUNCHES += self.kernels_per_step - 4
             return
         if self.use_graph and self.graphs.get(staged) is None:
             try:

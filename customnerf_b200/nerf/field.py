@@ -11,7 +11,7 @@ from torch.amp import custom_bwd, custom_fwd
 
 from ..gridencoder import GridEncoder
 from .mlp import Network
-from .fused_field import fused_field, _PackedWeights
+from .fused_field import fused_field, fused_encode_field, fused_density, fused_encode_eligible, _PackedWeights
 from .rendering import NeRFRenderer
 
 
@@ -78,6 +78,9 @@ class NeRFNetwork(NeRFRenderer):
         # the per-layer library path (mlp.Network.forward) stays available through use_fused_field = False
         self.use_fused_field = self.pos_en_dim == 32
         self._packed = _PackedWeights()
+        # under autocast the grid gather runs inside the field kernel (no [M,32] feature tensor in HBM); False keeps the
+        # encoder and the field network as two launches (tests compare the two)
+        self.fuse_encoder = True
         # eval on the occupancy path: device-driven rounds in a CUDA graph (fused_infer.py) instead of the reference's
         # host-driven n_step loop; set False to run the loop of NeRFRenderer.run_cuda
         self.fast_inference = True
@@ -91,6 +94,11 @@ class NeRFNetwork(NeRFRenderer):
         return 5 * torch.exp(-(x ** 2).sum(-1) / (2 * 0.2 ** 2))
 
     def _fused(self, x, d):
+        if self.fuse_encoder and x.dim() == 2 and fused_encode_eligible(self.pos_en, x):
+            # grid gather + MLPs in one kernel: the [M,32] features never round-trip HBM (csrc/field_fused.cu)
+            sigma, rgba = fused_encode_field(x.reshape(-1, 3), d.reshape(-1, 3), self.pos_en, self.opt.bound, self.network.params,
+                                             self.density_network.params, self.rgb_network.params, self._packed)
+            return sigma, rgba[:, :self.rgb_network.n_output_dims]
         x_en = self.pos_en(x, bound=self.opt.bound)
         sigma, rgba = fused_field(x_en, x, d, self.network.params, self.density_network.params,
                                   self.rgb_network.params, self._packed)
@@ -109,6 +117,10 @@ class NeRFNetwork(NeRFRenderer):
         return sigma, radiances, None
 
     def density(self, x):
+        if (self.use_fused_field and self.fuse_encoder and not torch.is_grad_enabled() and x.dim() == 2
+                and fused_encode_eligible(self.pos_en, x)):
+            return {'sigma': fused_density(x, self.pos_en, self.opt.bound, self.network.params, self.density_network.params,
+                                           self.rgb_network.params, self._packed)}
         if self.use_fused_field:
             sigma, _ = self._fused(x, torch.zeros_like(x))
             return {'sigma': sigma}
@@ -140,6 +152,35 @@ class NeRFNetwork(NeRFRenderer):
         #  utils_init_nerf.py:358-365, which must not reach the image)
         return {'image': image.view(*prefix, 3), 'depth': depth.view(*prefix), 'weights_sum': weights_sum.reshape(*prefix),
                 'mask': (nears < fars).reshape(*prefix)}
+
+    def _occ_density_into(self, tmp_grid, decay, S):
+        """Occupancy update, density query (renderer.py:1667-1698) as ONE kernel: cell -> jittered position -> hash-grid gather ->
+        trunk + density head -> tmp_grid[cas, morton] (csrc/field_fused.cu: nb200_occ_density; no positions, features or
+        activations in HBM).  Same jitter draws and the same arithmetic as the op-by-op path of NeRFRenderer (bit-identical
+        grid under autocast, tests/test_gpu_render.py); taken when the field is the stock fused one and autocast is on (the
+        fused kernel rounds table entries to fp16 as the autocast encoder does)."""
+        stock = ('density' not in self.__dict__ and self.use_fused_field and torch.is_autocast_enabled()
+                 and S >= self.grid_size and self.pos_en.input_dim == 3 and self.pos_en.level_dim == 2
+                 and self.pos_en.num_levels == 16 and self.pos_en.embeddings.dtype == torch.float32)
+        if not stock:
+            return super()._occ_density_into(tmp_grid, decay, S)
+        import numpy as np
+        from .. import _lib as L
+        dev = tmp_grid.device
+        enc = self.pos_en
+        _, xyzs = self._occ_cell_table(dev)
+        noise = self.__dict__.get('_occ_noise')
+        if noise is None or noise.device != dev or noise.shape[0] != self.cascade:
+            noise = self.__dict__['_occ_noise'] = torch.empty(self.cascade, xyzs.shape[0], 3, dtype=torch.float32, device=dev)
+        for cas in range(self.cascade):
+            noise[cas].copy_(torch.rand_like(xyzs))         # the reference's draws, one per cascade (:1690)
+        fwd_img, _ = self._packed.get(self.network.params, self.density_network.params, self.rgb_network.params)
+        L.check(L.lib().nb200_occ_density(L.ptr(xyzs), L.ptr(noise), L.u32(self.grid_size), L.u32(self.cascade),
+                                          L.f32(float(self.bound)), L.ptr(enc.embeddings.detach()), L.ptr(enc.offsets),
+                                          L.u32(enc.num_levels), L.f32(float(np.log2(enc.per_level_scale))),
+                                          L.u32(int(enc.base_resolution)), L.u32(enc.gridtype_id),
+                                          L.i32(int(enc.align_corners)), L.u32(enc.interp_id), L.ptr(fwd_img),
+                                          L.ptr(tmp_grid), L.stream()), "occ_density")
 
     def get_params(self, lr):
         return [

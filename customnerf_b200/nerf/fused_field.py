@@ -89,3 +89,87 @@ def fused_field(x_en, xyz, dirs, trunk, density, rgb, packed):
         raise RuntimeError("customnerf_b200 fused field network runs on CUDA only (no CPU fallback)")
     save = torch.is_grad_enabled() and any(t.requires_grad for t in (x_en, trunk, density, rgb))
     return _FusedField.apply(x_en, xyz, dirs, trunk, density, rgb, packed, save)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# grid encoding + field network as ONE kernel / one autograd node (csrc/field_fused.cu): the [M,32] features are gathered by
+# producer warps straight into the tensor-core operand tile; in training they are written once (for the backward pass only)
+def fused_encode_eligible(enc, x):
+    """the fused kernel covers the product's shape under autocast: D = 3, C = 2, 16 levels, fp32 master table (entries are
+    rounded to fp16 on load, as the autocast encoder does, grid.py:45-46), positions without gradient"""
+    return (x.is_cuda and torch.is_autocast_enabled() and enc.input_dim == 3 and enc.level_dim == 2 and enc.num_levels == 16
+            and enc.embeddings.dtype == torch.float32 and not x.requires_grad)
+
+
+def _enc_args(enc):
+    import numpy as np
+    return (L.ptr(enc.embeddings.detach()), L.ptr(enc.offsets), L.u32(enc.num_levels), L.f32(float(np.log2(enc.per_level_scale))),
+            L.u32(int(enc.base_resolution)), L.u32(enc.gridtype_id), L.i32(int(enc.align_corners)), L.u32(enc.interp_id))
+
+
+class _FusedEncodeField(Function):
+    @staticmethod
+    def forward(ctx, xyz, dirs, embeddings, trunk, density, rgb, enc, bound, packed, save):
+        M = xyz.shape[0]
+        dev = xyz.device
+        xyz = xyz.float().contiguous()
+        dirs = dirs.float().contiguous()
+        fwd_img, bwd_img = packed.get(trunk, density, rgb)
+        sigma = torch.empty(M, dtype=torch.float32, device=dev)
+        rgba = torch.empty(M, 4, dtype=torch.half, device=dev)
+        sigma_arg = torch.empty(M, dtype=torch.float32, device=dev) if save else None
+        x_en = torch.empty(M, 32, dtype=torch.half, device=dev) if save else None
+        act = torch.empty(5, M, 64, dtype=torch.half, device=dev) if save else None
+        L.check(L.lib().nb200_field_fused_forward(L.ptr(xyz), L.ptr(dirs), L.f32(float(bound)), *_enc_args(enc), L.ptr(fwd_img),
+                                                  L.ptr(sigma), L.ptr(sigma_arg), L.ptr(rgba), L.ptr(x_en), L.ptr(act), L.u32(M),
+                                                  L.ptr(None), L.stream()), "field_fused_forward")
+        if save:
+            ctx.save_for_backward(xyz, dirs, x_en, sigma_arg, rgba, act, bwd_img, enc.offsets)
+            ctx.enc, ctx.bound = enc, float(bound)
+            ctx.shapes = (tuple(embeddings.shape), trunk.numel(), density.numel(), rgb.numel())
+        return sigma, rgba
+
+    @staticmethod
+    def backward(ctx, d_sigma, d_rgba):
+        import numpy as np
+        xyz, dirs, x_en, sigma_arg, rgba, act, bwd_img, offsets = ctx.saved_tensors
+        enc = ctx.enc
+        M = xyz.shape[0]
+        dev = xyz.device
+        d_sigma = (torch.zeros(M, device=dev) if d_sigma is None else d_sigma.float()).contiguous()
+        d_rgba = (torch.zeros(M, 4, device=dev) if d_rgba is None else d_rgba.float()).contiguous()
+        emb_shape, nt, nd, nr = ctx.shapes
+        g_trunk = torch.zeros(nt, dtype=torch.float32, device=dev)
+        g_density = torch.zeros(nd, dtype=torch.float32, device=dev)
+        g_rgb = torch.zeros(nr, dtype=torch.float32, device=dev)
+        g_table = torch.zeros(emb_shape, dtype=torch.float32, device=dev)
+        d_x_en = torch.empty(M, 32, dtype=torch.half, device=dev)
+        L.check(L.lib().nb200_field_backward(L.ptr(d_sigma), L.ptr(d_rgba), L.ptr(sigma_arg), L.ptr(rgba), L.ptr(x_en),
+                                             L.ptr(dirs), L.ptr(act), L.ptr(bwd_img), L.ptr(d_x_en), L.ptr(g_trunk),
+                                             L.ptr(g_density), L.ptr(g_rgb), L.u32(M), L.ptr(None), L.ptr(_wg_scratch(dev)),
+                                             L.stream()),
+                "field_backward")
+        L.check(L.lib().nb200_fs_encode_backward(L.ptr(d_x_en), L.ptr(xyz), L.f32(ctx.bound), L.ptr(offsets), L.ptr(g_table),
+                                                 L.u32(M), L.u32(enc.num_levels), L.f32(float(np.log2(enc.per_level_scale))),
+                                                 L.u32(int(enc.base_resolution)), L.u32(enc.gridtype_id),
+                                                 L.i32(int(enc.align_corners)), L.u32(enc.interp_id), L.ptr(None), L.stream()),
+                "fs_encode_backward")
+        return None, None, g_table, g_trunk, g_density, g_rgb, None, None, None, None
+
+
+def fused_encode_field(xyz, dirs, enc, bound, trunk, density, rgb, packed):
+    """positions [M,3] in [-bound, bound], view directions [M,3] -> (sigma f32 [M], rgba f16 [M,4]) in one launch"""
+    save = torch.is_grad_enabled() and any(t.requires_grad for t in (enc.embeddings, trunk, density, rgb))
+    return _FusedEncodeField.apply(xyz, dirs, enc.embeddings, trunk, density, rgb, enc, bound, packed, save)
+
+
+def fused_density(xyz, enc, bound, trunk, density, rgb, packed):
+    """density only (trunk + density head), no autograd: sigma f32 [M] in one launch"""
+    M = xyz.shape[0]
+    xyz = xyz.float().contiguous()
+    fwd_img, _ = packed.get(trunk, density, rgb)
+    sigma = torch.empty(M, dtype=torch.float32, device=xyz.device)
+    L.check(L.lib().nb200_field_fused_forward(L.ptr(xyz), L.ptr(None), L.f32(float(bound)), *_enc_args(enc), L.ptr(fwd_img),
+                                              L.ptr(sigma), L.ptr(None), L.ptr(None), L.ptr(None), L.ptr(None), L.u32(M),
+                                              L.ptr(None), L.stream()), "field_fused_forward(density)")
+    return sigma

@@ -287,46 +287,116 @@ class NeRFRenderer(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------------- occupancy grid
-    @torch.no_grad()
-    def update_extra_state(self, decay=0.95, S=128):
-        if not self.cuda_ray:
-            return
-        dev = self.density_bitfield.device
+    # mean_density / mean_count are produced on the device by update_extra_state (no blocking read inside the update); the
+    # attributes the reference keeps as Python numbers are read back on first use
+    def _occ_sync(self):
+        ev = self.__dict__.get('_occ_event')
+        if ev is not None:
+            ev.synchronize()
+            h = self._occ_state_host
+            self.__dict__['_mean_density'] = float(h[0])
+            if self.__dict__.get('_occ_counted'):
+                self.__dict__['_mean_count'] = int(h.view(torch.int32)[2])
+            self.__dict__['_occ_event'] = None
+
+    @property
+    def mean_density(self):
+        self._occ_sync()
+        return self.__dict__.get('_mean_density', 0)
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self._occ_sync()
+        self.__dict__['_mean_density'] = v
+
+    @property
+    def mean_count(self):
+        self._occ_sync()
+        return self.__dict__.get('_mean_count', 0)
+
+    @mean_count.setter
+    def mean_count(self, v):
+        self._occ_sync()
+        self.__dict__['_mean_count'] = v
+
+    def _occ_cell_table(self, dev):
+        """(morton index [G^3] int64, cell centre [G^3, 3] in [-1, 1]) of every cell in the reference's x-major order.  The
+        centres are evaluated on the HOST with the reference's expression (renderer.py:1678: 2 * coords.float() / (G - 1) - 1)
+        -- on a CUDA tensor the division by a Python scalar becomes a multiplication by the rounded reciprocal, one ulp off
+        the reference's values for some cells -- and cached: they never change."""
         G = self.grid_size
-        tmp_grid = -torch.ones_like(self.density_grid)
-        axis = torch.arange(G, dtype=torch.int32, device=dev)
-        cache = getattr(self, '_occ_cells', None)            # (morton index, cell-centre coordinate) of every cell: constant
-        for xs in axis.split(S):
-            for ys in axis.split(S):
-                for zs in axis.split(S):
-                    if S >= G and cache is not None and cache[0].device == dev and cache[0].numel() == G ** 3:
-                        indices, xyzs = cache
-                    else:
+        cache = self.__dict__.get('_occ_cells')
+        if cache is None or cache[0].device != dev or cache[0].numel() != G ** 3:
+            axis = torch.arange(G, dtype=torch.int32)
+            xx, yy, zz = torch.meshgrid(axis, axis, axis, indexing='ij')
+            coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
+            xyzs = (2 * coords.float() / (G - 1) - 1).to(dev)
+            indices = raymarching.morton3D(coords.to(dev)).long()
+            cache = self.__dict__['_occ_cells'] = (indices, xyzs)
+        return cache
+
+    def _occ_buffers(self, dev):
+        from .. import _lib as L
+        if self.__dict__.get('_occ_state') is None or self._occ_state.device != dev:
+            L.lib().nb200_occ_scratch_bytes.restype = L.u32
+            self.__dict__['_occ_state'] = torch.zeros(8, dtype=torch.float32, device=dev)
+            self.__dict__['_occ_state_host'] = torch.zeros(8, dtype=torch.float32).pin_memory()
+            self.__dict__['_occ_scratch'] = torch.empty(int(L.lib().nb200_occ_scratch_bytes()) // 8 + 1, dtype=torch.float64, device=dev)
+            self.__dict__['_occ_tmp'] = torch.empty_like(self.density_grid)
+        return self._occ_state, self._occ_scratch, self._occ_tmp
+
+    def _occ_density_into(self, tmp_grid, decay, S):
+        """density of one jittered point per cell and cascade -> tmp_grid[cas, morton] (renderer.py:1667-1698).  This is the
+        reference's torch-op sequence around ``self.density`` (any callable); NeRFNetwork overrides it with the fused kernel."""
+        dev = tmp_grid.device
+        G = self.grid_size
+        tmp_grid.fill_(-1)
+        if S >= G:
+            chunks = [self._occ_cell_table(dev)]
+        else:                                   # smaller chunks (never used by the reference's callers): built on the fly
+            axis = torch.arange(G, dtype=torch.int32)
+            chunks = []
+            for xs in axis.split(S):
+                for ys in axis.split(S):
+                    for zs in axis.split(S):
                         xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
                         coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
-                        indices = raymarching.morton3D(coords).long()
-                        xyzs = 2 * coords.float() / (G - 1) - 1
-                        if S >= G:
-                            self._occ_cells = (indices, xyzs)
-                    for cas in range(self.cascade):
-                        bound = min(2 ** cas, self.bound)
-                        half_grid_size = bound / G
-                        cas_xyzs = xyzs * (bound - half_grid_size)
-                        cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half_grid_size
-                        sigmas = self.density(cas_xyzs)['sigma'].reshape(-1).detach()
-                        tmp_grid[cas, indices] = sigmas.float()
-        # EMA-max update where the grid is valid (:1701-1703), written with where() instead of boolean-mask indexing
-        # (no nonzero() synchronisation); the buffer is updated in place, captured graphs keep pointing at it
-        valid = self.density_grid >= 0
-        self.density_grid.copy_(torch.where(valid, torch.maximum(self.density_grid * decay, tmp_grid), self.density_grid))
-        n_valid = valid.sum()
-        self.mean_density = (torch.where(valid, self.density_grid, torch.zeros_like(self.density_grid)).sum() / n_valid).item()
+                        chunks.append((raymarching.morton3D(coords.to(dev)).long(), (2 * coords.float() / (G - 1) - 1).to(dev)))
+        for indices, xyzs in chunks:
+            for cas in range(self.cascade):
+                bound = min(2 ** cas, self.bound)
+                half_grid_size = bound / G
+                cas_xyzs = xyzs * (bound - half_grid_size)
+                cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half_grid_size
+                sigmas = self.density(cas_xyzs)['sigma'].reshape(-1).detach()
+                tmp_grid[cas, indices] = sigmas.float()
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128):
+        """renderer.py:1658-1715.  The density query fills tmp_grid; the EMA-max update, the mean of the valid cells, the
+        threshold min(mean, density_thresh), packbits and mean_count run on the device in three launches
+        (csrc/occupancy.cu: nb200_occ_finalize) -- the update never blocks on the host; mean_density / mean_count are read
+        back when something asks for them."""
+        if not self.cuda_ray:
+            return
+        from .. import _lib as L
+        dev = self.density_bitfield.device
+        self._occ_sync()                        # a previous update's numbers, before its state buffer is reused
+        state, scratch, tmp_grid = self._occ_buffers(dev)
+        with torch.cuda.device(dev):
+            self._occ_density_into(tmp_grid, decay, S)
+            total_step = min(16, self.local_step)
+            L.check(L.lib().nb200_occ_finalize(L.ptr(self.density_grid), L.ptr(tmp_grid), L.u32(self.density_grid.numel()),
+                                               L.f32(decay), L.f32(float(self.density_thresh)), L.ptr(self.step_counter),
+                                               L.u32(total_step), L.ptr(self.density_bitfield), L.ptr(state), L.ptr(scratch),
+                                               L.stream()), "occ_finalize")
+            L.LAUNCHES += 2
+            self._occ_state_host.copy_(state, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self.__dict__['_occ_counted'] = total_step > 0
+        self.__dict__['_occ_event'] = ev
         self.iter_density += 1
-        density_thresh = min(self.mean_density, self.density_thresh)
-        self.density_bitfield = raymarching.packbits(self.density_grid, density_thresh, self.density_bitfield)
-        total_step = min(16, self.local_step)
-        if total_step > 0:
-            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
         self.local_step = 0
 
     def render(self, rays_o, rays_d, staged=False, max_ray_batch=2048, **kwargs):

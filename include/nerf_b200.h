@@ -196,6 +196,41 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
 /* wg_scratch: nb200_field_wgrad_scratch_bytes() bytes (16-byte aligned) of per-CTA partial weight-gradient sums that a
  * second small kernel adds into g_* (deterministic, no contended atomics); NULL = fp32 atomics straight on g_*. */
 uint32_t nb200_field_wgrad_scratch_bytes(void);
+/* Grid encoding + field network in ONE kernel (csrc/field_fused.cu): the [M,32] hash-grid features are gathered by producer
+ * warps straight into the tensor-core operand tile and never round-trip HBM.  Replaces GridEncoder.forward
+ * (gridencoder/grid.py:151-168, gridencoder.cu:87-244) followed by NeRFNetwork.forward / .density (nerf/network_grid.py:159-193).
+ * xyz f32 [M,3] in [-bound, bound] (normalised to [0,1] inside, grid.py:156); table = fp32 master embeddings, entries
+ * rounded to fp16 on load (the autocast path of grid.py:45-46); L must be 16, D = 3, C = 2.
+ *   rgba == NULL (dirs may be NULL): density only (trunk + density head)     -> sigma f32 [M]
+ *   rgba != NULL, act == NULL:       inference forward                       -> sigma, rgba f16 [M,4]
+ *   act != NULL:                     training forward: also writes x_en f16 [M,32], sigma_arg f32 [M], act f16 [5,M,64]
+ *                                    (what nb200_field_backward + nb200_fs_encode_backward read)
+ * count_dev as nb200_field_forward. */
+int nb200_field_fused_forward(const float *xyz, const float *dirs, float bound, const float *table, const int32_t *offsets,
+                              uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp,
+                              const void *fwd_img, float *sigma, float *sigma_arg, void *rgba, void *x_en, void *act,
+                              uint32_t M, const int32_t *count_dev, void *stream);
+
+/* ============================================================================================
+ * occupancy-grid update: replaces NeRFRenderer.update_extra_state (nerf/renderer.py:1658-1715).
+ * nb200_occ_density: the density query of every cell of every cascade in one launch (same fused kernel, positions
+ * generated in place): cell_xyz f32 [G^3,3] = cell centres in [-1,1] in the reference's x-major order (:1678), noise f32
+ * [cascade,G^3,3] = the torch.rand_like draws of :1690 (NULL: no jitter); point of cell c in cascade k:
+ * cell_xyz[c] * (b_k - h_k) + (2 noise - 1) * h_k with b_k = min(2^k, bound), h_k = b_k / G, products and sums rounded
+ * one by one as the reference's chain of torch ops rounds them.  tmp_grid f32 [cascade, G^3] indexed by Morton code (:1696).
+ * nb200_occ_finalize: density_grid = max(density_grid * decay, tmp_grid) where density_grid >= 0 (:1700-1702; tmp_grid NULL:
+ * skip), mean of the valid cells (fixed summation order, double accumulation), threshold = min(mean, density_thresh),
+ * bitfield = packbits(density_grid, threshold) (:1709), mean_count = int(sum(step_counter[:total_step, 0]) / total_step)
+ * (:1712-1714; step_counter i32 [16,2], total_step <= 16, 0: left unchanged).  No host synchronisation: state f32/i32 [8] =
+ * {mean density, threshold, mean_count (i32), valid cells (u32), ...} stays on the device.  scratch: nb200_occ_scratch_bytes(). */
+int nb200_occ_density(const float *cell_xyz, const float *noise, uint32_t G, uint32_t cascade, float bound, const float *table,
+                      const int32_t *offsets, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                      uint32_t interp, const void *fwd_img, float *tmp_grid, void *stream);
+uint32_t nb200_occ_scratch_bytes(void);
+int nb200_occ_finalize(float *density_grid, const float *tmp_grid, uint32_t n_cells, float decay, float density_thresh,
+                       const int32_t *step_counter, uint32_t total_step, uint8_t *bitfield, float *state, void *scratch,
+                       void *stream);
+
 /* get_embedder(4) of nerf/base.py:42-77 exactly as the field kernels evaluate it: dirs f32 [M,3] -> out f32 [M,27] =
  * [d, sin d, cos d, sin 2d, cos 2d, sin 4d, cos 4d, sin 8d, cos 8d] (one sincos + three angle doublings per component). */
 int nb200_freq_embed(const float *dirs, float *out, uint32_t M, void *stream);
@@ -265,10 +300,13 @@ int nb200_fused_adam(float *param, float *grad, float *exp_avg, float *exp_avg_s
  * decay_iters}; lr = lr0 * decay_base^min((t-1)/decay_iters, 1) (LambdaLR of main.py:189; decay_iters <= 0: constant). */
 int nb200_adam_hyper(int32_t *step, const float *sched, float *hyper, void *stream);
 
+#define NB200_PLAN_FUSED_FORWARD 1u   /* encode + field forward as one kernel (nb200_field_fused_forward): the stage timer
+                                         then reports the pair under "field_forward" and ~0 under "grid_encode_forward" */
 typedef struct nb200_train_plan {
     /* sizes and scalars */
     uint32_t N, M_cap, C, H, L, base_res, gridtype, max_steps;
-    float bound, dt_gamma, S, T_thresh, min_near, loss_scale, inv_n_total, pad0;
+    float bound, dt_gamma, S, T_thresh, min_near, loss_scale, inv_n_total;
+    uint32_t flags;                                              /* NB200_PLAN_* */
     uint64_t n_params, n_table_params;
     /* inputs (device) */
     const float *rays_o, *rays_d, *target, *aabb, *noises;      /* noises may be NULL (perturb off) */
