@@ -390,7 +390,8 @@ def run_b200(args):
         args.no_breakdown = True
     else:
         fs = fused_trainer.FusedTrainStep(model, n_rays, lr=5e-4, world_size=world, grad_sync=sync, use_graph=not args.no_graph,
-                                          pipeline_update=not args.no_pipeline, mask_weight=TRAIN_CONF, peer=peer, raygen=raygen)
+                                          pipeline_update=not args.no_pipeline, mask_weight=TRAIN_CONF, peer=peer, raygen=raygen,
+                                          fused_forward=os.environ.get("NB200_FUSED_FORWARD", "0") == "1")
     fs.target_mask.copy_(gt_mask)     # [N] ground-truth mask: resident (59 KB; not part of the per-step H2D count)
     # the batch is handed over the way a loader would: written into one of the trainer's two pinned staging slots, from where
     # step() copies it to the device (one H2D copy of 537 KB per step, inside the timed region)

@@ -4,9 +4,25 @@
 #pragma once
 #include "common.cuh"
 
-struct AdamHyper {          // 8 floats per parameter group, written by the host before every step
-    float lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale, pad;
+struct AdamHyper {          // 8 floats per parameter group, written on the device before every step (k_adam_hyper*)
+    float lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale;
+    float skip;             // != 0: a gradient of this step was not finite -- leave p, m, v alone (GradScaler.step semantics)
 };
+
+// Dynamic loss scaling on the device -- torch.cuda.amp.GradScaler as the reference trains with it
+// (nerf/utils_init_nerf.py:100,612-629): scaler state, 8 x 32 bit:
+//   [0] scale f32        [1] growth tracker i32        [2] iteration u32 (every update, taken or skipped)
+//   [3] skipped steps u32        [4], [5] status words of even / odd iterations: bit 31 = found-inf (set by the backward
+//   kernels), bits 0..30 = the step's sample count (so that ray-sharded ranks agree on buffer growth)
+//   [6] growth interval i32 (2000)        [7] unused
+// The backward kernels of iteration `it` raise bit 31 of word [4 + (it & 1)]; the update skips the optimiser step when any
+// rank's bit is up and nb200_scaler_commit halves the scale (else counts towards doubling it) and clears the OTHER word for
+// iteration it + 1 -- two alternating words so that a fast rank never clears one a slow peer has yet to read.  (bit 31 so
+// that an all-reduce(MAX) of the words -- the NCCL form of the exchange -- preserves it.)
+constexpr uint32_t kScalerScale = 0, kScalerTracker = 1, kScalerIter = 2, kScalerSkipped = 3, kScalerFlag0 = 4, kScalerInterval = 6;
+constexpr uint32_t kScalerInfBit = 0x80000000u;
+__device__ __forceinline__ uint32_t *scaler_flag(uint32_t *scaler) { return scaler + kScalerFlag0 + (scaler[kScalerIter] & 1u); }
+__device__ __forceinline__ void scaler_raise(uint32_t *scaler) { atomicOr(scaler_flag(scaler), kScalerInfBit); }
 
 // per-group constants hoisted out of the sweep (two of the three divisions of the update are per-step constants)
 struct AdamConst {

@@ -161,19 +161,16 @@ k_field_fused(const FusedArgs p, const __grid_constant__ CUtensorMap act_map) {
             // ---- the 16 x 8 corner gathers of this sample, four levels (32 loads) in flight at a time
             uint4 xe[4];
             {
-                const float x0 = xf(px), x1 = xf(py), x2 = xf(pz);
+                float x0 = xf(px), x1 = xf(py), x2 = xf(pz);
                 const bool live = valid && !((x0 < 0 || x0 > 1) || (x1 < 0 || x1 > 1) || (x2 < 0 || x2 > 1));
+                if (!live) { x0 = x1 = x2 = 0.5f; }          // branch-free gather: dead rows read a valid cell and are zeroed below
 #pragma unroll
                 for (uint32_t l0 = 0; l0 < kFusedLevels; l0 += 4) {
                     float res[8];
-#pragma unroll
-                    for (uint32_t j = 0; j < 4; j++) {
-                        float r0 = 0.0f, r1 = 0.0f;
-                        if (live) ge_level_gather<float, true>(info[l0 + j], p.table, x0, x1, x2, half_off, p.interp, r0, r1);
-                        res[2 * j] = r0; res[2 * j + 1] = r1;
-                    }
-                    xe[l0 >> 2] = make_uint4(pack_h2(res[0], res[1]), pack_h2(res[2], res[3]), pack_h2(res[4], res[5]),
-                                             pack_h2(res[6], res[7]));
+                    ge_gather4<float, true>(info + l0, p.table, x0, x1, x2, half_off, p.interp, res);
+                    const uint4 pk = make_uint4(pack_h2(res[0], res[1]), pack_h2(res[2], res[3]), pack_h2(res[4], res[5]),
+                                                pack_h2(res[6], res[7]));
+                    xe[l0 >> 2] = live ? pk : make_uint4(0, 0, 0, 0);
                 }
             }
             // ---- hand the row over once the consumers have released the tile

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include "field_common.cuh"
+#include "adam.cuh"
 #include <string.h>
 
 namespace {
@@ -678,7 +679,8 @@ k_field_backward(const FieldBwdArgs p) {
 // and 4 -> 16 outputs) are never written by the flush and never read here.  256 threads = 64 parameters x 4 slab groups.
 __global__ void __launch_bounds__(256)
 k_field_wgrad_reduce(const float *__restrict__ slabs, uint32_t grid, uint32_t M, const int32_t *__restrict__ count_dev,
-                     float *__restrict__ g_trunk, float *__restrict__ g_density, float *__restrict__ g_rgb) {
+                     float *__restrict__ g_trunk, float *__restrict__ g_density, float *__restrict__ g_rgb,
+                     uint32_t *__restrict__ scaler) {
     __shared__ float part[4][64];
     const uint32_t Mrows = count_dev ? min(M, (uint32_t)max(*count_dev, 0)) : M;
     const uint32_t nslab = min(grid, (Mrows + 127) / 128);
@@ -690,14 +692,23 @@ k_field_wgrad_reduce(const float *__restrict__ slabs, uint32_t grid, uint32_t M,
     __syncthreads();
     if (cg != 0 || i >= kWgradFloats || nslab == 0) return;
     const float sum = (part[0][pl] + part[1][pl]) + (part[2][pl] + part[3][pl]);
-    if (i < kTrunkFloats) { g_trunk[i] += sum; return; }
-    uint32_t j = i - kTrunkFloats;
-    if (j < kDensityFloats) {
-        if (j < D_W2 || j < D_W2 + 64) g_density[j] += sum;            // layer 0, and row 0 of the padded head
-        return;
+    // every gradient tile of the step (head gradients, dHR .. dH1) is an operand of some weight-gradient GEMM: an fp16
+    // overflow anywhere in the backward chain shows up here as inf / NaN (inf x 0 included) -- GradScaler's found_inf.
+    // Only entries the flush wrote are looked at (the padded head rows of a slab are never written).
+    float *dst = nullptr;
+    if (i < kTrunkFloats) dst = g_trunk + i;
+    else {
+        uint32_t j = i - kTrunkFloats;
+        if (j < kDensityFloats) {
+            if (j < D_W2 + 64) dst = g_density + j;                        // layer 0, and row 0 of the padded head
+        } else {
+            j -= kDensityFloats;
+            if (j < R_W2 + 4 * 64) dst = g_rgb + j;                        // layer 0, and rows 0..3 of the padded head
+        }
     }
-    j -= kDensityFloats;
-    if (j < R_W2 || j < R_W2 + 4 * 64) g_rgb[j] += sum;                // layer 0, and rows 0..3 of the padded head
+    if (!dst) return;
+    if (scaler && !isfinite(sum)) scaler_raise(scaler);
+    *dst += sum;
 }
 
 }  // namespace
@@ -777,8 +788,9 @@ int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, c
 int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,
                          const void *x_en, const float *dirs, const void *act, const void *bwd_img, void *d_x_en,
                          float *g_trunk, float *g_density, float *g_rgb, uint32_t M, const int32_t *count_dev,
-                         float *wg_scratch, void *stream) {
+                         float *wg_scratch, uint32_t *scaler, void *stream) {
     if (M == 0) return 0;
+    if (scaler && !wg_scratch) return NB200_E_BAD_ARG;      // the finite check lives in the slab reduction
     if (!d_sigma || !d_rgba || !sigma_arg || !rgba || !x_en || !dirs || !act || !bwd_img || !d_x_en || !g_trunk ||
         !g_density || !g_rgb)
         return NB200_E_BAD_ARG;
@@ -805,7 +817,7 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
     NB_LAUNCH_CHECK();
     if (wg_scratch) {
         k_field_wgrad_reduce<<<nb_div_up(kWgradFloats, 64), 256, 0, nb_stream(stream)>>>(wg_scratch, grid, M, count_dev, g_trunk,
-                                                                                  g_density, g_rgb);
+                                                                                  g_density, g_rgb, scaler);
         NB_LAUNCH_CHECK();
     }
     return 0;

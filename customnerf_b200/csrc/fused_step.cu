@@ -111,18 +111,22 @@ rest:
     if ((rc = nb200_fs_composite_forward(p->sigma, p->rgba, p->deltas, p->rays, p->M_cap, p->N, p->T_thresh,
                                          p->weights_sum, p->depth, p->image, p->target, p->inv_n_total, p->loss_scale,
                                          p->loss, p->g_image, p->target_mask, p->mask_weight, p->render_mask,
-                                         p->g_render_mask, stream))) return rc;
+                                         p->g_render_mask, (const float *)p->scaler, stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_fs_composite_backward(p->g_weights_sum, p->g_image, p->sigma, p->rgba, p->deltas, p->rays,
                                           p->weights_sum, p->image, p->M_cap, p->N, p->T_thresh, p->d_sigma, p->d_rgba,
                                           p->target_mask ? p->g_render_mask : nullptr, p->render_mask, stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_field_backward(p->d_sigma, p->d_rgba, p->sigma_arg, p->rgba, p->x_en, p->dirs, p->act, p->w_bwd,
-                                   p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, stream))) return rc;
+                                   p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, p->scaler, stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_fs_encode_backward(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
-                                       p->base_res, p->gridtype, 0, 0, p->m_eff, stream))) return rc;
+                                       p->base_res, p->gridtype, 0, 0, p->m_eff, p->scaler, stream))) return rc;
     tick(ev, k++, st);
+    // the step's sample count, parked where the (possibly concurrent: pipelined update next to the NEXT step's march, which
+    // resets the counter) update reads it for the status word of the loss scaler
+    if (p->scaler && (e = cudaMemcpyAsync(p->counter + 6, p->counter, sizeof(int32_t), cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
+        return (int)e;
     if (tm) tm->fb_done = true;
     return 0;
 }
@@ -153,9 +157,14 @@ int nb200_train_lgie_backward(const nb200_train_plan *p, const nb200_lgie_plan *
                                                    g->conf_thr, g->soft_mask, g->detach_bg, g->detach_mask_from_field,
                                                    p->d_sigma, p->d_rgba, stream))) return rc;
     if ((rc = nb200_field_backward(p->d_sigma, p->d_rgba, p->sigma_arg, p->rgba, p->x_en, p->dirs, p->act, p->w_bwd,
-                                   p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, stream))) return rc;
-    return nb200_fs_encode_backward(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
-                                    p->base_res, p->gridtype, 0, 0, p->m_eff, stream);
+                                   p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, p->scaler, stream))) return rc;
+    if ((rc = nb200_fs_encode_backward(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
+                                       p->base_res, p->gridtype, 0, 0, p->m_eff, p->scaler, stream))) return rc;
+    if (p->scaler) {
+        cudaError_t e = cudaMemcpyAsync(p->counter + 6, p->counter, sizeof(int32_t), cudaMemcpyDeviceToDevice, nb_stream(stream));
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
 }
 
 int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
@@ -169,9 +178,12 @@ int nb200_train_update(const nb200_train_plan *p, void *stream) {
     StageTimer *tm = (StageTimer *)p->timer;
     cudaEvent_t *ev = tm ? tm->up : nullptr;
     tick(ev, 0, st);
-    if ((rc = nb200_adam_hyper(p->step, p->sched, p->hyper, stream))) return rc;
+    if (p->scaler) {        // dynamic loss scale: hyper-parameters for step + 1, sweep (skipped on a non-finite gradient), commit
+        if ((rc = nb200_adam_hyper_scaled(p->step, p->sched, p->hyper, p->scaler, 1, p->counter + 6, stream))) return rc;
+    } else if ((rc = nb200_adam_hyper(p->step, p->sched, p->hyper, stream))) return rc;
     if ((rc = nb200_fused_adam(p->params_flat, p->grads_flat, p->exp_avg, p->exp_avg_sq, p->n_params, p->n_table_params,
                                p->hyper, 1, stream))) return rc;
+    if (p->scaler && (rc = nb200_scaler_commit(p->step, p->scaler, nullptr, 1, p->counter + 5, stream))) return rc;
     tick(ev, 1, st);
     if ((rc = nb200_field_pack_weights(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, stream))) return rc;
     tick(ev, 2, st);
@@ -188,8 +200,13 @@ int nb200_train_update_peer(const nb200_train_plan *p, const nb200_peer_plan *pe
     StageTimer *tm = (StageTimer *)p->timer;
     cudaEvent_t *ev = tm ? tm->up : nullptr;
     tick(ev, 0, st);
-    if ((rc = nb200_adam_hyper(p->step, p->sched, p->hyper, stream))) return rc;
+    const bool scaled = p->scaler != nullptr;
+    if (scaled && peer->scalers[peer->rank] != p->scaler) return NB200_E_BAD_ARG;   // the peers must be able to read the flags
+    if (scaled) {
+        if ((rc = nb200_adam_hyper_scaled(p->step, p->sched, p->hyper, p->scaler, 0, p->counter + 6, stream))) return rc;
+    } else if ((rc = nb200_adam_hyper(p->step, p->sched, p->hyper, stream))) return rc;
     if ((rc = nb200_peer_reduce_adam_bcast(peer, stream))) return rc;
+    if (scaled && (rc = nb200_scaler_commit(p->step, p->scaler, peer->scalers, peer->world, p->counter + 5, stream))) return rc;
     tick(ev, 1, st);
     if ((rc = nb200_field_pack_weights(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, stream))) return rc;
     tick(ev, 2, st);

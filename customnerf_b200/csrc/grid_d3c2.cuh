@@ -22,6 +22,7 @@ constexpr uint32_t P1 = 2654435761u, P2 = 805459861u;
 struct InXform {
     float add, mul;                 // mul == 0: identity (inputs are already in [0, 1])
     const int32_t *count_dev;       // when non-null only rows < min(B, *count_dev) are processed
+    uint32_t *scaler = nullptr;     // backward only: loss-scaler words (adam.cuh); a non-finite feature gradient raises its flag
     __device__ __forceinline__ float operator()(float x) const { return mul != 0.0f ? __fmul_rn(__fadd_rn(x, add), mul) : x; }
 };
 
@@ -104,6 +105,64 @@ __device__ __forceinline__ void ge_level_gather(const LevelInfo &li, const TE *_
         w *= (idx & 4u) ? p2 : 1 - p2;
         r0 += w * v[idx].x;
         r1 += w * v[idx].y;
+    }
+}
+
+// ge_row_d3 with the (never taken on the reference's table layouts: dense levels index below their size, capped levels have
+// power-of-two sizes) modulo kept out of line: 32 inlined copies of the division sequence per 4-level group cost ~2400
+// instructions of I-cache footprint in ge_gather4
+__device__ __noinline__ uint32_t ge_mod_slow(uint32_t raw, uint32_t size) { return raw % size; }
+__device__ __forceinline__ uint32_t ge_row_d3_compact(const LevelInfo &li, uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t raw = li.use_hash ? (x ^ (y * P1) ^ (z * P2)) : (x + y * li.m1 + z * li.m2);
+    if (li.mask) return raw & li.mask;
+    if (raw >= li.size) return ge_mod_slow(raw, li.size);
+    return raw;
+}
+
+// Four consecutive levels at once for the latency-bound callers (field_fused.cu: few gather warps per SM): all 32 row
+// indices first, then the 32 loads back to back (32 independent requests in flight per thread), then the interpolation --
+// per level the very expression sequence of ge_level_gather, so the results are bit-identical to it.
+template <typename TE, bool kRoundHalf>
+__device__ __forceinline__ void ge_gather4(const LevelInfo *__restrict__ info4, const TE *__restrict__ grid, float x0, float x1,
+                                           float x2, float half_off, uint32_t interp, float (&res)[8]) {
+    float p[4][3];
+    const TE *src[4][8];
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+        const LevelInfo li = info4[j];
+        float p0 = x0 * li.scale + half_off, p1 = x1 * li.scale + half_off, p2 = x2 * li.scale + half_off;
+        const uint32_t g0 = (uint32_t)floorf(p0), g1 = (uint32_t)floorf(p1), g2 = (uint32_t)floorf(p2);
+        p0 -= (float)g0; p1 -= (float)g1; p2 -= (float)g2;
+        if (interp == 1) { p0 = ge_smoothstep(p0); p1 = ge_smoothstep(p1); p2 = ge_smoothstep(p2); }
+        p[j][0] = p0; p[j][1] = p1; p[j][2] = p2;
+        const TE *lg = grid + (size_t)li.offset * 2;
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; idx++)
+            src[j][idx] = lg + (size_t)ge_row_d3_compact(li, g0 + (idx & 1u), g1 + ((idx >> 1) & 1u), g2 + ((idx >> 2) & 1u)) * 2;
+    }
+    float2 v[4][8];
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; idx++) {
+            if constexpr (kRoundHalf) v[j][idx] = ge_ld2_round_half(src[j][idx]);
+            else v[j][idx] = ge_ld2(src[j][idx]);
+        }
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+        const float p0 = p[j][0], p1 = p[j][1], p2 = p[j][2];
+        float r0 = 0.0f, r1 = 0.0f;
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; idx++) {
+            float w = 1;
+            w *= (idx & 1u) ? p0 : 1 - p0;
+            w *= (idx & 2u) ? p1 : 1 - p1;
+            w *= (idx & 4u) ? p2 : 1 - p2;
+            r0 += w * v[j][idx].x;
+            r1 += w * v[j][idx].y;
+        }
+        res[2 * j] = r0; res[2 * j + 1] = r1;
     }
 }
 

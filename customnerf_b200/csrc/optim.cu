@@ -9,6 +9,7 @@
 // Arithmetic follows torch's fused Adam (aten/src/ATen/native/cuda/fused_adam_utils.cuh, non-amsgrad, no weight
 // decay): m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2; p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps).
 #include "adam.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -19,6 +20,12 @@ k_fused_adam(float4 *__restrict__ param, float4 *__restrict__ grad, float4 *__re
              float4 *__restrict__ exp_avg_sq, uint64_t n4, uint64_t split4, const AdamHyper *__restrict__ hyper,
              int zero_grad) {
     const AdamConst h0(hyper[0]), h1(hyper[1]);
+    if (hyper[0].skip != 0.0f) {            // a non-finite gradient this step: no update, only the gradient reset
+        if (zero_grad)
+            for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x)
+                grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
         const AdamConst &h = i < split4 ? h0 : h1;
         // the moments are touched once per step: streaming loads / stores keep them from displacing the table and its
@@ -38,6 +45,7 @@ k_fused_adam_tail(float *__restrict__ param, float *__restrict__ grad, float *__
     const uint64_t i = begin + threadIdx.x;
     if (i >= n) return;
     const AdamConst h(hyper[i < split ? 0 : 1]);
+    if (hyper[0].skip != 0.0f) { if (zero_grad) grad[i] = 0.0f; return; }
     float p = param[i], g = grad[i], m = exp_avg[i], v = exp_avg_sq[i];
     adam1(p, g, m, v, h);
     param[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
@@ -60,9 +68,62 @@ __global__ void k_adam_hyper(int32_t *__restrict__ step, const float *__restrict
         AdamHyper h;
         h.lr = (float)((double)sched[g] * decay);
         h.beta1 = sched[2]; h.beta2 = sched[3]; h.eps = sched[4];
-        h.bc1 = bc1; h.bc2_sqrt = bc2s; h.grad_scale = sched[5]; h.pad = 0.0f;
+        h.bc1 = bc1; h.bc2_sqrt = bc2s; h.grad_scale = sched[5]; h.skip = 0.0f;
         out[g] = h;
     }
+}
+
+// The same for a step under the device-side loss scaler (adam.cuh): t = *step + 1 WITHOUT committing it (the step count only
+// advances when the update is taken: nb200_scaler_commit), grad_scale = 1 / scaler.scale, skip = this rank's found-inf flag
+// (local_skip; the peer-memory update ORs every rank's flag itself and ignores it).
+__global__ void k_adam_hyper_scaled(const int32_t *__restrict__ step, const float *__restrict__ sched, AdamHyper *__restrict__ out,
+                                    uint32_t *__restrict__ scaler, int local_skip, const int32_t *__restrict__ samples) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (samples) atomicOr(scaler_flag(scaler), (uint32_t)max(*samples, 0) & ~kScalerInfBit);   // this step's sample count, for the peers
+    const int32_t t = *step + 1;
+    const double b1 = sched[2], b2 = sched[3];
+    double decay = 1.0;
+    if (sched[7] > 0.0f) decay = pow((double)sched[6], fmin((double)(t - 1) / (double)sched[7], 1.0));
+    const float bc1 = (float)(1.0 - pow(b1, (double)t)), bc2s = (float)sqrt(1.0 - pow(b2, (double)t));
+    const float scale = __uint_as_float(scaler[kScalerScale]);
+    const float skip = (local_skip && (*scaler_flag(scaler) & kScalerInfBit)) ? 1.0f : 0.0f;
+    for (int g = 0; g < 2; g++) {
+        AdamHyper h;
+        h.lr = (float)((double)sched[g] * decay);
+        h.beta1 = sched[2]; h.beta2 = sched[3]; h.eps = sched[4];
+        h.bc1 = bc1; h.bc2_sqrt = bc2s; h.grad_scale = 1.0f / scale; h.skip = skip;
+        out[g] = h;
+    }
+}
+
+// GradScaler.update() (torch/amp/grad_scaler.py: backoff 0.5, growth 2.0 every `interval` clean steps) + the optimiser's own
+// step count.  peers[q] = the scaler words of rank q (this rank's included); world = 1: only the local flag.
+struct ScalerPeers { uint32_t *s[NB200_PEER_MAX]; };
+__global__ void k_scaler_commit(int32_t *__restrict__ step, uint32_t *__restrict__ scaler, ScalerPeers peers, uint32_t world,
+                                int32_t *__restrict__ max_samples) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t it = scaler[kScalerIter], slot = kScalerFlag0 + (it & 1u);
+    uint32_t word = scaler[slot], found = word & kScalerInfBit, smax = word & ~kScalerInfBit;
+    for (uint32_t q = 0; q < world; q++)
+        if (peers.s[q]) {
+            word = *(volatile uint32_t *)(peers.s[q] + slot);
+            found |= word & kScalerInfBit;
+            smax = max(smax, word & ~kScalerInfBit);
+        }
+    if (max_samples) *max_samples = (int32_t)smax;          // the same number on every rank: buffer growth is a joint decision
+    float scale = __uint_as_float(scaler[kScalerScale]);
+    int32_t tracker = (int32_t)scaler[kScalerTracker];
+    if (found) {
+        scale *= 0.5f; tracker = 0; scaler[kScalerSkipped] += 1u;
+    } else {
+        *step += 1;
+        const int32_t interval = (int32_t)scaler[kScalerInterval];
+        if (++tracker >= interval && interval > 0) { scale *= 2.0f; tracker = 0; }
+    }
+    scaler[kScalerScale] = __float_as_uint(scale);
+    scaler[kScalerTracker] = (uint32_t)tracker;
+    scaler[kScalerFlag0 + ((it + 1u) & 1u)] = 0u;           // the flag of iteration it + 1 (nobody reads it any more)
+    scaler[kScalerIter] = it + 1u;
 }
 
 // loss = sum (image - target)^2 * inv_n ; g_image = 2 (image - target) * inv_n * loss_scale     (one thread per ray)
@@ -108,8 +169,10 @@ int nb200_fused_adam(float *param, float *grad, float *exp_avg, float *exp_avg_s
     const uint64_t n4 = n / 4;
     cudaStream_t st = nb_stream(stream);
     if (n4) {
+        static int per_sm = -1;         // tuning knob: CTAs per SM (a thin sweep leaves room for a co-running kernel)
+        if (per_sm < 0) { const char *e = getenv("NB200_ADAM_CTAS_PER_SM"); per_sm = e ? atoi(e) : 0; if (per_sm <= 0 || per_sm > 8) per_sm = 8; }
         const uint32_t want = nb_div_up(n4, 256);
-        const uint32_t grid = want < (uint32_t)sms * 8 ? want : (uint32_t)sms * 8;
+        const uint32_t grid = want < (uint32_t)sms * per_sm ? want : (uint32_t)sms * per_sm;
         k_fused_adam<<<grid, 256, 0, st>>>((float4 *)param, (float4 *)grad, (float4 *)exp_avg, (float4 *)exp_avg_sq, n4,
                                            split / 4, (const AdamHyper *)hyper, zero_grad);
         NB_LAUNCH_CHECK();
@@ -125,6 +188,24 @@ int nb200_fused_adam(float *param, float *grad, float *exp_avg, float *exp_avg_s
 int nb200_adam_hyper(int32_t *step, const float *sched, float *hyper, void *stream) {
     if (!step || !sched || !hyper) return NB200_E_BAD_ARG;
     k_adam_hyper<<<1, 32, 0, nb_stream(stream)>>>(step, sched, (AdamHyper *)hyper);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_adam_hyper_scaled(const int32_t *step, const float *sched, float *hyper, uint32_t *scaler, int local_skip,
+                            const int32_t *samples, void *stream) {
+    if (!step || !sched || !hyper || !scaler) return NB200_E_BAD_ARG;
+    k_adam_hyper_scaled<<<1, 32, 0, nb_stream(stream)>>>(step, sched, (AdamHyper *)hyper, scaler, local_skip, samples);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_scaler_commit(int32_t *step, uint32_t *scaler, uint32_t *const *peer_scalers, uint32_t world, int32_t *max_samples,
+                        void *stream) {
+    if (!step || !scaler || world > NB200_PEER_MAX) return NB200_E_BAD_ARG;
+    ScalerPeers peers;
+    for (uint32_t q = 0; q < NB200_PEER_MAX; q++) peers.s[q] = (peer_scalers && q < world) ? peer_scalers[q] : nullptr;
+    k_scaler_commit<<<1, 32, 0, nb_stream(stream)>>>(step, scaler, peers, peer_scalers ? world : 0, max_samples);
     NB_LAUNCH_CHECK();
     return 0;
 }

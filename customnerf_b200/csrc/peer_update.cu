@@ -108,9 +108,18 @@ k_peer_reduce_adam_bcast(const nb200_peer_plan pl) {
 
     peer_barrier<W>(pl, 0, epoch);                                       // every rank's gradient is complete
 
+    // dynamic loss scaling (adam.cuh): a non-finite gradient on ANY rank skips the step on EVERY rank -- each CTA ORs the
+    // ranks' found-inf flags of this iteration (final since the start barrier; all ranks run the same iteration)
+    bool skip = false;
+    if (pl.scalers[pl.rank]) {
+        const uint32_t slot = kScalerFlag0 + (pl.scalers[pl.rank][kScalerIter] & 1u);
+#pragma unroll
+        for (int q = 0; q < W; q++) skip |= (*(volatile const uint32_t *)(pl.scalers[q] + slot) & kScalerInfBit) != 0u;
+    }
+
     float4 *const p_own = (float4 *)pl.params[pl.rank];
     float4 *const m_own = (float4 *)pl.exp_avg, *const v_own = (float4 *)pl.exp_avg_sq;
-    for (uint64_t base = c_lo + threadIdx.x; base < c_hi; base += (uint64_t)blockDim.x * U) {
+    for (uint64_t base = c_lo + threadIdx.x; base < c_hi && !skip; base += (uint64_t)blockDim.x * U) {
         float4 gq[U][MC ? 1 : W], p[U], m[U], v[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -280,6 +289,8 @@ int nb200_peer_reduce_adam_bcast(const nb200_peer_plan *pl, void *stream) {
         al |= reinterpret_cast<uintptr_t>(pl->params[q]) | reinterpret_cast<uintptr_t>(pl->grads[q]);
     }
     if ((pl->mc_grads == nullptr) != (pl->mc_params == nullptr)) return NB200_E_BAD_ARG;
+    for (uint32_t q = 0; q < pl->world; q++)
+        if ((pl->scalers[q] == nullptr) != (pl->scalers[pl->rank] == nullptr)) return NB200_E_BAD_ARG;
     al |= reinterpret_cast<uintptr_t>(pl->mc_grads) | reinterpret_cast<uintptr_t>(pl->mc_params);
     if (al & 15u) return NB200_E_BAD_ARG;
     if (pl->n == 0) return 0;

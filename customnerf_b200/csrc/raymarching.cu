@@ -773,6 +773,7 @@ __device__ __forceinline__ void ld_rgb(const TC *__restrict__ rgbs, size_t s, fl
 struct MseArgs {
     const float *target; float *loss, *g_image; float inv_n, scale;
     const float *target_mask; float *render_mask, *g_render_mask; float mask_weight;
+    const float *scale_dev = nullptr;       // device-side loss scale (the scaler words of adam.cuh): overrides `scale`
 };
 
 // LGIE composites (the editing render of nerf/renderer.py:383-474, on the occupancy path: rendering._lgie_composites):
@@ -862,12 +863,13 @@ k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ r
     if (mse.target) {
         if (lane == 0) {
             const float d0 = r - mse.target[index * 3], d1 = g - mse.target[index * 3 + 1], d2 = b - mse.target[index * 3 + 2];
-            const float k = 2.0f * mse.inv_n * mse.scale;
+            const float lscale = mse.scale_dev ? __ldg(mse.scale_dev) : mse.scale;
+            const float k = 2.0f * mse.inv_n * lscale;
             mse.g_image[index * 3] = d0 * k; mse.g_image[index * 3 + 1] = d1 * k; mse.g_image[index * 3 + 2] = d2 * k;
             float part = d0 * d0 + d1 * d1 + d2 * d2;
             if (mse.target_mask) {          // mean over N x 1 entries = 3 x the per-element weight of the N x 3 image
                 const float dm = mk - mse.target_mask[index];
-                mse.g_render_mask[index] = 2.0f * dm * (3.0f * mse.inv_n) * mse.mask_weight * mse.scale;
+                mse.g_render_mask[index] = 2.0f * dm * (3.0f * mse.inv_n) * mse.mask_weight * lscale;
                 part += 3.0f * mse.mask_weight * dm * dm;
             }
             loss_part[threadIdx.x >> 5] = part;
@@ -1357,13 +1359,13 @@ int nb200_fs_composite_forward(const float *sigmas, const void *rgba, const floa
                                uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image,
                                const float *target, float inv_n, float loss_scale, float *loss, float *g_image,
                                const float *target_mask, float mask_weight, float *render_mask, float *g_render_mask,
-                               void *stream) {
+                               const float *loss_scale_dev, void *stream) {
     if (N == 0) return 0;
     if (target && (!loss || !g_image)) return NB200_E_BAD_ARG;
     if (target_mask && (!target || !render_mask || !g_render_mask)) return NB200_E_BAD_ARG;
     k_composite_train_fwd<__half><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
         sigmas, (const __half *)rgba, deltas, rays, M, N, T_thresh, weights_sum, depth, image,
-        MseArgs{target, loss, g_image, inv_n, loss_scale, target_mask, render_mask, g_render_mask, mask_weight});
+        MseArgs{target, loss, g_image, inv_n, loss_scale, target_mask, render_mask, g_render_mask, mask_weight, loss_scale_dev});
     NB_LAUNCH_CHECK();
     return 0;
 }

@@ -81,7 +81,9 @@ class FusedEditStep(FusedTrainStep):
             for v, d in enumerate((out, out["fg"], out["bg"])):
                 for key, buf in (("weights_sum", self.g_ws), ("image", self.g_image), ("render_mask", self.g_mask)):
                     flat.append(d[key]); slots.append(buf[v])
-            grads = torch.autograd.grad(loss * LOSS_SCALE, flat, allow_unused=True)
+            # the loss scale is the device-side scaler's current value (a tensor: no host read), or the constant
+            scale = LOSS_SCALE if self.scaler is None else self.scaler[0:1].view(torch.float32)[0]
+            grads = torch.autograd.grad(loss * scale, flat, allow_unused=True)
         for gr, slot in zip(grads, slots):
             if gr is None:
                 slot.zero_()

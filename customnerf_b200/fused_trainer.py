@@ -32,7 +32,8 @@ import torch
 
 from . import _lib as L
 
-LOSS_SCALE = 128.0
+LOSS_SCALE = 128.0          # initial loss scale (tiny-cuda-nn's own backward loss scale); dynamic from there on, see below
+GROWTH_INTERVAL = 2000      # torch.cuda.amp.GradScaler's default: the scale doubles after this many steps without overflow
 # this library's kernels in one step: march count (+ near/far) + scan + expand, encode, field, composite (+ MSE),
 # composite^T, field^T + weight-gradient reduce, encode^T, adam hyper, adam, weight pack
 KERNELS_PER_STEP = 12
@@ -60,7 +61,7 @@ class TrainPlan(C.Structure):
             "nears", "fars", "weights_sum", "depth", "image", "g_weights_sum", "g_image", "loss",
             "rays", "counter", "m_eff", "scratch",
             "xyzs", "dirs", "deltas", "sigma", "sigma_arg", "d_sigma", "d_rgba",
-            "x_en", "rgba", "act", "d_x_en", "wg_scratch", "timer"]
+            "x_en", "rgba", "act", "d_x_en", "wg_scratch", "timer", "scaler"]
     _fields_ = ([(n, C.c_uint32) for n in _u32] + [(n, C.c_float) for n in _f32] + [(n, C.c_uint32) for n in _flags] +
                 [(n, C.c_uint64) for n in _u64] +
                 [(n, C.c_void_p) for n in _ptr0] + [(n, C.c_float) for n in _f32b] + [(n, C.c_void_p) for n in _ptr])
@@ -101,7 +102,7 @@ class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
                  lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0,
-                 peer=None, raygen=None, fused_forward=True):
+                 peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True):
         if not model.cuda_ray:
             raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
@@ -129,6 +130,8 @@ class FusedTrainStep:
         self.raygen = raygen
         if raygen is not None and int(raygen["H"]) * int(raygen["W"]) != int(n_rays):
             raise RuntimeError("FusedTrainStep: raygen H x W must equal n_rays")
+        if allreduce_chunks > 1:
+            dynamic_loss_scale = False          # the chunked all-reduce experiment keeps the constant scale
         if peer is not None and (grad_sync is not None or allreduce_chunks > 1):
             raise RuntimeError("FusedTrainStep: peer replaces grad_sync / allreduce_chunks")
         # pipeline_update: the optimiser update of step k (all-reduce, Adam, weight re-pack) runs on a second stream
@@ -140,7 +143,10 @@ class FusedTrainStep:
         # MSE(image, target) + mask_weight * MSE(render_mask, target_mask); render_mask composites the 4th field output
         self.mask_weight = float(mask_weight)
         # fused_forward: grid gather + field network forward as ONE kernel (csrc/field_fused.cu: the features are gathered by
-        # producer warps straight into the tensor-core operand tile); False: two launches (encode, then field)
+        # producer warps straight into the tensor-core operand tile); False (default): two launches (encode, then field).
+        # Measured on B200 at configs[1] (profiles/r02_fused_forward.md): the fused kernel is bit-identical but SLOWER in the
+        # training step (166 us against 55 + 47 us): the MLP's 2 x 112 KB of shared memory leave the gathers ~4 KB of L1 and
+        # 8 warps per SM, where the standalone encoder has ~220 KB and ~31
         self.fused_forward = bool(fused_forward) and model.pos_en.num_levels == 16
         self.kernels_per_step = KERNELS_PER_STEP - (1 if self.fused_forward else 0)
         self.pipeline_update = bool(pipeline_update)
@@ -163,6 +169,18 @@ class FusedTrainStep:
         self.sched = torch.tensor([self.lr * 10.0, self.lr, betas[0], betas[1], self.eps, 1.0 / LOSS_SCALE,
                                    float(lr_decay_base), float(lr_decay_iters)], dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        # dynamic loss scaling with skipped steps, all on the device (torch.cuda.amp.GradScaler as the reference trains with it,
+        # utils_init_nerf.py:100,612-629; csrc/adam.cuh): 8 words {scale, growth tracker, iteration, skipped steps, two found-inf
+        # flags, growth interval, -}.  The backward kernels raise the flag when a gradient is not finite; the update then leaves
+        # p, m, v and the step count alone and halves the scale -- no host synchronisation, captured in the step's graph.  With
+        # the peer-memory update the words live in peer-visible memory: any rank's overflow skips the step on every rank.
+        self.dynamic_loss_scale = bool(dynamic_loss_scale)
+        self.scaler = None
+        if self.dynamic_loss_scale:
+            self.scaler = peer.scaler if peer is not None else torch.zeros(8, dtype=torch.int32, device=dev)
+            self.scaler.zero_()
+            self.scaler[0:1].view(torch.float32).fill_(LOSS_SCALE)
+            self.scaler[6] = GROWTH_INTERVAL
         nb = int(self.lib.nb200_field_weight_image_bytes())
         self.w_fwd = torch.empty(nb, dtype=torch.uint8, device=dev)
         self.w_bwd = torch.empty(nb, dtype=torch.uint8, device=dev)
@@ -202,7 +220,7 @@ class FusedTrainStep:
         self._ring_events = [torch.cuda.Event(), torch.cuda.Event()]
         self._steps_launched = 0
         self.peer_plan = None if peer is None else peer.plan(self.layout[0][2], self.exp_avg, self.exp_avg_sq, self.hyper,
-                                                             status=self.stats[4:5])
+                                                             status=self.stats[4:5], use_scaler=self.dynamic_loss_scale)
         self.n_total = N * world_size
         self._pack()
         self.m_cap = 0
@@ -273,6 +291,7 @@ class FusedTrainStep:
         p.sigma, p.sigma_arg, p.d_sigma, p.d_rgba = a(self.sigma), a(self.sigma_arg), a(self.d_sigma), a(self.d_rgba)
         p.x_en, p.rgba, p.act, p.d_x_en = a(self.x_en), a(self.rgba), a(self.act), a(self.d_x_en)
         p.wg_scratch = a(self.wg_scratch)
+        p.scaler = a(self.scaler)
         assert C.sizeof(p) == int(self.lib.nb200_train_plan_bytes()), "nb200_train_plan layout mismatch"
         self.plan = p
 
@@ -289,6 +308,17 @@ class FusedTrainStep:
             L.u32(o.shape[0]), L.u32(m.cascade), L.u32(m.grid_size), L.ptr(nears), L.ptr(fars), L.ptr(None), L.ptr(rays),
             L.ptr(counter), L.ptr(self.scratch), L.stream()), "count")
         return int(counter[0].item())
+
+    def _max_over_ranks(self, n):
+        """the sample-buffer capacity is the same on every rank of a ray-sharded job: growth (which drops the captured graph
+        and re-runs warm-up steps that contain the collective / peer update) must happen on all ranks at the same step"""
+        if self.world_size > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                t = torch.tensor([int(n)], dtype=torch.int64, device=self.dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.process_group if self.peer is None else self.peer.group)
+                return int(t[0])
+        return int(n)
 
     @staticmethod
     def _round_cap(samples):
@@ -362,6 +392,10 @@ class FusedTrainStep:
                 return
             if self.grad_sync is not None:
                 self.grad_sync(self.grads_flat)
+                if self.scaler is not None and self.world_size > 1:
+                    # an overflow on any rank skips the step on every rank: the found-inf flags travel with the gradient
+                    import torch.distributed as dist
+                    dist.all_reduce(self.scaler[4:6], op=dist.ReduceOp.MAX, group=self.process_group)
             _check(self.lib.nb200_train_update(C.byref(self.plan), st), "train_update")
 
     def _launch(self, staged=False):
@@ -385,6 +419,13 @@ class FusedTrainStep:
             main.wait_stream(self._side)
             _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(2), st), "train_phase(rest)")
         self.stats_host.copy_(self.stats, non_blocking=True)
+
+    def scaler_state(self):
+        """(loss scale, skipped steps, optimiser steps taken) -- synchronises with the device"""
+        if self.scaler is None:
+            return LOSS_SCALE, 0, int(self.step_count)
+        h = self.scaler.cpu()
+        return float(h[0:1].view(torch.float32)[0]), int(h[3]), int(self.step_count)
 
     def flush(self):
         """pipeline_update: apply the update of the last step() now, so that the parameters are current"""
@@ -416,7 +457,7 @@ class FusedTrainStep:
     def _capture(self, staged=False):
         """warm up on a side stream (first-call cudaFuncSetAttribute, allocator, RNG registration), capture one step,
         then restore the optimiser state the warm-up steps advanced"""
-        state = (self.params_flat, self.exp_avg, self.exp_avg_sq, self.step_count)
+        state = (self.params_flat, self.exp_avg, self.exp_avg_sq, self.step_count) + (() if self.scaler is None else (self.scaler,))
         if self.pipeline_update:            # the gradient of the step before is still waiting for its update: keep it
             state = state + (self.grads_flat,)
         keep = [t.clone() for t in state]
@@ -504,8 +545,9 @@ class FusedTrainStep:
                     self._stage(pose_staged)  # the capacity measurement below needs this camera's rays
                 rays_o = rays_d = target = None
             if self.m_cap == 0:
-                self._alloc_samples(self._round_cap(self.measure_samples(rays_o if rays_o is not None else self.rays_o,
-                                                                         rays_d if rays_d is not None else self.rays_d)))
+                n0 = self.measure_samples(rays_o if rays_o is not None else self.rays_o,
+                                          rays_d if rays_d is not None else self.rays_d)
+                self._alloc_samples(self._round_cap(self._max_over_ranks(n0)))
             # a batch handed over in the pinned staging buffer is copied by the graph itself (one H2D node)
             staged = False
             if rays_o is not None and not rays_o.is_cuda:
@@ -570,6 +612,14 @@ class FusedTrainStep:
                                "a rank left the job or launched fewer steps" % int(s[4]))
         return float(s[3:4].view(torch.float32)[0]), int(s[0]), int(s[2])
 
+    def _needed_rows(self, s, samples):
+        """rows the sample buffers must hold.  One rank: this step's count.  Ray-sharded: ONLY the maximum over all ranks that
+        the update published in the stats block (the same number on every rank, csrc/adam.cuh status words), so that every
+        rank grows -- and re-captures, warm-up updates included -- at the same step."""
+        if self.world_size > 1 and self.scaler is not None:
+            return int(s[5])
+        return samples
+
     def previous_stats(self):
         """(loss, samples, rows_used) of the step BEFORE the most recent ``step()`` -- waits for that step only, so the
         device never idles between steps (issue step k + 1, then read step k).  None before the second step.  A step that
@@ -579,10 +629,11 @@ class FusedTrainStep:
         i = (self._steps_launched - 2) & 1
         self._ring_events[i].synchronize()
         out = self._parse_stats(self.stats_ring[i])
-        if out[1] > self.m_cap:
+        need = self._needed_rows(self.stats_ring[i], out[1])
+        if need > self.m_cap:
             torch.cuda.current_stream(self.dev).synchronize()
             self.overflows += 1
-            self._alloc_samples(self._round_cap(out[1]))
+            self._alloc_samples(self._round_cap(need))
         return out
 
     # ------------------------------------------------------------------------------------------ checkpoints
@@ -633,7 +684,8 @@ class FusedTrainStep:
         buffers (and drops the captured graph) when that step overflowed ``m_cap``."""
         torch.cuda.current_stream(self.dev).synchronize()
         loss, samples, used = self._parse_stats(self.stats_host)
-        if samples > self.m_cap:
+        need = self._needed_rows(self.stats_host, samples)
+        if need > self.m_cap:
             self.overflows += 1
-            self._alloc_samples(self._round_cap(samples))
+            self._alloc_samples(self._round_cap(need))
         return loss, samples, used

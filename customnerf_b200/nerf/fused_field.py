@@ -78,7 +78,7 @@ class _FusedField(Function):
         L.check(L.lib().nb200_field_backward(L.ptr(d_sigma), L.ptr(d_rgba), L.ptr(sigma_arg), L.ptr(rgba), L.ptr(x_en),
                                              L.ptr(dirs), L.ptr(act), L.ptr(bwd_img), L.ptr(d_x_en), L.ptr(g_trunk),
                                              L.ptr(g_density), L.ptr(g_rgb), L.u32(M), L.ptr(None), L.ptr(_wg_scratch(dev)),
-                                             L.stream()),
+                                             L.ptr(None), L.stream()),
                 "field_backward")
         return d_x_en, None, None, g_trunk, g_density, g_rgb, None, None
 
@@ -147,12 +147,12 @@ class _FusedEncodeField(Function):
         L.check(L.lib().nb200_field_backward(L.ptr(d_sigma), L.ptr(d_rgba), L.ptr(sigma_arg), L.ptr(rgba), L.ptr(x_en),
                                              L.ptr(dirs), L.ptr(act), L.ptr(bwd_img), L.ptr(d_x_en), L.ptr(g_trunk),
                                              L.ptr(g_density), L.ptr(g_rgb), L.u32(M), L.ptr(None), L.ptr(_wg_scratch(dev)),
-                                             L.stream()),
+                                             L.ptr(None), L.stream()),
                 "field_backward")
         L.check(L.lib().nb200_fs_encode_backward(L.ptr(d_x_en), L.ptr(xyz), L.f32(ctx.bound), L.ptr(offsets), L.ptr(g_table),
                                                  L.u32(M), L.u32(enc.num_levels), L.f32(float(np.log2(enc.per_level_scale))),
                                                  L.u32(int(enc.base_resolution)), L.u32(enc.gridtype_id),
-                                                 L.i32(int(enc.align_corners)), L.u32(enc.interp_id), L.ptr(None), L.stream()),
+                                                 L.i32(int(enc.align_corners)), L.u32(enc.interp_id), L.ptr(None), L.ptr(None), L.stream()),
                 "fs_encode_backward")
         return None, None, g_table, g_trunk, g_density, g_rgb, None, None, None, None
 

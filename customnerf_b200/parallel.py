@@ -103,7 +103,8 @@ class PeerPlan(_C.Structure):
     _fields_ = [("world", _C.c_uint32), ("rank", _C.c_uint32), ("grid", _C.c_uint32), ("pad", _C.c_uint32),
                 ("n", _C.c_uint64), ("split", _C.c_uint64), ("params", _C.c_void_p * 8), ("grads", _C.c_void_p * 8),
                 ("signals", _C.c_void_p * 8), ("exp_avg", _C.c_void_p), ("exp_avg_sq", _C.c_void_p), ("hyper", _C.c_void_p),
-                ("epoch", _C.c_void_p), ("status", _C.c_void_p), ("mc_params", _C.c_void_p), ("mc_grads", _C.c_void_p)]
+                ("epoch", _C.c_void_p), ("status", _C.c_void_p), ("mc_params", _C.c_void_p), ("mc_grads", _C.c_void_p),
+                ("scalers", _C.c_void_p * 8)]
 
 
 class PeerMemory:
@@ -140,7 +141,9 @@ class PeerMemory:
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.grid = int(lib.nb200_peer_grid(C.c_uint64(self.n), C.c_uint32(self.world), C.c_uint32(sms)))
         self.sig_off = 2 * self.n * 4
-        self.bytes = self.sig_off + int(lib.nb200_peer_signal_bytes(C.c_uint32(self.grid)))
+        # [params | grads | flag words | loss-scaler words (8 x 4 B, 64-byte slot)]: the peers read each other's found-inf flags
+        self.scaler_off = self.sig_off + (int(lib.nb200_peer_signal_bytes(C.c_uint32(self.grid))) + 63) // 64 * 64
+        self.bytes = self.scaler_off + 64
         self.base = C.c_void_p()
         self.imported = []
         self.mc_base = 0
@@ -172,6 +175,7 @@ class PeerMemory:
         self.bases = bases
         self.params = torch.as_tensor(_DevArray(self.base.value, self.n, "<f4", self), device=self.device)
         self.grads = torch.as_tensor(_DevArray(self.base.value + 4 * self.n, self.n, "<f4", self), device=self.device)
+        self.scaler = torch.as_tensor(_DevArray(self.base.value + self.scaler_off, 8, "<i4", self), device=self.device)
         self.epoch = torch.zeros(self.grid + 1, dtype=torch.int32, device=self.device)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         if self.world > 1:
@@ -192,6 +196,7 @@ class PeerMemory:
             self.bases = [int(p) for p in self._symm.buffer_ptrs]
             assert self.bases[self.rank] == self._symm_buf.data_ptr()
             self.params, self.grads = self._symm_buf[:self.n], self._symm_buf[self.n:2 * self.n]
+            self.scaler = self._symm_buf[self.scaler_off // 4:self.scaler_off // 4 + 8].view(torch.int32)
             self.epoch = torch.zeros(self.grid + 1, dtype=torch.int32, device=self.device)
             self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
             got = [None] * self.world
@@ -201,7 +206,9 @@ class PeerMemory:
             torch.cuda.synchronize(self.device)
             dist.barrier(group=group)
 
-    def plan(self, n_table_params, exp_avg, exp_avg_sq, hyper, status=None):
+    def plan(self, n_table_params, exp_avg, exp_avg_sq, hyper, status=None, use_scaler=False):
+        """use_scaler: the update is skipped on every rank when any rank's found-inf flag (``self.scaler``: the device-side
+        dynamic loss scaler, csrc/adam.cuh) is up"""
         C = self.C
         p = PeerPlan()
         p.world, p.rank, p.grid, p.n, p.split = self.world, self.rank, self.grid, self.n, int(n_table_params)
@@ -212,6 +219,9 @@ class PeerMemory:
         p.status = (status if status is not None else self.status).data_ptr()
         if self.mc_base:
             p.mc_params, p.mc_grads = self.mc_base, self.mc_base + 4 * self.n
+        if use_scaler:
+            for r, b in enumerate(self.bases):
+                p.scalers[r] = b + self.scaler_off
         assert C.sizeof(p) == int(self.lib.nb200_peer_plan_bytes()), "nb200_peer_plan layout mismatch"
         return p
 

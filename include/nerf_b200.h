@@ -192,9 +192,10 @@ int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, c
 int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,
                          const void *x_en, const float *dirs, const void *act, const void *bwd_img, void *d_x_en,
                          float *g_trunk, float *g_density, float *g_rgb, uint32_t M, const int32_t *count_dev,
-                         float *wg_scratch, void *stream);
+                         float *wg_scratch, uint32_t *scaler, void *stream);
 /* wg_scratch: nb200_field_wgrad_scratch_bytes() bytes (16-byte aligned) of per-CTA partial weight-gradient sums that a
- * second small kernel adds into g_* (deterministic, no contended atomics); NULL = fp32 atomics straight on g_*. */
+ * second small kernel adds into g_* (deterministic, no contended atomics); NULL = fp32 atomics straight on g_*.
+ * scaler (may be NULL; needs wg_scratch): loss-scaler words whose found-inf flag is raised when a weight gradient is not finite. */
 uint32_t nb200_field_wgrad_scratch_bytes(void);
 /* Grid encoding + field network in ONE kernel (csrc/field_fused.cu): the [M,32] hash-grid features are gathered by producer
  * warps straight into the tensor-core operand tile and never round-trip HBM.  Replaces GridEncoder.forward
@@ -264,15 +265,17 @@ int nb200_fs_encode_forward(const float *xyz, float bound, const float *table, c
 /* scatter of d_x_en f16 [M_cap, 2L] into grad_table f32 [rows, 2] (accumulated; warp-aggregated fp32 atomics). */
 int nb200_fs_encode_backward(const void *d_x_en, const float *xyz, float bound, const int32_t *offsets, float *grad_table,
                              uint32_t M_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
-                             uint32_t interp, const int32_t *count_dev, void *stream);
-/* composite_rays_train forward / backward reading the field kernel's rgba f16 [M,4] rows directly (the reference
+                             uint32_t interp, const int32_t *count_dev, uint32_t *scaler, void *stream);
+/* (scaler, may be NULL: loss-scaler words whose found-inf flag is raised when a feature gradient is not finite)
+ * composite_rays_train forward / backward reading the field kernel's rgba f16 [M,4] rows directly (the reference
  * slices [..., :3] and casts to float, renderer.py:510,635) and writing grad_rgba as float4 rows [g_r, g_g, g_b, 0]. */
 int nb200_fs_composite_forward(const float *sigmas, const void *rgba, const float *deltas, const int32_t *rays,
                                uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image,
                                const float *target, float inv_n, float loss_scale, float *loss, float *g_image,
                                const float *target_mask, float mask_weight, float *render_mask, float *g_render_mask,
-                               void *stream);
-/* target != NULL: nb200_mse_loss_grad fused in (per ray).  target_mask != NULL (the reference's train_conf term,
+                               const float *loss_scale_dev, void *stream);
+/* loss_scale_dev (may be NULL): the loss scale is read from this device word instead of `loss_scale` (dynamic scaler).
+ * target != NULL: nb200_mse_loss_grad fused in (per ray).  target_mask != NULL (the reference's train_conf term,
  * utils_init_nerf.py:231-233): render_mask[n] = sum_i w_i * mask_i (mask = 4th channel of the rgba rows; what
  * weights_sum_i renders on the dense path, renderer.py:460-463), loss += mask_weight * mean((render_mask - target_mask)^2),
  * g_render_mask = its gradient times loss_scale. */
@@ -299,6 +302,28 @@ int nb200_fused_adam(float *param, float *grad, float *exp_avg, float *exp_avg_s
  * depends on host memory): sched f32[8] = {lr0 group 0, lr0 group 1, beta1, beta2, eps, grad_scale, decay_base,
  * decay_iters}; lr = lr0 * decay_base^min((t-1)/decay_iters, 1) (LambdaLR of main.py:189; decay_iters <= 0: constant). */
 int nb200_adam_hyper(int32_t *step, const float *sched, float *hyper, void *stream);
+
+/* Dynamic loss scaling with skipped steps, on the device -- torch.cuda.amp.GradScaler as the reference trains with it
+ * (nerf/utils_init_nerf.py:100,612-629: scale(loss).backward(); scaler.step(optimizer) skips the step when a gradient is
+ * inf / NaN; scaler.update() halves the scale then, and doubles it after 2000 clean steps).  scaler = 8 device words:
+ *   [0] scale f32   [1] growth tracker i32   [2] iteration u32   [3] skipped steps u32   [4], [5] status words of even / odd
+ *   iterations (bit 31 = found-inf)   [6] growth interval i32   [7] unused.     Initialise to {scale, 0, 0, 0, 0, 0, 2000, 0}.
+ * A step: the loss gradient is multiplied by [0] (nb200_fs_composite_forward: loss_scale_dev = scaler); the backward kernels
+ * raise bit 31 of word [4 + (iteration & 1)] when a feature gradient (nb200_fs_encode_backward) or an MLP weight gradient
+ * (nb200_field_backward) is not finite; nb200_adam_hyper_scaled evaluates the hyper-parameters for step *step + 1 WITHOUT
+ * advancing it, with grad_scale = 1 / scale and (local_skip != 0) skip = the local flag; the Adam sweep / the peer-memory
+ * update leave p, m, v untouched when skipping (the gradient is still reset); nb200_scaler_commit then advances *step only
+ * if the step was taken, updates scale / tracker, clears the flag of the next iteration and increments the iteration.
+ * peer_scalers (world > 1, peer-memory update): the scaler words of every rank -- the decision is the OR of all flags. */
+int nb200_adam_hyper_scaled(const int32_t *step, const float *sched, float *hyper, uint32_t *scaler, int local_skip,
+                            const int32_t *samples, void *stream);
+int nb200_scaler_commit(int32_t *step, uint32_t *scaler, uint32_t *const *peer_scalers, uint32_t world, int32_t *max_samples,
+                        void *stream);
+/* The status words [4], [5] carry two things: bit 31 = found-inf, bits 0..30 = the step's sample count (samples, device i32, may
+ * be NULL; nb200_adam_hyper_scaled ORs it in).  nb200_scaler_commit writes the maximum count over all ranks to *max_samples (may
+ * be NULL) -- the same number on every rank, so that ray-sharded ranks grow their sample buffers at the same step.  In
+ * nb200_train_update[_peer] samples = plan->counter + 6 (where the forward/backward parks the step's count) and
+ * max_samples = plan->counter + 5: plan->counter must then be an 8-word block {count, rays, -, -, -, max over ranks, count copy, -}. */
 
 #define NB200_PLAN_FUSED_FORWARD 1u   /* encode + field forward as one kernel (nb200_field_fused_forward): the stage timer
                                          then reports the pair under "field_forward" and ~0 under "grid_encode_forward" */
@@ -331,6 +356,8 @@ typedef struct nb200_train_plan {
     void *x_en, *rgba, *act, *d_x_en;
     float *wg_scratch;                                           /* nb200_field_wgrad_scratch_bytes() or NULL */
     void *timer;                                                 /* nb200_stage_timer or NULL */
+    uint32_t *scaler;                                            /* device-side dynamic loss scaler (8 words, see
+                                                                    nb200_scaler_commit) or NULL: constant loss_scale */
 } nb200_train_plan;
 
 /* ---- LGIE editing step (BASELINE.json configs[3]; reference: the fg / bg / all renders of NeRFRenderer.run,
@@ -427,6 +454,8 @@ typedef struct nb200_peer_plan {
     float *mc_params, *mc_grads;          /* NVSwitch multicast mappings of the same two vectors (both or neither; NULL:
                                              plain peer loads / stores): multimem.ld_reduce sums the gradient inside the
                                              switch, multimem.st delivers the parameters to every replica */
+    uint32_t *scalers[NB200_PEER_MAX];    /* every rank's loss-scaler words (nb200_scaler_commit), or all NULL: when given, the
+                                             update is skipped on EVERY rank if any rank's found-inf flag of this iteration is up */
 } nb200_peer_plan;
 uint32_t nb200_peer_plan_bytes(void);
 uint32_t nb200_peer_handle_bytes(void);

@@ -318,3 +318,55 @@ def test_mask_loss_term_matches_the_autograd_path():
     # the mask head really receives gradient: rows 3 of the colour head's last layer
     gr = fs.grads_flat[fs.layout[3][1]:].cpu().numpy()[64 * 96:].reshape(16, 64)
     assert np.abs(gr[3]).sum() > 0
+
+
+def test_dynamic_loss_scale_skips_the_step_on_a_non_finite_gradient():
+    """GradScaler semantics on the device (the reference trains under torch.cuda.amp.GradScaler, utils_init_nerf.py:100,612-629):
+    a non-finite gradient -> the optimiser step is skipped (parameters, moments and the step count untouched, the gradient
+    reset), the loss scale is halved; clean steps count towards doubling it.  No host synchronisation is involved: the same
+    sequence runs inside the captured graph."""
+    from customnerf_b200 import fused_trainer
+    _, mb = _models()
+    o, d, tgt = _batch()
+    for use_graph in (False, True):
+        fs = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False, use_graph=use_graph, lr=1e-3)
+        fs.scaler[6] = 3                                    # growth interval: 3 clean steps
+        for _ in range(2):
+            fs.step(o, d, tgt)
+        loss, _, _ = fs.last_stats()
+        scale, skipped, steps = fs.scaler_state()
+        assert (scale, skipped, steps) == (128.0, 0, 2) and np.isfinite(loss)
+        p0, m0, v0 = fs.params_flat.clone(), fs.exp_avg.clone(), fs.exp_avg_sq.clone()
+        bad = tgt.clone()
+        bad[7, 1] = float("inf")                            # one poisoned pixel: the loss and every gradient become inf / NaN
+        fs.step(o, d, bad)
+        fs.last_stats()
+        scale, skipped, steps = fs.scaler_state()
+        assert (scale, skipped, steps) == (64.0, 1, 2), (scale, skipped, steps)
+        assert torch.equal(fs.params_flat, p0) and torch.equal(fs.exp_avg, m0) and torch.equal(fs.exp_avg_sq, v0)
+        assert float(fs.grads_flat.abs().max()) == 0.0 and torch.isfinite(fs.params_flat).all()
+        for _ in range(3):                                  # three clean steps: the update resumes, then the scale doubles
+            fs.step(o, d, tgt)
+        loss2, _, _ = fs.last_stats()
+        scale, skipped, steps = fs.scaler_state()
+        assert (scale, skipped, steps) == (128.0, 1, 5), (scale, skipped, steps)
+        assert not torch.equal(fs.params_flat, p0) and torch.isfinite(fs.params_flat).all() and np.isfinite(loss2)
+        assert loss2 < loss
+
+
+def test_dynamic_loss_scale_changes_nothing_while_gradients_are_finite():
+    """with finite gradients the scaled step is the constant-scale step: same parameters after 4 steps (the unscale factor
+    1 / 128 is the same number either way)"""
+    from customnerf_b200 import fused_trainer
+    outs = []
+    for dyn in (True, False):
+        _, mb = _models()
+        o, d, tgt = _batch()
+        fs = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False, use_graph=False, lr=1e-3, dynamic_loss_scale=dyn)
+        for _ in range(4):
+            fs.step(o, d, tgt)
+        fs.last_stats()
+        outs.append((fs.params_flat.clone(), int(fs.step_count)))
+    assert outs[0][1] == outs[1][1] == 4
+    # fp32 atomics in the scatter: order differs run to run, so compare to the run-to-run noise level, not bit for bit
+    assert float((outs[0][0] - outs[1][0]).abs().max()) < 2e-3
