@@ -41,3 +41,36 @@ __device__ __forceinline__ void adam1(float &p, float &g, float &m, float &v, co
     const float denom = __fmaf_rn(sqrtf(v), h.inv_bc2_sqrt, h.eps);
     p = __fmaf_rn(-h.step_size, __fdividef(m, denom), p);   // 2-ulp division: the update is <= lr, its error ~1e-10
 }
+
+// GradScaler.update() (torch/amp/grad_scaler.py: backoff 0.5, growth 2.0 every `interval` clean steps) + the optimiser's own
+// step count; ONE thread.  peers[q] = the scaler words of rank q (world > 1, peer-memory update): the decision is the OR of
+// every rank's found-inf bit, *max_samples the maximum of their sample counts (the same numbers on every rank).
+struct ScalerCommit {
+    int32_t *step; uint32_t *scaler; int32_t *max_samples; uint32_t world, pad;
+    uint32_t *peers[NB200_PEER_MAX];
+};
+__device__ __forceinline__ void scaler_commit(const ScalerCommit &c) {
+    uint32_t *scaler = c.scaler;
+    const uint32_t it = scaler[kScalerIter], slot = kScalerFlag0 + (it & 1u);
+    uint32_t word = scaler[slot], found = word & kScalerInfBit, smax = word & ~kScalerInfBit;
+    for (uint32_t q = 0; q < c.world; q++)
+        if (c.peers[q]) {
+            word = *(volatile uint32_t *)(c.peers[q] + slot);
+            found |= word & kScalerInfBit;
+            smax = max(smax, word & ~kScalerInfBit);
+        }
+    if (c.max_samples) *c.max_samples = (int32_t)smax;      // the same number on every rank: buffer growth is a joint decision
+    float scale = __uint_as_float(scaler[kScalerScale]);
+    int32_t tracker = (int32_t)scaler[kScalerTracker];
+    if (found) {
+        scale *= 0.5f; tracker = 0; scaler[kScalerSkipped] += 1u;
+    } else {
+        *c.step += 1;
+        const int32_t interval = (int32_t)scaler[kScalerInterval];
+        if (++tracker >= interval && interval > 0) { scale *= 2.0f; tracker = 0; }
+    }
+    scaler[kScalerScale] = __float_as_uint(scale);
+    scaler[kScalerTracker] = (uint32_t)tracker;
+    scaler[kScalerFlag0 + ((it + 1u) & 1u)] = 0u;           // the word of iteration it + 1 (nobody reads it any more)
+    scaler[kScalerIter] = it + 1u;
+}

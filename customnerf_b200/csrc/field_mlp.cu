@@ -24,10 +24,16 @@
 
 namespace {
 
+constexpr uint32_t kPackBlocks = 16;
 // every byte of both images that a descriptor can reach is written here (no separate zero fill)
 __global__ void k_pack_field_weights(const float *__restrict__ trunk, const float *__restrict__ density,
-                                      const float *__restrict__ rgb, uint8_t *__restrict__ fwd, uint8_t *__restrict__ bwd) {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+                                      const float *__restrict__ rgb, uint8_t *__restrict__ fwd, uint8_t *__restrict__ bwd,
+                                      ScalerCommit sc) {
+    if (blockIdx.x == kPackBlocks) {        // the extra block: GradScaler.update() + the optimiser's step count (adam.cuh)
+        if (threadIdx.x == 0) scaler_commit(sc);
+        return;
+    }
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = kPackBlocks * blockDim.x;
     for (uint32_t i = tid; i < 64 * 64; i += nth) {
         const uint32_t n = i >> 6, k = i & 63;
         if (k < 32) {
@@ -305,6 +311,7 @@ struct FieldBwdArgs {
     float *slabs;                         // [gridDim.x][kWgradFloats] per-CTA partial sums, or null (atomics)
     uint32_t M;               // rows allocated (the stride of `act` planes)
     const int32_t *count_dev; // when non-null only rows < min(M, *count_dev) are processed
+    uint32_t *scaler;         // loss-scaler words (adam.cuh) or null: a feature gradient that leaves the fp16 range raises found-inf
 };
 
 // MN-major descriptor of K-step ks (16 rows = 2 swizzle atoms) starting at column `col0` (multiple of 8 halves)
@@ -509,6 +516,7 @@ k_field_backward(const FieldBwdArgs p) {
     }
     const bool issuer_warp = warp == 0;
     uint32_t xv_sel = 0;                   // which XV buffer the current tile uses
+    bool bad_dx = false;                   // a feature gradient of this thread's rows left the fp16 range (GradScaler's found_inf)
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t g = tile * 128 + row;
@@ -594,6 +602,8 @@ k_field_backward(const FieldBwdArgs p) {
             umma::tmem_ld16(trow + C_DG + 16 * half, a);
             umma::tmem_ld_wait();
             if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) bad_dx |= !(fabsf(__uint_as_float(a[j])) <= 65504.0f);   // inf / NaN / fp16 overflow
                 uint4 *dst = reinterpret_cast<uint4 *>(p.d_x_en + (size_t)g * 32) + half * 2;
 #pragma unroll
                 for (uint32_t c = 0; c < 2; c++)
@@ -611,6 +621,7 @@ k_field_backward(const FieldBwdArgs p) {
         first_tile = false;
         xv_sel ^= 1u;
     }
+    if (p.scaler && __any_sync(0xffffffffu, bad_dx) && (tid & 31u) == 0) scaler_raise(p.scaler);
     cp_async_wait<0>();
     // drain the last weight-gradient MMAs before reading their accumulators
     if (issuer_warp && umma::elect_one()) umma::commit(&bar);
@@ -736,7 +747,23 @@ int nb200_field_pack_weights(const float *trunk, const float *density, const flo
                              void *stream) {
     if (!trunk || !density || !rgb || !fwd_img || !bwd_img) return NB200_E_BAD_ARG;
     cudaStream_t st = nb_stream(stream);
-    k_pack_field_weights<<<16, 256, 0, st>>>(trunk, density, rgb, (uint8_t *)fwd_img, (uint8_t *)bwd_img);
+    ScalerCommit none;
+    memset(&none, 0, sizeof(none));
+    k_pack_field_weights<<<kPackBlocks, 256, 0, st>>>(trunk, density, rgb, (uint8_t *)fwd_img, (uint8_t *)bwd_img, none);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+// the same launch with one extra block that runs nb200_scaler_commit's work (saves a launch per train step)
+int nb200_field_pack_weights_commit(const float *trunk, const float *density, const float *rgb, void *fwd_img, void *bwd_img,
+                                    int32_t *step, uint32_t *scaler, uint32_t *const *peer_scalers, uint32_t world,
+                                    int32_t *max_samples, void *stream) {
+    if (!trunk || !density || !rgb || !fwd_img || !bwd_img || !step || !scaler || world > NB200_PEER_MAX) return NB200_E_BAD_ARG;
+    ScalerCommit sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.step = step; sc.scaler = scaler; sc.max_samples = max_samples; sc.world = peer_scalers ? world : 0;
+    for (uint32_t q = 0; q < sc.world; q++) sc.peers[q] = peer_scalers[q];
+    k_pack_field_weights<<<kPackBlocks + 1, 256, 0, nb_stream(stream)>>>(trunk, density, rgb, (uint8_t *)fwd_img, (uint8_t *)bwd_img, sc);
     NB_LAUNCH_CHECK();
     return 0;
 }
@@ -809,6 +836,7 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
     a.x_en = (const __half *)x_en; a.dirs = dirs; a.act = (const __half *)act; a.wimg = (const uint8_t *)bwd_img;
     a.d_x_en = (__half *)d_x_en; a.g_trunk = g_trunk; a.g_density = g_density; a.g_rgb = g_rgb; a.M = M;
     a.count_dev = count_dev;
+    a.scaler = scaler;
     a.slabs = wg_scratch;
     const uint32_t ntiles = (M + 127) / 128;
     const uint32_t grid = ntiles < (uint32_t)sms ? ntiles : (uint32_t)sms;

@@ -121,7 +121,7 @@ rest:
                                    p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, p->scaler, stream))) return rc;
     tick(ev, k++, st);
     if ((rc = nb200_fs_encode_backward(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
-                                       p->base_res, p->gridtype, 0, 0, p->m_eff, p->scaler, stream))) return rc;
+                                       p->base_res, p->gridtype, 0, 0, p->m_eff, stream))) return rc;
     tick(ev, k++, st);
     // the step's sample count, parked where the (possibly concurrent: pipelined update next to the NEXT step's march, which
     // resets the counter) update reads it for the status word of the loss scaler
@@ -159,7 +159,7 @@ int nb200_train_lgie_backward(const nb200_train_plan *p, const nb200_lgie_plan *
     if ((rc = nb200_field_backward(p->d_sigma, p->d_rgba, p->sigma_arg, p->rgba, p->x_en, p->dirs, p->act, p->w_bwd,
                                    p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, p->scaler, stream))) return rc;
     if ((rc = nb200_fs_encode_backward(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
-                                       p->base_res, p->gridtype, 0, 0, p->m_eff, p->scaler, stream))) return rc;
+                                       p->base_res, p->gridtype, 0, 0, p->m_eff, stream))) return rc;
     if (p->scaler) {
         cudaError_t e = cudaMemcpyAsync(p->counter + 6, p->counter, sizeof(int32_t), cudaMemcpyDeviceToDevice, nb_stream(stream));
         if (e != cudaSuccess) return (int)e;
@@ -183,9 +183,11 @@ int nb200_train_update(const nb200_train_plan *p, void *stream) {
     } else if ((rc = nb200_adam_hyper(p->step, p->sched, p->hyper, stream))) return rc;
     if ((rc = nb200_fused_adam(p->params_flat, p->grads_flat, p->exp_avg, p->exp_avg_sq, p->n_params, p->n_table_params,
                                p->hyper, 1, stream))) return rc;
-    if (p->scaler && (rc = nb200_scaler_commit(p->step, p->scaler, nullptr, 1, p->counter + 5, stream))) return rc;
     tick(ev, 1, st);
-    if ((rc = nb200_field_pack_weights(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, stream))) return rc;
+    if (p->scaler) {        // weight re-pack + GradScaler.update() / step count in one launch
+        if ((rc = nb200_field_pack_weights_commit(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, p->step, p->scaler, nullptr, 1,
+                                                  p->counter + 5, stream))) return rc;
+    } else if ((rc = nb200_field_pack_weights(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, stream))) return rc;
     tick(ev, 2, st);
     if (tm) tm->up_done = true;
     return 0;
@@ -206,9 +208,11 @@ int nb200_train_update_peer(const nb200_train_plan *p, const nb200_peer_plan *pe
         if ((rc = nb200_adam_hyper_scaled(p->step, p->sched, p->hyper, p->scaler, 0, p->counter + 6, stream))) return rc;
     } else if ((rc = nb200_adam_hyper(p->step, p->sched, p->hyper, stream))) return rc;
     if ((rc = nb200_peer_reduce_adam_bcast(peer, stream))) return rc;
-    if (scaled && (rc = nb200_scaler_commit(p->step, p->scaler, peer->scalers, peer->world, p->counter + 5, stream))) return rc;
     tick(ev, 1, st);
-    if ((rc = nb200_field_pack_weights(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, stream))) return rc;
+    if (scaled) {
+        if ((rc = nb200_field_pack_weights_commit(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, p->step, p->scaler,
+                                                  peer->scalers, peer->world, p->counter + 5, stream))) return rc;
+    } else if ((rc = nb200_field_pack_weights(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, stream))) return rc;
     tick(ev, 2, st);
     if (tm) tm->up_done = true;
     return 0;

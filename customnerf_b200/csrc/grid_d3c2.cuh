@@ -22,7 +22,6 @@ constexpr uint32_t P1 = 2654435761u, P2 = 805459861u;
 struct InXform {
     float add, mul;                 // mul == 0: identity (inputs are already in [0, 1])
     const int32_t *count_dev;       // when non-null only rows < min(B, *count_dev) are processed
-    uint32_t *scaler = nullptr;     // backward only: loss-scaler words (adam.cuh); a non-finite feature gradient raises its flag
     __device__ __forceinline__ float operator()(float x) const { return mul != 0.0f ? __fmul_rn(__fadd_rn(x, add), mul) : x; }
 };
 

@@ -20,7 +20,6 @@
 // device with the reference's expression exp2f(level * S) * H - 1.0f so fine-level positions are identical.
 #include "common.cuh"
 #include "grid_d3c2.cuh"
-#include "adam.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -354,12 +353,10 @@ k_grid_bwd_d3c2(const T *__restrict__ grad, const float *__restrict__ inputs, co
     const T *g = grad + (size_t)(inb ? b : 0) * L * 2;
     const float half_off = align_corners ? 0.0f : 0.5f;
 
-    bool bad = false;                  // a non-finite feature gradient (fp16 overflow upstream): GradScaler's found_inf
     for (uint32_t l = 0; l < max_level; l++) {
         const LevelInfo li = info[l];
         float g0v = 0.0f, g1v = 0.0f;
         if (!oob) { g0v = nb_to_float<T>(g[l * 2]); g1v = nb_to_float<T>(g[l * 2 + 1]); }
-        bad |= !(isfinite(g0v) && isfinite(g1v));
         float p0 = x0 * li.scale + half_off, p1 = x1 * li.scale + half_off, p2 = x2 * li.scale + half_off;
         const uint32_t c0 = (uint32_t)floorf(p0), c1 = (uint32_t)floorf(p1), c2 = (uint32_t)floorf(p2);
         p0 -= (float)c0; p1 -= (float)c1; p2 -= (float)c2;
@@ -407,7 +404,6 @@ k_grid_bwd_d3c2(const T *__restrict__ grad, const float *__restrict__ inputs, co
             }
         }
     }
-    if (xf.scaler && __any_sync(0xffffffffu, bad) && lane == 0) scaler_raise(xf.scaler);
 }
 
 __global__ void k_level_scales(float *scales, uint32_t L, float S, uint32_t H) {
@@ -598,10 +594,10 @@ int nb200_fs_encode_forward(const float *xyz, float bound, const float *table, c
 
 int nb200_fs_encode_backward(const void *d_x_en, const float *xyz, float bound, const int32_t *offsets, float *grad_table,
                              uint32_t M_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
-                             uint32_t interp, const int32_t *count_dev, uint32_t *scaler, void *stream) {
+                             uint32_t interp, const int32_t *count_dev, void *stream) {
     if (M_cap == 0 || L == 0) return 0;
     if (!d_x_en || !xyz || !offsets || !grad_table || L > kMaxFastLevels || !(bound > 0.0f)) return NB200_E_BAD_ARG;
-    const InXform xf{bound, 1.0f / (2.0f * bound), count_dev, scaler};
+    const InXform xf{bound, 1.0f / (2.0f * bound), count_dev};
     k_grid_bwd_d3c2<__half, true><<<nb_div_up(M_cap, 256), 256, 0, nb_stream(stream)>>>(
         (const __half *)d_x_en, xyz, offsets, grad_table, M_cap, L, L, S, H, gridtype, align_corners != 0, interp, xf,
         ge_agg_max_heads());

@@ -10,6 +10,7 @@
 // decay): m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2; p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps).
 #include "adam.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -96,34 +97,8 @@ __global__ void k_adam_hyper_scaled(const int32_t *__restrict__ step, const floa
     }
 }
 
-// GradScaler.update() (torch/amp/grad_scaler.py: backoff 0.5, growth 2.0 every `interval` clean steps) + the optimiser's own
-// step count.  peers[q] = the scaler words of rank q (this rank's included); world = 1: only the local flag.
-struct ScalerPeers { uint32_t *s[NB200_PEER_MAX]; };
-__global__ void k_scaler_commit(int32_t *__restrict__ step, uint32_t *__restrict__ scaler, ScalerPeers peers, uint32_t world,
-                                int32_t *__restrict__ max_samples) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const uint32_t it = scaler[kScalerIter], slot = kScalerFlag0 + (it & 1u);
-    uint32_t word = scaler[slot], found = word & kScalerInfBit, smax = word & ~kScalerInfBit;
-    for (uint32_t q = 0; q < world; q++)
-        if (peers.s[q]) {
-            word = *(volatile uint32_t *)(peers.s[q] + slot);
-            found |= word & kScalerInfBit;
-            smax = max(smax, word & ~kScalerInfBit);
-        }
-    if (max_samples) *max_samples = (int32_t)smax;          // the same number on every rank: buffer growth is a joint decision
-    float scale = __uint_as_float(scaler[kScalerScale]);
-    int32_t tracker = (int32_t)scaler[kScalerTracker];
-    if (found) {
-        scale *= 0.5f; tracker = 0; scaler[kScalerSkipped] += 1u;
-    } else {
-        *step += 1;
-        const int32_t interval = (int32_t)scaler[kScalerInterval];
-        if (++tracker >= interval && interval > 0) { scale *= 2.0f; tracker = 0; }
-    }
-    scaler[kScalerScale] = __float_as_uint(scale);
-    scaler[kScalerTracker] = (uint32_t)tracker;
-    scaler[kScalerFlag0 + ((it + 1u) & 1u)] = 0u;           // the flag of iteration it + 1 (nobody reads it any more)
-    scaler[kScalerIter] = it + 1u;
+__global__ void k_scaler_commit(ScalerCommit c) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) scaler_commit(c);
 }
 
 // loss = sum (image - target)^2 * inv_n ; g_image = 2 (image - target) * inv_n * loss_scale     (one thread per ray)
@@ -203,9 +178,11 @@ int nb200_adam_hyper_scaled(const int32_t *step, const float *sched, float *hype
 int nb200_scaler_commit(int32_t *step, uint32_t *scaler, uint32_t *const *peer_scalers, uint32_t world, int32_t *max_samples,
                         void *stream) {
     if (!step || !scaler || world > NB200_PEER_MAX) return NB200_E_BAD_ARG;
-    ScalerPeers peers;
-    for (uint32_t q = 0; q < NB200_PEER_MAX; q++) peers.s[q] = (peer_scalers && q < world) ? peer_scalers[q] : nullptr;
-    k_scaler_commit<<<1, 32, 0, nb_stream(stream)>>>(step, scaler, peers, peer_scalers ? world : 0, max_samples);
+    ScalerCommit c;
+    memset(&c, 0, sizeof(c));
+    c.step = step; c.scaler = scaler; c.max_samples = max_samples; c.world = peer_scalers ? world : 0;
+    for (uint32_t q = 0; q < c.world; q++) c.peers[q] = peer_scalers[q];
+    k_scaler_commit<<<1, 32, 0, nb_stream(stream)>>>(c);
     NB_LAUNCH_CHECK();
     return 0;
 }

@@ -411,7 +411,12 @@ class FusedTrainStep:
             # [update of the previous step] on the side stream  ||  [march of this step] here, then join
             main = torch.cuda.current_stream(self.dev)
             if self._side is None:
-                self._side = torch.cuda.Stream(device=self.dev)
+                # high priority: when both branches are runnable the update's (thin) grid is placed first and the march fills
+                # the rest of every SM -- launched the other way round, the march's single resident wave leaves the update no
+                # room until it drains and the two run back to back
+                import os
+                prio = -1 if os.environ.get("NB200_SIDE_PRIORITY", "1") == "1" else 0
+                self._side = torch.cuda.Stream(device=self.dev, priority=prio)
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 self._update(L.stream())

@@ -152,7 +152,7 @@ class _FusedEncodeField(Function):
         L.check(L.lib().nb200_fs_encode_backward(L.ptr(d_x_en), L.ptr(xyz), L.f32(ctx.bound), L.ptr(offsets), L.ptr(g_table),
                                                  L.u32(M), L.u32(enc.num_levels), L.f32(float(np.log2(enc.per_level_scale))),
                                                  L.u32(int(enc.base_resolution)), L.u32(enc.gridtype_id),
-                                                 L.i32(int(enc.align_corners)), L.u32(enc.interp_id), L.ptr(None), L.ptr(None), L.stream()),
+                                                 L.i32(int(enc.align_corners)), L.u32(enc.interp_id), L.ptr(None), L.stream()),
                 "fs_encode_backward")
         return None, None, g_table, g_trunk, g_density, g_rgb, None, None, None, None
 

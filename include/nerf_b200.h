@@ -180,6 +180,10 @@ uint32_t nb200_field_weight_image_bytes(void);
  * nb200_field_weight_image_bytes() long and 16-byte aligned.  Run once per optimiser step. */
 int nb200_field_pack_weights(const float *trunk, const float *density, const float *rgb, void *fwd_img, void *bwd_img,
                              void *stream);
+/* the same launch with one extra block doing nb200_scaler_commit's work (see there): one launch less per train step */
+int nb200_field_pack_weights_commit(const float *trunk, const float *density, const float *rgb, void *fwd_img, void *bwd_img,
+                                    int32_t *step, uint32_t *scaler, uint32_t *const *peer_scalers, uint32_t world,
+                                    int32_t *max_samples, void *stream);
 /* x_en f16 [M,32] (grid encoding), xyz f32 [M,3], dirs f32 [M,3] -> sigma f32 [M], rgba f16 [M,4].
  * Optional (training): sigma_arg f32 [M] (argument of trunc_exp) and act f16 [5,M,64] (h1, h2, fea, hd, hr).
  * count_dev (device i32, may be NULL): when given only rows < min(M, *count_dev) are evaluated. */
@@ -195,7 +199,8 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
                          float *wg_scratch, uint32_t *scaler, void *stream);
 /* wg_scratch: nb200_field_wgrad_scratch_bytes() bytes (16-byte aligned) of per-CTA partial weight-gradient sums that a
  * second small kernel adds into g_* (deterministic, no contended atomics); NULL = fp32 atomics straight on g_*.
- * scaler (may be NULL; needs wg_scratch): loss-scaler words whose found-inf flag is raised when a weight gradient is not finite. */
+ * scaler (may be NULL; needs wg_scratch): loss-scaler words whose found-inf bit is raised when a weight gradient is not finite
+ * or a feature gradient (d_x_en) leaves the fp16 range. */
 uint32_t nb200_field_wgrad_scratch_bytes(void);
 /* Grid encoding + field network in ONE kernel (csrc/field_fused.cu): the [M,32] hash-grid features are gathered by producer
  * warps straight into the tensor-core operand tile and never round-trip HBM.  Replaces GridEncoder.forward
@@ -265,9 +270,8 @@ int nb200_fs_encode_forward(const float *xyz, float bound, const float *table, c
 /* scatter of d_x_en f16 [M_cap, 2L] into grad_table f32 [rows, 2] (accumulated; warp-aggregated fp32 atomics). */
 int nb200_fs_encode_backward(const void *d_x_en, const float *xyz, float bound, const int32_t *offsets, float *grad_table,
                              uint32_t M_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
-                             uint32_t interp, const int32_t *count_dev, uint32_t *scaler, void *stream);
-/* (scaler, may be NULL: loss-scaler words whose found-inf flag is raised when a feature gradient is not finite)
- * composite_rays_train forward / backward reading the field kernel's rgba f16 [M,4] rows directly (the reference
+                             uint32_t interp, const int32_t *count_dev, void *stream);
+/* composite_rays_train forward / backward reading the field kernel's rgba f16 [M,4] rows directly (the reference
  * slices [..., :3] and casts to float, renderer.py:510,635) and writing grad_rgba as float4 rows [g_r, g_g, g_b, 0]. */
 int nb200_fs_composite_forward(const float *sigmas, const void *rgba, const float *deltas, const int32_t *rays,
                                uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image,
@@ -309,8 +313,8 @@ int nb200_adam_hyper(int32_t *step, const float *sched, float *hyper, void *stre
  *   [0] scale f32   [1] growth tracker i32   [2] iteration u32   [3] skipped steps u32   [4], [5] status words of even / odd
  *   iterations (bit 31 = found-inf)   [6] growth interval i32   [7] unused.     Initialise to {scale, 0, 0, 0, 0, 0, 2000, 0}.
  * A step: the loss gradient is multiplied by [0] (nb200_fs_composite_forward: loss_scale_dev = scaler); the backward kernels
- * raise bit 31 of word [4 + (iteration & 1)] when a feature gradient (nb200_fs_encode_backward) or an MLP weight gradient
- * (nb200_field_backward) is not finite; nb200_adam_hyper_scaled evaluates the hyper-parameters for step *step + 1 WITHOUT
+ * raise bit 31 of word [4 + (iteration & 1)] when a feature gradient or an MLP weight gradient is not finite
+ * (nb200_field_backward: every gradient of the step flows through that kernel); nb200_adam_hyper_scaled evaluates the hyper-parameters for step *step + 1 WITHOUT
  * advancing it, with grad_scale = 1 / scale and (local_skip != 0) skip = the local flag; the Adam sweep / the peer-memory
  * update leave p, m, v untouched when skipping (the gradient is still reset); nb200_scaler_commit then advances *step only
  * if the step was taken, updates scale / tracker, clears the flag of the next iteration and increments the iteration.

@@ -15,7 +15,6 @@ except Exception as e:
 PY
 }
 run base NB200_X=0
-run fused_forward NB200_FUSED_FORWARD=1
-run encf_batch NB200_GE_FWD_BATCH=1
-for c in 1 2 4; do run adam_ctas$c NB200_ADAM_CTAS_PER_SM=$c; done
+run noprio NB200_SIDE_PRIORITY=0
+for c in 1 2 3 4; do run prio_adam$c NB200_ADAM_CTAS_PER_SM=$c; done
 EXTRA=--no-pipeline run nopipe NB200_X=0

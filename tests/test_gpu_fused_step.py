@@ -338,7 +338,7 @@ def test_dynamic_loss_scale_skips_the_step_on_a_non_finite_gradient():
         assert (scale, skipped, steps) == (128.0, 0, 2) and np.isfinite(loss)
         p0, m0, v0 = fs.params_flat.clone(), fs.exp_avg.clone(), fs.exp_avg_sq.clone()
         bad = tgt.clone()
-        bad[7, 1] = float("inf")                            # one poisoned pixel: the loss and every gradient become inf / NaN
+        bad[:, 1] = float("inf")                            # a poisoned channel: the loss and every gradient become inf / NaN
         fs.step(o, d, bad)
         fs.last_stats()
         scale, skipped, steps = fs.scaler_state()
