@@ -171,6 +171,14 @@ int nb200_train_forward_backward(const nb200_train_plan *p, void *stream) {
     return nb200_train_phase(p, NB200_PHASE_MARCH | NB200_PHASE_REST, stream);
 }
 
+// dynamic loss scale: hyper-parameters for step + 1 without committing it (the sweep is skipped on a non-finite gradient and
+// the commit rides with the weight re-pack); constant scale: the classic hyper kernel that advances the step itself
+int nb200_train_update_hyper(const nb200_train_plan *p, int peer, void *stream) {
+    if (!p) return NB200_E_BAD_ARG;
+    if (p->scaler) return nb200_adam_hyper_scaled(p->step, p->sched, p->hyper, p->scaler, peer ? 0 : 1, p->counter + 6, stream);
+    return nb200_adam_hyper(p->step, p->sched, p->hyper, stream);
+}
+
 int nb200_train_update(const nb200_train_plan *p, void *stream) {
     if (!p) return NB200_E_BAD_ARG;
     int rc;
@@ -178,9 +186,7 @@ int nb200_train_update(const nb200_train_plan *p, void *stream) {
     StageTimer *tm = (StageTimer *)p->timer;
     cudaEvent_t *ev = tm ? tm->up : nullptr;
     tick(ev, 0, st);
-    if (p->scaler) {        // dynamic loss scale: hyper-parameters for step + 1, sweep (skipped on a non-finite gradient), commit
-        if ((rc = nb200_adam_hyper_scaled(p->step, p->sched, p->hyper, p->scaler, 1, p->counter + 6, stream))) return rc;
-    } else if ((rc = nb200_adam_hyper(p->step, p->sched, p->hyper, stream))) return rc;
+    if (!(p->flags & NB200_PLAN_HYPER_DONE) && (rc = nb200_train_update_hyper(p, 0, stream))) return rc;
     if ((rc = nb200_fused_adam(p->params_flat, p->grads_flat, p->exp_avg, p->exp_avg_sq, p->n_params, p->n_table_params,
                                p->hyper, 1, stream))) return rc;
     tick(ev, 1, st);
@@ -204,9 +210,7 @@ int nb200_train_update_peer(const nb200_train_plan *p, const nb200_peer_plan *pe
     tick(ev, 0, st);
     const bool scaled = p->scaler != nullptr;
     if (scaled && peer->scalers[peer->rank] != p->scaler) return NB200_E_BAD_ARG;   // the peers must be able to read the flags
-    if (scaled) {
-        if ((rc = nb200_adam_hyper_scaled(p->step, p->sched, p->hyper, p->scaler, 0, p->counter + 6, stream))) return rc;
-    } else if ((rc = nb200_adam_hyper(p->step, p->sched, p->hyper, stream))) return rc;
+    if (!(p->flags & NB200_PLAN_HYPER_DONE) && (rc = nb200_train_update_hyper(p, 1, stream))) return rc;
     if ((rc = nb200_peer_reduce_adam_bcast(peer, stream))) return rc;
     tick(ev, 1, st);
     if (scaled) {

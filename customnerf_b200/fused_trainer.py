@@ -417,9 +417,18 @@ class FusedTrainStep:
                 import os
                 prio = -1 if os.environ.get("NB200_SIDE_PRIORITY", "1") == "1" else 0
                 self._side = torch.cuda.Stream(device=self.dev, priority=prio)
+            # the update's first (one-thread) kernel runs here, BEFORE the fork: the sweep and the march then become runnable
+            # at the same moment and the high-priority side stream gets its (thin) grid resident first -- forked earlier, the
+            # march's single wave takes every SM while that little kernel runs and the sweep waits for the wave to drain
+            hyper_first = self.allreduce_chunks <= 1 and self.grad_sync is None
+            if hyper_first:
+                _check(self.lib.nb200_train_update_hyper(C.byref(self.plan), C.c_int(1 if self.peer_plan is not None else 0), st),
+                       "train_update_hyper")
+                self.plan.flags |= 2
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 self._update(L.stream())
+            self.plan.flags &= ~2
             _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(1), st), "train_phase(march)")
             main.wait_stream(self._side)
             _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(2), st), "train_phase(rest)")

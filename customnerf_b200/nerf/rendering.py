@@ -93,6 +93,68 @@ class NeRFRenderer(nn.Module):
 
     # ------------------------------------------------------------------------------------- dense path
     def run(self, rays_o, rays_d, num_steps=128, upsample_steps=128, bg_color=None, perturb=False, **kwargs):
+        if (getattr(self, 'fused_dense', True) and rays_o.is_cuda and upsample_steps > 0 and num_steps >= 3
+                and num_steps + upsample_steps <= 256):
+            return self._run_dense_fused(rays_o, rays_d, num_steps, upsample_steps, perturb)
+        return self._run_dense_ops(rays_o, rays_d, num_steps, upsample_steps, bg_color, perturb, **kwargs)
+
+    def _run_dense_fused(self, rays_o, rays_d, num_steps, upsample_steps, perturb):
+        """The dense renderer (renderer.py:278-405) with its sampler as two kernels (csrc/dense_sampler.cu) and everything
+        after the sampler on the occupancy path's code: the merged coarse + importance samples are written as xyzs / dirs /
+        deltas / rays, so the field network runs through the fused tcgen05 kernels and the three LGIE composites through the
+        composite kernels (T_thresh = 0: the dense formula, no early termination).  The coarse density pass carries no
+        autograd graph (nothing downstream of it is differentiated, :328-346) and the reference's second, unused density
+        evaluation of the importance samples (:353) is dropped.  Same random draws as the reference, in the same order:
+        torch.rand(N, num_steps) for the stratified jitter, torch.rand(N, upsample_steps) inside sample_pdf."""
+        from .. import _lib as L
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3).float()
+        rays_d = rays_d.contiguous().view(-1, 3).float()
+        N, S, Su = rays_o.shape[0], int(num_steps), int(upsample_steps)
+        T = S + Su
+        dev = rays_o.device
+        aabb = self.aabb_train if self.training else self.aabb_infer
+        f32 = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), torch.no_grad():
+            nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, aabb, self.min_near)
+            lin = torch.linspace(0.0, 1.0, S, device=dev)
+            noise = torch.rand(N, S, device=dev) if perturb else None
+            z_c, xyz_c = torch.empty(N, S, **f32), torch.empty(N * S, 3, **f32)
+            L.check(L.lib().nb200_dense_coarse(L.ptr(rays_o), L.ptr(rays_d), L.ptr(nears), L.ptr(fars), L.ptr(aabb), L.ptr(lin),
+                                               L.ptr(noise), L.u32(N), L.u32(S), L.ptr(z_c), L.ptr(xyz_c), L.stream()), "dense_coarse")
+            sigma_c = self.density(xyz_c)['sigma'].reshape(-1).float().contiguous()
+            if self.training:
+                u, per_ray = torch.rand(N, Su, device=dev), 1
+            else:
+                u, per_ray = torch.linspace(0.5 / Su, 1.0 - 0.5 / Su, steps=Su, device=dev), 0
+            z_all, xyzs, dirs = torch.empty(N, T, **f32), torch.empty(N * T, 3, **f32), torch.empty(N * T, 3, **f32)
+            deltas, rays = torch.empty(N * T, 2, **f32), torch.empty(N, 3, dtype=torch.int32, device=dev)
+            L.check(L.lib().nb200_dense_importance(L.ptr(rays_o), L.ptr(rays_d), L.ptr(nears), L.ptr(fars), L.ptr(aabb), L.ptr(z_c),
+                                                   L.ptr(sigma_c), L.ptr(u.contiguous()), L.i32(per_ray), L.u32(N), L.u32(S), L.u32(Su),
+                                                   L.ptr(z_all), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas), L.ptr(rays), L.stream()),
+                    "dense_importance")
+        sigmas, rgba, _ = self(xyzs, dirs)
+        rgbs = rgba[..., :3].float()
+        results = {}
+        if self._flag('train_conf') and rgba.shape[-1] > 3:
+            results.update(self._lgie_composites(sigmas.float(), rgbs, rgba[..., 3:].float(), deltas, rays, 0.0, prefix))
+            weights_sum, depth, image = results.pop('_all')
+            results['sigma'], results['rgbs'] = sigmas.view(N, T, 1), rgbs.view(N, T, 3)
+            results['edit_mask'] = results['edit_mask'].view(N, T, -1)
+            for part in ('fg', 'bg'):
+                results[part]['weights_sum'] = results[part]['weights_sum'].reshape(-1)
+                results[part]['mask'] = (nears < fars).reshape(*prefix)
+        else:
+            weights_sum, depth, image = raymarching.composite_rays_train(sigmas.float(), rgbs, deltas, rays, 0.0)
+        results['image'] = image.view(*prefix, 3)
+        results['depth'] = depth.view(*prefix)
+        results['weights_sum'] = weights_sum
+        results['mask'] = (nears < fars).reshape(*prefix)
+        results['z_vals'] = z_all
+        return results
+
+    def _run_dense_ops(self, rays_o, rays_d, num_steps=128, upsample_steps=128, bg_color=None, perturb=False, **kwargs):
+        """the same renderer as the reference's op-by-op torch sequence (any sample counts; also returns 'weights')"""
         prefix = rays_o.shape[:-1]
         rays_o = rays_o.contiguous().view(-1, 3)
         rays_d = rays_d.contiguous().view(-1, 3)

@@ -237,6 +237,23 @@ int nb200_occ_finalize(float *density_grid, const float *tmp_grid, uint32_t n_ce
                        const int32_t *step_counter, uint32_t total_step, uint8_t *bitfield, float *state, void *scratch,
                        void *stream);
 
+/* ============================================================================================
+ * dense (non-cuda_ray) renderer: the sampler of NeRFRenderer.run (nerf/renderer.py:297-367) and sample_pdf (:21-55).
+ * nb200_dense_coarse: z_c[n,i] = near + (far - near) * lin[i] (+ (noise[n,i] - 0.5) * (far - near) / S when noise != NULL),
+ *   xyzs[n*S+i] = clamp(o + d * z, aabb) (:306-317); lin f32 [S] = torch.linspace(0, 1, S).
+ * nb200_dense_importance (one CTA per ray): coarse weights alpha * cumprod(1 - alpha + 1e-15) (:330-336), inverse-CDF sampling of
+ *   S_up depths from weights[1:-1] over the interval mid-points (:338-339, :21-55; u f32 [S_up] shared by all rays -- the
+ *   deterministic linspace of eval mode -- or [N,S_up] when u_per_ray), all S + S_up depths sorted (:360-361) and written in
+ *   the occupancy path's layout: z_all f32 [N,T], xyzs / dirs f32 [N*T,3], deltas f32 [N*T,2] = (z[k+1] - z[k] | last:
+ *   (far - near) / S, ori_z[k] - ori_z[k-1]) with ori_z = clamp((z - near) / (far - near), 0, 1) (:431-432), rays i32 [N,3] =
+ *   (n, n*T, T) -- so that nb200_composite_rays_train_* with T_thresh = 0 evaluates weights_sum_i (:420-439) and the field /
+ *   LGIE kernels of the occupancy path serve the dense path unchanged.  3 <= S, S + S_up <= 256. */
+int nb200_dense_coarse(const float *rays_o, const float *rays_d, const float *nears, const float *fars, const float *aabb,
+                       const float *lin, const float *noise, uint32_t N, uint32_t S, float *z_c, float *xyzs, void *stream);
+int nb200_dense_importance(const float *rays_o, const float *rays_d, const float *nears, const float *fars, const float *aabb,
+                           const float *z_c, const float *sigma_c, const float *u, int u_per_ray, uint32_t N, uint32_t S,
+                           uint32_t S_up, float *z_all, float *xyzs, float *dirs, float *deltas, int32_t *rays, void *stream);
+
 /* get_embedder(4) of nerf/base.py:42-77 exactly as the field kernels evaluate it: dirs f32 [M,3] -> out f32 [M,27] =
  * [d, sin d, cos d, sin 2d, cos 2d, sin 4d, cos 4d, sin 8d, cos 8d] (one sincos + three angle doublings per component). */
 int nb200_freq_embed(const float *dirs, float *out, uint32_t M, void *stream);
@@ -331,6 +348,9 @@ int nb200_scaler_commit(int32_t *step, uint32_t *scaler, uint32_t *const *peer_s
 
 #define NB200_PLAN_FUSED_FORWARD 1u   /* encode + field forward as one kernel (nb200_field_fused_forward): the stage timer
                                          then reports the pair under "field_forward" and ~0 under "grid_encode_forward" */
+#define NB200_PLAN_HYPER_DONE 2u      /* nb200_train_update[_peer] skips its first kernel (nb200_adam_hyper[_scaled]): the caller
+                                         has launched it already -- a pipelined trainer does so BEFORE forking the update onto its
+                                         side stream, so that the sweep and the next step's march become runnable together */
 typedef struct nb200_train_plan {
     /* sizes and scalars */
     uint32_t N, M_cap, C, H, L, base_res, gridtype, max_steps;
@@ -419,6 +439,8 @@ int nb200_train_forward_backward(const nb200_train_plan *plan, void *stream);
 int nb200_train_phase(const nb200_train_plan *plan, int phases, void *stream);
 /* fused Adam over params_flat (zeroing grads_flat) and re-pack of the MLP operand images. */
 int nb200_train_update(const nb200_train_plan *plan, void *stream);
+/* the first kernel of nb200_train_update[_peer] on its own (see NB200_PLAN_HYPER_DONE); peer != 0: for nb200_train_update_peer */
+int nb200_train_update_hyper(const nb200_train_plan *plan, int peer, void *stream);
 
 /* ============================================================================================
  * Ray generation.  Replaces the direction / origin arithmetic of get_rays
