@@ -2,11 +2,11 @@
 //
 // Replaces gridencoder/src/gridencoder.cu of the reference (per-entry file:line map in include/nerf_b200.h).
 //
-// Two families of kernels:
-//   * generic  <T, D, C>: one thread per (point, level), any D in 2..5, C in {1,2,4,8}; produces dy_dx,
-//     supports both output layouts.  Used for every shape that is not the product's.
+// Two families of kernels, both ONE THREAD PER POINT walking the levels (the reference launches a thread per (point, level)):
+//   * generic  <T, D, C> (grid_generic.cuh): any D in 2..5, C in {1,2,4,8}, both output layouts, input gradients (every
+//     corner gathered once, features and all D derivatives from the same loads), total-variation gradient.
 //   * d3c2 fast path (D=3, C=2, layout [B, L*C], L <= 32 -- the only shape nerf/network_grid.py:95 and
-//     nerf/encoding.py:55-58 ever build): one thread per POINT looping over levels, so that
+//     nerf/encoding.py:55-58 ever build):
 //       - a warp holds 32 consecutive samples of a ray: at coarse levels their 8 corners fall in the same
 //         cells and the gathers coalesce into a few sectors,
 //       - each thread owns one [L*C] output row and writes it with 16/32-byte vector stores straight in the
@@ -20,257 +20,12 @@
 // device with the reference's expression exp2f(level * S) * H - 1.0f so fine-level positions are identical.
 #include "common.cuh"
 #include "grid_d3c2.cuh"
+#include "grid_generic.cuh"
 #include <stdlib.h>
 
 namespace {
 
 
-
-template <uint32_t D>
-__device__ __forceinline__ uint32_t ge_fast_hash(const uint32_t pos_grid[D]) {
-    constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
-    uint32_t result = 0;
-#pragma unroll
-    for (uint32_t i = 0; i < D; ++i) result ^= pos_grid[i] * primes[i];
-    return result;
-}
-
-// gridencoder.cu:66-84, returns the ROW index (the reference multiplies by C and adds the channel)
-template <uint32_t D>
-__device__ __forceinline__ uint32_t ge_grid_row(uint32_t gridtype, bool align_corners, uint32_t hashmap_size,
-                                                uint32_t resolution, const uint32_t pos_grid[D]) {
-    uint32_t stride = 1, index = 0;
-#pragma unroll
-    for (uint32_t d = 0; d < D && stride <= hashmap_size; d++) {
-        index += pos_grid[d] * stride;
-        stride *= align_corners ? resolution : (resolution + 1);
-    }
-    if (gridtype == 0 && stride > hashmap_size) index = ge_fast_hash<D>(pos_grid);
-    return index % hashmap_size;
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// generic forward: gridencoder.cu:87-244
-// ------------------------------------------------------------------------------------------------
-template <typename T, uint32_t D, uint32_t C>
-__global__ void __launch_bounds__(256)
-k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ grid, const int32_t *__restrict__ offsets,
-           T *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, T *__restrict__ dy_dx,
-           uint32_t gridtype, bool align_corners, uint32_t interp, int layout) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const uint32_t level = blockIdx.y;
-    grid += (size_t)(uint32_t)offsets[level] * C;
-    inputs += (size_t)b * D;
-    outputs += (layout == NB200_LAYOUT_LBC) ? ((size_t)level * B + b) * C : ((size_t)b * L + level) * C;
-    if (dy_dx) dy_dx += (size_t)b * D * L * C + (size_t)level * D * C;
-
-    float x[D];
-    bool oob = false;
-#pragma unroll
-    for (uint32_t d = 0; d < D; d++) {
-        x[d] = inputs[d];
-        if (x[d] < 0 || x[d] > 1) oob = true;
-    }
-    if (oob) {
-#pragma unroll
-        for (uint32_t ch = 0; ch < C; ch++) outputs[ch] = nb_from_float<T>(0.0f);
-        if (dy_dx) {
-#pragma unroll
-            for (uint32_t i = 0; i < D * C; i++) dy_dx[i] = nb_from_float<T>(0.0f);
-        }
-        return;
-    }
-    const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
-    const float scale = ge_level_scale(level, S, H);
-    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
-
-    float pos[D], pos_deriv[D];
-    uint32_t pos_grid[D];
-#pragma unroll
-    for (uint32_t d = 0; d < D; d++) {
-        pos[d] = x[d] * scale + (align_corners ? 0.0f : 0.5f);
-        pos_grid[d] = (uint32_t)floorf(pos[d]);
-        pos[d] -= (float)pos_grid[d];
-        if (interp == 1) {
-            pos_deriv[d] = ge_smoothstep_d(pos[d]);
-            pos[d] = ge_smoothstep(pos[d]);
-        } else {
-            pos_deriv[d] = 1.0f;
-        }
-    }
-    float results[C];
-#pragma unroll
-    for (uint32_t ch = 0; ch < C; ch++) results[ch] = 0.0f;
-#pragma unroll
-    for (uint32_t idx = 0; idx < (1u << D); idx++) {
-        float w = 1;
-        uint32_t pgl[D];
-#pragma unroll
-        for (uint32_t d = 0; d < D; d++) {
-            if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pgl[d] = pos_grid[d]; }
-            else { w *= pos[d]; pgl[d] = pos_grid[d] + 1; }
-        }
-        const size_t row = ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
-#pragma unroll
-        for (uint32_t ch = 0; ch < C; ch++) results[ch] += w * nb_to_float<T>(grid[row * C + ch]);
-    }
-#pragma unroll
-    for (uint32_t ch = 0; ch < C; ch++) outputs[ch] = nb_from_float<T>(results[ch]);
-
-    if (dy_dx) {   // gridencoder.cu:200-243
-#pragma unroll
-        for (uint32_t gd = 0; gd < D; gd++) {
-            float rg[C];
-#pragma unroll
-            for (uint32_t ch = 0; ch < C; ch++) rg[ch] = 0.0f;
-#pragma unroll
-            for (uint32_t idx = 0; idx < (1u << (D - 1)); idx++) {
-                float w = scale;
-                uint32_t pgl[D];
-#pragma unroll
-                for (uint32_t nd = 0; nd < D - 1; nd++) {
-                    const uint32_t d = (nd >= gd) ? (nd + 1) : nd;
-                    if ((idx & (1u << nd)) == 0) { w *= 1 - pos[d]; pgl[d] = pos_grid[d]; }
-                    else { w *= pos[d]; pgl[d] = pos_grid[d] + 1; }
-                }
-                pgl[gd] = pos_grid[gd];
-                const size_t il = ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
-                pgl[gd] = pos_grid[gd] + 1;
-                const size_t ir = ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
-#pragma unroll
-                for (uint32_t ch = 0; ch < C; ch++)
-                    rg[ch] += w * (nb_to_float<T>(grid[ir * C + ch]) - nb_to_float<T>(grid[il * C + ch])) * pos_deriv[gd];
-            }
-#pragma unroll
-            for (uint32_t ch = 0; ch < C; ch++) dy_dx[gd * C + ch] = nb_from_float<T>(rg[ch]);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// generic backward: gridencoder.cu:247-339 (fp32 accumulation, one thread per (point, level))
-// ------------------------------------------------------------------------------------------------
-template <typename T, uint32_t D, uint32_t C>
-__global__ void __launch_bounds__(256)
-k_grid_bwd(const T *__restrict__ grad, const float *__restrict__ inputs, const int32_t *__restrict__ offsets,
-           float *__restrict__ grad_grid, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
-           bool align_corners, uint32_t interp, int layout) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const uint32_t level = blockIdx.y;
-    grad_grid += (size_t)(uint32_t)offsets[level] * C;
-    inputs += (size_t)b * D;
-    grad += (layout == NB200_LAYOUT_LBC) ? ((size_t)level * B + b) * C : ((size_t)b * L + level) * C;
-    const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
-    const float scale = ge_level_scale(level, S, H);
-    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
-    float pos[D];
-    uint32_t pos_grid[D];
-#pragma unroll
-    for (uint32_t d = 0; d < D; d++) {
-        const float xd = inputs[d];
-        if (xd < 0 || xd > 1) return;
-        pos[d] = xd * scale + (align_corners ? 0.0f : 0.5f);
-        pos_grid[d] = (uint32_t)floorf(pos[d]);
-        pos[d] -= (float)pos_grid[d];
-        if (interp == 1) pos[d] = ge_smoothstep(pos[d]);
-    }
-    float g[C];
-#pragma unroll
-    for (uint32_t ch = 0; ch < C; ch++) g[ch] = nb_to_float<T>(grad[ch]);
-#pragma unroll
-    for (uint32_t idx = 0; idx < (1u << D); idx++) {
-        float w = 1;
-        uint32_t pgl[D];
-#pragma unroll
-        for (uint32_t d = 0; d < D; d++) {
-            if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pgl[d] = pos_grid[d]; }
-            else { w *= pos[d]; pgl[d] = pos_grid[d] + 1; }
-        }
-        const size_t row = ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pgl);
-        if constexpr (C % 2 == 0) {
-#pragma unroll
-            for (uint32_t ch = 0; ch < C; ch += 2)
-                atomicAdd(reinterpret_cast<float2 *>(grad_grid + row * C + ch), make_float2(w * g[ch], w * g[ch + 1]));
-        } else {
-#pragma unroll
-            for (uint32_t ch = 0; ch < C; ch++) atomicAdd(grad_grid + row * C + ch, w * g[ch]);
-        }
-    }
-}
-
-// gridencoder.cu:342-368
-template <typename T>
-__global__ void k_input_bwd(const T *__restrict__ grad, const T *__restrict__ dy_dx, T *__restrict__ grad_inputs,
-                            uint32_t B, uint32_t D, uint32_t C, uint32_t L, int layout) {
-    const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
-    if (t >= B * D) return;
-    const uint32_t b = t / D, d = t - b * D;
-    dy_dx += (size_t)b * L * D * C;
-    float result = 0;
-    for (uint32_t l = 0; l < L; l++)
-        for (uint32_t ch = 0; ch < C; ch++) {
-            const size_t gi = (layout == NB200_LAYOUT_LBC) ? ((size_t)l * B + b) * C + ch : ((size_t)b * L + l) * C + ch;
-            result += nb_to_float<T>(grad[gi]) * nb_to_float<T>(dy_dx[l * D * C + d * C + ch]);
-        }
-    grad_inputs[t] = nb_from_float<T>(result);
-}
-
-// gridencoder.cu:505-609
-template <uint32_t D, uint32_t C>
-__global__ void __launch_bounds__(256)
-k_grad_tv(const float *__restrict__ inputs, const float *__restrict__ grid, float *__restrict__ grad,
-          const int32_t *__restrict__ offsets, float weight, uint32_t B, uint32_t L, float S, uint32_t H,
-          uint32_t gridtype, bool align_corners) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const uint32_t level = blockIdx.y;
-    inputs += (size_t)b * D;
-    grid += (size_t)(uint32_t)offsets[level] * C;
-    grad += (size_t)(uint32_t)offsets[level] * C;
-    const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
-    const float scale = ge_level_scale(level, S, H);
-    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
-    uint32_t pos_grid[D];
-#pragma unroll
-    for (uint32_t d = 0; d < D; d++) {
-        const float xd = inputs[d];
-        if (xd < 0 || xd > 1) return;
-        pos_grid[d] = (uint32_t)floorf(xd * scale + (align_corners ? 0.0f : 0.5f));
-    }
-    float results[C], idelta[C];
-#pragma unroll
-    for (uint32_t ch = 0; ch < C; ch++) results[ch] = idelta[ch] = 0.0f;
-    const size_t index = (size_t)ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pos_grid) * C;
-    const float w = weight / (2 * D);
-#pragma unroll
-    for (uint32_t d = 0; d < D; d++) {
-        const uint32_t cur_d = pos_grid[d];
-        if (cur_d < resolution) {
-            pos_grid[d] = cur_d + 1;
-            const size_t ir = (size_t)ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pos_grid) * C;
-#pragma unroll
-            for (uint32_t ch = 0; ch < C; ch++) {
-                const float gv = grid[index + ch] - grid[ir + ch];
-                results[ch] += gv; idelta[ch] += gv * gv;
-            }
-        }
-        if (cur_d > 0) {
-            pos_grid[d] = cur_d - 1;
-            const size_t il = (size_t)ge_grid_row<D>(gridtype, align_corners, hashmap_size, resolution, pos_grid) * C;
-#pragma unroll
-            for (uint32_t ch = 0; ch < C; ch++) {
-                const float gv = grid[index + ch] - grid[il + ch];
-                results[ch] += gv; idelta[ch] += gv * gv;
-            }
-        }
-        pos_grid[d] = cur_d;
-    }
-#pragma unroll
-    for (uint32_t ch = 0; ch < C; ch++) atomicAdd(&grad[index + ch], w * results[ch] * rsqrtf(idelta[ch] + 1e-9f));
-}
 
 // one thread per point; outputs [B, L*2].  TE = table storage type, T = value / output type.
 template <typename TE, typename T, bool kBatch = false>
@@ -436,14 +191,17 @@ template <typename T, uint32_t D>
 int launch_fwd_c(const float *inputs, const T *emb, const int32_t *offsets, T *out, uint32_t B, uint32_t C, uint32_t L,
                  uint32_t max_level, float S, uint32_t H, T *dy_dx, uint32_t gridtype, bool ac, uint32_t interp,
                  int layout, cudaStream_t st) {
-    const dim3 grid(nb_div_up(B, 256), max_level, 1);
+    if (max_level > kGenMaxLevels) return NB200_E_BAD_ARG;
+    const uint32_t grid = nb_div_up(B, 128);
+#define NB_GEN_FWD(CC) k_gen_encode<T, D, CC><<<grid, 128, 0, st>>>(inputs, emb, offsets, out, dy_dx, B, L, max_level, S, H, gridtype, ac, interp, layout)
     switch (C) {
-        case 1: k_grid_fwd<T, D, 1><<<grid, 256, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, dy_dx, gridtype, ac, interp, layout); break;
-        case 2: k_grid_fwd<T, D, 2><<<grid, 256, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, dy_dx, gridtype, ac, interp, layout); break;
-        case 4: k_grid_fwd<T, D, 4><<<grid, 256, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, dy_dx, gridtype, ac, interp, layout); break;
-        case 8: k_grid_fwd<T, D, 8><<<grid, 256, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, dy_dx, gridtype, ac, interp, layout); break;
+        case 1: NB_GEN_FWD(1); break;
+        case 2: NB_GEN_FWD(2); break;
+        case 4: NB_GEN_FWD(4); break;
+        case 8: NB_GEN_FWD(8); break;
         default: return NB200_E_BAD_DIM;
     }
+#undef NB_GEN_FWD
     return 0;
 }
 
@@ -468,14 +226,17 @@ template <typename T, uint32_t D>
 int launch_bwd_c(const T *grad, const float *inputs, const int32_t *offsets, float *gg, uint32_t B, uint32_t C,
                  uint32_t L, uint32_t max_level, float S, uint32_t H, uint32_t gridtype, bool ac, uint32_t interp,
                  int layout, cudaStream_t st) {
-    const dim3 grid(nb_div_up(B, 256), max_level, 1);
+    if (max_level > kGenMaxLevels) return NB200_E_BAD_ARG;
+    const uint32_t grid = nb_div_up(B, 128);
+#define NB_GEN_BWD(CC) k_gen_scatter<T, D, CC><<<grid, 128, 0, st>>>(grad, inputs, offsets, gg, B, L, max_level, S, H, gridtype, ac, interp, layout)
     switch (C) {
-        case 1: k_grid_bwd<T, D, 1><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype, ac, interp, layout); break;
-        case 2: k_grid_bwd<T, D, 2><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype, ac, interp, layout); break;
-        case 4: k_grid_bwd<T, D, 4><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype, ac, interp, layout); break;
-        case 8: k_grid_bwd<T, D, 8><<<grid, 256, 0, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype, ac, interp, layout); break;
+        case 1: NB_GEN_BWD(1); break;
+        case 2: NB_GEN_BWD(2); break;
+        case 4: NB_GEN_BWD(4); break;
+        case 8: NB_GEN_BWD(8); break;
         default: return NB200_E_BAD_DIM;
     }
+#undef NB_GEN_BWD
     return 0;
 }
 
@@ -499,21 +260,24 @@ int launch_bwd(const T *grad, const float *inputs, const int32_t *offsets, float
     }
     if (rc) return rc;
     if (dy_dx && grad_inputs)
-        k_input_bwd<T><<<nb_div_up((uint64_t)B * D, 256), 256, 0, st>>>(grad, dy_dx, grad_inputs, B, D, C, L, layout);
+        k_gen_input_grad<T><<<nb_div_up(B, 128), 128, 0, st>>>(grad, dy_dx, grad_inputs, B, D, C, L, layout);
     return 0;
 }
 
 template <uint32_t D>
 int launch_tv_c(const float *inputs, const float *emb, float *grad, const int32_t *offsets, float weight, uint32_t B,
                 uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool ac, cudaStream_t st) {
-    const dim3 grid(nb_div_up(B, 256), L, 1);
+    if (L > kGenMaxLevels) return NB200_E_BAD_ARG;
+    const uint32_t grid = nb_div_up(B, 128);
+#define NB_GEN_TV(CC) k_gen_tv<D, CC><<<grid, 128, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac)
     switch (C) {
-        case 1: k_grad_tv<D, 1><<<grid, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
-        case 2: k_grad_tv<D, 2><<<grid, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
-        case 4: k_grad_tv<D, 4><<<grid, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
-        case 8: k_grad_tv<D, 8><<<grid, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
+        case 1: NB_GEN_TV(1); break;
+        case 2: NB_GEN_TV(2); break;
+        case 4: NB_GEN_TV(4); break;
+        case 8: NB_GEN_TV(8); break;
         default: return NB200_E_BAD_DIM;
     }
+#undef NB_GEN_TV
     return 0;
 }
 

@@ -66,9 +66,39 @@ def both_prio():
     main.wait_stream(side); main.wait_stream(hi)
 
 
+def both_update_prio():
+    main = torch.cuda.current_stream()
+    hi.wait_stream(main)
+    with torch.cuda.stream(hi):
+        update(L.stream())
+    march(L.stream())
+    main.wait_stream(hi)
+
+
+def adam_only(st):
+    p = fs.plan
+    fused_trainer._check(lib.nb200_fused_adam(C.c_void_p(p.params_flat), C.c_void_p(p.grads_flat), C.c_void_p(p.exp_avg),
+                                              C.c_void_p(p.exp_avg_sq), C.c_uint64(p.n_params), C.c_uint64(p.n_table_params),
+                                              C.c_void_p(p.hyper), C.c_int(1), st), "adam")
+
+
+def both_adam_only_prio():
+    """only the sweep kernel (no one-thread hyper kernel in front of it) on the high-priority stream, issued first"""
+    main = torch.cuda.current_stream()
+    hi.wait_stream(main)
+    with torch.cuda.stream(hi):
+        adam_only(L.stream())
+    march(L.stream())
+    main.wait_stream(hi)
+
+
+print("NB200_ADAM_CTAS_PER_SM =", os.environ.get("NB200_ADAM_CTAS_PER_SM"))
 print("march alone   %.1f us" % timeit(lambda: march(L.stream())))
 print("update alone  %.1f us" % timeit(lambda: update(L.stream())))
 print("serial        %.1f us" % timeit(lambda: (update(L.stream()), march(L.stream()))))
 print("two streams (update issued first) %.1f us" % timeit(both))
 print("two streams (march issued first)  %.1f us" % timeit(both_march_first))
 print("two streams, march on a high-priority stream %.1f us" % timeit(both_prio))
+print("two streams, update on a high-priority stream, issued first %.1f us" % timeit(both_update_prio))
+print("adam alone    %.1f us" % timeit(lambda: adam_only(L.stream())))
+print("two streams, sweep kernel only on a high-priority stream, issued first %.1f us" % timeit(both_adam_only_prio))

@@ -72,9 +72,13 @@ def test_sampler_kernels_match_the_torch_restatement(S, Su, det):
     new_z = b0 + (uu - c0) / den * (b1 - b0)
     z_want, _ = torch.sort(torch.cat([zc, new_z], 1), 1)
     span = float((fars - nears).max())
-    # a sample can fall the other side of a cdf entry when u sits within rounding of it: compare depths with a tolerance of
-    # 1e-5 of the ray span (the cumulative sums differ from torch's by summation order only)
-    assert_close(z_all.cpu().numpy(), z_want.numpy(), 0, 2e-5 * span, "merged depths")
+    # The cumulative sums differ from torch's by summation order only (~1e-7), so the depths agree to 2e-5 of the ray span --
+    # except where u sits within that rounding of a cdf entry AND the neighbouring bin is (nearly) empty: sample_pdf replaces a
+    # denominator below 1e-5 by 1 (:50-51), a discontinuity of up to one bin width.  Allow that for at most 0.1 % of the samples.
+    err = (z_all.cpu() - z_want).abs()
+    off = err > 2e-5 * span
+    assert float(off.float().mean()) <= 1e-3, float(off.float().mean())
+    assert float(err.max()) <= 1.01 * span / (S - 1), float(err.max())
     got = z_all.cpu()
     assert (got[:, 1:] >= got[:, :-1]).all(), "sorted"
     want_d0 = torch.cat([got[:, 1:] - got[:, :-1], sdc], -1)

@@ -170,3 +170,36 @@ def test_grid_encoder_against_reference_kernels(scene, cfg, half):
         assert_close(mine_g, g0, 1e-3, 1e-5 * np.abs(g0).max(), "grad fp16 path vs fp64 oracle")
     else:
         assert_close(mine_g, ref_g, 1e-4, 1e-5 * np.abs(ref_g).max(), "grad fp32")
+
+
+@pytest.mark.parametrize("cfg", [dict(D=3, C=2, L=16, log2=19, res=2048, gridtype="hash"),
+                                 dict(D=3, C=2, L=16, log2=21, res=8192, gridtype="tiled"),
+                                 dict(D=2, C=4, L=8, log2=14, res=512, gridtype="hash"),
+                                 dict(D=3, C=8, L=6, log2=15, res=256, gridtype="hash", align_corners=True)])
+def test_total_variation_gradient_against_the_reference_kernel(cfg):
+    """grad_total_variation (gridencoder.cu:505-644, grid.py:171-192) -- this repo's point-major kernel (csrc/grid_generic.cuh:
+    k_gen_tv) against the reference's kernel_grad_tv on the same points and table.  Both accumulate with fp32 atomics into the
+    same cells: rel 1e-4 with an absolute floor of 1e-6 of the largest entry (the order of the additions differs)."""
+    from customnerf_b200.gridencoder import GridEncoder
+    ge = ref_ext.gridencoder()
+    torch.manual_seed(0)
+    enc = GridEncoder(input_dim=cfg["D"], num_levels=cfg["L"], level_dim=cfg["C"], base_resolution=16,
+                      log2_hashmap_size=cfg["log2"], desired_resolution=cfg["res"], gridtype=cfg["gridtype"],
+                      align_corners=cfg.get("align_corners", False)).cuda()
+    with torch.no_grad():
+        enc.embeddings.uniform_(-1, 1)
+    B = 200000
+    x = torch.rand(B, cfg["D"], device="cuda")
+    x[:7] = torch.tensor([0.0, 1.0, 0.5, 1e-7, 1 - 1e-7, 0.25, 0.75], device="cuda")[:, None]     # faces and cell boundaries
+    x[7] = -0.1                                                                                   # outside: contributes nothing
+    enc.embeddings.grad = torch.zeros_like(enc.embeddings)
+    enc.grad_total_variation(weight=1e-3, inputs=x * 2 - 1, bound=1)
+    got = enc.embeddings.grad.clone()
+    want = torch.zeros_like(enc.embeddings)
+    xin = ((x * 2 - 1) + 1) / 2                 # the wrapper's own mapping to [0, 1] (grid.py:185), same expression as the product's
+    ge.grad_total_variation(xin.contiguous(), enc.embeddings.detach(), want, enc.offsets, 1e-3, B, cfg["D"], cfg["C"], cfg["L"],
+                            float(np.log2(enc.per_level_scale)), int(enc.base_resolution), enc.gridtype_id, bool(enc.align_corners))
+    torch.cuda.synchronize()
+    w = want.cpu().numpy()
+    assert np.abs(w).max() > 0
+    assert_close(got.cpu().numpy(), w, 1e-4, 1e-6 * np.abs(w).max(), "TV gradient vs kernel_grad_tv")
