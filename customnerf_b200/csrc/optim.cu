@@ -83,8 +83,11 @@ __global__ void k_adam_hyper_scaled(const int32_t *__restrict__ step, const floa
     if (samples) atomicOr(scaler_flag(scaler), (uint32_t)max(*samples, 0) & ~kScalerInfBit);   // this step's sample count, for the peers
     const int32_t t = *step + 1;
     const double b1 = sched[2], b2 = sched[3];
+    // LambdaLR (main.py:189) is stepped after EVERY train step, skipped or not (utils_init_nerf.py:626-629): its epoch is the
+    // scaler's iteration count, not the optimiser's step count
+    const double epoch = (double)scaler[kScalerIter];
     double decay = 1.0;
-    if (sched[7] > 0.0f) decay = pow((double)sched[6], fmin((double)(t - 1) / (double)sched[7], 1.0));
+    if (sched[7] > 0.0f) decay = pow((double)sched[6], fmin(epoch / (double)sched[7], 1.0));
     const float bc1 = (float)(1.0 - pow(b1, (double)t)), bc2s = (float)sqrt(1.0 - pow(b2, (double)t));
     const float scale = __uint_as_float(scaler[kScalerScale]);
     const float skip = (local_skip && (*scaler_flag(scaler) & kScalerInfBit)) ? 1.0f : 0.0f;

@@ -92,3 +92,69 @@ class TrainStep:
         torch._foreach_mul_([p.grad for p in self.params if p.grad is not None], inv)
         self.optimizer.step()
         return loss
+
+
+# ------------------------------------------------------------------------------------------------ editing step (LGIE)
+def editing_bg_color(opt, n, device):
+    """the background colour ``train_step_editing`` hands to ``render`` (nerf/utils_init_nerf.py:357-364): one random /
+    black / white colour for all ``n`` rays, or None.  (The renderer ignores the argument, as the reference's does.)"""
+    if getattr(opt, 'random_bg_c', False):
+        return torch.rand((1, 3), device=device).repeat(n, 1)
+    if getattr(opt, 'black_bg_c', False):
+        return torch.zeros((1, 3), device=device).repeat(n, 1)
+    if getattr(opt, 'white_bg_c', False):
+        return torch.ones((1, 3), device=device).repeat(n, 1)
+    return None
+
+
+class TeacherCache:
+    """``Trainer_Nerf.get_pt`` (nerf/utils_init_nerf.py:243-265): the frozen pre-trained model's render of a training view --
+    rendered mask, fg / bg images and the fg depth in [B, C, H, W] layout -- computed once per image path, kept on the
+    host, moved back to the device (detached) on every later visit.  ``render`` is the teacher's render callable."""
+
+    def __init__(self, render):
+        self.render = render
+        self.pt_dict = {}
+
+    def get(self, rays_o, rays_d, img_path, bg_color, B, H, W, opt):
+        if img_path not in self.pt_dict:
+            out = self.render(rays_o, rays_d, staged=False, perturb=True, bg_color=bg_color, force_all_rays=True, **vars(opt))
+            pt_mask = out['render_mask'].reshape(B, H, W, -1).contiguous()
+            pt_rgb_bg = out['bg']['image'].reshape(B, H, W, 3).permute(0, 3, 1, 2).contiguous()
+            pt_rgb_fg = out['fg']['image'].reshape(B, H, W, 3).permute(0, 3, 1, 2).contiguous()
+            pt_depth_fg = out['fg']['depth'].reshape(B, H, W, 1).permute(0, 3, 1, 2).contiguous()
+            self.pt_dict[img_path] = (pt_rgb_bg.cpu().detach(), pt_rgb_fg.cpu().detach(), pt_mask.cpu().detach(),
+                                      pt_depth_fg.cpu().detach(), None)
+        else:
+            dev = rays_o.device
+            pt_rgb_bg, pt_rgb_fg, pt_mask, pt_depth_fg = [t.detach().to(dev) for t in self.pt_dict[img_path][:-1]]
+        return pt_rgb_fg, pt_rgb_bg, pt_mask, pt_depth_fg, None
+
+
+def editing_loss(outputs, rgbs, teacher, opt, B, H, W, guidance_loss=None):
+    """The loss of ``Trainer_Nerf.train_step_editing`` (nerf/utils_init_nerf.py:366-392) on a render result:
+        loss = guidance_loss(pred_rgb, outputs)            (the Stable-Diffusion SDS term, out of scope: any callable
+                                                            returning (loss, dict); the reference's train_step_sd)
+             + keep_bg * L1(teacher background, rendered background)
+    with, under ``ori_bg``, the teacher background replaced by the ground-truth pixels wherever neither the teacher's nor the
+    current rendered mask marks the pixel as edited ((pt_mask + pred_mask) < 0.5).  ``teacher`` = (pt_rgb_fg, pt_rgb_bg,
+    pt_mask, pt_depth_fg, _) as TeacherCache.get returns it.  Returns (pred_rgb, pred_ws, loss, loss_dict)."""
+    pred_rgb = outputs['image'].reshape(B, H, W, 3).permute(0, 3, 1, 2).contiguous()
+    pred_ws = outputs['weights_sum'].reshape(B, H, W)
+    pred_mask = outputs['render_mask'].reshape(B, H, W, -1)
+    pred_rgb_bg = outputs['bg']['image'].reshape(B, H, W, 3).permute(0, 3, 1, 2).contiguous()
+    pt_rgb_fg, pt_rgb_bg, pt_mask, pt_depth_fg, _ = teacher
+    if getattr(opt, 'ori_bg', False):
+        # the reference multiplies [B,3,H,W] by this [B,H,W,1] mask as it is (:375-377), which only broadcasts for H == 3;
+        # the mask is brought to [B,1,H,W] here (DESIGN.md section 8b, B15)
+        non_edit = ((pt_mask + pred_mask) < 0.5)[..., :1].permute(0, 3, 1, 2)
+        pt_rgb_bg = rgbs.reshape(B, H, W, 3).permute(0, 3, 1, 2) * non_edit + (~non_edit) * pt_rgb_bg
+    loss, loss_dict = None, {}
+    if getattr(opt, 'lambda_sd', 0) and guidance_loss is not None:
+        loss, d = guidance_loss(pred_rgb, outputs)
+        loss_dict.update(d)
+    if getattr(opt, 'keep_bg', 0):
+        loss_bg = opt.keep_bg * F.l1_loss(pt_rgb_bg, pred_rgb_bg)
+        loss = loss_bg if loss is None else loss + loss_bg
+        loss_dict.update(dict(loss_bg=loss_bg.item()))
+    return pred_rgb, pred_ws, loss, loss_dict
