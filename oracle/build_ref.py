@@ -94,6 +94,26 @@ def build_one(name, verbose=True):
     return so
 
 
+# The reference's own Python wrappers around its two extensions.  They are staged -- byte for byte, next to the compiled
+# extensions, in the same git-ignored build directory -- so that the GPU box (which has no /root/reference) can run the
+# reference's UNMODIFIED grid.py / raymarching.py over this repo's library (tests/test_gpu_reference_wrappers.py: the
+# drop-in boundary proof).  Like the .so files they are build products of this recipe: never committed, never imported by
+# the product.
+WRAPPERS = {"gridencoder/grid.py": "pysrc/ref_gridencoder/grid.py", "raymarching/raymarching.py": "pysrc/ref_raymarching/raymarching.py"}
+
+
+def stage_wrappers(verbose=True):
+    for src, dst in WRAPPERS.items():
+        a, b = os.path.join(REF, src), os.path.join(OUT, dst)
+        os.makedirs(os.path.dirname(b), exist_ok=True)
+        shutil.copyfile(a, b)
+        init = os.path.join(os.path.dirname(b), "__init__.py")
+        if not os.path.isfile(init):
+            open(init, "w").close()
+    if verbose:
+        print("[build_ref] staged the reference's wrappers under", os.path.join(OUT, "pysrc"))
+
+
 def build_all(force=False, verbose=True):
     if not available():
         if verbose:
@@ -102,6 +122,7 @@ def build_all(force=False, verbose=True):
     for name in TARGETS:
         if force or not built(name):
             build_one(name, verbose=verbose)
+    stage_wrappers(verbose=verbose)
     return True
 
 
