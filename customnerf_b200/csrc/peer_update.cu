@@ -93,7 +93,7 @@ __device__ __forceinline__ void multimem_st(float4 *mc, const float4 &v) {
 // W ranks, U float4 groups per thread and trip (U * W gradient loads in flight per thread before the first add);
 // MC: reduce and broadcast through the multicast mappings (plan.mc_grads / mc_params) instead of W-1 peer loads / stores
 template <int W, int U, bool MC>
-__global__ void __launch_bounds__(kPeerThreads, 2)
+__global__ void __launch_bounds__(512, 1)
 k_peer_reduce_adam_bcast(const nb200_peer_plan pl) {
     const uint32_t epoch = pl.epoch[blockIdx.x] + 1u;
     const uint64_t n4 = pl.n / 4, split4 = pl.split / 4;
@@ -198,7 +198,7 @@ int launch_peer(const nb200_peer_plan *pl, cudaStream_t st) {
     if (unroll_env < 0) { const char *e = getenv("NB200_PEER_UNROLL"); unroll_env = e ? atoi(e) : 0; }
     static int threads_env = -1;        // threads per CTA (tuning knob): a thin CTA leaves the SM's registers to a co-running kernel
     if (threads_env < 0) { const char *e = getenv("NB200_PEER_THREADS"); threads_env = e ? atoi(e) : 0; }
-    const int T = (threads_env == 64 || threads_env == 128) ? threads_env : kPeerThreads;
+    const int T = (threads_env == 64 || threads_env == 128 || threads_env == 512) ? threads_env : kPeerThreads;
     const bool mc = pl->mc_grads && pl->mc_params;
     const int U = unroll_env > 0 ? unroll_env : (mc || W <= 2 ? 4 : W <= 4 ? 2 : 1);
     if (mc) {
@@ -233,8 +233,11 @@ uint32_t nb200_peer_grid(uint64_t n, uint32_t world, uint32_t sms) {
     if (world == 0) return 0;
     static int per_sm_env = -1;         // CTAs per SM (tuning knob); every CTA must be resident: the barriers are per CTA
     if (per_sm_env < 0) { const char *e = getenv("NB200_PEER_CTAS_PER_SM"); per_sm_env = e ? atoi(e) : 0; }
+    static int grid_env = -1;           // absolute CTA count (tuning knob): a NARROW grid leaves most SMs to a co-running kernel
+    if (grid_env < 0) { const char *e = getenv("NB200_PEER_GRID"); grid_env = e ? atoi(e) : 0; }
     const uint64_t per = (n / 4 + world - 1) / world;
-    const uint64_t want = (per + kPeerThreads - 1) / kPeerThreads, cap = (uint64_t)sms * (per_sm_env > 0 ? per_sm_env : 2);
+    const uint64_t want = (per + kPeerThreads - 1) / kPeerThreads;
+    const uint64_t cap = grid_env > 0 ? (uint64_t)grid_env : (uint64_t)sms * (per_sm_env > 0 ? per_sm_env : 2);
     const uint64_t g = want < cap ? want : cap;
     return (uint32_t)(g ? g : 1);
 }
