@@ -520,6 +520,7 @@ def run_b200(args):
                                    ("; the update of step k runs on a second stream next to the march of step k+1 (every "
                                     "replay contains exactly one update and one forward/backward)" if not args.no_pipeline else ""),
                            "sample_rows_capacity": fs.m_cap,
+                           "l2_persist": ({k: v for k, v in fs.l2.items() if k != "base"} if getattr(fs, "l2", None) else None),
                            "l2": "256 MB memset between steps, outside the per-step CUDA-event pairs",
                            "timing": "sum of per-step CUDA-event intervals, max over ranks" +
                                      ("; the ranks are re-aligned by a one-CTA flag barrier after each L2 flush, outside the "

@@ -16,6 +16,42 @@ namespace {
 
 // n4 = number of float4 groups; elements [0, split) use group 0, [split, n) group 1.  split % 4 == 0 is required
 // when vectorised (the launcher checks).
+template <int U>
+__global__ void __launch_bounds__(512)
+k_fused_adam_deep(float4 *__restrict__ param, float4 *__restrict__ grad, float4 *__restrict__ exp_avg,
+                  float4 *__restrict__ exp_avg_sq, uint64_t n4, uint64_t split4, const AdamHyper *__restrict__ hyper,
+                  int zero_grad) {
+    // the same sweep on a NARROW grid (few SMs, wide CTAs, U float4 groups of every vector in flight per thread): enough
+    // requests in flight to pull the HBM stream from a fraction of the SMs, so that a latency-bound kernel of the next step
+    // (the ray march) can run beside it on the rest -- the pipelined update of FusedTrainStep
+    const AdamConst h0(hyper[0]), h1(hyper[1]);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    if (hyper[0].skip != 0.0f) {
+        if (zero_grad)
+            for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n4; base += stride * U) {
+        float4 p[U], g[U], m[U], v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t i = base + (uint64_t)u * stride;
+            if (i < n4) { p[u] = param[i]; g[u] = grad[i]; m[u] = __ldcs(exp_avg + i); v[u] = __ldcs(exp_avg_sq + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t i = base + (uint64_t)u * stride;
+            if (i < n4) {
+                const AdamConst &h = i < split4 ? h0 : h1;
+                adam1(p[u].x, g[u].x, m[u].x, v[u].x, h); adam1(p[u].y, g[u].y, m[u].y, v[u].y, h);
+                adam1(p[u].z, g[u].z, m[u].z, v[u].z, h); adam1(p[u].w, g[u].w, m[u].w, v[u].w, h);
+                param[i] = p[u]; __stcs(exp_avg + i, m[u]); __stcs(exp_avg_sq + i, v[u]);
+                if (zero_grad) grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_fused_adam(float4 *__restrict__ param, float4 *__restrict__ grad, float4 *__restrict__ exp_avg,
              float4 *__restrict__ exp_avg_sq, uint64_t n4, uint64_t split4, const AdamHyper *__restrict__ hyper,
@@ -149,8 +185,21 @@ int nb200_fused_adam(float *param, float *grad, float *exp_avg, float *exp_avg_s
     if (n4) {
         static int per_sm = -1;         // tuning knob: CTAs per SM (a thin sweep leaves room for a co-running kernel)
         if (per_sm < 0) { const char *e = getenv("NB200_ADAM_CTAS_PER_SM"); per_sm = e ? atoi(e) : 0; if (per_sm <= 0 || per_sm > 8) per_sm = 8; }
+        static int deep_grid = -1, deep_thr = 512, deep_u = 2;     // tuning knobs of the narrow form (0: the wide sweep)
+        if (deep_grid < 0) {
+            const char *e = getenv("NB200_ADAM_GRID"); deep_grid = e ? atoi(e) : 0;
+            e = getenv("NB200_ADAM_THREADS"); if (e) deep_thr = atoi(e);
+            e = getenv("NB200_ADAM_UNROLL"); if (e) deep_u = atoi(e);
+            if (deep_thr != 256 && deep_thr != 512) deep_thr = 512;
+        }
         const uint32_t want = nb_div_up(n4, 256);
         const uint32_t grid = want < (uint32_t)sms * per_sm ? want : (uint32_t)sms * per_sm;
+        if (deep_grid > 0 && n4 > (uint64_t)deep_grid * deep_thr * 4) {
+#define NB_ADAM_DEEP(UU) k_fused_adam_deep<UU><<<deep_grid, deep_thr, 0, st>>>((float4 *)param, (float4 *)grad, (float4 *)exp_avg, \
+                                                                              (float4 *)exp_avg_sq, n4, split / 4, (const AdamHyper *)hyper, zero_grad)
+            if (deep_u >= 4) NB_ADAM_DEEP(4); else if (deep_u >= 2) NB_ADAM_DEEP(2); else NB_ADAM_DEEP(1);
+#undef NB_ADAM_DEEP
+        } else
         k_fused_adam<<<grid, 256, 0, st>>>((float4 *)param, (float4 *)grad, (float4 *)exp_avg, (float4 *)exp_avg_sq, n4,
                                            split / 4, (const AdamHyper *)hyper, zero_grad);
         NB_LAUNCH_CHECK();

@@ -222,11 +222,43 @@ class FusedTrainStep:
         self.peer_plan = None if peer is None else peer.plan(self.layout[0][2], self.exp_avg, self.exp_avg_sq, self.hyper,
                                                              status=self.stats[4:5], use_scaler=self.dynamic_loss_scale)
         self.n_total = N * world_size
+        self.l2 = self._setup_l2_persist()
         self._pack()
         self.m_cap = 0
         self._alloc_samples(int(m_cap) if m_cap else 0)
 
     # ------------------------------------------------------------------------------------------ setup
+    def _setup_l2_persist(self):
+        """L2 residency of the hash table (north_star kernel 1; csrc/l2_residency.cu): a carve-out of the L2 for persisting
+        lines and an access-policy window over the table on the step's stream(s), so that the ~350 MB of activations a step
+        streams through the L2 do not evict the table between two encode passes.  NB200_L2_PERSIST=0 turns it off;
+        NB200_L2_PERSIST=grad puts the window on the table's gradient instead (the scatter's read-modify-write target)."""
+        import os
+        mode = os.environ.get("NB200_L2_PERSIST", "1")
+        if mode == "0":
+            return None
+        n_table = self.layout[0][2]
+        base = (self.grads_flat if mode == "grad" else self.params_flat).data_ptr()
+        granted, maxwin = C.c_uint64(0), C.c_uint64(0)
+        with torch.cuda.device(self.dev):
+            rc = self.lib.nb200_l2_persist_limit(C.c_uint64(n_table * 4), C.byref(granted), C.byref(maxwin))
+        if rc != 0 or granted.value == 0:
+            return None
+        win = min(n_table * 4, int(maxwin.value))
+        ratio = min(1.0, granted.value / float(win))
+        info = {"mode": "table" if mode != "grad" else "grad", "carve_out_bytes": int(granted.value), "window_bytes": int(win),
+                "hit_ratio": round(ratio, 3), "base": base}
+        self._apply_l2_window(torch.cuda.current_stream(self.dev), info)
+        return info
+
+    def _apply_l2_window(self, stream, info=None):
+        info = info or self.l2
+        if info is None:
+            return
+        with torch.cuda.device(self.dev):
+            self.lib.nb200_stream_access_window(C.c_void_p(stream.cuda_stream), C.c_void_p(info["base"]),
+                                                C.c_uint64(info["window_bytes"]), C.c_float(info["hit_ratio"]))
+
     def _pack(self):
         m = self.model
         with torch.cuda.device(self.dev):
@@ -417,6 +449,7 @@ class FusedTrainStep:
                 import os
                 prio = -1 if os.environ.get("NB200_SIDE_PRIORITY", "1") == "1" else 0
                 self._side = torch.cuda.Stream(device=self.dev, priority=prio)
+                self._apply_l2_window(self._side)
             # the update's first (one-thread) kernel runs here, BEFORE the fork: the sweep and the march then become runnable
             # at the same moment and the high-priority side stream gets its (thin) grid resident first -- forked earlier, the
             # march's single wave takes every SM while that little kernel runs and the sweep waits for the wave to drain
@@ -477,6 +510,7 @@ class FusedTrainStep:
         keep = [t.clone() for t in state]
         try:
             s = torch.cuda.Stream(device=self.dev)
+            self._apply_l2_window(s)
             s.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(s):
                 for _ in range(2):
@@ -485,7 +519,8 @@ class FusedTrainStep:
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             # thread_local: NCCL's watchdog thread may touch the CUDA API while the all-reduce of a sharded step is captured
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            # the capture stream carries the L2 access-policy window: kernel nodes inherit it from the stream they are captured on
+            with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
                 self._launch(staged)
             self.graphs[staged] = g
         finally:

@@ -254,6 +254,17 @@ int nb200_dense_importance(const float *rays_o, const float *rays_d, const float
                            const float *z_c, const float *sigma_c, const float *u, int u_per_ray, uint32_t N, uint32_t S,
                            uint32_t S_up, float *z_all, float *xyzs, float *dirs, float *deltas, int32_t *rays, void *stream);
 
+/* ============================================================================================
+ * L2 residency of the hash table (north_star kernel 1: "per-level tables staged so the working set stays L2-resident"; the
+ * reference's intent at gridencoder.cu:387).  nb200_l2_persist_limit sets aside up to `bytes` of the L2 for persisting lines
+ * (host pointers: *granted = what the device gave, *max_window = the largest access-policy window it accepts);
+ * nb200_stream_access_window makes every later launch on `stream` (CUDA-graph captures included) keep a hit_ratio share of
+ * the lines it touches in [base, base + bytes) in that carve-out and treat everything else as streaming; bytes == 0
+ * removes the window.  nb200_l2_persist_reset demotes all persisting lines. */
+int nb200_l2_persist_limit(uint64_t bytes, uint64_t *granted, uint64_t *max_window);
+int nb200_stream_access_window(void *stream, const void *base, uint64_t bytes, float hit_ratio);
+int nb200_l2_persist_reset(void);
+
 /* get_embedder(4) of nerf/base.py:42-77 exactly as the field kernels evaluate it: dirs f32 [M,3] -> out f32 [M,27] =
  * [d, sin d, cos d, sin 2d, cos 2d, sin 4d, cos 4d, sin 8d, cos 8d] (one sincos + three angle doublings per component). */
 int nb200_freq_embed(const float *dirs, float *out, uint32_t M, void *stream);
