@@ -231,10 +231,13 @@ class FusedTrainStep:
     def _setup_l2_persist(self):
         """L2 residency of the hash table (north_star kernel 1; csrc/l2_residency.cu): a carve-out of the L2 for persisting
         lines and an access-policy window over the table on the step's stream(s), so that the ~350 MB of activations a step
-        streams through the L2 do not evict the table between two encode passes.  NB200_L2_PERSIST=0 turns it off;
-        NB200_L2_PERSIST=grad puts the window on the table's gradient instead (the scatter's read-modify-write target)."""
+        streams through the L2 do not evict the table between two encode passes.  NB200_L2_PERSIST=1 turns it on,
+        NB200_L2_PERSIST=grad puts the window on the table's gradient instead (the scatter's read-modify-write target).
+        Measured on B200 at configs[1] (2^19 table, carve-out limit 47.4 MiB): window on the table: encode forward 51.9 ->
+        50.5 us but field forward + 3.6 us and Adam + 3.9 us (the carve-out is taken from everybody's L2): 0.502 vs 0.488
+        ms/step; window on the gradient: scatter 130 -> 119 us, encode / field forward + 2.5 / + 3.8 us: 0.4905 ms/step."""
         import os
-        mode = os.environ.get("NB200_L2_PERSIST", "1")
+        mode = os.environ.get("NB200_L2_PERSIST", "0")       # measured (profiles/r02m_l2_persist.txt): no net gain at 2^19 -> off by default
         if mode == "0":
             return None
         n_table = self.layout[0][2]

@@ -15,9 +15,7 @@ except Exception as e:
 PY
 }
 run base NB200_L2_PERSIST=0
-run l2table NB200_L2_PERSIST=1
-run l2grad NB200_L2_PERSIST=grad
-for cfg in "64 512 2" "48 512 4" "96 512 2" "64 512 4" "32 512 4" "128 256 2"; do
+for cfg in "56 512 4" "64 512 4" "72 512 4" "80 512 4" "88 512 4" "64 512 1" "74 512 2" "148 512 4" "148 256 4"; do
   set -- $cfg
   run deep_$1_$2_$3 NB200_L2_PERSIST=0 NB200_ADAM_GRID=$1 NB200_ADAM_THREADS=$2 NB200_ADAM_UNROLL=$3
 done
