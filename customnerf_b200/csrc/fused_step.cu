@@ -187,8 +187,8 @@ int nb200_train_update(const nb200_train_plan *p, void *stream) {
     cudaEvent_t *ev = tm ? tm->up : nullptr;
     tick(ev, 0, st);
     if (!(p->flags & NB200_PLAN_HYPER_DONE) && (rc = nb200_train_update_hyper(p, 0, stream))) return rc;
-    if ((rc = nb200_fused_adam(p->params_flat, p->grads_flat, p->exp_avg, p->exp_avg_sq, p->n_params, p->n_table_params,
-                               p->hyper, 1, stream))) return rc;
+    if ((rc = nb200_fused_adam_cfg(p->params_flat, p->grads_flat, p->exp_avg, p->exp_avg_sq, p->n_params, p->n_table_params,
+                                   p->hyper, 1, p->adam_grid, p->adam_threads, p->adam_unroll, stream))) return rc;
     tick(ev, 1, st);
     if (p->scaler) {        // weight re-pack + GradScaler.update() / step count in one launch
         if ((rc = nb200_field_pack_weights_commit(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, p->step, p->scaler, nullptr, 1,

@@ -172,6 +172,12 @@ extern "C" {
 
 int nb200_fused_adam(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, uint64_t split,
                      const float *hyper, int zero_grad, void *stream) {
+    return nb200_fused_adam_cfg(param, grad, exp_avg, exp_avg_sq, n, split, hyper, zero_grad, 0, 0, 0, stream);
+}
+
+int nb200_fused_adam_cfg(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, uint64_t split,
+                         const float *hyper, int zero_grad, uint32_t cfg_grid, uint32_t cfg_threads, uint32_t cfg_unroll,
+                         void *stream) {
     if (n == 0) return 0;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || split > n) return NB200_E_BAD_ARG;
     const uintptr_t al = reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
@@ -185,13 +191,15 @@ int nb200_fused_adam(float *param, float *grad, float *exp_avg, float *exp_avg_s
     if (n4) {
         static int per_sm = -1;         // tuning knob: CTAs per SM (a thin sweep leaves room for a co-running kernel)
         if (per_sm < 0) { const char *e = getenv("NB200_ADAM_CTAS_PER_SM"); per_sm = e ? atoi(e) : 0; if (per_sm <= 0 || per_sm > 8) per_sm = 8; }
-        static int deep_grid = -1, deep_thr = 512, deep_u = 2;     // tuning knobs of the narrow form (0: the wide sweep)
-        if (deep_grid < 0) {
-            const char *e = getenv("NB200_ADAM_GRID"); deep_grid = e ? atoi(e) : 0;
-            e = getenv("NB200_ADAM_THREADS"); if (e) deep_thr = atoi(e);
-            e = getenv("NB200_ADAM_UNROLL"); if (e) deep_u = atoi(e);
-            if (deep_thr != 256 && deep_thr != 512) deep_thr = 512;
+        static int env_grid = -1, env_thr = 512, env_u = 2;     // tuning knobs: override the caller's shape
+        if (env_grid < 0) {
+            const char *e = getenv("NB200_ADAM_GRID"); env_grid = e ? atoi(e) : 0;
+            e = getenv("NB200_ADAM_THREADS"); if (e) env_thr = atoi(e);
+            e = getenv("NB200_ADAM_UNROLL"); if (e) env_u = atoi(e);
         }
+        int deep_grid = env_grid > 0 ? env_grid : (int)cfg_grid;
+        int deep_thr = env_grid > 0 ? env_thr : (int)cfg_threads, deep_u = env_grid > 0 ? env_u : (int)cfg_unroll;
+        if (deep_thr != 256 && deep_thr != 512) deep_thr = 512;
         const uint32_t want = nb_div_up(n4, 256);
         const uint32_t grid = want < (uint32_t)sms * per_sm ? want : (uint32_t)sms * per_sm;
         if (deep_grid > 0 && n4 > (uint64_t)deep_grid * deep_thr * 4) {

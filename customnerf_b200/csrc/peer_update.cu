@@ -198,9 +198,11 @@ int launch_peer(const nb200_peer_plan *pl, cudaStream_t st) {
     if (unroll_env < 0) { const char *e = getenv("NB200_PEER_UNROLL"); unroll_env = e ? atoi(e) : 0; }
     static int threads_env = -1;        // threads per CTA (tuning knob): a thin CTA leaves the SM's registers to a co-running kernel
     if (threads_env < 0) { const char *e = getenv("NB200_PEER_THREADS"); threads_env = e ? atoi(e) : 0; }
-    const int T = (threads_env == 64 || threads_env == 128 || threads_env == 512) ? threads_env : kPeerThreads;
+    const int want_t = threads_env > 0 ? threads_env : (int)pl->threads;
+    const int T = (want_t == 64 || want_t == 128 || want_t == 512) ? want_t : kPeerThreads;
     const bool mc = pl->mc_grads && pl->mc_params;
-    const int U = unroll_env > 0 ? unroll_env : (mc || W <= 2 ? 4 : W <= 4 ? 2 : 1);
+    const int want_u = unroll_env > 0 ? unroll_env : (int)pl->unroll;
+    const int U = want_u > 0 ? want_u : (mc || W <= 2 ? 4 : W <= 4 ? 2 : 1);
     if (mc) {
         if (U >= 4) k_peer_reduce_adam_bcast<W, 4, true><<<pl->grid, T, 0, st>>>(*pl);
         else if (U >= 2) k_peer_reduce_adam_bcast<W, 2, true><<<pl->grid, T, 0, st>>>(*pl);

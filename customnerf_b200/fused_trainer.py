@@ -62,9 +62,11 @@ class TrainPlan(C.Structure):
             "rays", "counter", "m_eff", "scratch",
             "xyzs", "dirs", "deltas", "sigma", "sigma_arg", "d_sigma", "d_rgba",
             "x_en", "rgba", "act", "d_x_en", "wg_scratch", "timer", "scaler"]
+    _tail = ["adam_grid", "adam_threads", "adam_unroll", "pad2"]
     _fields_ = ([(n, C.c_uint32) for n in _u32] + [(n, C.c_float) for n in _f32] + [(n, C.c_uint32) for n in _flags] +
                 [(n, C.c_uint64) for n in _u64] +
-                [(n, C.c_void_p) for n in _ptr0] + [(n, C.c_float) for n in _f32b] + [(n, C.c_void_p) for n in _ptr])
+                [(n, C.c_void_p) for n in _ptr0] + [(n, C.c_float) for n in _f32b] + [(n, C.c_void_p) for n in _ptr] +
+                [(n, C.c_uint32) for n in _tail])
 
 
 def flat_parameter_count(model):
@@ -102,7 +104,7 @@ class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
                  lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0,
-                 peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True):
+                 peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True, update_shape=(64, 512, 4)):
         if not model.cuda_ray:
             raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
@@ -150,6 +152,7 @@ class FusedTrainStep:
         self.fused_forward = bool(fused_forward) and model.pos_en.num_levels == 16
         self.kernels_per_step = KERNELS_PER_STEP - (1 if self.fused_forward else 0)
         self.pipeline_update = bool(pipeline_update)
+        self.update_shape = tuple(int(v) for v in update_shape) if update_shape else None   # (CTAs, threads, unroll) of the pipelined sweep
         self._pending_update = False
         self._side = None
         self.use_graph = use_graph
@@ -327,6 +330,12 @@ class FusedTrainStep:
         p.x_en, p.rgba, p.act, p.d_x_en = a(self.x_en), a(self.rgba), a(self.act), a(self.d_x_en)
         p.wg_scratch = a(self.wg_scratch)
         p.scaler = a(self.scaler)
+        # pipelined update: the Adam sweep runs beside the next step's ray march, as a NARROW grid -- 64 CTAs of 512 threads with
+        # 4 float4 groups of every vector in flight pull 3.9 TB/s from 64 SMs and leave the other 84 (and half of those 64)
+        # to the march.  Measured on B200 (profiles/r02n_adam_narrow_sweep.txt): 0.464 ms/step against 0.491 with the wide
+        # sweep (which the march cannot share an SM with); more than ~72 CTAs and the overlap collapses again.
+        if self.pipeline_update and self.update_shape is not None:
+            p.adam_grid, p.adam_threads, p.adam_unroll = self.update_shape
         assert C.sizeof(p) == int(self.lib.nb200_train_plan_bytes()), "nb200_train_plan layout mismatch"
         self.plan = p
 

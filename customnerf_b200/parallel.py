@@ -100,11 +100,11 @@ class _DevArray:
 
 class PeerPlan(_C.Structure):
     """mirror of nb200_peer_plan (include/nerf_b200.h)"""
-    _fields_ = [("world", _C.c_uint32), ("rank", _C.c_uint32), ("grid", _C.c_uint32), ("pad", _C.c_uint32),
+    _fields_ = [("world", _C.c_uint32), ("rank", _C.c_uint32), ("grid", _C.c_uint32), ("threads", _C.c_uint32),
                 ("n", _C.c_uint64), ("split", _C.c_uint64), ("params", _C.c_void_p * 8), ("grads", _C.c_void_p * 8),
                 ("signals", _C.c_void_p * 8), ("exp_avg", _C.c_void_p), ("exp_avg_sq", _C.c_void_p), ("hyper", _C.c_void_p),
                 ("epoch", _C.c_void_p), ("status", _C.c_void_p), ("mc_params", _C.c_void_p), ("mc_grads", _C.c_void_p),
-                ("scalers", _C.c_void_p * 8)]
+                ("unroll", _C.c_uint32), ("pad", _C.c_uint32), ("scalers", _C.c_void_p * 8)]
 
 
 class PeerMemory:
@@ -120,7 +120,12 @@ class PeerMemory:
     multicast mapping (multimem.ld_reduce / multimem.st: the sum happens inside the switch).  Raises when the fabric has
     no multicast support."""
 
-    def __init__(self, n_params, device, group=None, multicast=False):
+    def __init__(self, n_params, device, group=None, multicast=False, shape=(64, 512, 2)):
+        """shape = (CTAs, threads per CTA, float4 groups in flight per thread and rank) of the update kernel, or None for the
+        wide default (2 CTAs of 256 threads per SM).  The narrow default keeps the kernel on <= 64 SMs with deep loads: on its
+        own it is ~8 % slower than the wide grid (126 vs 117 us at 2 GPUs), but the next step's ray march then runs BESIDE it
+        (a wide grid and the march's single resident wave exclude each other): 0.483 vs 0.534 ms/step at 2 GPUs
+        (profiles/r02l_peer_narrow_2gpu.txt)."""
         import ctypes as C
         from . import _lib as L
         self.lib, self.C, self.L = L.lib(), C, L
@@ -140,6 +145,9 @@ class PeerMemory:
         lib.nb200_peer_plan_bytes.restype = C.c_uint32
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.grid = int(lib.nb200_peer_grid(C.c_uint64(self.n), C.c_uint32(self.world), C.c_uint32(sms)))
+        self.threads, self.unroll = 0, 0
+        if shape is not None and self.world > 1 and not os.environ.get("NB200_PEER_GRID"):
+            self.grid, self.threads, self.unroll = min(self.grid, int(shape[0])), int(shape[1]), int(shape[2])
         self.sig_off = 2 * self.n * 4
         # [params | grads | flag words | loss-scaler words (8 x 4 B, 64-byte slot)]: the peers read each other's found-inf flags
         self.scaler_off = self.sig_off + (int(lib.nb200_peer_signal_bytes(C.c_uint32(self.grid))) + 63) // 64 * 64
@@ -212,6 +220,7 @@ class PeerMemory:
         C = self.C
         p = PeerPlan()
         p.world, p.rank, p.grid, p.n, p.split = self.world, self.rank, self.grid, self.n, int(n_table_params)
+        p.threads, p.unroll = getattr(self, "threads", 0), getattr(self, "unroll", 0)
         for r, b in enumerate(self.bases):
             p.params[r], p.grads[r], p.signals[r] = b, b + 4 * self.n, b + self.sig_off
         p.exp_avg, p.exp_avg_sq, p.hyper = exp_avg.data_ptr(), exp_avg_sq.data_ptr(), hyper.data_ptr()

@@ -334,6 +334,11 @@ int nb200_fused_adam(float *param, float *grad, float *exp_avg, float *exp_avg_s
  * depends on host memory): sched f32[8] = {lr0 group 0, lr0 group 1, beta1, beta2, eps, grad_scale, decay_base,
  * decay_iters}; lr = lr0 * decay_base^min((t-1)/decay_iters, 1) (LambdaLR of main.py:189; decay_iters <= 0: constant). */
 int nb200_adam_hyper(int32_t *step, const float *sched, float *hyper, void *stream);
+/* nb200_fused_adam on an explicit launch shape: `grid` CTAs of `threads` (256 or 512) threads, `unroll` (1, 2 or 4) float4
+ * groups of every vector in flight per thread; grid == 0: the default wide sweep (8 CTAs of 256 threads per SM).  Few wide
+ * CTAs with deep loads pull most of the HBM stream from a fraction of the SMs and leave the rest to a concurrent kernel. */
+int nb200_fused_adam_cfg(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, uint64_t split,
+                         const float *hyper, int zero_grad, uint32_t grid, uint32_t threads, uint32_t unroll, void *stream);
 
 /* Dynamic loss scaling with skipped steps, on the device -- torch.cuda.amp.GradScaler as the reference trains with it
  * (nerf/utils_init_nerf.py:100,612-629: scale(loss).backward(); scaler.step(optimizer) skips the step when a gradient is
@@ -393,6 +398,10 @@ typedef struct nb200_train_plan {
     void *timer;                                                 /* nb200_stage_timer or NULL */
     uint32_t *scaler;                                            /* device-side dynamic loss scaler (8 words, see
                                                                     nb200_scaler_commit) or NULL: constant loss_scale */
+    uint32_t adam_grid, adam_threads, adam_unroll, pad2;         /* shape of the Adam sweep (nb200_fused_adam_cfg); all 0: the
+                                                                    wide default.  A pipelined trainer runs a NARROW sweep
+                                                                    (e.g. 64 CTAs x 512 threads x 4 groups in flight) so that the
+                                                                    next step's ray march overlaps it */
 } nb200_train_plan;
 
 /* ---- LGIE editing step (BASELINE.json configs[3]; reference: the fg / bg / all renders of NeRFRenderer.run,
@@ -478,8 +487,8 @@ int nb200_get_rays(const float *poses, float fx, float fy, float cx, float cy, u
 #define NB200_PEER_MAX 8
 typedef struct nb200_peer_plan {
     uint32_t world, rank;
-    uint32_t grid;                        /* CTAs: nb200_peer_grid(n, world, sms) -- identical on every rank */
-    uint32_t pad;
+    uint32_t grid;                        /* CTAs: nb200_peer_grid(n, world, sms) or fewer -- identical on every rank */
+    uint32_t threads;                     /* threads per CTA: 0 (= 256), 64, 128, 256 or 512 */
     uint64_t n, split;                    /* parameters; [0, split) hyper group 0, [split, n) group 1; both % 4 == 0 */
     float *params[NB200_PEER_MAX];        /* every rank's parameter vector  ([rank] local, the others imported) */
     float *grads[NB200_PEER_MAX];         /* every rank's gradient vector */
@@ -491,6 +500,7 @@ typedef struct nb200_peer_plan {
     float *mc_params, *mc_grads;          /* NVSwitch multicast mappings of the same two vectors (both or neither; NULL:
                                              plain peer loads / stores): multimem.ld_reduce sums the gradient inside the
                                              switch, multimem.st delivers the parameters to every replica */
+    uint32_t unroll, pad;                 /* float4 groups in flight per thread and rank: 0 (default by world size), 1, 2 or 4 */
     uint32_t *scalers[NB200_PEER_MAX];    /* every rank's loss-scaler words (nb200_scaler_commit), or all NULL: when given, the
                                              update is skipped on EVERY rank if any rank's found-inf flag of this iteration is up */
 } nb200_peer_plan;

@@ -186,3 +186,9 @@ def test_peer_plan_is_filled_from_the_mapped_bases():
     pm.mc_base = 0x7000000000
     q = pm.plan(600, m, v, h, status=torch.zeros(1, dtype=torch.int32))
     assert (q.mc_params, q.mc_grads) == (pm.mc_base, pm.mc_base + 4000) and q.status != p.status
+    # launch shape of the narrow update and the loss-scaler words of every rank
+    pm.threads, pm.unroll, pm.scaler_off = 512, 2, 9000
+    z = pm.plan(600, m, v, h, use_scaler=True)
+    assert (z.threads, z.unroll) == (512, 2)
+    assert [z.scalers[r] for r in range(4)] == [b + 9000 for b in pm.bases] and z.scalers[4] is None
+    assert p.scalers[0] is None and (p.threads, p.unroll) == (0, 0)
