@@ -142,6 +142,49 @@ def edit_case(rank, world, dev):
 
 
 
+def scaler_case(rank, world, dev):
+    """GradScaler semantics across ranks: a non-finite gradient on ONE rank skips the optimiser step on EVERY rank (the found-inf
+    bits travel through peer memory), the loss scale halves everywhere, the replicas stay bit-identical, the step count
+    stays; sample-buffer growth is a joint decision (every rank sees the same maximum sample count)"""
+    model = trainer.build_scene_model(dev, log2_hashmap_size=15, desired_resolution=512, seed=3)
+    o, d = syn.camera_rays(105, 142)
+    idx = parallel.shard_rays(4096, rank, world) + 5000
+    o, d = o[idx].contiguous().to(dev), d[idx].contiguous().to(dev)
+    tgt = syn.bear_color(o.cpu() + d.cpu() * 1.5).to(dev)
+    peer = parallel.PeerMemory(fused_trainer.flat_parameter_count(model), dev)
+    fs = fused_trainer.FusedTrainStep(model, o.shape[0], world_size=world, peer=peer, perturb=False, use_graph=True)
+    for _ in range(2):
+        fs.step(o, d, tgt)
+    fs.last_stats()
+    torch.cuda.synchronize(); dist.barrier()
+    assert fs.scaler_state() == (128.0, 0, 2), fs.scaler_state()
+    caps = [None] * world
+    dist.all_gather_object(caps, fs.m_cap)
+    assert len(set(caps)) == 1, "sample-buffer capacity differs across ranks: %r" % (caps,)
+    peak = [None] * world
+    dist.all_gather_object(peak, int(fs.stats_host[5]))
+    assert len(set(peak)) == 1 and peak[0] > 0, "the published maximum sample count differs across ranks: %r" % (peak,)
+    p0, m0 = fs.params_flat.clone(), fs.exp_avg.clone()
+    bad = tgt.clone()
+    if rank == world - 1:
+        bad[:, 1] = float("inf")                    # only the last rank's batch is poisoned
+    fs.step(o, d, bad)
+    fs.last_stats()
+    torch.cuda.synchronize(); dist.barrier()
+    assert fs.scaler_state() == (64.0, 1, 2), (rank, fs.scaler_state())
+    assert torch.equal(fs.params_flat, p0) and torch.equal(fs.exp_avg, m0), "rank %d took the step" % rank
+    assert float(fs.grads_flat.abs().max()) == 0.0
+    fs.step(o, d, tgt)
+    fs.last_stats()
+    torch.cuda.synchronize(); dist.barrier()
+    assert fs.scaler_state() == (64.0, 1, 3) and not torch.equal(fs.params_flat, p0)
+    mine = fs.params_flat.clone()
+    ref = mine.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(mine, ref) and torch.isfinite(mine).all(), "replicas diverged after the skipped step"
+    return fs, peer
+
+
 def main():
     rank, local_rank, world = parallel.init_from_env()
     dev = torch.device("cuda", local_rank)
@@ -156,6 +199,7 @@ def main():
         nvls = "unavailable"
     keep.append(train_case(rank, world, dev))
     keep.append(edit_case(rank, world, dev))
+    keep.append(scaler_case(rank, world, dev))
     dist.barrier()
     torch.cuda.synchronize()
     if rank == 0:
