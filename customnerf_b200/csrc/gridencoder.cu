@@ -28,7 +28,7 @@ namespace {
 
 
 // one thread per point; outputs [B, L*2].  TE = table storage type, T = value / output type.
-template <typename TE, typename T, bool kBatch = false>
+template <typename TE, typename T>
 __global__ void __launch_bounds__(256)
 k_grid_fwd_d3c2(const float *__restrict__ inputs, const TE *__restrict__ grid, const int32_t *__restrict__ offsets,
                 T *__restrict__ outputs, uint32_t B, uint32_t L, uint32_t max_level, float S, uint32_t H,
@@ -47,16 +47,6 @@ k_grid_fwd_d3c2(const float *__restrict__ inputs, const TE *__restrict__ grid, c
 
     for (uint32_t l0 = 0; l0 < max_level; l0 += 4) {
         float res[8];
-        if (kBatch && l0 + 4 <= max_level) {
-            // all 32 corner loads of four levels in flight at once (ge_gather4): fewer resident warps, 4 x the requests each
-            const bool dead = oob;
-            ge_gather4<TE, (sizeof(TE) == 4 && sizeof(T) == 2)>(info + l0, grid, dead ? 0.5f : x0, dead ? 0.5f : x1, dead ? 0.5f : x2,
-                                                                half_off, interp, res);
-            if (dead) {
-#pragma unroll
-                for (int q = 0; q < 8; q++) res[q] = 0.0f;
-            }
-        } else
 #pragma unroll
         for (uint32_t j = 0; j < 4; j++) {
             const uint32_t l = l0 + j;
@@ -151,11 +141,21 @@ k_grid_bwd_d3c2(const T *__restrict__ grad, const float *__restrict__ inputs, co
             }
         }
         if (emit) {
+            // the x-pair of corners is one aligned 16-byte word for half of all cells (grid_d3c2.cuh: ge_ld_pair): one
+            // RED.ADD.F32x4 instead of two F32x2 -- a quarter fewer L2 reductions per sample
             float *lg = grad_grid + (size_t)li.offset * 2;
 #pragma unroll
-            for (uint32_t idx = 0; idx < 8; idx++) {
-                const uint32_t row = ge_row_d3(li, c0 + (idx & 1u), c1 + ((idx >> 1) & 1u), c2 + ((idx >> 2) & 1u));
-                atomicAdd(reinterpret_cast<float2 *>(lg + (size_t)row * 2), v[idx]);
+            for (uint32_t pr = 0; pr < 4; pr++) {
+                const uint32_t ra = ge_row_d3(li, c0, c1 + (pr & 1u), c2 + (pr >> 1));
+                const uint32_t rb = ge_row_d3(li, c0 + 1u, c1 + (pr & 1u), c2 + (pr >> 1));
+                const float2 va = v[2 * pr], vb = v[2 * pr + 1];
+                if ((ra ^ rb) == 1u) {
+                    const float4 q = (ra & 1u) ? make_float4(vb.x, vb.y, va.x, va.y) : make_float4(va.x, va.y, vb.x, vb.y);
+                    atomicAdd(reinterpret_cast<float4 *>(lg + (size_t)(ra & ~1u) * 2), q);
+                } else {
+                    atomicAdd(reinterpret_cast<float2 *>(lg + (size_t)ra * 2), va);
+                    atomicAdd(reinterpret_cast<float2 *>(lg + (size_t)rb * 2), vb);
+                }
             }
         }
     }
@@ -344,12 +344,6 @@ int nb200_fs_encode_forward(const float *xyz, float bound, const float *table, c
     if (M_cap == 0 || L == 0) return 0;
     if (!xyz || !table || !offsets || !x_en || L > kMaxFastLevels || !(bound > 0.0f)) return NB200_E_BAD_ARG;
     const InXform xf{bound, 1.0f / (2.0f * bound), count_dev};
-    static int batch = -1;              // tuning knob: NB200_GE_FWD_BATCH=1 -> 32 loads in flight per thread (ge_gather4)
-    if (batch < 0) { const char *e = getenv("NB200_GE_FWD_BATCH"); batch = e ? atoi(e) : 0; }
-    if (batch)
-        k_grid_fwd_d3c2<float, __half, true><<<nb_div_up(M_cap, 256), 256, 0, nb_stream(stream)>>>(
-            xyz, table, offsets, (__half *)x_en, M_cap, L, L, S, H, gridtype, align_corners != 0, interp, xf);
-    else
     k_grid_fwd_d3c2<float, __half><<<nb_div_up(M_cap, 256), 256, 0, nb_stream(stream)>>>(
         xyz, table, offsets, (__half *)x_en, M_cap, L, L, S, H, gridtype, align_corners != 0, interp, xf);
     NB_LAUNCH_CHECK();
