@@ -104,7 +104,12 @@ int nb200_train_phase(const nb200_train_plan *p, int phases, void *stream) {
                                    p->H, p->M_cap, p->nears, p->fars, p->noises, p->rays, p->xyzs, p->dirs, p->deltas,
                                    p->m_eff, p->scratch, stream))) return rc;
 rest:
-    if (!(phases & NB200_PHASE_REST)) return 0;
+    if (phases & NB200_PHASE_REST_B) {      // split step, second scatter launch: the coarse levels
+        if ((rc = nb200_fs_encode_backward_levels(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
+                                                  p->base_res, p->gridtype, 0, 0, p->m_eff, 0, p->split_level, stream))) return rc;
+        return 0;
+    }
+    if (!(phases & (NB200_PHASE_REST | NB200_PHASE_REST_A))) return 0;
     if ((e = cudaMemsetAsync(p->loss, 0, sizeof(float), st)) != cudaSuccess) return (int)e;
     tick(ev, k++, st);
     if ((rc = fs_encode_field_forward(p, stream, ev, &k))) return rc;
@@ -120,8 +125,9 @@ rest:
     if ((rc = nb200_field_backward(p->d_sigma, p->d_rgba, p->sigma_arg, p->rgba, p->x_en, p->dirs, p->act, p->w_bwd,
                                    p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, p->scaler, stream))) return rc;
     tick(ev, k++, st);
-    if ((rc = nb200_fs_encode_backward(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
-                                       p->base_res, p->gridtype, 0, 0, p->m_eff, stream))) return rc;
+    if ((rc = nb200_fs_encode_backward_levels(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
+                                              p->base_res, p->gridtype, 0, 0, p->m_eff,
+                                              (phases & NB200_PHASE_REST_A) ? p->split_level : 0, p->L, stream))) return rc;
     tick(ev, k++, st);
     // the step's sample count, parked where the (possibly concurrent: pipelined update next to the NEXT step's march, which
     // resets the counter) update reads it for the status word of the loss scaler
@@ -219,6 +225,32 @@ int nb200_train_update_peer(const nb200_train_plan *p, const nb200_peer_plan *pe
     } else if ((rc = nb200_field_pack_weights(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, stream))) return rc;
     tick(ev, 2, st);
     if (tm) tm->up_done = true;
+    return 0;
+}
+
+int nb200_train_update_peer_part(const nb200_train_plan *p, const nb200_peer_plan *peer, int part, void *stream) {
+    if (!p || !peer || (part != 1 && part != 2) || p->split_level == 0 || p->split_elem == 0 || p->split_elem >= p->n_table_params ||
+        (p->split_elem & 3u)) return NB200_E_BAD_ARG;
+    if (peer->n != p->n_params || peer->split != p->n_table_params || peer->params[peer->rank] != p->params_flat ||
+        peer->grads[peer->rank] != p->grads_flat) return NB200_E_BAD_ARG;
+    const bool scaled = p->scaler != nullptr;
+    if (scaled && peer->scalers[peer->rank] != p->scaler) return NB200_E_BAD_ARG;
+    int rc;
+    const uint64_t e0 = part == 1 ? p->split_elem : 0, e1 = part == 1 ? p->n_params : p->split_elem;
+    if (part == 1 && !(p->flags & NB200_PLAN_HYPER_DONE) && (rc = nb200_train_update_hyper(p, 1, stream))) return rc;
+    nb200_peer_plan sub = *peer;            // the same kernel on a sub-range: rank r owns the r-th 1/world of [e0, e1)
+    for (uint32_t q = 0; q < peer->world; q++) { sub.params[q] += e0; sub.grads[q] += e0; }
+    sub.exp_avg += e0; sub.exp_avg_sq += e0;
+    if (sub.mc_params) { sub.mc_params += e0; sub.mc_grads += e0; }
+    sub.n = e1 - e0;
+    sub.split = p->n_table_params > e0 ? (p->n_table_params - e0 < sub.n ? p->n_table_params - e0 : sub.n) : 0;
+    if ((rc = nb200_peer_reduce_adam_bcast(&sub, stream))) return rc;
+    if (part == 2) {
+        if (scaled) {
+            if ((rc = nb200_field_pack_weights_commit(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, p->step, p->scaler,
+                                                      peer->scalers, peer->world, p->counter + 5, stream))) return rc;
+        } else if ((rc = nb200_field_pack_weights(p->trunk, p->density, p->rgb, p->w_fwd, p->w_bwd, stream))) return rc;
+    }
     return 0;
 }
 

@@ -22,6 +22,8 @@ constexpr uint32_t P1 = 2654435761u, P2 = 805459861u;
 struct InXform {
     float add, mul;                 // mul == 0: identity (inputs are already in [0, 1])
     const int32_t *count_dev;       // when non-null only rows < min(B, *count_dev) are processed
+    uint32_t level_begin = 0;       // scatter only: levels [level_begin, max_level) (the ray-sharded step scatters the table in two
+                                    // launches so that the update of the first part runs beside the second launch)
     __device__ __forceinline__ float operator()(float x) const { return mul != 0.0f ? __fmul_rn(__fadd_rn(x, add), mul) : x; }
 };
 
@@ -77,22 +79,6 @@ __device__ __forceinline__ float2 ge_ld2_round_half(const float *p) {
 }
 
 
-// The two corners of a cell that differ in x only sit in rows r and r ^ 1 for half of all cells: on a hashed level the x
-// coordinate enters the hash with prime 1, so for even x the neighbour's row is the same hash with bit 0 flipped; on a dense
-// level the rows are r and r + 1.  Such a pair is one aligned 16-byte word of the fp32 table: ONE load (or ONE four-float
-// reduction in the scatter) instead of two -- a quarter fewer memory requests per sample, same values, same arithmetic.
-__device__ __forceinline__ void ge_ld_pair(const float *lg, uint32_t r0, uint32_t r1, bool round_half, float2 &a, float2 &b) {
-    const float4 q = __ldg(reinterpret_cast<const float4 *>(lg + (size_t)(r0 & ~1u) * 2));
-    const bool odd = r0 & 1u;
-    a = odd ? make_float2(q.z, q.w) : make_float2(q.x, q.y);
-    if ((r0 ^ r1) == 1u) b = odd ? make_float2(q.x, q.y) : make_float2(q.z, q.w);
-    else b = __ldg(reinterpret_cast<const float2 *>(lg + (size_t)r1 * 2));
-    if (round_half) {
-        a = __half22float2(__float22half2_rn(a));
-        b = __half22float2(__float22half2_rn(b));
-    }
-}
-
 // the 8 corners of level `li` around x (already in [0, 1]^3): r0, r1 = the two interpolated features (fp32 accumulation in
 // corner order 0..7, weights multiplied x, y, z -- gridencoder.cu:166-187).  kRoundHalf: fp32 table entries are rounded
 // to fp16 as they are loaded (the autocast path of grid.py:45-46 without the table copy).
@@ -105,19 +91,11 @@ __device__ __forceinline__ void ge_level_gather(const LevelInfo &li, const TE *_
     if (interp == 1) { p0 = ge_smoothstep(p0); p1 = ge_smoothstep(p1); p2 = ge_smoothstep(p2); }
     const TE *lg = grid + (size_t)li.offset * 2;
     float2 v[8];
-    if constexpr (sizeof(TE) == 4) {
 #pragma unroll
-        for (uint32_t pr = 0; pr < 4; pr++) {
-            const uint32_t ra = ge_row_d3(li, g0, g1 + (pr & 1u), g2 + (pr >> 1));
-            const uint32_t rb = ge_row_d3(li, g0 + 1u, g1 + (pr & 1u), g2 + (pr >> 1));
-            ge_ld_pair(reinterpret_cast<const float *>(lg), ra, rb, kRoundHalf, v[2 * pr], v[2 * pr + 1]);
-        }
-    } else {
-#pragma unroll
-        for (uint32_t idx = 0; idx < 8; idx++) {
-            const uint32_t row = ge_row_d3(li, g0 + (idx & 1u), g1 + ((idx >> 1) & 1u), g2 + ((idx >> 2) & 1u));
-            v[idx] = ge_ld2(lg + (size_t)row * 2);
-        }
+    for (uint32_t idx = 0; idx < 8; idx++) {
+        const uint32_t row = ge_row_d3(li, g0 + (idx & 1u), g1 + ((idx >> 1) & 1u), g2 + ((idx >> 2) & 1u));
+        if constexpr (kRoundHalf) v[idx] = ge_ld2_round_half(lg + (size_t)row * 2);
+        else v[idx] = ge_ld2(lg + (size_t)row * 2);
     }
     r0 = 0.0f; r1 = 0.0f;
 #pragma unroll
@@ -148,10 +126,8 @@ __device__ __forceinline__ uint32_t ge_row_d3_compact(const LevelInfo &li, uint3
 template <typename TE, bool kRoundHalf>
 __device__ __forceinline__ void ge_gather4(const LevelInfo *__restrict__ info4, const TE *__restrict__ grid, float x0, float x1,
                                            float x2, float half_off, uint32_t interp, float (&res)[8]) {
-    static_assert(sizeof(TE) == 4, "ge_gather4 reads the fp32 master table");
     float p[4][3];
-    const float *lgs[4];
-    uint32_t rows[4][8];
+    const TE *src[4][8];
 #pragma unroll
     for (uint32_t j = 0; j < 4; j++) {
         const LevelInfo li = info4[j];
@@ -160,17 +136,19 @@ __device__ __forceinline__ void ge_gather4(const LevelInfo *__restrict__ info4, 
         p0 -= (float)g0; p1 -= (float)g1; p2 -= (float)g2;
         if (interp == 1) { p0 = ge_smoothstep(p0); p1 = ge_smoothstep(p1); p2 = ge_smoothstep(p2); }
         p[j][0] = p0; p[j][1] = p1; p[j][2] = p2;
-        lgs[j] = reinterpret_cast<const float *>(grid) + (size_t)li.offset * 2;
+        const TE *lg = grid + (size_t)li.offset * 2;
 #pragma unroll
         for (uint32_t idx = 0; idx < 8; idx++)
-            rows[j][idx] = ge_row_d3_compact(li, g0 + (idx & 1u), g1 + ((idx >> 1) & 1u), g2 + ((idx >> 2) & 1u));
+            src[j][idx] = lg + (size_t)ge_row_d3_compact(li, g0 + (idx & 1u), g1 + ((idx >> 1) & 1u), g2 + ((idx >> 2) & 1u)) * 2;
     }
     float2 v[4][8];
 #pragma unroll
     for (uint32_t j = 0; j < 4; j++) {
 #pragma unroll
-        for (uint32_t pr = 0; pr < 4; pr++)
-            ge_ld_pair(lgs[j], rows[j][2 * pr], rows[j][2 * pr + 1], kRoundHalf, v[j][2 * pr], v[j][2 * pr + 1]);
+        for (uint32_t idx = 0; idx < 8; idx++) {
+            if constexpr (kRoundHalf) v[j][idx] = ge_ld2_round_half(src[j][idx]);
+            else v[j][idx] = ge_ld2(src[j][idx]);
+        }
     }
 #pragma unroll
     for (uint32_t j = 0; j < 4; j++) {

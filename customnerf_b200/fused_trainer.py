@@ -62,11 +62,11 @@ class TrainPlan(C.Structure):
             "rays", "counter", "m_eff", "scratch",
             "xyzs", "dirs", "deltas", "sigma", "sigma_arg", "d_sigma", "d_rgba",
             "x_en", "rgba", "act", "d_x_en", "wg_scratch", "timer", "scaler"]
-    _tail = ["adam_grid", "adam_threads", "adam_unroll", "pad2"]
+    _tail = ["adam_grid", "adam_threads", "adam_unroll", "split_level"]
     _fields_ = ([(n, C.c_uint32) for n in _u32] + [(n, C.c_float) for n in _f32] + [(n, C.c_uint32) for n in _flags] +
                 [(n, C.c_uint64) for n in _u64] +
                 [(n, C.c_void_p) for n in _ptr0] + [(n, C.c_float) for n in _f32b] + [(n, C.c_void_p) for n in _ptr] +
-                [(n, C.c_uint32) for n in _tail])
+                [(n, C.c_uint32) for n in _tail] + [("split_elem", C.c_uint64)])
 
 
 def flat_parameter_count(model):
@@ -104,7 +104,7 @@ class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
                  lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0,
-                 peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True, update_shape=(64, 512, 4)):
+                 peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True, update_shape=(64, 512, 4), split_level=10):
         if not model.cuda_ray:
             raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
@@ -153,6 +153,16 @@ class FusedTrainStep:
         self.kernels_per_step = KERNELS_PER_STEP - (1 if self.fused_forward else 0)
         self.pipeline_update = bool(pipeline_update)
         self.update_shape = tuple(int(v) for v in update_shape) if update_shape else None   # (CTAs, threads, unroll) of the pipelined sweep
+        # split update (ray-sharded, peer-memory update, pipelined): the table gradient is scattered in two launches -- levels
+        # [split_level, 16) first -- and the NVLink update of those levels (+ the MLPs; ~half of the bytes) runs beside the second
+        # scatter launch; the update of the coarse levels runs beside the next step's ray march.  Within each part rank r owns
+        # the r-th 1/world of the part's element range (update_ranges).
+        import os
+        self.split_level = int(os.environ.get("NB200_SPLIT_LEVEL", split_level or 0))
+        if peer is None or peer.world < 2 or not pipeline_update or not (0 < self.split_level < model.pos_en.num_levels):
+            self.split_level = 0
+        if self.split_level:
+            self.kernels_per_step += 2      # a second scatter launch and a second peer-update launch
         self._pending_update = False
         self._side = None
         self.use_graph = use_graph
@@ -336,6 +346,12 @@ class FusedTrainStep:
         # sweep (which the march cannot share an SM with); more than ~72 CTAs and the overlap collapses again.
         if self.pipeline_update and self.update_shape is not None:
             p.adam_grid, p.adam_threads, p.adam_unroll = self.update_shape
+        n = self.params_flat.numel()
+        self.update_ranges = [(0, n)]
+        if self.split_level:
+            p.split_level = self.split_level
+            p.split_elem = 2 * int(enc.offsets[self.split_level])
+            self.update_ranges = [(int(p.split_elem), n), (0, int(p.split_elem))]
         assert C.sizeof(p) == int(self.lib.nb200_train_plan_bytes()), "nb200_train_plan layout mismatch"
         self.plan = p
 
@@ -432,6 +448,10 @@ class FusedTrainStep:
             self._pipelined_allreduce_update(st)
         else:
             if self.peer_plan is not None:
+                if self.split_level:
+                    self._update_part(1, st)
+                    self._update_part(2, st)
+                    return
                 _check(self.lib.nb200_train_update_peer(C.byref(self.plan), C.byref(self.peer_plan), st), "train_update_peer")
                 return
             if self.grad_sync is not None:
@@ -442,6 +462,38 @@ class FusedTrainStep:
                     dist.all_reduce(self.scaler[4:6], op=dist.ReduceOp.MAX, group=self.process_group)
             _check(self.lib.nb200_train_update(C.byref(self.plan), st), "train_update")
 
+    def _update_part(self, part, st):
+        _check(self.lib.nb200_train_update_peer_part(C.byref(self.plan), C.byref(self.peer_plan), C.c_int(part), st),
+               "train_update_peer_part")
+
+    def _launch_split(self, staged, st):
+        """one step of the split, pipelined, ray-sharded form:
+              [update part 2 of the step before (coarse levels) + weight re-pack + commit]  ||  [march]
+              encode .. field^T, scatter of the fine levels, hyper kernel
+              [update part 1 (fine levels + MLPs)]  ||  [scatter of the coarse levels]
+        the update's kernels on the high-priority side stream (narrow grids: they run beside the main stream's kernels)"""
+        main = torch.cuda.current_stream(self.dev)
+        if self._side is None:
+            import os
+            prio = -1 if os.environ.get("NB200_SIDE_PRIORITY", "1") == "1" else 0
+            self._side = torch.cuda.Stream(device=self.dev, priority=prio)
+            self._apply_l2_window(self._side)
+        side = self._side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._update_part(2, L.stream())
+        _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(1), st), "train_phase(march)")
+        main.wait_stream(side)
+        _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(4), st), "train_phase(rest A)")
+        _check(self.lib.nb200_train_update_hyper(C.byref(self.plan), C.c_int(1), st), "train_update_hyper")
+        self.plan.flags |= 2
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._update_part(1, L.stream())
+        self.plan.flags &= ~2
+        _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(8), st), "train_phase(rest B)")
+        main.wait_stream(side)
+
     def _launch(self, staged=False):
         """every device-side action of one step, on the current stream (this is what the graph captures)"""
         st = L.stream()
@@ -451,6 +503,8 @@ class FusedTrainStep:
         if not self.pipeline_update:
             _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), st), "train_forward_backward")
             self._update(st)
+        elif self.split_level:
+            self._launch_split(staged, st)
         else:
             # [update of the previous step] on the side stream  ||  [march of this step] here, then join
             main = torch.cuda.current_stream(self.dev)
@@ -490,7 +544,10 @@ class FusedTrainStep:
         """pipeline_update: apply the update of the last step() now, so that the parameters are current"""
         if self.pipeline_update and self._pending_update:
             with torch.cuda.device(self.dev):
-                self._update(L.stream())
+                if self.split_level and self._pending_update == "part2":
+                    self._update_part(2, L.stream())        # part 1 ran inside the step
+                else:
+                    self._update(L.stream())
             self._pending_update = False
 
     def _pipelined_allreduce_update(self, st):
@@ -643,6 +700,9 @@ class FusedTrainStep:
             _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
             self.stats_host.copy_(self.stats, non_blocking=True)
             self._pending_update = True
+            if self.split_level:            # the split form always enters a step with part 2 of the step before outstanding
+                self._update_part(1, L.stream())
+                self._pending_update = "part2"
             L.LAUNCHES += self.kernels_per_step - 4
             return
         if self.use_graph and self.graphs.get(staged) is None:
@@ -710,8 +770,9 @@ class FusedTrainStep:
         if self.peer is not None and self.peer.world > 1:
             from . import parallel
             m, v = m.clone(), v.clone()
-            parallel.gather_owned_slices(m, self.peer.world, self.peer.rank, self.peer.group)
-            parallel.gather_owned_slices(v, self.peer.world, self.peer.rank, self.peer.group)
+            for a, b in self.update_ranges:          # rank r owns the r-th 1/world of every update range
+                parallel.gather_owned_slices(m[a:b], self.peer.world, self.peer.rank, self.peer.group)
+                parallel.gather_owned_slices(v[a:b], self.peer.world, self.peer.rank, self.peer.group)
         t = float(int(self.step_count))
         params = dict(self.model.named_parameters())
         state, groups = {}, []

@@ -299,6 +299,11 @@ int nb200_fs_encode_forward(const float *xyz, float bound, const float *table, c
 int nb200_fs_encode_backward(const void *d_x_en, const float *xyz, float bound, const int32_t *offsets, float *grad_table,
                              uint32_t M_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
                              uint32_t interp, const int32_t *count_dev, void *stream);
+/* the same scatter for levels [level_begin, level_end) only (the ray-sharded step scatters in two launches, NB200_PLAN_SPLIT) */
+int nb200_fs_encode_backward_levels(const void *d_x_en, const float *xyz, float bound, const int32_t *offsets, float *grad_table,
+                                    uint32_t M_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                    uint32_t interp, const int32_t *count_dev, uint32_t level_begin, uint32_t level_end,
+                                    void *stream);
 /* composite_rays_train forward / backward reading the field kernel's rgba f16 [M,4] rows directly (the reference
  * slices [..., :3] and casts to float, renderer.py:510,635) and writing grad_rgba as float4 rows [g_r, g_g, g_b, 0]. */
 int nb200_fs_composite_forward(const float *sigmas, const void *rgba, const float *deltas, const int32_t *rays,
@@ -398,10 +403,16 @@ typedef struct nb200_train_plan {
     void *timer;                                                 /* nb200_stage_timer or NULL */
     uint32_t *scaler;                                            /* device-side dynamic loss scaler (8 words, see
                                                                     nb200_scaler_commit) or NULL: constant loss_scale */
-    uint32_t adam_grid, adam_threads, adam_unroll, pad2;         /* shape of the Adam sweep (nb200_fused_adam_cfg); all 0: the
+    uint32_t adam_grid, adam_threads, adam_unroll, split_level;         /* shape of the Adam sweep (nb200_fused_adam_cfg); all 0: the
                                                                     wide default.  A pipelined trainer runs a NARROW sweep
                                                                     (e.g. 64 CTAs x 512 threads x 4 groups in flight) so that the
                                                                     next step's ray march overlaps it */
+    uint64_t split_elem;                                         /* split_level > 0 (ray-sharded step): the table gradient is
+                                                                    scattered in two launches -- levels [split_level, L) first,
+                                                                    then [0, split_level) -- and the peer-memory update in two
+                                                                    parts: elements [split_elem, n) (= 2 * offsets[split_level]:
+                                                                    the fine levels and the MLPs) while the second scatter
+                                                                    launch still runs, then [0, split_elem) */
 } nb200_train_plan;
 
 /* ---- LGIE editing step (BASELINE.json configs[3]; reference: the fg / bg / all renders of NeRFRenderer.run,
@@ -456,6 +467,8 @@ int nb200_train_forward_backward(const nb200_train_plan *plan, void *stream);
  * nb200_train_update (a memory-bound sweep next to an issue-bound traversal); NB200_PHASE_REST is encode .. encode^T. */
 #define NB200_PHASE_MARCH 1
 #define NB200_PHASE_REST  2
+#define NB200_PHASE_REST_A 4   /* split step: encode .. field^T and the scatter of levels [split_level, L) */
+#define NB200_PHASE_REST_B 8   /* split step: the scatter of levels [0, split_level) */
 int nb200_train_phase(const nb200_train_plan *plan, int phases, void *stream);
 /* fused Adam over params_flat (zeroing grads_flat) and re-pack of the MLP operand images. */
 int nb200_train_update(const nb200_train_plan *plan, void *stream);
@@ -523,6 +536,10 @@ int nb200_peer_reduce_adam_bcast(const nb200_peer_plan *plan, void *stream);
 int nb200_peer_rank_barrier(const nb200_peer_plan *plan, void *stream);
 /* nb200_train_update with the Adam sweep replaced by nb200_peer_reduce_adam_bcast. */
 int nb200_train_update_peer(const nb200_train_plan *plan, const nb200_peer_plan *peer, void *stream);
+/* The same in two parts (plan->split_level > 0): part 1 = hyper kernel (unless NB200_PLAN_HYPER_DONE) + reduce / Adam /
+ * broadcast of elements [split_elem, n); part 2 = elements [0, split_elem) + weight re-pack (+ scaler commit).  Within
+ * each part rank r owns the r-th 1/world of that part's range.  Every rank must call both parts, in this order. */
+int nb200_train_update_peer_part(const nb200_train_plan *plan, const nb200_peer_plan *peer, int part, void *stream);
 
 /* L2 bandwidth probes (measurement aid, no reference counterpart): MEASURED_PEAKS.json carries no L2 figure, so bench.py
  * measures (a) a coalesced float4 stream over an L2-resident buffer and (b) random 8-byte gathers (one 32-byte sector

@@ -154,6 +154,16 @@ def _gather_worker(rank, world, port, out_dir):
         vec[lo:hi] = full[lo:hi]                 # every rank holds only what it owns
         parallel.gather_owned_slices(vec, world, rank)
         assert torch.equal(vec, full), (n, rank)
+    # the split update (FusedTrainStep.update_ranges): rank r owns the r-th 1/world of EVERY range; views are gathered in place
+    n, cut = 2072, 1040
+    full = torch.arange(n, dtype=torch.float32) + 1
+    vec = torch.zeros(n)
+    for a, b in ((cut, n), (0, cut)):
+        lo, hi = parallel.peer_slice(b - a, world, rank)
+        vec[a + lo:a + hi] = full[a + lo:a + hi]
+    for a, b in ((cut, n), (0, cut)):
+        parallel.gather_owned_slices(vec[a:b], world, rank)
+    assert torch.equal(vec, full), rank
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     dist.destroy_process_group()
 
