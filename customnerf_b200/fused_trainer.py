@@ -104,11 +104,14 @@ class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
                  lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0,
-                 peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True, update_shape=(64, 512, 4), split_level=10):
+                 peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True, update_shape=(64, 512, 4), split_level=0):
         if not model.cuda_ray:
             raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
             raise RuntimeError("FusedTrainStep needs the reference field shape (D=3, 16 levels x 2 features)")
+        if getattr(model, "two_heads", False):
+            raise RuntimeError("FusedTrainStep covers the single colour + mask head; the two-head RGB_network "
+                               "(--detach_mask_from_field / --mask_no_dir) trains through trainer.TrainStep")
         self.model = model
         self.lib = L.lib()
         self.dev = model.pos_en.embeddings.device
@@ -153,7 +156,8 @@ class FusedTrainStep:
         self.kernels_per_step = KERNELS_PER_STEP - (1 if self.fused_forward else 0)
         self.pipeline_update = bool(pipeline_update)
         self.update_shape = tuple(int(v) for v in update_shape) if update_shape else None   # (CTAs, threads, unroll) of the pipelined sweep
-        # split update (ray-sharded, peer-memory update, pipelined): the table gradient is scattered in two launches -- levels
+        # split update (ray-sharded, peer-memory update, pipelined; OFF by default, split_level=10 or NB200_SPLIT_LEVEL=10 turns it
+        # on -- measured at 2 GPUs it costs more than it hides: 0.508 vs 0.459 ms/step, profiles/README.md): the table gradient is scattered in two launches -- levels
         # [split_level, 16) first -- and the NVLink update of those levels (+ the MLPs; ~half of the bytes) runs beside the second
         # scatter launch; the update of the coarse levels runs beside the next step's ray march.  Within each part rank r owns
         # the r-th 1/world of the part's element range (update_ranges).
@@ -573,7 +577,8 @@ class FusedTrainStep:
     def _capture(self, staged=False):
         """warm up on a side stream (first-call cudaFuncSetAttribute, allocator, RNG registration), capture one step,
         then restore the optimiser state the warm-up steps advanced"""
-        state = (self.params_flat, self.exp_avg, self.exp_avg_sq, self.step_count) + (() if self.scaler is None else (self.scaler,))
+        # (hyper too: in the split form the second half of an update uses the hyper-parameters its first half computed one launch earlier)
+        state = (self.params_flat, self.exp_avg, self.exp_avg_sq, self.step_count, self.hyper) + (() if self.scaler is None else (self.scaler,))
         if self.pipeline_update:            # the gradient of the step before is still waiting for its update: keep it
             state = state + (self.grads_flat,)
         keep = [t.clone() for t in state]

@@ -61,6 +61,35 @@ def _mlp_cfg(out_act, n_hidden):
             "n_hidden_layers": n_hidden}
 
 
+class RGB_network(nn.Module):
+    """The two-head colour network of --detach_mask_from_field / --mask_no_dir (nerf/network_grid.py:13-68): a colour MLP
+    [view_en | fea] -> 3 and a separate confidence (mask) MLP that must not train the field -- fed the DETACHED input, or,
+    with mask_no_dir, the (detached unless mask_no_dir_nodetach) field features alone.  Output [rgb(3) | conf].  Same
+    sub-module names as the reference (state-dict keys rgb_network.rgb_network.params / rgb_network.conf_network.params).
+    Runs on the per-layer library path: the fused tcgen05 field kernel covers the single 3+1 head only."""
+
+    def __init__(self, input_ch_views, opt=None):
+        super().__init__()
+        self.opt = opt
+        self.mask_no_dir = bool(getattr(opt, 'mask_no_dir', False))
+        self.rgb_network = Network(input_ch_views + 64, 3, _mlp_cfg("Sigmoid", 1), seed=1339)
+        if self.mask_no_dir:
+            self.conf_network = Network(64, 1, _mlp_cfg("Sigmoid", 1), seed=1340)
+        else:
+            ndim = 1 if getattr(opt, 'keyword2', None) is None else 2       # opt.keyword2 is undefined in main.py (Appendix B6)
+            self.conf_network = Network(input_ch_views + 64, ndim, _mlp_cfg("Sigmoid", 1), seed=1340)
+        self.n_output_dims = 3 + self.conf_network.n_output_dims
+
+    def forward(self, x):
+        rgb = self.rgb_network(x)
+        if self.mask_no_dir:
+            fea = x[..., x.shape[-1] - 64:]
+            conf = self.conf_network(fea if getattr(self.opt, 'mask_no_dir_nodetach', False) else fea.detach())
+        else:
+            conf = self.conf_network(x.detach())
+        return torch.cat([rgb, conf], dim=-1)
+
+
 class NeRFNetwork(NeRFRenderer):
     def __init__(self, opt, encoding='tiledgrid', log2_hashmap_size=21, desired_resolution=8192, **unused):
         """Defaults are the reference's hard-coded grid (network_grid.py:89-96); BASELINE.json's configs use
@@ -72,11 +101,16 @@ class NeRFNetwork(NeRFRenderer):
         self.density_network = Network(64, 1, _mlp_cfg("None", 1), seed=1338)
         self.input_ch_views = 27
         n_out = 3 + (1 if getattr(opt, 'train_conf', 0) else 0)
-        self.rgb_network = Network(self.input_ch_views + 64, n_out, _mlp_cfg("Sigmoid", 1), seed=1339)
+        self.two_heads = bool(getattr(opt, 'train_conf', 0) and (getattr(opt, 'detach_mask_from_field', False)
+                                                                   or getattr(opt, 'mask_no_dir', False)))
+        if self.two_heads:              # network_grid.py:117-118
+            self.rgb_network = RGB_network(self.input_ch_views, opt=opt)
+        else:
+            self.rgb_network = Network(self.input_ch_views + 64, n_out, _mlp_cfg("Sigmoid", 1), seed=1339)
         self.bg_net = None
         # one fused tcgen05 kernel for trunk + heads when the shapes are the reference's (32 -> 64 ... -> 1 | 3(+1));
         # the per-layer library path (mlp.Network.forward) stays available through use_fused_field = False
-        self.use_fused_field = self.pos_en_dim == 32
+        self.use_fused_field = self.pos_en_dim == 32 and not self.two_heads
         self._packed = _PackedWeights()
         # under autocast the grid gather runs inside the field kernel (no [M,32] feature tensor in HBM); False keeps the
         # encoder and the field network as two launches (tests compare the two)

@@ -112,6 +112,31 @@ def main():
         G["ori_bg_runs_in_reference"] = np.int64(1)
     except RuntimeError:
         G["ori_bg_runs_in_reference"] = np.int64(0)
+    # ---- RGB_network (nerf/network_grid.py:13-68): separate colour and confidence heads, the confidence head fed DETACHED
+    #      inputs (--detach_mask_from_field) or the detached field features only (--mask_no_dir); tcnn.Network served by the
+    #      oracle MLP (what is pinned is the wiring: which inputs, which detach, output order, parameter names)
+    from oracle import torch_ref
+    tc = types.ModuleType("tinycudann")
+    tc.Network = torch_ref.Network
+    sys.modules["tinycudann"] = tc
+    ng = importlib.import_module("nerf.network_grid")
+    xin = torch.from_numpy(rng.uniform(-1, 1, (40, 91)).astype(np.float32))
+    G["rgbnet_x"] = xin.numpy()
+    for tag, o in (("detach", dict(mask_no_dir=False, keyword2=None, mask_no_dir_nodetach=False)),
+                   ("nodir", dict(mask_no_dir=True, keyword2=None, mask_no_dir_nodetach=False)),
+                   ("nodir_nodetach", dict(mask_no_dir=True, keyword2=None, mask_no_dir_nodetach=True))):
+        net = ng.RGB_network(27, opt=types.SimpleNamespace(**o))
+        for name in ("rgb_network", "conf_network"):
+            m = getattr(net, name)
+            w = (rng.uniform(-1, 1, m.params.numel()) * 0.4).astype(np.float32)
+            m.params.data.copy_(torch.from_numpy(w))
+            G["rgbnet_%s_%s" % (tag, name)] = w
+        x = xin.clone().requires_grad_()
+        y = net(x)
+        G["rgbnet_%s_out" % tag] = y.detach().numpy()
+        y[:, 3:].sum().backward()
+        G["rgbnet_%s_grad_x_from_conf" % tag] = x.grad.numpy().copy()
+        G["rgbnet_%s_keys" % tag] = np.array(sorted(net.state_dict().keys()))
     np.savez_compressed(os.path.join(HERE, "ref_trainer.npz"), **G)
     print("wrote ref_trainer.npz", {k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in G.items() if "loss" in k or "calls" in k})
 

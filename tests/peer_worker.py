@@ -65,11 +65,12 @@ def adam_case(rank, world, dev, multicast=False):
 
 
 def train_case(rank, world, dev):
-    """sharded FusedTrainStep: peer update vs NCCL all-reduce, same rays, no perturbation"""
+    """sharded FusedTrainStep: peer update (also in its split form: two scatter launches, two update parts) vs NCCL all-reduce,
+    same rays, no perturbation"""
     losses = {}
     finals = {}
     keep = []
-    for mode in ("nccl", "peer"):
+    for mode in ("nccl", "peer", "peer_split"):
         model = trainer.build_scene_model(dev, log2_hashmap_size=15, desired_resolution=512, seed=3)
         with torch.no_grad():
             g = torch.Generator(device=dev).manual_seed(11)
@@ -78,10 +79,12 @@ def train_case(rank, world, dev):
         idx = parallel.shard_rays(4096, rank, world) + 5000
         o, d = o[idx].contiguous().to(dev), d[idx].contiguous().to(dev)
         tgt = syn.bear_color(o.cpu() + d.cpu() * 1.5).to(dev)
-        peer = parallel.PeerMemory(fused_trainer.flat_parameter_count(model), dev) if mode == "peer" else None
+        peer = parallel.PeerMemory(fused_trainer.flat_parameter_count(model), dev) if mode != "nccl" else None
         sync = (lambda flat: dist.all_reduce(flat)) if mode == "nccl" else None
         fs = fused_trainer.FusedTrainStep(model, o.shape[0], world_size=world, grad_sync=sync, peer=peer, perturb=False,
-                                          use_graph=True, pipeline_update=(mode == "peer"))
+                                          use_graph=True, pipeline_update=(mode != "nccl"),
+                                          split_level=10 if mode == "peer_split" else 0)
+        assert bool(fs.split_level) == (mode == "peer_split")
         ls = []
         for it in range(6):
             fs.step(o, d, tgt)
@@ -92,14 +95,15 @@ def train_case(rank, world, dev):
         losses[mode] = ls
         finals[mode] = fs.params_flat.clone()
         keep.append((fs, peer))
-    a, b = np.array(losses["nccl"]), np.array(losses["peer"])
-    # the gradients come from fp32 atomics whose order differs run to run: losses agree to rel 1e-4 over 6 steps
-    np.testing.assert_allclose(b, a, rtol=1e-4)
+    a = np.array(losses["nccl"])
     assert a[-1] < a[0], "training did not reduce the loss"
-    # Adam moves every touched parameter by ~lr whatever |g| is, so an entry whose gradient is rounding noise may step the
-    # other way: bound the mean drift, not the maximum
-    diff = float((finals["nccl"] - finals["peer"]).abs().mean())
-    assert diff < 1e-5, diff
+    for mode in ("peer", "peer_split"):
+        # the gradients come from fp32 atomics whose order differs run to run: losses agree to rel 1e-4 over 6 steps
+        np.testing.assert_allclose(np.array(losses[mode]), a, rtol=1e-4, err_msg=mode)
+        # Adam moves every touched parameter by ~lr whatever |g| is, so an entry whose gradient is rounding noise may step the
+        # other way: bound the mean drift, not the maximum
+        diff = float((finals["nccl"] - finals[mode]).abs().mean())
+        assert diff < 1e-5, (mode, diff)
     return keep
 
 

@@ -166,3 +166,38 @@ def test_view_embedding_matches_sin_cos():
     assert got.shape == want.shape
     assert np.array_equal(got[:, :3], d.numpy().astype(np.float64))
     assert np.abs(got - want).max() <= 2e-6, np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("tag,o", [("detach", dict(detach_mask_from_field=True, mask_no_dir=False)),
+                                   ("nodir", dict(mask_no_dir=True)),
+                                   ("nodir_nodetach", dict(mask_no_dir=True, mask_no_dir_nodetach=True))])
+def test_two_head_rgb_network_matches_the_reference_wiring(tag, o):
+    """RGB_network (--detach_mask_from_field / --mask_no_dir, nerf/network_grid.py:13-68) against the reference's own class run on
+    the CPU with tcnn.Network served by the oracle MLP (tests/golden/ref_trainer.npz): outputs within the fp16 contract
+    (abs 2e-3), the confidence head's gradient does not reach the inputs unless mask_no_dir_nodetach, state-dict names equal."""
+    import os
+    import types
+    from customnerf_b200.nerf.field import RGB_network, NeRFNetwork
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_trainer.npz"))
+    net = RGB_network(27, opt=types.SimpleNamespace(keyword2=None, **o)).cuda()
+    with torch.no_grad():
+        net.rgb_network.params.copy_(torch.from_numpy(G["rgbnet_%s_rgb_network" % tag]))
+        net.conf_network.params.copy_(torch.from_numpy(G["rgbnet_%s_conf_network" % tag]))
+    assert sorted(net.state_dict().keys()) == list(G["rgbnet_%s_keys" % tag])
+    x = torch.from_numpy(G["rgbnet_x"]).cuda().requires_grad_()
+    y = net(x)
+    assert_close(y.detach().float().cpu().numpy(), G["rgbnet_%s_out" % tag], 1e-2, 2e-3, "two-head output")
+    y[:, 3:].float().sum().backward()
+    gx, want = x.grad.float().cpu().numpy(), G["rgbnet_%s_grad_x_from_conf" % tag]
+    if np.abs(want).max() == 0:
+        assert np.abs(gx).max() == 0.0, "the confidence head must not send a gradient to its inputs"
+    else:
+        assert_close(gx, want, 5e-2, 2e-2 * np.abs(want).max(), "gradient through the confidence head")
+    # the field network builds it when the reference does, and falls back to the per-layer path
+    opt = torch_ref.default_opt(train_conf=0.01, **o)
+    full = NeRFNetwork(opt, encoding="hashgrid", log2_hashmap_size=12, desired_resolution=64).cuda()
+    assert isinstance(full.rgb_network, RGB_network) and not full.use_fused_field
+    assert {"rgb_network.rgb_network.params", "rgb_network.conf_network.params"} <= set(full.state_dict().keys())
+    xx, dd = _inputs(300)
+    s, c, _ = full(xx, dd)
+    assert c.shape == (300, 4) and torch.isfinite(c).all() and len(full.get_params(1e-3)) == 4
