@@ -366,7 +366,24 @@ def run_b200(args):
     # call inside the step.  --update nccl: one NCCL all-reduce of the flat gradient + a full Adam sweep per rank (measured
     # at N = 2: 0.67 ms/step; in 4 pieces pipelined with Adam -- allreduce_chunks=4 -- 0.77 ms).
     peer, sync = None, None
-    if (world > 1 or args.peer_at_1) and args.update in ("peer", "nvls"):
+    if args.update == "auto":
+        # measured (profiles/r02t_*): the multicast form moves n (1 + 1/W) words per link direction against 2 n (W - 1) / W
+        # for P2P loads / stores -- fewer from W = 4 on (0.523 vs 0.560 ms/step at W = 8), more at W = 2
+        args.update = "nvls" if world >= 4 else "peer"
+        if args.update == "nvls":
+            try:
+                peer = parallel.PeerMemory(fused_trainer.flat_parameter_count(model), dev, multicast=True)
+                ok = 1
+            except Exception as e:                      # no multicast object on this fabric / driver: P2P form, on every rank
+                sys.stderr.write("[bench] NVSwitch multicast unavailable (%s); P2P peer update\n" % (e,))
+                peer, ok = None, 0
+            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag) == 0:
+                peer, args.update = None, "peer"
+    if peer is not None:
+        pass
+    elif (world > 1 or args.peer_at_1) and args.update in ("peer", "nvls"):
         peer = parallel.PeerMemory(fused_trainer.flat_parameter_count(model), dev, multicast=args.update == "nvls")
     elif world > 1:
         sync = (lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM))
@@ -549,7 +566,9 @@ def run_b200(args):
             nb = fs.params_flat.numel() * 4
             # per rank and link direction: IN = the peers' gradient slices it reads (read responses) + the parameters the
             # peers store into it; OUT = the same two streams the other way round: 2 x 4 B x n x (W - 1) / W each way
-            wire = 2 * nb * (world - 1) / world
+            # multicast form: OUT = its gradient to the switch (n words, reduced there) + its parameter slice once (n / W);
+            # IN = the reduced slice (n / W) + everybody's parameters (n)
+            wire = nb * (1 + 1.0 / world) if args.update == "nvls" else 2 * nb * (world - 1) / world
             line["update"] = {"kind": args.update, "us": round(update_us, 1),
                               "what": "adam_hyper + " + ("k_peer_reduce_adam_bcast" if peer is not None else
                                                         "ncclAllReduce(grads_flat) + k_fused_adam") + " + weight re-pack, "
@@ -601,9 +620,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="run each step's optimiser update before the next step starts instead of next to its ray march")
-    ap.add_argument("--update", default="peer", choices=["peer", "nvls", "nccl"],
-                    help="N > 1: optimiser update as one NVLink peer-memory kernel (peer: P2P loads / stores, default; nvls: "
-                         "through the NVSwitch multicast mapping, reduced in the switch) or NCCL all-reduce + Adam")
+    ap.add_argument("--update", default="auto", choices=["auto", "peer", "nvls", "nccl"],
+                    help="N > 1: optimiser update as one NVLink peer-memory kernel (peer: P2P loads / stores; nvls: through "
+                         "the NVSwitch multicast mapping, reduced in the switch; auto = nvls from 4 GPUs on, else peer) or "
+                         "NCCL all-reduce + Adam")
     ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4],
                     help="BASELINE.json configs[] index: 1 = the bench line (default); 3 = LGIE editing step; "
                          "4 = 2^22 table, 1 M rays per step")
