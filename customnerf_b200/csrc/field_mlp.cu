@@ -324,10 +324,36 @@ __device__ __forceinline__ uint64_t mndesc(uint32_t tile_addr, uint32_t ks, uint
 // kernel and twice as many warps are in flight to hide the TMEM / shared-memory / barrier latencies between the MMAs.
 constexpr uint32_t kBwdThreads = 256;
 
+// shared-space 16-byte accesses on 32-bit shared addresses (the generic LD.E / ST.E forms cost an address-space check and a
+// descriptor per access on the epilogue's critical path)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// relu'(x) masks of one row and column half as 0xffff / 0 half lanes: loaded and converted BEFORE the wait for the dgrad
+// MMAs (the activation tile is in shared memory long before the accumulator is ready), so that nothing but the TMEM load
+// sits between the wake-up and the gradient tile's stores
+struct ReluMask { uint32_t w[16]; };
+__device__ __forceinline__ void load_relu_mask(ReluMask &m, uint32_t act_tile, uint32_t row, uint32_t half) {
+    const __half2 zero = __float2half2_rn(0.0f);
+#pragma unroll
+    for (uint32_t c = 0; c < 4; c++) {
+        const uint4 v = lds128(act_tile + umma::sw128_offset(row, half * 4 + c));
+        const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) m.w[c * 4 + j] = __hgt2_mask(*reinterpret_cast<const __half2 *>(&vw[j]), zero);
+    }
+}
+
 // dgrad epilogue of one row and one column half: DG (32 fp32) * relu'(activation) -> fp16 -> gradient tile.
-// Deliberately not inlined: five call sites per tile, and the kernel's instruction footprint matters (one CTA per SM).
-__device__ __noinline__ void bwd_epilogue_half(uint32_t taddr, const uint8_t *act_tile, uint8_t *dst_tile, uint32_t row,
-                                               uint32_t half) {
+// (inlined at its six call sites: the masks stay in registers)
+template <bool kMask>
+__device__ __forceinline__ void bwd_epilogue_half(uint32_t taddr, const ReluMask &m, uint32_t dst_tile, uint32_t row, uint32_t half) {
     uint32_t a[32];
     umma::tmem_ld32(taddr, a);
     umma::tmem_ld_wait();
@@ -335,18 +361,11 @@ __device__ __noinline__ void bwd_epilogue_half(uint32_t taddr, const uint8_t *ac
     for (uint32_t c = 0; c < 4; c++) {
         uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) pk[j] = pack_h2(__uint_as_float(a[c * 8 + 2 * j]), __uint_as_float(a[c * 8 + 2 * j + 1]));
-        if (act_tile) {
-            // relu'(x) on packed halves: (act > 0) as a 0xffff / 0 lane mask ANDed onto the packed gradient
-            const uint4 m = *reinterpret_cast<const uint4 *>(act_tile + umma::sw128_offset(row, half * 4 + c));
-            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-            const __half2 zero = __float2half2_rn(0.0f);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                pk[j] &= __hgt2_mask(*reinterpret_cast<const __half2 *>(&mw[j]), zero);
-            }
+        for (int j = 0; j < 4; j++) {
+            pk[j] = pack_h2(__uint_as_float(a[c * 8 + 2 * j]), __uint_as_float(a[c * 8 + 2 * j + 1]));
+            if (kMask) pk[j] &= m.w[c * 4 + j];
         }
-        *reinterpret_cast<uint4 *>(dst_tile + umma::sw128_offset(row, half * 4 + c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        sts128(dst_tile + umma::sw128_offset(row, half * 4 + c), make_uint4(pk[0], pk[1], pk[2], pk[3]));
     }
 }
 
@@ -452,9 +471,7 @@ k_field_backward(const FieldBwdArgs p) {
         __syncthreads();
         umma::fence_after_sync();
     };
-    auto epilogue = [&](const uint8_t *mask_tile, uint32_t dst_off) {
-        bwd_epilogue_half(trow + C_DG + 32 * half, mask_tile, smem + dst_off, row, half);
-    };
+    ReluMask mk, mk2;                      // relu' masks of the coming epilogue(s), loaded while the MMAs run
 
     // ---- per-row inputs prefetched one tile ahead into registers: the warps of column half 0 build the head
     //      gradients of their row (T16), the warps of half 1 its direction encoding (XV chunks 4..7)
@@ -513,6 +530,8 @@ k_field_backward(const FieldBwdArgs p) {
         cp_async_commit();
         prefetch_row(blockIdx.x);
         if (half == 1) write_view_chunks(smem + SB_XV, row, n_d0, n_d1, n_d2, row0 + row < Mrows);
+        write_t16();                       // later tiles: written one tile ahead, under the stage-4 MMAs
+        prefetch_row(blockIdx.x + gridDim.x);
     }
     const bool issuer_warp = warp == 0;
     uint32_t xv_sel = 0;                   // which XV buffer the current tile uses
@@ -527,10 +546,9 @@ k_field_backward(const FieldBwdArgs p) {
         const uint32_t sXVc = xv_sel ? base + SB_XV2 : sXV, sXVn = xv_sel ? sXV : base + SB_XV2;
         uint8_t *xv_next = smem + (xv_sel ? SB_XV : SB_XV2);
 
-        write_t16();                       // from the registers prefetched one tile ago
-        prefetch_row(next);                // consumed by the refill below (view chunks) and by the next write_t16
         cp_async_wait<3>();                // G1 landed (this thread's part); the barrier below covers the other threads
-        publish();
+        publish();                         // (also: every warp has read the previous tile's dX accumulator; T16 was written
+                                           //  and published during the previous tile, or by the prologue)
 
         // ---- stages 1 + 2: dHR = (dOr Wr2) * [hr > 0] and dHD = (dOd Wd2) * [hd > 0] are independent (both read only the
         //      head gradients): one commit, one epilogue pass over two accumulators;  wgrad of the two heads (A = T16^T)
@@ -541,9 +559,11 @@ k_field_backward(const FieldBwdArgs p) {
             wgrad(C_R2, sT16, sHR, 0, WG64);
             wgrad(C_D2, sT16, sHD, 0, WG64);
         }
+        load_relu_mask(mk, sHR, row, half);
+        load_relu_mask(mk2, sHD, row, half);
         wait_mma();
-        epilogue(smem + SB_HR, SB_GA);
-        bwd_epilogue_half(trow + C_DG2 + 32 * half, smem + SB_HD, smem + SB_GB, row, half);
+        bwd_epilogue_half<true>(trow + C_DG + 32 * half, mk, sGA, row, half);
+        bwd_epilogue_half<true>(trow + C_DG2 + 32 * half, mk2, sGB, row, half);
         cp_async_wait<2>();                // G2: FEA (and G1's x_en) for the weight gradients of stage 3
         publish();
         // ---- stage 3: dFEA = dHR Wr1f + dHD Wd1;   wgrad Wr1f | Wd1 (A = [dHR | dHD]^T, B = fea), Wr1v (A = dHR^T, B = view)
@@ -554,6 +574,9 @@ k_field_backward(const FieldBwdArgs p) {
             wgrad(C_PAIR, sGA, sFEA, 0, WG64);
             wgrad(C_R1V, sGA, sXVc, 32, WG32);
         }
+        // while the MMAs run: the direction encoding of the NEXT tile (its XV buffer was last read by the previous tile's
+        // weight gradients, which the stage-1 commit of this tile has covered)
+        if (half == 1) write_view_chunks(xv_next, row, n_d0, n_d1, n_d2, has_next && nrow0 + row < Mrows);
         wait_mma();                        // ... which also means the head weight gradients of stage 2 are done:
         if (has_next) {                    // HR / HD and the other XV buffer are free, refill them for the next tile
             load_tile_async(sHR, p.act + 4 * act_stride, nrow0, Mrows, tid);
@@ -561,8 +584,7 @@ k_field_backward(const FieldBwdArgs p) {
             load_xen_async(sXVn, p.x_en, nrow0, Mrows, tid);
         }
         cp_async_commit();                 // G1'
-        if (half == 1) write_view_chunks(xv_next, row, n_d0, n_d1, n_d2, has_next && nrow0 + row < Mrows);
-        epilogue(nullptr, SB_GC);
+        bwd_epilogue_half<false>(trow + C_DG + 32 * half, mk, sGC, row, half);
         cp_async_wait<2>();                // G3: H2
         publish();
         // ---- stage 4: dH2 = (dFEA W3) * [h2 > 0];   wgrad W3 (A = dFEA^T, B = h2)
@@ -571,10 +593,15 @@ k_field_backward(const FieldBwdArgs p) {
             umma::commit(&bar);
             wgrad(C_W3, sGC, sH2, 0, WG64);
         }
+        load_relu_mask(mk, sH2, row, half);
+        // while the MMAs run: the head gradients of the NEXT tile (T16's readers -- stages 1 + 2 and their weight gradients --
+        // were covered by the stage-3 commit), then the prefetch of the per-row inputs of the tile after it
+        write_t16();
+        prefetch_row(next + gridDim.x);
         wait_mma();                        // stage-3 weight gradients done: FEA is free
         if (has_next) load_tile_async(sFEA, p.act + 2 * act_stride, nrow0, Mrows, tid);
         cp_async_commit();                 // G2'
-        epilogue(smem + SB_H2, SB_GA);
+        bwd_epilogue_half<true>(trow + C_DG + 32 * half, mk, sGA, row, half);
         cp_async_wait<2>();                // G4: H1
         publish();
         // ---- stage 5: dH1 = (dH2 W2) * [h1 > 0];   wgrad W2 (A = dH2^T, B = h1)
@@ -583,10 +610,11 @@ k_field_backward(const FieldBwdArgs p) {
             umma::commit(&bar);
             wgrad(C_W2, sGA, sH1, 0, WG64);
         }
+        load_relu_mask(mk, sH1, row, half);
         wait_mma();                        // stage-4 weight gradients done: H2 is free
         if (has_next) load_tile_async(sH2, p.act + act_stride, nrow0, Mrows, tid);
         cp_async_commit();                 // G3'
-        epilogue(smem + SB_H1, SB_GB);
+        bwd_epilogue_half<true>(trow + C_DG + 32 * half, mk, sGB, row, half);
         publish();
         // ---- stage 6: dX = dH1 W1 (N = 32) -> global;   wgrad W1 (A = dH1^T, B = x_en)
         if (issuer_warp && umma::elect_one()) {
@@ -614,10 +642,8 @@ k_field_backward(const FieldBwdArgs p) {
             }
         }
         // (the W1 weight gradient may still be running: nothing it reads -- GB, this tile's XV buffer -- is written
-        //  before the next tile's stage-1 commit has completed)
-        umma::fence_before_sync();
-        __syncthreads();
-        umma::fence_after_sync();
+        //  before the next tile's stage-1 commit has completed; the publish() that heads the next tile is the barrier
+        //  between this tile's last accumulator read and the next tile's first MMA)
         first_tile = false;
         xv_sel ^= 1u;
     }
