@@ -72,6 +72,7 @@ __device__ __noinline__ void epilogue_row64(uint32_t tmem_row_addr, uint8_t *til
     uint32_t a[32], b[32];
     umma::tmem_ld32(tmem_row_addr, a);
     umma::tmem_ld32(tmem_row_addr + 32, b);
+    const uint32_t tile_s = umma::smem_u32(tile);
     umma::tmem_ld_wait();
 #pragma unroll
     for (uint32_t c = 0; c < 8; c++) {
@@ -86,7 +87,9 @@ __device__ __noinline__ void epilogue_row64(uint32_t tmem_row_addr, uint8_t *til
             }
         }
         const uint4 pk = make_uint4(q[0], q[1], q[2], q[3]);
-        *reinterpret_cast<uint4 *>(tile + umma::sw128_offset(row, c)) = pk;
+        // shared-space store on the 32-bit shared address (a generic ST.E pays an address-space check per access)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tile_s + umma::sw128_offset(row, c)), "r"(pk.x), "r"(pk.y),
+                     "r"(pk.z), "r"(pk.w) : "memory");
         if (gdst) *reinterpret_cast<uint4 *>(gdst + c * 8) = pk;
     }
 }

@@ -241,15 +241,16 @@ k_field_forward(const FieldFwdArgs p, const __grid_constant__ CUtensorMap act_ma
             mma_run(sXV, 2, sW + F_W1V, 2, 2, ID64, false);
         }
         sync_mma();
-        // the XV tile is free from here on: stage the next tile's inputs (published by the barriers below)
-        write_xv(true);
-        px = npx; py = npy; pz = npz;
         epilogue_row64<true>(trow, smem + S_H1, tid, nullptr);
         drain1();
         publish();
         // ---- colour layer 1: rgba = sigmoid(hr Wr2^T) (N = 16, lanes 0..3)
         if (tid == 0) mma_run(sH1, 0, sW + F_WR2, 0, 4, ID16, true);
         store_tile(sH1, 4, row0);
+        // the XV tile has been free since colour layer 0 completed: stage the next tile's inputs (and its direction
+        // encoding) while the last MMA runs; published by the fence + barrier that end the tile
+        write_xv(true);
+        px = npx; py = npy; pz = npz;
         sync_mma();
         {
             uint32_t r[16];
