@@ -5,6 +5,12 @@
 #include "common.cuh"
 #include "umma.cuh"
 
+// Kernel status word (include/nerf_b200.h: nb200_set_kernel_status_word): a device word of the CURRENT device into which the
+// field kernels OR a bit when one of their bounded mbarrier waits times out (a descriptor / protocol mistake must neither
+// hang the GPU nor pass silently).  Without a registered word the forward kernels poison sigma[0] and the backward kernel
+// d_x_en[0] with NaN instead.  Defined in field_mlp.cu.
+uint32_t *nb_kernel_status_word();
+
 namespace {
 
 // ---- packed weight images (bytes) ---------------------------------------------------------------------
@@ -65,6 +71,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ uint64_t kdesc(uint32_t tile_addr, uint32_t ks) {
     return umma::make_desc(tile_addr + ks * 32, 16, 1024, umma::kLayoutSW128);
 }
+
+constexpr uint32_t kStatusFieldFwdTimeout = 1u, kStatusFieldBwdTimeout = 2u, kStatusFieldFusedTimeout = 4u;
 
 // accumulator row (64 fp32) -> optional ReLU -> fp16 -> row of a swizzled tile (+ optional global copy)
 template <bool kRelu>

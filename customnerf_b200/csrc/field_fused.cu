@@ -54,6 +54,7 @@ struct FusedArgs {
     float S, bound;
     uint32_t H, gridtype, align_corners, interp;
     uint32_t M, G, cascade, pad;
+    uint32_t *status;         // kernel status word or null (field_common.cuh)
 };
 
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -315,7 +316,10 @@ k_field_fused(const FusedArgs p, const __grid_constant__ CUtensorMap act_map) {
     umma::fence_before_sync();
     bar_consumers();
     if (warp == 0) umma::tmem_dealloc(tmem, kCols);
-    if (tid == 0 && fail_s) p.sigma[0] = __int_as_float(0x7fc00000);   // make a barrier time-out visible (NaN)
+    if (tid == 0 && fail_s) {           // make a barrier time-out visible: status word, else NaN
+        if (p.status) atomicOr(p.status, kStatusFieldFusedTimeout);
+        else p.sigma[0] = __int_as_float(0x7fc00000);
+    }
 }
 
 // the saved activations as a rank-3 tensor [5 planes][M rows][64 halves], boxes of 128 rows, 128B swizzle
@@ -369,6 +373,7 @@ int nb200_field_fused_forward(const float *xyz, const float *dirs, float bound, 
     a.xyz = xyz; a.dirs = dirs; a.table = table; a.offsets = offsets; a.wimg = (const uint8_t *)fwd_img;
     a.sigma = sigma; a.sigma_arg = sigma_arg; a.rgba = (__half *)rgba; a.x_en = (__half *)x_en; a.count_dev = count_dev;
     a.S = S; a.bound = bound; a.H = H; a.gridtype = gridtype; a.align_corners = align_corners != 0; a.interp = interp; a.M = M;
+    a.status = nb_kernel_status_word();
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     if (save) {
@@ -391,6 +396,7 @@ int nb200_occ_density(const float *cell_xyz, const float *noise, uint32_t G, uin
     a.xyz = cell_xyz; a.noise = noise; a.table = table; a.offsets = offsets; a.wimg = (const uint8_t *)fwd_img;
     a.sigma = tmp_grid; a.S = S; a.bound = bound; a.H = H; a.gridtype = gridtype; a.align_corners = align_corners != 0;
     a.interp = interp; a.M = cascade * G * G * G; a.G = G; a.cascade = cascade;
+    a.status = nb_kernel_status_word();
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     return launch_fused<false, false, SRC_OCC>(a, map, nb_stream(stream));

@@ -73,6 +73,7 @@ struct FieldFwdArgs {
     __half *act;            // [5, M, 64] or null: h1, h2, fea, hd, hr saved for backward
     uint32_t M;             // rows allocated (the stride of `act` planes)
     const int32_t *count_dev;   // when non-null only rows < min(M, *count_dev) are evaluated
+    uint32_t *status;           // kernel status word or null (field_common.cuh)
 };
 
 // the embedding as the field kernels compute it, fp32 [M, 27] (get_embedder(4) as a device op; also the test hook that
@@ -272,7 +273,10 @@ k_field_forward(const FieldFwdArgs p, const __grid_constant__ CUtensorMap act_ma
     if (save && tid == 0) umma::tma_store_wait<0>();
 
     if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
-    if (tid == 0 && fail_s) p.sigma[0] = __int_as_float(0x7fc00000);   // make a barrier time-out visible (NaN)
+    if (tid == 0 && fail_s) {           // make a barrier time-out visible: status word, else NaN
+        if (p.status) atomicOr(p.status, kStatusFieldFwdTimeout);
+        else p.sigma[0] = __int_as_float(0x7fc00000);
+    }
 }
 
 
@@ -313,6 +317,7 @@ struct FieldBwdArgs {
     uint32_t M;               // rows allocated (the stride of `act` planes)
     const int32_t *count_dev; // when non-null only rows < min(M, *count_dev) are processed
     uint32_t *scaler;         // loss-scaler words (adam.cuh) or null: a feature gradient that leaves the fp16 range raises found-inf
+    uint32_t *status;         // kernel status word or null (field_common.cuh)
 };
 
 // MN-major descriptor of K-step ks (16 rows = 2 swizzle atoms) starting at column `col0` (multiple of 8 halves)
@@ -461,8 +466,9 @@ k_field_backward(const FieldBwdArgs p) {
         for (uint32_t k = 0; k < 8; k++)
             umma::mma_f16_ss(tmem + dcol, mndesc(a, k, 0), mndesc(b, k, bcol0), idesc, !(first_tile && k == 0));
     };
+    bool timed_out = false;
     auto wait_mma = [&]() {                 // completion of everything committed by the issuing thread so far
-        umma::mbar_wait(&bar, phase);
+        timed_out |= !umma::mbar_wait(&bar, phase);
         phase ^= 1;
         umma::fence_after_sync();
     };
@@ -708,6 +714,10 @@ k_field_backward(const FieldBwdArgs p) {
         flush(C_R2, 64, gr + R_W2 + n * 64, n < 4);
         flush(C_D2, 64, gd + D_W2, n == 16);
     }
+    if (timed_out && (tid & 31u) == 0) {    // a bounded wait gave up: status word, else poison the feature gradient
+        if (p.status) atomicOr(p.status, kStatusFieldBwdTimeout);
+        else if (tid == 0) p.d_x_en[0] = __ushort_as_half((unsigned short)0x7e00);
+    }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, kTmemColsBwd);
@@ -749,9 +759,34 @@ k_field_wgrad_reduce(const float *__restrict__ slabs, uint32_t grid, uint32_t M,
     *dst += sum;
 }
 
+constexpr int kMaxDevices = 64;
+uint32_t *g_status_word[kMaxDevices] = {};      // per device ordinal; registered by nb200_set_kernel_status_word
 }  // namespace
 
+uint32_t *nb_kernel_status_word() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    return g_status_word[dev];
+}
+
 extern "C" {
+
+int nb200_set_kernel_status_word(uint32_t *word) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= kMaxDevices) return NB200_E_BAD_ARG;
+    g_status_word[dev] = word;
+    return 0;
+}
+
+int nb200_release_kernel_status_word(uint32_t *word) {     // unregisters `word` if it is the registered one
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < kMaxDevices && g_status_word[dev] == word) g_status_word[dev] = nullptr;
+    return 0;
+}
 
 uint32_t nb200_field_wgrad_scratch_bytes(void) {
     int dev = 0, sms = 148;
@@ -811,20 +846,22 @@ int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, c
                         float *sigma_arg, void *rgba, void *act, uint32_t M, const int32_t *count_dev, void *stream) {
     if (M == 0) return 0;
     if (!x_en || !xyz || !dirs || !fwd_img || !sigma || !rgba) return NB200_E_BAD_ARG;
-    static int configured = 0;
+    // per device: the attribute belongs to the function on the CURRENT device (one flag per device ordinal)
+    static bool configured[kMaxDevices] = {};
     const int smem = (int)S_FWD_BYTES + 1024;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_field_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = 1;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_field_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
+    }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     FieldFwdArgs a;
     a.x_en = (const __half *)x_en; a.xyz = xyz; a.dirs = dirs; a.wimg = (const uint8_t *)fwd_img;
     a.sigma = sigma; a.sigma_arg = sigma_arg; a.rgba = (__half *)rgba; a.act = (__half *)act; a.M = M;
     a.count_dev = count_dev;
+    a.status = nb_kernel_status_word();
     const uint32_t ntiles = (M + 127) / 128;
     const uint32_t grid = ntiles < (uint32_t)(2 * sms) ? ntiles : (uint32_t)(2 * sms);
     CUtensorMap act_map;
@@ -848,15 +885,15 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
     if (!d_sigma || !d_rgba || !sigma_arg || !rgba || !x_en || !dirs || !act || !bwd_img || !d_x_en || !g_trunk ||
         !g_density || !g_rgb)
         return NB200_E_BAD_ARG;
-    static int configured = 0;
+    static bool configured[kMaxDevices] = {};
     const int smem = (int)S_BWD_BYTES + 1024;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_field_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = 1;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_field_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
+    }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     FieldBwdArgs a;
     a.d_sigma = d_sigma; a.d_rgba = d_rgba; a.sigma_arg = sigma_arg; a.rgba = (const __half *)rgba;
@@ -864,6 +901,7 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
     a.d_x_en = (__half *)d_x_en; a.g_trunk = g_trunk; a.g_density = g_density; a.g_rgb = g_rgb; a.M = M;
     a.count_dev = count_dev;
     a.scaler = scaler;
+    a.status = nb_kernel_status_word();
     a.slabs = wg_scratch;
     const uint32_t ntiles = (M + 127) / 128;
     const uint32_t grid = ntiles < (uint32_t)sms ? ntiles : (uint32_t)sms;

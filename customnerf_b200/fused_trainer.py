@@ -28,6 +28,8 @@ import ctypes as C
 import math
 
 import numpy as np
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -39,6 +41,14 @@ GROWTH_INTERVAL = 2000      # torch.cuda.amp.GradScaler's default: the scale dou
 KERNELS_PER_STEP = 12
 STAGES = ["march_count", "march_write", "grid_encode_forward", "field_forward", "composite_forward",
           "composite_backward", "field_backward", "grid_encode_backward", "adam", "pack_weights"]
+
+
+def _release_status_word(lib, stats, dev):
+    try:
+        with torch.cuda.device(dev):
+            lib.nb200_release_kernel_status_word(C.c_void_p(stats[7:8].data_ptr()))
+    except Exception:           # interpreter shutdown
+        pass
 
 
 def _check(rc, what):
@@ -104,7 +114,8 @@ class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
                  lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0,
-                 peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True, update_shape=(64, 512, 4), split_level=0):
+                 peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True, update_shape=(64, 512, 4), split_level=0,
+                 rgb_weight=1.0):
         if not model.cuda_ray:
             raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
@@ -147,6 +158,11 @@ class FusedTrainStep:
         # mask_weight > 0: the reference's reconstruction loss with train_conf (utils_init_nerf.py:224-234):
         # MSE(image, target) + mask_weight * MSE(render_mask, target_mask); render_mask composites the 4th field output
         self.mask_weight = float(mask_weight)
+        # rgb_weight = opt.train_rgb (utils_init_nerf.py:224: loss = train_rgb * MSE(rgb) [+ train_conf * MSE(mask)]; 1 in every
+        # shipped configuration).  Folded into the kernel's two constants: inv_n carries it, the mask weight is divided by it.
+        self.rgb_weight = float(rgb_weight)
+        if not self.rgb_weight > 0.0:
+            raise NotImplementedError("FusedTrainStep: rgb_weight (opt.train_rgb) must be positive")
         # fused_forward: grid gather + field network forward as ONE kernel (csrc/field_fused.cu: the features are gathered by
         # producer warps straight into the tensor-core operand tile); False (default): two launches (encode, then field).
         # Measured on B200 at configs[1] (profiles/r02_fused_forward.md): the fused kernel is bit-identical but SLOWER in the
@@ -227,9 +243,12 @@ class FusedTrainStep:
         self.g_weights_sum = torch.zeros(N, **f32)
         self.rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
         self.scratch = torch.empty(int(self.lib.nb200_march_scratch_ints(L.u32(N))), dtype=torch.int32, device=dev)
-        # [counter0, counter1, m_eff, loss bits, peer-update status, 3 spare]: one 32-byte D2H returns everything the host
-        # wants to know
+        # [counter0, counter1, m_eff, loss bits, peer-update status, max samples over ranks, parked sample count, kernel
+        # status (NB200_STATUS_*: a field kernel's bounded mbarrier wait timed out)]: one 32-byte D2H returns everything the
+        # host wants to know
         self.stats = torch.zeros(8, dtype=torch.int32, device=dev)
+        _check(self.lib.nb200_set_kernel_status_word(C.c_void_p(self.stats[7:8].data_ptr())), "set_kernel_status_word")
+        weakref.finalize(self, _release_status_word, self.lib, self.stats, self.dev)    # keeps `stats` alive until then
         self.stats_host = torch.zeros(8, dtype=torch.int32).pin_memory()
         # results of the last two steps, copied out after each step and fenced by an event each: previous_stats() reads step
         # k - 1 while step k runs (no pipeline bubble between steps; last_stats() is the synchronous form)
@@ -311,7 +330,7 @@ class FusedTrainStep:
         p.bound, p.dt_gamma = float(m.bound), self.dt_gamma
         p.S = float(np.log2(enc.per_level_scale))
         p.T_thresh, p.min_near = self.T_thresh, 0.2          # run_cuda leaves min_near at its default (Appendix B5)
-        p.loss_scale, p.inv_n_total = LOSS_SCALE, 1.0 / (3.0 * self.n_total)
+        p.loss_scale, p.inv_n_total = LOSS_SCALE, self.rgb_weight / (3.0 * self.n_total)
         p.flags = 1 if self.fused_forward else 0
         p.n_params, p.n_table_params = self.params_flat.numel(), self.layout[0][2]
 
@@ -321,7 +340,7 @@ class FusedTrainStep:
         p.noises = a(self.noises) if self.perturb else None
         use_mask = self.mask_weight > 0.0
         p.target_mask = a(self.target_mask) if use_mask else None
-        p.render_mask, p.g_render_mask, p.mask_weight = a(self.render_mask), a(self.g_render_mask), self.mask_weight
+        p.render_mask, p.g_render_mask, p.mask_weight = a(self.render_mask), a(self.g_render_mask), self.mask_weight / self.rgb_weight
         p.bitfield = a(m.density_bitfield)
         p.params_flat, p.grads_flat, p.exp_avg, p.exp_avg_sq = a(self.params_flat), a(self.grads_flat), a(self.exp_avg), a(self.exp_avg_sq)
         p.hyper, p.sched, p.step = a(self.hyper), a(self.sched), a(self.step_count)
@@ -736,6 +755,9 @@ class FusedTrainStep:
         if int(s[4]):
             raise RuntimeError("FusedTrainStep: the peer-memory update timed out waiting for another rank (status %d): "
                                "a rank left the job or launched fewer steps" % int(s[4]))
+        if int(s[7]):
+            raise RuntimeError("FusedTrainStep: a field kernel gave up waiting for its tensor-core work (status 0x%x: 1 forward, "
+                               "2 backward, 4 fused forward) -- the results of this step are invalid" % int(s[7]))
         return float(s[3:4].view(torch.float32)[0]), int(s[0]), int(s[2])
 
     def _needed_rows(self, s, samples):

@@ -21,9 +21,10 @@ class _PackedWeights:
     def get(self, trunk, density, rgb):
         n = _image_bytes()
         if self.fwd is None or self.fwd.device != trunk.device or torch.is_grad_enabled():
-            # a fresh pair while autograd may still hold the previous one for a pending backward
-            self.fwd = torch.empty(n, dtype=torch.uint8, device=trunk.device)
-            self.bwd = torch.empty(n, dtype=torch.uint8, device=trunk.device)
+            # a fresh pair (one allocation from torch's caching allocator) while autograd may still hold the previous one
+            # for a pending backward
+            both = torch.empty(2, n, dtype=torch.uint8, device=trunk.device)
+            self.fwd, self.bwd = both[0], both[1]
         L.check(L.lib().nb200_field_pack_weights(L.ptr(trunk.detach()), L.ptr(density.detach()), L.ptr(rgb.detach()),
                                                  L.ptr(self.fwd), L.ptr(self.bwd), L.stream()), "field_pack_weights")
         return self.fwd, self.bwd

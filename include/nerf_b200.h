@@ -202,6 +202,15 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
  * scaler (may be NULL; needs wg_scratch): loss-scaler words whose found-inf bit is raised when a weight gradient is not finite
  * or a feature gradient (d_x_en) leaves the fp16 range. */
 uint32_t nb200_field_wgrad_scratch_bytes(void);
+/* Kernel status word of the CURRENT device (no reference counterpart: tcnn's kernels cannot time out).  The field kernels
+ * wait for their tensor-core work on mbarriers with a bounded spin; when a wait gives up they OR NB200_STATUS_* into
+ * `word` (a device uint32 the caller owns and zeroes; NULL unregisters).  Without a registered word the forward kernels
+ * write NaN into sigma[0] and the backward kernel into d_x_en[0] instead, so that a time-out can never pass as a result. */
+#define NB200_STATUS_FIELD_FWD_TIMEOUT   1u
+#define NB200_STATUS_FIELD_BWD_TIMEOUT   2u
+#define NB200_STATUS_FIELD_FUSED_TIMEOUT 4u
+int nb200_set_kernel_status_word(uint32_t *word);
+int nb200_release_kernel_status_word(uint32_t *word);   /* unregisters `word` if it is the registered one (owner going away) */
 /* Grid encoding + field network in ONE kernel (csrc/field_fused.cu): the [M,32] hash-grid features are gathered by producer
  * warps straight into the tensor-core operand tile and never round-trip HBM.  Replaces GridEncoder.forward
  * (gridencoder/grid.py:151-168, gridencoder.cu:87-244) followed by NeRFNetwork.forward / .density (nerf/network_grid.py:159-193).

@@ -201,3 +201,26 @@ def test_two_head_rgb_network_matches_the_reference_wiring(tag, o):
     xx, dd = _inputs(300)
     s, c, _ = full(xx, dd)
     assert c.shape == (300, 4) and torch.isfinite(c).all() and len(full.get_params(1e-3)) == 4
+
+
+def test_kernel_status_word_stays_clear_and_unregisters():
+    """nb200_set_kernel_status_word: the field kernels OR a bit into the registered word only when a bounded mbarrier wait
+    gives up; a healthy forward + backward leaves it zero, and the owner can unregister it"""
+    import ctypes as C
+    from customnerf_b200 import _lib
+    lib = _lib.lib()
+    word = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert lib.nb200_set_kernel_status_word(C.c_void_p(word.data_ptr())) == 0
+    try:
+        net, opt = _net()
+        x, d = _inputs(20000, seed=11)
+        with torch.autocast("cuda", dtype=torch.float16):
+            s, c, m = net(x, d)
+        (s.float().sum() + c.float().sum()).backward()
+        torch.cuda.synchronize()
+        assert int(word) == 0
+        assert torch.isfinite(s).all() and torch.isfinite(net.pos_en.embeddings.grad).all()
+    finally:
+        assert lib.nb200_release_kernel_status_word(C.c_void_p(word.data_ptr())) == 0
+    other = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert lib.nb200_release_kernel_status_word(C.c_void_p(other.data_ptr())) == 0      # not the registered one: no-op

@@ -278,8 +278,9 @@ def test_pipelined_update_matches_the_serial_step():
     assert np.isfinite(piped.last_stats()[0])
 
 
-def test_mask_loss_term_matches_the_autograd_path():
-    """train_conf: loss = MSE(image, target) + w * MSE(render_mask, gt_mask) (nerf/utils_init_nerf.py:224-234) with
+@pytest.mark.parametrize("rgb_w", [1.0, 0.25])
+def test_mask_loss_term_matches_the_autograd_path(rgb_w):
+    """train_rgb / train_conf: loss = rgb_w * MSE(image, target) + w * MSE(render_mask, gt_mask) (nerf/utils_init_nerf.py:224-234) with
     render_mask = sum_i w_i mask_i composited from the 4th field output.  Fused step (mask as a 4th composited channel)
     against autograd over the drop-in ops (run_cuda + _lgie_composites): loss rel 1e-5, gradients 1e-2 of the largest."""
     import torch.nn.functional as F
@@ -297,10 +298,10 @@ def test_mask_loss_term_matches_the_autograd_path():
     ma.train()
     with torch.autocast("cuda", dtype=torch.float16):
         out = ma.render(o[None], d[None], staged=False, perturb=False, force_all_rays=True, **vars(opt))
-        loss_ref = (F.mse_loss(out["image"].reshape(-1, 3), tgt, reduction="sum") / (3.0 * N_RAYS)
+        loss_ref = (rgb_w * F.mse_loss(out["image"].reshape(-1, 3), tgt, reduction="sum") / (3.0 * N_RAYS)
                     + w * F.mse_loss(out["render_mask"].reshape(-1), gt_mask, reduction="sum") / N_RAYS)
     (loss_ref * fused_trainer.LOSS_SCALE).backward()
-    fs = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False, use_graph=False, mask_weight=w)
+    fs = fused_trainer.FusedTrainStep(mb, N_RAYS, perturb=False, use_graph=False, mask_weight=w, rgb_weight=rgb_w)
     fs._alloc_samples(fs._round_cap(fs.measure_samples(o, d)))
     fs.set_batch(o, d, tgt, gt_mask)
     fs.forward_backward()

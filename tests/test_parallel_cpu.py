@@ -202,3 +202,19 @@ def test_peer_plan_is_filled_from_the_mapped_bases():
     assert (z.threads, z.unroll) == (512, 2)
     assert [z.scalers[r] for r in range(4)] == [b + 9000 for b in pm.bases] and z.scalers[4] is None
     assert p.scalers[0] is None and (p.threads, p.unroll) == (0, 0)
+
+
+def test_stats_block_reports_kernel_and_peer_status():
+    """FusedTrainStep._parse_stats: words 4 (peer update timed out) and 7 (a field kernel's mbarrier wait timed out) raise"""
+    import pytest
+    from customnerf_b200 import fused_trainer
+    fs = object.__new__(fused_trainer.FusedTrainStep)
+    s = torch.zeros(8, dtype=torch.int32)
+    s[0], s[2] = 1234, 1200
+    s[3:4] = torch.tensor([0.25]).view(torch.int32)
+    assert fs._parse_stats(s) == (0.25, 1234, 1200)
+    for word, what in ((4, "peer-memory update"), (7, "field kernel")):
+        t = s.clone()
+        t[word] = 2
+        with pytest.raises(RuntimeError, match=what):
+            fs._parse_stats(t)
