@@ -115,9 +115,22 @@ class FusedTrainStep:
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
                  lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0,
                  peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True, update_shape=(64, 512, 4), split_level=0,
-                 rgb_weight=1.0):
-        if not model.cuda_ray:
-            raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path")
+                 rgb_weight=1.0, dense=None):
+        # dense = (num_steps, upsample_steps): the DENSE renderer (nerf/renderer.py:278-405, the path the published -O2 commands
+        # run) instead of the occupancy march -- per step: near/far, coarse samples (csrc/dense_sampler.cu), their densities
+        # by the fused encode + trunk + density-head launch (no autograd, no saves), inverse-cdf importance samples merged with
+        # the coarse ones and written as xyzs / dirs / deltas / rays -- then exactly the occupancy path's encode .. encode^T
+        # (T_thresh = 0: the dense compositing formula) and the update.  The sample count is the constant N (S + Su).
+        self.dense = None if dense is None else (int(dense[0]), int(dense[1]))
+        if self.dense is None and not model.cuda_ray:
+            raise RuntimeError("FusedTrainStep drives the occupancy (cuda_ray) path; pass dense=(num_steps, upsample_steps) "
+                               "for the dense renderer")
+        if self.dense is not None:
+            if self.dense[0] < 2 or self.dense[1] < 1 or model.pos_en.num_levels != 16:
+                raise RuntimeError("FusedTrainStep(dense=(S, Su)): S >= 2, Su >= 1 and the 16-level encoder are required")
+            if pipeline_update or peer is not None or raygen is not None:
+                raise RuntimeError("FusedTrainStep(dense=...): single stream, single GPU, rays from the caller")
+            T_thresh, m_cap = 0.0, int(n_rays) * (self.dense[0] + self.dense[1])
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
             raise RuntimeError("FusedTrainStep needs the reference field shape (D=3, 16 levels x 2 features)")
         if getattr(model, "two_heads", False):
@@ -170,6 +183,8 @@ class FusedTrainStep:
         # 8 warps per SM, where the standalone encoder has ~220 KB and ~31
         self.fused_forward = bool(fused_forward) and model.pos_en.num_levels == 16
         self.kernels_per_step = KERNELS_PER_STEP - (1 if self.fused_forward else 0)
+        if self.dense is not None:
+            self.kernels_per_step += 1          # near/far, coarse, density, importance instead of the march's three launches
         self.pipeline_update = bool(pipeline_update)
         self.update_shape = tuple(int(v) for v in update_shape) if update_shape else None   # (CTAs, threads, unroll) of the pipelined sweep
         # split update (ray-sharded, peer-memory update, pipelined; OFF by default, split_level=10 or NB200_SPLIT_LEVEL=10 turns it
@@ -243,6 +258,12 @@ class FusedTrainStep:
         self.g_weights_sum = torch.zeros(N, **f32)
         self.rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
         self.scratch = torch.empty(int(self.lib.nb200_march_scratch_ints(L.u32(N))), dtype=torch.int32, device=dev)
+        if self.dense is not None:
+            S_, Su_ = self.dense
+            self.lin = torch.linspace(0.0, 1.0, S_, **f32)
+            self.noise_c, self.u_fine = torch.zeros(N, S_, **f32), torch.zeros(N, Su_, **f32)
+            self.z_c, self.xyz_c, self.sigma_c = torch.empty(N, S_, **f32), torch.empty(N * S_, 3, **f32), torch.empty(N * S_, **f32)
+            self.z_all = torch.empty(N, S_ + Su_, **f32)
         # [counter0, counter1, m_eff, loss bits, peer-update status, max samples over ranks, parked sample count, kernel
         # status (NB200_STATUS_*: a field kernel's bounded mbarrier wait timed out)]: one 32-byte D2H returns everything the
         # host wants to know
@@ -320,12 +341,14 @@ class FusedTrainStep:
         self.x_en, self.d_x_en = torch.zeros(M, 32, **f16), torch.zeros(M, 32, **f16)
         self.rgba = torch.zeros(M, 4, **f16)
         self.act = torch.zeros(5, M, 64, **f16)
+        if self.dense is not None:          # the sample count is a constant: counter[0] = m_eff = N (S + Su)
+            self.stats[0], self.stats[2] = M, M
         self._fill_plan()
 
     def _fill_plan(self):
         m, enc = self.model, self.model.pos_en
         p = TrainPlan()
-        p.N, p.M_cap, p.C, p.H = self.N, self.m_cap, m.cascade, m.grid_size
+        p.N, p.M_cap, p.C, p.H = self.N, self.m_cap, int(getattr(m, 'cascade', 1)), int(getattr(m, 'grid_size', 128))
         p.L, p.base_res, p.gridtype, p.max_steps = enc.num_levels, int(enc.base_resolution), enc.gridtype_id, self.max_steps
         p.bound, p.dt_gamma = float(m.bound), self.dt_gamma
         p.S = float(np.log2(enc.per_level_scale))
@@ -341,7 +364,7 @@ class FusedTrainStep:
         use_mask = self.mask_weight > 0.0
         p.target_mask = a(self.target_mask) if use_mask else None
         p.render_mask, p.g_render_mask, p.mask_weight = a(self.render_mask), a(self.g_render_mask), self.mask_weight / self.rgb_weight
-        p.bitfield = a(m.density_bitfield)
+        p.bitfield = a(getattr(m, 'density_bitfield', None))
         p.params_flat, p.grads_flat, p.exp_avg, p.exp_avg_sq = a(self.params_flat), a(self.grads_flat), a(self.exp_avg), a(self.exp_avg_sq)
         p.hyper, p.sched, p.step = a(self.hyper), a(self.sched), a(self.step_count)
         es = 4
@@ -523,7 +546,11 @@ class FusedTrainStep:
         self._stage(staged)
         if self.perturb:
             self.noises.uniform_()
-        if not self.pipeline_update:
+        if self.dense is not None:
+            self._launch_dense_sampler(st)
+            _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(2), st), "train_phase(rest)")
+            self._update(st)
+        elif not self.pipeline_update:
             _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), st), "train_forward_backward")
             self._update(st)
         elif self.split_level:
@@ -555,6 +582,30 @@ class FusedTrainStep:
             main.wait_stream(self._side)
             _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(2), st), "train_phase(rest)")
         self.stats_host.copy_(self.stats, non_blocking=True)
+
+    def _launch_dense_sampler(self, st):
+        """the dense renderer's sampler (nerf/renderer.py:297-367) in five launches, writing the rows the rest of the step reads;
+        random draws in the reference's order: rand(N, S) for the stratified jitter, rand(N, Su) inside sample_pdf"""
+        p, m, lib = self.plan, self.model, self.lib
+        S_, Su_ = self.dense
+        V, N = C.c_void_p, C.c_uint32(self.N)
+        if self.perturb:
+            self.noise_c.uniform_()
+        self.u_fine.uniform_()              # training mode: sample_pdf draws u per ray (det=False)
+        L.LAUNCHES += 2 if self.perturb else 1
+        _check(lib.nb200_near_far_from_aabb(V(p.rays_o), V(p.rays_d), V(p.aabb), N, C.c_float(float(m.min_near)), V(p.nears),
+                                            V(p.fars), st), "near_far_from_aabb")
+        _check(lib.nb200_dense_coarse(V(p.rays_o), V(p.rays_d), V(p.nears), V(p.fars), V(p.aabb), V(self.lin.data_ptr()),
+                                      V(self.noise_c.data_ptr()) if self.perturb else None, N, C.c_uint32(S_),
+                                      V(self.z_c.data_ptr()), V(self.xyz_c.data_ptr()), st), "dense_coarse")
+        _check(lib.nb200_field_fused_forward(V(self.xyz_c.data_ptr()), None, C.c_float(p.bound), V(p.table), V(p.offsets),
+                                             C.c_uint32(p.L), C.c_float(p.S), C.c_uint32(p.base_res), C.c_uint32(p.gridtype),
+                                             C.c_int(0), C.c_uint32(0), V(p.w_fwd), V(self.sigma_c.data_ptr()), None, None, None,
+                                             None, C.c_uint32(self.N * S_), None, st), "field_fused_forward(density)")
+        _check(lib.nb200_dense_importance(V(p.rays_o), V(p.rays_d), V(p.nears), V(p.fars), V(p.aabb), V(self.z_c.data_ptr()),
+                                          V(self.sigma_c.data_ptr()), V(self.u_fine.data_ptr()), C.c_int(1), N, C.c_uint32(S_),
+                                          C.c_uint32(Su_), V(self.z_all.data_ptr()), V(p.xyzs), V(p.dirs), V(p.deltas), V(p.rays),
+                                          st), "dense_importance")
 
     def scaler_state(self):
         """(loss scale, skipped steps, optimiser steps taken) -- synchronises with the device"""
@@ -627,9 +678,13 @@ class FusedTrainStep:
     def forward_backward(self):
         """forward + backward only, not captured (tests): gradients accumulate into ``grads_flat``"""
         with torch.cuda.device(self.dev):
-            if self.perturb:
-                self.noises.uniform_()
-            _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
+            if self.dense is not None:
+                self._launch_dense_sampler(L.stream())
+                _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(2), L.stream()), "train_phase(rest)")
+            else:
+                if self.perturb:
+                    self.noises.uniform_()
+                _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
             self.stats_host.copy_(self.stats, non_blocking=True)
 
     def profile_stages(self, n_steps=10, flush=None):
@@ -719,9 +774,13 @@ class FusedTrainStep:
         if self.pipeline_update and not self._pending_update:
             # first step of a pipelined run: nothing to update yet -- forward + backward only, launched directly
             self._stage(staged)
-            if self.perturb:
-                self.noises.uniform_()
-            _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
+            if self.dense is not None:
+                self._launch_dense_sampler(L.stream())
+                _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(2), L.stream()), "train_phase(rest)")
+            else:
+                if self.perturb:
+                    self.noises.uniform_()
+                _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
             self.stats_host.copy_(self.stats, non_blocking=True)
             self._pending_update = True
             if self.split_level:            # the split form always enters a step with part 2 of the step before outstanding

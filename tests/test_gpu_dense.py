@@ -144,3 +144,55 @@ def test_fused_dense_renderer_matches_the_op_by_op_renderer(soft_mask, detach_bg
             assert_close(u, v, 2e-2, 2e-2 * np.abs(v).max(), name)
         else:
             assert np.abs(u - v).max() <= 0.2 * np.abs(v).max(), name
+
+
+def test_fused_dense_train_step_matches_autograd_over_the_dense_renderer():
+    """FusedTrainStep(dense=(64, 64)): sampler kernels + density-only fused launch + the occupancy path's encode .. encode^T,
+    against autograd over NeRFNetwork.run (training mode, the same rand(N, Su) draw through the same seed, no jitter):
+    loss rel 1e-4, every parameter gradient within 2e-2 of its largest entry; then the step trains (graph replay)."""
+    import torch.nn.functional as F
+    from customnerf_b200 import trainer, fused_trainer
+    from customnerf_b200.nerf import NeRFNetwork
+    w, N = 0.5, 1024
+    opt = trainer.make_opt(cuda_ray=False, train_conf=w)
+    nets = []
+    for _ in range(3):
+        torch.manual_seed(0)
+        net = NeRFNetwork(opt, encoding="hashgrid", log2_hashmap_size=15, desired_resolution=512).cuda()
+        with torch.no_grad():
+            net.pos_en.embeddings.uniform_(-0.5, 0.5)
+        nets.append(net.train())
+    ma, mb, mc = nets
+    o, d = _rays(N, seed=2)
+    g = torch.Generator().manual_seed(3)
+    tgt, gt_mask = torch.rand(N, 3, generator=g).cuda(), (torch.rand(N, generator=g) > 0.5).float().cuda()
+    torch.manual_seed(11)
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = ma.run(o[None], d[None], num_steps=64, upsample_steps=64, perturb=False)
+        loss_ref = (F.mse_loss(out["image"].reshape(-1, 3).float(), tgt, reduction="sum") / (3.0 * N)
+                    + w * F.mse_loss(out["render_mask"].reshape(-1).float(), gt_mask, reduction="sum") / N)
+    (loss_ref * fused_trainer.LOSS_SCALE).backward()
+    fs = fused_trainer.FusedTrainStep(mb, N, perturb=False, use_graph=False, mask_weight=w, dense=(64, 64), dynamic_loss_scale=False)
+    fs.set_batch(o, d, tgt, gt_mask)
+    torch.manual_seed(11)
+    fs.forward_backward()
+    loss, samples, used = fs.last_stats()
+    assert samples == used == N * 128
+    ref = float(loss_ref.detach())
+    assert abs(loss - ref) <= 1e-4 * abs(ref) + 1e-7, (loss, ref)
+    np.testing.assert_allclose(fs.z_all.cpu().numpy(), out["z_vals"].cpu().numpy(), rtol=0, atol=1e-6)
+    for name, off, n in fs.layout:
+        mod, attr = name.split(".")
+        g_ref = getattr(getattr(ma, mod), attr).grad.reshape(-1).float().cpu().numpy()
+        got = fs.grads_flat[off:off + n].cpu().numpy()
+        scale = np.abs(g_ref).max()
+        assert scale > 0 and np.abs(got - g_ref).max() <= 2e-2 * scale, (name, np.abs(got - g_ref).max(), scale)
+
+    # and it trains: captured graph, jittered samples
+    fs2 = fused_trainer.FusedTrainStep(mc, N, perturb=True, use_graph=True, mask_weight=w, dense=(64, 64))
+    fs2.set_batch(o, d, tgt, gt_mask)
+    losses = []
+    for _ in range(40):
+        fs2.step()
+        losses.append(fs2.last_stats()[0])
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < 0.8 * np.mean(losses[:5]), losses
