@@ -40,6 +40,9 @@ class FusedEditStep(FusedTrainStep):
     def __init__(self, model, n_rays, loss_fn, **kw):
         if kw.pop("pipeline_update", False):
             raise RuntimeError("FusedEditStep: pipeline_update is not supported (the loss sits between forward and backward)")
+        if getattr(model, "two_heads", False):
+            raise RuntimeError("FusedEditStep covers the single colour + mask head; the two-head RGB_network "
+                               "(--detach_mask_from_field / --mask_no_dir) renders through NeRFNetwork.render")
         if model.rgb_network.n_output_dims < 4:
             raise RuntimeError("FusedEditStep needs the mask head (opt.train_conf > 0: 4-output colour network)")
         super().__init__(model, n_rays, **kw)

@@ -41,10 +41,17 @@ def _split_mask_head(model, spread=12.0):
 
 
 def _models(**flags):
+    """two identical single-head models.  detach_mask_from_field is switched on AFTER construction: at construction time the
+    flag selects the two-head RGB_network (network_grid.py:117-118), which the fused kernels do not cover (separate test);
+    here it exercises the other half of its meaning, the mask composited with detached weights (renderer.py:437-441)"""
     from customnerf_b200 import trainer
+    late = {k: flags.pop(k) for k in ("detach_mask_from_field",) if k in flags}
     opt = dict(train_conf=0.01, **flags)
     a = trainer.build_scene_model(torch.device("cuda"), log2_hashmap_size=15, desired_resolution=512, seed=3, opt=trainer.make_opt(**opt))
     b = trainer.build_scene_model(torch.device("cuda"), log2_hashmap_size=15, desired_resolution=512, seed=3, opt=trainer.make_opt(**opt))
+    for m in (a, b):
+        for k, v in late.items():
+            setattr(m.opt, k, v)
     with torch.no_grad():
         a.pos_en.embeddings.uniform_(-0.5, 0.5)
         b.pos_en.embeddings.copy_(a.pos_en.embeddings)
@@ -78,7 +85,7 @@ def _make_loss(tgt, gt_mask):
                                    dict(soft_mask=True, detach_bg=False, detach_mask_from_field=True)])
 def test_edit_step_matches_autograd_composition(flags):
     from customnerf_b200 import trainer, fused_edit
-    ma, mb = _models(**flags)
+    ma, mb = _models(**dict(flags))
     o, d, tgt, gt_mask = _batch()
     loss_fn = _make_loss(tgt, gt_mask)
     # reference-shaped path: autograd over the drop-in ops
@@ -185,3 +192,15 @@ def test_gated_composite_kernels_match_the_cpu_oracle():
         got_s, got_q = gs.cpu().numpy(), grgba.cpu().numpy()
         for got, want, what in ((got_s, want_s, "d_sigma"), (got_q[:, :3], want_c, "d_rgb"), (got_q[:, 3], want_m, "d_mask")):
             assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), (soft, dbg, dmf, what, np.abs(got - want).max())
+
+
+def test_edit_step_refuses_the_two_head_network():
+    """--detach_mask_from_field builds RGB_network (two MLPs); the fused steps cover the single 3 + 1 head and say so"""
+    from customnerf_b200 import trainer, fused_edit, fused_trainer
+    opt = trainer.make_opt(train_conf=0.01, detach_mask_from_field=True)
+    m = trainer.build_scene_model(torch.device("cuda"), log2_hashmap_size=14, desired_resolution=256, opt=opt)
+    assert m.two_heads
+    with pytest.raises(RuntimeError, match="two-head"):
+        fused_edit.FusedEditStep(m, 256, lambda out: out["image"].sum())
+    with pytest.raises(RuntimeError, match="two-head"):
+        fused_trainer.FusedTrainStep(m, 256)
