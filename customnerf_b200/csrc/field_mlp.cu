@@ -88,6 +88,9 @@ k_freq_embed(const float *__restrict__ dirs, float *__restrict__ out, uint32_t M
     for (int j = 0; j < 27; j++) out[(size_t)g * 27 + j] = e[j];
 }
 
+// kColor = false: trunk + density head only (sigma; no view encoding, no colour layers, no saves): the occupancy update's
+// chunked density query and any density() call that already holds the features
+template <bool kColor>
 __global__ void __launch_bounds__(128, 2)
 k_field_forward(const FieldFwdArgs p, const __grid_constant__ CUtensorMap act_map) {
     extern __shared__ uint8_t smem_raw[];
@@ -165,7 +168,9 @@ k_field_forward(const FieldFwdArgs p, const __grid_constant__ CUtensorMap act_ma
         if (tile < ntiles && g < Mrows) {
             const uint4 *src = reinterpret_cast<const uint4 *>(p.x_en + (size_t)g * 32);
             nx0 = __ldg(src); nx1 = __ldg(src + 1); nx2 = __ldg(src + 2); nx3 = __ldg(src + 3);
-            nd0 = __ldg(p.dirs + (size_t)g * 3); nd1 = __ldg(p.dirs + (size_t)g * 3 + 1); nd2 = __ldg(p.dirs + (size_t)g * 3 + 2);
+            if (kColor) {
+                nd0 = __ldg(p.dirs + (size_t)g * 3); nd1 = __ldg(p.dirs + (size_t)g * 3 + 1); nd2 = __ldg(p.dirs + (size_t)g * 3 + 2);
+            }
             npx = __ldg(p.xyz + (size_t)g * 3); npy = __ldg(p.xyz + (size_t)g * 3 + 1); npz = __ldg(p.xyz + (size_t)g * 3 + 2);
         }
     };
@@ -175,7 +180,7 @@ k_field_forward(const FieldFwdArgs p, const __grid_constant__ CUtensorMap act_ma
         *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 1)) = nx1;
         *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 2)) = nx2;
         *reinterpret_cast<uint4 *>(xv + umma::sw128_offset(tid, 3)) = nx3;
-        write_view_chunks(xv, tid, nd0, nd1, nd2, true);
+        if (kColor) write_view_chunks(xv, tid, nd0, nd1, nd2, true);
         (void)valid;
     };
 
@@ -220,19 +225,31 @@ k_field_forward(const FieldFwdArgs p, const __grid_constant__ CUtensorMap act_ma
         // ---- density layer 1: raw = hd Wd2^T (N = 16, lane 0 is the output); sigma = exp(raw + 5 exp(-|x|^2 / 0.08))
         if (tid == 0) mma_run(sH0, 0, sW + F_WD2, 0, 4, ID16, true);
         store_tile(sH0, 3, row0);
+        float cx = px, cy = py, cz = pz;
+        if (!kColor) {                      // density only: this is the tile's last MMA -- stage the next tile's inputs under it
+            write_xv(true);
+            px = npx; py = npy; pz = npz;
+        }
         sync_mma();
         {
             uint32_t r[16];
             umma::tmem_ld16(trow, r);
             umma::tmem_ld_wait();
             if (valid) {
-                const float gauss = 5.0f * expf(-(px * px + py * py + pz * pz) / (2 * 0.2f * 0.2f));
+                const float gauss = 5.0f * expf(-(cx * cx + cy * cy + cz * cz) / (2 * 0.2f * 0.2f));
                 const float arg = __uint_as_float(r[0]) + gauss;
                 p.sigma[g] = expf(arg);
                 if (p.sigma_arg) p.sigma_arg[g] = arg;
             }
         }
         drain1();
+        if (!kColor) {
+            umma::fence_proxy_async();      // the XV rows just written feed the next tile's first MMA
+            umma::fence_before_sync();
+            __syncthreads();
+            umma::fence_after_sync();
+            continue;
+        }
         umma::fence_before_sync();
         __syncthreads();
         umma::fence_after_sync();
@@ -761,6 +778,26 @@ k_field_wgrad_reduce(const float *__restrict__ slabs, uint32_t grid, uint32_t M,
 
 constexpr int kMaxDevices = 64;
 uint32_t *g_status_word[kMaxDevices] = {};      // per device ordinal; registered by nb200_set_kernel_status_word
+
+template <bool kColor>
+int launch_field_forward(const FieldFwdArgs &a, const CUtensorMap &act_map, uint32_t M, cudaStream_t st) {
+    // per device: the attribute belongs to the function on the CURRENT device (one flag per device ordinal)
+    static bool configured[kMaxDevices] = {};
+    const int smem = (int)S_FWD_BYTES + 1024;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_field_forward<kColor>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
+    }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t ntiles = (M + 127) / 128;
+    const uint32_t grid = ntiles < (uint32_t)(2 * sms) ? ntiles : (uint32_t)(2 * sms);
+    k_field_forward<kColor><<<grid, 128, smem, st>>>(a, act_map);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
 }  // namespace
 
 uint32_t *nb_kernel_status_word() {
@@ -845,25 +882,14 @@ static int make_act_map(CUtensorMap *map, void *act, uint32_t M) {
 int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, const void *fwd_img, float *sigma,
                         float *sigma_arg, void *rgba, void *act, uint32_t M, const int32_t *count_dev, void *stream) {
     if (M == 0) return 0;
-    if (!x_en || !xyz || !dirs || !fwd_img || !sigma || !rgba) return NB200_E_BAD_ARG;
-    // per device: the attribute belongs to the function on the CURRENT device (one flag per device ordinal)
-    static bool configured[kMaxDevices] = {};
-    const int smem = (int)S_FWD_BYTES + 1024;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_field_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
-    }
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!x_en || !xyz || !fwd_img || !sigma) return NB200_E_BAD_ARG;
+    const bool color = rgba != nullptr;         // rgba == NULL: density only (dirs unused, nothing saved)
+    if (color ? !dirs : act != nullptr) return NB200_E_BAD_ARG;
     FieldFwdArgs a;
     a.x_en = (const __half *)x_en; a.xyz = xyz; a.dirs = dirs; a.wimg = (const uint8_t *)fwd_img;
     a.sigma = sigma; a.sigma_arg = sigma_arg; a.rgba = (__half *)rgba; a.act = (__half *)act; a.M = M;
     a.count_dev = count_dev;
     a.status = nb_kernel_status_word();
-    const uint32_t ntiles = (M + 127) / 128;
-    const uint32_t grid = ntiles < (uint32_t)(2 * sms) ? ntiles : (uint32_t)(2 * sms);
     CUtensorMap act_map;
     memset(&act_map, 0, sizeof(act_map));
     if (act) {
@@ -871,9 +897,8 @@ int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, c
         const int rc = make_act_map(&act_map, act, M);
         if (rc) return rc;
     }
-    k_field_forward<<<grid, 128, smem, nb_stream(stream)>>>(a, act_map);
-    NB_LAUNCH_CHECK();
-    return 0;
+    return color ? launch_field_forward<true>(a, act_map, M, nb_stream(stream))
+                 : launch_field_forward<false>(a, act_map, M, nb_stream(stream));
 }
 
 int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,

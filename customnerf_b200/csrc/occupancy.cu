@@ -14,6 +14,31 @@ namespace {
 
 constexpr uint32_t kOccBlocks = 592;      // 4 per SM; the partial-sum buffer has this many entries
 
+// rows [row0, row0 + n) of the density query in tmp_grid order (cascade-major, Morton index within a cascade) -> positions.
+// update_extra_state (renderer.py:1680-1690): cell (x, y, z) <- Morton index, position = centre * (bound_c - hgs) +
+// (2 u - 1) * hgs with hgs = bound_c / G, bound_c = min(2^cas, bound); every product / sum rounded separately, as the chain
+// of torch kernels rounds them (the same lines as the SRC_OCC producer of field_fused.cu: the two paths are bit-identical)
+__global__ void __launch_bounds__(256)
+k_occ_positions(const float *__restrict__ cell_xyz, const float *__restrict__ noise, uint32_t G, float bound, uint32_t row0,
+                uint32_t n, float *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t g = row0 + i, G3 = G * G * G;
+    const uint32_t cas = g / G3, m = g - cas * G3;
+    const uint32_t cx = nb_morton3D_invert(m), cy = nb_morton3D_invert(m >> 1), cz = nb_morton3D_invert(m >> 2);
+    const size_t c = ((size_t)cx * G + cy) * G + cz;
+    const float bc = fminf((float)(1u << cas), bound), hgs = bc / (float)G, span = bc - hgs;
+    float px = __fmul_rn(__ldg(cell_xyz + c * 3), span), py = __fmul_rn(__ldg(cell_xyz + c * 3 + 1), span),
+          pz = __fmul_rn(__ldg(cell_xyz + c * 3 + 2), span);
+    if (noise) {
+        const float *u = noise + ((size_t)cas * G3 + c) * 3;
+        px = __fadd_rn(px, __fmul_rn(__fsub_rn(__fmul_rn(__ldg(u), 2.0f), 1.0f), hgs));
+        py = __fadd_rn(py, __fmul_rn(__fsub_rn(__fmul_rn(__ldg(u + 1), 2.0f), 1.0f), hgs));
+        pz = __fadd_rn(pz, __fmul_rn(__fsub_rn(__fmul_rn(__ldg(u + 2), 2.0f), 1.0f), hgs));
+    }
+    out[(size_t)i * 3] = px; out[(size_t)i * 3 + 1] = py; out[(size_t)i * 3 + 2] = pz;
+}
+
 // state (8 x 4 bytes): [0] mean density f32, [1] threshold f32, [2] mean_count i32 (unchanged when total_step == 0),
 // [3] number of valid cells u32
 __global__ void __launch_bounds__(256)
@@ -84,6 +109,31 @@ __global__ void k_packbits_dev(const float *__restrict__ grid, uint32_t N, const
 }  // namespace
 
 extern "C" {
+
+// The density query as encoder + density-only field launches over chunks of the grid (the standalone encoder runs at full
+// occupancy with the whole L1; the one-kernel form nb200_occ_density has 8 gather warps per SM): per chunk positions ->
+// nb200_fs_encode_forward -> nb200_field_forward(rgba = NULL) writing sigma straight into tmp_grid (rows are in tmp_grid
+// order).  chunk_rows samples of scratch: xyz_buf f32 [chunk_rows,3], x_en_buf f16 [chunk_rows,32] -- sized to stay in L2.
+int nb200_occ_density_chunked(const float *cell_xyz, const float *noise, uint32_t G, uint32_t cascade, float bound,
+                              const float *table, const int32_t *offsets, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                              int align_corners, uint32_t interp, const void *fwd_img, float *tmp_grid, float *xyz_buf,
+                              void *x_en_buf, uint32_t chunk_rows, void *stream) {
+    if (!cell_xyz || !table || !offsets || !fwd_img || !tmp_grid || !xyz_buf || !x_en_buf || !(bound > 0.0f) || G == 0 ||
+        G > 1024 || cascade == 0 || cascade > 8 || (uint64_t)cascade * G * G * G > 0x7fffffffull || chunk_rows == 0)
+        return NB200_E_BAD_ARG;
+    const uint32_t total = cascade * G * G * G;
+    for (uint32_t row0 = 0; row0 < total; row0 += chunk_rows) {
+        const uint32_t n = total - row0 < chunk_rows ? total - row0 : chunk_rows;
+        k_occ_positions<<<nb_div_up(n, 256), 256, 0, nb_stream(stream)>>>(cell_xyz, noise, G, bound, row0, n, xyz_buf);
+        NB_LAUNCH_CHECK();
+        int rc;
+        if ((rc = nb200_fs_encode_forward(xyz_buf, bound, table, offsets, x_en_buf, n, L, S, H, gridtype, align_corners, interp,
+                                          nullptr, stream))) return rc;
+        if ((rc = nb200_field_forward(x_en_buf, xyz_buf, nullptr, fwd_img, tmp_grid + row0, nullptr, nullptr, nullptr, n,
+                                      nullptr, stream))) return rc;
+    }
+    return 0;
+}
 
 uint32_t nb200_occ_scratch_bytes(void) { return kOccBlocks * (uint32_t)(sizeof(double) + sizeof(uint32_t)); }
 

@@ -119,6 +119,8 @@ class NeRFNetwork(NeRFRenderer):
         # host-driven n_step loop; set False to run the loop of NeRFRenderer.run_cuda
         self.fast_inference = True
         self._infer = None
+        # occupancy update: cells per encoder + density launch pair (0: the one-kernel form nb200_occ_density)
+        self.occ_chunk_rows = 1 << 20
 
     def background(self, d):
         return torch.zeros(d.size(), dtype=d.dtype, device=d.device)
@@ -209,6 +211,26 @@ class NeRFNetwork(NeRFRenderer):
         for cas in range(self.cascade):
             noise[cas].copy_(torch.rand_like(xyzs))         # the reference's draws, one per cascade (:1690)
         fwd_img, _ = self._packed.get(self.network.params, self.density_network.params, self.rgb_network.params)
+        import os
+        chunk = int(os.environ.get("NB200_OCC_CHUNK", self.occ_chunk_rows))
+        if chunk > 0:
+            # default: encoder + density-only field launches over chunks whose features stay in L2 (measured on B200:
+            # profiles/README.md -- the standalone encoder runs at full occupancy, the one-kernel form has 8 gather warps
+            # per SM); bit-identical to the one-kernel form
+            chunk = (chunk + 127) // 128 * 128
+            buf = self.__dict__.get('_occ_chunk_buf')
+            if buf is None or buf[0].device != dev or buf[0].shape[0] != chunk:
+                buf = self.__dict__['_occ_chunk_buf'] = (torch.empty(chunk, 3, dtype=torch.float32, device=dev),
+                                                         torch.empty(chunk, 32, dtype=torch.float16, device=dev))
+            L.check(L.lib().nb200_occ_density_chunked(L.ptr(xyzs), L.ptr(noise), L.u32(self.grid_size), L.u32(self.cascade),
+                                                      L.f32(float(self.bound)), L.ptr(enc.embeddings.detach()), L.ptr(enc.offsets),
+                                                      L.u32(enc.num_levels), L.f32(float(np.log2(enc.per_level_scale))),
+                                                      L.u32(int(enc.base_resolution)), L.u32(enc.gridtype_id),
+                                                      L.i32(int(enc.align_corners)), L.u32(enc.interp_id), L.ptr(fwd_img),
+                                                      L.ptr(tmp_grid), L.ptr(buf[0]), L.ptr(buf[1]), L.u32(chunk), L.stream()),
+                    "occ_density_chunked")
+            L.LAUNCHES += 3 * ((self.cascade * self.grid_size ** 3 + chunk - 1) // chunk)
+            return
         L.check(L.lib().nb200_occ_density(L.ptr(xyzs), L.ptr(noise), L.u32(self.grid_size), L.u32(self.cascade),
                                           L.f32(float(self.bound)), L.ptr(enc.embeddings.detach()), L.ptr(enc.offsets),
                                           L.u32(enc.num_levels), L.f32(float(np.log2(enc.per_level_scale))),

@@ -189,6 +189,7 @@ int nb200_field_pack_weights_commit(const float *trunk, const float *density, co
  * count_dev (device i32, may be NULL): when given only rows < min(M, *count_dev) are evaluated. */
 int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, const void *fwd_img, float *sigma,
                         float *sigma_arg, void *rgba, void *act, uint32_t M, const int32_t *count_dev, void *stream);
+/* rgba == NULL (then act must be NULL, dirs is unused): trunk + density head only -- NeRFNetwork.density (network_grid.py:179-193) */
 
 /* Backward of nb200_field_forward.  d_sigma f32 [M], d_rgba f32 [M,4] are the upstream gradients; sigma_arg, rgba, act
  * are what the forward saved.  Writes d_x_en f16 [M,32] (gradient of the grid encoding, input of
@@ -241,6 +242,12 @@ int nb200_field_fused_forward(const float *xyz, const float *dirs, float bound, 
 int nb200_occ_density(const float *cell_xyz, const float *noise, uint32_t G, uint32_t cascade, float bound, const float *table,
                       const int32_t *offsets, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
                       uint32_t interp, const void *fwd_img, float *tmp_grid, void *stream);
+/* the same query as encoder + density-only field launches over chunks of chunk_rows cells (default of update_extra_state:
+ * measured faster than the one-kernel form, profiles/); xyz_buf f32 [chunk_rows,3], x_en_buf f16 [chunk_rows,32] scratch */
+int nb200_occ_density_chunked(const float *cell_xyz, const float *noise, uint32_t G, uint32_t cascade, float bound,
+                              const float *table, const int32_t *offsets, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                              int align_corners, uint32_t interp, const void *fwd_img, float *tmp_grid, float *xyz_buf,
+                              void *x_en_buf, uint32_t chunk_rows, void *stream);
 uint32_t nb200_occ_scratch_bytes(void);
 int nb200_occ_finalize(float *density_grid, const float *tmp_grid, uint32_t n_cells, float decay, float density_thresh,
                        const int32_t *step_counter, uint32_t total_step, uint8_t *bitfield, float *state, void *scratch,

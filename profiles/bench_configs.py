@@ -63,12 +63,15 @@ def c2_inference():
         ms_loop = timeit(lambda: model.render(o[None], d[None], perturb=False), 3, warm=1)
         model.fast_inference = True
         model.train()
-        upd = timeit(lambda: model.update_extra_state(), 5, warm=2)                  # fused: one density kernel + 3 small launches
+        upd = timeit(lambda: model.update_extra_state(), 5, warm=2)                  # default: encoder + density-only field over 8 chunks
+        model.occ_chunk_rows = 0
+        upd_one = timeit(lambda: model.update_extra_state(), 5, warm=2)              # the one-kernel density query
+        model.occ_chunk_rows = 1 << 20
         model.density = model.density                                               # instance attribute -> the op-by-op path
         upd_ops = timeit(lambda: model.update_extra_state(), 3, warm=1)
     return {"config": "configs[2] inference 248x184 (45632 rays), device-driven rounds; occupancy update of 2x128^3 cells",
             "ms_per_frame": ms, "rays_per_s": o.shape[0] / ms * 1e3, "ms_per_frame_host_loop": ms_loop, "update_extra_state_ms": upd,
-            "update_extra_state_op_by_op_ms": upd_ops}
+            "update_extra_state_one_kernel_ms": upd_one, "update_extra_state_op_by_op_ms": upd_ops}
 
 
 def c3_lgie():

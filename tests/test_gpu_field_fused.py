@@ -143,27 +143,31 @@ def test_fused_forward_honours_the_device_side_row_count():
 
 
 def test_fused_occupancy_update_equals_the_op_by_op_update():
-    """update_extra_state with the one-kernel density query (nb200_occ_density) against the reference-shaped op-by-op path
-    (cell table -> jitter -> self.density per cascade -> scatter by Morton index), same generator state: bit-identical
-    density grid and bit field, same mean density and mean_count."""
+    """update_extra_state three ways -- encoder + density-only field launches over chunks (nb200_occ_density_chunked, the
+    default; a chunk size that does not divide the grid), the one-kernel density query (nb200_occ_density), and the
+    reference-shaped op-by-op path (cell table -> jitter -> self.density per cascade -> scatter by Morton index) -- from the
+    same generator state: bit-identical density grid and bit field, same mean density and mean_count."""
     grids = {}
-    for fused in (True, False):
+    for mode in ("chunked", "one_kernel", "ops"):
         net, opt = _net(train_conf=0, seed=4)
         net.fuse_encoder = True
         net.local_step = 2
         net.step_counter[:2, 0] = torch.tensor([111, 224], dtype=torch.int32, device="cuda")
-        if not fused:
+        if mode == "ops":
             net.density = net.density               # an instance attribute: the stock-field test fails -> op-by-op path
+        net.occ_chunk_rows = {"chunked": 300000, "one_kernel": 0, "ops": 0}[mode]
         torch.manual_seed(77)
         with torch.autocast("cuda", dtype=torch.float16):
             net.update_extra_state()
             net.update_extra_state()
-        grids[fused] = (net.density_grid.clone(), net.density_bitfield.clone(), net.mean_density, net.mean_count, net.iter_density)
-    a, b = grids[True], grids[False]
-    assert torch.equal(a[0], b[0]), float((a[0] - b[0]).abs().max())
-    assert torch.equal(a[1], b[1])
-    assert a[2] == b[2] and a[2] > 0 and a[3] == b[3] == 167 and a[4] == b[4] == 2
-    assert int(a[1].count_nonzero()) > 0
+        grids[mode] = (net.density_grid.clone(), net.density_bitfield.clone(), net.mean_density, net.mean_count, net.iter_density)
+    b = grids["ops"]
+    for mode in ("chunked", "one_kernel"):
+        a = grids[mode]
+        assert torch.equal(a[0], b[0]), (mode, float((a[0] - b[0]).abs().max()))
+        assert torch.equal(a[1], b[1]), mode
+        assert a[2] == b[2] and a[2] > 0 and a[3] == b[3] == 167 and a[4] == b[4] == 2, mode
+    assert int(b[1].count_nonzero()) > 0
 
 
 def test_fused_train_step_matches_the_two_kernel_step():
