@@ -1093,6 +1093,72 @@ k_march_rays_dev(const int32_t *__restrict__ state, const int32_t *__restrict__ 
     }
 }
 
+// The same round from the RECORDS of one whole-ray traversal (nb200_march_rays_train_count's speculative-segment march, once per
+// frame): a round then only looks up the ray's next n_step recorded sample parameters instead of walking the grid from
+// rays_t again -- the per-round DDA (one thread per ray, hundreds of dependent voxel visits in the first rounds) was 58 %
+// of an inference frame.  Bit-identical by construction, with a check: the records are the chain started at the ray's
+// (perturbed) near point; a round may consume them only if rays_t -- which compositing re-accumulates from the deltas,
+// t += delta (raymarching.cu:1058), normally exactly -- still equals the parameter the chain reached after the samples
+// consumed so far.  A ray for which it does not (or whose record list was truncated at max_steps / tcap) walks the grid
+// from rays_t like k_march_rays_dev, from then on (consumed = -1; state[5] counts such rays per frame).
+__global__ void __launch_bounds__(128)
+k_march_rays_rec(int32_t *__restrict__ state, const int32_t *__restrict__ rays_alive, const float *__restrict__ rays_t,
+                 const float *__restrict__ rays_o, const float *__restrict__ rays_d, float bound, float dt_gamma,
+                 uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *__restrict__ grid,
+                 const float *__restrict__ fars, float *__restrict__ xyzs, float *__restrict__ dirs,
+                 float *__restrict__ deltas, const float *__restrict__ noises, const int32_t *__restrict__ rays,
+                 const float *__restrict__ trec, uint32_t tcap, int32_t *__restrict__ consumed) {
+    const uint32_t n_alive = (uint32_t)state[0], n_step = (uint32_t)state[1];
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int32_t index = rays_alive[n];
+    RayCtx r;
+    rm_setup(r, rays_o + (size_t)index * 3, rays_d + (size_t)index * 3, grid, bound, dt_gamma, max_steps, C, H);
+    float *px = xyzs + (size_t)n * n_step * 3, *pd = dirs + (size_t)n * n_step * 3, *pl = deltas + (size_t)n * n_step * 2;
+    float t = rays_t[index];
+    const bool first_round = state[2] == 0;
+    t = __fmaf_rn(rm_dt(r, t), (noises && first_round) ? noises[n] : 0.0f, t);      // perturb in the first round only (:677)
+    const uint32_t num = (uint32_t)rays[index * 3 + 2];
+    const int32_t c = consumed[index];
+    const float *rec = trec + (size_t)index * tcap;
+    bool fast = c >= 0 && num <= tcap && num < max_steps;
+    if (fast && c > 0) { const float tp = rec[c - 1]; fast = t == __fadd_rn(tp, rm_dt(r, tp)); }
+    if (fast && c == 0) fast = first_round;
+    uint32_t step = 0;
+    if (fast) {
+        float last_t = t;
+        for (; step < n_step && (uint32_t)c + step < num; step++) {
+            const float ti = rec[c + step], dt = rm_dt(r, ti), tn = __fadd_rn(ti, dt);
+            px[0] = rm_clamp(__fmaf_rn(ti, r.dx, r.ox), -r.bound, r.bound);
+            px[1] = rm_clamp(__fmaf_rn(ti, r.dy, r.oy), -r.bound, r.bound);
+            px[2] = rm_clamp(__fmaf_rn(ti, r.dz, r.oz), -r.bound, r.bound);
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            pl[0] = dt; pl[1] = __fsub_rn(tn, last_t);
+            last_t = tn;
+            px += 3; pd += 3; pl += 2;
+        }
+        consumed[index] = c + (int32_t)step;
+    } else {
+        if (c >= 0) { consumed[index] = -1; atomicAdd(state + 5, 1); }
+        const float far = fars[index];
+        float last_t = t, x, y, z, dt;
+        while (t < far && step < n_step) {
+            if (rm_step(r, t, x, y, z, dt)) {
+                px[0] = x; px[1] = y; px[2] = z;
+                pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+                t = __fadd_rn(t, dt);
+                pl[0] = dt; pl[1] = __fsub_rn(t, last_t);
+                last_t = t;
+                px += 3; pd += 3; pl += 2; step++;
+            }
+        }
+    }
+    for (; step < n_step; step++) {          // unused slots read as "ray finished" (the reference zero-fills, raymarching.py:391-393)
+        px[0] = px[1] = px[2] = 0.0f; pd[0] = pd[1] = pd[2] = 0.0f; pl[0] = pl[1] = 0.0f;
+        px += 3; pd += 3; pl += 2;
+    }
+}
+
 template <typename TC>
 __global__ void __launch_bounds__(128)
 k_composite_rays_dev(const int32_t *__restrict__ state, float T_thresh, int32_t *__restrict__ rays_alive,
@@ -1476,6 +1542,20 @@ int nb200_march_rays_dev(const int32_t *state, uint32_t N, const int32_t *rays_a
     if (!state) return NB200_E_BAD_ARG;
     k_march_rays_dev<<<nb_div_up(N, 128), 128, 0, nb_stream(stream)>>>(state, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma,
                                                                        max_steps, C, H, grid, fars, xyzs, dirs, deltas, noises);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nb200_march_rays_rec(int32_t *state, uint32_t N, const int32_t *rays_alive, const float *rays_t, const float *rays_o,
+                         const float *rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                         const uint8_t *grid, const float *fars, float *xyzs, float *dirs, float *deltas, const float *noises,
+                         const int32_t *rays, const int32_t *scratch, int32_t *consumed, void *stream) {
+    if (N == 0) return 0;
+    if (!state || !rays || !scratch || !consumed) return NB200_E_BAD_ARG;
+    k_march_rays_rec<<<nb_div_up(N, 128), 128, 0, nb_stream(stream)>>>(state, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma,
+                                                                       max_steps, C, H, grid, fars, xyzs, dirs, deltas, noises, rays,
+                                                                       march_trec(const_cast<int32_t *>(scratch), N), march_tcap(N),
+                                                                       consumed);
     NB_LAUNCH_CHECK();
     return 0;
 }

@@ -22,7 +22,8 @@ def _check(rc, what):
 
 
 class FusedInference:
-    def __init__(self, model, n_rays, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, rounds_per_check=8, use_graph=True):
+    def __init__(self, model, n_rays, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, rounds_per_check=8, use_graph=True,
+                 recorded_march=True):
         if not model.cuda_ray:
             raise RuntimeError("FusedInference drives the occupancy (cuda_ray) path")
         if model.pos_en.input_dim != 3 or model.pos_en.level_dim != 2 or model.pos_en_dim != 32:
@@ -49,6 +50,17 @@ class FusedInference:
         self.w_fwd = torch.empty(nb, dtype=torch.uint8, device=dev)
         self.w_bwd = torch.empty(nb, dtype=torch.uint8, device=dev)
         self.M_cap = M
+        # recorded_march: ONE whole-ray traversal per frame (the training march's speculative-segment kernel) records every
+        # ray's sample parameters; a round then looks its next n_step samples up instead of walking the occupancy grid from
+        # rays_t again (csrc/raymarching.cu: k_march_rays_rec; same samples bit for bit, rays that leave the recorded chain
+        # fall back to the walk -- state[5] counts them)
+        self.recorded_march = bool(recorded_march)
+        if self.recorded_march:
+            self.lib.nb200_march_scratch_ints.restype = C.c_uint32
+            self.rec_rays = torch.zeros(N, 3, **i32)
+            self.rec_counter = torch.zeros(2, **i32)
+            self.rec_scratch = torch.empty(int(self.lib.nb200_march_scratch_ints(L.u32(N))), **i32)
+            self.consumed = torch.zeros(N, **i32)
         self.graph = None
         self.use_noise = False
         self.rounds = 0
@@ -59,11 +71,19 @@ class FusedInference:
         p = L.ptr
         cnt = C.c_void_p(self.state.data_ptr() + 12)
         _check(lib.nb200_infer_plan(p(self.state), L.u32(self.N), L.u32(self.max_steps), st), "infer_plan")
-        _check(lib.nb200_march_rays_dev(p(self.state), L.u32(self.N), p(self.rays_alive), p(self.rays_t), p(self.rays_o),
-                                        p(self.rays_d), L.f32(m.bound), L.f32(self.dt_gamma), L.u32(self.max_steps),
-                                        L.u32(m.cascade), L.u32(m.grid_size), p(m.density_bitfield), p(self.fars),
-                                        p(self.xyzs), p(self.dirs), p(self.deltas),
-                                        p(self.noises if self.use_noise else None), st), "march_rays_dev")
+        if self.recorded_march:
+            _check(lib.nb200_march_rays_rec(p(self.state), L.u32(self.N), p(self.rays_alive), p(self.rays_t), p(self.rays_o),
+                                            p(self.rays_d), L.f32(m.bound), L.f32(self.dt_gamma), L.u32(self.max_steps),
+                                            L.u32(m.cascade), L.u32(m.grid_size), p(m.density_bitfield), p(self.fars),
+                                            p(self.xyzs), p(self.dirs), p(self.deltas),
+                                            p(self.noises if self.use_noise else None), p(self.rec_rays), p(self.rec_scratch),
+                                            p(self.consumed), st), "march_rays_rec")
+        else:
+            _check(lib.nb200_march_rays_dev(p(self.state), L.u32(self.N), p(self.rays_alive), p(self.rays_t), p(self.rays_o),
+                                            p(self.rays_d), L.f32(m.bound), L.f32(self.dt_gamma), L.u32(self.max_steps),
+                                            L.u32(m.cascade), L.u32(m.grid_size), p(m.density_bitfield), p(self.fars),
+                                            p(self.xyzs), p(self.dirs), p(self.deltas),
+                                            p(self.noises if self.use_noise else None), st), "march_rays_dev")
         # grid gather + field network in one launch: the features never exist in HBM (csrc/field_fused.cu)
         _check(lib.nb200_field_fused_forward(p(self.xyzs), p(self.dirs), L.f32(m.bound), p(enc.embeddings.detach()), p(enc.offsets),
                                              L.u32(enc.num_levels), L.f32(float(np.log2(enc.per_level_scale))),
@@ -77,7 +97,10 @@ class FusedInference:
         L.LAUNCHES += 7
 
     def _capture(self):
-        keep = [t.clone() for t in (self.state, self.rays_alive, self.rays_t, self.weights_sum, self.depth, self.image)]
+        live = [self.state, self.rays_alive, self.rays_t, self.weights_sum, self.depth, self.image]
+        if self.recorded_march:
+            live.append(self.consumed)
+        keep = [t.clone() for t in live]
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
@@ -87,7 +110,7 @@ class FusedInference:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._round()
-        for t, k in zip((self.state, self.rays_alive, self.rays_t, self.weights_sum, self.depth, self.image), keep):
+        for t, k in zip(live, keep):
             t.copy_(k)
         self.graph = g
 
@@ -113,6 +136,15 @@ class FusedInference:
                 self.use_noise, self.graph = bool(perturb), None
             if perturb:
                 self.noises.copy_(noises) if noises is not None else self.noises.uniform_()
+            if self.recorded_march:         # the frame's one traversal: every ray's sample parameters up to its far point
+                self.rec_counter.zero_()
+                _check(self.lib.nb200_march_rays_train_count(
+                    L.ptr(self.rays_o), L.ptr(self.rays_d), L.ptr(m.density_bitfield), L.f32(m.bound), L.f32(self.dt_gamma),
+                    L.u32(self.max_steps), L.u32(self.N), L.u32(m.cascade), L.u32(m.grid_size), L.ptr(self.nears), L.ptr(self.fars),
+                    L.ptr(self.noises if self.use_noise else None), L.ptr(self.rec_rays), L.ptr(self.rec_counter),
+                    L.ptr(self.rec_scratch), L.stream()), "march_rays_train_count")
+                self.consumed.zero_()
+                L.LAUNCHES += 3
             if self.use_graph and self.graph is None:
                 self._capture()
             self.rounds = 0
@@ -128,4 +160,5 @@ class FusedInference:
                 torch.cuda.current_stream(self.dev).synchronize()
                 if int(self.state_host[0]) <= 0 or self.rounds > self.max_steps + self.rounds_per_check:
                     break
+            self.march_fallbacks = int(self.state_host[5])      # rays that left the recorded chain and walked the grid instead
         return self.weights_sum, self.depth, self.image, self.nears, self.fars

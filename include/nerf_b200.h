@@ -164,6 +164,15 @@ int nb200_march_rays_dev(const int32_t *state, uint32_t N, const int32_t *rays_a
                          const float *rays_o, const float *rays_d, float bound, float dt_gamma, uint32_t max_steps,
                          uint32_t C, uint32_t H, const uint8_t *grid, const float *fars, float *xyzs, float *dirs,
                          float *deltas, const float *noises, void *stream);
+/* nb200_march_rays_dev served from the sample records of ONE whole-ray traversal per frame: call
+ * nb200_march_rays_train_count(rays_o, rays_d, grid, ..., nears, fars, noises, rays, counter, scratch) once (the
+ * speculative-segment march; rays i32 [N,3], scratch of nb200_march_scratch_ints(N) ints), zero consumed i32 [N], then this
+ * entry every round.  Same samples bit for bit: a ray whose rays_t has left the recorded chain (compositing re-accumulates
+ * it from the deltas) or whose records were truncated walks the grid as nb200_march_rays_dev does; state[5] counts them. */
+int nb200_march_rays_rec(int32_t *state, uint32_t N, const int32_t *rays_alive, const float *rays_t, const float *rays_o,
+                         const float *rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                         const uint8_t *grid, const float *fars, float *xyzs, float *dirs, float *deltas, const float *noises,
+                         const int32_t *rays, const int32_t *scratch, int32_t *consumed, void *stream);
 int nb200_composite_rays_dev(const int32_t *state, uint32_t N, float T_thresh, int32_t *rays_alive, float *rays_t,
                              const float *sigmas, const void *rgba, const float *deltas, float *weights_sum, float *depth,
                              float *image, void *stream);

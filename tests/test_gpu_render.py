@@ -250,9 +250,25 @@ def test_device_driven_inference_matches_the_host_loop(scene):
         net.fast_inference = True
         fast = net.render(o[None], d[None], perturb=False)
         again = net.render(o[None], d[None], perturb=False)           # graph replay on a re-used instance
+        assert net._infer.recorded_march                               # default: rounds served from one traversal's records
+        fallbacks = net._infer.march_fallbacks
+        net._infer.recorded_march, net._infer.graph = False, None      # every round walks the grid from rays_t
+        walk = net.render(o[None], d[None], perturb=False)
+        net._infer.recorded_march, net._infer.graph = True, None
+        noise = torch.rand(4096, device="cuda")
+        pert = {}
+        for rec in (True, False):                                      # perturbed first round, both forms, same draws
+            net._infer.recorded_march, net._infer.graph = rec, None
+            w, dp, im, _, _ = net._infer.render(o, d, perturb=True, noises=noise)
+            pert[rec] = (w.clone(), dp.clone(), im.clone())
+        net._infer.recorded_march, net._infer.graph = True, None
     assert net._infer is not None and net._infer.rounds >= 8
     assert float(slow["weights_sum"].sum()) > 100
     for k in ("image", "depth", "weights_sum"):
         assert torch.equal(fast[k], slow[k]), k
         assert torch.equal(again[k], slow[k]), k
+        assert torch.equal(walk[k], slow[k]), k
     assert torch.equal(fast["mask"], slow["mask"])
+    for a, b in zip(pert[True], pert[False]):
+        assert torch.equal(a, b)
+    assert 0 <= fallbacks <= 0.05 * 4096, fallbacks                    # the recorded chain serves (nearly) every ray
