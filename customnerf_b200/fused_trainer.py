@@ -188,10 +188,12 @@ class FusedTrainStep:
         self.pipeline_update = bool(pipeline_update)
         self.update_shape = tuple(int(v) for v in update_shape) if update_shape else None   # (CTAs, threads, unroll) of the pipelined sweep
         # split update (ray-sharded, peer-memory update, pipelined; OFF by default, split_level=10 or NB200_SPLIT_LEVEL=10 turns it
-        # on -- measured at 2 GPUs it costs more than it hides: 0.508 vs 0.459 ms/step, profiles/README.md): the table gradient is scattered in two launches -- levels
-        # [split_level, 16) first -- and the NVLink update of those levels (+ the MLPs; ~half of the bytes) runs beside the second
-        # scatter launch; the update of the coarse levels runs beside the next step's ray march.  Within each part rank r owns
-        # the r-th 1/world of the part's element range (update_ranges).
+        # on): the table gradient is scattered in two launches -- levels [split_level, 16) first -- and the NVLink update of those
+        # levels (+ the MLPs; ~half of the bytes) runs beside the second scatter launch AND the next step's ray march
+        # (_launch_split).  Correct (tests/peer_worker.py) but measured slower at 2 GPUs: 0.470 vs 0.449 ms/step
+        # (profiles/r03k_split_2gpu.txt) -- the second scatter launch and the L2 traffic the update adds to it cost more than the
+        # ~35 us of exposed update they hide.  Within each part rank r owns the r-th 1/world of the part's element range
+        # (update_ranges).
         import os
         self.split_level = int(os.environ.get("NB200_SPLIT_LEVEL", split_level or 0))
         if peer is None or peer.world < 2 or not pipeline_update or not (0 < self.split_level < model.pos_en.num_levels):
@@ -200,6 +202,7 @@ class FusedTrainStep:
             self.kernels_per_step += 2      # a second scatter launch and a second peer-update launch
         self._pending_update = False
         self._side = None
+        self._scattered = None
         self.use_graph = use_graph
         self.perturb = perturb
         self.T_thresh, self.dt_gamma, self.max_steps = float(T_thresh), float(dt_gamma), int(max_steps)
@@ -328,6 +331,8 @@ class FusedTrainStep:
 
     def _alloc_samples(self, m_cap):
         dev = self.dev
+        if self.split_level and self._pending_update:
+            self.flush()                    # the pending coarse scatter reads the buffers that are about to be replaced
         self.graphs = {}
         self.m_cap = m_cap
         if m_cap == 0:
@@ -513,32 +518,38 @@ class FusedTrainStep:
                "train_update_peer_part")
 
     def _launch_split(self, staged, st):
-        """one step of the split, pipelined, ray-sharded form:
-              [update part 2 of the step before (coarse levels) + weight re-pack + commit]  ||  [march]
-              encode .. field^T, scatter of the fine levels, hyper kernel
-              [update part 1 (fine levels + MLPs)]  ||  [scatter of the coarse levels]
-        the update's kernels on the high-priority side stream (narrow grids: they run beside the main stream's kernels)"""
+        """one step of the split, pipelined, ray-sharded form.  The table gradient is scattered in two launches -- levels
+        [split_level, L) with the rest of the backward (REST_A), the coarse levels afterwards (REST_B) -- and the NVLink update
+        of the fine levels + MLPs (part 1, ~all of the bytes) starts as soon as REST_A and the hyper kernel are through.  A
+        replay is cut AFTER the hyper kernel, so that part 1 of step k runs beside BOTH the coarse scatter of step k and the
+        ray march of step k + 1:
+              side:  update part 1 (k)                          -> [after REST_B] update part 2 (k) + re-pack + commit
+              main:  REST_B (k: coarse scatter) -> march (k + 1)                                   -> join
+                     REST_A (k + 1: encode .. field^T, fine scatter) -> hyper kernel (k + 1)
+        REST_B stays on the main stream in front of the march (it reads the sample buffers the march overwrites)."""
         main = torch.cuda.current_stream(self.dev)
         if self._side is None:
             import os
             prio = -1 if os.environ.get("NB200_SIDE_PRIORITY", "1") == "1" else 0
             self._side = torch.cuda.Stream(device=self.dev, priority=prio)
             self._apply_l2_window(self._side)
+        if self._scattered is None:
+            self._scattered = torch.cuda.Event()
         side = self._side
         side.wait_stream(main)
+        self.plan.flags |= 2                # the hyper kernel of the pending step ran at the end of its own launch
         with torch.cuda.stream(side):
-            self._update_part(2, L.stream())
+            self._update_part(1, L.stream())
+        _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(8), st), "train_phase(rest B)")
+        self._scattered.record(main)
         _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(1), st), "train_phase(march)")
+        with torch.cuda.stream(side):
+            side.wait_event(self._scattered)
+            self._update_part(2, L.stream())
+        self.plan.flags &= ~2
         main.wait_stream(side)
         _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(4), st), "train_phase(rest A)")
         _check(self.lib.nb200_train_update_hyper(C.byref(self.plan), C.c_int(1), st), "train_update_hyper")
-        self.plan.flags |= 2
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            self._update_part(1, L.stream())
-        self.plan.flags &= ~2
-        _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(8), st), "train_phase(rest B)")
-        main.wait_stream(side)
 
     def _launch(self, staged=False):
         """every device-side action of one step, on the current stream (this is what the graph captures)"""
@@ -618,8 +629,13 @@ class FusedTrainStep:
         """pipeline_update: apply the update of the last step() now, so that the parameters are current"""
         if self.pipeline_update and self._pending_update:
             with torch.cuda.device(self.dev):
-                if self.split_level and self._pending_update == "part2":
-                    self._update_part(2, L.stream())        # part 1 ran inside the step
+                if self.split_level and self._pending_update == "split":
+                    # the step ended after its hyper kernel: coarse scatter, then both halves of the update
+                    _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(8), L.stream()), "train_phase(rest B)")
+                    self.plan.flags |= 2
+                    self._update_part(1, L.stream())
+                    self._update_part(2, L.stream())
+                    self.plan.flags &= ~2
                 else:
                     self._update(L.stream())
             self._pending_update = False
@@ -770,34 +786,47 @@ class FusedTrainStep:
                 self._slot_free[slot].record()
             self._publish_stats()
 
+    def _try_capture(self, staged):
+        try:
+            self._capture(staged)
+        except Exception as e:      # e.g. a collective that cannot be captured on this NCCL build
+            import warnings
+            warnings.warn("FusedTrainStep: CUDA-graph capture failed (%s); launching the step's kernels "
+                          "directly instead" % (e,))
+            self.use_graph = False
+            self.graphs.clear()
+            torch.cuda.synchronize(self.dev)
+
     def _step_staged(self, staged):
+        need_graph = self.use_graph and self.graphs.get(staged) is None
+        if self.split_level and need_graph and self._pending_update:
+            # the split form's graph starts with the second half of the step before: capture only from a clean state (its
+            # warm-up launches would otherwise scatter the pending coarse levels from their own samples)
+            self.flush()
         if self.pipeline_update and not self._pending_update:
+            if self.split_level and need_graph:
+                self._try_capture(staged)   # warm-ups run on a zero gradient; every piece of state they touch is restored
             # first step of a pipelined run: nothing to update yet -- forward + backward only, launched directly
             self._stage(staged)
             if self.dense is not None:
                 self._launch_dense_sampler(L.stream())
                 _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(2), L.stream()), "train_phase(rest)")
+            elif self.split_level:          # the split form ends a step after REST_A + the hyper kernel (see _launch_split)
+                if self.perturb:
+                    self.noises.uniform_()
+                _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(1), L.stream()), "train_phase(march)")
+                _check(self.lib.nb200_train_phase(C.byref(self.plan), C.c_int(4), L.stream()), "train_phase(rest A)")
+                _check(self.lib.nb200_train_update_hyper(C.byref(self.plan), C.c_int(1), L.stream()), "train_update_hyper")
             else:
                 if self.perturb:
                     self.noises.uniform_()
                 _check(self.lib.nb200_train_forward_backward(C.byref(self.plan), L.stream()), "train_forward_backward")
             self.stats_host.copy_(self.stats, non_blocking=True)
-            self._pending_update = True
-            if self.split_level:            # the split form always enters a step with part 2 of the step before outstanding
-                self._update_part(1, L.stream())
-                self._pending_update = "part2"
+            self._pending_update = "split" if self.split_level else True
             L.LAUNCHES += self.kernels_per_step - 4
             return
         if self.use_graph and self.graphs.get(staged) is None:
-            try:
-                self._capture(staged)
-            except Exception as e:      # e.g. a collective that cannot be captured on this NCCL build
-                import warnings
-                warnings.warn("FusedTrainStep: CUDA-graph capture failed (%s); launching the step's kernels "
-                              "directly instead" % (e,))
-                self.use_graph = False
-                self.graphs.clear()
-                torch.cuda.synchronize(self.dev)
+            self._try_capture(staged)
         if self.use_graph:
             self.graphs[staged].replay()
         else:
