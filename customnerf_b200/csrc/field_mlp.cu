@@ -335,6 +335,7 @@ struct FieldBwdArgs {
     const int32_t *count_dev; // when non-null only rows < min(M, *count_dev) are processed
     uint32_t *scaler;         // loss-scaler words (adam.cuh) or null: a feature gradient that leaves the fp16 range raises found-inf
     uint32_t *status;         // kernel status word or null (field_common.cuh)
+    uint32_t dbg;             // timing experiments only (NB200_FIELDB_DBG): 1 = skip the weight-gradient MMAs
 };
 
 // MN-major descriptor of K-step ks (16 rows = 2 swizzle atoms) starting at column `col0` (multiple of 8 halves)
@@ -480,6 +481,7 @@ k_field_backward(const FieldBwdArgs p) {
     };
     // D[cols] (+)= A_tile^T (M = 128: this tile and the next) x B_tile[:, col0 : col0 + N], contraction over the 128 points
     auto wgrad = [&](uint32_t dcol, uint32_t a, uint32_t b, uint32_t bcol0, uint32_t idesc) {
+        if (p.dbg & 1u) return;
         for (uint32_t k = 0; k < 8; k++)
             umma::mma_f16_ss(tmem + dcol, mndesc(a, k, 0), mndesc(b, k, bcol0), idesc, !(first_tile && k == 0));
     };
@@ -927,6 +929,7 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
     a.count_dev = count_dev;
     a.scaler = scaler;
     a.status = nb_kernel_status_word();
+    { static int dbg = -1; if (dbg < 0) { const char *e = getenv("NB200_FIELDB_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = (uint32_t)dbg; }
     a.slabs = wg_scratch;
     const uint32_t ntiles = (M + 127) / 128;
     const uint32_t grid = ntiles < (uint32_t)sms ? ntiles : (uint32_t)sms;
