@@ -36,9 +36,10 @@ from . import _lib as L
 
 LOSS_SCALE = 128.0          # initial loss scale (tiny-cuda-nn's own backward loss scale); dynamic from there on, see below
 GROWTH_INTERVAL = 2000      # torch.cuda.amp.GradScaler's default: the scale doubles after this many steps without overflow
-# this library's kernels in one step: march count (+ near/far) + scan + expand, encode, field, composite (+ MSE),
-# composite^T, field^T + weight-gradient reduce, encode^T, adam hyper, adam, weight pack
-KERNELS_PER_STEP = 12
+# this library's kernels in one step (the ncu launch list profiles/r03_ncu_summary.txt shows the same fourteen): march count
+# (+ near/far) + scan + finalize + expand, encode, field, composite (+ MSE), composite^T, field^T + weight-gradient reduce,
+# encode^T, adam hyper, adam, weight pack (+ scaler commit)
+KERNELS_PER_STEP = 14
 STAGES = ["march_count", "march_write", "grid_encode_forward", "field_forward", "composite_forward",
           "composite_backward", "field_backward", "grid_encode_backward", "adam", "pack_weights"]
 
@@ -178,13 +179,13 @@ class FusedTrainStep:
             raise NotImplementedError("FusedTrainStep: rgb_weight (opt.train_rgb) must be positive")
         # fused_forward: grid gather + field network forward as ONE kernel (csrc/field_fused.cu: the features are gathered by
         # producer warps straight into the tensor-core operand tile); False (default): two launches (encode, then field).
-        # Measured on B200 at configs[1] (profiles/r02_fused_forward.md): the fused kernel is bit-identical but SLOWER in the
+        # Measured on B200 at configs[1] (profiles/r02c_fused_forward_ncu.txt, r02e_bench_*.json): the fused kernel is bit-identical but SLOWER in the
         # training step (166 us against 55 + 47 us): the MLP's 2 x 112 KB of shared memory leave the gathers ~4 KB of L1 and
         # 8 warps per SM, where the standalone encoder has ~220 KB and ~31
         self.fused_forward = bool(fused_forward) and model.pos_en.num_levels == 16
         self.kernels_per_step = KERNELS_PER_STEP - (1 if self.fused_forward else 0)
         if self.dense is not None:
-            self.kernels_per_step += 1          # near/far, coarse, density, importance instead of the march's three launches
+            pass                                # near/far, coarse, density, importance instead of the march's four launches
         self.pipeline_update = bool(pipeline_update)
         self.update_shape = tuple(int(v) for v in update_shape) if update_shape else None   # (CTAs, threads, unroll) of the pipelined sweep
         # split update (ray-sharded, peer-memory update, pipelined; OFF by default, split_level=10 or NB200_SPLIT_LEVEL=10 turns it
