@@ -113,15 +113,25 @@ rest:
     if ((e = cudaMemsetAsync(p->loss, 0, sizeof(float), st)) != cudaSuccess) return (int)e;
     tick(ev, k++, st);
     if ((rc = fs_encode_field_forward(p, stream, ev, &k))) return rc;
-    if ((rc = nb200_fs_composite_forward(p->sigma, p->rgba, p->deltas, p->rays, p->M_cap, p->N, p->T_thresh,
-                                         p->weights_sum, p->depth, p->image, p->target, p->inv_n_total, p->loss_scale,
-                                         p->loss, p->g_image, p->target_mask, p->mask_weight, p->render_mask,
-                                         p->g_render_mask, (const float *)p->scaler, stream))) return rc;
-    tick(ev, k++, st);
-    if ((rc = nb200_fs_composite_backward(p->g_weights_sum, p->g_image, p->sigma, p->rgba, p->deltas, p->rays,
-                                          p->weights_sum, p->image, p->M_cap, p->N, p->T_thresh, p->d_sigma, p->d_rgba,
-                                          p->target_mask ? p->g_render_mask : nullptr, p->render_mask, stream))) return rc;
-    tick(ev, k++, st);
+    if (!(p->flags & NB200_PLAN_SPLIT_COMPOSITE) && p->target) {
+        // compositing forward + MSE + compositing backward in one launch (the stage timer then books it all under the forward)
+        if ((rc = nb200_fs_composite_fused(p->sigma, p->rgba, p->deltas, p->rays, p->M_cap, p->N, p->T_thresh, p->weights_sum,
+                                           p->depth, p->image, p->target, p->inv_n_total, p->loss_scale, p->loss, p->g_image,
+                                           p->target_mask, p->mask_weight, p->render_mask, p->g_render_mask,
+                                           (const float *)p->scaler, p->g_weights_sum, p->d_sigma, p->d_rgba, stream))) return rc;
+        tick(ev, k++, st);
+        tick(ev, k++, st);
+    } else {
+        if ((rc = nb200_fs_composite_forward(p->sigma, p->rgba, p->deltas, p->rays, p->M_cap, p->N, p->T_thresh,
+                                             p->weights_sum, p->depth, p->image, p->target, p->inv_n_total, p->loss_scale,
+                                             p->loss, p->g_image, p->target_mask, p->mask_weight, p->render_mask,
+                                             p->g_render_mask, (const float *)p->scaler, stream))) return rc;
+        tick(ev, k++, st);
+        if ((rc = nb200_fs_composite_backward(p->g_weights_sum, p->g_image, p->sigma, p->rgba, p->deltas, p->rays,
+                                              p->weights_sum, p->image, p->M_cap, p->N, p->T_thresh, p->d_sigma, p->d_rgba,
+                                              p->target_mask ? p->g_render_mask : nullptr, p->render_mask, stream))) return rc;
+        tick(ev, k++, st);
+    }
     if ((rc = nb200_field_backward(p->d_sigma, p->d_rgba, p->sigma_arg, p->rgba, p->x_en, p->dirs, p->act, p->w_bwd,
                                    p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, p->scaler, stream))) return rc;
     tick(ev, k++, st);

@@ -797,29 +797,12 @@ __device__ __forceinline__ float lgie_gate(float m, const LgieArgs &a, float &dg
     return e;
 }
 
-template <typename TC, int V = -1>
-__global__ void __launch_bounds__(kCompBlock)
-k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ rgbs, const float *__restrict__ deltas,
-                      const int32_t *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
-                      float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image, MseArgs mse,
-                      LgieArgs lg = LgieArgs{}) {
-    __shared__ float loss_part[kCompBlock / 32];
-    const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
-    const uint32_t lane = nb_lane();
-    if (mse.target) {                       // whole block stays alive for the block-level loss reduction
-        if (lane == 0) loss_part[threadIdx.x >> 5] = 0.0f;
-        if (n >= N) {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                float v = 0.0f;
-                for (int i = 0; i < kCompBlock / 32; i++) v += loss_part[i];
-                if (v != 0.0f) atomicAdd(mse.loss, v * mse.inv_n);
-            }
-            return;
-        }
-    } else if (n >= N) return;
-    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
-    float r = 0, g = 0, b = 0, ws = 0, d = 0, mk = 0;
+// forward compositing of one ray by one warp: 32 samples per trip, prefixes by shuffle scans; every lane returns the sums
+template <typename TC, int V>
+__device__ __forceinline__ void comp_fwd_ray(const float *__restrict__ sigmas, const TC *__restrict__ rgbs,
+                                             const float *__restrict__ deltas, uint32_t offset, uint32_t num_steps, uint32_t M,
+                                             float T_thresh, uint32_t lane, const LgieArgs &lg, bool need_mask, float &r, float &g,
+                                             float &b, float &ws, float &d, float &mk) {
     if (num_steps != 0 && offset + num_steps <= M) {
         float T_carry = 1.0f, t_carry = 0.0f;
         for (uint32_t base = 0; base < num_steps; base += 32) {
@@ -852,8 +835,34 @@ k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ r
             t_carry = __shfl_sync(0xffffffffu, t_i, 31);
         }
         r = nb_warp_sum(r); g = nb_warp_sum(g); b = nb_warp_sum(b); ws = nb_warp_sum(ws); d = nb_warp_sum(d);
-        if (mse.render_mask) mk = nb_warp_sum(mk);
+        if (need_mask) mk = nb_warp_sum(mk);
     }
+}
+
+template <typename TC, int V = -1>
+__global__ void __launch_bounds__(kCompBlock)
+k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ rgbs, const float *__restrict__ deltas,
+                      const int32_t *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
+                      float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image, MseArgs mse,
+                      LgieArgs lg = LgieArgs{}) {
+    __shared__ float loss_part[kCompBlock / 32];
+    const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
+    const uint32_t lane = nb_lane();
+    if (mse.target) {                       // whole block stays alive for the block-level loss reduction
+        if (lane == 0) loss_part[threadIdx.x >> 5] = 0.0f;
+        if (n >= N) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float v = 0.0f;
+                for (int i = 0; i < kCompBlock / 32; i++) v += loss_part[i];
+                if (v != 0.0f) atomicAdd(mse.loss, v * mse.inv_n);
+            }
+            return;
+        }
+    } else if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+    float r = 0, g = 0, b = 0, ws = 0, d = 0, mk = 0;
+    comp_fwd_ray<TC, V>(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane, lg, mse.render_mask != nullptr, r, g, b, ws, d, mk);
     if (lane == 0) {
         weights_sum[index] = ws;
         depth[index] = d;
@@ -883,33 +892,15 @@ k_composite_train_fwd(const float *__restrict__ sigmas, const TC *__restrict__ r
     }
 }
 
-// GS = row stride of grad_rgbs: 3 (reference layout) or 4 (float4 rows [g_r, g_g, g_b, 0] for the field backward)
-// V >= 0 (LGIE, GS == 4): contributions of variant V to the per-sample gradients -- d sigma = gs * gate * a,
-// d m = g_mask * w + gs * sigma * d gate / d m, d rgb = a * g_rgb, with a = [m >= 0.5] for the "all" variant under
-// detach_bg (background samples give values but no gradient to the global image, :409-418) and 1 otherwise;
-// detach_mask: the rendered mask's weights are detached (:460-463), so its term leaves gs.  accumulate: add to the rows.
-template <typename TC, int GS, int V = -1>
-__global__ void __launch_bounds__(kCompBlock)
-k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *__restrict__ grad_image,
-                      const float *__restrict__ sigmas, const TC *__restrict__ rgbs, const float *__restrict__ deltas,
-                      const int32_t *__restrict__ rays, const float *__restrict__ weights_sum,
-                      const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
-                      float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs,
-                      const float *__restrict__ grad_render_mask, const float *__restrict__ render_mask,
-                      LgieArgs lg = LgieArgs{}) {
-    const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
-    if (n >= N) return;
-    const uint32_t lane = nb_lane();
-    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
-    if (num_steps == 0 || offset + num_steps > M) return;
-    // optional 4th composited channel (the rendered mask): same recurrences as a colour channel
-    const bool has_m = grad_render_mask != nullptr;
-    const float gm = has_m ? grad_render_mask[index] : 0.0f, m_final = has_m ? render_mask[index] : 0.0f;
+// backward compositing of one ray by one warp (the loop of k_composite_train_bwd; also the second half of the fused kernel)
+template <typename TC, int GS, int V>
+__device__ __forceinline__ void comp_bwd_ray(const float *__restrict__ sigmas, const TC *__restrict__ rgbs,
+                                             const float *__restrict__ deltas, uint32_t offset, uint32_t num_steps, float T_thresh,
+                                             uint32_t lane, const LgieArgs &lg, bool has_m, float gm, float m_final, float gws,
+                                             float gi0, float gi1, float gi2, float r_final, float g_final, float b_final,
+                                             float ws_final, float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs) {
     float m_c = 0;
-    const float gws = grad_weights_sum[index];
-    const float gi0 = grad_image[index * 3], gi1 = grad_image[index * 3 + 1], gi2 = grad_image[index * 3 + 2];
-    const float r_final = image[index * 3], g_final = image[index * 3 + 1], b_final = image[index * 3 + 2];
-    const float ws_term = gws * (1.0f - weights_sum[index]);
+    const float ws_term = gws * (1.0f - ws_final);
     float T_carry = 1.0f, r_c = 0, g_c = 0, b_c = 0;
     bool done = false;
     for (uint32_t base = 0; base < num_steps; base += 32) {
@@ -974,6 +965,90 @@ k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *_
                 grad_rgbs[s * 3] = gr0; grad_rgbs[s * 3 + 1] = gr1; grad_rgbs[s * 3 + 2] = gr2;
             }
         }
+    }
+}
+
+// GS = row stride of grad_rgbs: 3 (reference layout) or 4 (float4 rows [g_r, g_g, g_b, 0] for the field backward)
+// V >= 0 (LGIE, GS == 4): contributions of variant V to the per-sample gradients -- d sigma = gs * gate * a,
+// d m = g_mask * w + gs * sigma * d gate / d m, d rgb = a * g_rgb, with a = [m >= 0.5] for the "all" variant under
+// detach_bg (background samples give values but no gradient to the global image, :409-418) and 1 otherwise;
+// detach_mask: the rendered mask's weights are detached (:460-463), so its term leaves gs.  accumulate: add to the rows.
+template <typename TC, int GS, int V = -1>
+__global__ void __launch_bounds__(kCompBlock)
+k_composite_train_bwd(const float *__restrict__ grad_weights_sum, const float *__restrict__ grad_image,
+                      const float *__restrict__ sigmas, const TC *__restrict__ rgbs, const float *__restrict__ deltas,
+                      const int32_t *__restrict__ rays, const float *__restrict__ weights_sum,
+                      const float *__restrict__ image, uint32_t M, uint32_t N, float T_thresh,
+                      float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs,
+                      const float *__restrict__ grad_render_mask, const float *__restrict__ render_mask,
+                      LgieArgs lg = LgieArgs{}) {
+    const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
+    if (n >= N) return;
+    const uint32_t lane = nb_lane();
+    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) return;
+    // optional 4th composited channel (the rendered mask): same recurrences as a colour channel
+    const bool has_m = grad_render_mask != nullptr;
+    const float gm = has_m ? grad_render_mask[index] : 0.0f, m_final = has_m ? render_mask[index] : 0.0f;
+    const float gws = grad_weights_sum[index];
+    comp_bwd_ray<TC, GS, V>(sigmas, rgbs, deltas, offset, num_steps, T_thresh, lane, lg, has_m, gm, m_final, gws,
+                            grad_image[index * 3], grad_image[index * 3 + 1], grad_image[index * 3 + 2], image[index * 3],
+                            image[index * 3 + 1], image[index * 3 + 2], weights_sum[index], grad_sigmas, grad_rgbs);
+}
+
+// Fused train step: compositing forward + MSE (+ mask term) + compositing backward of a ray in ONE launch.  Everything the
+// backward needs from the forward is per ray (the final sums and the loss gradient of that ray's pixel), so the warp that
+// composited a ray turns round and walks its samples again -- they are still in L1 / L2 -- instead of a second kernel
+// re-reading the per-ray results (two launch-latency-sized kernels of 12 + 10 us at 270 k samples).  Same loops, same
+// arithmetic and the same outputs as k_composite_train_fwd<TC> followed by k_composite_train_bwd<TC, 4>.
+template <typename TC>
+__global__ void __launch_bounds__(kCompBlock)
+k_composite_train_fused(const float *__restrict__ sigmas, const TC *__restrict__ rgbs, const float *__restrict__ deltas,
+                        const int32_t *__restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
+                        float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image, MseArgs mse,
+                        const float *__restrict__ grad_weights_sum, float *__restrict__ grad_sigmas,
+                        float *__restrict__ grad_rgbs) {
+    __shared__ float loss_part[kCompBlock / 32];
+    const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5;
+    const uint32_t lane = nb_lane();
+    if (lane == 0) loss_part[threadIdx.x >> 5] = 0.0f;
+    if (n < N) {
+        const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+        const LgieArgs lg{};
+        const bool has_m = mse.target_mask != nullptr;
+        float r = 0, g = 0, b = 0, ws = 0, d = 0, mk = 0;
+        comp_fwd_ray<TC, -1>(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane, lg, mse.render_mask != nullptr, r, g, b, ws,
+                             d, mk);
+        // the pixel's loss gradient, in every lane (the loads are warp-uniform)
+        const float e0 = r - mse.target[index * 3], e1 = g - mse.target[index * 3 + 1], e2 = b - mse.target[index * 3 + 2];
+        const float lscale = mse.scale_dev ? __ldg(mse.scale_dev) : mse.scale;
+        const float k = 2.0f * mse.inv_n * lscale;
+        const float gi0 = e0 * k, gi1 = e1 * k, gi2 = e2 * k;
+        float gm = 0.0f, part = e0 * e0 + e1 * e1 + e2 * e2;
+        if (has_m) {                        // mean over N x 1 entries = 3 x the per-element weight of the N x 3 image
+            const float dm = mk - mse.target_mask[index];
+            gm = 2.0f * dm * (3.0f * mse.inv_n) * mse.mask_weight * lscale;
+            part += 3.0f * mse.mask_weight * dm * dm;
+        }
+        if (lane == 0) {
+            weights_sum[index] = ws;
+            depth[index] = d;
+            image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+            if (mse.render_mask) mse.render_mask[index] = mk;
+            mse.g_image[index * 3] = gi0; mse.g_image[index * 3 + 1] = gi1; mse.g_image[index * 3 + 2] = gi2;
+            if (has_m) mse.g_render_mask[index] = gm;
+            loss_part[threadIdx.x >> 5] = part;
+        }
+        if (num_steps != 0 && offset + num_steps <= M)
+            comp_bwd_ray<TC, 4, -1>(sigmas, rgbs, deltas, offset, num_steps, T_thresh, lane, lg, has_m, gm, mk,
+                                    grad_weights_sum ? grad_weights_sum[index] : 0.0f, gi0, gi1, gi2, r, g, b, ws, grad_sigmas,
+                                    grad_rgbs);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = 0.0f;
+        for (int i = 0; i < kCompBlock / 32; i++) v += loss_part[i];
+        if (v != 0.0f) atomicAdd(mse.loss, v * mse.inv_n);
     }
 }
 
@@ -1445,6 +1520,23 @@ int nb200_fs_composite_backward(const float *grad_weights_sum, const float *grad
     k_composite_train_bwd<__half, 4><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
         grad_weights_sum, grad_image, sigmas, (const __half *)rgba, deltas, rays, weights_sum, image, M, N, T_thresh,
         grad_sigmas, grad_rgba, grad_render_mask, render_mask);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+// compositing forward + MSE + compositing backward of the fused train step in one launch (same outputs as the two calls)
+int nb200_fs_composite_fused(const float *sigmas, const void *rgba, const float *deltas, const int32_t *rays, uint32_t M,
+                             uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image, const float *target,
+                             float inv_n, float loss_scale, float *loss, float *g_image, const float *target_mask,
+                             float mask_weight, float *render_mask, float *g_render_mask, const float *loss_scale_dev,
+                             const float *grad_weights_sum, float *grad_sigmas, float *grad_rgba, void *stream) {
+    if (N == 0) return 0;
+    if (!target || !loss || !g_image || !grad_sigmas || !grad_rgba) return NB200_E_BAD_ARG;
+    if (target_mask && (!render_mask || !g_render_mask)) return NB200_E_BAD_ARG;
+    k_composite_train_fused<__half><<<nb_div_up((uint64_t)N * 32, kCompBlock), kCompBlock, 0, nb_stream(stream)>>>(
+        sigmas, (const __half *)rgba, deltas, rays, M, N, T_thresh, weights_sum, depth, image,
+        MseArgs{target, loss, g_image, inv_n, loss_scale, target_mask, render_mask, g_render_mask, mask_weight, loss_scale_dev},
+        grad_weights_sum, grad_sigmas, grad_rgba);
     NB_LAUNCH_CHECK();
     return 0;
 }

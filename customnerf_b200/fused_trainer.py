@@ -183,7 +183,11 @@ class FusedTrainStep:
         # training step (166 us against 55 + 47 us): the MLP's 2 x 112 KB of shared memory leave the gathers ~4 KB of L1 and
         # 8 warps per SM, where the standalone encoder has ~220 KB and ~31
         self.fused_forward = bool(fused_forward) and model.pos_en.num_levels == 16
-        self.kernels_per_step = KERNELS_PER_STEP - (1 if self.fused_forward else 0)
+        # compositing forward + MSE + compositing backward as one launch (csrc/raymarching.cu: k_composite_train_fused); the
+        # two-launch form stays selectable (NB200_SPLIT_COMPOSITE=1) for comparison
+        import os as _os
+        self.fused_composite = _os.environ.get("NB200_SPLIT_COMPOSITE", "0") != "1"
+        self.kernels_per_step = KERNELS_PER_STEP - (1 if self.fused_forward else 0) - (1 if self.fused_composite else 0)
         if self.dense is not None:
             pass                                # near/far, coarse, density, importance instead of the march's four launches
         self.pipeline_update = bool(pipeline_update)
@@ -360,7 +364,7 @@ class FusedTrainStep:
         p.S = float(np.log2(enc.per_level_scale))
         p.T_thresh, p.min_near = self.T_thresh, 0.2          # run_cuda leaves min_near at its default (Appendix B5)
         p.loss_scale, p.inv_n_total = LOSS_SCALE, self.rgb_weight / (3.0 * self.n_total)
-        p.flags = 1 if self.fused_forward else 0
+        p.flags = (1 if self.fused_forward else 0) | (0 if self.fused_composite else 4)
         p.n_params, p.n_table_params = self.params_flat.numel(), self.layout[0][2]
 
         def a(t):

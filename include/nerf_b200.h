@@ -345,6 +345,14 @@ int nb200_fs_composite_backward(const float *grad_weights_sum, const float *grad
                                 const void *rgba, const float *deltas, const int32_t *rays, const float *weights_sum,
                                 const float *image, uint32_t M, uint32_t N, float T_thresh, float *grad_sigmas,
                                 float *grad_rgba, const float *grad_render_mask, const float *render_mask, void *stream);
+/* both in ONE launch (target required): the warp that composited a ray walks its samples again for the backward -- same
+ * outputs (weights_sum, depth, image, render_mask, loss, g_image, g_render_mask, grad_sigmas, grad_rgba) as the two calls.
+ * grad_weights_sum may be NULL (0). */
+int nb200_fs_composite_fused(const float *sigmas, const void *rgba, const float *deltas, const int32_t *rays, uint32_t M,
+                             uint32_t N, float T_thresh, float *weights_sum, float *depth, float *image, const float *target,
+                             float inv_n, float loss_scale, float *loss, float *g_image, const float *target_mask,
+                             float mask_weight, float *render_mask, float *g_render_mask, const float *loss_scale_dev,
+                             const float *grad_weights_sum, float *grad_sigmas, float *grad_rgba, void *stream);
 /* grad_render_mask / render_mask (both or neither): the rendered mask as a 4th composited channel; its gradient lands in
  * grad_rgba[:, 3] and in grad_sigmas. */
 /* loss[0] += sum((image - target)^2) * inv_n ;  g_image = 2 (image - target) * inv_n * loss_scale.
@@ -394,6 +402,7 @@ int nb200_scaler_commit(int32_t *step, uint32_t *scaler, uint32_t *const *peer_s
 
 #define NB200_PLAN_FUSED_FORWARD 1u   /* encode + field forward as one kernel (nb200_field_fused_forward): the stage timer
                                          then reports the pair under "field_forward" and ~0 under "grid_encode_forward" */
+#define NB200_PLAN_SPLIT_COMPOSITE 4u /* compositing forward and backward as two launches (default: nb200_fs_composite_fused) */
 #define NB200_PLAN_HYPER_DONE 2u      /* nb200_train_update[_peer] skips its first kernel (nb200_adam_hyper[_scaled]): the caller
                                          has launched it already -- a pipelined trainer does so BEFORE forking the update onto its
                                          side stream, so that the sweep and the next step's march become runnable together */
