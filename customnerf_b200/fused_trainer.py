@@ -115,7 +115,7 @@ class FusedTrainStep:
     def __init__(self, model, n_rays, lr=5e-4, m_cap=None, world_size=1, grad_sync=None, use_graph=True, perturb=True,
                  betas=(0.9, 0.99), eps=1e-15, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, lr_decay_base=1.0,
                  lr_decay_iters=0, allreduce_chunks=0, process_group=None, pipeline_update=False, mask_weight=0.0,
-                 peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True, update_shape=(64, 512, 4), split_level=0,
+                 peer=None, raygen=None, fused_forward=False, dynamic_loss_scale=True, update_shape=(64, 512, 4), split_level=None,
                  rgb_weight=1.0, dense=None):
         # dense = (num_steps, upsample_steps): the DENSE renderer (nerf/renderer.py:278-405, the path the published -O2 commands
         # run) instead of the occupancy march -- per step: near/far, coarse samples (csrc/dense_sampler.cu), their densities
@@ -199,8 +199,16 @@ class FusedTrainStep:
         # (profiles/r03k_split_2gpu.txt) -- the second scatter launch and the L2 traffic the update adds to it cost more than the
         # ~35 us of exposed update they hide.  Within each part rank r owns the r-th 1/world of the part's element range
         # (update_ranges).
+        # split_level=None: on (level 8) for tables of 2^25 parameters and more, where the kernels are milliseconds long and the
+        # split gains (configs[4], 2^22 rows per level: 12.20 vs 12.62 ms/step at 2 GPUs, 3.48 vs 3.54 at 8 --
+        # profiles/r03o_c4_split_2gpu.txt, r03p_c4_strong_8gpu_split*.json); off below that.
         import os
-        self.split_level = int(os.environ.get("NB200_SPLIT_LEVEL", split_level or 0))
+        if "NB200_SPLIT_LEVEL" in os.environ:
+            self.split_level = int(os.environ["NB200_SPLIT_LEVEL"])
+        elif split_level is None:
+            self.split_level = 8 if model.pos_en.embeddings.numel() >= (1 << 25) else 0
+        else:
+            self.split_level = int(split_level)
         if peer is None or peer.world < 2 or not pipeline_update or not (0 < self.split_level < model.pos_en.num_levels):
             self.split_level = 0
         if self.split_level:
