@@ -320,6 +320,10 @@ constexpr uint32_t S_BWD_BYTES = SB_XV2 + 16384;    // 45056 + 11 * 16384 = 2252
 // TMEM columns
 constexpr uint32_t C_DG = 0, C_W1 = 64, C_W2 = 96, C_W3 = 160, C_PAIR = 224, C_R1V = 288, C_D2 = 320, C_R2 = 384, C_DG2 = 448;
 constexpr uint32_t kTmemColsBwd = 512;
+// per-CTA weight-gradient slab: one column-major block per accumulator (floats); 22528 in total == kWgradFloats
+constexpr uint32_t kSlabW1 = 0, kSlabW2 = kSlabW1 + 32 * 64, kSlabW3 = kSlabW2 + 64 * 64, kSlabPair = kSlabW3 + 64 * 64,
+                   kSlabR1V = kSlabPair + 64 * 128, kSlabR2 = kSlabR1V + 32 * 64, kSlabD2 = kSlabR2 + 64 * 16;
+static_assert(kSlabD2 + 64 * 16 == kWgradFloats, "slab blocks must tile kWgradFloats");
 
 struct FieldBwdArgs {
     const float *d_sigma;     // [M]
@@ -337,7 +341,7 @@ struct FieldBwdArgs {
     const int32_t *count_dev; // when non-null only rows < min(M, *count_dev) are processed
     uint32_t *scaler;         // loss-scaler words (adam.cuh) or null: a feature gradient that leaves the fp16 range raises found-inf
     uint32_t *status;         // kernel status word or null (field_common.cuh)
-    uint32_t dbg;             // timing experiments only (NB200_FIELDB_DBG): 1 = skip the weight-gradient MMAs
+    uint32_t dbg;             // timing experiments only (NB200_FIELDB_DBG): 1 = skip the weight-gradient MMAs, 2 = skip their flush, 4 = skip the slab reduce launch
 };
 
 // MN-major descriptor of K-step ks (16 rows = 2 swizzle atoms) starting at column `col0` (multiple of 8 halves)
@@ -683,15 +687,45 @@ k_field_backward(const FieldBwdArgs p) {
 
     // ---- flush the weight-gradient accumulators: TMEM lane == output neuron n (row of dW); the two column halves of
     //      every accumulator go to the two warps that own the lane quarter
-    if (!first_tile) {
+    if (!first_tile && !(p.dbg & 2u) && p.slabs) {
+        // Slab layout (kSlab*): one block per accumulator, COLUMN-major within the block -- element (row n, column c) at
+        // off + c * rows + n -- so that a warp's store of one accumulator column covers 32 consecutive floats (TMEM lane ==
+        // row == thread: the natural row-major slab made every store instruction touch 32 half-filled sectors, and the
+        // misaligned / remapped columns of the colour layer went out as scalar stores: 9.4 us of the kernel at configs[1]).
+        // The mapping to the tcnn parameter layout happens once, in k_field_wgrad_reduce.
+        float *sl = p.slabs + (size_t)blockIdx.x * kWgradFloats;
+        const uint32_t wq = warp & 3u;              // lane quarter: rows 32 wq .. 32 wq + 31
+        auto flush32 = [&](uint32_t col, uint32_t off, uint32_t rows, uint32_t row_base) {      // 64-column accumulator
+            if (wq * 32u >= row_base + rows || wq * 32u + 32u <= row_base) return;              // (warp-uniform)
+            uint32_t r[32];
+            umma::tmem_ld32(trow + col + 32 * half, r);
+            umma::tmem_ld_wait();
+            if (row >= row_base && row < row_base + rows) {
+                float *dst = sl + off + (size_t)(32 * half) * rows + (row - row_base);
+#pragma unroll
+                for (int j = 0; j < 32; j++) dst[(size_t)j * rows] = __uint_as_float(r[j]);
+            }
+        };
+        auto flush16 = [&](uint32_t col, uint32_t off, uint32_t rows) {                         // 32-column accumulator
+            if (wq * 32u >= rows) return;
+            uint32_t r[16];
+            umma::tmem_ld16(trow + col + 16 * half, r);
+            umma::tmem_ld_wait();
+            float *dst = sl + off + (size_t)(16 * half) * rows + row;
+#pragma unroll
+            for (int j = 0; j < 16; j++) dst[(size_t)j * rows] = __uint_as_float(r[j]);
+        };
+        flush16(C_W1, kSlabW1, 64);
+        flush32(C_W2, kSlabW2, 64, 0);
+        flush32(C_W3, kSlabW3, 64, 0);
+        flush32(C_PAIR, kSlabPair, 128, 0);
+        flush16(C_R1V, kSlabR1V, 64);
+        flush32(C_R2, kSlabR2, 16, 0);              // A = T16: rows 0..15 = colour outputs (4 real)
+        flush32(C_D2, kSlabD2, 16, 16);             //          rows 16..31 = density outputs (1 real)
+    } else if (!first_tile && !(p.dbg & 2u)) {
         const uint32_t n = row;
-        const bool slab = p.slabs != nullptr;
+        const bool slab = false;
         float *gt = p.g_trunk, *gd = p.g_density, *gr = p.g_rgb;
-        if (slab) {
-            gt = p.slabs + (size_t)blockIdx.x * kWgradFloats;
-            gd = gt + kTrunkFloats;
-            gr = gd + kDensityFloats;
-        }
         auto flush = [&](uint32_t col, uint32_t ncols, float *dst, bool on) {
             const uint32_t hc = ncols / 2;
             for (uint32_t c0 = half * hc; c0 < (half + 1) * hc; c0 += 16) bwd_flush16(trow + col + c0, dst + c0, on, slab);
@@ -744,8 +778,9 @@ k_field_backward(const FieldBwdArgs p) {
     if (warp == 0) umma::tmem_dealloc(tmem, kTmemColsBwd);
 }
 
-// slabs [nslab][kWgradFloats] -> += into the three flat gradients.  Padded output rows of the two heads (tcnn pads 1 -> 16
-// and 4 -> 16 outputs) are never written by the flush and never read here.  256 threads = 64 parameters x 4 slab groups.
+// slabs [nslab][kWgradFloats] (the column-major accumulator blocks of the flush) -> += into the three flat gradients in tcnn's
+// layout.  Padded output rows of the two heads (tcnn pads 1 -> 16 and 4 -> 16 outputs) are dropped here.  256 threads = 64
+// slab elements x 4 slab groups; a warp reads 128 contiguous bytes of every slab it visits.
 __global__ void __launch_bounds__(256)
 k_field_wgrad_reduce(const float *__restrict__ slabs, uint32_t grid, uint32_t M, const int32_t *__restrict__ count_dev,
                      float *__restrict__ g_trunk, float *__restrict__ g_density, float *__restrict__ g_rgb,
@@ -755,26 +790,35 @@ k_field_wgrad_reduce(const float *__restrict__ slabs, uint32_t grid, uint32_t M,
     const uint32_t nslab = min(grid, (Mrows + 127) / 128);
     const uint32_t pl = threadIdx.x & 63u, cg = threadIdx.x >> 6, i = blockIdx.x * 64 + pl;
     float acc = 0.0f;
-    if (i < kWgradFloats)
+    if (i < kWgradFloats) {
+#pragma unroll 8
         for (uint32_t c = cg; c < nslab; c += 4) acc += __ldg(slabs + (size_t)c * kWgradFloats + i);
+    }
     part[cg][pl] = acc;
     __syncthreads();
     if (cg != 0 || i >= kWgradFloats || nslab == 0) return;
     const float sum = (part[0][pl] + part[1][pl]) + (part[2][pl] + part[3][pl]);
+    // slab element -> parameter: block, column c, row n (output neuron)
+    float *dst = nullptr;
+    if (i < kSlabW2) { const uint32_t c = i / 64, n = i % 64; dst = g_trunk + T_W1 + n * 32 + c; }
+    else if (i < kSlabW3) { const uint32_t e = i - kSlabW2, c = e / 64, n = e % 64; dst = g_trunk + T_W2 + n * 64 + c; }
+    else if (i < kSlabPair) { const uint32_t e = i - kSlabW3, c = e / 64, n = e % 64; dst = g_trunk + T_W3 + n * 64 + c; }
+    else if (i < kSlabR1V) {        // rows 0..63 = colour layer 0 (fea columns 27..90), rows 64..127 = density layer 0
+        const uint32_t e = i - kSlabPair, c = e / 128, n = e % 128;
+        dst = n < 64 ? g_rgb + R_W1 + n * 96 + 27 + c : g_density + D_W1 + (n - 64) * 64 + c;
+    } else if (i < kSlabR2) {       // colour layer 0, view columns: internal column c -> input lane c (c < 27) or 91 + (c - 27)
+        const uint32_t e = i - kSlabR1V, c = e / 64, n = e % 64;
+        dst = g_rgb + R_W1 + n * 96 + (c < 27 ? c : 91 + (c - 27));
+    } else if (i < kSlabD2) {       // colour head: rows 0..3 real
+        const uint32_t e = i - kSlabR2, c = e / 16, n = e % 16;
+        if (n < 4) dst = g_rgb + R_W2 + n * 64 + c;
+    } else {                        // density head: row 0 real
+        const uint32_t e = i - kSlabD2, c = e / 16, n = e % 16;
+        if (n == 0) dst = g_density + D_W2 + c;
+    }
     // every gradient tile of the step (head gradients, dHR .. dH1) is an operand of some weight-gradient GEMM: an fp16
     // overflow anywhere in the backward chain shows up here as inf / NaN (inf x 0 included) -- GradScaler's found_inf.
-    // Only entries the flush wrote are looked at (the padded head rows of a slab are never written).
-    float *dst = nullptr;
-    if (i < kTrunkFloats) dst = g_trunk + i;
-    else {
-        uint32_t j = i - kTrunkFloats;
-        if (j < kDensityFloats) {
-            if (j < D_W2 + 64) dst = g_density + j;                        // layer 0, and row 0 of the padded head
-        } else {
-            j -= kDensityFloats;
-            if (j < R_W2 + 4 * 64) dst = g_rgb + j;                        // layer 0, and rows 0..3 of the padded head
-        }
-    }
+    // Only entries that map to a parameter are looked at.
     if (!dst) return;
     if (scaler && !isfinite(sum)) scaler_raise(scaler);
     *dst += sum;
@@ -938,7 +982,7 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
     if (wg_scratch && (reinterpret_cast<uintptr_t>(wg_scratch) & 15u)) return NB200_E_BAD_ARG;
     k_field_backward<<<grid, kBwdThreads, smem, nb_stream(stream)>>>(a);
     NB_LAUNCH_CHECK();
-    if (wg_scratch) {
+    if (wg_scratch && !(a.dbg & 4u)) {
         k_field_wgrad_reduce<<<nb_div_up(kWgradFloats, 64), 256, 0, nb_stream(stream)>>>(wg_scratch, grid, M, count_dev, g_trunk,
                                                                                   g_density, g_rgb, scaler);
         NB_LAUNCH_CHECK();
