@@ -13,5 +13,4 @@ print("ms/step=%.4f rays/s=%.4e e2e=%.4e launches=%s" % (d["ms_per_step"], d["va
 print(d.get("kernel_us")); print(d.get("roofline")); print(d.get("cpu_baseline")); print(d.get("clocks"))
 P
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/r03_final_bench_reference.json 2> $OUT/r03_final_bench_reference.err; echo "reference rc=$?"; cut -c1-600 $OUT/r03_final_bench_reference.json
-timeout 600 python bench.py --config 4 --steps 10 --warmup 3 > $OUT/r03_final_c4_1gpu.json 2> $OUT/r03_final_c4_1gpu.err; python -c "import json; d=json.load(open(\"gpurun_out/r03_final_c4_1gpu.json\")); print(\"configs[4] N=1: ms/step %.3f Mrays/s %.2f\" % (d[\"ms_per_step\"], d[\"value\"]/1e6))"
 bash profiles/run_ncu.sh r03 > $OUT/r03_run_ncu.log 2>&1; tail -3 $OUT/r03_run_ncu.log
