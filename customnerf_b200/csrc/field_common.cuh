@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
+#include "wgrad_reduce.cuh"
 
 // Kernel status word (include/nerf_b200.h: nb200_set_kernel_status_word): a device word of the CURRENT device into which the
 // field kernels OR a bit when one of their bounded mbarrier waits times out (a descriptor / protocol mistake must neither
@@ -32,12 +33,7 @@ constexpr uint32_t B_WR1FT = 28672;
 constexpr uint32_t B_W16T = 36864;   // 64 rows: cols 0..15 = Wr2^T, cols 16..31 = Wd2^T
 constexpr uint32_t B_BYTES = 45056;
 
-// flat tcnn-layout parameter offsets (elements)
-constexpr uint32_t T_W1 = 0, T_W2 = 64 * 32, T_W3 = 64 * 32 + 64 * 64;      // trunk:   [64x32][64x64][64x64]
-constexpr uint32_t D_W1 = 0, D_W2 = 64 * 64;                                 // density: [64x64][16x64]
-constexpr uint32_t R_W1 = 0, R_W2 = 64 * 96;                                 // colour:  [64x96][16x64]
-constexpr uint32_t kTrunkFloats = 64 * 32 + 2 * 64 * 64, kDensityFloats = 64 * 64 + 16 * 64, kRgbFloats = 64 * 96 + 16 * 64;
-constexpr uint32_t kWgradFloats = kTrunkFloats + kDensityFloats + kRgbFloats;   // 22528: one slab = [trunk | density | rgb]
+// (the flat tcnn-layout parameter offsets T_* / D_* / R_* and the slab layout live in wgrad_reduce.cuh)
 
 __device__ __forceinline__ void put(uint8_t *img, uint32_t row, uint32_t col, float v) {
     *reinterpret_cast<__half *>(img + umma::sw128_offset(row, col >> 3) + (col & 7u) * 2) = __float2half_rn(v);

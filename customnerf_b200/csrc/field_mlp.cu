@@ -320,10 +320,7 @@ constexpr uint32_t S_BWD_BYTES = SB_XV2 + 16384;    // 45056 + 11 * 16384 = 2252
 // TMEM columns
 constexpr uint32_t C_DG = 0, C_W1 = 64, C_W2 = 96, C_W3 = 160, C_PAIR = 224, C_R1V = 288, C_D2 = 320, C_R2 = 384, C_DG2 = 448;
 constexpr uint32_t kTmemColsBwd = 512;
-// per-CTA weight-gradient slab: one column-major block per accumulator (floats); 22528 in total == kWgradFloats
-constexpr uint32_t kSlabW1 = 0, kSlabW2 = kSlabW1 + 32 * 64, kSlabW3 = kSlabW2 + 64 * 64, kSlabPair = kSlabW3 + 64 * 64,
-                   kSlabR1V = kSlabPair + 64 * 128, kSlabR2 = kSlabR1V + 32 * 64, kSlabD2 = kSlabR2 + 64 * 16;
-static_assert(kSlabD2 + 64 * 16 == kWgradFloats, "slab blocks must tile kWgradFloats");
+// (slab layout: wgrad_reduce.cuh)
 
 struct FieldBwdArgs {
     const float *d_sigma;     // [M]
@@ -778,50 +775,12 @@ k_field_backward(const FieldBwdArgs p) {
     if (warp == 0) umma::tmem_dealloc(tmem, kTmemColsBwd);
 }
 
-// slabs [nslab][kWgradFloats] (the column-major accumulator blocks of the flush) -> += into the three flat gradients in tcnn's
-// layout.  Padded output rows of the two heads (tcnn pads 1 -> 16 and 4 -> 16 outputs) are dropped here.  256 threads = 64
-// slab elements x 4 slab groups; a warp reads 128 contiguous bytes of every slab it visits.
+// slabs -> += flat gradients as a kernel of its own (nb200_field_backward; the fused train step runs the same blocks inside
+// its table-scatter launch instead: wgrad_reduce.cuh)
 __global__ void __launch_bounds__(256)
-k_field_wgrad_reduce(const float *__restrict__ slabs, uint32_t grid, uint32_t M, const int32_t *__restrict__ count_dev,
-                     float *__restrict__ g_trunk, float *__restrict__ g_density, float *__restrict__ g_rgb,
-                     uint32_t *__restrict__ scaler) {
+k_field_wgrad_reduce(const NbWgradRed r) {
     __shared__ float part[4][64];
-    const uint32_t Mrows = count_dev ? min(M, (uint32_t)max(*count_dev, 0)) : M;
-    const uint32_t nslab = min(grid, (Mrows + 127) / 128);
-    const uint32_t pl = threadIdx.x & 63u, cg = threadIdx.x >> 6, i = blockIdx.x * 64 + pl;
-    float acc = 0.0f;
-    if (i < kWgradFloats) {
-#pragma unroll 8
-        for (uint32_t c = cg; c < nslab; c += 4) acc += __ldg(slabs + (size_t)c * kWgradFloats + i);
-    }
-    part[cg][pl] = acc;
-    __syncthreads();
-    if (cg != 0 || i >= kWgradFloats || nslab == 0) return;
-    const float sum = (part[0][pl] + part[1][pl]) + (part[2][pl] + part[3][pl]);
-    // slab element -> parameter: block, column c, row n (output neuron)
-    float *dst = nullptr;
-    if (i < kSlabW2) { const uint32_t c = i / 64, n = i % 64; dst = g_trunk + T_W1 + n * 32 + c; }
-    else if (i < kSlabW3) { const uint32_t e = i - kSlabW2, c = e / 64, n = e % 64; dst = g_trunk + T_W2 + n * 64 + c; }
-    else if (i < kSlabPair) { const uint32_t e = i - kSlabW3, c = e / 64, n = e % 64; dst = g_trunk + T_W3 + n * 64 + c; }
-    else if (i < kSlabR1V) {        // rows 0..63 = colour layer 0 (fea columns 27..90), rows 64..127 = density layer 0
-        const uint32_t e = i - kSlabPair, c = e / 128, n = e % 128;
-        dst = n < 64 ? g_rgb + R_W1 + n * 96 + 27 + c : g_density + D_W1 + (n - 64) * 64 + c;
-    } else if (i < kSlabR2) {       // colour layer 0, view columns: internal column c -> input lane c (c < 27) or 91 + (c - 27)
-        const uint32_t e = i - kSlabR1V, c = e / 64, n = e % 64;
-        dst = g_rgb + R_W1 + n * 96 + (c < 27 ? c : 91 + (c - 27));
-    } else if (i < kSlabD2) {       // colour head: rows 0..3 real
-        const uint32_t e = i - kSlabR2, c = e / 16, n = e % 16;
-        if (n < 4) dst = g_rgb + R_W2 + n * 64 + c;
-    } else {                        // density head: row 0 real
-        const uint32_t e = i - kSlabD2, c = e / 16, n = e % 16;
-        if (n == 0) dst = g_density + D_W2 + c;
-    }
-    // every gradient tile of the step (head gradients, dHR .. dH1) is an operand of some weight-gradient GEMM: an fp16
-    // overflow anywhere in the backward chain shows up here as inf / NaN (inf x 0 included) -- GradScaler's found_inf.
-    // Only entries that map to a parameter are looked at.
-    if (!dst) return;
-    if (scaler && !isfinite(sum)) scaler_raise(scaler);
-    *dst += sum;
+    wgrad_reduce_block(r, blockIdx.x, part);
 }
 
 constexpr int kMaxDevices = 64;
@@ -847,6 +806,15 @@ int launch_field_forward(const FieldFwdArgs &a, const CUtensorMap &act_map, uint
     return 0;
 }
 }  // namespace
+
+uint32_t nb_wgrad_reduce_blocks() { return nb_div_up(kWgradFloats, 64); }
+uint32_t nb_field_backward_grid(uint32_t M) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t ntiles = (M + 127) / 128;
+    return ntiles < (uint32_t)sms ? ntiles : (uint32_t)sms;
+}
 
 uint32_t *nb_kernel_status_word() {
     int dev = 0;
@@ -949,25 +917,25 @@ int nb200_field_forward(const void *x_en, const float *xyz, const float *dirs, c
                  : launch_field_forward<false>(a, act_map, M, nb_stream(stream));
 }
 
-int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,
-                         const void *x_en, const float *dirs, const void *act, const void *bwd_img, void *d_x_en,
-                         float *g_trunk, float *g_density, float *g_rgb, uint32_t M, const int32_t *count_dev,
-                         float *wg_scratch, uint32_t *scaler, void *stream) {
+// reduce = false: the slabs stay in wg_scratch (required) for a reduction the caller runs itself (wgrad_reduce.cuh)
+int nb_field_backward_launch(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,
+                             const void *x_en, const float *dirs, const void *act, const void *bwd_img, void *d_x_en,
+                             float *g_trunk, float *g_density, float *g_rgb, uint32_t M, const int32_t *count_dev,
+                             float *wg_scratch, uint32_t *scaler, bool reduce, void *stream) {
     if (M == 0) return 0;
-    if (scaler && !wg_scratch) return NB200_E_BAD_ARG;      // the finite check lives in the slab reduction
+    if ((scaler || !reduce) && !wg_scratch) return NB200_E_BAD_ARG;      // the finite check lives in the slab reduction
     if (!d_sigma || !d_rgba || !sigma_arg || !rgba || !x_en || !dirs || !act || !bwd_img || !d_x_en || !g_trunk ||
         !g_density || !g_rgb)
         return NB200_E_BAD_ARG;
     static bool configured[kMaxDevices] = {};
     const int smem = (int)S_BWD_BYTES + 1024;
-    int dev = 0, sms = 148;
+    int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_field_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
     }
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     FieldBwdArgs a;
     a.d_sigma = d_sigma; a.d_rgba = d_rgba; a.sigma_arg = sigma_arg; a.rgba = (const __half *)rgba;
     a.x_en = (const __half *)x_en; a.dirs = dirs; a.act = (const __half *)act; a.wimg = (const uint8_t *)bwd_img;
@@ -977,17 +945,24 @@ int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float 
     a.status = nb_kernel_status_word();
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("NB200_FIELDB_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = (uint32_t)dbg; }
     a.slabs = wg_scratch;
-    const uint32_t ntiles = (M + 127) / 128;
-    const uint32_t grid = ntiles < (uint32_t)sms ? ntiles : (uint32_t)sms;
+    const uint32_t grid = nb_field_backward_grid(M);
     if (wg_scratch && (reinterpret_cast<uintptr_t>(wg_scratch) & 15u)) return NB200_E_BAD_ARG;
     k_field_backward<<<grid, kBwdThreads, smem, nb_stream(stream)>>>(a);
     NB_LAUNCH_CHECK();
-    if (wg_scratch && !(a.dbg & 4u)) {
-        k_field_wgrad_reduce<<<nb_div_up(kWgradFloats, 64), 256, 0, nb_stream(stream)>>>(wg_scratch, grid, M, count_dev, g_trunk,
-                                                                                  g_density, g_rgb, scaler);
+    if (wg_scratch && reduce && !(a.dbg & 4u)) {
+        const NbWgradRed r{wg_scratch, count_dev, g_trunk, g_density, g_rgb, scaler, grid, M, nb_wgrad_reduce_blocks()};
+        k_field_wgrad_reduce<<<r.blocks, 256, 0, nb_stream(stream)>>>(r);
         NB_LAUNCH_CHECK();
     }
     return 0;
+}
+
+int nb200_field_backward(const float *d_sigma, const float *d_rgba, const float *sigma_arg, const void *rgba,
+                         const void *x_en, const float *dirs, const void *act, const void *bwd_img, void *d_x_en,
+                         float *g_trunk, float *g_density, float *g_rgb, uint32_t M, const int32_t *count_dev,
+                         float *wg_scratch, uint32_t *scaler, void *stream) {
+    return nb_field_backward_launch(d_sigma, d_rgba, sigma_arg, rgba, x_en, dirs, act, bwd_img, d_x_en, g_trunk, g_density, g_rgb,
+                                    M, count_dev, wg_scratch, scaler, true, stream);
 }
 
 }  // extern "C"

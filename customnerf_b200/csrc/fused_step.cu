@@ -14,6 +14,7 @@
 // exactly as the reference drops them when its mean_count budget overflows (raymarching.cu:415-416); the caller
 // watches counter[0] against M_cap and grows the buffers.
 #include "common.cuh"
+#include "wgrad_reduce.cuh"
 
 namespace {
 struct StageTimer {
@@ -132,13 +133,22 @@ rest:
                                               p->target_mask ? p->g_render_mask : nullptr, p->render_mask, stream))) return rc;
         tick(ev, k++, st);
     }
-    if ((rc = nb200_field_backward(p->d_sigma, p->d_rgba, p->sigma_arg, p->rgba, p->x_en, p->dirs, p->act, p->w_bwd,
-                                   p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch, p->scaler, stream))) return rc;
-    tick(ev, k++, st);
-    if ((rc = nb200_fs_encode_backward_levels(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S,
-                                              p->base_res, p->gridtype, 0, 0, p->m_eff,
-                                              (phases & NB200_PHASE_REST_A) ? p->split_level : 0, p->L, stream))) return rc;
-    tick(ev, k++, st);
+    {
+        // the slab reduction of the field backward (the MLPs' weight gradients) depends on nothing but the slabs and only the
+        // optimiser depends on it: its blocks ride at the tail of the table-scatter launch instead of being a launch of their
+        // own between the two kernels (10 us of launch gap + run time off the critical path at configs[1])
+        const bool ride = p->wg_scratch != nullptr;
+        if ((rc = nb_field_backward_launch(p->d_sigma, p->d_rgba, p->sigma_arg, p->rgba, p->x_en, p->dirs, p->act, p->w_bwd,
+                                           p->d_x_en, p->g_trunk, p->g_density, p->g_rgb, p->M_cap, p->m_eff, p->wg_scratch,
+                                           p->scaler, !ride, stream))) return rc;
+        tick(ev, k++, st);
+        const NbWgradRed red{p->wg_scratch, p->m_eff, p->g_trunk, p->g_density, p->g_rgb, p->scaler,
+                             nb_field_backward_grid(p->M_cap), p->M_cap, ride ? nb_wgrad_reduce_blocks() : 0u};
+        if ((rc = nb_fs_encode_backward_red(p->d_x_en, p->xyzs, p->bound, p->offsets, p->g_table, p->M_cap, p->L, p->S, p->base_res,
+                                            p->gridtype, 0, 0, p->m_eff, (phases & NB200_PHASE_REST_A) ? p->split_level : 0,
+                                            p->L, &red, stream))) return rc;
+        tick(ev, k++, st);
+    }
     // the step's sample count, parked where the (possibly concurrent: pipelined update next to the NEXT step's march, which
     // resets the counter) update reads it for the status word of the loss scaler
     if (p->scaler && (e = cudaMemcpyAsync(p->counter + 6, p->counter, sizeof(int32_t), cudaMemcpyDeviceToDevice, st)) != cudaSuccess)

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "grid_d3c2.cuh"
 #include "grid_generic.cuh"
+#include "wgrad_reduce.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -83,13 +84,22 @@ template <typename T, bool kAgg>
 __global__ void __launch_bounds__(256)
 k_grid_bwd_d3c2(const T *__restrict__ grad, const float *__restrict__ inputs, const int32_t *__restrict__ offsets,
                 float *__restrict__ grad_grid, uint32_t B, uint32_t L, uint32_t max_level, float S, uint32_t H,
-                uint32_t gridtype, bool align_corners, uint32_t interp, InXform xf, uint32_t agg_max_heads) {
+                uint32_t gridtype, bool align_corners, uint32_t interp, InXform xf, uint32_t agg_max_heads,
+                NbWgradRed red = NbWgradRed{}) {
     __shared__ LevelInfo info[kMaxFastLevels];
+    // fused train step: the LAST red.blocks blocks of this launch are the slab reduction of the field backward's weight
+    // gradients (wgrad_reduce.cuh) -- independent of the scatter; dispatched last, they run in the scatter's draining tail
+    if (blockIdx.x >= gridDim.x - red.blocks) {
+        __shared__ float part[4][64];
+        wgrad_reduce_block(red, blockIdx.x - (gridDim.x - red.blocks), part);
+        return;
+    }
+    const uint32_t bid = blockIdx.x;
     if (xf.count_dev) B = min(B, (uint32_t)max(*xf.count_dev, 0));
-    if (blockIdx.x * blockDim.x >= B) return;
+    if (bid * blockDim.x >= B) return;
     ge_fill_level_info(info, offsets, max_level, S, H, gridtype, align_corners);
     __syncthreads();
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = bid * blockDim.x + threadIdx.x;
     const uint32_t lane = nb_lane();
     const bool inb = b < B;            // keep whole warps alive for the shuffles
     float x0 = -1.0f, x1 = -1.0f, x2 = -1.0f;
@@ -365,14 +375,8 @@ int nb200_fs_encode_backward_levels(const void *d_x_en, const float *xyz, float 
                                     uint32_t M_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
                                     uint32_t interp, const int32_t *count_dev, uint32_t level_begin, uint32_t level_end,
                                     void *stream) {
-    if (M_cap == 0 || L == 0 || level_begin >= level_end) return 0;
-    if (!d_x_en || !xyz || !offsets || !grad_table || L > kMaxFastLevels || !(bound > 0.0f) || level_end > L) return NB200_E_BAD_ARG;
-    const InXform xf{bound, 1.0f / (2.0f * bound), count_dev, level_begin};
-    k_grid_bwd_d3c2<__half, true><<<nb_div_up(M_cap, 256), 256, 0, nb_stream(stream)>>>(
-        (const __half *)d_x_en, xyz, offsets, grad_table, M_cap, L, level_end, S, H, gridtype, align_corners != 0, interp, xf,
-        ge_agg_max_heads());
-    NB_LAUNCH_CHECK();
-    return 0;
+    return nb_fs_encode_backward_red(d_x_en, xyz, bound, offsets, grad_table, M_cap, L, S, H, gridtype, align_corners, interp,
+                                     count_dev, level_begin, level_end, nullptr, stream);
 }
 
 int nb200_grad_total_variation(const float *inputs, const float *embeddings, float *grad, const int32_t *offsets,
@@ -424,3 +428,18 @@ const char *nb200_error_string(int code) {
 int nb200_version(void) { return 1; }
 
 }  // extern "C"
+
+int nb_fs_encode_backward_red(const void *d_x_en, const float *xyz, float bound, const int32_t *offsets, float *grad_table,
+                              uint32_t M_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                              uint32_t interp, const int32_t *count_dev, uint32_t level_begin, uint32_t level_end,
+                              const NbWgradRed *red, void *stream) {
+    const NbWgradRed r = red ? *red : NbWgradRed{};
+    if ((M_cap == 0 || L == 0 || level_begin >= level_end) && r.blocks == 0) return 0;
+    if (!d_x_en || !xyz || !offsets || !grad_table || L > kMaxFastLevels || !(bound > 0.0f) || level_end > L) return NB200_E_BAD_ARG;
+    const InXform xf{bound, 1.0f / (2.0f * bound), count_dev, level_begin};
+    k_grid_bwd_d3c2<__half, true><<<nb_div_up(M_cap, 256) + r.blocks, 256, 0, nb_stream(stream)>>>(
+        (const __half *)d_x_en, xyz, offsets, grad_table, M_cap, L, level_end, S, H, gridtype, align_corners != 0, interp, xf,
+        ge_agg_max_heads(), r);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
