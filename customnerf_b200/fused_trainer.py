@@ -36,10 +36,10 @@ from . import _lib as L
 
 LOSS_SCALE = 128.0          # initial loss scale (tiny-cuda-nn's own backward loss scale); dynamic from there on, see below
 GROWTH_INTERVAL = 2000      # torch.cuda.amp.GradScaler's default: the scale doubles after this many steps without overflow
-# this library's kernels in one step (the ncu launch list profiles/r03_ncu_summary.txt shows the same fourteen): march count
+# this library's kernels in one step (the ncu launch list profiles/r03_ncu_summary.txt shows the same): march count
 # (+ near/far) + scan + finalize + expand, encode, field, composite (+ MSE), composite^T, field^T + weight-gradient reduce,
 # encode^T, adam hyper, adam, weight pack (+ scaler commit)
-KERNELS_PER_STEP = 14
+KERNELS_PER_STEP = 13
 STAGES = ["march_count", "march_write", "grid_encode_forward", "field_forward", "composite_forward",
           "composite_backward", "field_backward", "grid_encode_backward", "adam", "pack_weights"]
 
