@@ -209,6 +209,7 @@ BYTES_PER_SAMPLE = {
     "field_forward": 64.0 + 24.0 + 4 + 4 + 8 + 640.0,      # x_en + xyz/dirs + sigma + sigma_arg + rgba + 5 saved activations
     "composite_forward": 4.0 + 8 + 8,                      # sigma + rgba(f16x4) + deltas
     "composite_backward": 4.0 + 8 + 8 + 4 + 16,            # same reads + d_sigma + d_rgba(float4)
+    "composite_forward_backward": 2 * (4.0 + 8 + 8) + 4 + 16,      # one launch: the reads twice (second time from L1 / L2), the gradients out
     "field_backward": 640.0 + 64 + 12 + 4 + 16 + 4 + 8 + 64,   # activations, x_en, dirs, d_sigma, d_rgba, sigma_arg, rgba; d_x_en out
     "grid_encode_backward": 12.0 + 64 + 2 * 16 * 8 * 8,    # coords + feature grads + 128 float2 atomic read-modify-writes
 }
@@ -249,12 +250,12 @@ def l2_probe(dev):
 # scatter touches DRAM for 8 % of its algorithmic bytes), so the encode kernels are measured against the L2 rates probed in
 # this run; the field kernels stream activations from / to HBM and run the only dense contraction (tensor pipe); the
 # composites and Adam stream HBM; the march is issue / latency bound (samples/s reported).
-STAGE_BOUND = {"grid_encode_forward": "l2", "grid_encode_backward": "l2", "composite_forward": "l2", "composite_backward": "l2",
+STAGE_BOUND = {"grid_encode_forward": "l2", "grid_encode_backward": "l2", "composite_forward": "l2", "composite_backward": "l2", "composite_forward_backward": "l2",
                "field_forward": "hbm", "field_backward": "hbm", "adam": "hbm", "march_write": "hbm"}
 FLOPS_PER_SAMPLE = {"field_forward": 2.0 * 20480, "field_backward": 4.0 * 20480}     # useful MACs x 2; backward = dgrad + wgrad
 
 
-def rooflines(stage_us, samples, n_params, peaks, l2=None):
+def rooflines(stage_us, samples, n_params, peaks, l2=None, fused_composite=False):
     """achieved algorithmic GB/s of every stage against the roofline that bounds it; the dominant stage is the headline"""
     hbm = peaks.get("hbm_gbs", 6650.0)
     src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
@@ -262,6 +263,11 @@ def rooflines(stage_us, samples, n_params, peaks, l2=None):
     l2_stream = (l2 or {}).get("stream_32MB_gbs")
     l2_sector = (l2 or {}).get("gather_32MB_sector_gbs")
     per = {}
+    stage_us = dict(stage_us)
+    # compositing forward + MSE + backward as ONE launch (FusedTrainStep.fused_composite): the second stage is an empty pair of
+    # events -- report the launch as one stage with the bytes of both directions
+    if fused_composite and "composite_forward" in stage_us and "composite_backward" in stage_us:
+        stage_us["composite_forward_backward"] = stage_us.pop("composite_forward") + stage_us.pop("composite_backward")
     for k, us in stage_us.items():
         if k in BYTES_PER_SAMPLE:
             units, bpu = samples, BYTES_PER_SAMPLE[k]
@@ -594,7 +600,7 @@ def run_b200(args):
             except Exception as e:
                 line["l2_probe"] = {"error": repr(e)}
                 l2 = None
-            line["roofline"], line["stage_rooflines"] = rooflines(stage_us, samples, fs.params_flat.numel(), peaks, l2)
+            line["roofline"], line["stage_rooflines"] = rooflines(stage_us, samples, fs.params_flat.numel(), peaks, l2, fused_composite=getattr(fs, "fused_composite", False))
             if not args.no_cpu:
                 n_cpu = 2048
                 line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(3, 1, n_cpu).items() if k != "ms_per_step"}
